@@ -1,0 +1,571 @@
+/* TEST INFRASTRUCTURE ONLY — CPU restatement ("port") of the reference LIO hot path.
+ *
+ * Nothing in the product (lidar-slam-detection_b200/, liblsdreg.so) may include, link or call this
+ * file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * use it, as the checker.  All citations are relative to /root/reference.
+ *
+ * Pinning status (DESIGN.md "Oracle"):
+ *   - iVox k-NN, ikd-Tree k-NN, esti_plane: pinned against the compiled reference (oracle/_ref,
+ *     tests/test_oracle_vs_ref.py) and the golden vectors it generated (tests/golden/).
+ *   - PCL VoxelGrid: PCL 1.9.1 is not vendored in the reference tree -> restated from the
+ *     published algorithm (pcl/filters/impl/voxel_grid.hpp, PCL 1.9.1); PARITY UNPINNED.
+ *
+ * Build: oracle/Makefile (gcc -O3 -ffp-contract=off, no -march=native: fp32 distance arithmetic
+ * is evaluated left-to-right without FMA exactly like the reference x86-64 build).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <omp.h>
+
+/* ===================================================================================== */
+/* a1  pcl::VoxelGrid<PointXYZINormal>::filter — call site laserMapping.cpp:1206-1207,   */
+/*     leaf 0.5 (laserMapping.cpp:1027,1073).  Semantics (PCL 1.9.1 voxel_grid.hpp):     */
+/*     bbox -> min_b = floor(min*inv_leaf); idx = (ijk-min_b).(1,dx,dx*dy); sort by idx;  */
+/*     per-run centroid of all fields (fp32 sums in input order); output ascending idx.   */
+/* ===================================================================================== */
+typedef struct { int idx; int pi; } OrcVoxKey;
+
+static int cmp_voxkey(const void* a, const void* b) {
+  const OrcVoxKey* x = (const OrcVoxKey*)a; const OrcVoxKey* y = (const OrcVoxKey*)b;
+  if (x->idx != y->idx) return x->idx < y->idx ? -1 : 1;
+  return x->pi < y->pi ? -1 : (x->pi > y->pi);  /* stable: input order inside a voxel */
+}
+
+/* in/out: [n,4] = x,y,z,intensity.  Returns the number of output points, or -1 when the grid
+ * would overflow int32 (PCL then warns and returns the input unchanged: out = in, caller uses n). */
+int orc_voxelgrid(const float* in, int n, float leaf, float* out, int* out_vidx) {
+  if (n <= 0) return 0;
+  float inv = 1.0f / leaf;
+  float mn[3] = {in[0], in[1], in[2]}, mx[3] = {in[0], in[1], in[2]};
+  for (int i = 1; i < n; i++)
+    for (int d = 0; d < 3; d++) {
+      float v = in[4 * i + d];
+      if (v < mn[d]) mn[d] = v;
+      if (v > mx[d]) mx[d] = v;
+    }
+  int64_t dx = (int64_t)((mx[0] - mn[0]) * inv) + 1;
+  int64_t dy = (int64_t)((mx[1] - mn[1]) * inv) + 1;
+  int64_t dz = (int64_t)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > (int64_t)INT32_MAX) {
+    memcpy(out, in, sizeof(float) * 4 * (size_t)n);
+    return -1;
+  }
+  int minb[3], maxb[3], divb[3];
+  for (int d = 0; d < 3; d++) {
+    minb[d] = (int)floorf(mn[d] * inv);
+    maxb[d] = (int)floorf(mx[d] * inv);
+    divb[d] = maxb[d] - minb[d] + 1;
+  }
+  int mul[3] = {1, divb[0], divb[0] * divb[1]};
+  OrcVoxKey* keys = (OrcVoxKey*)malloc(sizeof(OrcVoxKey) * (size_t)n);
+  for (int i = 0; i < n; i++) {
+    int i0 = (int)(floorf(in[4 * i + 0] * inv) - (float)minb[0]);
+    int i1 = (int)(floorf(in[4 * i + 1] * inv) - (float)minb[1]);
+    int i2 = (int)(floorf(in[4 * i + 2] * inv) - (float)minb[2]);
+    keys[i].idx = i0 * mul[0] + i1 * mul[1] + i2 * mul[2];
+    keys[i].pi = i;
+  }
+  qsort(keys, (size_t)n, sizeof(OrcVoxKey), cmp_voxkey);
+  int m = 0;
+  for (int s = 0; s < n;) {
+    int e = s;
+    float acc[4] = {0, 0, 0, 0};
+    while (e < n && keys[e].idx == keys[s].idx) {
+      const float* p = in + 4 * (size_t)keys[e].pi;
+      acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
+      e++;
+    }
+    float cnt = (float)(e - s);
+    for (int d = 0; d < 4; d++) out[4 * (size_t)m + d] = acc[d] / cnt;
+    if (out_vidx) out_vidx[m] = keys[s].idx;
+    m++;
+    s = e;
+  }
+  free(keys);
+  return m;
+}
+
+/* ===================================================================================== */
+/* a2/a3  faster_lio::IVox  (include/ivox3d/ivox3d.h:31-261, ivox3d_node.hpp:38-127)      */
+/* ===================================================================================== */
+typedef struct { float x, y, z; int id; } OrcPt;
+typedef struct { int kx, ky, kz; int used; int n, cap; OrcPt* pts; } OrcCell;
+typedef struct {
+  float res, inv_res;
+  int nearby_n; int nearby[125][3];
+  size_t tab_size, n_cells, n_points; OrcCell* tab;
+} OrcIvox;
+
+static uint64_t cell_hash(int x, int y, int z) {
+  uint64_t h = (uint64_t)(uint32_t)x * 0x9E3779B97F4A7C15ull;
+  h ^= ((uint64_t)(uint32_t)y + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+  h ^= ((uint64_t)(uint32_t)z + 0x165667B1ull) * 0xD6E8FEB86659FD93ull;
+  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  return h;
+}
+
+/* GenerateNearbyGrids, ivox3d.h:178-215 */
+static void set_nearby(OrcIvox* m, int nearby) {
+  static const int n18[19][3] = {{0,0,0},{-1,0,0},{1,0,0},{0,1,0},{0,-1,0},{0,0,-1},{0,0,1},{1,1,0},{-1,1,0},
+    {1,-1,0},{-1,-1,0},{1,0,1},{-1,0,1},{1,0,-1},{-1,0,-1},{0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1}};
+  m->nearby_n = 0;
+  if (nearby == 0) { m->nearby_n = 1; memset(m->nearby[0], 0, sizeof(int) * 3); }
+  else if (nearby == 6 || nearby == 18) {
+    int c = nearby == 6 ? 7 : 19;
+    for (int i = 0; i < c; i++) memcpy(m->nearby[i], n18[i], sizeof(int) * 3);
+    m->nearby_n = c;
+  } else if (nearby == 26) {
+    for (int i = -1; i <= 1; i++) for (int j = -1; j <= 1; j++) for (int k = -1; k <= 1; k++) {
+      int* d = m->nearby[m->nearby_n++]; d[0] = i; d[1] = j; d[2] = k; }
+  } else { /* NEARBY74: 5x5x3, ivox3d.h:205-211 */
+    for (int i = -2; i <= 2; i++) for (int j = -2; j <= 2; j++) for (int k = -1; k <= 1; k++) {
+      int* d = m->nearby[m->nearby_n++]; d[0] = i; d[1] = j; d[2] = k; }
+  }
+}
+
+OrcIvox* orc_ivox_create(float res, int nearby, size_t expected_cells) {
+  OrcIvox* m = (OrcIvox*)calloc(1, sizeof(OrcIvox));
+  m->res = res;
+  m->inv_res = (float)(1.0 / (double)res); /* ivox3d.h:58 */
+  set_nearby(m, nearby);
+  size_t t = 1024;
+  while (t < expected_cells * 2) t <<= 1;
+  m->tab_size = t;
+  m->tab = (OrcCell*)calloc(t, sizeof(OrcCell));
+  return m;
+}
+void orc_ivox_set_nearby(OrcIvox* m, int nearby) { set_nearby(m, nearby); }
+void orc_ivox_destroy(OrcIvox* m) {
+  if (!m) return;
+  for (size_t i = 0; i < m->tab_size; i++) free(m->tab[i].pts);
+  free(m->tab); free(m);
+}
+size_t orc_ivox_num_cells(const OrcIvox* m) { return m->n_cells; }
+size_t orc_ivox_num_points(const OrcIvox* m) { return m->n_points; }
+
+static OrcCell* find_cell(const OrcIvox* m, int x, int y, int z) {
+  size_t mask = m->tab_size - 1, s = cell_hash(x, y, z) & mask;
+  for (;;) {
+    OrcCell* c = &m->tab[s];
+    if (!c->used) return NULL;
+    if (c->kx == x && c->ky == y && c->kz == z) return c;
+    s = (s + 1) & mask;
+  }
+}
+static void grow(OrcIvox* m);
+static OrcCell* find_or_add_cell(OrcIvox* m, int x, int y, int z) {
+  if ((m->n_cells + 1) * 2 > m->tab_size) grow(m);
+  size_t mask = m->tab_size - 1, s = cell_hash(x, y, z) & mask;
+  for (;;) {
+    OrcCell* c = &m->tab[s];
+    if (!c->used) { c->used = 1; c->kx = x; c->ky = y; c->kz = z; m->n_cells++; return c; }
+    if (c->kx == x && c->ky == y && c->kz == z) return c;
+    s = (s + 1) & mask;
+  }
+}
+static void grow(OrcIvox* m) {
+  OrcCell* old = m->tab; size_t on = m->tab_size;
+  m->tab_size = on * 2; m->tab = (OrcCell*)calloc(m->tab_size, sizeof(OrcCell));
+  size_t mask = m->tab_size - 1;
+  for (size_t i = 0; i < on; i++) if (old[i].used) {
+    size_t s = cell_hash(old[i].kx, old[i].ky, old[i].kz) & mask;
+    while (m->tab[s].used) s = (s + 1) & mask;
+    m->tab[s] = old[i];
+  }
+  free(old);
+}
+
+/* Pos2Grid, ivox3d.h:258-261: round(pt * inv_res) with round-half-away-from-zero */
+static inline void pos2grid(const OrcIvox* m, const float* p, int* k) {
+  k[0] = (int)roundf(p[0] * m->inv_res);
+  k[1] = (int)roundf(p[1] * m->inv_res);
+  k[2] = (int)roundf(p[2] * m->inv_res);
+}
+
+/* AddPoints, ivox3d.h:231-256 (LRU eviction not restated: capacity is raised above the map size,
+ * BASELINE.md §3 config 2).  Point i gets id ids ? ids[i] : id0 + i. */
+void orc_ivox_add(OrcIvox* m, const float* xyz, int stride, int n, int id0, const int* ids) {
+  for (int i = 0; i < n; i++) {
+    const float* p = xyz + (size_t)stride * i;
+    int k[3]; pos2grid(m, p, k);
+    OrcCell* c = find_or_add_cell(m, k[0], k[1], k[2]);
+    if (c->n == c->cap) { c->cap = c->cap ? c->cap * 2 : 4; c->pts = (OrcPt*)realloc(c->pts, sizeof(OrcPt) * (size_t)c->cap); }
+    OrcPt* q = &c->pts[c->n++];
+    q->x = p[0]; q->y = p[1]; q->z = p[2]; q->id = ids ? ids[i] : id0 + i;
+    m->n_points++;
+  }
+}
+
+typedef struct { float d2; int id; float x, y, z; } OrcCand;
+/* canonical order used everywhere in this repo: ascending (d2, id) */
+static inline int cand_less(const OrcCand* a, const OrcCand* b) {
+  return a->d2 < b->d2 || (a->d2 == b->d2 && a->id < b->id);
+}
+static inline void topk_insert(OrcCand* best, int* nb, int k, const OrcCand* c) {
+  if (*nb == k && !cand_less(c, &best[k - 1])) return;
+  int j = *nb < k ? (*nb)++ : k - 1;
+  while (j > 0 && cand_less(c, &best[j - 1])) { best[j] = best[j - 1]; j--; }
+  best[j] = *c;
+}
+/* distance2, ivox3d_node.hpp:11-14: (dx*dx + dy*dy) + dz*dz in fp32 */
+static inline float dist2f(const float* a, const OrcPt* b) {
+  float dx = b->x - a[0], dy = b->y - a[1], dz = b->z - a[2];
+  return dx * dx + dy * dy + dz * dz;
+}
+
+/* GetClosestPoint(pt, out, k, max_sq), ivox3d.h:139-171 + KNNPointByCondition,
+ * ivox3d_node.hpp:107-127.  The reference keeps per-cell top-k then the global top-k; the union of
+ * per-cell top-k contains the global top-k, so this is the k smallest with d2 < max_sq in the
+ * stencil.  Returned in canonical (d2,id) order; the reference's order is "nearest first, rest
+ * unspecified (nth_element)". */
+static int ivox_knn_one(const OrcIvox* m, const float* q, int k, double max_sq, OrcCand* best) {
+  int key[3]; pos2grid(m, q, key);
+  int nb = 0;
+  for (int c = 0; c < m->nearby_n; c++) {
+    const OrcCell* cell = find_cell(m, key[0] + m->nearby[c][0], key[1] + m->nearby[c][1], key[2] + m->nearby[c][2]);
+    if (!cell) continue;
+    for (int j = 0; j < cell->n; j++) {
+      float d = dist2f(q, &cell->pts[j]);
+      if ((double)d < max_sq) {
+        OrcCand cd = {d, cell->pts[j].id, cell->pts[j].x, cell->pts[j].y, cell->pts[j].z};
+        topk_insert(best, &nb, k, &cd);
+      }
+    }
+  }
+  return nb;
+}
+
+/* Exact k-NN within radius (d2 <= max_sq) by shell expansion over the same grid: equals the
+ * ikd-Tree result Nearest_Search (ikd_Tree.cpp:367-397, :869-1013) whenever the reference accepts
+ * it (5 found and d2[4] <= 5, laserMapping.cpp:846-847). */
+static int exact_knn_one(const OrcIvox* m, const float* q, int k, double max_sq, OrcCand* best) {
+  int key[3]; pos2grid(m, q, key);
+  int nb = 0;
+  int rmax = (int)ceil(sqrt(max_sq) / (double)m->res) + 1;
+  for (int r = 0; r <= rmax; r++) {
+    if (r >= 1 && nb == k) {
+      double lo = (double)(r - 1) * (double)m->res * (1.0 - 1e-5); /* unseen points are farther than this */
+      if ((double)best[k - 1].d2 < lo * lo) break;
+    }
+    for (int i = -r; i <= r; i++) for (int j = -r; j <= r; j++) for (int l = -r; l <= r; l++) {
+      int a = abs(i) > abs(j) ? abs(i) : abs(j); if (abs(l) > a) a = abs(l);
+      if (a != r) continue;
+      const OrcCell* cell = find_cell(m, key[0] + i, key[1] + j, key[2] + l);
+      if (!cell) continue;
+      for (int p = 0; p < cell->n; p++) {
+        float d = dist2f(q, &cell->pts[p]);
+        if ((double)d <= max_sq) {
+          OrcCand cd = {d, cell->pts[p].id, cell->pts[p].x, cell->pts[p].y, cell->pts[p].z};
+          topk_insert(best, &nb, k, &cd);
+        }
+      }
+    }
+  }
+  return nb;
+}
+
+/* mode 0: iVox stencil (d2 < max_sq); mode 1: exact within radius (d2 <= max_sq).
+ * q stride in floats; outputs [nq,k] (-1 / 0 padded), out_xyz [nq,k,3] optional. */
+void orc_knn(const OrcIvox* m, int mode, const float* q, int stride, int nq, int k, double max_sq,
+             int* out_ids, float* out_d2, float* out_xyz, int* out_cnt, int nthreads) {
+  omp_set_num_threads(nthreads > 0 ? nthreads : 1);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < nq; i++) {
+    OrcCand best[64];
+    int kk = k > 64 ? 64 : k;
+    int nb = mode == 0 ? ivox_knn_one(m, q + (size_t)stride * i, kk, max_sq, best)
+                       : exact_knn_one(m, q + (size_t)stride * i, kk, max_sq, best);
+    out_cnt[i] = nb;
+    for (int j = 0; j < k; j++) {
+      out_ids[(size_t)i * k + j] = j < nb ? best[j].id : -1;
+      out_d2[(size_t)i * k + j] = j < nb ? best[j].d2 : -1.f;
+      if (out_xyz) {
+        float* o = out_xyz + ((size_t)i * k + j) * 3;
+        o[0] = j < nb ? best[j].x : 0; o[1] = j < nb ? best[j].y : 0; o[2] = j < nb ? best[j].z : 0;
+      }
+    }
+  }
+}
+
+/* ===================================================================================== */
+/* a5  esti_plane<float>  (include/common_lib.h:236-268): 5x3 A n = -1 solved with Eigen's */
+/*     ColPivHouseholderQR in fp32 (Eigen/src/QR/ColPivHouseholderQR.h:480-570,            */
+/*     Householder/Householder.h:65-130), normalise, reject if any point is > thr off.     */
+/* ===================================================================================== */
+#define FEPS 1.1920929e-07f
+static float colnorm(const float A[5][3], int c, int r0) {
+  float s = 0.f;
+  for (int r = r0; r < 5; r++) s += A[r][c] * A[r][c];
+  return sqrtf(s);
+}
+int orc_esti_plane(const float* pts, float thr, float* pabcd) {
+  float A[5][3], b[5];
+  for (int r = 0; r < 5; r++) { A[r][0] = pts[3 * r]; A[r][1] = pts[3 * r + 1]; A[r][2] = pts[3 * r + 2]; b[r] = -1.0f; }
+  const int rows = 5, cols = 3, size = 3;
+  float hc[3], nu[3], nd[3]; int perm[3] = {0, 1, 2};
+  for (int k = 0; k < cols; k++) nu[k] = nd[k] = colnorm(A, k, 0);
+  float mxn = nu[0]; if (nu[1] > mxn) mxn = nu[1]; if (nu[2] > mxn) mxn = nu[2];
+  float th_helper = (mxn * FEPS) * (mxn * FEPS) / (float)rows;
+  float downdate = sqrtf(FEPS);
+  int nonzero = size;
+  for (int k = 0; k < size; k++) {
+    int big = k; float bn = nu[k];
+    for (int j = k + 1; j < cols; j++) if (nu[j] > bn) { bn = nu[j]; big = j; }
+    if (nonzero == size && bn * bn < th_helper * (float)(rows - k)) nonzero = k;
+    if (big != k) {
+      for (int r = 0; r < rows; r++) { float t = A[r][k]; A[r][k] = A[r][big]; A[r][big] = t; }
+      float t = nu[k]; nu[k] = nu[big]; nu[big] = t;
+      t = nd[k]; nd[k] = nd[big]; nd[big] = t;
+      int ti = perm[k]; perm[k] = perm[big]; perm[big] = ti;
+    }
+    /* makeHouseholderInPlace on A[k..4][k] */
+    float tail = 0.f;
+    for (int r = k + 1; r < rows; r++) tail += A[r][k] * A[r][k];
+    float c0 = A[k][k], beta, tau;
+    if (tail <= 1.17549435e-38f) { tau = 0.f; beta = c0; for (int r = k + 1; r < rows; r++) A[r][k] = 0.f; }
+    else {
+      beta = sqrtf(c0 * c0 + tail);
+      if (c0 >= 0.f) beta = -beta;
+      float den = c0 - beta;
+      for (int r = k + 1; r < rows; r++) A[r][k] = A[r][k] / den;
+      tau = (beta - c0) / beta;
+    }
+    hc[k] = tau; A[k][k] = beta;
+    /* applyHouseholderOnTheLeft to the trailing columns */
+    if (tau != 0.f)
+      for (int j = k + 1; j < cols; j++) {
+        float tmp = 0.f;
+        for (int r = k + 1; r < rows; r++) tmp += A[r][k] * A[r][j];
+        tmp += A[k][j];
+        A[k][j] -= tau * tmp;
+        for (int r = k + 1; r < rows; r++) A[r][j] -= tau * A[r][k] * tmp;
+      }
+    for (int j = k + 1; j < cols; j++) {
+      if (nu[j] != 0.f) {
+        float t = fabsf(A[k][j]) / nu[j];
+        t = (1.f + t) * (1.f - t);
+        if (t < 0.f) t = 0.f;
+        float rr = nu[j] / nd[j];
+        float t2 = t * rr * rr;
+        if (t2 <= downdate) { nd[j] = colnorm(A, j, k + 1); nu[j] = nd[j]; }
+        else nu[j] *= sqrtf(t);
+      }
+    }
+  }
+  /* solve: c = Q^T b (first `nonzero` reflectors), back-substitute, un-permute */
+  float x[3] = {0, 0, 0};
+  if (nonzero > 0) {
+    for (int k = 0; k < nonzero; k++) {
+      if (hc[k] == 0.f) continue;
+      float tmp = 0.f;
+      for (int r = k + 1; r < rows; r++) tmp += A[r][k] * b[r];
+      tmp += b[k];
+      b[k] -= hc[k] * tmp;
+      for (int r = k + 1; r < rows; r++) b[r] -= hc[k] * A[r][k] * tmp;
+    }
+    float c[3];
+    for (int i = nonzero - 1; i >= 0; i--) {
+      float s = b[i];
+      for (int j = i + 1; j < nonzero; j++) s -= A[i][j] * c[j];
+      c[i] = s / A[i][i];
+    }
+    for (int i = 0; i < nonzero; i++) x[perm[i]] = c[i];
+  }
+  float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  pabcd[0] = x[0] / n; pabcd[1] = x[1] / n; pabcd[2] = x[2] / n; pabcd[3] = (float)(1.0 / (double)n);
+  for (int j = 0; j < 5; j++) {
+    float v = pabcd[0] * pts[3 * j] + pabcd[1] * pts[3 * j + 1] + pabcd[2] * pts[3 * j + 2] + pabcd[3];
+    if (fabs((double)v) > (double)thr) return 0;
+  }
+  return 1;
+}
+void orc_esti_plane_batch(const float* pts5, int n, float thr, float* pabcd, int* ok) {
+  for (int i = 0; i < n; i++) ok[i] = orc_esti_plane(pts5 + 15 * (size_t)i, thr, pabcd + 4 * (size_t)i);
+}
+
+/* ===================================================================================== */
+/* a3+a5+a6+a7+a8  h_share_model_geometric  (src/laserMapping.cpp:813-982) and the         */
+/*     HTH / H^T h products the ESKF forms from it (esekfom.hpp:1782-1809).                */
+/* ===================================================================================== */
+static void mat3_vec(const double* R, const double* v, double* o) {
+  for (int i = 0; i < 3; i++) o[i] = R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2];
+}
+static void mat3T_vec(const double* R, const double* v, double* o) {
+  for (int i = 0; i < 3; i++) o[i] = R[i] * v[0] + R[3 + i] * v[1] + R[6 + i] * v[2];
+}
+/* cyclic Jacobi for a symmetric 3x3 (stands in for Eigen::SelfAdjointEigenSolver,
+ * laserMapping.cpp:941-943; only |v.n| and V diag(mask) V^T are used, both sign/order free) */
+static void eig3_sym(const double* Ain, double* w, double* V) {
+  double A[9]; memcpy(A, Ain, sizeof(A));
+  for (int i = 0; i < 9; i++) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+      double apq = A[3 * p + q];
+      if (fabs(apq) < 1e-300) continue;
+      double th = (A[3 * q + q] - A[3 * p + p]) / (2.0 * apq);
+      double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      for (int k = 0; k < 3; k++) { double akp = A[3 * k + p], akq = A[3 * k + q]; A[3 * k + p] = c * akp - s * akq; A[3 * k + q] = s * akp + c * akq; }
+      for (int k = 0; k < 3; k++) { double apk = A[3 * p + k], aqk = A[3 * q + k]; A[3 * p + k] = c * apk - s * aqk; A[3 * q + k] = s * apk + c * aqk; }
+      for (int k = 0; k < 3; k++) { double vkp = V[3 * k + p], vkq = V[3 * k + q]; V[3 * k + p] = c * vkp - s * vkq; V[3 * k + q] = s * vkp + c * vkq; }
+    }
+  }
+  w[0] = A[0]; w[1] = A[4]; w[2] = A[8];
+}
+
+/* One call of the measurement model.
+ *   body      [n,4] downsampled scan in the lidar frame (feats_down_body)
+ *   R,t       state rot (row-major 3x3), pos;  R_LI,t_LI extrinsics (offset_R_L_I, offset_T_L_I)
+ *   search    ekfom_data.converge: redo the k-NN (laserMapping.cpp:842)
+ *   knn_mode  0 = iVox NEARBY stencil (live path), 1 = exact (ikd-Tree path, accept d2[4] <= 5)
+ * Per-scan persistent arrays (Nearest_Points, point_selected_surf): near_xyz [n,5,3],
+ * near_ids [n,5], near_cnt [n], selected [n].  Outputs: world [n,4], plane [n,4] = (normal, pd2),
+ * HTH [36] (the non-zero 6x6 block of the 15x15), HTh [6], res_sum, n_eff, degenerate.
+ * hx_out [n,6] / h_out [n] (optional) receive the compacted Jacobian rows and -pd2.
+ * Returns n_eff (0 -> ekfom_data.valid = false, "No Effective Points"). */
+int orc_lio_hmodel(const OrcIvox* map, const float* body, int n, const double* R, const double* t,
+                   const double* R_LI, const double* t_LI, int search, int knn_mode,
+                   float* near_xyz, int* near_ids, int* near_cnt, unsigned char* selected,
+                   float* world, float* plane, double* HTH, double* HTh, double* res_sum,
+                   int* degenerate, int degenerate_detect_en, double* hx_out, double* h_out,
+                   int nthreads) {
+  omp_set_num_threads(nthreads > 0 ? nthreads : 1);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < n; i++) {
+    const float* pb = body + 4 * (size_t)i;
+    double p_body[3] = {pb[0], pb[1], pb[2]}, pl[3], pw[3];
+    mat3_vec(R_LI, p_body, pl);
+    for (int d = 0; d < 3; d++) pl[d] += t_LI[d];
+    mat3_vec(R, pl, pw);
+    float* w = world + 4 * (size_t)i;
+    for (int d = 0; d < 3; d++) w[d] = (float)(pw[d] + t[d]);
+    w[3] = pb[3];
+    if (search) {
+      OrcCand best[5];
+      int nb = knn_mode == 0 ? ivox_knn_one(map, w, 5, 5.0, best) : exact_knn_one(map, w, 5, 5.0, best);
+      near_cnt[i] = nb;
+      for (int j = 0; j < 5; j++) {
+        near_ids[5 * (size_t)i + j] = j < nb ? best[j].id : -1;
+        float* o = near_xyz + (5 * (size_t)i + j) * 3;
+        o[0] = j < nb ? best[j].x : 0; o[1] = j < nb ? best[j].y : 0; o[2] = j < nb ? best[j].z : 0;
+      }
+      selected[i] = nb >= 5; /* laserMapping.cpp:847,850 */
+    }
+    if (!selected[i]) continue;
+    selected[i] = 0;
+    float pabcd[4];
+    if (orc_esti_plane(near_xyz + 15 * (size_t)i, 0.1f, pabcd)) {
+      float pd2 = pabcd[0] * w[0] + pabcd[1] * w[1] + pabcd[2] * w[2] + pabcd[3];
+      double nb2 = sqrt(p_body[0] * p_body[0] + p_body[1] * p_body[1] + p_body[2] * p_body[2]);
+      float s = (float)(1 - 0.9 * fabs((double)pd2) / sqrt(nb2)); /* laserMapping.cpp:861 */
+      if (s > 0.9) {
+        selected[i] = 1;
+        float* pl4 = plane + 4 * (size_t)i;
+        pl4[0] = pabcd[0]; pl4[1] = pabcd[1]; pl4[2] = pabcd[2]; pl4[3] = pd2;
+      }
+    }
+  }
+  /* compaction + H rows (laserMapping.cpp:875-932), extrinsic_est_en = false */
+  double* hx = (double*)malloc(sizeof(double) * 6 * (size_t)(n > 0 ? n : 1));
+  double* hh = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  int ne = 0; double total = 0.0;
+  for (int i = 0; i < n; i++) {
+    if (!selected[i]) continue;
+    const float* pb = body + 4 * (size_t)i; const float* pl4 = plane + 4 * (size_t)i;
+    total += (double)fabsf(pl4[3]); /* res_last[i] = abs(pd2) */
+    double pbe[3] = {pb[0], pb[1], pb[2]}, pt[3];
+    mat3_vec(R_LI, pbe, pt);
+    for (int d = 0; d < 3; d++) pt[d] += t_LI[d];
+    double nv[3] = {pl4[0], pl4[1], pl4[2]}, C[3];
+    mat3T_vec(R, nv, C); /* s.rot.conjugate() * norm_vec */
+    double Ax = pt[1] * C[2] - pt[2] * C[1], Ay = pt[2] * C[0] - pt[0] * C[2], Az = pt[0] * C[1] - pt[1] * C[0];
+    double* row = hx + 6 * (size_t)ne;
+    row[0] = nv[0]; row[1] = nv[1]; row[2] = nv[2]; row[3] = Ax; row[4] = Ay; row[5] = Az;
+    hh[ne] = -(double)pl4[3];
+    ne++;
+  }
+  *res_sum = total; *degenerate = 0;
+  memset(HTH, 0, sizeof(double) * 36); memset(HTh, 0, sizeof(double) * 6);
+  if (ne < 1) { free(hx); free(hh); return 0; }
+  if (degenerate_detect_en) { /* laserMapping.cpp:934-980 */
+    double H3[9] = {0};
+    for (int j = 0; j < ne; j++) for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) H3[3 * a + b] += hx[6 * (size_t)j + a] * hx[6 * (size_t)j + b];
+    double ew[3], V[9]; eig3_sym(H3, ew, V);
+    int mask[3] = {1, 1, 1}, deg = 0;
+    for (int i = 0; i < 3; i++) {
+      float contri = 0, strong = 0;
+      for (int j = 0; j < ne; j++) {
+        double r0 = hx[6 * (size_t)j], r1 = hx[6 * (size_t)j + 1], r2 = hx[6 * (size_t)j + 2];
+        double nn = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+        float dotp = (float)fabs((r0 / nn) * V[i] + (r1 / nn) * V[3 + i] + (r2 / nn) * V[6 + i]);
+        if (dotp > 0.1736) contri += dotp;
+        if (dotp > 0.7070) strong += dotp;
+      }
+      if (contri < 250.0 && strong < 50.0) { mask[i] = 0; deg = 1; }
+    }
+    if (deg) { /* mat_p = (V^T)^-1 V2 = V diag(mask) V^T ; rows n -> mat_p n */
+      double P[9] = {0};
+      for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int i = 0; i < 3; i++) if (mask[i]) P[3 * a + b] += V[3 * a + i] * V[3 * b + i];
+      for (int j = 0; j < ne; j++) {
+        double* row = hx + 6 * (size_t)j; double o[3];
+        mat3_vec(P, row, o); row[0] = o[0]; row[1] = o[1]; row[2] = o[2];
+      }
+      *degenerate = 1;
+    }
+  }
+  for (int j = 0; j < ne; j++) {
+    const double* row = hx + 6 * (size_t)j;
+    for (int a = 0; a < 6; a++) { for (int b = 0; b < 6; b++) HTH[6 * a + b] += row[a] * row[b]; HTh[a] += row[a] * hh[j]; }
+  }
+  if (hx_out) memcpy(hx_out, hx, sizeof(double) * 6 * (size_t)ne);
+  if (h_out) memcpy(h_out, hh, sizeof(double) * (size_t)ne);
+  free(hx); free(hh);
+  return ne;
+}
+
+/* ===================================================================================== */
+/* a10  map_incremental  (src/laserMapping.cpp:523-576).  flag[i]: 0 skip, 1 PointToAdd,   */
+/*      2 PointNoNeedDownsample.  Points are then added with id = id0 + i.                 */
+/* ===================================================================================== */
+static inline float calc_dist3(const float* a, const float* b) {
+  return (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
+}
+int orc_map_incremental(OrcIvox* map, const float* body, int n, const double* R, const double* t,
+                        const double* R_LI, const double* t_LI, const float* near_xyz, const int* near_cnt,
+                        int ekf_inited, double fsize, float* world, unsigned char* flag, int id0) {
+  int added = 0;
+  for (int i = 0; i < n; i++) {
+    const float* pb = body + 4 * (size_t)i;
+    double p_body[3] = {pb[0], pb[1], pb[2]}, pl[3], pw[3];
+    mat3_vec(R_LI, p_body, pl);
+    for (int d = 0; d < 3; d++) pl[d] += t_LI[d];
+    mat3_vec(R, pl, pw);
+    float* w = world + 4 * (size_t)i;
+    for (int d = 0; d < 3; d++) w[d] = (float)(pw[d] + t[d]);
+    w[3] = pb[3];
+    int f = 1;
+    if (near_cnt[i] > 0 && ekf_inited) {
+      const float* nr = near_xyz + 15 * (size_t)i;
+      float mid[3];
+      for (int d = 0; d < 3; d++) mid[d] = (float)(floor((double)w[d] / fsize) * fsize + 0.5 * fsize);
+      float dist = calc_dist3(w, mid);
+      if (fabs((double)nr[0] - (double)mid[0]) > 0.5 * fsize && fabs((double)nr[1] - (double)mid[1]) > 0.5 * fsize &&
+          fabs((double)nr[2] - (double)mid[2]) > 0.5 * fsize) {
+        f = 2;
+      } else {
+        for (int r = 0; r < 5; r++) {
+          if (near_cnt[i] < 5) break;
+          if (calc_dist3(nr + 3 * r, mid) < dist) { f = 0; break; }
+        }
+      }
+    }
+    flag[i] = (unsigned char)f;
+  }
+  for (int pass = 1; pass <= 2; pass++) /* PointToAdd first, then PointNoNeedDownsample */
+    for (int i = 0; i < n; i++) if (flag[i] == pass) { int id = id0 + i; orc_ivox_add(map, world + 4 * (size_t)i, 4, 1, 0, &id); added++; }
+  return added;
+}

@@ -1,0 +1,219 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes bindings for the CPU oracle.
+
+Two libraries (built by oracle/Makefile):
+  liblsd_oracle.so      our plain-C restatement ("port") of the reference algorithms
+  _ref/libref_lio.so    the UNMODIFIED reference sources (iVox, ikd-Tree, esti_plane) compiled
+                        where they lie under /root/reference ("reference")
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT = os.path.join(_HERE, "liblsd_oracle.so")
+_REF = os.path.join(_HERE, "_ref", "libref_lio.so")
+
+_f = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_d = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def _load_port():
+    if not os.path.exists(_PORT):
+        raise RuntimeError(f"{_PORT} missing: run `make -C oracle` (or __graft_entry__.build())")
+    L = C.CDLL(_PORT)
+    L.orc_voxelgrid.restype = C.c_int
+    L.orc_voxelgrid.argtypes = [_f, C.c_int, C.c_float, _f, C.c_void_p]
+    L.orc_ivox_create.restype = C.c_void_p
+    L.orc_ivox_create.argtypes = [C.c_float, C.c_int, C.c_size_t]
+    L.orc_ivox_set_nearby.argtypes = [C.c_void_p, C.c_int]
+    L.orc_ivox_destroy.argtypes = [C.c_void_p]
+    L.orc_ivox_num_cells.restype = C.c_size_t
+    L.orc_ivox_num_cells.argtypes = [C.c_void_p]
+    L.orc_ivox_num_points.restype = C.c_size_t
+    L.orc_ivox_num_points.argtypes = [C.c_void_p]
+    L.orc_ivox_add.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.orc_knn.argtypes = [C.c_void_p, C.c_int, _f, C.c_int, C.c_int, C.c_int, C.c_double, _i, _f, _f, _i, C.c_int]
+    L.orc_esti_plane_batch.argtypes = [_f, C.c_int, C.c_float, _f, _i]
+    L.orc_lio_hmodel.restype = C.c_int
+    L.orc_lio_hmodel.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, C.c_int, C.c_int, _f, _i, _i, _u8,
+                                 _f, _f, _d, _d, _d, _i, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_map_incremental.restype = C.c_int
+    L.orc_map_incremental.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, _f, _i, C.c_int, C.c_double, _f, _u8, C.c_int]
+    return L
+
+
+def _load_ref():
+    if not os.path.exists(_REF):
+        return None
+    L = C.CDLL(_REF)
+    L.ref_ivox_create.restype = C.c_void_p
+    L.ref_ivox_create.argtypes = [C.c_float, C.c_int, C.c_size_t]
+    L.ref_ivox_destroy.argtypes = [C.c_void_p]
+    L.ref_ivox_add.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_double]
+    L.ref_ivox_num_cells.restype = C.c_size_t
+    L.ref_ivox_num_cells.argtypes = [C.c_void_p]
+    L.ref_ivox_knn.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_double, _i, _f, _i, C.c_int]
+    L.ref_ikd_create.restype = C.c_void_p
+    L.ref_ikd_destroy.argtypes = [C.c_void_p]
+    L.ref_ikd_build.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
+    L.ref_ikd_knn.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _i, _f, _i, C.c_int]
+    L.ref_esti_plane.argtypes = [_f, C.c_int, C.c_float, _f, _i]
+    return L
+
+
+port = _load_port()
+ref = _load_ref()
+HAVE_REF = ref is not None
+
+
+def _c32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ------------------------------------------------------------------ voxel grid
+def voxelgrid(pts: np.ndarray, leaf: float = 0.5, want_vidx: bool = False):
+    """PCL VoxelGrid restatement.  pts [n,4] -> [m,4] (ascending voxel index)."""
+    pts = _c32(pts)
+    n = pts.shape[0]
+    out = np.empty((max(n, 1), 4), np.float32)
+    vidx = np.empty(max(n, 1), np.int32)
+    m = port.orc_voxelgrid(pts, n, leaf, out, vidx.ctypes.data)
+    if m < 0:
+        return (pts.copy(), None) if want_vidx else pts.copy()
+    return (out[:m].copy(), vidx[:m].copy()) if want_vidx else out[:m].copy()
+
+
+# ------------------------------------------------------------------ iVox (port)
+class OracleIvox:
+    """Restated faster_lio::IVox (ivox3d.h).  nearby in {0, 6, 18, 26, 74}."""
+
+    def __init__(self, res: float = 0.5, nearby: int = 18, expected_cells: int = 1 << 16):
+        self.h = port.orc_ivox_create(res, nearby, expected_cells)
+        self.res = res
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            port.orc_ivox_destroy(self.h)
+            self.h = None
+
+    def set_nearby(self, nearby: int):
+        port.orc_ivox_set_nearby(self.h, nearby)
+
+    def add(self, xyz: np.ndarray, id0: int):
+        xyz = _c32(xyz)
+        port.orc_ivox_add(self.h, xyz, xyz.shape[1], xyz.shape[0], id0, None)
+
+    @property
+    def num_cells(self):
+        return port.orc_ivox_num_cells(self.h)
+
+    @property
+    def num_points(self):
+        return port.orc_ivox_num_points(self.h)
+
+    def knn(self, q: np.ndarray, k: int = 5, max_sq: float = 5.0, exact: bool = False, nthreads: int = 8):
+        """-> ids [nq,k] (-1 pad), d2 [nq,k] (-1 pad), xyz [nq,k,3], cnt [nq]; canonical (d2,id) order."""
+        q = _c32(q)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        d2 = np.empty((nq, k), np.float32)
+        xyz = np.empty((nq, k, 3), np.float32)
+        cnt = np.empty(nq, np.int32)
+        port.orc_knn(self.h, 1 if exact else 0, q, q.shape[1], nq, k, max_sq, ids, d2, xyz, cnt, nthreads)
+        return ids, d2, xyz, cnt
+
+
+def esti_plane(pts5: np.ndarray, thr: float = 0.1):
+    pts5 = _c32(pts5).reshape(-1, 5, 3)
+    n = pts5.shape[0]
+    pabcd = np.empty((n, 4), np.float32)
+    ok = np.empty(n, np.int32)
+    port.orc_esti_plane_batch(pts5, n, thr, pabcd, ok)
+    return pabcd, ok
+
+
+# ------------------------------------------------------------------ compiled reference
+class RefIvox:
+    """The reference's own faster_lio::IVox, compiled unmodified (oracle/_ref)."""
+
+    def __init__(self, res: float = 0.5, nearby: int = 18, capacity: int = 1 << 30):
+        assert HAVE_REF, "oracle/_ref/libref_lio.so not built"
+        self.h = ref.ref_ivox_create(res, nearby, capacity)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref.ref_ivox_destroy(self.h)
+            self.h = None
+
+    def add(self, xyz: np.ndarray, id0: int):
+        xyz = _c32(xyz[:, :3])
+        ref.ref_ivox_add(self.h, xyz, xyz.shape[0], id0, 0.0)
+
+    @property
+    def num_cells(self):
+        return ref.ref_ivox_num_cells(self.h)
+
+    def knn(self, q: np.ndarray, k: int = 5, max_sq: float = 5.0, nthreads: int = 8):
+        """-> ids [nq,k], xyz [nq,k,3], cnt [nq] in the REFERENCE's order (nearest first)."""
+        q = _c32(q[:, :3])
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        xyz = np.empty((nq, k, 3), np.float32)
+        cnt = np.empty(nq, np.int32)
+        ref.ref_ivox_knn(self.h, q, nq, k, max_sq, ids, xyz, cnt, nthreads)
+        return ids, xyz, cnt
+
+
+class RefIkd:
+    """The reference's ikd-Tree (KD_TREE<PointXYZINormal>), compiled unmodified."""
+
+    def __init__(self):
+        assert HAVE_REF
+        self.h = ref.ref_ikd_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref.ref_ikd_destroy(self.h)
+            self.h = None
+
+    def build(self, xyz: np.ndarray, id0: int = 0):
+        xyz = _c32(xyz[:, :3])
+        ref.ref_ikd_build(self.h, xyz, xyz.shape[0], id0)
+
+    def knn(self, q: np.ndarray, k: int = 5, nthreads: int = 8):
+        q = _c32(q[:, :3])
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        d2 = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.int32)
+        ref.ref_ikd_knn(self.h, q, nq, k, ids, d2, cnt, nthreads)
+        return ids, d2, cnt
+
+
+def ref_esti_plane(pts5: np.ndarray, thr: float = 0.1):
+    assert HAVE_REF
+    pts5 = _c32(pts5).reshape(-1, 5, 3)
+    n = pts5.shape[0]
+    pabcd = np.empty((n, 4), np.float32)
+    ok = np.empty(n, np.int32)
+    ref.ref_esti_plane(pts5, n, thr, pabcd, ok)
+    return pabcd, ok
+
+
+def canonical_rows(ids: np.ndarray, d2: np.ndarray):
+    """Sort each k-NN row ascending by (d2, id) with -1 padding last (the repo-wide canonical order)."""
+    big = np.where(ids < 0, np.inf, d2.astype(np.float64))
+    idk = np.where(ids < 0, np.iinfo(np.int32).max, ids)
+    key = np.empty(ids.shape, dtype=[("d", np.float64), ("i", np.int64)])
+    key["d"] = big
+    key["i"] = idk
+    order = np.argsort(key, axis=1, order=("d", "i"), kind="stable")
+    return np.take_along_axis(ids, order, 1), np.take_along_axis(d2, order, 1)
