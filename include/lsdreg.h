@@ -1,0 +1,176 @@
+/* lsdreg.h — C ABI of liblsdreg.so: the B200-native registration hot path for LSD.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain
+ * pointers and sizes, returns an `lsd_status_t` (0 = ok, < 0 = error, > 0 = informational), never
+ * throws across the boundary, and cites the reference interface it replaces (paths relative to
+ * /root/reference).  INTEGRATION.md shows the reference-side bindings (the C++ seams in
+ * slam/mapping/fastlio/src/fastlio.cpp:9-16 and hdl_graph_slam/registrations.hpp:15-16, and the
+ * pybind11 `slam_wrapper` module).
+ *
+ * Conventions
+ *   - points are float32 [n,4] = (x, y, z, intensity), row-major, the layout py_utils.cpp:149-169
+ *     hands to the reference;
+ *   - `*_dev` variants take DEVICE pointers (inputs already resident in HBM) and never synchronise
+ *     unless they must return a scalar; the plain variants take HOST pointers and include the
+ *     H2D/D2H copies;
+ *   - handles are confined to one thread at a time (SURVEY.md §8b "Thread-safety");
+ *   - there is NO CPU fallback: every call fails with LSD_ERR_NO_DEVICE when no sm_100 GPU /
+ *     CUDA driver is present.
+ */
+#ifndef LSDREG_H
+#define LSDREG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int lsd_status_t;
+#define LSD_OK 0
+#define LSD_NO_EFFECTIVE_POINTS 1   /* ekfom_data.valid == false, laserMapping.cpp:888-893      */
+#define LSD_SCAN_TOO_SMALL 2        /* feats_down_size < 5, laserMapping.cpp:1252-1256           */
+#define LSD_MAP_SEEDED 3            /* first scan only seeded the map, laserMapping.cpp:1227-1239 */
+#define LSD_ERR_INVALID (-1)
+#define LSD_ERR_CUDA (-2)
+#define LSD_ERR_NO_DEVICE (-3)
+#define LSD_ERR_CAPACITY (-4)       /* hash table / bucket levels / scratch capacity exceeded    */
+#define LSD_ERR_GRID_OVERFLOW (-5)  /* voxel grid larger than int32 (PCL returns input unchanged) */
+
+const char* lsd_version(void);
+const char* lsd_last_error(void);
+/* Select the CUDA device for this thread's subsequent lsd_* calls (default 0). */
+lsd_status_t lsd_init(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Hash-voxel map — replaces faster_lio::IVox (slam/mapping/fastlio/include/ivox3d/ivox3d.h:31-112:
+ * AddPoints :231-256, GetClosestPoint :139-171, Pos2Grid :258-261) and, through the EXACT stencil,
+ * the ikd-Tree queries (include/ikd-Tree/ikd_Tree.cpp:367-397 Nearest_Search).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_map lsd_map_t;
+
+/* stencils: IVox::NearbyType (ivox3d.h:40-46) + exact radius search */
+#define LSD_STENCIL_CENTER 0
+#define LSD_STENCIL_NEARBY6 6
+#define LSD_STENCIL_NEARBY18 18
+#define LSD_STENCIL_NEARBY26 26
+#define LSD_STENCIL_NEARBY74 74
+#define LSD_STENCIL_EXACT 1000 /* all cells meeting the sqrt(max_sq) ball; accepts d2 <= max_sq */
+
+/* resolution: IVox::Options::resolution_ (0.5, laserMapping.cpp:1061).  log2_lines: the table has
+ * 2^log2_lines 128-byte cell lines; keep the load factor <= 0.5 (one line per occupied voxel). */
+lsd_status_t lsd_map_create(lsd_map_t** out, float resolution, int log2_lines);
+lsd_status_t lsd_map_destroy(lsd_map_t* m);
+lsd_status_t lsd_map_clear(lsd_map_t* m);
+/* IVox::AddPoints.  Point i is stored with id = id0 + i (ids are what k-NN queries return). */
+lsd_status_t lsd_map_insert(lsd_map_t* m, const float* xyzi_host, int n, int32_t id0);
+lsd_status_t lsd_map_insert_dev(lsd_map_t* m, const float* xyzi_dev, int n, int32_t id0);
+/* IVox::NumValidGrids / NumPoints; n_dropped counts points refused for capacity/range. */
+lsd_status_t lsd_map_stats(lsd_map_t* m, uint64_t* n_cells, uint64_t* n_points, uint64_t* n_dropped);
+/* IVox::GetClosestPoint(pt, out, k, max_sq) for a batch.  k in {1, 5, 20}.  Results per query are
+ * sorted ascending by (d2, id); out_idx is -1 padded, out_d2 is -1 padded; out_cnt = #found.
+ * fp32 d2 = (dx*dx + dy*dy) + dz*dz without FMA, as ivox3d_node.hpp:11-14 / ikd_Tree.cpp:1374. */
+lsd_status_t lsd_knn_query(lsd_map_t* m, const float* q_host, int nq, int k, float max_sq, int stencil,
+                           int32_t* out_idx, float* out_d2, int32_t* out_cnt);
+lsd_status_t lsd_knn_query_dev(lsd_map_t* m, const float* q_dev, int nq, int k, float max_sq, int stencil,
+                               int32_t* out_idx_dev, float* out_d2_dev, int32_t* out_cnt_dev);
+
+/* ------------------------------------------------------------------------------------------
+ * Voxel-grid downsample — replaces pcl::VoxelGrid<PointXYZINormal>::filter as called at
+ * laserMapping.cpp:1206-1207 (leaf 0.5) and hdl_localization_nodelet.cpp:333-344.
+ * Output: one centroid (all 4 channels) per occupied leaf, ascending leaf index like PCL.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_voxelgrid lsd_voxelgrid_t;
+lsd_status_t lsd_voxelgrid_create(lsd_voxelgrid_t** out, int max_points, int log2_max_cells);
+lsd_status_t lsd_voxelgrid_destroy(lsd_voxelgrid_t* g);
+/* out_host must hold n points; *m receives the output count. */
+lsd_status_t lsd_voxelgrid_filter(lsd_voxelgrid_t* g, const float* in_host, int n, float leaf, float* out_host, int* m);
+lsd_status_t lsd_voxelgrid_filter_dev(lsd_voxelgrid_t* g, const float* in_dev, int n, float leaf, float* out_dev,
+                                      int* m_dev);
+
+/* ------------------------------------------------------------------------------------------
+ * LIO front-end — replaces the per-scan body of fastlio_main (laserMapping.cpp:1126-1387):
+ * VoxelGrid -> iterated ESKF update (esekf::update_iterated_dyn_share_modified,
+ * IKFoM_toolkit/esekfom/esekfom.hpp:1619-1931) with h_share_model_geometric
+ * (laserMapping.cpp:813-982) -> map_incremental (laserMapping.cpp:523-576).
+ *
+ * State vector (26 doubles), state_ikfom of use-ikfom.hpp:12-21 with quaternions as (x,y,z,w):
+ *   pos[3] rot[4] offset_R_L_I[4] offset_T_L_I[3] vel[3] bg[3] ba[3] grav[3]
+ * Covariance: 23x23 row-major doubles (DOF order pos, rot, offset_R, offset_T, vel, bg, ba, grav2).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_lio lsd_lio_t;
+
+typedef struct lsd_lio_params {
+  int max_points;            /* scratch capacity; reference static cap 100000, laserMapping.cpp:86   */
+  int max_scan_points;       /* raw scan capacity for lsd_lio_scan (pre-downsample)                 */
+  float filter_size_surf;    /* 0.5, laserMapping.cpp:1027                                          */
+  float filter_size_map;     /* 0.5, laserMapping.cpp:1028                                          */
+  float ivox_resolution;     /* 0.5, laserMapping.cpp:1061                                          */
+  int ivox_nearby;           /* LSD_STENCIL_*; reference: NEARBY74 first second, then NEARBY18      */
+  int map_log2_lines;        /* hash table size                                                     */
+  int max_iterations;        /* NUM_MAX_ITERATIONS = 4, laserMapping.cpp:1026                       */
+  double laser_point_cov;    /* LASER_POINT_COV = 0.001, laserMapping.cpp:71                        */
+  double converge_eps;       /* 0.001, laserMapping.cpp:1114-1116                                   */
+  int degenerate_detect_en;  /* laserMapping.cpp:83                                                 */
+  int knn_mode_exact;        /* 0: iVox stencil (live path), 1: exact k-NN (ikd-Tree path)          */
+} lsd_lio_params_t;
+
+typedef struct lsd_lio_info {
+  int n_down;       /* feats_down_size                                   */
+  int iterations;   /* h-model evaluations run                            */
+  int n_eff;        /* effct_feat_num of the last evaluation              */
+  int degenerate;   /* is_degenerate of the last evaluation               */
+  int n_added;      /* points inserted by map_incremental                 */
+  int converged;    /* the update returned through the t > 1 exit         */
+  double res_mean;  /* res_mean_last                                      */
+  double gpu_ms;    /* device time of this scan (CUDA events)             */
+  int kernel_launches;
+} lsd_lio_info_t;
+
+void lsd_lio_default_params(lsd_lio_params_t* p);
+lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p);
+lsd_status_t lsd_lio_destroy(lsd_lio_t* l);
+lsd_map_t* lsd_lio_map(lsd_lio_t* l);
+lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil); /* IVox::SetNearByType, laserMapping.cpp:1241-1243 */
+lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag);
+/* Id given to the next point map_incremental inserts (ids of points inserted through
+ * lsd_map_insert(lsd_lio_map(l), ...) are the caller's). */
+lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, laserMapping.cpp:1196 */
+
+/* Load the undistorted scan (feats_undistort) and, if `downsample`, run the 0.5 m VoxelGrid
+ * (laserMapping.cpp:1206-1207).  Returns the downsampled size in *n_down. */
+lsd_status_t lsd_lio_load_scan(lsd_lio_t* l, const float* scan_host, int n, int downsample, int* n_down);
+lsd_status_t lsd_lio_load_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, int downsample, int* n_down);
+/* Copy back the downsampled scan (feats_down_body), [n_down,4]. */
+lsd_status_t lsd_lio_get_down(lsd_lio_t* l, float* out_host, int cap, int* n_down);
+
+/* One evaluation of h_share_model_geometric on the loaded scan at `state`; search != 0 redoes the
+ * k-NN (ekfom_data.converge).  HTH[36]: the non-zero 6x6 block of h_x^T h_x; HTh[6] = h_x^T h.
+ * Returns LSD_NO_EFFECTIVE_POINTS when n_eff < 1. */
+lsd_status_t lsd_lio_linearize(lsd_lio_t* l, const double* state26, int search, double* HTH36, double* HTh6,
+                               double* res_sum, int* n_eff, int* degenerate);
+/* Debug/parity taps after lsd_lio_linearize: per downsampled point neighbours, plane and flags. */
+lsd_status_t lsd_lio_get_matches(lsd_lio_t* l, int32_t* near_idx /*[n,5]*/, float* near_xyz /*[n,5,3]*/,
+                                 int32_t* near_cnt /*[n]*/, uint8_t* selected /*[n]*/, float* plane /*[n,4]*/,
+                                 float* world /*[n,4]*/);
+/* esekf::update_iterated_dyn_share_modified on the loaded scan. */
+lsd_status_t lsd_lio_update(lsd_lio_t* l, double* state26_inout, double* P529_inout, lsd_lio_info_t* info);
+/* map_incremental at `state` using the neighbour lists of the last search. */
+lsd_status_t lsd_lio_map_incremental(lsd_lio_t* l, const double* state26, int* n_added);
+/* The whole per-scan pass: load (+downsample) -> [seed map | update -> map_incremental]. */
+lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* state26_inout, double* P529_inout,
+                          lsd_lio_info_t* info);
+lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double* state26_inout,
+                              double* P529_inout, lsd_lio_info_t* info);
+
+/* Host-side manifold helpers (exported so bindings/tests use the same algebra as the filter).
+ * IMU_Processing.hpp:224-230 initial covariance; state_ikfom boxplus/boxminus. */
+void lsd_lio_init_cov(double* P529);
+void lsd_state_boxplus(double* state26_inout, const double* delta23);
+void lsd_state_boxminus(const double* a26, const double* b26, double* out23);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSDREG_H */

@@ -1,1 +1,12 @@
-"""lsdreg — B200-native registration hot path for LSD (lidar-slam-detection).  See DESIGN.md."""
+"""lsdreg — B200-native registration hot path for LSD (lidar-slam-detection).
+
+Import as ``import lsdreg`` (alias module at the repo root; the directory name carries a hyphen).
+The compute path is liblsdreg.so (hand-written sm_100a CUDA behind a C ABI, include/lsdreg.h);
+this package is its thin host-side mirror.  See DESIGN.md / INTEGRATION.md.
+"""
+from . import synth  # noqa: F401
+from .capi import (  # noqa: F401
+    ERR_CAPACITY, ERR_CUDA, ERR_GRID_OVERFLOW, ERR_INVALID, ERR_NO_DEVICE, MAP_SEEDED, NO_EFFECTIVE_POINTS, OK,
+    SCAN_TOO_SMALL, STENCIL_CENTER, STENCIL_EXACT, STENCIL_NEARBY6, STENCIL_NEARBY18, STENCIL_NEARBY26,
+    STENCIL_NEARBY74, HashVoxelMap, LioFrontend, LsdError, VoxelGrid, init, init_cov, lib, make_state,
+    state_boxminus, state_boxplus)

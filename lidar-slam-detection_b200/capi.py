@@ -1,0 +1,320 @@
+"""ctypes bindings of liblsdreg.so (include/lsdreg.h) and thin numpy / torch front-ends.
+
+The product path is the CUDA library: importing this module fails loudly when liblsdreg.so has not
+been built, and every call raises :class:`LsdError` when no CUDA device is present.  There is no
+CPU fallback and nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblsdreg.so")
+
+OK, NO_EFFECTIVE_POINTS, SCAN_TOO_SMALL, MAP_SEEDED = 0, 1, 2, 3
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_GRID_OVERFLOW = -1, -2, -3, -4, -5
+STENCIL_CENTER, STENCIL_NEARBY6, STENCIL_NEARBY18, STENCIL_NEARBY26, STENCIL_NEARBY74, STENCIL_EXACT = 0, 6, 18, 26, 74, 1000
+
+
+class LsdError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"lsdreg status {status}: {msg}")
+        self.status = status
+
+
+class LioParams(C.Structure):
+    _fields_ = [("max_points", C.c_int), ("max_scan_points", C.c_int), ("filter_size_surf", C.c_float),
+                ("filter_size_map", C.c_float), ("ivox_resolution", C.c_float), ("ivox_nearby", C.c_int),
+                ("map_log2_lines", C.c_int), ("max_iterations", C.c_int), ("laser_point_cov", C.c_double),
+                ("converge_eps", C.c_double), ("degenerate_detect_en", C.c_int), ("knn_mode_exact", C.c_int)]
+
+
+class LioInfo(C.Structure):
+    _fields_ = [("n_down", C.c_int), ("iterations", C.c_int), ("n_eff", C.c_int), ("degenerate", C.c_int),
+                ("n_added", C.c_int), ("converged", C.c_int), ("res_mean", C.c_double), ("gpu_ms", C.c_double),
+                ("kernel_launches", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/lsdreg.h declares: (name, restype, argtypes)
+_vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
+_pp = C.POINTER(C.c_void_p)
+_pi = C.POINTER(C.c_int)
+_pu64 = C.POINTER(C.c_uint64)
+SIGNATURES = [
+    ("lsd_version", C.c_char_p, []),
+    ("lsd_last_error", C.c_char_p, []),
+    ("lsd_init", _i, [_i]),
+    ("lsd_map_create", _i, [_pp, _f, _i]),
+    ("lsd_map_destroy", _i, [_vp]),
+    ("lsd_map_clear", _i, [_vp]),
+    ("lsd_map_insert", _i, [_vp, _vp, _i, C.c_int32]),
+    ("lsd_map_insert_dev", _i, [_vp, _vp, _i, C.c_int32]),
+    ("lsd_map_stats", _i, [_vp, _pu64, _pu64, _pu64]),
+    ("lsd_knn_query", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
+    ("lsd_knn_query_dev", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
+    ("lsd_voxelgrid_create", _i, [_pp, _i, _i]),
+    ("lsd_voxelgrid_destroy", _i, [_vp]),
+    ("lsd_voxelgrid_filter", _i, [_vp, _vp, _i, _f, _vp, _pi]),
+    ("lsd_voxelgrid_filter_dev", _i, [_vp, _vp, _i, _f, _vp, _vp]),
+    ("lsd_lio_default_params", None, [C.POINTER(LioParams)]),
+    ("lsd_lio_create", _i, [_pp, C.POINTER(LioParams)]),
+    ("lsd_lio_destroy", _i, [_vp]),
+    ("lsd_lio_map", _vp, [_vp]),
+    ("lsd_lio_set_nearby", _i, [_vp, _i]),
+    ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
+    ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
+    ("lsd_lio_load_scan", _i, [_vp, _vp, _i, _i, _pi]),
+    ("lsd_lio_load_scan_dev", _i, [_vp, _vp, _i, _i, _pi]),
+    ("lsd_lio_get_down", _i, [_vp, _vp, _i, _pi]),
+    ("lsd_lio_linearize", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_d), _pi, _pi]),
+    ("lsd_lio_get_matches", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("lsd_lio_update", _i, [_vp, _vp, _vp, C.POINTER(LioInfo)]),
+    ("lsd_lio_map_incremental", _i, [_vp, _vp, _pi]),
+    ("lsd_lio_scan", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(LioInfo)]),
+    ("lsd_lio_scan_dev", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(LioInfo)]),
+    ("lsd_lio_init_cov", None, [_vp]),
+    ("lsd_state_boxplus", None, [_vp, _vp]),
+    ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
+]
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python __graft_entry__.py` "
+                          "(nvcc, sm_100a). lsdreg has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, res, args in SIGNATURES:
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load_library()
+
+
+def check(status: int) -> int:
+    if status < 0:
+        raise LsdError(status, lib.lsd_last_error().decode())
+    return status
+
+
+def _ptr(a) -> int:
+    """Address of a numpy array's data or of a torch tensor's storage (host or device)."""
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def _f32(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("points must be float32 [n,4] = (x, y, z, intensity)")
+    return a
+
+
+def init(device: int = 0):
+    check(lib.lsd_init(device))
+
+
+class HashVoxelMap:
+    """Device-resident hash-voxel map: the replacement of faster_lio::IVox (ivox3d.h)."""
+
+    def __init__(self, resolution: float = 0.5, log2_lines: int = 20, _borrow: int | None = None):
+        self._own = _borrow is None
+        if _borrow is not None:
+            self.h = C.c_void_p(_borrow)
+        else:
+            self.h = C.c_void_p()
+            check(lib.lsd_map_create(C.byref(self.h), resolution, log2_lines))
+
+    def close(self):
+        if self._own and self.h:
+            lib.lsd_map_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def clear(self):
+        check(lib.lsd_map_clear(self.h))
+
+    def insert(self, pts, id0: int = 0):
+        """IVox::AddPoints.  numpy [n,4] (host path) or a CUDA torch tensor [n,4] (device path)."""
+        if isinstance(pts, np.ndarray):
+            pts = _f32(pts)
+            check(lib.lsd_map_insert(self.h, _ptr(pts), pts.shape[0], id0))
+        else:
+            check(lib.lsd_map_insert_dev(self.h, _ptr(pts), pts.shape[0], id0))
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib.lsd_map_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(cells=a.value, points=b.value, dropped=c.value)
+
+    def knn(self, q, k: int = 5, max_sq: float = 5.0, stencil: int = STENCIL_NEARBY18):
+        """IVox::GetClosestPoint for a batch -> (idx [nq,k], d2 [nq,k], cnt [nq]), canonical order."""
+        q = _f32(q)
+        nq = q.shape[0]
+        idx = np.empty((nq, k), np.int32)
+        d2 = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.int32)
+        check(lib.lsd_knn_query(self.h, _ptr(q), nq, k, max_sq, stencil, _ptr(idx), _ptr(d2), _ptr(cnt)))
+        return idx, d2, cnt
+
+    def knn_dev(self, q, idx, d2, cnt, k: int = 5, max_sq: float = 5.0, stencil: int = STENCIL_NEARBY18):
+        """Device-pointer variant on CUDA torch tensors; asynchronous."""
+        check(lib.lsd_knn_query_dev(self.h, _ptr(q), q.shape[0], k, max_sq, stencil, _ptr(idx), _ptr(d2), _ptr(cnt)))
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid replacement (centroid per leaf, ascending leaf index)."""
+
+    def __init__(self, max_points: int = 400000, log2_max_cells: int = 28):
+        self.h = C.c_void_p()
+        check(lib.lsd_voxelgrid_create(C.byref(self.h), max_points, log2_max_cells))
+
+    def close(self):
+        if self.h:
+            lib.lsd_voxelgrid_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def filter(self, pts: np.ndarray, leaf: float = 0.5) -> np.ndarray:
+        pts = _f32(pts)
+        out = np.empty_like(pts)
+        m = C.c_int()
+        st = lib.lsd_voxelgrid_filter(self.h, _ptr(pts), pts.shape[0], leaf, _ptr(out), C.byref(m))
+        if st == ERR_GRID_OVERFLOW:  # PCL: warns and returns the input cloud
+            return out[:m.value].copy()
+        check(st)
+        return out[:m.value].copy()
+
+
+STATE_DIM, DOF = 26, 23
+
+
+def init_cov() -> np.ndarray:
+    P = np.zeros((DOF, DOF))
+    lib.lsd_lio_init_cov(_ptr(P))
+    return P
+
+
+def make_state(pos=(0, 0, 0), rot_xyzw=(0, 0, 0, 1), off_R_xyzw=(0, 0, 0, 1), off_T=(0, 0, 0), vel=(0, 0, 0),
+               bg=(0, 0, 0), ba=(0, 0, 0), grav=(0, 0, -9.809)) -> np.ndarray:
+    return np.concatenate([pos, rot_xyzw, off_R_xyzw, off_T, vel, bg, ba, grav]).astype(np.float64)
+
+
+def state_boxplus(x: np.ndarray, d: np.ndarray) -> np.ndarray:
+    x = np.array(x, np.float64)
+    d = np.ascontiguousarray(d, np.float64)
+    lib.lsd_state_boxplus(_ptr(x), _ptr(d))
+    return x
+
+
+def state_boxminus(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    r = np.zeros(DOF)
+    lib.lsd_state_boxminus(_ptr(a), _ptr(b), _ptr(r))
+    return r
+
+
+class LioFrontend:
+    """Per-scan LIO pass (fastlio_main body): downsample -> iterated ESKF update -> map_incremental."""
+
+    def __init__(self, **kw):
+        self.params = LioParams()
+        lib.lsd_lio_default_params(C.byref(self.params))
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown LIO parameter {k}")
+            setattr(self.params, k, v)
+        self.h = C.c_void_p()
+        check(lib.lsd_lio_create(C.byref(self.h), C.byref(self.params)))
+        self.map = HashVoxelMap(_borrow=lib.lsd_lio_map(self.h))
+
+    def close(self):
+        if self.h:
+            lib.lsd_lio_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def set_nearby(self, stencil: int):
+        check(lib.lsd_lio_set_nearby(self.h, stencil))
+
+    def set_next_id(self, i: int):
+        check(lib.lsd_lio_set_next_id(self.h, i))
+
+    def set_ekf_inited(self, flag: bool):
+        check(lib.lsd_lio_set_ekf_inited(self.h, int(flag)))
+
+    def load_scan(self, scan, downsample: bool = True) -> int:
+        n_down = C.c_int()
+        if isinstance(scan, np.ndarray):
+            scan = _f32(scan)
+            check(lib.lsd_lio_load_scan(self.h, _ptr(scan), scan.shape[0], int(downsample), C.byref(n_down)))
+        else:
+            check(lib.lsd_lio_load_scan_dev(self.h, _ptr(scan), scan.shape[0], int(downsample), C.byref(n_down)))
+        self.n_down = n_down.value
+        return n_down.value
+
+    def get_down(self) -> np.ndarray:
+        out = np.empty((max(self.n_down, 1), 4), np.float32)
+        n = C.c_int()
+        check(lib.lsd_lio_get_down(self.h, _ptr(out), out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
+
+    def linearize(self, state: np.ndarray, search: bool = True):
+        state = np.ascontiguousarray(state, np.float64)
+        HTH, HTh = np.zeros((6, 6)), np.zeros(6)
+        rs, ne, dg = C.c_double(), C.c_int(), C.c_int()
+        st = check(lib.lsd_lio_linearize(self.h, _ptr(state), int(search), _ptr(HTH), _ptr(HTh), C.byref(rs),
+                                         C.byref(ne), C.byref(dg)))
+        return dict(status=st, HTH=HTH, HTh=HTh, res_sum=rs.value, n_eff=ne.value, degenerate=dg.value)
+
+    def get_matches(self):
+        n = self.n_down
+        idx = np.empty((n, 5), np.int32)
+        xyz = np.empty((n, 5, 3), np.float32)
+        cnt = np.empty(n, np.int32)
+        sel = np.empty(n, np.uint8)
+        plane = np.empty((n, 4), np.float32)
+        world = np.empty((n, 4), np.float32)
+        check(lib.lsd_lio_get_matches(self.h, _ptr(idx), _ptr(xyz), _ptr(cnt), _ptr(sel), _ptr(plane), _ptr(world)))
+        return dict(idx=idx, xyz=xyz, cnt=cnt, selected=sel, plane=plane, world=world)
+
+    def update(self, state: np.ndarray, P: np.ndarray):
+        state = np.array(state, np.float64)
+        P = np.array(P, np.float64)
+        info = LioInfo()
+        st = check(lib.lsd_lio_update(self.h, _ptr(state), _ptr(P), C.byref(info)))
+        return state, P, dict(info.as_dict(), status=st)
+
+    def map_incremental(self, state: np.ndarray) -> int:
+        state = np.ascontiguousarray(state, np.float64)
+        n = C.c_int()
+        check(lib.lsd_lio_map_incremental(self.h, _ptr(state), C.byref(n)))
+        return n.value
+
+    def scan(self, scan, state: np.ndarray, P: np.ndarray):
+        """Whole pass.  `scan`: numpy [n,4] (host pointer, H2D inside) or CUDA torch tensor (device)."""
+        state = np.array(state, np.float64)
+        P = np.array(P, np.float64)
+        info = LioInfo()
+        if isinstance(scan, np.ndarray):
+            scan = _f32(scan)
+            st = lib.lsd_lio_scan(self.h, _ptr(scan), scan.shape[0], _ptr(state), _ptr(P), C.byref(info))
+        elif scan.is_cuda:
+            st = lib.lsd_lio_scan_dev(self.h, _ptr(scan), scan.shape[0], _ptr(state), _ptr(P), C.byref(info))
+        else:  # pinned / pageable host torch tensor
+            st = lib.lsd_lio_scan(self.h, _ptr(scan), scan.shape[0], _ptr(state), _ptr(P), C.byref(info))
+        check(st)
+        return state, P, dict(info.as_dict(), status=st)

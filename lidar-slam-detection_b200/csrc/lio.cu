@@ -1,0 +1,797 @@
+// lio.cu — LIO front-end hot path: fused k-NN + plane fit + point-to-plane residual/Jacobian (K3+K4)
+// with in-kernel J^T J / J^T r reduction (K5), degeneracy sums, map_incremental (K2), and the host
+// driver of the iterated ESKF.
+//
+// Replaces (reference: slam/mapping/fastlio/src/laserMapping.cpp):
+//   h_share_model_geometric :813-982   -> lio_hmodel_kernel (+ lio_degen_kernel for :934-980)
+//   esti_plane  include/common_lib.h:236-268 -> esti_plane_dev (Householder QR with column
+//                                          pivoting in fp32, as Eigen's ColPivHouseholderQR)
+//   map_incremental :523-576            -> lio_map_incremental_kernel
+//   fastlio_main per-scan body :1126-1387 -> lsd_lio_scan
+// Reduction layout: the reference materialises h_x (N_eff x 15 doubles) and forms h_x^T h_x on the
+// CPU (esekfom.hpp:1784).  Here every thread owns one Jacobian row in registers, the 21 unique
+// entries of the non-zero 6x6 block + 6 entries of h_x^T h + sum|res| + count are reduced by warp
+// shuffles, per-block partials go to HBM and the last block to finish folds them in a fixed order
+// (bit-reproducible).  No N x 15 matrix ever exists.
+#include "eskf.hpp"
+#include "knn.cuh"
+#include "lio.h"
+#include "map.h"
+#include "voxelgrid.h"
+
+namespace lsd {
+
+constexpr int kNV = 32;        // reduction slots per block (29 used + n)
+constexpr int kLioBlock = 128;
+
+struct LioPose { double R[9], t[3], RL[9], tL[3]; };
+
+// ---------------------------------------------------------------- esti_plane (common_lib.h:236-268)
+// A (5x3) n = -1 by Householder QR with column pivoting, fp32, same operation order as
+// oracle/lsd_oracle.c::orc_esti_plane (-fmad=false), so GPU and oracle agree bit for bit.
+__device__ __forceinline__ void swap_f(float& a, float& b) { float t = a; a = b; b = t; }
+__device__ __forceinline__ bool esti_plane_dev(const float (&px)[5], const float (&py)[5], const float (&pz)[5], float thr,
+                                               float (&pabcd)[4]) {
+  const float FEPS = 1.1920929e-07f;
+  float A[5][3], b[5];
+#pragma unroll
+  for (int r = 0; r < 5; r++) { A[r][0] = px[r]; A[r][1] = py[r]; A[r][2] = pz[r]; b[r] = -1.0f; }
+  float hc[3], nu[3], nd[3];
+  int perm[3] = {0, 1, 2};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 5; r++) s += A[r][k] * A[r][k];
+    nu[k] = nd[k] = sqrtf(s);
+  }
+  float mxn = nu[0];
+  if (nu[1] > mxn) mxn = nu[1];
+  if (nu[2] > mxn) mxn = nu[2];
+  const float th_helper = (mxn * FEPS) * (mxn * FEPS) / 5.0f;
+  const float downdate = sqrtf(FEPS);
+  int nonzero = 3;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    int big = k;
+    float bn = nu[k];
+#pragma unroll
+    for (int j = k + 1; j < 3; j++) if (nu[j] > bn) { bn = nu[j]; big = j; }
+    if (nonzero == 3 && bn * bn < th_helper * (float)(5 - k)) nonzero = k;
+#pragma unroll
+    for (int j = k + 1; j < 3; j++) {
+      if (big == j) {
+#pragma unroll
+        for (int r = 0; r < 5; r++) swap_f(A[r][k], A[r][j]);
+        swap_f(nu[k], nu[j]); swap_f(nd[k], nd[j]);
+        int ti = perm[k]; perm[k] = perm[j]; perm[j] = ti;
+      }
+    }
+    float tail = 0.f;
+#pragma unroll
+    for (int r = k + 1; r < 5; r++) tail += A[r][k] * A[r][k];
+    const float c0 = A[k][k];
+    float beta, tau;
+    if (tail <= 1.17549435e-38f) {
+      tau = 0.f; beta = c0;
+#pragma unroll
+      for (int r = k + 1; r < 5; r++) A[r][k] = 0.f;
+    } else {
+      beta = sqrtf(c0 * c0 + tail);
+      if (c0 >= 0.f) beta = -beta;
+      const float den = c0 - beta;
+#pragma unroll
+      for (int r = k + 1; r < 5; r++) A[r][k] = A[r][k] / den;
+      tau = (beta - c0) / beta;
+    }
+    hc[k] = tau; A[k][k] = beta;
+    if (tau != 0.f) {
+#pragma unroll
+      for (int j = k + 1; j < 3; j++) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int r = k + 1; r < 5; r++) tmp += A[r][k] * A[r][j];
+        tmp += A[k][j];
+        A[k][j] -= tau * tmp;
+#pragma unroll
+        for (int r = k + 1; r < 5; r++) A[r][j] -= tau * A[r][k] * tmp;
+      }
+    }
+#pragma unroll
+    for (int j = k + 1; j < 3; j++) {
+      if (nu[j] != 0.f) {
+        float t = fabsf(A[k][j]) / nu[j];
+        t = (1.f + t) * (1.f - t);
+        if (t < 0.f) t = 0.f;
+        const float rr = nu[j] / nd[j];
+        const float t2 = t * rr * rr;
+        if (t2 <= downdate) {
+          float s = 0.f;
+#pragma unroll
+          for (int r = k + 1; r < 5; r++) s += A[r][j] * A[r][j];
+          nd[j] = sqrtf(s); nu[j] = nd[j];
+        } else {
+          nu[j] *= sqrtf(t);
+        }
+      }
+    }
+  }
+  float x[3] = {0.f, 0.f, 0.f};
+  if (nonzero > 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (k < nonzero && hc[k] != 0.f) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int r = k + 1; r < 5; r++) tmp += A[r][k] * b[r];
+        tmp += b[k];
+        b[k] -= hc[k] * tmp;
+#pragma unroll
+        for (int r = k + 1; r < 5; r++) b[r] -= hc[k] * A[r][k] * tmp;
+      }
+    }
+    float c[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 2; i >= 0; i--) {
+      if (i < nonzero) {
+        float s = b[i];
+#pragma unroll
+        for (int j = i + 1; j < 3; j++) if (j < nonzero) s -= A[i][j] * c[j];
+        c[i] = s / A[i][i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (i < nonzero) {
+        if (perm[i] == 0) x[0] = c[i]; else if (perm[i] == 1) x[1] = c[i]; else x[2] = c[i];
+      }
+    }
+  }
+  const float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  pabcd[0] = x[0] / n; pabcd[1] = x[1] / n; pabcd[2] = x[2] / n; pabcd[3] = (float)(1.0 / (double)n);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const float v = pabcd[0] * px[j] + pabcd[1] * py[j] + pabcd[2] * pz[j] + pabcd[3];
+    if (fabs((double)v) > (double)thr) ok = false;
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------- block / grid reduction
+// vals[NV] per thread -> partials[block][kNV]; the last block folds all partials in a fixed order.
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&vals)[NV], double* __restrict__ partials, unsigned* __restrict__ done,
+                                            double* __restrict__ result, int n_extra, double extra) {
+  __shared__ double sm[kLioBlock / 32][kNV];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const double v = warp_sum(vals[j]);
+    if (lane == 0) sm[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLioBlock / 32; w++) s += sm[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * kNV + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(done, 1u);
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // 4 slices x 32 value lanes, each slice walks its blocks in ascending order
+  const int j = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  double s = 0.0;
+  if (j < NV)
+    for (int b = slice; b < (int)gridDim.x; b += kLioBlock / 32) s += __ldcg(partials + (size_t)b * kNV + j);
+  __syncthreads();
+  sm[slice][j] = s;
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLioBlock / 32; w++) t += sm[w][threadIdx.x];
+    result[threadIdx.x] = t;
+  }
+  if (threadIdx.x == 0) {
+    result[n_extra] = extra;
+    *done = 0u;
+  }
+}
+
+// ---------------------------------------------------------------- K3+K4+K5: one h-model evaluation
+template <bool SEARCH>
+__global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(MapView mv, int stencil, const float4* __restrict__ body,
+                                                               const int* __restrict__ n_ptr, int cap, LioPose ps,
+                                                               float4* __restrict__ near, int* __restrict__ near_cnt,
+                                                               unsigned char* __restrict__ selected,
+                                                               float4* __restrict__ plane, float4* __restrict__ world,
+                                                               double* __restrict__ partials, unsigned* __restrict__ done,
+                                                               double* __restrict__ result) {
+  const int n_true = *n_ptr;
+  const int n = min(n_true, cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double vals[29];
+#pragma unroll
+  for (int j = 0; j < 29; j++) vals[j] = 0.0;
+  if (i < n) {
+    const float4 pb = __ldg(body + i);
+    // body -> world in double (laserMapping.cpp:831-836), stored as fp32 like PointType
+    const double bx = pb.x, by = pb.y, bz = pb.z;
+    const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+    const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+    const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+    const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
+    const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
+    const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+    world[i] = make_float4(wx, wy, wz, pb.w);
+    float px[5], py[5], pz[5];
+    bool sel;
+    if (SEARCH) {
+      TopK<5> tk;
+      knn_search<5>(mv, stencil, wx, wy, wz, 5.0f, tk);
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (j < tk.n) q = load_loc(mv, tk.loc[j]);
+        px[j] = q.x; py[j] = q.y; pz[j] = q.z;
+        near[(size_t)i * 5 + j] = q;
+      }
+      near_cnt[i] = tk.n;
+      sel = tk.n >= 5;  // laserMapping.cpp:847,850
+    } else {
+      sel = selected[i] != 0;
+      if (sel) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) { const float4 q = near[(size_t)i * 5 + j]; px[j] = q.x; py[j] = q.y; pz[j] = q.z; }
+      }
+    }
+    bool keep = false;
+    if (sel) {
+      float pabcd[4];
+      if (esti_plane_dev(px, py, pz, 0.1f, pabcd)) {
+        const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];
+        const double s = 1 - 0.9 * fabs((double)pd2) / sqrt(sqrt(bx * bx + by * by + bz * bz));  // :861
+        if ((float)s > 0.9) {
+          keep = true;
+          plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
+          // Jacobian row (laserMapping.cpp:903-932, extrinsic_est_en == false)
+          const double nx = pabcd[0], ny = pabcd[1], nz = pabcd[2];
+          const double cx = ps.R[0] * nx + ps.R[3] * ny + ps.R[6] * nz;  // R^T n
+          const double cy = ps.R[1] * nx + ps.R[4] * ny + ps.R[7] * nz;
+          const double cz = ps.R[2] * nx + ps.R[5] * ny + ps.R[8] * nz;
+          const double row[6] = {nx, ny, nz, ly * cz - lz * cy, lz * cx - lx * cz, lx * cy - ly * cx};
+          const double h = -(double)pd2;
+          int q = 0;
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+#pragma unroll
+            for (int c = a; c < 6; c++) vals[q++] = row[a] * row[c];
+          }
+#pragma unroll
+          for (int a = 0; a < 6; a++) vals[21 + a] = row[a] * h;
+          vals[27] = (double)fabsf(pd2);  // res_last
+          vals[28] = 1.0;
+        }
+      }
+    }
+    selected[i] = keep ? 1 : 0;
+  }
+  grid_reduce<29>(vals, partials, done, result, 29, (double)n_true);
+}
+
+// ---------------------------------------------------------------- degeneracy sums (laserMapping.cpp:946-970)
+struct Eig3 { double V[9]; };  // columns = eigenvectors
+__global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restrict__ n_ptr, int cap, const unsigned char* __restrict__ selected,
+                                                              const float4* __restrict__ plane, Eig3 e,
+                                                              double* __restrict__ partials, unsigned* __restrict__ done,
+                                                              double* __restrict__ result) {
+  const int n = min(*n_ptr, cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double vals[6] = {0, 0, 0, 0, 0, 0};
+  if (i < n && selected[i]) {
+    const float4 p = plane[i];
+    const double r0 = p.x, r1 = p.y, r2 = p.z;
+    const double nn = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float dotp = (float)fabs((r0 / nn) * e.V[k] + (r1 / nn) * e.V[3 + k] + (r2 / nn) * e.V[6 + k]);
+      if (dotp > 0.1736) vals[k] = dotp;
+      if (dotp > 0.7070) vals[3 + k] = dotp;
+    }
+  }
+  grid_reduce<6>(vals, partials, done, result, 6, 0.0);
+}
+
+// ---------------------------------------------------------------- map_incremental (laserMapping.cpp:523-576)
+__device__ __forceinline__ float calc_dist3(float ax, float ay, float az, float bx, float by, float bz) {
+  return (ax - bx) * (ax - bx) + (ay - by) * (ay - by) + (az - bz) * (az - bz);
+}
+__global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, const float4* __restrict__ body,
+                                                                  const int* __restrict__ n_ptr, int cap, LioPose ps,
+                                                                  const float4* __restrict__ near, const int* __restrict__ near_cnt,
+                                                                  int ekf_inited, double fsize, int id0, int use_near,
+                                                                  float4* __restrict__ world, unsigned char* __restrict__ flags,
+                                                                  unsigned* __restrict__ n_added) {
+  const int n = min(*n_ptr, cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 pb = __ldg(body + i);
+  const double bx = pb.x, by = pb.y, bz = pb.z;
+  const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+  const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+  const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+  const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
+  const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
+  const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+  world[i] = make_float4(wx, wy, wz, pb.w);
+  int f = 1;  // PointToAdd
+  const int cnt = use_near ? near_cnt[i] : 0;
+  if (cnt > 0 && ekf_inited) {
+    const float mx = (float)(floor((double)wx / fsize) * fsize + 0.5 * fsize);
+    const float my = (float)(floor((double)wy / fsize) * fsize + 0.5 * fsize);
+    const float mz = (float)(floor((double)wz / fsize) * fsize + 0.5 * fsize);
+    const float dist = calc_dist3(wx, wy, wz, mx, my, mz);
+    const float4 n0 = near[(size_t)i * 5];
+    if ((double)fabsf(n0.x - mx) > 0.5 * fsize && (double)fabsf(n0.y - my) > 0.5 * fsize && (double)fabsf(n0.z - mz) > 0.5 * fsize) {
+      f = 2;  // PointNoNeedDownsample
+    } else if (cnt >= 5) {
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        const float4 q = near[(size_t)i * 5 + r];
+        if (calc_dist3(q.x, q.y, q.z, mx, my, mz) < dist) f = 0;
+      }
+    }
+  }
+  flags[i] = (unsigned char)f;
+  if (f) {
+    map_insert_point(mv, wx, wy, wz, id0 + i);
+    atomicAdd(n_added, 1u);
+  }
+}
+
+__global__ void lio_fill_u8_kernel(unsigned char* p, int n, unsigned char v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void lio_set_int_kernel(int* p, int v) { *p = v; }
+
+// ---------------------------------------------------------------- host side
+static void pose_from_state(const double* x, LioPose* ps) {
+  eskf::q2R(x + eskf::S_ROT, ps->R);
+  eskf::q2R(x + eskf::S_OFFR, ps->RL);
+  for (int i = 0; i < 3; i++) { ps->t[i] = x[eskf::S_POS + i]; ps->tL[i] = x[eskf::S_OFFT + i]; }
+}
+
+// symmetric 3x3 eigen-decomposition (cyclic Jacobi); V columns = eigenvectors.  Stands in for
+// Eigen::SelfAdjointEigenSolver at laserMapping.cpp:941; only |v . n| and V diag(mask) V^T are used.
+static void eig3_sym(const double* Ain, double* V) {
+  double A[9];
+  memcpy(A, Ain, sizeof(A));
+  for (int i = 0; i < 9; i++) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    if (fabs(A[1]) + fabs(A[2]) + fabs(A[5]) < 1e-300) break;
+    for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+      const double apq = A[3 * p + q];
+      if (fabs(apq) < 1e-300) continue;
+      const double th = (A[3 * q + q] - A[3 * p + p]) / (2.0 * apq);
+      const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      for (int k = 0; k < 3; k++) { double a = A[3 * k + p], b = A[3 * k + q]; A[3 * k + p] = c * a - s * b; A[3 * k + q] = s * a + c * b; }
+      for (int k = 0; k < 3; k++) { double a = A[3 * p + k], b = A[3 * q + k]; A[3 * p + k] = c * a - s * b; A[3 * q + k] = s * a + c * b; }
+      for (int k = 0; k < 3; k++) { double a = V[3 * k + p], b = V[3 * k + q]; V[3 * k + p] = c * a - s * b; V[3 * k + q] = s * a + c * b; }
+    }
+  }
+}
+
+static int grid_for(int n) { return std::max(1, (n + kLioBlock - 1) / kLioBlock); }
+
+// One h_share_model_geometric evaluation on the loaded scan.  Fills HTH6/HTh6 (after the
+// degeneracy projection when it triggers).
+lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH6, double* HTh6, double* res_sum,
+                           int* n_eff, int* degenerate) {
+  LioPose ps;
+  pose_from_state(x, &ps);
+  cudaStream_t st = l->stream;
+  const int nb = grid_for(l->n_bound);
+  const int stencil = l->p.knn_mode_exact ? LSD_STENCIL_EXACT : l->p.ivox_nearby;
+  if (search)
+    lio_hmodel_kernel<true><<<nb, kLioBlock, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                                                      l->d_selected, l->d_plane, l->d_world, l->d_partials, l->d_done, l->d_result);
+  else
+    lio_hmodel_kernel<false><<<nb, kLioBlock, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                                                       l->d_selected, l->d_plane, l->d_world, l->d_partials, l->d_done, l->d_result);
+  LSD_CUDA(cudaGetLastError());
+  l->launches++;
+  LSD_CUDA(cudaMemcpyAsync(l->h_result, l->d_result, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaStreamSynchronize(st));
+  const double* r = l->h_result;
+  int q = 0;
+  for (int a = 0; a < 6; a++) for (int c = a; c < 6; c++) { HTH6[6 * a + c] = HTH6[6 * c + a] = r[q]; q++; }
+  for (int a = 0; a < 6; a++) HTh6[a] = r[21 + a];
+  *res_sum = r[27];
+  *n_eff = (int)(r[28] + 0.5);
+  l->n_down = (int)(r[29] + 0.5);
+  if (l->n_down > l->p.max_points) { set_error("downsampled scan of %d points exceeds max_points %d", l->n_down, l->p.max_points); return LSD_ERR_CAPACITY; }
+  l->n_bound = std::max(l->n_down, 1);  // later launches cover exactly the downsampled scan
+  *degenerate = 0;
+  if (*n_eff < 1) return LSD_NO_EFFECTIVE_POINTS;
+  if (l->p.degenerate_detect_en) {
+    double H3[9], V[9];
+    for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) H3[3 * a + c] = HTH6[6 * a + c];
+    Eig3 e;
+    eig3_sym(H3, V);
+    memcpy(e.V, V, sizeof(V));
+    lio_degen_kernel<<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_n, l->p.max_points, l->d_selected, l->d_plane, e, l->d_partials, l->d_done, l->d_result2);
+    LSD_CUDA(cudaGetLastError());
+    l->launches++;
+    LSD_CUDA(cudaMemcpyAsync(l->h_result2, l->d_result2, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LSD_CUDA(cudaStreamSynchronize(st));
+    int mask[3] = {1, 1, 1};
+    bool deg = false;
+    for (int k = 0; k < 3; k++)
+      if ((float)l->h_result2[k] < 250.0f && (float)l->h_result2[3 + k] < 50.0f) { mask[k] = 0; deg = true; }
+    if (deg) {
+      // rows n -> Pm n with Pm = V diag(mask) V^T  (mat_p, laserMapping.cpp:975-978):
+      // HTH <- B HTH B^T, HTh <- B HTh with B = blockdiag(Pm, I3)
+      double Pm[9] = {0};
+      for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) if (mask[k]) Pm[3 * a + c] += V[3 * a + k] * V[3 * c + k];
+      double B[36] = {0}, T[36];
+      for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) B[6 * a + c] = Pm[3 * a + c];
+      for (int a = 3; a < 6; a++) B[6 * a + a] = 1.0;
+      for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { double s = 0; for (int k = 0; k < 6; k++) s += B[6 * a + k] * HTH6[6 * k + c]; T[6 * a + c] = s; }
+      for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { double s = 0; for (int k = 0; k < 6; k++) s += T[6 * a + k] * B[6 * c + k]; HTH6[6 * a + c] = s; }
+      double h2[6];
+      for (int a = 0; a < 6; a++) { double s = 0; for (int k = 0; k < 6; k++) s += B[6 * a + k] * HTh6[k]; h2[a] = s; }
+      memcpy(HTh6, h2, sizeof(h2));
+      memcpy(l->last_Pm, Pm, sizeof(Pm));
+      *degenerate = 1;
+    }
+  }
+  return LSD_OK;
+}
+
+// Rows of h_x for the rare n_eff < 23 branch of the filter (esekfom.hpp:1727): rebuilt on the host
+// from the per-point taps.
+static lsd_status_t fetch_rows(lsd_lio* l, const double* x, bool degenerate, std::vector<double>* h_x, std::vector<double>* h) {
+  const int n = l->n_down;
+  std::vector<float4> body(n), plane(n);
+  std::vector<unsigned char> sel(n);
+  LSD_CUDA(cudaMemcpyAsync(body.data(), l->d_body, (size_t)n * 16, cudaMemcpyDeviceToHost, l->stream));
+  LSD_CUDA(cudaMemcpyAsync(plane.data(), l->d_plane, (size_t)n * 16, cudaMemcpyDeviceToHost, l->stream));
+  LSD_CUDA(cudaMemcpyAsync(sel.data(), l->d_selected, (size_t)n, cudaMemcpyDeviceToHost, l->stream));
+  LSD_CUDA(cudaStreamSynchronize(l->stream));
+  LioPose ps;
+  pose_from_state(x, &ps);
+  h_x->clear(); h->clear();
+  for (int i = 0; i < n; i++) {
+    if (!sel[i]) continue;
+    const double bx = body[i].x, by = body[i].y, bz = body[i].z;
+    const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+    const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+    const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+    double nv[3] = {plane[i].x, plane[i].y, plane[i].z};
+    const double cx = ps.R[0] * nv[0] + ps.R[3] * nv[1] + ps.R[6] * nv[2];
+    const double cy = ps.R[1] * nv[0] + ps.R[4] * nv[1] + ps.R[7] * nv[2];
+    const double cz = ps.R[2] * nv[0] + ps.R[5] * nv[1] + ps.R[8] * nv[2];
+    if (degenerate) { double o[3]; eskf::mv3(l->last_Pm, nv, o); nv[0] = o[0]; nv[1] = o[1]; nv[2] = o[2]; }
+    double row[15] = {nv[0], nv[1], nv[2], ly * cz - lz * cy, lz * cx - lx * cz, lx * cy - ly * cx, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    h_x->insert(h_x->end(), row, row + 15);
+    h->push_back(-(double)plane[i].w);
+  }
+  return LSD_OK;
+}
+
+lsd_status_t lio_update(lsd_lio* l, double* x, double* P, lsd_lio_info_t* info) {
+  lsd_status_t err = LSD_OK;
+  int last_neff = 0, last_deg = 0;
+  double last_res = 0.0;
+  auto hm = [&](const double* xs, bool converge, eskf::HModel* out) {
+    double HTH6[36], HTh6[6], rs;
+    int ne, dg;
+    lsd_status_t s = lio_linearize(l, xs, converge, HTH6, HTh6, &rs, &ne, &dg);
+    if (s < 0) { err = s; out->valid = false; return; }
+    if (l->n_down < 5) { out->valid = false; return; }  // laserMapping.cpp:1252-1256: scan skipped, state untouched
+    last_neff = ne; last_deg = dg; last_res = ne > 0 ? rs / ne : 0.0;
+    out->valid = ne >= 1;
+    out->n = ne;
+    if (!out->valid) return;
+    memset(out->HTH, 0, sizeof(out->HTH)); memset(out->HTh, 0, sizeof(out->HTh));
+    for (int a = 0; a < 6; a++) { for (int c = 0; c < 6; c++) out->HTH[15 * a + c] = HTH6[6 * a + c]; out->HTh[a] = HTh6[a]; }
+    if (ne < eskf::N) { lsd_status_t f = fetch_rows(l, xs, dg != 0, &out->h_x, &out->h); if (f < 0) { err = f; out->valid = false; } }
+  };
+  eskf::UpdateResult r = eskf::update_iterated(x, P, hm, l->p.laser_point_cov, l->p.max_iterations, l->p.converge_eps);
+  if (info) {
+    info->iterations = r.evaluations; info->n_eff = last_neff; info->degenerate = last_deg; info->res_mean = last_res;
+    info->converged = r.returned_converged ? 1 : 0; info->n_down = l->n_down;
+  }
+  if (err < 0) return err;
+  return last_neff >= 1 ? LSD_OK : LSD_NO_EFFECTIVE_POINTS;
+}
+
+lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int* n_added) {
+  LioPose ps;
+  pose_from_state(x, &ps);
+  cudaStream_t st = l->stream;
+  LSD_CUDA(cudaMemsetAsync(l->d_added, 0, sizeof(unsigned), st));
+  const int nb = std::max(1, (l->n_bound + 255) / 256);
+  lio_map_incremental_kernel<<<nb, 256, 0, st>>>(l->map->view, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt, l->ekf_inited,
+                                                 (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added);
+  LSD_CUDA(cudaGetLastError());
+  l->launches++;
+  unsigned h = 0;
+  LSD_CUDA(cudaMemcpyAsync(&h, l->d_added, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaStreamSynchronize(st));
+  l->next_id += l->n_bound;
+  if (n_added) *n_added = (int)h;
+  return LSD_OK;
+}
+
+lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
+  cudaStream_t st = l->stream;
+  if (n < 0 || n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
+  if (downsample) {
+    lsd_status_t s = vg_run(l->vg, d_scan, n, l->p.filter_size_surf, l->d_body, l->d_n, st);
+    if (s) return s;
+    l->launches += 7;
+    l->n_bound = std::min(n, l->p.max_points);
+    l->n_down = -1;  // learned with the first reduction (or lsd_lio_load_scan's explicit read)
+  } else {
+    if (n > l->p.max_points) { set_error("scan of %d points exceeds max_points %d", n, l->p.max_points); return LSD_ERR_CAPACITY; }
+    LSD_CUDA(cudaMemcpyAsync(l->d_body, d_scan, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+    lio_set_int_kernel<<<1, 1, 0, st>>>(l->d_n, n);
+    l->launches++;
+    l->n_bound = std::max(n, 1);
+    l->n_down = n;
+  }
+  return LSD_OK;
+}
+
+static lsd_status_t read_n_down(lsd_lio* l) {
+  int h = 0;
+  LSD_CUDA(cudaMemcpyAsync(&h, l->d_n, sizeof(int), cudaMemcpyDeviceToHost, l->stream));
+  LSD_CUDA(cudaStreamSynchronize(l->stream));
+  if (h > l->p.max_points) { set_error("downsampled scan of %d points exceeds max_points %d", h, l->p.max_points); return LSD_ERR_CAPACITY; }
+  l->n_down = h;
+  l->n_bound = std::max(h, 1);
+  return LSD_OK;
+}
+
+lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double* P, lsd_lio_info_t* info) {
+  cudaStream_t st = l->stream;
+  const long long launches0 = l->launches;
+  LSD_CUDA(cudaEventRecord(l->ev0, st));
+  lsd_status_t s = lio_load(l, d_scan, n, 1);
+  if (s) return s;
+  lsd_lio_info_t inf;
+  memset(&inf, 0, sizeof(inf));
+  lsd_status_t ret = LSD_OK;
+  uint64_t cells = l->map_cells_known;
+  if (cells == 0) { s = lsd_map_stats(l->map, &cells, nullptr, nullptr); if (s) return s; l->map_cells_known = cells; }
+  if (cells == 0) {  // first scan seeds the map (laserMapping.cpp:1227-1239)
+    s = read_n_down(l);
+    if (s) return s;
+    inf.n_down = l->n_down;
+    if (l->n_down > 5) { s = lio_map_incremental(l, x, 0, &inf.n_added); if (s) return s; l->map_cells_known = 1; }
+    ret = LSD_MAP_SEEDED;
+  } else {
+    s = lio_update(l, x, P, &inf);
+    if (s < 0) return s;
+    if (l->n_down < 5) ret = LSD_SCAN_TOO_SMALL;  // laserMapping.cpp:1252-1256 (state untouched: n_eff == 0)
+    else {
+      ret = s;
+      lsd_status_t m = lio_map_incremental(l, x, 1, &inf.n_added);
+      if (m) return m;
+    }
+  }
+  LSD_CUDA(cudaEventRecord(l->ev1, st));
+  LSD_CUDA(cudaEventSynchronize(l->ev1));
+  float ms = 0.f;
+  LSD_CUDA(cudaEventElapsedTime(&ms, l->ev0, l->ev1));
+  inf.gpu_ms = ms;
+  inf.kernel_launches = (int)(l->launches - launches0);
+  if (info) *info = inf;
+  return ret;
+}
+
+}  // namespace lsd
+
+using namespace lsd;
+
+extern "C" {
+
+void lsd_lio_default_params(lsd_lio_params_t* p) {
+  if (!p) return;
+  p->max_points = 100000;        // laserMapping.cpp:86,103
+  p->max_scan_points = 400000;
+  p->filter_size_surf = 0.5f;    // laserMapping.cpp:1027
+  p->filter_size_map = 0.5f;     // laserMapping.cpp:1028
+  p->ivox_resolution = 0.5f;     // laserMapping.cpp:1061
+  p->ivox_nearby = LSD_STENCIL_NEARBY18;
+  p->map_log2_lines = 22;
+  p->max_iterations = 4;         // laserMapping.cpp:1026
+  p->laser_point_cov = 0.001;    // laserMapping.cpp:71
+  p->converge_eps = 0.001;       // laserMapping.cpp:1114-1116
+  p->degenerate_detect_en = 1;   // laserMapping.cpp:83
+  p->knn_mode_exact = 0;
+}
+
+lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
+  if (!out || !p || p->max_points <= 0 || p->max_scan_points < p->max_points) { set_error("lsd_lio_create: bad params"); return LSD_ERR_INVALID; }
+  lsd_status_t s = ensure_device();
+  if (s) return s;
+  lsd_lio* l = new lsd_lio();
+  l->p = *p;
+  cudaGetDevice(&l->device);
+  s = lsd_map_create(&l->map, p->ivox_resolution, p->map_log2_lines);
+  if (s) { delete l; return s; }
+  s = lsd_voxelgrid_create(&l->vg, p->max_scan_points, 28);
+  if (s) { lsd_map_destroy(l->map); delete l; return s; }
+  const size_t mp = (size_t)p->max_points;
+  const size_t max_blocks = (size_t)grid_for(p->max_points) + 1;
+  cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);
+  auto A = [&](void** ptr, size_t b) { if (e == cudaSuccess) e = cudaMalloc(ptr, b); if (e == cudaSuccess) e = cudaMemset(*ptr, 0, b); };
+  A((void**)&l->d_scan, (size_t)p->max_scan_points * 16);
+  A((void**)&l->d_body, (size_t)p->max_scan_points * 16);  // voxel-grid output may equal the input size
+  A((void**)&l->d_n, 64);
+  A((void**)&l->d_near, mp * 5 * 16);
+  A((void**)&l->d_near_cnt, mp * 4);
+  A((void**)&l->d_selected, mp);
+  A((void**)&l->d_flags, mp);
+  A((void**)&l->d_plane, mp * 16);
+  A((void**)&l->d_world, mp * 16);
+  A((void**)&l->d_partials, max_blocks * kNV * 8);
+  A((void**)&l->d_done, 64);
+  A((void**)&l->d_added, 64);
+  A((void**)&l->d_result, 64 * 8);
+  A((void**)&l->d_result2, 64 * 8);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_result, 64 * 8);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_result2, 64 * 8);
+  if (e == cudaSuccess) e = cudaEventCreate(&l->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&l->ev1);
+  if (e == cudaSuccess) {  // memset(point_selected_surf, true), laserMapping.cpp:1089
+    lio_fill_u8_kernel<<<(int)((mp + 255) / 256), 256, 0, l->stream>>>(l->d_selected, (int)mp, 1);
+    e = cudaStreamSynchronize(l->stream);
+  }
+  if (e != cudaSuccess) { lsd_status_t r = cuda_fail(e, "lsd_lio_create", __FILE__, __LINE__); lsd_lio_destroy(l); return r; }
+  // the map and the voxel grid run on the LIO stream
+  cudaStreamDestroy(l->map->stream); l->map->stream = l->stream;
+  cudaStreamDestroy(l->vg->stream); l->vg->stream = l->stream;
+  *out = l;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
+  if (!l) return LSD_OK;
+  cudaSetDevice(l->device);
+  if (l->stream) cudaStreamSynchronize(l->stream);
+  void* ptrs[] = {l->d_scan, l->d_body, l->d_n, l->d_near, l->d_near_cnt, l->d_selected, l->d_flags, l->d_plane, l->d_world,
+                  l->d_partials, l->d_done, l->d_added, l->d_result, l->d_result2};
+  for (void* p : ptrs) cudaFree(p);
+  cudaFreeHost(l->h_result); cudaFreeHost(l->h_result2);
+  if (l->ev0) cudaEventDestroy(l->ev0);
+  if (l->ev1) cudaEventDestroy(l->ev1);
+  cudaStream_t own = l->stream;
+  if (l->map) { if (l->map->stream == own) l->map->stream = nullptr; lsd_map_destroy(l->map); }
+  if (l->vg) { if (l->vg->stream == own) l->vg->stream = nullptr; lsd_voxelgrid_destroy(l->vg); }
+  if (own) cudaStreamDestroy(own);
+  delete l;
+  return LSD_OK;
+}
+
+lsd_map_t* lsd_lio_map(lsd_lio_t* l) { return l ? l->map : nullptr; }
+
+lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil) {
+  if (!l || (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0)) return LSD_ERR_INVALID;
+  l->p.ivox_nearby = stencil;
+  return LSD_OK;
+}
+lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id) { if (!l) return LSD_ERR_INVALID; l->next_id = id; l->map_cells_known = 0; return LSD_OK; }
+lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag) { if (!l) return LSD_ERR_INVALID; l->ekf_inited = flag ? 1 : 0; return LSD_OK; }
+
+lsd_status_t lsd_lio_load_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, int downsample, int* n_down) {
+  if (!l || (n > 0 && !scan_dev)) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  lsd_status_t s = lio_load(l, reinterpret_cast<const float4*>(scan_dev), n, downsample);
+  if (s) return s;
+  s = read_n_down(l);
+  if (s) return s;
+  if (n_down) *n_down = l->n_down;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_lio_load_scan(lsd_lio_t* l, const float* scan_host, int n, int downsample, int* n_down) {
+  if (!l || (n > 0 && !scan_host)) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
+  LSD_CUDA(cudaMemcpyAsync(l->d_scan, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
+  return lsd_lio_load_scan_dev(l, reinterpret_cast<const float*>(l->d_scan), n, downsample, n_down);
+}
+
+lsd_status_t lsd_lio_get_down(lsd_lio_t* l, float* out_host, int cap, int* n_down) {
+  if (!l || !out_host) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  if (l->n_down < 0) { lsd_status_t s = read_n_down(l); if (s) return s; }
+  if (n_down) *n_down = l->n_down;
+  const int c = std::min(cap, l->n_down);
+  if (c > 0) LSD_CUDA(cudaMemcpyAsync(out_host, l->d_body, (size_t)c * 16, cudaMemcpyDeviceToHost, l->stream));
+  LSD_CUDA(cudaStreamSynchronize(l->stream));
+  return LSD_OK;
+}
+
+lsd_status_t lsd_lio_linearize(lsd_lio_t* l, const double* state26, int search, double* HTH36, double* HTh6, double* res_sum,
+                               int* n_eff, int* degenerate) {
+  if (!l || !state26 || !HTH36 || !HTh6 || !res_sum || !n_eff || !degenerate) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  return lio_linearize(l, state26, search != 0, HTH36, HTh6, res_sum, n_eff, degenerate);
+}
+
+lsd_status_t lsd_lio_get_matches(lsd_lio_t* l, int32_t* near_idx, float* near_xyz, int32_t* near_cnt, uint8_t* selected,
+                                 float* plane, float* world) {
+  if (!l || l->n_down < 0) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  const int n = l->n_down;
+  cudaStream_t st = l->stream;
+  std::vector<float4> nr;
+  if (near_idx || near_xyz) { nr.resize((size_t)n * 5); LSD_CUDA(cudaMemcpyAsync(nr.data(), l->d_near, (size_t)n * 80, cudaMemcpyDeviceToHost, st)); }
+  if (near_cnt) LSD_CUDA(cudaMemcpyAsync(near_cnt, l->d_near_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (selected) LSD_CUDA(cudaMemcpyAsync(selected, l->d_selected, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (plane) LSD_CUDA(cudaMemcpyAsync(plane, l->d_plane, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  if (world) LSD_CUDA(cudaMemcpyAsync(world, l->d_world, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < nr.size(); i++) {
+    if (near_idx) memcpy(&near_idx[i], &nr[i].w, 4);
+    if (near_xyz) { near_xyz[3 * i] = nr[i].x; near_xyz[3 * i + 1] = nr[i].y; near_xyz[3 * i + 2] = nr[i].z; }
+  }
+  return LSD_OK;
+}
+
+lsd_status_t lsd_lio_update(lsd_lio_t* l, double* state26_inout, double* P529_inout, lsd_lio_info_t* info) {
+  if (!l || !state26_inout || !P529_inout) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  lsd_lio_info_t inf;
+  memset(&inf, 0, sizeof(inf));
+  const long long l0 = l->launches;
+  lsd_status_t s = lio_update(l, state26_inout, P529_inout, &inf);
+  inf.kernel_launches = (int)(l->launches - l0);
+  if (info) *info = inf;
+  return s;
+}
+
+lsd_status_t lsd_lio_map_incremental(lsd_lio_t* l, const double* state26, int* n_added) {
+  if (!l || !state26) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  lsd_status_t s = lio_map_incremental(l, state26, 1, n_added);
+  if (s == LSD_OK) l->map_cells_known = 1;
+  return s;
+}
+
+lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double* state26_inout, double* P529_inout,
+                              lsd_lio_info_t* info) {
+  if (!l || (n > 0 && !scan_dev) || !state26_inout || !P529_inout) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  return lio_scan(l, reinterpret_cast<const float4*>(scan_dev), n, state26_inout, P529_inout, info);
+}
+
+lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* state26_inout, double* P529_inout,
+                          lsd_lio_info_t* info) {
+  if (!l || (n > 0 && !scan_host) || !state26_inout || !P529_inout) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
+  LSD_CUDA(cudaMemcpyAsync(l->d_scan, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
+  return lio_scan(l, l->d_scan, n, state26_inout, P529_inout, info);
+}
+
+void lsd_lio_init_cov(double* P529) { if (P529) eskf::init_cov(P529); }
+void lsd_state_boxplus(double* state26_inout, const double* delta23) { if (state26_inout && delta23) eskf::boxplus(state26_inout, delta23); }
+void lsd_state_boxminus(const double* a26, const double* b26, double* out23) { if (a26 && b26 && out23) eskf::boxminus(a26, b26, out23); }
+
+}  // extern "C"

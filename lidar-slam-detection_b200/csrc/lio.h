@@ -1,0 +1,38 @@
+// lio.h — host-side handle of the LIO front-end.
+#pragma once
+#include <vector>
+
+#include "lsd_common.cuh"
+
+struct lsd_map;
+struct lsd_voxelgrid;
+
+struct lsd_lio {
+  lsd_lio_params_t p{};
+  int device = 0;
+  lsd_map* map = nullptr;       // hash-voxel map (iVox replacement), owned
+  lsd_voxelgrid* vg = nullptr;  // scan downsampler, owned
+  cudaStream_t stream = nullptr;
+  float4* d_scan = nullptr;     // raw scan staging (host-pointer entry points)
+  float4* d_body = nullptr;     // feats_down_body
+  int* d_n = nullptr;           // feats_down_size, device resident
+  float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)
+  int* d_near_cnt = nullptr;
+  unsigned char* d_selected = nullptr;  // point_selected_surf
+  unsigned char* d_flags = nullptr;     // map_incremental decision per point
+  float4* d_plane = nullptr;    // normvec: (normal, pd2)
+  float4* d_world = nullptr;    // feats_down_world
+  double* d_partials = nullptr;
+  unsigned* d_done = nullptr;
+  unsigned* d_added = nullptr;
+  double *d_result = nullptr, *d_result2 = nullptr;
+  double *h_result = nullptr, *h_result2 = nullptr;  // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int n_bound = 1;   // launch bound for per-point kernels (>= true feats_down_size)
+  int n_down = -1;   // feats_down_size once known on the host
+  int next_id = 0;   // id of the next inserted map point
+  int ekf_inited = 1;
+  long long launches = 0;
+  uint64_t map_cells_known = 0;
+  double last_Pm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+};

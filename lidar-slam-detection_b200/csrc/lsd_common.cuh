@@ -1,0 +1,86 @@
+// lsd_common.cuh — shared device/host helpers for liblsdreg (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/lsdreg.h"
+
+namespace lsd {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+lsd_status_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+lsd_status_t ensure_device();
+
+#define LSD_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) return lsd::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------ hash-voxel map layout
+// One 128-byte line per (voxel, level): header + 7 points.  A query resolves a voxel with ONE
+// 32-byte sector read (header + first point) and no pointer chase; sectors 1..3 hold points 1..6.
+// Level L > 0 lines hold points 7L .. 7L+6 of voxels with more than 7 points and are found by
+// hashing (cell, L) — no linked lists, so inserts never wait on each other.
+struct __align__(128) CellLine {
+  unsigned long long key;  // packed (level, x, y, z); 0 = empty
+  unsigned int count;      // level-0 line: total points in the voxel (all levels)
+  unsigned int pad;
+  float4 pts[7];           // (x, y, z, id as int bits)
+};
+static_assert(sizeof(CellLine) == 128, "CellLine must be one 128-byte line");
+
+constexpr int kPtsPerLine = 7;
+constexpr int kMaxLevel = 127;
+constexpr int kCoordBias = 1 << 18;  // voxel coordinates in (-2^18, 2^18)
+constexpr unsigned kMaxProbe = 4096;
+
+struct MapView {
+  CellLine* lines;
+  unsigned long long mask;  // n_lines - 1
+  float res, inv_res;
+  unsigned long long* counters;  // [0] cells, [1] points, [2] dropped
+};
+
+__host__ __device__ __forceinline__ bool coord_ok(int x, int y, int z) {
+  return x > -kCoordBias && x < kCoordBias && y > -kCoordBias && y < kCoordBias && z > -kCoordBias && z < kCoordBias;
+}
+__host__ __device__ __forceinline__ unsigned long long pack_key(int x, int y, int z, int level) {
+  return ((unsigned long long)level << 57) | ((unsigned long long)(x + kCoordBias) << 38) |
+         ((unsigned long long)(y + kCoordBias) << 19) | (unsigned long long)(z + kCoordBias);
+}
+__host__ __device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+
+// Pos2Grid (ivox3d.h:258-261): round-half-away-from-zero of p * inv_res, in fp32
+__device__ __forceinline__ int3 pos2grid(float x, float y, float z, float inv_res) {
+  return make_int3((int)roundf(x * inv_res), (int)roundf(y * inv_res), (int)roundf(z * inv_res));
+}
+
+// distance2 (ivox3d_node.hpp:11-14): (dx*dx + dy*dy) + dz*dz, fp32, no FMA (built with -fmad=false)
+__device__ __forceinline__ float dist2(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = bx - ax, dy = by - ay, dz = bz - az;
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 ldg_f4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// warp-level double sum
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ stencils (ivox3d.h:178-215)
+constexpr int kStencilMax = 75;
+struct Stencil { int n; signed char off[kStencilMax][3]; };
+const Stencil* host_stencil(int type);  // nullptr for EXACT / unknown
+
+}  // namespace lsd

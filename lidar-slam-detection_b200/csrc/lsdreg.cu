@@ -1,0 +1,5 @@
+// lsdreg.cu — unity translation unit of liblsdreg.so (device functions and __constant__ tables are
+// shared between kernels without relocatable device code).
+#include "map.cu"
+#include "voxelgrid.cu"
+#include "lio.cu"

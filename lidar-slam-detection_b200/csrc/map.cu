@@ -1,0 +1,290 @@
+// map.cu — hash-voxel map build/insert (K2) and batched k-NN query (K3) + their C ABI.
+//
+// Replaces faster_lio::IVox (reference: slam/mapping/fastlio/include/ivox3d/ivox3d.h):
+//   AddPoints :231-256  -> map_insert_kernel      (open addressing, 64-bit atomicCAS claim,
+//                                                  atomicAdd slot claim, float4 stores)
+//   GetClosestPoint :139-171 -> knn_query_kernel   (knn.cuh)
+// The LRU list of the reference (ivox3d.h:246-255) is not reproduced: the table is sized for the
+// whole map in HBM (180 GB) instead of evicting at 100 000 voxels.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "knn.cuh"
+#include "map.h"
+
+namespace lsd {
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+lsd_status_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+  bool nodev = e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice;
+  cudaGetLastError();
+  return nodev ? LSD_ERR_NO_DEVICE : LSD_ERR_CUDA;
+}
+static thread_local int g_device = 0;
+lsd_status_t ensure_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s): liblsdreg has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return LSD_ERR_NO_DEVICE;
+  }
+  LSD_CUDA(cudaSetDevice(g_device));
+  return LSD_OK;
+}
+
+// ------------------------------------------------------------------ stencil tables (ivox3d.h:178-215)
+static Stencil h_stencils[5];
+static std::once_flag g_stencil_once;
+static void build_stencils() {
+  static const signed char n18[19][3] = {{0,0,0},{-1,0,0},{1,0,0},{0,1,0},{0,-1,0},{0,0,-1},{0,0,1},{1,1,0},{-1,1,0},
+    {1,-1,0},{-1,-1,0},{1,0,1},{-1,0,1},{1,0,-1},{-1,0,-1},{0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1}};
+  memset(h_stencils, 0, sizeof(h_stencils));
+  h_stencils[0].n = 1;
+  h_stencils[1].n = 7; memcpy(h_stencils[1].off, n18, 7 * 3);
+  h_stencils[2].n = 19; memcpy(h_stencils[2].off, n18, 19 * 3);
+  for (int i = -1; i <= 1; i++) for (int j = -1; j <= 1; j++) for (int k = -1; k <= 1; k++) {
+    signed char* o = h_stencils[3].off[h_stencils[3].n++]; o[0] = i; o[1] = j; o[2] = k; }
+  for (int i = -2; i <= 2; i++) for (int j = -2; j <= 2; j++) for (int k = -1; k <= 1; k++) {
+    signed char* o = h_stencils[4].off[h_stencils[4].n++]; o[0] = i; o[1] = j; o[2] = k; }
+}
+const Stencil* host_stencil(int type) {
+  std::call_once(g_stencil_once, build_stencils);
+  int s = stencil_slot(type);
+  return s < 0 ? nullptr : &h_stencils[s];
+}
+lsd_status_t upload_stencils() {
+  std::call_once(g_stencil_once, build_stencils);
+  LSD_CUDA(cudaMemcpyToSymbol(c_stencils, h_stencils, sizeof(h_stencils)));
+  return LSD_OK;
+}
+
+// ------------------------------------------------------------------ K2: insert
+__device__ __forceinline__ long long find_or_claim(const MapView& mv, unsigned long long key, bool* fresh) {
+  unsigned long long s = hash_key(key) & mv.mask;
+  *fresh = false;
+  for (unsigned probe = 0; probe < kMaxProbe; probe++) {
+    unsigned long long* kp = &mv.lines[s].key;
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+    if (cur == key) return (long long)s;
+    if (cur == 0ull) {
+      unsigned long long old = atomicCAS(kp, 0ull, key);
+      if (old == 0ull) { *fresh = true; return (long long)s; }
+      if (old == key) return (long long)s;
+    }
+    s = (s + 1) & mv.mask;
+  }
+  return -1;
+}
+
+// Insert one point (device function shared with map_incremental in lio.cu).
+__device__ void map_insert_point(const MapView& mv, float x, float y, float z, int id) {
+  int3 c = pos2grid(x, y, z, mv.inv_res);
+  if (!coord_ok(c.x, c.y, c.z)) { atomicAdd(&mv.counters[2], 1ull); return; }
+  unsigned long long key0 = pack_key(c.x, c.y, c.z, 0);
+  bool fresh;
+  long long s = find_or_claim(mv, key0, &fresh);
+  if (s < 0) { atomicAdd(&mv.counters[2], 1ull); return; }
+  if (fresh) atomicAdd(&mv.counters[0], 1ull);
+  unsigned pos = atomicAdd(&mv.lines[s].count, 1u);
+  unsigned L = pos / kPtsPerLine, j = pos % kPtsPerLine;
+  if (L > 0) {
+    if (L > (unsigned)kMaxLevel) { atomicAdd(&mv.counters[2], 1ull); return; }
+    s = find_or_claim(mv, key0 | ((unsigned long long)L << 57), &fresh);
+    if (s < 0) { atomicAdd(&mv.counters[2], 1ull); return; }
+  }
+  mv.lines[s].pts[j] = make_float4(x, y, z, __int_as_float(id));
+  atomicAdd(&mv.counters[1], 1ull);
+}
+
+__global__ void __launch_bounds__(256) map_insert_kernel(MapView mv, const float4* __restrict__ pts, int n, int id0) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(pts + i);  // coalesced 16-byte loads
+  map_insert_point(mv, p.x, p.y, p.z, id0 + i);
+}
+
+// ------------------------------------------------------------------ K3: batched k-NN query
+template <int K>
+__global__ void __launch_bounds__(128) knn_query_kernel(MapView mv, const float4* __restrict__ q, int nq, float max_sq,
+                                                        int stencil, int* __restrict__ out_idx,
+                                                        float* __restrict__ out_d2, int* __restrict__ out_cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  float4 p = __ldg(q + i);
+  TopK<K> tk;
+  knn_search<K>(mv, stencil, p.x, p.y, p.z, max_sq, tk);
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    out_idx[(size_t)i * K + j] = j < tk.n ? tk.id[j] : -1;
+    out_d2[(size_t)i * K + j] = j < tk.n ? tk.d[j] : -1.0f;
+  }
+  out_cnt[i] = tk.n;
+}
+
+lsd_status_t launch_insert(lsd_map* m, const float4* d_pts, int n, int id0, cudaStream_t st) {
+  if (n <= 0) return LSD_OK;
+  map_insert_kernel<<<(n + 255) / 256, 256, 0, st>>>(m->view, d_pts, n, id0);
+  LSD_CUDA(cudaGetLastError());
+  m->launches++;
+  return LSD_OK;
+}
+
+lsd_status_t launch_knn(lsd_map* m, const float4* d_q, int nq, int k, float max_sq, int stencil, int* d_idx, float* d_d2,
+                        int* d_cnt, cudaStream_t st) {
+  if (nq <= 0) return LSD_OK;
+  if (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0) { set_error("unknown stencil %d", stencil); return LSD_ERR_INVALID; }
+  dim3 g((nq + 127) / 128), b(128);
+  switch (k) {
+    case 1: knn_query_kernel<1><<<g, b, 0, st>>>(m->view, d_q, nq, max_sq, stencil, d_idx, d_d2, d_cnt); break;
+    case 5: knn_query_kernel<5><<<g, b, 0, st>>>(m->view, d_q, nq, max_sq, stencil, d_idx, d_d2, d_cnt); break;
+    case 20: knn_query_kernel<20><<<g, b, 0, st>>>(m->view, d_q, nq, max_sq, stencil, d_idx, d_d2, d_cnt); break;
+    default: set_error("k must be 1, 5 or 20 (got %d)", k); return LSD_ERR_INVALID;
+  }
+  LSD_CUDA(cudaGetLastError());
+  m->launches++;
+  return LSD_OK;
+}
+
+}  // namespace lsd
+
+using namespace lsd;
+
+// ==================================================================== C ABI
+extern "C" {
+
+const char* lsd_version(void) { return "lsdreg 0.1.0 (sm_100a)"; }
+const char* lsd_last_error(void) { return g_err; }
+
+lsd_status_t lsd_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { cudaGetLastError(); set_error("no CUDA device: liblsdreg has no CPU fallback"); return LSD_ERR_NO_DEVICE; }
+  if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return LSD_ERR_INVALID; }
+  g_device = device;
+  LSD_CUDA(cudaSetDevice(device));
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_create(lsd_map_t** out, float resolution, int log2_lines) {
+  if (!out || resolution <= 0.f || log2_lines < 10 || log2_lines > 28) { set_error("lsd_map_create: bad arguments"); return LSD_ERR_INVALID; }
+  lsd_status_t s = ensure_device();
+  if (s) return s;
+  s = upload_stencils();
+  if (s) return s;
+  lsd_map* m = new lsd_map();
+  m->device = g_device;
+  m->n_lines = 1ull << log2_lines;
+  m->view.mask = m->n_lines - 1;
+  m->view.res = resolution;
+  m->view.inv_res = (float)(1.0 / (double)resolution);  // ivox3d.h:58
+  cudaError_t e = cudaMalloc(&m->view.lines, m->n_lines * sizeof(CellLine));
+  if (e == cudaSuccess) e = cudaMalloc(&m->view.counters, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { lsd_status_t r = cuda_fail(e, "lsd_map_create alloc", __FILE__, __LINE__); delete m; return r; }
+  *out = m;
+  return lsd_map_clear(m);
+}
+
+lsd_status_t lsd_map_destroy(lsd_map_t* m) {
+  if (!m) return LSD_OK;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream); else cudaDeviceSynchronize();
+  cudaFree(m->view.lines); cudaFree(m->view.counters); cudaFree(m->scratch);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_clear(lsd_map_t* m) {
+  if (!m) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(m->device));
+  LSD_CUDA(cudaMemsetAsync(m->view.lines, 0, m->n_lines * sizeof(CellLine), m->stream));
+  LSD_CUDA(cudaMemsetAsync(m->view.counters, 0, 4 * sizeof(unsigned long long), m->stream));
+  LSD_CUDA(cudaStreamSynchronize(m->stream));
+  return LSD_OK;
+}
+
+static lsd_status_t map_scratch(lsd_map* m, size_t bytes) {
+  if (m->scratch_bytes >= bytes) return LSD_OK;
+  if (m->scratch) LSD_CUDA(cudaFree(m->scratch));
+  m->scratch = nullptr; m->scratch_bytes = 0;
+  LSD_CUDA(cudaMalloc(&m->scratch, bytes));
+  m->scratch_bytes = bytes;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_insert_dev(lsd_map_t* m, const float* xyzi_dev, int n, int32_t id0) {
+  if (!m || (n > 0 && !xyzi_dev) || n < 0) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(m->device));
+  return launch_insert(m, reinterpret_cast<const float4*>(xyzi_dev), n, id0, m->stream);
+}
+
+lsd_status_t lsd_map_insert(lsd_map_t* m, const float* xyzi_host, int n, int32_t id0) {
+  if (!m || (n > 0 && !xyzi_host) || n < 0) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(m->device));
+  const int chunk = 1 << 22;  // 64 MB staging
+  lsd_status_t s = map_scratch(m, (size_t)std::min(n, chunk) * 16);
+  if (s) return s;
+  for (int o = 0; o < n; o += chunk) {
+    int c = std::min(chunk, n - o);
+    LSD_CUDA(cudaMemcpyAsync(m->scratch, xyzi_host + (size_t)o * 4, (size_t)c * 16, cudaMemcpyHostToDevice, m->stream));
+    s = launch_insert(m, reinterpret_cast<const float4*>(m->scratch), c, id0 + o, m->stream);
+    if (s) return s;
+    LSD_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_stats(lsd_map_t* m, uint64_t* n_cells, uint64_t* n_points, uint64_t* n_dropped) {
+  if (!m) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(m->device));
+  unsigned long long h[4];
+  LSD_CUDA(cudaMemcpyAsync(h, m->view.counters, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+  LSD_CUDA(cudaStreamSynchronize(m->stream));
+  if (n_cells) *n_cells = h[0];
+  if (n_points) *n_points = h[1];
+  if (n_dropped) *n_dropped = h[2];
+  return LSD_OK;
+}
+
+lsd_status_t lsd_knn_query_dev(lsd_map_t* m, const float* q_dev, int nq, int k, float max_sq, int stencil,
+                               int32_t* out_idx_dev, float* out_d2_dev, int32_t* out_cnt_dev) {
+  if (!m || nq < 0 || (nq > 0 && (!q_dev || !out_idx_dev || !out_d2_dev || !out_cnt_dev))) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(m->device));
+  return launch_knn(m, reinterpret_cast<const float4*>(q_dev), nq, k, max_sq, stencil, out_idx_dev, out_d2_dev, out_cnt_dev, m->stream);
+}
+
+lsd_status_t lsd_knn_query(lsd_map_t* m, const float* q_host, int nq, int k, float max_sq, int stencil,
+                           int32_t* out_idx, float* out_d2, int32_t* out_cnt) {
+  if (!m || nq < 0 || (nq > 0 && (!q_host || !out_idx || !out_d2 || !out_cnt))) return LSD_ERR_INVALID;
+  if (nq == 0) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(m->device));
+  size_t bq = (size_t)nq * 16, bi = (size_t)nq * k * 4, bc = (size_t)nq * 4;
+  lsd_status_t s = map_scratch(m, bq + 2 * bi + bc + 256);
+  if (s) return s;
+  char* base = static_cast<char*>(m->scratch);
+  float4* dq = reinterpret_cast<float4*>(base);
+  int* didx = reinterpret_cast<int*>(base + bq);
+  float* dd2 = reinterpret_cast<float*>(base + bq + bi);
+  int* dcnt = reinterpret_cast<int*>(base + bq + 2 * bi);
+  LSD_CUDA(cudaMemcpyAsync(dq, q_host, bq, cudaMemcpyHostToDevice, m->stream));
+  s = launch_knn(m, dq, nq, k, max_sq, stencil, didx, dd2, dcnt, m->stream);
+  if (s) return s;
+  LSD_CUDA(cudaMemcpyAsync(out_idx, didx, bi, cudaMemcpyDeviceToHost, m->stream));
+  LSD_CUDA(cudaMemcpyAsync(out_d2, dd2, bi, cudaMemcpyDeviceToHost, m->stream));
+  LSD_CUDA(cudaMemcpyAsync(out_cnt, dcnt, bc, cudaMemcpyDeviceToHost, m->stream));
+  LSD_CUDA(cudaStreamSynchronize(m->stream));
+  return LSD_OK;
+}
+
+}  // extern "C"

@@ -553,8 +553,9 @@ int orc_map_incremental(OrcIvox* map, const float* body, int n, const double* R,
       float mid[3];
       for (int d = 0; d < 3; d++) mid[d] = (float)(floor((double)w[d] / fsize) * fsize + 0.5 * fsize);
       float dist = calc_dist3(w, mid);
-      if (fabs((double)nr[0] - (double)mid[0]) > 0.5 * fsize && fabs((double)nr[1] - (double)mid[1]) > 0.5 * fsize &&
-          fabs((double)nr[2] - (double)mid[2]) > 0.5 * fsize) {
+      /* float subtraction, std::fabs(float), then compared against a double (laserMapping.cpp:545) */
+      if ((double)fabsf(nr[0] - mid[0]) > 0.5 * fsize && (double)fabsf(nr[1] - mid[1]) > 0.5 * fsize &&
+          (double)fabsf(nr[2] - mid[2]) > 0.5 * fsize) {
         f = 2;
       } else {
         for (int r = 0; r < 5; r++) {

@@ -1,0 +1,139 @@
+"""GPU parity: fused k-NN + plane + residual/Jacobian + reduction (K3-K5), the iterated ESKF update
+and map_incremental, against the CPU oracle, through the C ABI.
+Bars (BASELINE.json north_star): neighbour ids bit-exact; pose within 1e-4 m / 1e-5 rad."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, ROT_TOL = 1e-4, 1e-5
+
+
+def _pair(small_world, **kw):
+    import lsdreg
+    from oracle import eskf
+    from oracle.lio import OracleLio
+    m = small_world["map"]
+    g = lsdreg.LioFrontend(map_log2_lines=20, **kw)
+    g.map.insert(m, 0)
+    g.set_next_id(m.shape[0])
+    o = OracleLio(kw.get("ivox_nearby", 18), knn_exact=bool(kw.get("knn_mode_exact", 0)), expected_cells=1 << 18)
+    o.add_map_points(m)
+    prior = eskf.State()
+    prior.rot = eskf.R_to_quat(small_world["Rprior"])
+    prior.pos = small_world["tprior"].copy()
+    return g, o, prior
+
+
+def _rot_err(qa, qb):
+    from oracle import eskf
+    return np.linalg.norm(eskf.so3_log(eskf.quat_mul(eskf.quat_conj(qa), qb)))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(ivox_nearby=74), dict(knn_mode_exact=1)])
+def test_linearize_matches_oracle(small_world, kw):
+    from oracle import oracle as O
+    g, o, prior = _pair(small_world, **kw)
+    n = g.load_scan(small_world["scan"])
+    body = g.get_down()
+    ref_body = O.voxelgrid(small_world["scan"], 0.5)
+    assert n == ref_body.shape[0]
+    # feed the oracle the SAME downsampled cloud (K1 parity is tolerance-level)
+    o.near_xyz = np.zeros((n, 5, 3), np.float32); o.near_ids = np.full((n, 5), -1, np.int32)
+    o.near_cnt = np.zeros(n, np.int32); o.selected = np.ones(n, np.uint8)
+    o.world = np.zeros((n, 4), np.float32); o.plane = np.zeros((n, 4), np.float32)
+    ro = o._hmodel(body, prior, True)
+    rg = g.linearize(prior.to_vec(), True)
+    mt = g.get_matches()
+    assert (mt["world"][:, :3].view(np.int32) == o.world[:, :3].view(np.int32)).all()
+    assert (mt["cnt"] == o.near_cnt).all()
+    assert (mt["idx"] == o.near_ids).all()                      # bit-exact neighbour indices
+    assert (mt["selected"] == o.selected[:n]).all()
+    sel = mt["selected"].astype(bool)
+    assert (mt["plane"][sel].view(np.int32) == o.plane[sel].view(np.int32)).all()
+    assert rg["n_eff"] == ro["n"] and rg["n_eff"] > 1000
+    np.testing.assert_allclose(rg["HTH"], o.last["HTH6"], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(rg["HTh"], o.last["HTh6"], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(rg["res_sum"], o.last["res_sum"], rtol=1e-12)
+    # second evaluation without search reuses neighbours and the selected flags
+    st2 = prior.copy(); st2.pos = st2.pos + np.array([0.01, -0.02, 0.005])
+    ro2 = o._hmodel(body, st2, False)
+    rg2 = g.linearize(st2.to_vec(), False)
+    assert rg2["n_eff"] == ro2["n"]
+    np.testing.assert_allclose(rg2["HTH"], o.last["HTH6"], rtol=1e-10, atol=1e-9)
+
+
+def test_update_pose_parity_and_map_incremental(small_world):
+    from oracle import eskf
+    g, o, prior = _pair(small_world)
+    n = g.load_scan(small_world["scan"])
+    body = g.get_down()
+    P0 = eskf.init_P()
+    r = o.process_scan(body, prior, P0, downsample=False, update_map=False)
+    xg, Pg, info = g.update(prior.to_vec(), P0)
+    xo = o.x.to_vec()
+    assert info["iterations"] == r["iters"]
+    assert np.abs(xg[0:3] - xo[0:3]).max() < POS_TOL
+    assert _rot_err(xg[3:7], xo[3:7]) < ROT_TOL
+    np.testing.assert_allclose(xg, xo, atol=1e-7)
+    np.testing.assert_allclose(Pg, o.P, rtol=1e-6, atol=1e-12)
+    # converged onto the ground truth (scan noise 2 cm)
+    assert np.abs(xg[0:3] - small_world["tgt"]).max() < 0.02
+    # map_incremental: same add / skip decisions, same resulting map
+    added_o = o.map_incremental(body)
+    added_g = g.map_incremental(xo)  # same state on both sides
+    assert added_g == added_o
+    st = g.map.stats()
+    assert st["points"] == o.map.num_points and st["cells"] == o.map.num_cells
+
+
+def test_scan_sequence_full_pipeline(small_world):
+    """Three consecutive scans through lsd_lio_scan (host pointers): pose parity at every step."""
+    import lsdreg
+    from lsdreg import synth
+    from oracle import eskf
+    g, o, prior = _pair(small_world)
+    x = prior.to_vec(); P = eskf.init_P()
+    xo_state = prior.copy(); Po = P.copy()
+    for k in range(3):
+        Rk = small_world["Rgt"] @ synth.rot_from_rpy(0, 0, 0.02 * k)
+        tk = small_world["tgt"] + np.array([0.4 * k, 0.1 * k, 0.0])
+        scan = synth.scan64(10 + k, 250, Rk, tk)
+        # prior = previous posterior (constant-position motion model stands in for the IMU)
+        x, P, info = g.scan(scan, x, P)
+        assert info["status"] == lsdreg.OK and info["n_eff"] > 1000
+        # oracle consumes the GPU's downsampled cloud so k-NN inputs are identical
+        r = o.process_scan(g.get_down(), xo_state, Po, downsample=False)
+        xo_state, Po = o.x.copy(), o.P.copy()
+        xo = xo_state.to_vec()
+        assert np.abs(x[0:3] - xo[0:3]).max() < POS_TOL, k
+        assert _rot_err(x[3:7], xo[3:7]) < ROT_TOL, k
+        assert abs(info["n_added"] - r["added"]) <= 3, k
+        assert np.abs(x[0:3] - tk).max() < 0.03
+
+
+def test_first_scan_seeds_map_and_small_scan_is_skipped(small_world):
+    import lsdreg
+    from oracle import eskf
+    g = lsdreg.LioFrontend(map_log2_lines=18)
+    x = lsdreg.make_state(pos=small_world["tgt"], rot_xyzw=eskf.R_to_quat(small_world["Rgt"]))
+    P = lsdreg.init_cov()
+    x1, P1, info = g.scan(small_world["scan"], x, P)
+    assert info["status"] == lsdreg.MAP_SEEDED
+    assert g.map.stats()["points"] == info["n_down"] == info["n_added"]
+    np.testing.assert_array_equal(x1, x)
+    tiny = small_world["scan"][:3].copy()
+    x2, P2, info = g.scan(tiny, x, P)
+    assert info["status"] == lsdreg.SCAN_TOO_SMALL
+    np.testing.assert_array_equal(x2, x); np.testing.assert_array_equal(P2, P)
+
+
+def test_no_effective_points(small_world):
+    import lsdreg
+    g = lsdreg.LioFrontend(map_log2_lines=18)
+    g.map.insert(small_world["map"][:1000], 0)
+    x = lsdreg.make_state(pos=(5000.0, 5000.0, 0.0))  # nowhere near the map
+    P = lsdreg.init_cov()
+    x1, P1, info = g.scan(small_world["scan"], x, P)
+    assert info["status"] == lsdreg.NO_EFFECTIVE_POINTS and info["n_eff"] == 0
+    np.testing.assert_array_equal(x1, x)

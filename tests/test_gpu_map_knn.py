@@ -1,0 +1,108 @@
+"""GPU parity: hash-voxel map insert + k-NN (K2, K3) against the CPU oracle, through the C ABI.
+Bar: bit-exact neighbour ids and fp32 squared distances (integer/index work)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def maps(small_world):
+    import lsdreg
+    from oracle import oracle as O
+    m = small_world["map"]
+    g = lsdreg.HashVoxelMap(0.5, 20)
+    g.insert(m, 0)
+    o = O.OracleIvox(0.5, 18, 1 << 18)
+    o.add(m, 0)
+    return g, o
+
+
+def _queries(small_world):
+    from oracle import oracle as O
+    from lsdreg import synth
+    ds = O.voxelgrid(small_world["scan"], 0.5)
+    q = ds.copy()
+    R, t = small_world["Rprior"], small_world["tprior"]
+    q[:, :3] = (ds[:, :3].astype(np.float64) @ R.T + t).astype(np.float32)
+    return q
+
+
+def test_map_stats_match_oracle(maps, small_world):
+    g, o = maps
+    st = g.stats()
+    assert st["points"] == o.num_points == small_world["map"].shape[0]
+    assert st["cells"] == o.num_cells
+    assert st["dropped"] == 0
+
+
+@pytest.mark.parametrize("nearby", [0, 6, 18, 26, 74])
+def test_knn_stencil_bit_exact(maps, small_world, nearby):
+    g, o = maps
+    q = _queries(small_world)
+    o.set_nearby(nearby)
+    oi, od, _, oc = o.knn(q, 5, 5.0)
+    gi, gd, gc = g.knn(q, 5, 5.0, nearby)
+    assert (gc == oc).all()
+    assert (gi == oi).all()
+    assert (gd.view(np.int32) == od.view(np.int32)).all()  # bit-exact fp32 d2
+    o.set_nearby(18)
+
+
+@pytest.mark.parametrize("k", [1, 5, 20])
+def test_knn_exact_matches_oracle(maps, small_world, k):
+    import lsdreg
+    g, o = maps
+    q = _queries(small_world)
+    oi, od, _, oc = o.knn(q, k, 5.0, exact=True)
+    gi, gd, gc = g.knn(q, k, 5.0, lsdreg.STENCIL_EXACT)
+    assert (gc == oc).all()
+    assert (gi == oi).all()
+    assert (gd.view(np.int32) == od.view(np.int32)).all()
+
+
+def test_knn_empty_and_far_queries(maps):
+    g, _ = maps
+    idx, d2, cnt = g.knn(np.zeros((0, 4), np.float32))
+    assert idx.shape == (0, 5)
+    far = np.array([[1e4, 1e4, 50.0, 0.0], [-3000.0, 12.0, 3.0, 0.0]], np.float32)
+    idx, d2, cnt = g.knn(far)
+    assert (cnt == 0).all() and (idx == -1).all()
+
+
+def test_bucket_overflow_levels():
+    """> 7 points in one voxel spill to (voxel, level) lines; every point must stay findable."""
+    import lsdreg
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    pts = np.zeros((500, 4), np.float32)
+    pts[:, :3] = rng.uniform(-0.2, 0.2, size=(500, 3)) + np.array([10.0, -4.0, 2.0])  # one 0.5 m voxel
+    extra = np.zeros((200, 4), np.float32)
+    extra[:, :3] = rng.uniform(-3, 3, size=(200, 3)) + np.array([10.0, -4.0, 2.0])
+    allp = np.concatenate([pts, extra])
+    g = lsdreg.HashVoxelMap(0.5, 12)
+    g.insert(allp, 100)
+    o = O.OracleIvox(0.5, 18, 1 << 10)
+    o.add(allp, 100)
+    st = g.stats()
+    assert st["points"] == 700 and st["dropped"] == 0 and st["cells"] == o.num_cells
+    q = allp[::7].copy()
+    for k in (5, 20):
+        oi, od, _, oc = o.knn(q, k, 5.0)
+        gi, gd, gc = g.knn(q, k, 5.0, 18)
+        assert (gi == oi).all() and (gc == oc).all()
+
+
+def test_incremental_insert_equals_bulk(small_world):
+    import lsdreg
+    m = small_world["map"][:50000]
+    a = lsdreg.HashVoxelMap(0.5, 18)
+    a.insert(m, 0)
+    b = lsdreg.HashVoxelMap(0.5, 18)
+    for s in range(0, 50000, 7777):
+        b.insert(m[s:s + 7777], s)
+    assert a.stats() == b.stats()
+    q = m[::50].copy()
+    ia, da, ca = a.knn(q)
+    ib, db, cb = b.knn(q)
+    assert (ia == ib).all() and (da == db).all() and (ca == cb).all()
