@@ -239,6 +239,7 @@ class LioFrontend:
         self.h = C.c_void_p()
         check(lib.lsd_lio_create(C.byref(self.h), C.byref(self.params)))
         self.map = HashVoxelMap(_borrow=lib.lsd_lio_map(self.h))
+        self.n_down = 0
 
     def close(self):
         if self.h:
@@ -296,6 +297,7 @@ class LioFrontend:
         P = np.array(P, np.float64)
         info = LioInfo()
         st = check(lib.lsd_lio_update(self.h, _ptr(state), _ptr(P), C.byref(info)))
+        self.n_down = info.n_down
         return state, P, dict(info.as_dict(), status=st)
 
     def map_incremental(self, state: np.ndarray) -> int:
@@ -317,4 +319,5 @@ class LioFrontend:
         else:  # pinned / pageable host torch tensor
             st = lib.lsd_lio_scan(self.h, _ptr(scan), scan.shape[0], _ptr(state), _ptr(P), C.byref(info))
         check(st)
+        self.n_down = info.n_down
         return state, P, dict(info.as_dict(), status=st)

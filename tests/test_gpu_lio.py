@@ -99,7 +99,9 @@ def test_scan_sequence_full_pipeline(small_world):
         Rk = small_world["Rgt"] @ synth.rot_from_rpy(0, 0, 0.02 * k)
         tk = small_world["tgt"] + np.array([0.4 * k, 0.1 * k, 0.0])
         scan = synth.scan64(10 + k, 250, Rk, tk)
-        # prior = previous posterior (constant-position motion model stands in for the IMU)
+        # prior = previous posterior + inflated covariance (stands in for IMU propagation noise)
+        P = P + np.eye(23) * 1e-2
+        Po = Po + np.eye(23) * 1e-2
         x, P, info = g.scan(scan, x, P)
         assert info["status"] == lsdreg.OK and info["n_eff"] > 1000
         # oracle consumes the GPU's downsampled cloud so k-NN inputs are identical
@@ -109,7 +111,7 @@ def test_scan_sequence_full_pipeline(small_world):
         assert np.abs(x[0:3] - xo[0:3]).max() < POS_TOL, k
         assert _rot_err(x[3:7], xo[3:7]) < ROT_TOL, k
         assert abs(info["n_added"] - r["added"]) <= 3, k
-        assert np.abs(x[0:3] - tk).max() < 0.03
+        assert np.abs(x[0:3] - tk).max() < 0.05
 
 
 def test_first_scan_seeds_map_and_small_scan_is_skipped(small_world):
