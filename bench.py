@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the registration hot path (BASELINE.json metric: scans/sec,
+100 k-pt 64-beam scan vs 10 M-pt map, full LIO iterate-to-converge).
+
+One "step" = one pass of the per-scan LIO hot path (lsd_lio_scan): voxel-grid downsample (K1) ->
+iterated ESKF update with fused k-NN + plane + residual/Jacobian + J^T J reduction per iteration
+(K3-K5, host 23x23 algebra in double) -> map_incremental insert (K2).  Every step visits a
+different 120 m x 80 m block of the map, so the map lines it touches are cold (the table + points
+are far larger than L2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (C ABI)
+  python bench.py --impl reference ...                         the CPU reference arm
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCKS_X, BLOCKS_Y, SPACING = 13, 13, 0.5   # 169 blocks x ~60 k pts = ~10.1 M map points
+N_AZ = 1563                                  # 64 x 1563 = 100 032 rays
+MAP_SEED, SCAN_SEED = 20260922 + 2, 20260922 + 102
+WORKLOAD = "config[1]: 100k-pt 64-beam synthetic scan vs 10M-pt map, full LIO iterate-to-converge"
+
+
+def step_block(s: int):
+    return (s * 5 + 2) % BLOCKS_X, (s * 7 + 3) % BLOCKS_Y
+
+
+def make_step(s: int):
+    """Scan s: ground-truth pose inside block step_block(s), the scan seen from it, and a prior
+    perturbed by |t| <= 0.3 m, |theta| <= 1 deg."""
+    from lsdreg import synth
+    bi, bj = step_block(s)
+    rng = np.random.default_rng([SCAN_SEED, s])
+    Rgt = synth.rot_from_rpy(*np.deg2rad(rng.uniform(-2, 2, 2)), rng.uniform(-np.pi, np.pi))
+    tgt = synth.block_center(bi, bj) + np.append(rng.uniform(-3, 3, 2), 0.0)
+    scan = synth.scan64(SCAN_SEED + s, N_AZ, Rgt, tgt, bi, bj)
+    dR, dt = synth.perturb(SCAN_SEED + 1000 + s)
+    return scan, Rgt, tgt, Rgt @ dR, tgt + dt
+
+
+def quat_from_R(R):
+    t = np.trace(R)
+    q = np.zeros(4)
+    if t > 0:
+        t = np.sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t
+        q[0] = (R[2, 1] - R[1, 2]) * t; q[1] = (R[0, 2] - R[2, 0]) * t; q[2] = (R[1, 0] - R[0, 1]) * t
+    else:
+        i = int(np.argmax(np.diag(R))); j, k = (i + 1) % 3, (i + 2) % 3
+        t = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0); q[i] = 0.5 * t; t = 0.5 / t
+        q[3] = (R[k, j] - R[j, k]) * t; q[j] = (R[j, i] + R[i, j]) * t; q[k] = (R[k, i] + R[i, k]) * t
+    return q
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.rows, self.index, self.proc = [], index, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_cpu(args, rank, world):
+    """Reference arm / cpu_baseline: the reference's CPU path on the host cores.  Uses oracle/_ref
+    (compiled reference iVox + esti_plane) when it exists, else the plain-C port."""
+    from oracle import eskf
+    from oracle.lio import OracleLio
+    from oracle import oracle as O
+    from lsdreg import synth
+    cores = os.cpu_count() or 1
+    kind = "reference" if (O.HAVE_REF and hasattr(O.ref, "ref_lio_hmodel")) else "port"
+    t0 = time.time()
+    m = synth.block_map(MAP_SEED, BLOCKS_X, BLOCKS_Y, SPACING)
+    lio = OracleLio(18, expected_cells=1 << 24, nthreads=cores, backend=kind) if "backend" in OracleLio.__init__.__code__.co_varnames \
+        else OracleLio(18, expected_cells=1 << 24, nthreads=cores)
+    lio.add_map_points(m)
+    setup_s = time.time() - t0
+    W, K = args.warmup, args.steps
+    steps = [make_step(s) for s in range(W + K)]
+    times, iters = [], []
+    for s, (scan, Rgt, tgt, Rp, tp) in enumerate(steps):
+        prior = eskf.State(); prior.rot = eskf.R_to_quat(Rp); prior.pos = tp.copy()
+        t1 = time.perf_counter()
+        r = lio.process_scan(scan, prior, eskf.init_P())
+        dt = time.perf_counter() - t1
+        if s >= W:
+            times.append(dt); iters.append(r["iters"])
+            err = float(np.abs(lio.x.pos - tgt).max())
+            assert err < 0.1, f"CPU LIO did not converge at step {s}: {err}"
+    total = float(np.sum(times))
+    value = K / total
+    return dict(value=value, ms_per_step=1e3 * total / K, cores=cores, kind=kind, setup_s=setup_s,
+                iters=float(np.mean(iters)), map_points=int(m.shape[0]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=3, help="scans timed for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_cpu(args, rank, world)
+        line = {"impl": "reference", "metric": "scans/sec", "value": r["value"], "unit": "scans/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "map_points": r["map_points"], "scan_points": 64 * N_AZ},
+                "cpu_baseline": {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": f"{args.steps} full scans of the workload after {args.warmup} warm-up scans"},
+                "e2e": {"value": r["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "mean_iterations": r["iters"]}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import lsdreg
+    from lsdreg import synth
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    lsdreg.init(local)
+    dev = torch.device("cuda", local)
+
+    # ---------------- map (each rank holds a replica; ranks draw different scan streams)
+    m = synth.block_map(MAP_SEED, BLOCKS_X, BLOCKS_Y, SPACING)
+    lio = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000)
+    t0 = time.perf_counter()
+    lio.map.insert(m, 0)
+    build_s = time.perf_counter() - t0
+    lio.set_next_id(m.shape[0])
+    st = lio.map.stats()
+    rho = st["points"] / max(st["cells"], 1)
+
+    W, K = args.warmup, args.steps
+    n_prof = 5
+    base = rank * (2 * (W + K) + n_prof)
+    steps_a = [make_step(base + s) for s in range(W + K)]
+    steps_b = [make_step(base + W + K + s) for s in range(W + K)]
+    steps_p = [make_step(base + 2 * (W + K) + s) for s in range(n_prof)]
+    P0 = lsdreg.init_cov()
+
+    def prior_vec(stp):
+        return lsdreg.make_state(pos=stp[4], rot_xyzw=quat_from_R(stp[3]))
+
+    def run_steps(steps, scans, timed_from):
+        """Returns (wall seconds of the timed part, per-step infos).  Bracketed by sync + barrier."""
+        infos = []
+        t_start = None
+        for s, stp in enumerate(steps):
+            if s == timed_from:
+                torch.cuda.synchronize()
+                if dist is not None:
+                    dist.barrier()
+                t_start = time.perf_counter()
+            x, P, info = lio.scan(scans[s], prior_vec(stp), P0)
+            if s >= timed_from:
+                info["pos_err"] = float(np.abs(x[:3] - stp[2]).max())
+                infos.append(info)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t_start
+        return wall, infos
+
+    # ---------------- (1) inputs resident in HBM
+    dev_scans = [torch.from_numpy(stp[0]).to(dev) for stp in steps_a]
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    wall_a, infos_a = run_steps(steps_a, dev_scans, W)
+    clocks = sampler.stop()
+    # ---------------- (2) end to end: pinned host buffers, H2D inside the timed region
+    host_scans = [torch.from_numpy(stp[0]).pin_memory() for stp in steps_b]
+    wall_b, infos_b = run_steps(steps_b, host_scans, W)
+    # ---------------- (3) per-kernel timing pass for the roofline (not part of any throughput number)
+    lio.set_profile(True)
+    n_down_p = []
+    for stp in steps_p:
+        x, P, info = lio.scan(torch.from_numpy(stp[0]).to(dev), prior_vec(stp), P0)
+        n_down_p.append(info["n_down"])
+    prof = lio.get_profile()
+    lio.set_profile(False)
+
+    dev_ms = float(np.sum([i["gpu_ms"] for i in infos_a]))
+    t = torch.tensor([wall_a, wall_b, dev_ms * 1e-3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_a, wall_b, dev_s = [float(v) for v in t.cpu()]
+    value = world * K / wall_a
+    e2e = world * K / wall_b
+    for i in infos_a + infos_b:
+        assert i["pos_err"] < 0.1, f"LIO did not converge: {i}"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    hs = prof["hmodel_search"]
+    n_q = float(np.mean(n_down_p))
+    bytes_per_query = 56 + 19 * (8 + 16 * rho)   # K3 algorithmic bytes, S = 19, k = 5
+    alg_bytes = n_q * bytes_per_query
+    dur_s = hs["ms"] / max(hs["count"], 1) * 1e-3
+    achieved = alg_bytes / dur_s / 1e9 if dur_s > 0 else 0.0
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("lio_hmodel_search_bytes_per_launch")
+    except Exception:
+        pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        a2 = argparse.Namespace(steps=args.cpu_sample, warmup=1)
+        r = run_cpu(a2, 0, 1)
+        cpu = {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{args.cpu_sample} full scans of the same workload (same map, same generator) after 1 warm-up scan",
+               "ms_per_scan": r["ms_per_step"], "mean_iterations": r["iters"]}
+
+    iters = float(np.mean([i["iterations"] for i in infos_a]))
+    h2d = int(64 * N_AZ * 16)
+    d2h = int(iters * (32 + 8) * 8 + 4)
+    line = {
+        "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * wall_a / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "map_points": int(st["points"]), "map_voxels": int(st["cells"]),
+                   "scan_points": 64 * N_AZ, "downsampled_points": float(np.mean([i["n_down"] for i in infos_a])),
+                   "mean_iterations": iters, "parallelism": "1 GPU" if world == 1 else f"{world} replicas, independent scan streams, no collective",
+                   "l2": "every step visits a different 120x80 m map block; table+points 4.3 GB >> 126 MB L2",
+                   "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream"},
+        "device_ms_per_step": 1e3 * dev_s / K,
+        "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * wall_b / K},
+        "gpu_launches": int(np.sum([i["kernel_launches"] for i in infos_a])),
+        "roofline": {"kernel": "lio_hmodel_kernel<search>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_query": bytes_per_query, "rho": rho,
+                     "queries_per_launch": n_q, "us_per_launch": dur_s * 1e6, "launches_timed": hs["count"]},
+        "kernels_ms": {k: (v["ms"] / max(v["count"], 1)) for k, v in prof.items()},
+        "cpu_baseline": cpu, "clocks": clocks, "map_build_s": build_s,
+        "pos_err_max_m": float(np.max([i["pos_err"] for i in infos_a])),
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

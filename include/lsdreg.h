@@ -138,6 +138,12 @@ lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag);
  * lsd_map_insert(lsd_lio_map(l), ...) are the caller's). */
 lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, laserMapping.cpp:1196 */
 
+/* Per-kernel CUDA-event timing for the roofline report (adds a sync per launch: never enable it in a
+ * throughput measurement).  ms4/cnt4: [0] h-model with k-NN search, [1] h-model reusing neighbours,
+ * [2] voxel grid (7 kernels), [3] map_incremental. */
+lsd_status_t lsd_lio_set_profile(lsd_lio_t* l, int on);
+lsd_status_t lsd_lio_get_profile(lsd_lio_t* l, double* ms4, long long* cnt4);
+
 /* Load the undistorted scan (feats_undistort) and, if `downsample`, run the 0.5 m VoxelGrid
  * (laserMapping.cpp:1206-1207).  Returns the downsampled size in *n_down. */
 lsd_status_t lsd_lio_load_scan(lsd_lio_t* l, const float* scan_host, int n, int downsample, int* n_down);

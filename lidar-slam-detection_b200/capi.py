@@ -69,6 +69,8 @@ SIGNATURES = [
     ("lsd_lio_set_nearby", _i, [_vp, _i]),
     ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
     ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
+    ("lsd_lio_set_profile", _i, [_vp, _i]),
+    ("lsd_lio_get_profile", _i, [_vp, _vp, _vp]),
     ("lsd_lio_load_scan", _i, [_vp, _vp, _i, _i, _pi]),
     ("lsd_lio_load_scan_dev", _i, [_vp, _vp, _i, _i, _pi]),
     ("lsd_lio_get_down", _i, [_vp, _vp, _i, _pi]),
@@ -256,6 +258,16 @@ class LioFrontend:
 
     def set_ekf_inited(self, flag: bool):
         check(lib.lsd_lio_set_ekf_inited(self.h, int(flag)))
+
+    def set_profile(self, on: bool):
+        check(lib.lsd_lio_set_profile(self.h, int(on)))
+
+    def get_profile(self):
+        ms = np.zeros(4)
+        cnt = np.zeros(4, np.int64)
+        check(lib.lsd_lio_get_profile(self.h, _ptr(ms), _ptr(cnt)))
+        names = ("hmodel_search", "hmodel_reuse", "voxelgrid", "map_incremental")
+        return {n: dict(ms=float(ms[i]), count=int(cnt[i])) for i, n in enumerate(names)}
 
     def load_scan(self, scan, downsample: bool = True) -> int:
         n_down = C.c_int()

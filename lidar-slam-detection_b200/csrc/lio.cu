@@ -392,6 +392,20 @@ static void eig3_sym(const double* Ain, double* V) {
   }
 }
 
+struct ProfScope {  // CUDA-event timing of one launch group on the LIO stream (profile mode only)
+  lsd_lio* l; int kind; bool on;
+  ProfScope(lsd_lio* l_, int kind_) : l(l_), kind(kind_), on(l_->profile != 0) { if (on) cudaEventRecord(l->pev[0], l->stream); }
+  void stop() {
+    if (!on) return;
+    cudaEventRecord(l->pev[1], l->stream);
+    cudaEventSynchronize(l->pev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, l->pev[0], l->pev[1]);
+    l->prof_ms[kind] += ms; l->prof_cnt[kind]++;
+    on = false;
+  }
+};
+
 static int grid_for(int n) { return std::max(1, (n + kLioBlock - 1) / kLioBlock); }
 
 // One h_share_model_geometric evaluation on the loaded scan.  Fills HTH6/HTh6 (after the
@@ -403,6 +417,7 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   cudaStream_t st = l->stream;
   const int nb = grid_for(l->n_bound);
   const int stencil = l->p.knn_mode_exact ? LSD_STENCIL_EXACT : l->p.ivox_nearby;
+  ProfScope prof(l, search ? 0 : 1);
   if (search)
     lio_hmodel_kernel<true><<<nb, kLioBlock, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                       l->d_selected, l->d_plane, l->d_world, l->d_partials, l->d_done, l->d_result);
@@ -411,6 +426,7 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
                                                        l->d_selected, l->d_plane, l->d_world, l->d_partials, l->d_done, l->d_result);
   LSD_CUDA(cudaGetLastError());
   l->launches++;
+  prof.stop();
   LSD_CUDA(cudaMemcpyAsync(l->h_result, l->d_result, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
   LSD_CUDA(cudaStreamSynchronize(st));
   const double* r = l->h_result;
@@ -522,11 +538,13 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
   pose_from_state(x, &ps);
   cudaStream_t st = l->stream;
   LSD_CUDA(cudaMemsetAsync(l->d_added, 0, sizeof(unsigned), st));
+  ProfScope prof(l, 3);
   const int nb = std::max(1, (l->n_bound + 255) / 256);
   lio_map_incremental_kernel<<<nb, 256, 0, st>>>(l->map->view, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt, l->ekf_inited,
                                                  (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added);
   LSD_CUDA(cudaGetLastError());
   l->launches++;
+  prof.stop();
   unsigned h = 0;
   LSD_CUDA(cudaMemcpyAsync(&h, l->d_added, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   LSD_CUDA(cudaStreamSynchronize(st));
@@ -539,8 +557,10 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
   cudaStream_t st = l->stream;
   if (n < 0 || n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
   if (downsample) {
+    ProfScope prof(l, 2);
     lsd_status_t s = vg_run(l->vg, d_scan, n, l->p.filter_size_surf, l->d_body, l->d_n, st);
     if (s) return s;
+    prof.stop();
     l->launches += 7;
     l->n_bound = std::min(n, l->p.max_points);
     l->n_down = -1;  // learned with the first reduction (or lsd_lio_load_scan's explicit read)
@@ -657,6 +677,8 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_result2, 64 * 8);
   if (e == cudaSuccess) e = cudaEventCreate(&l->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&l->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&l->pev[0]);
+  if (e == cudaSuccess) e = cudaEventCreate(&l->pev[1]);
   if (e == cudaSuccess) {  // memset(point_selected_surf, true), laserMapping.cpp:1089
     lio_fill_u8_kernel<<<(int)((mp + 255) / 256), 256, 0, l->stream>>>(l->d_selected, (int)mp, 1);
     e = cudaStreamSynchronize(l->stream);
@@ -679,6 +701,8 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   cudaFreeHost(l->h_result); cudaFreeHost(l->h_result2);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
+  if (l->pev[0]) cudaEventDestroy(l->pev[0]);
+  if (l->pev[1]) cudaEventDestroy(l->pev[1]);
   cudaStream_t own = l->stream;
   if (l->map) { if (l->map->stream == own) l->map->stream = nullptr; lsd_map_destroy(l->map); }
   if (l->vg) { if (l->vg->stream == own) l->vg->stream = nullptr; lsd_voxelgrid_destroy(l->vg); }
@@ -692,6 +716,17 @@ lsd_map_t* lsd_lio_map(lsd_lio_t* l) { return l ? l->map : nullptr; }
 lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil) {
   if (!l || (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0)) return LSD_ERR_INVALID;
   l->p.ivox_nearby = stencil;
+  return LSD_OK;
+}
+lsd_status_t lsd_lio_set_profile(lsd_lio_t* l, int on) {
+  if (!l) return LSD_ERR_INVALID;
+  l->profile = on ? 1 : 0;
+  for (int k = 0; k < 4; k++) { l->prof_ms[k] = 0; l->prof_cnt[k] = 0; }
+  return LSD_OK;
+}
+lsd_status_t lsd_lio_get_profile(lsd_lio_t* l, double* ms4, long long* cnt4) {
+  if (!l || !ms4 || !cnt4) return LSD_ERR_INVALID;
+  for (int k = 0; k < 4; k++) { ms4[k] = l->prof_ms[k]; cnt4[k] = l->prof_cnt[k]; }
   return LSD_OK;
 }
 lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id) { if (!l) return LSD_ERR_INVALID; l->next_id = id; l->map_cells_known = 0; return LSD_OK; }

@@ -35,4 +35,9 @@ struct lsd_lio {
   long long launches = 0;
   uint64_t map_cells_known = 0;
   double last_Pm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  // optional per-kernel timing (bench roofline): 0 hmodel<search>, 1 hmodel<reuse>, 2 voxel grid, 3 map_incremental
+  int profile = 0;
+  cudaEvent_t pev[2] = {nullptr, nullptr};
+  double prof_ms[4] = {0, 0, 0, 0};
+  long long prof_cnt[4] = {0, 0, 0, 0};
 };
