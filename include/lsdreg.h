@@ -114,6 +114,10 @@ typedef struct lsd_lio_params {
   double converge_eps;       /* 0.001, laserMapping.cpp:1114-1116                                   */
   int degenerate_detect_en;  /* laserMapping.cpp:83                                                 */
   int knn_mode_exact;        /* 0: iVox stencil (live path), 1: exact k-NN (ikd-Tree path)          */
+  int eskf_literal;          /* 1: evaluate the Kalman gain with the reference's two dense 23x23
+                                inversions (esekfom.hpp:1756-1789); 0 (default): the algebraically
+                                identical Schur-complement form (two 6x6 inverses), ~2x faster on
+                                the host and equally accurate (DESIGN.md "Host ESKF")             */
 } lsd_lio_params_t;
 
 typedef struct lsd_lio_info {
@@ -175,6 +179,12 @@ lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double
 void lsd_lio_init_cov(double* P529);
 void lsd_state_boxplus(double* state26_inout, const double* delta23);
 void lsd_state_boxminus(const double* a26, const double* b26, double* out23);
+/* The filter alone, on the host (no GPU): runs esekf::update_iterated_dyn_share_modified with the
+ * measurement model replaced by a caller-supplied table — evaluation e uses HTH36[e], HTh6[e],
+ * n_eff[e] (n_eff[e] < 1 = invalid).  Returns the number of evaluations consumed.  Used by the CPU
+ * test-suite to check the host algebra against the oracle without a device. */
+int lsd_eskf_update_table(double* state26_inout, double* P529_inout, const double* HTH36, const double* HTh6,
+                          const int* n_eff, int n_table, double R, int max_iterations, double eps, int literal);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ class LioParams(C.Structure):
     _fields_ = [("max_points", C.c_int), ("max_scan_points", C.c_int), ("filter_size_surf", C.c_float),
                 ("filter_size_map", C.c_float), ("ivox_resolution", C.c_float), ("ivox_nearby", C.c_int),
                 ("map_log2_lines", C.c_int), ("max_iterations", C.c_int), ("laser_point_cov", C.c_double),
-                ("converge_eps", C.c_double), ("degenerate_detect_en", C.c_int), ("knn_mode_exact", C.c_int)]
+                ("converge_eps", C.c_double), ("degenerate_detect_en", C.c_int), ("knn_mode_exact", C.c_int), ("eskf_literal", C.c_int)]
 
 
 class LioInfo(C.Structure):
@@ -83,6 +83,7 @@ SIGNATURES = [
     ("lsd_lio_init_cov", None, [_vp]),
     ("lsd_state_boxplus", None, [_vp, _vp]),
     ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
+    ("lsd_eskf_update_table", _i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _i, _d, _i]),
 ]
 
 
@@ -226,6 +227,18 @@ def state_boxminus(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     r = np.zeros(DOF)
     lib.lsd_state_boxminus(_ptr(a), _ptr(b), _ptr(r))
     return r
+
+
+def eskf_update_table(state, P, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=0.001, literal=False):
+    """Host-only filter run with a tabulated measurement model (include/lsdreg.h lsd_eskf_update_table)."""
+    state = np.array(state, np.float64)
+    P = np.array(P, np.float64)
+    HTH = np.ascontiguousarray(HTH, np.float64).reshape(-1, 36)
+    HTh = np.ascontiguousarray(HTh, np.float64).reshape(-1, 6)
+    n_eff = np.ascontiguousarray(n_eff, np.int32)
+    ev = lib.lsd_eskf_update_table(_ptr(state), _ptr(P), _ptr(HTH), _ptr(HTh), _ptr(n_eff), HTH.shape[0], R, max_iterations,
+                                   eps, int(literal))
+    return state, P, ev
 
 
 class LioFrontend:

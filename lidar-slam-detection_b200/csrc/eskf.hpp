@@ -249,15 +249,18 @@ using HFunc = std::function<void(const double* x26, bool converge, HModel* out)>
 struct UpdateResult { int evaluations = 0; bool returned_converged = false; };
 
 // esekfom.hpp:1619-1931
-inline UpdateResult update_iterated(double* x, double* P, const HFunc& h_model, double R, int maximum_iter, double limit) {
+inline UpdateResult update_iterated(double* x, double* P, const HFunc& h_model, double R, int maximum_iter, double limit,
+                                    bool literal = false) {
   UpdateResult res;
   double x_prop[S_DIM], P_prop[N * N];
   memcpy(x_prop, x, sizeof(x_prop)); memcpy(P_prop, P, sizeof(P_prop));
   bool converge = true;
   int t = 0;
   static thread_local HModel m;
-  std::vector<double> K_x(N * N, 0.0);
+  double K_x[N * N];
+  for (int i = 0; i < N * N; i++) K_x[i] = 0.0;
   double K_h[N];
+  int kx_cols = 15;  // non-zero columns of K_x
   const int so3_idx[2] = {D_ROT, D_OFFR};
   for (int it = -1; it < maximum_iter; it++) {
     m.valid = true;
@@ -296,7 +299,10 @@ inline UpdateResult update_iterated(double* x, double* P, const HFunc& h_model, 
       for (int i = 0; i < N; i++) for (int b = 0; b < dof; b++) { double s = 0; for (int k = 0; k < dof; k++) s += PHt[i * dof + k] * Sinv[k * dof + b]; K[i * dof + b] = s / R; }
       for (int i = 0; i < N; i++) { double s = 0; for (int k = 0; k < dof; k++) s += K[i * dof + k] * m.h[k]; K_h[i] = s; }
       for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { double s = 0; for (int k = 0; k < dof; k++) s += K[i * dof + k] * H[k * N + j]; K_x[i * N + j] = s; }
-    } else {
+      kx_cols = N;
+    } else if (literal) {
+      kx_cols = 15;
+      // the reference's literal evaluation: two dense 23x23 inversions (esekfom.hpp:1756-1789)
       double Pt[N * N], Pinv[N * N];
       for (int i = 0; i < N * N; i++) Pt[i] = P[i] / R;
       invert(Pt, Pinv, N);  // P_temp = (P/R)^-1
@@ -305,9 +311,27 @@ inline UpdateResult update_iterated(double* x, double* P, const HFunc& h_model, 
       for (int i = 0; i < N; i++) { double s = 0; for (int k = 0; k < 15; k++) s += Pt[i * N + k] * m.HTh[k]; K_h[i] = s; }
       for (int i = 0; i < N * N; i++) K_x[i] = 0;
       for (int i = 0; i < N; i++) for (int j = 0; j < 15; j++) { double s = 0; for (int k = 0; k < 15; k++) s += Pt[i * N + k] * m.HTH[k * 15 + j]; K_x[i * N + j] = s; }
+    } else {
+      // Same quantities without the two dense 23x23 inversions.  h_x^T h_x is non-zero only in its
+      // leading 6x6 block H (extrinsic_est_en == false, laserMapping.cpp:82,926-930).  With A = P/R
+      // partitioned at 6, the first 6 columns of P_inv = (A^-1 + U H U^T)^-1 — the only ones K_h and
+      // K_x use — follow from the Schur complement of the trailing block:
+      //   P_inv[:, 0:6] = [I; A21 A11^-1] (A11^-1 + H)^-1 = P[:, 0:6] P66^-1 (R P66^-1 + H)^-1
+      // Two 6x6 inverses of positive-definite sums (no cancellation), 23x6 products.
+      kx_cols = 6;
+      double H6[36], P66[36], P66i[36], S[36], Sinv[36], T1[36], C6[N * 6];
+      for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { H6[6 * a + c] = m.HTH[15 * a + c]; P66[6 * a + c] = P[a * N + c]; }
+      invert(P66, P66i, 6);
+      for (int i = 0; i < 36; i++) S[i] = R * P66i[i] + H6[i];
+      invert(S, Sinv, 6);
+      for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { double s = 0; for (int k = 0; k < 6; k++) s += P66i[6 * a + k] * Sinv[6 * k + c]; T1[6 * a + c] = s; }
+      for (int i = 0; i < N; i++) for (int c = 0; c < 6; c++) { double s = 0; for (int k = 0; k < 6; k++) s += P[i * N + k] * T1[6 * k + c]; C6[i * 6 + c] = s; }
+      for (int i = 0; i < N; i++) { double s = 0; for (int k = 0; k < 6; k++) s += C6[i * 6 + k] * m.HTh[k]; K_h[i] = s; }
+      for (int i = 0; i < N * N; i++) K_x[i] = 0;
+      for (int i = 0; i < N; i++) for (int j = 0; j < 6; j++) { double s = 0; for (int k = 0; k < 6; k++) s += C6[i * 6 + k] * H6[6 * k + j]; K_x[i * N + j] = s; }
     }
     double dx_[N];
-    for (int i = 0; i < N; i++) { double s = K_h[i]; for (int j = 0; j < N; j++) s += (K_x[i * N + j] - (i == j ? 1.0 : 0.0)) * dx_new[j]; dx_[i] = s; }
+    for (int i = 0; i < N; i++) { double s = K_h[i] - dx_new[i]; for (int j = 0; j < kx_cols; j++) s += K_x[i * N + j] * dx_new[j]; dx_[i] = s; }
     boxplus(x, dx_);
     converge = true;
     for (int i = 0; i < N; i++) if (fabs(dx_[i]) > limit) { converge = false; break; }

@@ -1,10 +1,15 @@
-// knn.cuh — k-NN over the hash-voxel map (K3).  One thread per query: neighbouring threads hold
-// neighbouring queries (the voxel-grid output is ordered by leaf index), so a warp's stencil
-// probes hit the same 128-byte cell lines and coalesce in L1.
+// knn.cuh — warp-cooperative k-NN over the hash-voxel map (K3).
+//
+// One WARP per query.  Lane L owns stencil cell L: it requests that voxel's header and first three
+// points (two 32-byte sectors of the 128-byte cell line) in one go, so all 19 (NEARBY18) probes of
+// a query are in flight together and the dependent-load depth is 1 for voxels with <= 3 points,
+// 2 otherwise.  Candidates inside the search radius are compacted with __ballot_sync into a
+// per-warp shared-memory list; the K best are then peeled off with warp-wide min reductions
+// (redux.sync) in canonical (d2, id) order.  Lane r ends up holding the r-th neighbour.
 //
 // Replaces IVox::GetClosestPoint (ivox3d.h:139-171) + IVoxNode::KNNPointByCondition
 // (ivox3d_node.hpp:107-127), and — with the EXACT shell search — KD_TREE::Nearest_Search
-// (ikd_Tree.cpp:367-397).  Result order is canonical: ascending (d2, id).
+// (ikd_Tree.cpp:367-397).
 #pragma once
 #include "lsd_common.cuh"
 
@@ -17,180 +22,279 @@ __host__ __device__ __forceinline__ int stencil_slot(int type) {
        : type == LSD_STENCIL_NEARBY26 ? 3 : type == LSD_STENCIL_NEARBY74 ? 4 : -1;
 }
 
-template <int K>
-struct TopK {
-  float d[K];
-  int id[K];
-  unsigned loc[K];  // line * 8 + slot (1..7): where the point lives, to re-read its coordinates
-  int n;
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int j = 0; j < K; j++) { d[j] = __int_as_float(0x7f800000); id[j] = 0x7fffffff; loc[j] = 0; }
-    n = 0;
-  }
-  // branch-free sorted insert: bubble the candidate through the K slots
-  __device__ __forceinline__ void insert(float cd, int cid, unsigned cloc) {
-    if (!(cd < d[K - 1] || (cd == d[K - 1] && cid < id[K - 1]))) return;
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      bool lt = cd < d[j] || (cd == d[j] && cid < id[j]);
-      float td = lt ? d[j] : cd; int ti = lt ? id[j] : cid; unsigned tl = lt ? loc[j] : cloc;
-      d[j] = lt ? cd : d[j]; id[j] = lt ? cid : id[j]; loc[j] = lt ? cloc : loc[j];
-      cd = td; cid = ti; cloc = tl;
-    }
-    n = n < K ? n + 1 : K;
-  }
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kCandCap = 256;  // per-warp candidate list capacity (one 32-cell chunk adds <= 224)
+constexpr unsigned kTaken = 0xffffffffu;
+
+// per-warp candidate list in shared memory (SoA)
+struct WarpList {
+  unsigned* d;    // fp32 bits of d2 (d2 >= 0, so unsigned order == float order)
+  int* id;
+  unsigned* loc;  // line * 8 + slot (1..7)
+  int n;          // warp-uniform
 };
+constexpr int kWarpListBytes = kCandCap * 12;
 
-template <int K>
-__device__ __forceinline__ void consider(TopK<K>& tk, const float4& p, unsigned loc, float qx, float qy, float qz,
-                                         float max_sq, bool inclusive) {
-  float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
-  bool ok = inclusive ? (d2 <= max_sq) : (d2 < max_sq);
-  if (ok) tk.insert(d2, __float_as_int(p.w), loc);
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// ballot-compact one candidate per lane into the list
+__device__ __forceinline__ void list_push(WarpList& wl, bool valid, float d2, int id, unsigned loc) {
+  const unsigned m = __ballot_sync(kFull, valid);
+  if (valid) {
+    const int pos = wl.n + __popc(m & lanemask_lt());
+    wl.d[pos] = __float_as_uint(d2); wl.id[pos] = id; wl.loc[pos] = loc;
+  }
+  wl.n += __popc(m);
 }
 
-// Scan points [first, min(count,7)) of a matched level-0 line, then any overflow levels
-// (lines keyed (voxel, L) holding points 7L..7L+6).  Runtime loops: one inlined copy of insert().
+// lane r (r < n) receives the r-th best of the list in canonical (d2, id) order
+struct Neighbor { float d2; int id; unsigned loc; };
+
 template <int K>
-__device__ __forceinline__ void scan_line(const MapView& mv, const CellLine* ln, unsigned long long s,
-                                          unsigned long long key, unsigned count, int first, TopK<K>& tk, float qx,
-                                          float qy, float qz, float max_sq, bool inclusive) {
-  const int n0 = (int)min(count, (unsigned)kPtsPerLine);
+__device__ __forceinline__ int list_select(WarpList& wl, Neighbor& out) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  const int nf = min(wl.n, K);
+  out.d2 = -1.0f; out.id = -1; out.loc = 0;
+  if (wl.n <= 32) {
+    // common case: one candidate per lane, selection entirely in registers (redux.sync)
+    unsigned d = kTaken; int id = 0x7fffffff; unsigned loc = 0;
+    if (lane < wl.n) { d = wl.d[lane]; id = wl.id[lane]; loc = wl.loc[lane]; }
 #pragma unroll 1
-  for (int j = first; j < n0; j++)
-    consider(tk, ldg_f4(&ln->pts[j]), (unsigned)(s * 8 + j + 1), qx, qy, qz, max_sq, inclusive);
-  if (count <= (unsigned)kPtsPerLine) return;
-  const int levels = min((int)((count - 1) / kPtsPerLine), kMaxLevel);
-#pragma unroll 1
-  for (int L = 1; L <= levels; L++) {
-    const unsigned long long kl = key | ((unsigned long long)L << 57);
-    unsigned long long sl = hash_key(kl) & mv.mask;
-#pragma unroll 1
-    for (unsigned probe = 0; probe < kMaxProbe; probe++) {
-      const CellLine* l2 = mv.lines + sl;
-      const uint4 h = ldg_u4(l2);
-      const unsigned long long k = (unsigned long long)h.x | ((unsigned long long)h.y << 32);
-      if (k == kl) {
-        const int n = (int)min(count - (unsigned)(L * kPtsPerLine), (unsigned)kPtsPerLine);
-#pragma unroll 1
-        for (int j = 0; j < n; j++)
-          consider(tk, ldg_f4(&l2->pts[j]), (unsigned)(sl * 8 + j + 1), qx, qy, qz, max_sq, inclusive);
-        break;
+    for (int r = 0; r < nf; r++) {
+      const unsigned m = __reduce_min_sync(kFull, d);
+      const unsigned eq = __ballot_sync(kFull, d == m);
+      int win = __ffs(eq) - 1;
+      if (eq & (eq - 1)) {  // equal distances: canonical order breaks ties by id
+        const int mi = __reduce_min_sync(kFull, d == m ? id : 0x7fffffff);
+        win = __ffs(__ballot_sync(kFull, d == m && id == mi)) - 1;
       }
-      if (k == 0) break;
-      sl = (sl + 1) & mv.mask;
+      const int wid = __shfl_sync(kFull, id, win);
+      const unsigned wloc = __shfl_sync(kFull, loc, win);
+      if (lane == r) { out.d2 = __uint_as_float(m); out.id = wid; out.loc = wloc; }
+      if (lane == win) d = kTaken;
     }
+    __syncwarp();
+    return nf;
   }
+#pragma unroll 1
+  for (int r = 0; r < nf; r++) {
+    unsigned bd = kTaken; int bi = 0x7fffffff; int bp = 0;
+    for (int p = lane; p < wl.n; p += 32) {
+      const unsigned d = wl.d[p]; const int i = wl.id[p];
+      if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; bp = p; }
+    }
+    const unsigned m = __reduce_min_sync(kFull, bd);
+    const int mi = __reduce_min_sync(kFull, bd == m ? bi : 0x7fffffff);
+    const unsigned wm = __ballot_sync(kFull, bd == m && bi == mi);
+    const int win = __ffs(wm) - 1;
+    unsigned wloc = 0;
+    if (lane == win) { wloc = wl.loc[bp]; wl.d[bp] = kTaken; }
+    wloc = __shfl_sync(kFull, wloc, win);
+    if (lane == r) { out.d2 = __uint_as_float(m); out.id = mi; out.loc = wloc; }
+    __syncwarp();
+  }
+  return nf;
 }
 
-// Generic (slow-path) voxel lookup: linear probe from `s`, scan every point of the voxel.
+// keep only the K best in the list
 template <int K>
-__device__ __forceinline__ void scan_voxel(const MapView& mv, unsigned long long key, unsigned long long s, TopK<K>& tk,
-                                           float qx, float qy, float qz, float max_sq, bool inclusive) {
-#pragma unroll 1
-  for (unsigned probe = 0; probe < kMaxProbe; probe++) {
-    const CellLine* ln = mv.lines + s;
-    const uint4 h = ldg_u4(ln);
-    const unsigned long long k = (unsigned long long)h.x | ((unsigned long long)h.y << 32);
-    if (k == key) { scan_line(mv, ln, s, key, h.z, 0, tk, qx, qy, qz, max_sq, inclusive); return; }
-    if (k == 0) return;
-    s = (s + 1) & mv.mask;
-  }
+__device__ __forceinline__ void list_compress(WarpList& wl) {
+  Neighbor nb;
+  const int nf = list_select<K>(wl, nb);
+  const int lane = threadIdx.x & 31;
+  if (lane < nf) { wl.d[lane] = __float_as_uint(nb.d2); wl.id[lane] = nb.id; wl.loc[lane] = nb.loc; }
+  wl.n = nf;
+  __syncwarp();
 }
 
-// Fixed-stencil search.  Chunks of CH cells: all CH header+first-point sectors are requested
-// before any is consumed (CH independent 32-byte sector loads in flight per thread).  Voxels whose
-// home slot is taken by another voxel, or that hold more than one point, are finished in runtime
-// loops afterwards so the unrolled fast path stays small.
-template <int K, int CH = 8>
-__device__ __forceinline__ void knn_stencil(const MapView& mv, int st_slot, float qx, float qy, float qz, float max_sq,
-                                            TopK<K>& tk) {
-  const Stencil& st = c_stencils[st_slot];
-  const int3 c = pos2grid(qx, qy, qz, mv.inv_res);
-#pragma unroll 1
-  for (int c0 = 0; c0 < st.n; c0 += CH) {
-    uint4 h[CH]; float4 p0[CH];
-    unsigned valid = 0;
-#pragma unroll
-    for (int u = 0; u < CH; u++) {
-      if (c0 + u < st.n) {
-        const int x = c.x + st.off[c0 + u][0], y = c.y + st.off[c0 + u][1], z = c.z + st.off[c0 + u][2];
-        if (coord_ok(x, y, z)) {
-          const unsigned long long key = pack_key(x, y, z, 0);
-          const CellLine* ln = mv.lines + (hash_key(key) & mv.mask);
-          h[u] = ldg_u4(ln);
-          p0[u] = ldg_f4(&ln->pts[0]);
-          valid |= 1u << u;
+// Each lane resolves ONE voxel (key == 0: none) and pushes its in-radius points.
+// Phase A: header + points 0..2 (sectors 0,1) requested together; phase B: points 3..6 if needed;
+// overflow levels (> 7 points in the voxel) are walked cooperatively afterwards.
+template <int K>
+__device__ __forceinline__ void warp_scan_cells(const MapView& mv, unsigned long long key, float qx, float qy, float qz,
+                                                float max_sq, bool inclusive, WarpList& wl) {
+  unsigned long long s = 0;
+  const CellLine* ln = mv.lines;
+  unsigned cnt = 0;
+  {
+    uint4 h = make_uint4(0, 0, 0, 0);
+    float4 p[3];
+    p[0] = p[1] = p[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (key != 0ull) {
+      s = hash_key(key) & mv.mask;
+      ln = mv.lines + s;
+      h = ldg_u4(ln);
+      p[0] = ldg_f4(&ln->pts[0]); p[1] = ldg_f4(&ln->pts[1]); p[2] = ldg_f4(&ln->pts[2]);
+      unsigned long long k = (unsigned long long)h.x | ((unsigned long long)h.y << 32);
+      if (k != key && k != 0ull) {  // home slot taken by another voxel: linear probe (rare at load <= 0.5)
+        for (unsigned probe = 1; probe < kMaxProbe; probe++) {
+          s = (s + 1) & mv.mask;
+          ln = mv.lines + s;
+          h = ldg_u4(ln);
+          k = (unsigned long long)h.x | ((unsigned long long)h.y << 32);
+          if (k == key || k == 0ull) break;
         }
+        if (k == key) { p[0] = ldg_f4(&ln->pts[0]); p[1] = ldg_f4(&ln->pts[1]); p[2] = ldg_f4(&ln->pts[2]); }
       }
+      if (k == key) cnt = h.z;
     }
-    unsigned more = 0;  // bit u: voxel needs the runtime path (collision chain or > 1 point)
 #pragma unroll
-    for (int u = 0; u < CH; u++) {
-      if (!(valid >> u & 1)) continue;
-      const int x = c.x + st.off[c0 + u][0], y = c.y + st.off[c0 + u][1], z = c.z + st.off[c0 + u][2];
-      const unsigned long long key = pack_key(x, y, z, 0);
-      const unsigned long long k = (unsigned long long)h[u].x | ((unsigned long long)h[u].y << 32);
-      if (k == key) {
-        if (h[u].z > 0) consider(tk, p0[u], (unsigned)((hash_key(key) & mv.mask) * 8 + 1), qx, qy, qz, max_sq, false);
-        if (h[u].z > 1) more |= 1u << u;
-      } else if (k != 0) {
-        more |= 1u << (u + 16);
+    for (int j = 0; j < 3; j++) {
+      bool valid = (unsigned)j < cnt;
+      float d2 = 0.f;
+      if (valid) {
+        d2 = dist2(qx, qy, qz, p[j].x, p[j].y, p[j].z);
+        valid = inclusive ? (d2 <= max_sq) : (d2 < max_sq);
       }
-    }
-#pragma unroll 1
-    while (more) {
-      const int b = __ffs(more) - 1;
-      more &= more - 1;
-      const int u = b & 15;
-      const int x = c.x + st.off[c0 + u][0], y = c.y + st.off[c0 + u][1], z = c.z + st.off[c0 + u][2];
-      const unsigned long long key = pack_key(x, y, z, 0);
-      const unsigned long long s = hash_key(key) & mv.mask;
-      if (b < 16) {  // matched at home slot: points 1.. (header re-read hits L1)
-        const CellLine* ln = mv.lines + s;
-        scan_line(mv, ln, s, key, ldg_u4(ln).z, 1, tk, qx, qy, qz, max_sq, false);
-      } else {
-        scan_voxel(mv, key, (s + 1) & mv.mask, tk, qx, qy, qz, max_sq, false);
-      }
+      list_push(wl, valid, d2, __float_as_int(p[j].w), (unsigned)(s * 8 + j + 1));
     }
   }
+  if (__any_sync(kFull, cnt > 3u)) {  // phase B: sectors 2,3 of the lines that need them
+    const unsigned n0 = min(cnt, (unsigned)kPtsPerLine);
+    float4 p[4];
+    p[0] = p[1] = p[2] = p[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 > 3) { p[0] = ldg_f4(&ln->pts[3]); p[1] = ldg_f4(&ln->pts[4]); p[2] = ldg_f4(&ln->pts[5]); p[3] = ldg_f4(&ln->pts[6]); }
+#pragma unroll
+    for (int j = 3; j < kPtsPerLine; j++) {
+      bool valid = (unsigned)j < n0;
+      float d2 = 0.f;
+      if (valid) {
+        d2 = dist2(qx, qy, qz, p[j - 3].x, p[j - 3].y, p[j - 3].z);
+        valid = inclusive ? (d2 <= max_sq) : (d2 < max_sq);
+      }
+      list_push(wl, valid, d2, __float_as_int(p[j - 3].w), (unsigned)(s * 8 + j + 1));
+    }
+  }
+  // overflow levels: voxels with more than 7 points (rare in a 0.5 m-thinned map)
+  unsigned ovf = __ballot_sync(kFull, cnt > (unsigned)kPtsPerLine);
+  while (ovf) {
+    const int src = __ffs(ovf) - 1;
+    ovf &= ovf - 1;
+    const unsigned long long okey = __shfl_sync(kFull, key, src);
+    const unsigned ocnt = __shfl_sync(kFull, cnt, src);
+    const int levels = min((int)((ocnt - 1) / kPtsPerLine), kMaxLevel);
+    for (int L = 1; L <= levels; L++) {
+      const unsigned long long kl = okey | ((unsigned long long)L << 57);
+      unsigned long long sl = hash_key(kl) & mv.mask;
+      bool found = false;
+      for (unsigned probe = 0; probe < kMaxProbe; probe++) {  // warp-uniform probe
+        const uint4 hh = ldg_u4(mv.lines + sl);
+        const unsigned long long k2 = (unsigned long long)hh.x | ((unsigned long long)hh.y << 32);
+        if (k2 == kl) { found = true; break; }
+        if (k2 == 0ull) break;
+        sl = (sl + 1) & mv.mask;
+      }
+      if (!found) continue;
+      const int n = (int)min(ocnt - (unsigned)(L * kPtsPerLine), (unsigned)kPtsPerLine);
+      const int lane = threadIdx.x & 31;
+      bool valid = lane < n;
+      float d2 = 0.f; float4 q = make_float4(0, 0, 0, 0);
+      if (valid) {
+        q = ldg_f4(&(mv.lines + sl)->pts[lane]);
+        d2 = dist2(qx, qy, qz, q.x, q.y, q.z);
+        valid = inclusive ? (d2 <= max_sq) : (d2 < max_sq);
+      }
+      if (wl.n + 7 > kCandCap) list_compress<K>(wl);
+      list_push(wl, valid, d2, __float_as_int(q.w), (unsigned)(sl * 8 + lane + 1));
+    }
+  }
+}
+
+// The stencil offsets a lane is responsible for (cell c*32 + lane of the stencil), loaded once per
+// kernel: constant-memory reads indexed by the lane would otherwise be replayed 32 ways per query.
+struct LaneStencil {
+  int n_chunks;
+  int off[3];  // packed (dx, dy, dz) + valid flag per 32-cell chunk
+};
+__device__ __forceinline__ LaneStencil lane_stencil(int st_slot) {
+  LaneStencil ls;
+  ls.n_chunks = 0;
+  ls.off[0] = ls.off[1] = ls.off[2] = 0;
+  if (st_slot < 0) return ls;
+  const Stencil& st = c_stencils[st_slot];
+  const int lane = threadIdx.x & 31;
+  ls.n_chunks = (st.n + 31) >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const int idx = c * 32 + lane;
+    if (idx < st.n)
+      ls.off[c] = 0x1000000 | ((st.off[idx][0] & 0xff) << 16) | ((st.off[idx][1] & 0xff) << 8) | (st.off[idx][2] & 0xff);
+  }
+  return ls;
+}
+
+// Fixed-stencil search (IVox NEARBY*).  32 stencil cells per pass.
+template <int K>
+__device__ __forceinline__ int knn_stencil_warp(const MapView& mv, const LaneStencil& ls, float qx, float qy, float qz,
+                                                float max_sq, WarpList& wl, Neighbor& out) {
+  const int3 c = pos2grid(qx, qy, qz, mv.inv_res);
+  wl.n = 0;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    if (ch < ls.n_chunks) {
+      if (ch > 0 && wl.n > kCandCap - 7 * 32) list_compress<K>(wl);
+      unsigned long long key = 0ull;
+      const int o = ls.off[ch];
+      if (o) {
+        const int x = c.x + (int)(signed char)(o >> 16), y = c.y + (int)(signed char)(o >> 8), z = c.z + (int)(signed char)o;
+        if (coord_ok(x, y, z)) key = pack_key(x, y, z, 0);
+      }
+      warp_scan_cells<K>(mv, key, qx, qy, qz, max_sq, false, wl);
+    }
+  }
+  return list_select<K>(wl, out);
 }
 
 // Exact k-NN with d2 <= max_sq by Chebyshev shells around the query's voxel; stops as soon as the
 // K-th best distance is below the lower bound of every unseen shell.
 template <int K>
-__device__ __forceinline__ void knn_exact(const MapView& mv, float qx, float qy, float qz, float max_sq, TopK<K>& tk) {
+__device__ __forceinline__ int knn_exact_warp(const MapView& mv, float qx, float qy, float qz, float max_sq, WarpList& wl,
+                                              Neighbor& out) {
+  const int lane = threadIdx.x & 31;
   const int3 c = pos2grid(qx, qy, qz, mv.inv_res);
   const int rmax = (int)ceilf(sqrtf(max_sq) * mv.inv_res) + 1;
-#pragma unroll 1
+  wl.n = 0;
+  int nf = 0;
+  out.d2 = -1.0f; out.id = -1; out.loc = 0;
   for (int r = 0; r <= rmax; r++) {
-    if (r >= 1 && tk.n == K) {
+    if (r >= 1 && nf == K) {
       // a point in shell >= r is at least (r-1)*res away along one axis (voxels are centred on
       // integer multiples of res, the query is anywhere inside its own voxel)
+      const float kth = __shfl_sync(kFull, out.d2, K - 1);
       const float lo = (float)(r - 1) * mv.res * (1.0f - 1e-5f);
-      if (tk.d[K - 1] < lo * lo) break;
+      if (kth < lo * lo) break;
     }
     const int side = 2 * r + 1;
     const int ncell = side * side * side;
-#pragma unroll 1
-    for (int t = 0; t < ncell; t++) {
-      const int i = t / (side * side) - r, j = (t / side) % side - r, l = t % side - r;
-      if (max(max(abs(i), abs(j)), abs(l)) != r) continue;
-      const int x = c.x + i, y = c.y + j, z = c.z + l;
-      if (!coord_ok(x, y, z)) continue;
-      const unsigned long long key = pack_key(x, y, z, 0);
-      scan_voxel(mv, key, hash_key(key) & mv.mask, tk, qx, qy, qz, max_sq, true);
+    for (int t0 = 0; t0 < ncell; t0 += 32) {
+      if (wl.n > kCandCap - 7 * 32) list_compress<K>(wl);
+      const int t = t0 + lane;
+      unsigned long long key = 0ull;
+      if (t < ncell) {
+        const int i = t / (side * side) - r, j = (t / side) % side - r, l = t % side - r;
+        if (max(max(abs(i), abs(j)), abs(l)) == r) {
+          const int x = c.x + i, y = c.y + j, z = c.z + l;
+          if (coord_ok(x, y, z)) key = pack_key(x, y, z, 0);
+        }
+      }
+      if (__any_sync(kFull, key != 0ull)) warp_scan_cells<K>(mv, key, qx, qy, qz, max_sq, true, wl);
     }
+    // top-K so far (needed for the stopping rule); the list is cut back to those K
+    nf = list_select<K>(wl, out);
+    if (lane < nf) { wl.d[lane] = __float_as_uint(out.d2); wl.id[lane] = out.id; wl.loc[lane] = out.loc; }
+    wl.n = nf;
+    __syncwarp();
   }
+  return nf;
 }
 
+// `ls` = lane_stencil(stencil_slot(stencil_type)), hoisted out of the caller's query loop
 template <int K>
-__device__ __forceinline__ void knn_search(const MapView& mv, int stencil_type, float qx, float qy, float qz, float max_sq,
-                                           TopK<K>& tk) {
-  tk.init();
-  if (stencil_type == LSD_STENCIL_EXACT) knn_exact<K>(mv, qx, qy, qz, max_sq, tk);
-  else knn_stencil<K>(mv, stencil_slot(stencil_type), qx, qy, qz, max_sq, tk);
+__device__ __forceinline__ int knn_search_warp(const MapView& mv, int stencil_type, const LaneStencil& ls, float qx, float qy,
+                                               float qz, float max_sq, WarpList& wl, Neighbor& out) {
+  if (stencil_type == LSD_STENCIL_EXACT) return knn_exact_warp<K>(mv, qx, qy, qz, max_sq, wl, out);
+  return knn_stencil_warp<K>(mv, ls, qx, qy, qz, max_sq, wl, out);
 }
 
 // coordinates of a stored neighbour from its location code

@@ -22,7 +22,8 @@
 namespace lsd {
 
 constexpr int kNV = 32;        // reduction slots per block (29 used + n)
-constexpr int kLioBlock = 128;
+constexpr int kLioBlock = 256;
+constexpr int kLioMaxGrid = 296;  // 2 blocks per SM: the final fold reads <= 296 x 32 partials
 
 struct LioPose { double R[9], t[3], RL[9], tL[3]; };
 
@@ -158,71 +159,130 @@ __device__ __forceinline__ bool esti_plane_dev(const float (&px)[5], const float
   return ok;
 }
 
-// ---------------------------------------------------------------- block / grid reduction
-// vals[NV] per thread -> partials[block][kNV]; the last block folds all partials in a fixed order.
+// ---------------------------------------------------------------- grid reduction
+// Result buffer layout (doubles): [0..20] upper triangle of the 6x6 h_x^T h_x, [21..26] h_x^T h,
+// [27] sum |res|, [28] n_eff, [29] feats_down_size, [48..53] degeneracy sums.
+constexpr int kResDegen = 48, kResDoubles = 64;
+
+// symmetric 3x3 eigen-decomposition (cyclic Jacobi); V columns = eigenvectors.  Stands in for
+// Eigen::SelfAdjointEigenSolver at laserMapping.cpp:941; only |v . n| and V diag(mask) V^T are used,
+// both independent of eigenvector sign and order.
+static void eig3_sym(const double* Ain, double* V, double* w) {
+  double A[9];
+  for (int i = 0; i < 9; i++) { A[i] = Ain[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; sweep++) {
+    if (fabs(A[1]) + fabs(A[2]) + fabs(A[5]) <= 1e-18 * (fabs(A[0]) + fabs(A[4]) + fabs(A[8]))) break;
+    for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+      const double apq = A[3 * p + q];
+      if (fabs(apq) < 1e-300) continue;
+      const double th = (A[3 * q + q] - A[3 * p + p]) / (2.0 * apq);
+      const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+      for (int k = 0; k < 3; k++) { double x = A[3 * k + p], y = A[3 * k + q]; A[3 * k + p] = c * x - sn * y; A[3 * k + q] = sn * x + c * y; }
+      for (int k = 0; k < 3; k++) { double x = A[3 * p + k], y = A[3 * q + k]; A[3 * p + k] = c * x - sn * y; A[3 * q + k] = sn * x + c * y; }
+      for (int k = 0; k < 3; k++) { double x = V[3 * k + p], y = V[3 * k + q]; V[3 * k + p] = c * x - sn * y; V[3 * k + q] = sn * x + c * y; }
+    }
+  }
+  w[0] = A[0]; w[1] = A[4]; w[2] = A[8];
+}
+
+// Called by every thread of every block after the block has written partials[blockIdx][0..NV).
+// The last block to arrive folds all partials in a fixed order (slices of blocks, ascending) into
+// result[0..NV) — bit-reproducible for a given grid size.
 template <int NV>
-__device__ __forceinline__ void grid_reduce(double (&vals)[NV], double* __restrict__ partials, unsigned* __restrict__ done,
-                                            double* __restrict__ result, int n_extra, double extra) {
-  __shared__ double sm[kLioBlock / 32][kNV];
+__device__ __forceinline__ void grid_finalize(double* __restrict__ partials, unsigned* __restrict__ done,
+                                              double* __restrict__ result, int res_off, int n_extra_slot, double extra) {
+  __shared__ double sm_fin[8][kNV];
   __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int j = 0; j < NV; j++) {
-    const double v = warp_sum(vals[j]);
-    if (lane == 0) sm[warp][j] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < NV) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLioBlock / 32; w++) s += sm[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * kNV + threadIdx.x] = s;
-  }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(done, 1u);
-    is_last = ticket == gridDim.x - 1;
-  }
+  if (threadIdx.x == 0) is_last = atomicAdd(done, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // 4 slices x 32 value lanes, each slice walks its blocks in ascending order
+  const int slices = blockDim.x >> 5;
   const int j = threadIdx.x & 31, slice = threadIdx.x >> 5;
   double s = 0.0;
-  if (j < NV)
-    for (int b = slice; b < (int)gridDim.x; b += kLioBlock / 32) s += __ldcg(partials + (size_t)b * kNV + j);
-  __syncthreads();
-  sm[slice][j] = s;
+  if (j < NV) {  // ascending block order per slice, 8 independent loads in flight
+    const int G = (int)gridDim.x;
+    int b = slice;
+    for (; b + 7 * slices < G; b += 8 * slices) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldcg(partials + (size_t)(b + u * slices) * kNV + j);
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += v[u];
+    }
+    for (; b < G; b += slices) s += __ldcg(partials + (size_t)b * kNV + j);
+  }
+  sm_fin[slice][j] = s;
   __syncthreads();
   if (threadIdx.x < NV) {
     double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLioBlock / 32; w++) t += sm[w][threadIdx.x];
-    result[threadIdx.x] = t;
+    for (int w = 0; w < slices; w++) t += sm_fin[w][threadIdx.x];
+    result[res_off + threadIdx.x] = t;
+    sm_fin[0][threadIdx.x] = t;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    result[n_extra] = extra;
+    if (n_extra_slot >= 0) result[n_extra_slot] = extra;
     *done = 0u;
   }
 }
 
-// ---------------------------------------------------------------- K3+K4+K5: one h-model evaluation
-template <bool SEARCH>
-__global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(MapView mv, int stencil, const float4* __restrict__ body,
-                                                               const int* __restrict__ n_ptr, int cap, LioPose ps,
-                                                               float4* __restrict__ near, int* __restrict__ near_cnt,
-                                                               unsigned char* __restrict__ selected,
-                                                               float4* __restrict__ plane, float4* __restrict__ world,
-                                                               double* __restrict__ partials, unsigned* __restrict__ done,
-                                                               double* __restrict__ result) {
-  const int n_true = *n_ptr;
-  const int n = min(n_true, cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double vals[29];
+// thread-per-item kernels: warp-shuffle reduce vals[NV] into partials[block]
+template <int NV>
+__device__ __forceinline__ void block_partials(double (&vals)[NV], double* __restrict__ partials) {
+  __shared__ double sm_bp[8][kNV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 29; j++) vals[j] = 0.0;
-  if (i < n) {
+  for (int j = 0; j < NV; j++) {
+    const double v = warp_sum(vals[j]);
+    if (lane == 0) sm_bp[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sm_bp[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * kNV + threadIdx.x] = s;
+  }
+}
+
+// Jacobian row (laserMapping.cpp:903-932, extrinsic_est_en == false) and residual for one point
+struct RowH { double row[6]; double h; };
+__device__ __forceinline__ RowH make_row(const LioPose& ps, double lx, double ly, double lz, const float (&pabcd)[4], float pd2) {
+  RowH r;
+  const double nx = pabcd[0], ny = pabcd[1], nz = pabcd[2];
+  const double cx = ps.R[0] * nx + ps.R[3] * ny + ps.R[6] * nz;  // R^T n
+  const double cy = ps.R[1] * nx + ps.R[4] * ny + ps.R[7] * nz;
+  const double cz = ps.R[2] * nx + ps.R[5] * ny + ps.R[8] * nz;
+  r.row[0] = nx; r.row[1] = ny; r.row[2] = nz;
+  r.row[3] = ly * cz - lz * cy; r.row[4] = lz * cx - lx * cz; r.row[5] = lx * cy - ly * cx;
+  r.h = -(double)pd2;
+  return r;
+}
+
+__constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},{2,2},{2,3},{2,4},{2,5},
+                                           {3,3},{3,4},{3,5},{4,4},{4,5},{5,5}};
+
+// ---------------------------------------------------------------- K3: neighbour search for the scan
+// One warp per downsampled point (knn.cuh): body -> world, 5-NN in the hash-voxel map, neighbours
+// written as Nearest_Points[i] (laserMapping.cpp:842-852).  Kept separate from the plane fit: the
+// search wants one warp per query (19 probes in flight), the plane fit one thread per query.
+constexpr int kHmWarps = 8;
+__global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, int stencil, const float4* __restrict__ body,
+                                                                const int* __restrict__ n_ptr, int cap, LioPose ps,
+                                                                float4* __restrict__ near, int* __restrict__ near_cnt) {
+  __shared__ __align__(16) unsigned char s_list[kHmWarps * kWarpListBytes];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = min(*n_ptr, cap);
+  WarpList wl;
+  wl.d = reinterpret_cast<unsigned*>(s_list + warp * kWarpListBytes);
+  wl.id = reinterpret_cast<int*>(wl.d + kCandCap);
+  wl.loc = reinterpret_cast<unsigned*>(wl.id + kCandCap);
+  wl.n = 0;
+  const LaneStencil ls = lane_stencil(stencil_slot(stencil));
+  for (int i = blockIdx.x * kHmWarps + warp; i < n; i += gridDim.x * kHmWarps) {
     const float4 pb = __ldg(body + i);
     // body -> world in double (laserMapping.cpp:831-836), stored as fp32 like PointType
     const double bx = pb.x, by = pb.y, bz = pb.z;
@@ -232,83 +292,110 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(MapView mv, int s
     const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
     const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
     const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
-    world[i] = make_float4(wx, wy, wz, pb.w);
-    float px[5], py[5], pz[5];
-    bool sel;
-    if (SEARCH) {
-      TopK<5> tk;
-      knn_search<5>(mv, stencil, wx, wy, wz, 5.0f, tk);
+    Neighbor nb;
+    const int nf = knn_search_warp<5>(mv, stencil, ls, wx, wy, wz, 5.0f, wl, nb);
+    float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (lane < nf) q = load_loc(mv, nb.loc);
+    if (lane < 5) near[(size_t)i * 5 + lane] = q;
+    if (lane == 0) near_cnt[i] = nf;
+  }
+}
+
+// ---------------------------------------------------------------- K4+K5: plane fit + residual/Jacobian + reduction
+// One thread per downsampled point.  FIT: first evaluation after a search — fit the plane through
+// Nearest_Points[i] and cache it; !FIT: iterations with ekfom_data.converge == false
+// (laserMapping.cpp:842) keep Nearest_Points and the reference refits the same plane from the same
+// 5 points, so the cached plane is exact.
+template <bool FIT>
+__global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __restrict__ body, const int* __restrict__ n_ptr,
+                                                               int cap, LioPose ps, const float4* __restrict__ near,
+                                                               const int* __restrict__ near_cnt, unsigned char* __restrict__ selected,
+                                                               float4* __restrict__ pabcd_io, unsigned char* __restrict__ plane_ok,
+                                                               float4* __restrict__ plane, float4* __restrict__ world,
+                                                               double* __restrict__ partials, unsigned* __restrict__ done,
+                                                               double* __restrict__ result) {
+  const int n_true = *n_ptr;
+  const int n = min(n_true, cap);
+  double vals[29];
 #pragma unroll
-      for (int j = 0; j < 5; j++) {
-        float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (j < tk.n) q = load_loc(mv, tk.loc[j]);
-        px[j] = q.x; py[j] = q.y; pz[j] = q.z;
-        near[(size_t)i * 5 + j] = q;
-      }
-      near_cnt[i] = tk.n;
-      sel = tk.n >= 5;  // laserMapping.cpp:847,850
-    } else {
-      sel = selected[i] != 0;
-      if (sel) {
+  for (int j = 0; j < 29; j++) vals[j] = 0.0;
+#pragma unroll 1
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 pb = __ldg(body + i);
+    const double bx = pb.x, by = pb.y, bz = pb.z;
+    const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+    const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+    const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+    const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
+    const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
+    const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+    world[i] = make_float4(wx, wy, wz, pb.w);
+    float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
+    bool ok = false;
+    if (FIT) {
+      if (near_cnt[i] >= 5) {  // point_selected_surf, laserMapping.cpp:847,850
+        float px[5], py[5], pz[5];
 #pragma unroll
         for (int j = 0; j < 5; j++) { const float4 q = near[(size_t)i * 5 + j]; px[j] = q.x; py[j] = q.y; pz[j] = q.z; }
+        ok = esti_plane_dev(px, py, pz, 0.1f, pabcd);
       }
+      pabcd_io[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
+      plane_ok[i] = ok ? 1 : 0;
+    } else if (selected[i] && plane_ok[i]) {
+      const float4 pl = pabcd_io[i];
+      pabcd[0] = pl.x; pabcd[1] = pl.y; pabcd[2] = pl.z; pabcd[3] = pl.w;
+      ok = true;
     }
     bool keep = false;
-    if (sel) {
-      float pabcd[4];
-      if (esti_plane_dev(px, py, pz, 0.1f, pabcd)) {
-        const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];
-        const double s = 1 - 0.9 * fabs((double)pd2) / sqrt(sqrt(bx * bx + by * by + bz * bz));  // :861
-        if ((float)s > 0.9) {
-          keep = true;
-          plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
-          // Jacobian row (laserMapping.cpp:903-932, extrinsic_est_en == false)
-          const double nx = pabcd[0], ny = pabcd[1], nz = pabcd[2];
-          const double cx = ps.R[0] * nx + ps.R[3] * ny + ps.R[6] * nz;  // R^T n
-          const double cy = ps.R[1] * nx + ps.R[4] * ny + ps.R[7] * nz;
-          const double cz = ps.R[2] * nx + ps.R[5] * ny + ps.R[8] * nz;
-          const double row[6] = {nx, ny, nz, ly * cz - lz * cy, lz * cx - lx * cz, lx * cy - ly * cx};
-          const double h = -(double)pd2;
-          int q = 0;
+    if (ok) {
+      const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];
+      const double s = 1 - 0.9 * fabs((double)pd2) / sqrt(sqrt(bx * bx + by * by + bz * bz));  // laserMapping.cpp:861
+      if ((float)s > 0.9) {
+        keep = true;
+        plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
+        const RowH r = make_row(ps, lx, ly, lz, pabcd, pd2);
+        int q = 0;
 #pragma unroll
-          for (int a = 0; a < 6; a++) {
+        for (int a = 0; a < 6; a++) {
 #pragma unroll
-            for (int c = a; c < 6; c++) vals[q++] = row[a] * row[c];
-          }
-#pragma unroll
-          for (int a = 0; a < 6; a++) vals[21 + a] = row[a] * h;
-          vals[27] = (double)fabsf(pd2);  // res_last
-          vals[28] = 1.0;
+          for (int c = a; c < 6; c++) vals[q++] += r.row[a] * r.row[c];
         }
+#pragma unroll
+        for (int a = 0; a < 6; a++) vals[21 + a] += r.row[a] * r.h;
+        vals[27] += (double)fabsf(pd2);  // res_last
+        vals[28] += 1.0;
       }
     }
     selected[i] = keep ? 1 : 0;
   }
-  grid_reduce<29>(vals, partials, done, result, 29, (double)n_true);
+  block_partials<29>(vals, partials);
+  grid_finalize<29>(partials, done, result, 0, 29, (double)n_true);
 }
 
 // ---------------------------------------------------------------- degeneracy sums (laserMapping.cpp:946-970)
+// Only launched when the host cannot certify non-degeneracy from the eigenvalues (lio_linearize).
 struct Eig3 { double V[9]; };  // columns = eigenvectors
-__global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restrict__ n_ptr, int cap, const unsigned char* __restrict__ selected,
-                                                              const float4* __restrict__ plane, Eig3 e,
-                                                              double* __restrict__ partials, unsigned* __restrict__ done,
-                                                              double* __restrict__ result) {
+__global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restrict__ n_ptr, int cap,
+                                                              const unsigned char* __restrict__ selected,
+                                                              const float4* __restrict__ plane, Eig3 e, double* __restrict__ partials,
+                                                              unsigned* __restrict__ done, double* __restrict__ result) {
   const int n = min(*n_ptr, cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* V = e.V;
   double vals[6] = {0, 0, 0, 0, 0, 0};
-  if (i < n && selected[i]) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!selected[i]) continue;
     const float4 p = plane[i];
     const double r0 = p.x, r1 = p.y, r2 = p.z;
     const double nn = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const float dotp = (float)fabs((r0 / nn) * e.V[k] + (r1 / nn) * e.V[3 + k] + (r2 / nn) * e.V[6 + k]);
-      if (dotp > 0.1736) vals[k] = dotp;
-      if (dotp > 0.7070) vals[3 + k] = dotp;
+      const float dotp = (float)fabs((r0 / nn) * V[k] + (r1 / nn) * V[3 + k] + (r2 / nn) * V[6 + k]);
+      if (dotp > 0.1736) vals[k] += dotp;
+      if (dotp > 0.7070) vals[3 + k] += dotp;
     }
   }
-  grid_reduce<6>(vals, partials, done, result, 6, 0.0);
+  block_partials<6>(vals, partials);
+  grid_finalize<6>(partials, done, result, kResDegen, -1, 0.0);
 }
 
 // ---------------------------------------------------------------- map_incremental (laserMapping.cpp:523-576)
@@ -371,27 +458,6 @@ static void pose_from_state(const double* x, LioPose* ps) {
   for (int i = 0; i < 3; i++) { ps->t[i] = x[eskf::S_POS + i]; ps->tL[i] = x[eskf::S_OFFT + i]; }
 }
 
-// symmetric 3x3 eigen-decomposition (cyclic Jacobi); V columns = eigenvectors.  Stands in for
-// Eigen::SelfAdjointEigenSolver at laserMapping.cpp:941; only |v . n| and V diag(mask) V^T are used.
-static void eig3_sym(const double* Ain, double* V) {
-  double A[9];
-  memcpy(A, Ain, sizeof(A));
-  for (int i = 0; i < 9; i++) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 60; sweep++) {
-    if (fabs(A[1]) + fabs(A[2]) + fabs(A[5]) < 1e-300) break;
-    for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
-      const double apq = A[3 * p + q];
-      if (fabs(apq) < 1e-300) continue;
-      const double th = (A[3 * q + q] - A[3 * p + p]) / (2.0 * apq);
-      const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-      for (int k = 0; k < 3; k++) { double a = A[3 * k + p], b = A[3 * k + q]; A[3 * k + p] = c * a - s * b; A[3 * k + q] = s * a + c * b; }
-      for (int k = 0; k < 3; k++) { double a = A[3 * p + k], b = A[3 * q + k]; A[3 * p + k] = c * a - s * b; A[3 * q + k] = s * a + c * b; }
-      for (int k = 0; k < 3; k++) { double a = V[3 * k + p], b = V[3 * k + q]; V[3 * k + p] = c * a - s * b; V[3 * k + q] = s * a + c * b; }
-    }
-  }
-}
-
 struct ProfScope {  // CUDA-event timing of one launch group on the LIO stream (profile mode only)
   lsd_lio* l; int kind; bool on;
   ProfScope(lsd_lio* l_, int kind_) : l(l_), kind(kind_), on(l_->profile != 0) { if (on) cudaEventRecord(l->pev[0], l->stream); }
@@ -406,26 +472,31 @@ struct ProfScope {  // CUDA-event timing of one launch group on the LIO stream (
   }
 };
 
-static int grid_for(int n) { return std::max(1, (n + kLioBlock - 1) / kLioBlock); }
+static int grid_for(int n) { return std::max(1, std::min((n + kLioBlock - 1) / kLioBlock, kLioMaxGrid)); }
 
 // One h_share_model_geometric evaluation on the loaded scan.  Fills HTH6/HTh6 (after the
-// degeneracy projection when it triggers).
+// degeneracy projection when it triggers).  One host synchronisation per evaluation.
 lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH6, double* HTh6, double* res_sum,
                            int* n_eff, int* degenerate) {
   LioPose ps;
   pose_from_state(x, &ps);
   cudaStream_t st = l->stream;
-  const int nb = grid_for(l->n_bound);
   const int stencil = l->p.knn_mode_exact ? LSD_STENCIL_EXACT : l->p.ivox_nearby;
   ProfScope prof(l, search ? 0 : 1);
-  if (search)
-    lio_hmodel_kernel<true><<<nb, kLioBlock, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                                                      l->d_selected, l->d_plane, l->d_world, l->d_partials, l->d_done, l->d_result);
-  else
-    lio_hmodel_kernel<false><<<nb, kLioBlock, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                                                       l->d_selected, l->d_plane, l->d_world, l->d_partials, l->d_done, l->d_result);
+  if (search) {
+    const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
+    lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt);
+    lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                                                                       l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+                                                                       l->d_partials, l->d_done, l->d_result);
+    l->launches += 2;
+  } else {
+    lio_hmodel_kernel<false><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                                                                        l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+                                                                        l->d_partials, l->d_done, l->d_result);
+    l->launches++;
+  }
   LSD_CUDA(cudaGetLastError());
-  l->launches++;
   prof.stop();
   LSD_CUDA(cudaMemcpyAsync(l->h_result, l->d_result, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
   LSD_CUDA(cudaStreamSynchronize(st));
@@ -441,35 +512,45 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   *degenerate = 0;
   if (*n_eff < 1) return LSD_NO_EFFECTIVE_POINTS;
   if (l->p.degenerate_detect_en) {
-    double H3[9], V[9];
+    // Degeneracy detection (laserMapping.cpp:934-980).  For an eigenvector v_k of the 3x3 normal
+    // block, sum_j (n_j . v_k)^2 = lambda_k because the rows are unit normals, hence
+    //   local_contri_k = sum_{|n.v| > 0.1736} |n.v| >= lambda_k - 0.1736^2 * n_eff.
+    // When that bound already clears the 250 threshold for every k the scan is certified
+    // non-degenerate without touching the points again; otherwise the exact sums are computed.
+    double H3[9], V[9], w[3];
     for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) H3[3 * a + c] = HTH6[6 * a + c];
-    Eig3 e;
-    eig3_sym(H3, V);
-    memcpy(e.V, V, sizeof(V));
-    lio_degen_kernel<<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_n, l->p.max_points, l->d_selected, l->d_plane, e, l->d_partials, l->d_done, l->d_result2);
-    LSD_CUDA(cudaGetLastError());
-    l->launches++;
-    LSD_CUDA(cudaMemcpyAsync(l->h_result2, l->d_result2, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    LSD_CUDA(cudaStreamSynchronize(st));
-    int mask[3] = {1, 1, 1};
-    bool deg = false;
-    for (int k = 0; k < 3; k++)
-      if ((float)l->h_result2[k] < 250.0f && (float)l->h_result2[3 + k] < 50.0f) { mask[k] = 0; deg = true; }
-    if (deg) {
-      // rows n -> Pm n with Pm = V diag(mask) V^T  (mat_p, laserMapping.cpp:975-978):
-      // HTH <- B HTH B^T, HTh <- B HTh with B = blockdiag(Pm, I3)
-      double Pm[9] = {0};
-      for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) if (mask[k]) Pm[3 * a + c] += V[3 * a + k] * V[3 * c + k];
-      double B[36] = {0}, T[36];
-      for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) B[6 * a + c] = Pm[3 * a + c];
-      for (int a = 3; a < 6; a++) B[6 * a + a] = 1.0;
-      for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { double s = 0; for (int k = 0; k < 6; k++) s += B[6 * a + k] * HTH6[6 * k + c]; T[6 * a + c] = s; }
-      for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { double s = 0; for (int k = 0; k < 6; k++) s += T[6 * a + k] * B[6 * c + k]; HTH6[6 * a + c] = s; }
-      double h2[6];
-      for (int a = 0; a < 6; a++) { double s = 0; for (int k = 0; k < 6; k++) s += B[6 * a + k] * HTh6[k]; h2[a] = s; }
-      memcpy(HTh6, h2, sizeof(h2));
-      memcpy(l->last_Pm, Pm, sizeof(Pm));
-      *degenerate = 1;
+    eig3_sym(H3, V, w);
+    const double wmin = std::min(w[0], std::min(w[1], w[2]));
+    if (wmin - 0.0302 * (double)*n_eff < 260.0) {
+      Eig3 e;
+      memcpy(e.V, V, sizeof(V));
+      lio_degen_kernel<<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_n, l->p.max_points, l->d_selected, l->d_plane, e, l->d_partials,
+                                                                  l->d_done, l->d_result);
+      LSD_CUDA(cudaGetLastError());
+      l->launches++;
+      LSD_CUDA(cudaMemcpyAsync(l->h_result + kResDegen, l->d_result + kResDegen, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      LSD_CUDA(cudaStreamSynchronize(st));
+      const double* dg = l->h_result + kResDegen;
+      int mask[3] = {1, 1, 1};
+      bool deg = false;
+      for (int k = 0; k < 3; k++)
+        if ((float)dg[k] < 250.0f && (float)dg[3 + k] < 50.0f) { mask[k] = 0; deg = true; }
+      if (deg) {
+        // rows n -> Pm n with Pm = V diag(mask) V^T  (mat_p, laserMapping.cpp:975-978):
+        // HTH <- B HTH B^T, HTh <- B HTh with B = blockdiag(Pm, I3)
+        double Pm[9] = {0};
+        for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) if (mask[k]) Pm[3 * a + c] += V[3 * a + k] * V[3 * c + k];
+        double B[36] = {0}, T[36];
+        for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) B[6 * a + c] = Pm[3 * a + c];
+        for (int a = 3; a < 6; a++) B[6 * a + a] = 1.0;
+        for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { double sum = 0; for (int k = 0; k < 6; k++) sum += B[6 * a + k] * HTH6[6 * k + c]; T[6 * a + c] = sum; }
+        for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) { double sum = 0; for (int k = 0; k < 6; k++) sum += T[6 * a + k] * B[6 * c + k]; HTH6[6 * a + c] = sum; }
+        double h2[6];
+        for (int a = 0; a < 6; a++) { double sum = 0; for (int k = 0; k < 6; k++) sum += B[6 * a + k] * HTh6[k]; h2[a] = sum; }
+        memcpy(HTh6, h2, sizeof(h2));
+        memcpy(l->last_Pm, Pm, sizeof(Pm));
+        *degenerate = 1;
+      }
     }
   }
   return LSD_OK;
@@ -524,7 +605,7 @@ lsd_status_t lio_update(lsd_lio* l, double* x, double* P, lsd_lio_info_t* info) 
     for (int a = 0; a < 6; a++) { for (int c = 0; c < 6; c++) out->HTH[15 * a + c] = HTH6[6 * a + c]; out->HTh[a] = HTh6[a]; }
     if (ne < eskf::N) { lsd_status_t f = fetch_rows(l, xs, dg != 0, &out->h_x, &out->h); if (f < 0) { err = f; out->valid = false; } }
   };
-  eskf::UpdateResult r = eskf::update_iterated(x, P, hm, l->p.laser_point_cov, l->p.max_iterations, l->p.converge_eps);
+  eskf::UpdateResult r = eskf::update_iterated(x, P, hm, l->p.laser_point_cov, l->p.max_iterations, l->p.converge_eps, l->p.eskf_literal != 0);
   if (info) {
     info->iterations = r.evaluations; info->n_eff = last_neff; info->degenerate = last_deg; info->res_mean = last_res;
     info->converged = r.returned_converged ? 1 : 0; info->n_down = l->n_down;
@@ -561,7 +642,7 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
     lsd_status_t s = vg_run(l->vg, d_scan, n, l->p.filter_size_surf, l->d_body, l->d_n, st);
     if (s) return s;
     prof.stop();
-    l->launches += 7;
+    l->launches += 5;
     l->n_bound = std::min(n, l->p.max_points);
     l->n_down = -1;  // learned with the first reduction (or lsd_lio_load_scan's explicit read)
   } else {
@@ -642,6 +723,7 @@ void lsd_lio_default_params(lsd_lio_params_t* p) {
   p->converge_eps = 0.001;       // laserMapping.cpp:1114-1116
   p->degenerate_detect_en = 1;   // laserMapping.cpp:83
   p->knn_mode_exact = 0;
+  p->eskf_literal = 0;
 }
 
 lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
@@ -657,6 +739,7 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   if (s) { lsd_map_destroy(l->map); delete l; return s; }
   const size_t mp = (size_t)p->max_points;
   const size_t max_blocks = (size_t)grid_for(p->max_points) + 1;
+  l->max_search_blocks = 148 * 6;
   cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);
   auto A = [&](void** ptr, size_t b) { if (e == cudaSuccess) e = cudaMalloc(ptr, b); if (e == cudaSuccess) e = cudaMemset(*ptr, 0, b); };
   A((void**)&l->d_scan, (size_t)p->max_scan_points * 16);
@@ -667,14 +750,14 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   A((void**)&l->d_selected, mp);
   A((void**)&l->d_flags, mp);
   A((void**)&l->d_plane, mp * 16);
+  A((void**)&l->d_pabcd, mp * 16);
+  A((void**)&l->d_plane_ok, mp);
   A((void**)&l->d_world, mp * 16);
   A((void**)&l->d_partials, max_blocks * kNV * 8);
   A((void**)&l->d_done, 64);
   A((void**)&l->d_added, 64);
-  A((void**)&l->d_result, 64 * 8);
-  A((void**)&l->d_result2, 64 * 8);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_result, 64 * 8);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_result2, 64 * 8);
+  A((void**)&l->d_result, kResDoubles * 8);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_result, kResDoubles * 8);
   if (e == cudaSuccess) e = cudaEventCreate(&l->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&l->ev1);
   if (e == cudaSuccess) e = cudaEventCreate(&l->pev[0]);
@@ -696,9 +779,9 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   cudaSetDevice(l->device);
   if (l->stream) cudaStreamSynchronize(l->stream);
   void* ptrs[] = {l->d_scan, l->d_body, l->d_n, l->d_near, l->d_near_cnt, l->d_selected, l->d_flags, l->d_plane, l->d_world,
-                  l->d_partials, l->d_done, l->d_added, l->d_result, l->d_result2};
+                  l->d_partials, l->d_done, l->d_added, l->d_result, l->d_pabcd, l->d_plane_ok};
   for (void* p : ptrs) cudaFree(p);
-  cudaFreeHost(l->h_result); cudaFreeHost(l->h_result2);
+  cudaFreeHost(l->h_result);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->pev[0]) cudaEventDestroy(l->pev[0]);
@@ -828,5 +911,23 @@ lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* s
 void lsd_lio_init_cov(double* P529) { if (P529) eskf::init_cov(P529); }
 void lsd_state_boxplus(double* state26_inout, const double* delta23) { if (state26_inout && delta23) eskf::boxplus(state26_inout, delta23); }
 void lsd_state_boxminus(const double* a26, const double* b26, double* out23) { if (a26 && b26 && out23) eskf::boxminus(a26, b26, out23); }
+
+int lsd_eskf_update_table(double* state26_inout, double* P529_inout, const double* HTH36, const double* HTh6, const int* n_eff,
+                          int n_table, double R, int max_iterations, double eps, int literal) {
+  if (!state26_inout || !P529_inout || !HTH36 || !HTh6 || !n_eff || n_table < 1) return LSD_ERR_INVALID;
+  int e = 0;
+  auto hm = [&](const double*, bool, eskf::HModel* out) {
+    const int k = e < n_table ? e : n_table - 1;
+    e++;
+    out->n = n_eff[k];
+    out->valid = n_eff[k] >= 1;
+    if (!out->valid) return;
+    memset(out->HTH, 0, sizeof(out->HTH)); memset(out->HTh, 0, sizeof(out->HTh));
+    for (int a = 0; a < 6; a++) { for (int c = 0; c < 6; c++) out->HTH[15 * a + c] = HTH36[36 * k + 6 * a + c]; out->HTh[a] = HTh6[6 * k + a]; }
+    if (out->n < eskf::N) { out->n = eskf::N; }  // the table form carries no h_x rows: small-n branch not exercised here
+  };
+  eskf::UpdateResult r = eskf::update_iterated(state26_inout, P529_inout, hm, R, max_iterations, eps, literal != 0);
+  return r.evaluations;
+}
 
 }  // extern "C"

@@ -21,12 +21,15 @@ struct lsd_lio {
   unsigned char* d_selected = nullptr;  // point_selected_surf
   unsigned char* d_flags = nullptr;     // map_incremental decision per point
   float4* d_plane = nullptr;    // normvec: (normal, pd2)
+  float4* d_pabcd = nullptr;    // cached plane (a, b, c, d) of the last neighbour search
+  unsigned char* d_plane_ok = nullptr;  // esti_plane accepted the 5 neighbours
   float4* d_world = nullptr;    // feats_down_world
   double* d_partials = nullptr;
   unsigned* d_done = nullptr;
   unsigned* d_added = nullptr;
-  double *d_result = nullptr, *d_result2 = nullptr;
-  double *h_result = nullptr, *h_result2 = nullptr;  // pinned
+  double* d_result = nullptr;
+  double* h_result = nullptr;   // pinned
+  int max_search_blocks = 888;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_bound = 1;   // launch bound for per-point kernels (>= true feats_down_size)
   int n_down = -1;   // feats_down_size once known on the host

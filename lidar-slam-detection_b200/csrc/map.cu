@@ -114,21 +114,29 @@ __global__ void __launch_bounds__(256) map_insert_kernel(MapView mv, const float
 }
 
 // ------------------------------------------------------------------ K3: batched k-NN query
+constexpr int kKnnWarps = 8;
 template <int K>
-__global__ void __launch_bounds__(128) knn_query_kernel(MapView mv, const float4* __restrict__ q, int nq, float max_sq,
-                                                        int stencil, int* __restrict__ out_idx,
-                                                        float* __restrict__ out_d2, int* __restrict__ out_cnt) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  float4 p = __ldg(q + i);
-  TopK<K> tk;
-  knn_search<K>(mv, stencil, p.x, p.y, p.z, max_sq, tk);
-#pragma unroll
-  for (int j = 0; j < K; j++) {
-    out_idx[(size_t)i * K + j] = j < tk.n ? tk.id[j] : -1;
-    out_d2[(size_t)i * K + j] = j < tk.n ? tk.d[j] : -1.0f;
+__global__ void __launch_bounds__(kKnnWarps * 32, 4) knn_query_kernel(MapView mv, const float4* __restrict__ q, int nq, float max_sq,
+                                                                   int stencil, int* __restrict__ out_idx,
+                                                                   float* __restrict__ out_d2, int* __restrict__ out_cnt) {
+  __shared__ __align__(16) unsigned char s_list[kKnnWarps * kWarpListBytes];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpList wl;
+  wl.d = reinterpret_cast<unsigned*>(s_list + warp * kWarpListBytes);
+  wl.id = reinterpret_cast<int*>(wl.d + kCandCap);
+  wl.loc = reinterpret_cast<unsigned*>(wl.id + kCandCap);
+  wl.n = 0;
+  const LaneStencil ls = lane_stencil(stencil_slot(stencil));
+  for (int i = blockIdx.x * kKnnWarps + warp; i < nq; i += gridDim.x * kKnnWarps) {
+    const float4 p = __ldg(q + i);
+    Neighbor nb;
+    const int nf = knn_search_warp<K>(mv, stencil, ls, p.x, p.y, p.z, max_sq, wl, nb);
+    if (lane < K) {
+      out_idx[(size_t)i * K + lane] = lane < nf ? nb.id : -1;
+      out_d2[(size_t)i * K + lane] = lane < nf ? nb.d2 : -1.0f;
+    }
+    if (lane == 0) out_cnt[i] = nf;
   }
-  out_cnt[i] = tk.n;
 }
 
 lsd_status_t launch_insert(lsd_map* m, const float4* d_pts, int n, int id0, cudaStream_t st) {
@@ -143,7 +151,7 @@ lsd_status_t launch_knn(lsd_map* m, const float4* d_q, int nq, int k, float max_
                         int* d_cnt, cudaStream_t st) {
   if (nq <= 0) return LSD_OK;
   if (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0) { set_error("unknown stencil %d", stencil); return LSD_ERR_INVALID; }
-  dim3 g((nq + 127) / 128), b(128);
+  dim3 g(std::min((nq + kKnnWarps - 1) / kKnnWarps, 148 * 8)), b(kKnnWarps * 32);
   switch (k) {
     case 1: knn_query_kernel<1><<<g, b, 0, st>>>(m->view, d_q, nq, max_sq, stencil, d_idx, d_d2, d_cnt); break;
     case 5: knn_query_kernel<5><<<g, b, 0, st>>>(m->view, d_q, nq, max_sq, stencil, d_idx, d_d2, d_cnt); break;

@@ -13,7 +13,10 @@
 // bit-stable; it differs from PCL's fp32 sequential sum only by fp32 rounding (<= 1e-5 m).
 //
 // Pipeline (all sizes stay on the device, no host round trip):
-//   vg_minmax -> vg_setup -> vg_mark -> vg_wordscan -> vg_blockscan -> vg_accum -> vg_finalize
+//   vg_minmax -> vg_mark (+grid setup) -> vg_scan (word scan; last block scans the chunk totals)
+//   -> vg_accum -> vg_finalize (+scratch cleanup).  A single cooperative kernel with grid barriers
+//   was measured and rejected: no faster (the barriers cost what the launches do) and cooperative
+//   launches serialise badly behind an in-flight H2D copy (e2e 3.5 ms/scan vs 0.39 ms).
 #include "lsd_common.cuh"
 #include "voxelgrid.h"
 
@@ -25,43 +28,20 @@ constexpr double kFix = 67108864.0;  // 2^26 fixed-point scale (1.5e-8 m)
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__global__ void __launch_bounds__(256) vg_minmax_kernel(const float4* __restrict__ in, int n, int* __restrict__ bbox) {
-  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float4 p = __ldg(in + i);
-    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
-  }
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
-      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
-    }
-  }
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int d = 0; d < 3; d++) { atomicMin(&bbox[d], f2ord(mn[d])); atomicMax(&bbox[3 + d], f2ord(mx[d])); }
-  }
-}
-
-__global__ void vg_setup_kernel(const int* __restrict__ bbox, float leaf, long long max_cells, VgGrid* g) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void vg_setup(const int* __restrict__ bbox, float leaf, long long max_cells, VgGrid* g) {
   const float inv = 1.0f / leaf;
   float mn[3], mx[3];
   for (int d = 0; d < 3; d++) { mn[d] = ord2f(bbox[d]); mx[d] = ord2f(bbox[3 + d]); }
-  long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
-            dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
+                  dz = (long long)((mx[2] - mn[2]) * inv) + 1;
   g->inv = inv;
   g->status = 0;
-  if (dx * dy * dz > 2147483647ll) g->status = LSD_ERR_GRID_OVERFLOW;
+  if (dx * dy * dz > 2147483647ll) g->status = LSD_ERR_GRID_OVERFLOW;  // PCL: "Leaf size is too small"
   for (int d = 0; d < 3; d++) {
     g->minb[d] = (int)floorf(mn[d] * inv);
     g->divb[d] = (int)floorf(mx[d] * inv) - g->minb[d] + 1;
   }
-  long long cells = (long long)g->divb[0] * g->divb[1] * g->divb[2];
+  const long long cells = (long long)g->divb[0] * g->divb[1] * g->divb[2];
   if (g->status == 0 && cells > max_cells) g->status = LSD_ERR_CAPACITY;
   g->mul[0] = 1; g->mul[1] = g->divb[0]; g->mul[2] = g->divb[0] * g->divb[1];
   g->n_words = g->status ? 0 : (int)((cells + 31) >> 5);
@@ -74,102 +54,138 @@ __device__ __forceinline__ int leaf_index(const VgGrid& g, const float4& p) {
   return i0 * g.mul[0] + i1 * g.mul[1] + i2 * g.mul[2];
 }
 
-__global__ void __launch_bounds__(256) vg_mark_kernel(const float4* __restrict__ in, int n, const VgGrid* __restrict__ gp,
-                                                      unsigned* __restrict__ bitmap, int* __restrict__ vidx) {
-  const VgGrid g = *gp;
-  if (g.status) return;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int idx = leaf_index(g, __ldg(in + i));
-  vidx[i] = idx;
-  const unsigned bit = 1u << (idx & 31);
-  // warp-aggregate: lanes of one warp often share a word (neighbouring returns of one beam)
-  unsigned* w = bitmap + (idx >> 5);
-  if (!(*reinterpret_cast<volatile unsigned*>(w) & bit)) atomicOr(w, bit);
+// block-wide exclusive scan helper over `count` ints starting at base (256 threads)
+__device__ __forceinline__ int block_scan_step(int v, int* warp_tot, int* carry, int* incl_out) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int k = 0; k < (int)(threadIdx.x >> 5); k++) woff += warp_tot[k];
+  const int c = *carry;
+  *incl_out = c + woff + inc;
+  __syncthreads();
+  if (threadIdx.x == blockDim.x - 1) *carry = c + woff + inc;
+  __syncthreads();
+  return c + woff + inc - v;  // exclusive
 }
 
-// Per chunk of kScanChunk bitmap words: exclusive popcount prefix per word + chunk total.
-__global__ void __launch_bounds__(256) vg_wordscan_kernel(const VgGrid* __restrict__ gp, const unsigned* __restrict__ bitmap,
-                                                          int* __restrict__ word_prefix, int* __restrict__ chunk_sum) {
-  const int n_words = gp->n_words;
+// ---- kernel 1: bounding box.  Block-level reduction, then 6 atomics per block.
+__global__ void __launch_bounds__(256) vg_minmax_kernel(const float4* __restrict__ in, int n, int* __restrict__ bbox) {
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(in + i);
+    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+  }
+  __shared__ float smn[8][3], smx[8][3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5][d] = mn[d]; smx[threadIdx.x >> 5][d] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float a = smn[0][threadIdx.x], b = smx[0][threadIdx.x];
+    for (int w = 1; w < 8; w++) { a = fminf(a, smn[w][threadIdx.x]); b = fmaxf(b, smx[w][threadIdx.x]); }
+    atomicMin(&bbox[threadIdx.x], f2ord(a));
+    atomicMax(&bbox[3 + threadIdx.x], f2ord(b));
+  }
+}
+
+// ---- kernel 2: grid description (every block derives it; block 0 publishes it), mark leaves
+__global__ void __launch_bounds__(256) vg_mark_kernel(const float4* __restrict__ in, int n, float leaf, long long max_cells,
+                                                      const int* __restrict__ bbox, VgGrid* __restrict__ gp,
+                                                      unsigned* __restrict__ bitmap, int* __restrict__ vidx) {
+  __shared__ VgGrid g;
+  if (threadIdx.x == 0) { vg_setup(bbox, leaf, max_cells, &g); if (blockIdx.x == 0) *gp = g; }
+  __syncthreads();
+  if (g.status) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int idx = leaf_index(g, __ldg(in + i));
+    vidx[i] = idx;
+    const unsigned bit = 1u << (idx & 31);
+    unsigned* w = bitmap + (idx >> 5);
+    if (!(*reinterpret_cast<volatile unsigned*>(w) & bit)) atomicOr(w, bit);
+  }
+}
+
+// ---- kernel 3: per chunk of kScanChunk bitmap words, exclusive popcount prefix + chunk total; the
+// last block to finish scans the chunk totals and writes the output count.
+__global__ void __launch_bounds__(256) vg_scan_kernel(const VgGrid* __restrict__ gp, const unsigned* __restrict__ bitmap,
+                                                      int* __restrict__ word_prefix, int* __restrict__ chunk_sum,
+                                                      unsigned* __restrict__ done, int* __restrict__ m_out, int n_in) {
   __shared__ int warp_tot[8];
   __shared__ int carry;
-  for (int chunk = blockIdx.x; chunk * kScanChunk < n_words; chunk += gridDim.x) {
+  __shared__ bool is_last;
+  const int n_words = gp->n_words, status = gp->status;
+  const int n_chunks = (n_words + kScanChunk - 1) / kScanChunk;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = chunk * kScanChunk; base < min((chunk + 1) * kScanChunk, n_words); base += 256) {
       const int w = base + threadIdx.x;
       const int v = w < n_words ? __popc(bitmap[w]) : 0;
-      int inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
-      if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
-      __syncthreads();
-      int woff = 0;
-      for (int k = 0; k < (threadIdx.x >> 5); k++) woff += warp_tot[k];
-      const int c = carry;
-      if (w < n_words) word_prefix[w] = c + woff + inc - v;
-      __syncthreads();
-      if (threadIdx.x == 255) carry = c + woff + inc;
-      __syncthreads();
+      int incl;
+      const int ex = block_scan_step(v, warp_tot, &carry, &incl);
+      if (w < n_words) word_prefix[w] = ex;
     }
     if (threadIdx.x == 0) chunk_sum[chunk] = carry;
     __syncthreads();
   }
-}
-
-// Exclusive scan of the chunk totals (single block); writes the output count.
-__global__ void __launch_bounds__(1024) vg_blockscan_kernel(const VgGrid* __restrict__ gp, int* __restrict__ chunk_sum,
-                                                            int* __restrict__ m_out, int n_in) {
-  const int n_chunks = (gp->n_words + kScanChunk - 1) / kScanChunk;
-  __shared__ int warp_tot[32];
-  __shared__ int carry;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < n_chunks; base += 1024) {
+  for (int base = 0; base < n_chunks; base += 256) {
     const int i = base + threadIdx.x;
-    const int v = i < n_chunks ? chunk_sum[i] : 0;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    int woff = 0;
-    for (int k = 0; k < (threadIdx.x >> 5); k++) woff += warp_tot[k];
-    const int c = carry;
-    if (i < n_chunks) chunk_sum[i] = c + woff + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = c + woff + inc;
-    __syncthreads();
+    const int v = i < n_chunks ? __ldcg(chunk_sum + i) : 0;
+    int incl;
+    const int ex = block_scan_step(v, warp_tot, &carry, &incl);
+    if (i < n_chunks) chunk_sum[i] = ex;
   }
-  if (threadIdx.x == 0) *m_out = gp->status == LSD_ERR_GRID_OVERFLOW ? n_in : (gp->status ? 0 : carry);
+  if (threadIdx.x == 0) {
+    *m_out = status == LSD_ERR_GRID_OVERFLOW ? n_in : (status ? 0 : carry);
+    *done = 0u;
+  }
 }
 
+// ---- kernel 4: rank of each point's leaf = its output slot; exact fixed-point channel sums
 __global__ void __launch_bounds__(256) vg_accum_kernel(const float4* __restrict__ in, int n, const VgGrid* __restrict__ gp,
                                                        const unsigned* __restrict__ bitmap, const int* __restrict__ vidx,
                                                        const int* __restrict__ word_prefix, const int* __restrict__ chunk_off,
                                                        long long* __restrict__ sums, int* __restrict__ cnt,
                                                        int* __restrict__ out_vidx, float4* __restrict__ out) {
   const int status = gp->status;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = __ldg(in + i);
-  if (status == LSD_ERR_GRID_OVERFLOW) { out[i] = p; return; }  // PCL: output = input
-  if (status) return;
-  const int idx = vidx[i];
-  const int w = idx >> 5;
-  const int rank = chunk_off[w / kScanChunk] + word_prefix[w] + __popc(bitmap[w] & ((1u << (idx & 31)) - 1u));
-  long long* s = sums + 4 * (size_t)rank;
-  atomicAdd(reinterpret_cast<unsigned long long*>(s + 0), (unsigned long long)__double2ll_rn((double)p.x * kFix));
-  atomicAdd(reinterpret_cast<unsigned long long*>(s + 1), (unsigned long long)__double2ll_rn((double)p.y * kFix));
-  atomicAdd(reinterpret_cast<unsigned long long*>(s + 2), (unsigned long long)__double2ll_rn((double)p.z * kFix));
-  atomicAdd(reinterpret_cast<unsigned long long*>(s + 3), (unsigned long long)__double2ll_rn((double)p.w * kFix));
-  atomicAdd(cnt + rank, 1);
-  out_vidx[rank] = idx;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(in + i);
+    if (status == LSD_ERR_GRID_OVERFLOW) { out[i] = p; continue; }  // PCL: output = input
+    if (status) return;
+    const int idx = vidx[i];
+    const int w = idx >> 5;
+    const int rank = chunk_off[w / kScanChunk] + word_prefix[w] + __popc(bitmap[w] & ((1u << (idx & 31)) - 1u));
+    long long* s = sums + 4 * (size_t)rank;
+    atomicAdd(reinterpret_cast<unsigned long long*>(s + 0), (unsigned long long)__double2ll_rn((double)p.x * kFix));
+    atomicAdd(reinterpret_cast<unsigned long long*>(s + 1), (unsigned long long)__double2ll_rn((double)p.y * kFix));
+    atomicAdd(reinterpret_cast<unsigned long long*>(s + 2), (unsigned long long)__double2ll_rn((double)p.z * kFix));
+    atomicAdd(reinterpret_cast<unsigned long long*>(s + 3), (unsigned long long)__double2ll_rn((double)p.w * kFix));
+    atomicAdd(cnt + rank, 1);
+    out_vidx[rank] = idx;
+  }
 }
 
-// Centroid per occupied leaf; also returns the scratch (bitmap words, sums, counts) to zero so the
-// next call needs no memset proportional to the grid volume.
+// ---- kernel 5: centroids; scratch (bitmap words, sums, counts, bbox) returns to its idle state so
+// the next call needs no memset proportional to the grid volume.
 __global__ void __launch_bounds__(256) vg_finalize_kernel(const VgGrid* __restrict__ gp, const int* __restrict__ m_ptr,
                                                           long long* __restrict__ sums, int* __restrict__ cnt,
                                                           const int* __restrict__ out_vidx, unsigned* __restrict__ bitmap,
@@ -180,35 +196,33 @@ __global__ void __launch_bounds__(256) vg_finalize_kernel(const VgGrid* __restri
   }
   if (gp->status) return;
   const int m = *m_ptr;
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= m) return;
-  long long* s = sums + 4 * (size_t)r;
-  const double c = (double)cnt[r];
-  float4 o;
-  o.x = (float)((double)s[0] / kFix / c);
-  o.y = (float)((double)s[1] / kFix / c);
-  o.z = (float)((double)s[2] / kFix / c);
-  o.w = (float)((double)s[3] / kFix / c);
-  out[r] = o;
-  s[0] = s[1] = s[2] = s[3] = 0;
-  cnt[r] = 0;
-  bitmap[out_vidx[r] >> 5] = 0u;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    long long* s = sums + 4 * (size_t)r;
+    const double c = (double)cnt[r];
+    float4 o;
+    o.x = (float)((double)s[0] / kFix / c);
+    o.y = (float)((double)s[1] / kFix / c);
+    o.z = (float)((double)s[2] / kFix / c);
+    o.w = (float)((double)s[3] / kFix / c);
+    out[r] = o;
+    s[0] = s[1] = s[2] = s[3] = 0;
+    cnt[r] = 0;
+    bitmap[out_vidx[r] >> 5] = 0u;
+  }
 }
 
 lsd_status_t vg_run(lsd_voxelgrid* g, const float4* d_in, int n, float leaf, float4* d_out, int* d_m, cudaStream_t st) {
   if (n > g->max_points) { set_error("voxelgrid: %d points exceed capacity %d", n, g->max_points); return LSD_ERR_CAPACITY; }
   if (n <= 0) { LSD_CUDA(cudaMemsetAsync(d_m, 0, sizeof(int), st)); return LSD_OK; }
-  const int nb = (n + 255) / 256;
-  vg_minmax_kernel<<<min(nb, 592), 256, 0, st>>>(d_in, n, g->bbox);
-  vg_setup_kernel<<<1, 32, 0, st>>>(g->bbox, leaf, g->max_cells, g->grid);
-  vg_mark_kernel<<<nb, 256, 0, st>>>(d_in, n, g->grid, g->bitmap, g->vidx);
-  vg_wordscan_kernel<<<g->scan_blocks, 256, 0, st>>>(g->grid, g->bitmap, g->word_prefix, g->chunk_sum);
-  vg_blockscan_kernel<<<1, 1024, 0, st>>>(g->grid, g->chunk_sum, d_m, n);
+  const int nb = std::min((n + 255) / 256, 592);
+  vg_minmax_kernel<<<std::min(nb, 148), 256, 0, st>>>(d_in, n, g->bbox);
+  vg_mark_kernel<<<nb, 256, 0, st>>>(d_in, n, leaf, g->max_cells, g->bbox, g->grid, g->bitmap, g->vidx);
+  vg_scan_kernel<<<g->scan_blocks, 256, 0, st>>>(g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->done, d_m, n);
   vg_accum_kernel<<<nb, 256, 0, st>>>(d_in, n, g->grid, g->bitmap, g->vidx, g->word_prefix, g->chunk_sum, g->sums, g->cnt,
                                       g->out_vidx, d_out);
   vg_finalize_kernel<<<nb, 256, 0, st>>>(g->grid, d_m, g->sums, g->cnt, g->out_vidx, g->bitmap, d_out, g->bbox);
   LSD_CUDA(cudaGetLastError());
-  g->launches += 7;
+  g->launches += 5;
   return LSD_OK;
 }
 
@@ -229,6 +243,7 @@ lsd_status_t lsd_voxelgrid_create(lsd_voxelgrid_t** out, int max_points, int log
   const size_t words = (size_t)((g->max_cells + 31) >> 5);
   const size_t chunks = (words + kScanChunk - 1) / kScanChunk;
   g->scan_blocks = (int)std::min<size_t>(chunks, 1184);
+  g->scan_blocks = (int)std::min<size_t>(g->scan_blocks, 296);
   cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
   auto A = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b); if (e == cudaSuccess) e = cudaMemset(*p, 0, b); };
   A((void**)&g->bbox, 8 * sizeof(int));
@@ -243,6 +258,7 @@ lsd_status_t lsd_voxelgrid_create(lsd_voxelgrid_t** out, int max_points, int log
   A((void**)&g->io_in, (size_t)max_points * 16);
   A((void**)&g->io_out, (size_t)max_points * 16);
   A((void**)&g->d_m, 64);
+  A((void**)&g->done, 64);
   if (e == cudaSuccess) e = cudaMemset(g->bbox, 0x7f, 3 * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(g->bbox + 3, 0x80, 3 * sizeof(int));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -255,7 +271,7 @@ lsd_status_t lsd_voxelgrid_destroy(lsd_voxelgrid_t* g) {
   if (!g) return LSD_OK;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  void* ptrs[] = {g->bbox, g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->vidx, g->out_vidx, g->sums, g->cnt, g->io_in, g->io_out, g->d_m};
+  void* ptrs[] = {g->bbox, g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->vidx, g->out_vidx, g->sums, g->cnt, g->io_in, g->io_out, g->d_m, g->done};
   for (void* p : ptrs) cudaFree(p);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;

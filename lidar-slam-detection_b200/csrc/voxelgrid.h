@@ -14,7 +14,7 @@ struct VgGrid {  // device-resident grid description, written by vg_setup_kernel
 }  // namespace lsd
 
 struct lsd_voxelgrid {
-  int device = 0, max_points = 0, scan_blocks = 0;
+  int device = 0, max_points = 0, scan_blocks = 0, coop_blocks = 148;
   long long max_cells = 0;
   cudaStream_t stream = nullptr;
   int* bbox = nullptr;            // ordered-int min[3], max[3]
@@ -28,6 +28,7 @@ struct lsd_voxelgrid {
   int* cnt = nullptr;
   float4 *io_in = nullptr, *io_out = nullptr;  // staging for the host-pointer entry point
   int* d_m = nullptr;
+  unsigned* done = nullptr;       // last-block ticket of vg_scan_kernel
   long long launches = 0;
 };
 

@@ -250,7 +250,7 @@ S2_IDX = 21
 
 
 def update_iterated(x: State, P: np.ndarray, h_model, R: float = 0.001, maximum_iter: int = 4,
-                    limit: float = 0.001, trace: list | None = None):
+                    limit: float = 0.001, trace: list | None = None, inv=np.linalg.inv):
     """esekfom.hpp:1619-1931.  h_model(state, converge) -> dict(valid, HTH[15,15], HTh[15], n)
     (and 'h_x' [n,15], 'h' [n] when n < 23).  Returns (x, P, n_iters_run)."""
     x = x.copy()
@@ -284,13 +284,13 @@ def update_iterated(x: State, P: np.ndarray, h_model, R: float = 0.001, maximum_
         if N > dof:
             h_x = np.zeros((dof, N))
             h_x[:, :15] = m["h_x"]
-            K = P @ h_x.T @ np.linalg.inv(h_x @ P @ h_x.T / R + np.eye(dof)) / R
+            K = P @ h_x.T @ inv(h_x @ P @ h_x.T / R + np.eye(dof)) / R
             K_h = K @ m["h"]
             K_x = K @ h_x
         else:
-            P_temp = np.linalg.inv(P / R)
+            P_temp = inv(P / R)
             P_temp[:15, :15] += m["HTH"]
-            P_inv = np.linalg.inv(P_temp)
+            P_inv = inv(P_temp)
             K_h = P_inv[:, :15] @ m["HTh"]
             K_x = np.zeros((N, N))
             K_x[:, :15] = P_inv[:, :15] @ m["HTH"]

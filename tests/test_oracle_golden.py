@@ -1,0 +1,118 @@
+"""CPU: the plain-C oracle port against (a) golden vectors generated from the COMPILED reference
+(tests/golden/make_golden.py) and (b) the compiled reference itself when oracle/_ref is present.
+Bars: neighbour id sets bit-exact; fp32 k-d tree distances bit-exact; plane residual |pd2| within 2e-4 m
+(Eigen's vectorised QR reductions are not bit-reproducible by scalar code, see oracle/lsd_oracle.c)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lio_ref_small.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(GOLD))
+
+
+@pytest.fixture(scope="module")
+def port_map(gold):
+    iv = O.OracleIvox(0.5, 18, 1 << 16)
+    iv.add(gold["map"], 0)
+    return iv
+
+
+@pytest.mark.parametrize("nearby", [18, 74])
+def test_ivox_knn_matches_reference_golden(gold, port_map, nearby):
+    port_map.set_nearby(nearby)
+    ids, d2, xyz, cnt = port_map.knn(gold["query"], 5, 5.0)
+    port_map.set_nearby(18)
+    assert (cnt == gold[f"ivox{nearby}_cnt"]).all()
+    assert (np.sort(ids, 1) == gold[f"ivox{nearby}_ids"]).all()
+
+
+def test_exact_knn_matches_ikdtree_golden(gold, port_map):
+    ids, d2, xyz, cnt = port_map.knn(gold["query"], 5, 5.0, exact=True)
+    kd_ok = (gold["ikd_cnt"] >= 5) & (gold["ikd_d2"][:, 4] <= 5)       # laserMapping.cpp:846-847
+    assert ((cnt >= 5) == kd_ok).all()
+    assert (np.sort(ids[kd_ok], 1) == np.sort(gold["ikd_ids"][kd_ok], 1)).all()
+    assert (d2[kd_ok].view(np.int32) == gold["ikd_d2"][kd_ok].view(np.int32)).all()  # same fp32 arithmetic
+
+
+def test_esti_plane_matches_reference_golden(gold):
+    pa, ok = O.esti_plane(gold["plane_in"], 0.1)
+    ra, rok = gold["plane_abcd"], gold["plane_ok"]
+    pts = gold["plane_in"]
+    cen = pts.mean(1)
+    pd = (pa[:, :3] * cen).sum(1) + pa[:, 3]
+    rpd = (ra[:, :3] * cen).sum(1) + ra[:, 3]
+    # accept/reject may only differ for planes within rounding of the 0.1 m threshold
+    flip = ok != rok
+    assert flip.mean() < 0.01
+    good = (ok == 1) & (rok == 1)
+    assert np.abs(pd - rpd)[good].max() < 2e-4
+    assert np.abs((pa[:, :3] * ra[:, :3]).sum(1))[good].min() > 1 - 1e-5  # same normal up to sign (same sign by construction)
+
+
+@pytest.mark.skipif(not O.HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
+def test_port_equals_compiled_reference_on_fresh_data():
+    from lsdreg import synth
+    m = synth.block_map(21, 1, 2, 0.5)
+    scan = synth.scan64(22, 120)
+    q = O.voxelgrid(scan, 0.5)
+    q[:, :3] += synth.block_center(0, 0).astype(np.float32)
+    iv = O.OracleIvox(0.5, 18, 1 << 17); iv.add(m, 0)
+    rv = O.RefIvox(0.5, 18); rv.add(m, 0)
+    assert iv.num_cells == rv.num_cells
+    ids, d2, xyz, cnt = iv.knn(q)
+    rids, rxyz, rcnt = rv.knn(q)
+    assert (cnt == rcnt).all() and (np.sort(ids, 1) == np.sort(rids, 1)).all()
+    # reference order: nearest neighbour first (ivox3d.h:163), ours: canonical ascending
+    has = cnt > 0
+    assert (ids[has, 0] == rids[has, 0]).all() or (d2[has, 0] == d2[has, 1]).any()
+    kd = O.RefIkd(); kd.build(m)
+    kids, kd2, kcnt = kd.knn(q)
+    eids, ed2, _, ecnt = iv.knn(q, 5, 5.0, exact=True)
+    acc = (kcnt >= 5) & (kd2[:, 4] <= 5)
+    assert ((ecnt >= 5) == acc).all()
+    assert (np.sort(kids[acc], 1) == np.sort(eids[acc], 1)).all() and (kd2[acc] == ed2[acc]).all()
+
+
+def test_voxelgrid_properties():
+    """PCL VoxelGrid restatement (parity unpinned: PCL is not vendored): structural properties."""
+    from lsdreg import synth
+    scan = synth.scan64(5, 200)
+    out, vidx = O.voxelgrid(scan, 0.5, want_vidx=True)
+    assert (np.diff(vidx) > 0).all()                       # ascending, unique leaf indices
+    inv = np.float32(1.0) / np.float32(0.5)
+    leaf_in = np.floor(scan[:, :3] * inv).astype(np.int64)
+    leaf_out = np.floor(out[:, :3] * inv).astype(np.int64)
+    assert len(np.unique(leaf_in, axis=0)) == out.shape[0]  # one output per occupied leaf
+    # centroid lies in (or on the boundary of) its leaf
+    key_in = set(map(tuple, leaf_in))
+    near = [tuple(k) in key_in for k in leaf_out]
+    assert np.mean(near) > 0.999
+    # idempotent up to rounding: filtering the centroids keeps one point per leaf
+    again = O.voxelgrid(out, 0.5)
+    assert abs(again.shape[0] - out.shape[0]) <= 0.001 * out.shape[0] + 2
+    assert O.voxelgrid(np.zeros((0, 4), np.float32), 0.5).shape == (0, 4)
+
+
+def test_oracle_lio_converges():
+    from lsdreg import synth
+    from oracle import eskf
+    from oracle.lio import OracleLio
+    m = synth.block_map(1, 1, 1, 0.5)
+    lio = OracleLio(18, expected_cells=1 << 17)
+    lio.add_map_points(m)
+    Rgt = synth.rot_from_rpy(0.01, -0.02, 0.3)
+    tgt = synth.block_center(0, 0) + np.array([1.0, -2.0, 0.0])
+    scan = synth.scan64(2, 120, Rgt, tgt)
+    dR, dt = synth.perturb(5)
+    prior = eskf.State(); prior.rot = eskf.R_to_quat(Rgt @ dR); prior.pos = tgt + dt
+    r = lio.process_scan(scan, prior, eskf.init_P())
+    assert r["iters"] >= 3 and r["log"][-1]["n_eff"] > 500
+    assert np.abs(lio.x.pos - tgt).max() < 0.03
+    assert np.linalg.norm(eskf.so3_log(eskf.R_to_quat(Rgt.T @ eskf.quat_to_R(lio.x.rot)))) < 2e-3
