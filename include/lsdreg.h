@@ -118,6 +118,10 @@ typedef struct lsd_lio_params {
                                 inversions (esekfom.hpp:1756-1789); 0 (default): the algebraically
                                 identical Schur-complement form (two 6x6 inverses), ~2x faster on
                                 the host and equally accurate (DESIGN.md "Host ESKF")             */
+  int async_map_insert;      /* 1: lsd_lio_scan returns as soon as the pose is final; map_incremental
+                                completes in the background on the handle's stream (the next call is
+                                ordered after it).  info->gpu_ms / n_added then describe the PREVIOUS
+                                scan; lsd_lio_sync() drains.  0 (default): fully synchronous.          */
 } lsd_lio_params_t;
 
 typedef struct lsd_lio_info {
@@ -145,6 +149,8 @@ lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, l
 /* Per-kernel CUDA-event timing for the roofline report (adds a sync per launch: never enable it in a
  * throughput measurement).  ms4/cnt4: [0] h-model with k-NN search, [1] h-model reusing neighbours,
  * [2] voxel grid (7 kernels), [3] map_incremental. */
+/* Wait for everything queued on the handle; returns device time / insert count of the last scan. */
+lsd_status_t lsd_lio_sync(lsd_lio_t* l, double* gpu_ms_last, int* n_added_last);
 lsd_status_t lsd_lio_set_profile(lsd_lio_t* l, int on);
 lsd_status_t lsd_lio_get_profile(lsd_lio_t* l, double* ms4, long long* cnt4);
 

@@ -29,7 +29,7 @@ class LioParams(C.Structure):
     _fields_ = [("max_points", C.c_int), ("max_scan_points", C.c_int), ("filter_size_surf", C.c_float),
                 ("filter_size_map", C.c_float), ("ivox_resolution", C.c_float), ("ivox_nearby", C.c_int),
                 ("map_log2_lines", C.c_int), ("max_iterations", C.c_int), ("laser_point_cov", C.c_double),
-                ("converge_eps", C.c_double), ("degenerate_detect_en", C.c_int), ("knn_mode_exact", C.c_int), ("eskf_literal", C.c_int)]
+                ("converge_eps", C.c_double), ("degenerate_detect_en", C.c_int), ("knn_mode_exact", C.c_int), ("eskf_literal", C.c_int), ("async_map_insert", C.c_int)]
 
 
 class LioInfo(C.Structure):
@@ -69,6 +69,7 @@ SIGNATURES = [
     ("lsd_lio_set_nearby", _i, [_vp, _i]),
     ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
     ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
+    ("lsd_lio_sync", _i, [_vp, C.POINTER(_d), _pi]),
     ("lsd_lio_set_profile", _i, [_vp, _i]),
     ("lsd_lio_get_profile", _i, [_vp, _vp, _vp]),
     ("lsd_lio_load_scan", _i, [_vp, _vp, _i, _i, _pi]),
@@ -271,6 +272,12 @@ class LioFrontend:
 
     def set_ekf_inited(self, flag: bool):
         check(lib.lsd_lio_set_ekf_inited(self.h, int(flag)))
+
+    def sync(self):
+        """Drain the handle's stream -> (gpu_ms, n_added) of the last scan."""
+        ms, na = C.c_double(), C.c_int()
+        check(lib.lsd_lio_sync(self.h, C.byref(ms), C.byref(na)))
+        return ms.value, na.value
 
     def set_profile(self, on: bool):
         check(lib.lsd_lio_set_profile(self.h, int(on)))

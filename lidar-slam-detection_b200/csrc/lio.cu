@@ -162,7 +162,7 @@ __device__ __forceinline__ bool esti_plane_dev(const float (&px)[5], const float
 // ---------------------------------------------------------------- grid reduction
 // Result buffer layout (doubles): [0..20] upper triangle of the 6x6 h_x^T h_x, [21..26] h_x^T h,
 // [27] sum |res|, [28] n_eff, [29] feats_down_size, [48..53] degeneracy sums.
-constexpr int kResDegen = 48, kResDoubles = 64;
+constexpr int kResDegen = 48, kResSeq = 62, kResSeqDegen = 63, kResDoubles = 64;
 
 // symmetric 3x3 eigen-decomposition (cyclic Jacobi); V columns = eigenvectors.  Stands in for
 // Eigen::SelfAdjointEigenSolver at laserMapping.cpp:941; only |v . n| and V diag(mask) V^T are used,
@@ -189,9 +189,12 @@ static void eig3_sym(const double* Ain, double* V, double* w) {
 // Called by every thread of every block after the block has written partials[blockIdx][0..NV).
 // The last block to arrive folds all partials in a fixed order (slices of blocks, ascending) into
 // result[0..NV) — bit-reproducible for a given grid size.
+// `result` is HOST memory mapped into the device address space: the last block publishes the sums
+// and then a sequence number the host spins on (no cudaMemcpy, no stream synchronise per iteration).
 template <int NV>
 __device__ __forceinline__ void grid_finalize(double* __restrict__ partials, unsigned* __restrict__ done,
-                                              double* __restrict__ result, int res_off, int n_extra_slot, double extra) {
+                                              volatile double* __restrict__ result, int res_off, int n_extra_slot, double extra,
+                                              int seq_slot, double seq) {
   __shared__ double sm_fin[8][kNV];
   __shared__ bool is_last;
   __threadfence();
@@ -221,12 +224,14 @@ __device__ __forceinline__ void grid_finalize(double* __restrict__ partials, uns
     double t = 0.0;
     for (int w = 0; w < slices; w++) t += sm_fin[w][threadIdx.x];
     result[res_off + threadIdx.x] = t;
-    sm_fin[0][threadIdx.x] = t;
+    __threadfence_system();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     if (n_extra_slot >= 0) result[n_extra_slot] = extra;
     *done = 0u;
+    __threadfence_system();
+    result[seq_slot] = seq;  // published last
   }
 }
 
@@ -282,6 +287,8 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
   wl.loc = reinterpret_cast<unsigned*>(wl.id + kCandCap);
   wl.n = 0;
   const LaneStencil ls = lane_stencil(stencil_slot(stencil));
+  // (An L2-prefetch pass over the warp's queries was measured here and removed: +9 us per launch —
+  // the kernel is bound by its dependent instruction chain per query, not by the cold HBM trip.)
   for (int i = blockIdx.x * kHmWarps + warp; i < n; i += gridDim.x * kHmWarps) {
     const float4 pb = __ldg(body + i);
     // body -> world in double (laserMapping.cpp:831-836), stored as fp32 like PointType
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
                                                                float4* __restrict__ pabcd_io, unsigned char* __restrict__ plane_ok,
                                                                float4* __restrict__ plane, float4* __restrict__ world,
                                                                double* __restrict__ partials, unsigned* __restrict__ done,
-                                                               double* __restrict__ result) {
+                                                               double* __restrict__ result, double seq) {
   const int n_true = *n_ptr;
   const int n = min(n_true, cap);
   double vals[29];
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
     selected[i] = keep ? 1 : 0;
   }
   block_partials<29>(vals, partials);
-  grid_finalize<29>(partials, done, result, 0, 29, (double)n_true);
+  grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq);
 }
 
 // ---------------------------------------------------------------- degeneracy sums (laserMapping.cpp:946-970)
@@ -378,7 +385,7 @@ struct Eig3 { double V[9]; };  // columns = eigenvectors
 __global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restrict__ n_ptr, int cap,
                                                               const unsigned char* __restrict__ selected,
                                                               const float4* __restrict__ plane, Eig3 e, double* __restrict__ partials,
-                                                              unsigned* __restrict__ done, double* __restrict__ result) {
+                                                              unsigned* __restrict__ done, double* __restrict__ result, double seq) {
   const int n = min(*n_ptr, cap);
   const double* V = e.V;
   double vals[6] = {0, 0, 0, 0, 0, 0};
@@ -395,7 +402,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restr
     }
   }
   block_partials<6>(vals, partials);
-  grid_finalize<6>(partials, done, result, kResDegen, -1, 0.0);
+  grid_finalize<6>(partials, done, result, kResDegen, -1, 0.0, kResSeqDegen, seq);
 }
 
 // ---------------------------------------------------------------- map_incremental (laserMapping.cpp:523-576)
@@ -472,6 +479,23 @@ struct ProfScope {  // CUDA-event timing of one launch group on the LIO stream (
   }
 };
 
+// Spin on the sequence number the kernel publishes into mapped host memory.
+static lsd_status_t wait_seq(lsd_lio* l, int slot, double seq) {
+  volatile double* r = l->h_result;
+  for (unsigned long long spins = 0;; spins++) {
+    if (r[slot] == seq) return LSD_OK;
+    if ((spins & 0xfff) == 0xfff) {
+      cudaError_t e = cudaStreamQuery(l->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "kernel while waiting for the reduction", __FILE__, __LINE__);
+      if (e == cudaSuccess && r[slot] != seq) {  // stream drained but nothing published: should not happen
+        if (r[slot] == seq) return LSD_OK;
+        set_error("reduction result never published");
+        return LSD_ERR_CUDA;
+      }
+    }
+  }
+}
+
 static int grid_for(int n) { return std::max(1, std::min((n + kLioBlock - 1) / kLioBlock, kLioMaxGrid)); }
 
 // One h_share_model_geometric evaluation on the loaded scan.  Fills HTH6/HTh6 (after the
@@ -482,24 +506,24 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   pose_from_state(x, &ps);
   cudaStream_t st = l->stream;
   const int stencil = l->p.knn_mode_exact ? LSD_STENCIL_EXACT : l->p.ivox_nearby;
+  const double seq = (double)(++l->seq);
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
     const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
     lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt);
     lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                                        l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                                       l->d_partials, l->d_done, l->d_result);
+                                                                       l->d_partials, l->d_done, l->d_result, seq);
     l->launches += 2;
   } else {
     lio_hmodel_kernel<false><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                                         l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                                        l->d_partials, l->d_done, l->d_result);
+                                                                        l->d_partials, l->d_done, l->d_result, seq);
     l->launches++;
   }
   LSD_CUDA(cudaGetLastError());
   prof.stop();
-  LSD_CUDA(cudaMemcpyAsync(l->h_result, l->d_result, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  LSD_CUDA(cudaStreamSynchronize(st));
+  { lsd_status_t w = wait_seq(l, kResSeq, seq); if (w) return w; }
   const double* r = l->h_result;
   int q = 0;
   for (int a = 0; a < 6; a++) for (int c = a; c < 6; c++) { HTH6[6 * a + c] = HTH6[6 * c + a] = r[q]; q++; }
@@ -525,11 +549,10 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
       Eig3 e;
       memcpy(e.V, V, sizeof(V));
       lio_degen_kernel<<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_n, l->p.max_points, l->d_selected, l->d_plane, e, l->d_partials,
-                                                                  l->d_done, l->d_result);
+                                                                  l->d_done, l->d_result, seq);
       LSD_CUDA(cudaGetLastError());
       l->launches++;
-      LSD_CUDA(cudaMemcpyAsync(l->h_result + kResDegen, l->d_result + kResDegen, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      LSD_CUDA(cudaStreamSynchronize(st));
+      { lsd_status_t w = wait_seq(l, kResSeqDegen, seq); if (w) return w; }
       const double* dg = l->h_result + kResDegen;
       int mask[3] = {1, 1, 1};
       bool deg = false;
@@ -614,7 +637,21 @@ lsd_status_t lio_update(lsd_lio* l, double* x, double* P, lsd_lio_info_t* info) 
   return last_neff >= 1 ? LSD_OK : LSD_NO_EFFECTIVE_POINTS;
 }
 
-lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int* n_added) {
+// Collect what an asynchronous lio_scan left pending (device time and insert count of that scan).
+static lsd_status_t lio_drain(lsd_lio* l) {
+  if (!l->pending) return LSD_OK;
+  LSD_CUDA(cudaEventSynchronize(l->ev1));
+  float ms = 0.f;
+  LSD_CUDA(cudaEventElapsedTime(&ms, l->ev0, l->ev1));
+  l->last_gpu_ms = ms;
+  l->last_added = (int)*l->h_added;
+  l->pending = false;
+  return LSD_OK;
+}
+
+// map_incremental on the stream; with wait == false the insert count is copied to pinned memory
+// asynchronously and picked up by lio_drain().
+lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int* n_added, bool wait) {
   LioPose ps;
   pose_from_state(x, &ps);
   cudaStream_t st = l->stream;
@@ -626,11 +663,14 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
   LSD_CUDA(cudaGetLastError());
   l->launches++;
   prof.stop();
-  unsigned h = 0;
-  LSD_CUDA(cudaMemcpyAsync(&h, l->d_added, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  LSD_CUDA(cudaStreamSynchronize(st));
+  LSD_CUDA(cudaMemcpyAsync(l->h_added, l->d_added, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   l->next_id += l->n_bound;
-  if (n_added) *n_added = (int)h;
+  if (wait) {
+    LSD_CUDA(cudaStreamSynchronize(st));
+    if (n_added) *n_added = (int)*l->h_added;
+  } else if (n_added) {
+    *n_added = -1;
+  }
   return LSD_OK;
 }
 
@@ -669,6 +709,8 @@ static lsd_status_t read_n_down(lsd_lio* l) {
 lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double* P, lsd_lio_info_t* info) {
   cudaStream_t st = l->stream;
   const long long launches0 = l->launches;
+  const bool async = l->p.async_map_insert != 0;
+  { lsd_status_t d = lio_drain(l); if (d) return d; }
   LSD_CUDA(cudaEventRecord(l->ev0, st));
   lsd_status_t s = lio_load(l, d_scan, n, 1);
   if (s) return s;
@@ -681,7 +723,7 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
     s = read_n_down(l);
     if (s) return s;
     inf.n_down = l->n_down;
-    if (l->n_down > 5) { s = lio_map_incremental(l, x, 0, &inf.n_added); if (s) return s; l->map_cells_known = 1; }
+    if (l->n_down > 5) { s = lio_map_incremental(l, x, 0, &inf.n_added, true); if (s) return s; l->map_cells_known = 1; }
     ret = LSD_MAP_SEEDED;
   } else {
     s = lio_update(l, x, P, &inf);
@@ -689,15 +731,25 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
     if (l->n_down < 5) ret = LSD_SCAN_TOO_SMALL;  // laserMapping.cpp:1252-1256 (state untouched: n_eff == 0)
     else {
       ret = s;
-      lsd_status_t m = lio_map_incremental(l, x, 1, &inf.n_added);
+      lsd_status_t m = lio_map_incremental(l, x, 1, &inf.n_added, !async);
       if (m) return m;
     }
   }
   LSD_CUDA(cudaEventRecord(l->ev1, st));
-  LSD_CUDA(cudaEventSynchronize(l->ev1));
-  float ms = 0.f;
-  LSD_CUDA(cudaEventElapsedTime(&ms, l->ev0, l->ev1));
-  inf.gpu_ms = ms;
+  if (async && inf.n_added == -1) {
+    // the pose is final; the map insert finishes in the background.  gpu_ms / n_added reported now
+    // are those of the PREVIOUS scan (collected by lio_drain), see lsd_lio_params::async_map_insert.
+    l->pending = true;
+    inf.gpu_ms = l->last_gpu_ms;
+    inf.n_added = l->last_added;
+  } else {
+    LSD_CUDA(cudaEventSynchronize(l->ev1));
+    float ms = 0.f;
+    LSD_CUDA(cudaEventElapsedTime(&ms, l->ev0, l->ev1));
+    inf.gpu_ms = ms;
+    l->last_gpu_ms = ms;
+    l->last_added = inf.n_added;
+  }
   inf.kernel_launches = (int)(l->launches - launches0);
   if (info) *info = inf;
   return ret;
@@ -724,6 +776,7 @@ void lsd_lio_default_params(lsd_lio_params_t* p) {
   p->degenerate_detect_en = 1;   // laserMapping.cpp:83
   p->knn_mode_exact = 0;
   p->eskf_literal = 0;
+  p->async_map_insert = 0;
 }
 
 lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
@@ -756,9 +809,10 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   A((void**)&l->d_partials, max_blocks * kNV * 8);
   A((void**)&l->d_done, 64);
   A((void**)&l->d_added, 64);
-  A((void**)&l->d_result, kResDoubles * 8);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_result, kResDoubles * 8);
-  if (e == cudaSuccess) e = cudaEventCreate(&l->ev0);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&l->h_result, kResDoubles * 8, cudaHostAllocMapped);
+  if (e == cudaSuccess) { memset(l->h_result, 0, kResDoubles * 8); e = cudaHostGetDevicePointer((void**)&l->d_result, l->h_result, 0); }
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_added, 64);
+  if (e == cudaSuccess) { *l->h_added = 0; e = cudaEventCreate(&l->ev0); }
   if (e == cudaSuccess) e = cudaEventCreate(&l->ev1);
   if (e == cudaSuccess) e = cudaEventCreate(&l->pev[0]);
   if (e == cudaSuccess) e = cudaEventCreate(&l->pev[1]);
@@ -779,9 +833,9 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   cudaSetDevice(l->device);
   if (l->stream) cudaStreamSynchronize(l->stream);
   void* ptrs[] = {l->d_scan, l->d_body, l->d_n, l->d_near, l->d_near_cnt, l->d_selected, l->d_flags, l->d_plane, l->d_world,
-                  l->d_partials, l->d_done, l->d_added, l->d_result, l->d_pabcd, l->d_plane_ok};
+                  l->d_partials, l->d_done, l->d_added, l->d_pabcd, l->d_plane_ok};
   for (void* p : ptrs) cudaFree(p);
-  cudaFreeHost(l->h_result);
+  cudaFreeHost(l->h_result); cudaFreeHost(l->h_added);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->pev[0]) cudaEventDestroy(l->pev[0]);
@@ -799,6 +853,16 @@ lsd_map_t* lsd_lio_map(lsd_lio_t* l) { return l ? l->map : nullptr; }
 lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil) {
   if (!l || (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0)) return LSD_ERR_INVALID;
   l->p.ivox_nearby = stencil;
+  return LSD_OK;
+}
+lsd_status_t lsd_lio_sync(lsd_lio_t* l, double* gpu_ms_last, int* n_added_last) {
+  if (!l) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  lsd_status_t s = lio_drain(l);
+  if (s) return s;
+  LSD_CUDA(cudaStreamSynchronize(l->stream));
+  if (gpu_ms_last) *gpu_ms_last = l->last_gpu_ms;
+  if (n_added_last) *n_added_last = l->last_added;
   return LSD_OK;
 }
 lsd_status_t lsd_lio_set_profile(lsd_lio_t* l, int on) {
@@ -887,7 +951,7 @@ lsd_status_t lsd_lio_update(lsd_lio_t* l, double* state26_inout, double* P529_in
 lsd_status_t lsd_lio_map_incremental(lsd_lio_t* l, const double* state26, int* n_added) {
   if (!l || !state26) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(l->device));
-  lsd_status_t s = lio_map_incremental(l, state26, 1, n_added);
+  lsd_status_t s = lio_map_incremental(l, state26, 1, n_added, true);
   if (s == LSD_OK) l->map_cells_known = 1;
   return s;
 }

@@ -27,8 +27,13 @@ struct lsd_lio {
   double* d_partials = nullptr;
   unsigned* d_done = nullptr;
   unsigned* d_added = nullptr;
-  double* d_result = nullptr;
-  double* h_result = nullptr;   // pinned
+  double* h_result = nullptr;   // pinned + mapped: the reduction result the kernels publish
+  double* d_result = nullptr;   // device alias of h_result
+  unsigned* h_added = nullptr;  // pinned: insert count of the last map_incremental
+  bool pending = false;         // an async lio_scan left its end event / insert count uncollected
+  double last_gpu_ms = 0.0;
+  int last_added = 0;
+  long long seq = 0;            // sequence number of the last published result
   int max_search_blocks = 888;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_bound = 1;   // launch bound for per-point kernels (>= true feats_down_size)
