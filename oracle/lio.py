@@ -24,8 +24,17 @@ class OracleLio:
     FILTER_MAP = 0.5  # laserMapping.cpp:1028
 
     def __init__(self, nearby: int = 18, knn_exact: bool = False, expected_cells: int = 1 << 18,
-                 nthreads: int = 8, degenerate_detect: bool = True):
-        self.map = O.OracleIvox(0.5, nearby, expected_cells)  # laserMapping.cpp:1060-1065
+                 nthreads: int = 8, degenerate_detect: bool = True, backend: str = "port"):
+        """backend "port": oracle/lsd_oracle.c; "reference": the compiled reference IVox +
+        esti_plane (oracle/_ref) inside the same restated loop."""
+        self.backend = backend
+        if backend == "reference":
+            assert O.HAVE_REF and not knn_exact
+            self.map = O.RefIvox(0.5, nearby)
+            self._hm, self._mi = O.ref.ref_lio_hmodel, O.ref.ref_map_incremental
+        else:
+            self.map = O.OracleIvox(0.5, nearby, expected_cells)  # laserMapping.cpp:1060-1065
+            self._hm, self._mi = O.port.orc_lio_hmodel, O.port.orc_map_incremental
         self.knn_mode = 1 if knn_exact else 0
         self.nthreads = nthreads
         self.degenerate_detect = degenerate_detect
@@ -37,7 +46,7 @@ class OracleLio:
 
     # -- map seeding (first scan / prebuilt map) : ivox->AddPoints, laserMapping.cpp:1227-1239
     def add_map_points(self, world_xyz: np.ndarray):
-        self.map.add(np.ascontiguousarray(world_xyz[:, :3], np.float32), self.next_id)
+        self.map.add(np.ascontiguousarray(world_xyz[:, :4] if self.backend == "reference" else world_xyz[:, :3], np.float32), self.next_id)
         self.next_id += world_xyz.shape[0]
 
     def _hmodel(self, body, st: eskf.State, converge: bool):
@@ -50,7 +59,7 @@ class OracleLio:
         degen = np.zeros(1, np.int32)
         hx = np.zeros((max(n, 1), 6))
         hh = np.zeros(max(n, 1))
-        ne = O.port.orc_lio_hmodel(self.map.h, body, n, R, np.ascontiguousarray(st.pos), R_LI,
+        ne = self._hm(self.map.h, body, n, R, np.ascontiguousarray(st.pos), R_LI,
                                    np.ascontiguousarray(st.offset_T_L_I), int(converge), self.knn_mode,
                                    self.near_xyz, self.near_ids, self.near_cnt, self.selected, self.world,
                                    self.plane, HTH6, HTh6, res_sum, degen, int(self.degenerate_detect),
@@ -118,7 +127,7 @@ class OracleLio:
         R = np.ascontiguousarray(eskf.quat_to_R(st.rot))
         R_LI = np.ascontiguousarray(eskf.quat_to_R(st.offset_R_L_I))
         self.flags = np.zeros(n, np.uint8)
-        added = O.port.orc_map_incremental(self.map.h, body, n, R, np.ascontiguousarray(st.pos), R_LI,
+        added = self._mi(self.map.h, body, n, R, np.ascontiguousarray(st.pos), R_LI,
                                            np.ascontiguousarray(st.offset_T_L_I), self.near_xyz, self.near_cnt,
                                            int(self.ekf_inited), self.FILTER_MAP, self.world, self.flags, self.next_id)
         self.next_id += n

@@ -66,6 +66,12 @@ def _load_ref():
     L.ref_ikd_build.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
     L.ref_ikd_knn.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _i, _f, _i, C.c_int]
     L.ref_esti_plane.argtypes = [_f, C.c_int, C.c_float, _f, _i]
+    if hasattr(L, "ref_lio_hmodel"):
+        L.ref_lio_hmodel.restype = C.c_int
+        L.ref_lio_hmodel.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, C.c_int, C.c_int, _f, _i, _i, _u8,
+                                     _f, _f, _d, _d, _d, _i, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_map_incremental.restype = C.c_int
+        L.ref_map_incremental.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, _f, _i, C.c_int, C.c_double, _f, _u8, C.c_int]
     return L
 
 

@@ -122,4 +122,153 @@ void ref_esti_plane(const float* pts5, int n, float thr, float* pabcd, int* ok) 
   }
 }
 
+
+// ---------------------------------------------------------------- full h-model on reference classes
+// Restates the loop of h_share_model_geometric (laserMapping.cpp:813-982) around the UNMODIFIED
+// reference IVox::GetClosestPoint and esti_plane<float> (Eigen ColPivHouseholderQR), with Eigen's
+// SelfAdjointEigenSolver for the degeneracy test exactly as the reference does.  Same signature as
+// orc_lio_hmodel (oracle/lsd_oracle.c) so oracle/lio.py can drive either.
+int ref_lio_hmodel(void* hv, const float* body, int n, const double* R_, const double* t_, const double* RL_,
+                   const double* tL_, int search, int /*knn_mode*/, float* near_xyz, int* near_ids, int* near_cnt,
+                   unsigned char* selected, float* world, float* plane, double* HTH, double* HTh, double* res_sum,
+                   int* degenerate, int degenerate_detect_en, double* hx_out, double* h_out, int nthreads) {
+  IVoxType* iv = static_cast<IVoxType*>(hv);
+  Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>> R(R_), RL(RL_);
+  Eigen::Map<const V3D> t(t_), tL(tL_);
+  omp_set_num_threads(nthreads > 0 ? nthreads : 1);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < n; i++) {
+    const float* pb = body + 4 * (size_t)i;
+    V3D p_body(pb[0], pb[1], pb[2]);
+    V3D p_global(R * (RL * p_body + tL) + t);
+    PointType point_world;
+    point_world.x = p_global(0); point_world.y = p_global(1); point_world.z = p_global(2);
+    float* w = world + 4 * (size_t)i;
+    w[0] = point_world.x; w[1] = point_world.y; w[2] = point_world.z; w[3] = pb[3];
+    PointVector points_near;
+    if (search) {
+      iv->GetClosestPoint(point_world, points_near, NUM_MATCH_POINTS, 5);
+      int c = int(points_near.size());
+      near_cnt[i] = c;
+      for (int j = 0; j < 5; j++) {
+        near_ids[5 * (size_t)i + j] = j < c ? id_of(points_near[j]) : -1;
+        for (int d = 0; d < 3; d++) near_xyz[(5 * (size_t)i + j) * 3 + d] = j < c ? (&points_near[j].x)[d] : 0.f;
+      }
+      selected[i] = c >= NUM_MATCH_POINTS;
+    } else if (selected[i]) {
+      points_near.resize(5);
+      for (int j = 0; j < 5; j++) for (int d = 0; d < 3; d++) (&points_near[j].x)[d] = near_xyz[(5 * (size_t)i + j) * 3 + d];
+    }
+    if (!selected[i]) continue;
+    VF(4) pabcd;
+    selected[i] = 0;
+    if (esti_plane(pabcd, points_near, 0.1f)) {
+      float pd2 = pabcd(0) * point_world.x + pabcd(1) * point_world.y + pabcd(2) * point_world.z + pabcd(3);
+      float s = 1 - 0.9 * fabs(pd2) / sqrt(p_body.norm());
+      if (s > 0.9) {
+        selected[i] = 1;
+        float* pl = plane + 4 * (size_t)i;
+        pl[0] = pabcd(0); pl[1] = pabcd(1); pl[2] = pabcd(2); pl[3] = pd2;
+      }
+    }
+  }
+  int ne = 0;
+  double total = 0.0;
+  for (int i = 0; i < n; i++) if (selected[i]) { total += std::abs(plane[4 * (size_t)i + 3]); ne++; }
+  *res_sum = total; *degenerate = 0;
+  memset(HTH, 0, sizeof(double) * 36); memset(HTh, 0, sizeof(double) * 6);
+  if (ne < 1) return 0;
+  Eigen::MatrixXd h_x = Eigen::MatrixXd::Zero(ne, 6);
+  Eigen::VectorXd h(ne);
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    if (!selected[i]) continue;
+    const float* pb = body + 4 * (size_t)i; const float* pl = plane + 4 * (size_t)i;
+    V3D point_this_be(pb[0], pb[1], pb[2]);
+    V3D point_this = RL * point_this_be + tL;
+    M3D point_crossmat;
+    point_crossmat << SKEW_SYM_MATRX(point_this);
+    V3D norm_vec(pl[0], pl[1], pl[2]);
+    V3D C(R.transpose() * norm_vec);
+    V3D A(point_crossmat * C);
+    h_x.row(k) << pl[0], pl[1], pl[2], A(0), A(1), A(2);
+    h(k) = -pl[3];
+    k++;
+  }
+  if (degenerate_detect_en) {  // laserMapping.cpp:934-980
+    Eigen::MatrixXd hn = h_x.leftCols(3);
+    Eigen::Matrix<double, 3, 3> H3 = hn.transpose() * hn;
+    Eigen::SelfAdjointEigenSolver<Eigen::Matrix<double, 3, 3>> esolver(H3);
+    Eigen::Matrix<double, 3, 3> mat_v = esolver.eigenvectors().real();
+    Eigen::Matrix<double, 3, 3> mat_v2 = mat_v.transpose();
+    bool deg = false;
+    for (int i = 0; i < 3; i++) {
+      float local_contri = 0, local_strong = 0;
+      for (int j = 0; j < ne; j++) {
+        V3D feat_row = hn.row(j).transpose();
+        feat_row.normalize();
+        V3D dir = mat_v.col(i);
+        const float dotp = fabs(feat_row.dot(dir));
+        if (dotp > 0.1736) local_contri += dotp;
+        if (dotp > 0.7070) local_strong += dotp;
+      }
+      if (local_contri < 250.0 && local_strong < 50.0) { for (int j = 0; j < 3; j++) mat_v2(i, j) = 0; deg = true; }
+    }
+    if (deg) {
+      Eigen::Matrix<double, 3, 3> mat_p = mat_v.transpose().inverse() * mat_v2;
+      h_x.leftCols(3) = (mat_p * hn.transpose()).transpose();
+      *degenerate = 1;
+    }
+  }
+  Eigen::Matrix<double, 6, 6> M = h_x.transpose() * h_x;
+  Eigen::Matrix<double, 6, 1> v = h_x.transpose() * h;
+  for (int a = 0; a < 6; a++) { for (int b = 0; b < 6; b++) HTH[6 * a + b] = M(a, b); HTh[a] = v(a); }
+  if (hx_out) for (int r = 0; r < ne; r++) for (int c = 0; c < 6; c++) hx_out[6 * (size_t)r + c] = h_x(r, c);
+  if (h_out) for (int r = 0; r < ne; r++) h_out[r] = h(r);
+  return ne;
+}
+
+// map_incremental (laserMapping.cpp:523-576) feeding the reference IVox::AddPoints.
+int ref_map_incremental(void* hv, const float* body, int n, const double* R_, const double* t_, const double* RL_,
+                        const double* tL_, const float* near_xyz, const int* near_cnt, int ekf_inited, double fsize,
+                        float* world, unsigned char* flag, int id0) {
+  IVoxType* iv = static_cast<IVoxType*>(hv);
+  Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>> R(R_), RL(RL_);
+  Eigen::Map<const V3D> t(t_), tL(tL_);
+  PointVector PointToAdd, PointNoNeedDownsample;
+  for (int i = 0; i < n; i++) {
+    const float* pb = body + 4 * (size_t)i;
+    V3D p_body(pb[0], pb[1], pb[2]);
+    V3D p_global(R * (RL * p_body + tL) + t);
+    PointType pw = mk(pb, id0 + i);
+    pw.x = p_global(0); pw.y = p_global(1); pw.z = p_global(2);
+    float* w = world + 4 * (size_t)i;
+    w[0] = pw.x; w[1] = pw.y; w[2] = pw.z; w[3] = pb[3];
+    int f = 1;
+    if (near_cnt[i] > 0 && ekf_inited) {
+      PointType mid_point, n0;
+      const float* nr = near_xyz + 15 * (size_t)i;
+      n0.x = nr[0]; n0.y = nr[1]; n0.z = nr[2];
+      mid_point.x = floor(pw.x / fsize) * fsize + 0.5 * fsize;
+      mid_point.y = floor(pw.y / fsize) * fsize + 0.5 * fsize;
+      mid_point.z = floor(pw.z / fsize) * fsize + 0.5 * fsize;
+      float dist = calc_dist(pw, mid_point);
+      if (fabs(n0.x - mid_point.x) > 0.5 * fsize && fabs(n0.y - mid_point.y) > 0.5 * fsize && fabs(n0.z - mid_point.z) > 0.5 * fsize) {
+        f = 2;
+      } else {
+        for (int r = 0; r < NUM_MATCH_POINTS; r++) {
+          if (near_cnt[i] < NUM_MATCH_POINTS) break;
+          PointType q; q.x = nr[3 * r]; q.y = nr[3 * r + 1]; q.z = nr[3 * r + 2];
+          if (calc_dist(q, mid_point) < dist) { f = 0; break; }
+        }
+      }
+    }
+    flag[i] = (unsigned char)f;
+    if (f == 1) PointToAdd.push_back(pw); else if (f == 2) PointNoNeedDownsample.push_back(pw);
+  }
+  iv->AddPoints(PointToAdd, 0.0);
+  iv->AddPoints(PointNoNeedDownsample, 0.0);
+  return int(PointToAdd.size() + PointNoNeedDownsample.size());
+}
+
 }  // extern "C"

@@ -116,3 +116,30 @@ def test_oracle_lio_converges():
     assert r["iters"] >= 3 and r["log"][-1]["n_eff"] > 500
     assert np.abs(lio.x.pos - tgt).max() < 0.03
     assert np.linalg.norm(eskf.so3_log(eskf.R_to_quat(Rgt.T @ eskf.quat_to_R(lio.x.rot)))) < 2e-3
+
+
+@pytest.mark.skipif(not (O.HAVE_REF and hasattr(O.ref, "ref_lio_hmodel")), reason="oracle/_ref not built")
+def test_full_lio_loop_port_equals_reference_classes():
+    """The whole per-scan loop (k-NN, plane fit, gate, H rows, degeneracy, ESKF, map_incremental) run on
+    the COMPILED reference IVox + esti_plane (Eigen QR) + Eigen eigensolver vs the plain-C port:
+    identical effective-point counts at every iteration, identical insert decisions, pose within
+    1e-6 m / 1e-7 rad (the only difference left is QR rounding)."""
+    from lsdreg import synth
+    from oracle import eskf
+    from oracle.lio import OracleLio
+    m = synth.block_map(1, 1, 2, 0.5)
+    Rgt = synth.rot_from_rpy(0.01, -0.02, 0.3)
+    tgt = synth.block_center(0, 0) + np.array([1.0, -2.0, 0.0])
+    scan = synth.scan64(2, 200, Rgt, tgt)
+    dR, dt = synth.perturb(5)
+    out = {}
+    for be in ("port", "reference"):
+        lio = OracleLio(18, expected_cells=1 << 17, backend=be)
+        lio.add_map_points(m)
+        prior = eskf.State(); prior.rot = eskf.R_to_quat(Rgt @ dR); prior.pos = tgt + dt
+        r = lio.process_scan(scan, prior, eskf.init_P())
+        out[be] = (lio.x.to_vec(), [l["n_eff"] for l in r["log"]], r["added"], lio.map.num_cells)
+    (xp, np_, ap, cp), (xr, nr, ar, cr) = out["port"], out["reference"]
+    assert np_ == nr and ap == ar and cp == cr
+    assert np.abs(xp[:3] - xr[:3]).max() < 1e-6
+    assert np.linalg.norm(eskf.so3_log(eskf.quat_mul(eskf.quat_conj(xp[3:7]), xr[3:7]))) < 1e-7
