@@ -63,6 +63,9 @@ typedef struct lsd_map lsd_map_t;
 lsd_status_t lsd_map_create(lsd_map_t** out, float resolution, int log2_lines);
 lsd_status_t lsd_map_destroy(lsd_map_t* m);
 lsd_status_t lsd_map_clear(lsd_map_t* m);
+/* Tile sharding: the map keeps only points in x-y tiles (tile_cells voxels wide) this
+ * rank owns, plus a halo of reach_cells voxels; queries are answered from the local shard. */
+lsd_status_t lsd_map_set_shard(lsd_map_t* m, int rank, int world, int tile_cells, int reach_cells);
 /* IVox::AddPoints.  Point i is stored with id = id0 + i (ids are what k-NN queries return). */
 lsd_status_t lsd_map_insert(lsd_map_t* m, const float* xyzi_host, int n, int32_t id0);
 lsd_status_t lsd_map_insert_dev(lsd_map_t* m, const float* xyzi_dev, int n, int32_t id0);
@@ -149,6 +152,18 @@ lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, l
 /* Per-kernel CUDA-event timing for the roofline report (adds a sync per launch: never enable it in a
  * throughput measurement).  ms4/cnt4: [0] h-model with k-NN search, [1] h-model reusing neighbours,
  * [2] voxel grid (7 kernels), [3] map_incremental. */
+/* Tile-sharded LIO across the GPUs of one box (no reference counterpart: the reference is single-GPU /
+ * CPU).  Every rank runs the same lsd_lio_* calls in lock-step on the same scans; a rank
+ * resolves the queries whose home voxel it owns, the 30-double normal equations are all-reduced inside
+ * the reduction kernel through peer memory (NVLink stores into every rank's inbox, rank-ordered fold),
+ * and map_incremental's decisions are exchanged the same way so halo copies stay consistent.
+ *   1. every rank: lsd_lio_shard_export(l, rank, world, tile_cells, reach_cells, blob)   (<= 8 ranks)
+ *   2. all-gather the LSD_SHARD_BLOB_BYTES blobs (torch.distributed / MPI / a pipe)
+ *   3. every rank: lsd_lio_shard_connect(l, blobs[world])
+ * reach_cells: 1 for NEARBY6/18/26, 2 for NEARBY74, ceil(sqrt(5)/res)+1 for the exact search. */
+#define LSD_SHARD_BLOB_BYTES 192
+lsd_status_t lsd_lio_shard_export(lsd_lio_t* l, int rank, int world, int tile_cells, int reach_cells, unsigned char* blob_out);
+lsd_status_t lsd_lio_shard_connect(lsd_lio_t* l, const unsigned char* blobs);
 /* Wait for everything queued on the handle; returns device time / insert count of the last scan. */
 lsd_status_t lsd_lio_sync(lsd_lio_t* l, double* gpu_ms_last, int* n_added_last);
 lsd_status_t lsd_lio_set_profile(lsd_lio_t* l, int on);

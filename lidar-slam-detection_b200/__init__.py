@@ -4,7 +4,7 @@ Import as ``import lsdreg`` (alias module at the repo root; the directory name c
 The compute path is liblsdreg.so (hand-written sm_100a CUDA behind a C ABI, include/lsdreg.h);
 this package is its thin host-side mirror.  See DESIGN.md / INTEGRATION.md.
 """
-from . import synth  # noqa: F401
+from . import shard, synth  # noqa: F401
 from .capi import (  # noqa: F401
     ERR_CAPACITY, ERR_CUDA, ERR_GRID_OVERFLOW, ERR_INVALID, ERR_NO_DEVICE, MAP_SEEDED, NO_EFFECTIVE_POINTS, OK,
     SCAN_TOO_SMALL, STENCIL_CENTER, STENCIL_EXACT, STENCIL_NEARBY6, STENCIL_NEARBY18, STENCIL_NEARBY26,

@@ -53,6 +53,7 @@ SIGNATURES = [
     ("lsd_map_create", _i, [_pp, _f, _i]),
     ("lsd_map_destroy", _i, [_vp]),
     ("lsd_map_clear", _i, [_vp]),
+    ("lsd_map_set_shard", _i, [_vp, _i, _i, _i, _i]),
     ("lsd_map_insert", _i, [_vp, _vp, _i, C.c_int32]),
     ("lsd_map_insert_dev", _i, [_vp, _vp, _i, C.c_int32]),
     ("lsd_map_stats", _i, [_vp, _pu64, _pu64, _pu64]),
@@ -69,6 +70,8 @@ SIGNATURES = [
     ("lsd_lio_set_nearby", _i, [_vp, _i]),
     ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
     ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
+    ("lsd_lio_shard_export", _i, [_vp, _i, _i, _i, _i, _vp]),
+    ("lsd_lio_shard_connect", _i, [_vp, _vp]),
     ("lsd_lio_sync", _i, [_vp, C.POINTER(_d), _pi]),
     ("lsd_lio_set_profile", _i, [_vp, _i]),
     ("lsd_lio_get_profile", _i, [_vp, _vp, _vp]),
@@ -272,6 +275,17 @@ class LioFrontend:
 
     def set_ekf_inited(self, flag: bool):
         check(lib.lsd_lio_set_ekf_inited(self.h, int(flag)))
+
+    SHARD_BLOB_BYTES = 192
+
+    def shard_export(self, rank: int, world: int, tile_cells: int = 32, reach_cells: int = 1) -> np.ndarray:
+        blob = np.zeros(self.SHARD_BLOB_BYTES, np.uint8)
+        check(lib.lsd_lio_shard_export(self.h, rank, world, tile_cells, reach_cells, _ptr(blob)))
+        return blob
+
+    def shard_connect(self, blobs: np.ndarray):
+        blobs = np.ascontiguousarray(blobs, np.uint8)
+        check(lib.lsd_lio_shard_connect(self.h, _ptr(blobs)))
 
     def sync(self):
         """Drain the handle's stream -> (gpu_ms, n_added) of the last scan."""

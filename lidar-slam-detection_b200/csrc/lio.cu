@@ -13,6 +13,8 @@
 // entries of the non-zero 6x6 block + 6 entries of h_x^T h + sum|res| + count are reduced by warp
 // shuffles, per-block partials go to HBM and the last block to finish folds them in a fixed order
 // (bit-reproducible).  No N x 15 matrix ever exists.
+#include <unistd.h>
+
 #include "eskf.hpp"
 #include "knn.cuh"
 #include "lio.h"
@@ -194,7 +196,7 @@ static void eig3_sym(const double* Ain, double* V, double* w) {
 template <int NV>
 __device__ __forceinline__ void grid_finalize(double* __restrict__ partials, unsigned* __restrict__ done,
                                               volatile double* __restrict__ result, int res_off, int n_extra_slot, double extra,
-                                              int seq_slot, double seq) {
+                                              int seq_slot, double seq, const ShardComm& sc, int inbox_region) {
   __shared__ double sm_fin[8][kNV];
   __shared__ bool is_last;
   __threadfence();
@@ -223,7 +225,39 @@ __device__ __forceinline__ void grid_finalize(double* __restrict__ partials, uns
   if (threadIdx.x < NV) {
     double t = 0.0;
     for (int w = 0; w < slices; w++) t += sm_fin[w][threadIdx.x];
-    result[res_off + threadIdx.x] = t;
+    sm_fin[0][threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (sc.world > 1) {
+    // Cross-rank all-reduce fused into the reduction kernel: the last block stores this rank's totals
+    // into every rank's inbox over NVLink, publishes a sequence number, waits for the other ranks'
+    // and folds the world's contributions in rank order (deterministic).  No NCCL call, no extra launch.
+    const long long iseq = (long long)seq;
+    const size_t base = (size_t)inbox_region * kInboxRegion + (size_t)((iseq & 1) * kMaxRanks) * kInboxSlot;
+    if (threadIdx.x < NV) {
+      const double v = sm_fin[0][threadIdx.x];
+      for (int p = 0; p < sc.world; p++) sc.inbox[p][base + (size_t)sc.rank * kInboxSlot + threadIdx.x] = v;
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < sc.world) {
+      volatile double* flag = sc.inbox[threadIdx.x] + base + (size_t)sc.rank * kInboxSlot + (kInboxSlot - 1);
+      *flag = seq;
+      __threadfence_system();
+      volatile double* mine = sc.inbox[sc.rank] + base + (size_t)threadIdx.x * kInboxSlot + (kInboxSlot - 1);
+      while (*mine != seq) {}
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x < NV) {
+      double t = 0.0;
+      for (int r = 0; r < sc.world; r++) t += *(volatile double*)(sc.inbox[sc.rank] + base + (size_t)r * kInboxSlot + threadIdx.x);
+      sm_fin[0][threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < NV) {
+    result[res_off + threadIdx.x] = sm_fin[0][threadIdx.x];
     __threadfence_system();
   }
   __syncthreads();
@@ -299,6 +333,10 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
     const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
     const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
     const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+    if (mv.shard_world > 1) {  // tile-sharded: only the owner of the query's home voxel resolves it
+      const int3 hc = pos2grid(wx, wy, wz, mv.inv_res);
+      if (!shard_owns(mv, hc.x, hc.y)) { if (lane == 0) near_cnt[i] = -1; continue; }
+    }
     Neighbor nb;
     const int nf = knn_search_warp<5>(mv, stencil, ls, wx, wy, wz, 5.0f, wl, nb);
     float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
@@ -320,7 +358,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
                                                                float4* __restrict__ pabcd_io, unsigned char* __restrict__ plane_ok,
                                                                float4* __restrict__ plane, float4* __restrict__ world,
                                                                double* __restrict__ partials, unsigned* __restrict__ done,
-                                                               double* __restrict__ result, double seq) {
+                                                               double* __restrict__ result, double seq, ShardComm sc) {
   const int n_true = *n_ptr;
   const int n = min(n_true, cap);
   double vals[29];
@@ -376,7 +414,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
     selected[i] = keep ? 1 : 0;
   }
   block_partials<29>(vals, partials);
-  grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq);
+  grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq, sc, 0);
 }
 
 // ---------------------------------------------------------------- degeneracy sums (laserMapping.cpp:946-970)
@@ -385,7 +423,8 @@ struct Eig3 { double V[9]; };  // columns = eigenvectors
 __global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restrict__ n_ptr, int cap,
                                                               const unsigned char* __restrict__ selected,
                                                               const float4* __restrict__ plane, Eig3 e, double* __restrict__ partials,
-                                                              unsigned* __restrict__ done, double* __restrict__ result, double seq) {
+                                                              unsigned* __restrict__ done, double* __restrict__ result, double seq,
+                                                              ShardComm sc) {
   const int n = min(*n_ptr, cap);
   const double* V = e.V;
   double vals[6] = {0, 0, 0, 0, 0, 0};
@@ -402,7 +441,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restr
     }
   }
   block_partials<6>(vals, partials);
-  grid_finalize<6>(partials, done, result, kResDegen, -1, 0.0, kResSeqDegen, seq);
+  grid_finalize<6>(partials, done, result, kResDegen, -1, 0.0, kResSeqDegen, seq, sc, 1);
 }
 
 // ---------------------------------------------------------------- map_incremental (laserMapping.cpp:523-576)
@@ -414,40 +453,87 @@ __global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, co
                                                                   const float4* __restrict__ near, const int* __restrict__ near_cnt,
                                                                   int ekf_inited, double fsize, int id0, int use_near,
                                                                   float4* __restrict__ world, unsigned char* __restrict__ flags,
-                                                                  unsigned* __restrict__ n_added) {
+                                                                  unsigned* __restrict__ n_added, ShardComm sc, double seq,
+                                                                  unsigned* __restrict__ done) {
   const int n = min(*n_ptr, cap);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 pb = __ldg(body + i);
-  const double bx = pb.x, by = pb.y, bz = pb.z;
-  const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
-  const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
-  const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
-  const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
-  const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
-  const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
-  world[i] = make_float4(wx, wy, wz, pb.w);
-  int f = 1;  // PointToAdd
-  const int cnt = use_near ? near_cnt[i] : 0;
-  if (cnt > 0 && ekf_inited) {
-    const float mx = (float)(floor((double)wx / fsize) * fsize + 0.5 * fsize);
-    const float my = (float)(floor((double)wy / fsize) * fsize + 0.5 * fsize);
-    const float mz = (float)(floor((double)wz / fsize) * fsize + 0.5 * fsize);
-    const float dist = calc_dist3(wx, wy, wz, mx, my, mz);
-    const float4 n0 = near[(size_t)i * 5];
-    if ((double)fabsf(n0.x - mx) > 0.5 * fsize && (double)fabsf(n0.y - my) > 0.5 * fsize && (double)fabsf(n0.z - mz) > 0.5 * fsize) {
-      f = 2;  // PointNoNeedDownsample
-    } else if (cnt >= 5) {
+  if (i < n) {
+    const float4 pb = __ldg(body + i);
+    const double bx = pb.x, by = pb.y, bz = pb.z;
+    const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+    const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+    const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+    const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
+    const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
+    const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+    world[i] = make_float4(wx, wy, wz, pb.w);
+    bool mine = true;
+    if (sc.world > 1) { const int3 hc = pos2grid(wx, wy, wz, mv.inv_res); mine = shard_owns(mv, hc.x, hc.y); }
+    if (mine) {
+      int f = 1;  // PointToAdd
+      const int cnt = use_near ? near_cnt[i] : 0;
+      if (cnt > 0 && ekf_inited) {
+        const float mx = (float)(floor((double)wx / fsize) * fsize + 0.5 * fsize);
+        const float my = (float)(floor((double)wy / fsize) * fsize + 0.5 * fsize);
+        const float mz = (float)(floor((double)wz / fsize) * fsize + 0.5 * fsize);
+        const float dist = calc_dist3(wx, wy, wz, mx, my, mz);
+        const float4 n0 = near[(size_t)i * 5];
+        if ((double)fabsf(n0.x - mx) > 0.5 * fsize && (double)fabsf(n0.y - my) > 0.5 * fsize && (double)fabsf(n0.z - mz) > 0.5 * fsize) {
+          f = 2;  // PointNoNeedDownsample
+        } else if (cnt >= 5) {
 #pragma unroll
-      for (int r = 0; r < 5; r++) {
-        const float4 q = near[(size_t)i * 5 + r];
-        if (calc_dist3(q.x, q.y, q.z, mx, my, mz) < dist) f = 0;
+          for (int r = 0; r < 5; r++) {
+            const float4 q = near[(size_t)i * 5 + r];
+            if (calc_dist3(q.x, q.y, q.z, mx, my, mz) < dist) f = 0;
+          }
+        }
       }
+      flags[i] = (unsigned char)f;
+      if (f) {
+        map_insert_point(mv, wx, wy, wz, id0 + i);
+        atomicAdd(n_added, 1u);
+      }
+      // halo exchange, step 1: tell every other rank what was decided for this point
+      for (int p = 0; p < sc.world; p++) if (p != sc.rank) sc.flagbox[p][i] = (unsigned char)f;
     }
   }
-  flags[i] = (unsigned char)f;
-  if (f) {
-    map_insert_point(mv, wx, wy, wz, id0 + i);
+  if (sc.world > 1) {  // last block: all decisions of this rank are out -> publish the sequence number
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && threadIdx.x < sc.world) {
+      volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(sc.flagbox[threadIdx.x] + cap) + sc.rank;
+      *d = (unsigned long long)seq;
+      __threadfence_system();
+      if (threadIdx.x == 0) *done = 0u;
+    }
+  }
+}
+
+// halo exchange, step 2: insert the points other ranks decided to add that fall in this rank's halo
+// (their world coordinates are known locally: every rank holds the whole downsampled scan).
+__global__ void __launch_bounds__(256) lio_halo_insert_kernel(MapView mv, const int* __restrict__ n_ptr, int cap,
+                                                              const float4* __restrict__ world, int id0, ShardComm sc, double seq,
+                                                              unsigned* __restrict__ n_added) {
+  __shared__ int ready;
+  if (threadIdx.x < sc.world && threadIdx.x != sc.rank) {
+    volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(sc.flagbox[sc.rank] + cap) + threadIdx.x;
+    while (*d != (unsigned long long)seq) {}
+  }
+  if (threadIdx.x == 0) ready = 1;
+  __syncthreads();
+  __threadfence_system();
+  const int n = min(*n_ptr, cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !ready) return;
+  const float4 w = world[i];
+  const int3 hc = pos2grid(w.x, w.y, w.z, mv.inv_res);
+  if (shard_owns(mv, hc.x, hc.y) || !shard_relevant(mv, hc.x, hc.y)) return;
+  const unsigned char f = *(volatile unsigned char*)(sc.flagbox[sc.rank] + i);
+  if (f == 1 || f == 2) {
+    map_insert_point(mv, w.x, w.y, w.z, id0 + i);
     atomicAdd(n_added, 1u);
   }
 }
@@ -513,12 +599,12 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
     lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt);
     lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                                        l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                                       l->d_partials, l->d_done, l->d_result, seq);
+                                                                       l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches += 2;
   } else {
     lio_hmodel_kernel<false><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                                         l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                                        l->d_partials, l->d_done, l->d_result, seq);
+                                                                        l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches++;
   }
   LSD_CUDA(cudaGetLastError());
@@ -549,7 +635,7 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
       Eig3 e;
       memcpy(e.V, V, sizeof(V));
       lio_degen_kernel<<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_n, l->p.max_points, l->d_selected, l->d_plane, e, l->d_partials,
-                                                                  l->d_done, l->d_result, seq);
+                                                                  l->d_done, l->d_result, seq, l->sc);
       LSD_CUDA(cudaGetLastError());
       l->launches++;
       { lsd_status_t w = wait_seq(l, kResSeqDegen, seq); if (w) return w; }
@@ -658,10 +744,17 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
   LSD_CUDA(cudaMemsetAsync(l->d_added, 0, sizeof(unsigned), st));
   ProfScope prof(l, 3);
   const int nb = std::max(1, (l->n_bound + 255) / 256);
+  const double mseq = (double)(++l->mi_seq);
   lio_map_incremental_kernel<<<nb, 256, 0, st>>>(l->map->view, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt, l->ekf_inited,
-                                                 (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added);
+                                                 (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added,
+                                                 l->sc, mseq, l->d_done);
   LSD_CUDA(cudaGetLastError());
   l->launches++;
+  if (l->sc.world > 1) {
+    lio_halo_insert_kernel<<<nb, 256, 0, st>>>(l->map->view, l->d_n, l->p.max_points, l->d_world, l->next_id, l->sc, mseq, l->d_added);
+    LSD_CUDA(cudaGetLastError());
+    l->launches++;
+  }
   prof.stop();
   LSD_CUDA(cudaMemcpyAsync(l->h_added, l->d_added, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   l->next_id += l->n_bound;
@@ -785,6 +878,8 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   if (s) return s;
   lsd_lio* l = new lsd_lio();
   l->p = *p;
+  memset(&l->sc, 0, sizeof(l->sc));
+  l->sc.world = 1;
   cudaGetDevice(&l->device);
   s = lsd_map_create(&l->map, p->ivox_resolution, p->map_log2_lines);
   if (s) { delete l; return s; }
@@ -836,6 +931,8 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
                   l->d_partials, l->d_done, l->d_added, l->d_pabcd, l->d_plane_ok};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(l->h_result); cudaFreeHost(l->h_added);
+  for (void* q : l->ipc_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(l->d_inbox); cudaFree(l->d_flagbox);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->pev[0]) cudaEventDestroy(l->pev[0]);
@@ -855,6 +952,74 @@ lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil) {
   l->p.ivox_nearby = stencil;
   return LSD_OK;
 }
+// Blob a rank publishes so the others can reach its inbox / flag box: same-process peers use the raw
+// device pointers, other processes open the cudaIpc handles.
+struct ShardBlob {
+  long long pid;
+  unsigned long long inbox, flagbox;
+  cudaIpcMemHandle_t h_inbox, h_flagbox;
+};
+static_assert(sizeof(ShardBlob) <= LSD_SHARD_BLOB_BYTES, "LSD_SHARD_BLOB_BYTES too small");
+
+lsd_status_t lsd_lio_shard_export(lsd_lio_t* l, int rank, int world, int tile_cells, int reach_cells, unsigned char* blob_out) {
+  if (!l || !blob_out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { set_error("lsd_lio_shard_export: bad rank/world (max %d ranks)", kMaxRanks); return LSD_ERR_INVALID; }
+  LSD_CUDA(cudaSetDevice(l->device));
+  lsd_status_t s = lsd_map_set_shard(l->map, rank, world, tile_cells, reach_cells);
+  if (s) return s;
+  if (!l->d_inbox) {
+    LSD_CUDA(cudaMalloc((void**)&l->d_inbox, 2 * kInboxRegion * sizeof(double)));
+    LSD_CUDA(cudaMemset(l->d_inbox, 0, 2 * kInboxRegion * sizeof(double)));
+    const size_t fb = (size_t)l->p.max_points + kMaxRanks * sizeof(unsigned long long) + 64;
+    LSD_CUDA(cudaMalloc((void**)&l->d_flagbox, fb));
+    LSD_CUDA(cudaMemset(l->d_flagbox, 0, fb));
+    LSD_CUDA(cudaDeviceSynchronize());
+  }
+  ShardBlob b;
+  memset(&b, 0, sizeof(b));
+  b.pid = (long long)getpid();
+  b.inbox = (unsigned long long)l->d_inbox;
+  b.flagbox = (unsigned long long)l->d_flagbox;
+  LSD_CUDA(cudaIpcGetMemHandle(&b.h_inbox, l->d_inbox));
+  LSD_CUDA(cudaIpcGetMemHandle(&b.h_flagbox, l->d_flagbox));
+  memset(blob_out, 0, LSD_SHARD_BLOB_BYTES);
+  memcpy(blob_out, &b, sizeof(b));
+  l->shard_rank = rank; l->shard_world = world;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_lio_shard_connect(lsd_lio_t* l, const unsigned char* blobs) {
+  if (!l || !blobs || l->shard_world < 1 || !l->d_inbox) { set_error("lsd_lio_shard_connect: call lsd_lio_shard_export first"); return LSD_ERR_INVALID; }
+  LSD_CUDA(cudaSetDevice(l->device));
+  ShardComm sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.rank = l->shard_rank; sc.world = l->shard_world;
+  for (int p = 0; p < sc.world; p++) {
+    ShardBlob b;
+    memcpy(&b, blobs + (size_t)p * LSD_SHARD_BLOB_BYTES, sizeof(b));
+    if (p == sc.rank) { sc.inbox[p] = l->d_inbox; sc.flagbox[p] = l->d_flagbox; continue; }
+    if (b.pid == (long long)getpid()) {  // peer handle in this process (possibly another device)
+      sc.inbox[p] = reinterpret_cast<double*>(b.inbox);
+      sc.flagbox[p] = reinterpret_cast<unsigned char*>(b.flagbox);
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, sc.inbox[p]) == cudaSuccess && at.device != l->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+      }
+    } else {
+      void *pi = nullptr, *pf = nullptr;
+      LSD_CUDA(cudaIpcOpenMemHandle(&pi, b.h_inbox, cudaIpcMemLazyEnablePeerAccess));
+      LSD_CUDA(cudaIpcOpenMemHandle(&pf, b.h_flagbox, cudaIpcMemLazyEnablePeerAccess));
+      sc.inbox[p] = static_cast<double*>(pi);
+      sc.flagbox[p] = static_cast<unsigned char*>(pf);
+      l->ipc_opened.push_back(pi); l->ipc_opened.push_back(pf);
+    }
+  }
+  l->sc = sc;
+  l->seq = 0; l->mi_seq = 0;  // all ranks restart their sequence numbers together
+  return LSD_OK;
+}
+
 lsd_status_t lsd_lio_sync(lsd_lio_t* l, double* gpu_ms_last, int* n_added_last) {
   if (!l) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(l->device));

@@ -6,6 +6,18 @@
 
 struct lsd_map;
 struct lsd_voxelgrid;
+namespace lsd {
+// Tile-sharded mode: peers' device buffers, reachable with plain stores/loads over
+// NVLink (cudaIpc-opened, or the same process' own pointers).  inbox[p] / flagbox[p] belong to rank p.
+constexpr int kMaxRanks = 8;
+constexpr int kInboxSlot = 32;                                  // doubles per (parity, source rank)
+constexpr int kInboxRegion = 2 * kMaxRanks * kInboxSlot;        // h-model region, then the degeneracy region
+struct ShardComm {
+  int rank, world;
+  double* inbox[kMaxRanks];
+  unsigned char* flagbox[kMaxRanks];   // [cap] map_incremental decisions, then kMaxRanks u64 "done" sequence numbers
+};
+}  // namespace lsd
 
 struct lsd_lio {
   lsd_lio_params_t p{};
@@ -34,6 +46,13 @@ struct lsd_lio {
   double last_gpu_ms = 0.0;
   int last_added = 0;
   long long seq = 0;            // sequence number of the last published result
+  long long mi_seq = 0;         // sequence number of the last map_incremental (halo exchange)
+  // tile-sharded mode (lsd_lio_shard_*): peers' inboxes / flag boxes
+  int shard_rank = 0, shard_world = 1;
+  double* d_inbox = nullptr;
+  unsigned char* d_flagbox = nullptr;
+  std::vector<void*> ipc_opened;
+  lsd::ShardComm sc;
   int max_search_blocks = 888;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_bound = 1;   // launch bound for per-point kernels (>= true feats_down_size)

@@ -43,7 +43,31 @@ struct MapView {
   unsigned long long mask;  // n_lines - 1
   float res, inv_res;
   unsigned long long* counters;  // [0] cells, [1] points, [2] dropped
+  // tile sharding: world == 1 -> everything is local
+  int shard_rank, shard_world, shard_tile, shard_reach;
 };
+
+// Tile ownership: x-y tiles of `tile` voxels, owner = hash(tile) mod world.  A voxel is RELEVANT to a
+// rank when any voxel within `reach` (Chebyshev, x-y) of it is owned by that rank: relevant points are
+// replicated (halo), so the owner of a query's home voxel holds every point its stencil can touch.
+__host__ __device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+__host__ __device__ __forceinline__ int tile_owner(int cx, int cy, int tile, int world) {
+  const unsigned tx = (unsigned)floor_div(cx, tile), ty = (unsigned)floor_div(cy, tile);
+  unsigned h = tx * 73856093u ^ ty * 19349663u;
+  h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+  return (int)(h % (unsigned)world);
+}
+__host__ __device__ __forceinline__ bool shard_owns(const MapView& mv, int cx, int cy) {
+  return mv.shard_world <= 1 || tile_owner(cx, cy, mv.shard_tile, mv.shard_world) == mv.shard_rank;
+}
+__host__ __device__ __forceinline__ bool shard_relevant(const MapView& mv, int cx, int cy) {
+  if (mv.shard_world <= 1) return true;
+  const int r = mv.shard_reach;
+  return tile_owner(cx - r, cy - r, mv.shard_tile, mv.shard_world) == mv.shard_rank ||
+         tile_owner(cx + r, cy - r, mv.shard_tile, mv.shard_world) == mv.shard_rank ||
+         tile_owner(cx - r, cy + r, mv.shard_tile, mv.shard_world) == mv.shard_rank ||
+         tile_owner(cx + r, cy + r, mv.shard_tile, mv.shard_world) == mv.shard_rank;
+}
 
 __host__ __device__ __forceinline__ bool coord_ok(int x, int y, int z) {
   return x > -kCoordBias && x < kCoordBias && y > -kCoordBias && y < kCoordBias && z > -kCoordBias && z < kCoordBias;

@@ -90,6 +90,7 @@ __device__ __forceinline__ long long find_or_claim(const MapView& mv, unsigned l
 __device__ void map_insert_point(const MapView& mv, float x, float y, float z, int id) {
   int3 c = pos2grid(x, y, z, mv.inv_res);
   if (!coord_ok(c.x, c.y, c.z)) { atomicAdd(&mv.counters[2], 1ull); return; }
+  if (!shard_relevant(mv, c.x, c.y)) return;  // another rank's tile and not in our halo
   unsigned long long key0 = pack_key(c.x, c.y, c.z, 0);
   bool fresh;
   long long s = find_or_claim(mv, key0, &fresh);
@@ -195,6 +196,7 @@ lsd_status_t lsd_map_create(lsd_map_t** out, float resolution, int log2_lines) {
   m->view.mask = m->n_lines - 1;
   m->view.res = resolution;
   m->view.inv_res = (float)(1.0 / (double)resolution);  // ivox3d.h:58
+  m->view.shard_rank = 0; m->view.shard_world = 1; m->view.shard_tile = 32; m->view.shard_reach = 1;
   cudaError_t e = cudaMalloc(&m->view.lines, m->n_lines * sizeof(CellLine));
   if (e == cudaSuccess) e = cudaMalloc(&m->view.counters, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
@@ -210,6 +212,15 @@ lsd_status_t lsd_map_destroy(lsd_map_t* m) {
   cudaFree(m->view.lines); cudaFree(m->view.counters); cudaFree(m->scratch);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_set_shard(lsd_map_t* m, int rank, int world, int tile_cells, int reach_cells) {
+  if (!m || world < 1 || rank < 0 || rank >= world || tile_cells < 1 || reach_cells < 0 || 2 * reach_cells >= tile_cells) {
+    set_error("lsd_map_set_shard: need 0 <= rank < world and 2*reach < tile");
+    return LSD_ERR_INVALID;
+  }
+  m->view.shard_rank = rank; m->view.shard_world = world; m->view.shard_tile = tile_cells; m->view.shard_reach = reach_cells;
   return LSD_OK;
 }
 
