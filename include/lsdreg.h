@@ -195,6 +195,59 @@ lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* s
 lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double* state26_inout,
                               double* P529_inout, lsd_lio_info_t* info);
 
+/* ------------------------------------------------------------------------------------------
+ * Scan matcher — replaces what select_registration_method() hands out
+ * (slam/backend/hdl_graph_slam/include/hdl_graph_slam/registrations.hpp:15-16, registrations.cpp:29-155):
+ * fast_gicp::NDTCuda ("NDT_CUDA": P2D, DIRECT7, res 1.0, 64 iters, eps 0.01 / 0.1 deg) and
+ * fast_gicp::FastGICP ("FAST_GICP": k = 20, max-corr 2.0 m), both driven by
+ * fast_gicp::LsqRegistration's Levenberg-Marquardt loop (lsq_registration_impl.hpp:71-208), plus
+ * pcl::Registration::getFitnessScore.  Call protocol mirrors pcl::Registration:
+ *   setInputTarget -> lsd_reg_set_target, setInputSource -> lsd_reg_set_source,
+ *   align(out, guess) -> lsd_reg_align, hasConverged / getFinalTransformation -> its outputs,
+ *   getFitnessScore(max_range) -> lsd_reg_fitness, setMaxCorrespondenceDistance -> same name.
+ * Transforms are 4x4 row-major.  A handle is confined to one thread at a time; set_target on one handle may
+ * run concurrently with align on another (the localisation ping-pong, hdl_localization_nodelet.cpp:291-307).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_reg lsd_reg_t;
+#define LSD_REG_NDT_P2D 0
+#define LSD_REG_GICP 1
+
+typedef struct lsd_reg_params {
+  int kind;                       /* LSD_REG_NDT_P2D | LSD_REG_GICP                                        */
+  double resolution;              /* NDT voxel size (1.0, registrations.cpp:106)                          */
+  int ndt_neighbors;              /* 1 | 7 | 27 = DIRECT1 / DIRECT7 / DIRECT27 (ndt_cuda.cu:35-69)        */
+  int max_iterations;             /* 64                                                                   */
+  double transformation_epsilon;  /* 0.01                                                                 */
+  double rotation_epsilon_deg;    /* NDT 0.1; LsqRegistration default 1e-2 (compared against degrees)     */
+  int lm_max_iterations;          /* 10  (lsq_registration_impl.hpp:30)                                   */
+  double lm_init_lambda_factor;   /* 1e-9 (lsq_registration_impl.hpp:31)                                  */
+  int64_t max_process_time_us;    /* soft timeout, hard stop at 1.5x (lsq_registration_impl.hpp:94-104)   */
+  int k_correspondences;          /* GICP covariance neighbourhood, 20 (<= 20)                            */
+  double max_corr_dist;           /* GICP max correspondence distance, 2.0 m                              */
+  double normal_search_sq;        /* GICP: squared radius bounding the exact k-NN (25 m^2)                */
+  double map_resolution;          /* voxel size of the exact-NN index (0.5 m)                             */
+  int map_log2_lines;             /* hash table size, 0 = derive from the cloud size                      */
+} lsd_reg_params_t;
+
+void lsd_reg_default_params(lsd_reg_params_t* p, int kind);
+lsd_status_t lsd_reg_create(lsd_reg_t** out, const lsd_reg_params_t* p);
+lsd_status_t lsd_reg_destroy(lsd_reg_t* r);
+lsd_status_t lsd_reg_set_target(lsd_reg_t* r, const float* pts_host, int n);      /* [n,4] */
+lsd_status_t lsd_reg_set_target_dev(lsd_reg_t* r, const float* pts_dev, int n);
+lsd_status_t lsd_reg_set_source(lsd_reg_t* r, const float* pts_host, int n);
+lsd_status_t lsd_reg_set_source_dev(lsd_reg_t* r, const float* pts_dev, int n);
+lsd_status_t lsd_reg_set_max_correspondence_distance(lsd_reg_t* r, double d);
+/* align(): guess/out are float32[16] like Eigen::Matrix4f; *converged = hasConverged(). */
+lsd_status_t lsd_reg_align(lsd_reg_t* r, const float* guess16, float* out16, int* converged, int* iterations);
+lsd_status_t lsd_reg_get_final(lsd_reg_t* r, double* T16, double* H36);           /* double pose, getFinalHessian */
+/* getFitnessScore(max_range) at T16 (NULL = the final transformation).  NB PCL compares the SQUARED
+ * nearest-neighbour distance with max_range. */
+lsd_status_t lsd_reg_fitness(lsd_reg_t* r, const double* T16_or_null, double max_range, double* score);
+/* One cost evaluation (parity tap): update != 0 = linearize(T) (correspondences refreshed), else
+ * compute_error(T).  H36/b6 may be NULL. */
+lsd_status_t lsd_reg_cost(lsd_reg_t* r, const double* T16, int update, double* H36, double* b6, double* err, int* n_corr);
+lsd_status_t lsd_reg_stats(lsd_reg_t* r, int* n_voxels, long long* launches);
+
 /* Host-side manifold helpers (exported so bindings/tests use the same algebra as the filter).
  * IMU_Processing.hpp:224-230 initial covariance; state_ikfom boxplus/boxminus. */
 void lsd_lio_init_cov(double* P529);

@@ -41,6 +41,16 @@ class LioInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class RegParams(C.Structure):
+    _fields_ = [("kind", C.c_int), ("resolution", C.c_double), ("ndt_neighbors", C.c_int), ("max_iterations", C.c_int),
+                ("transformation_epsilon", C.c_double), ("rotation_epsilon_deg", C.c_double), ("lm_max_iterations", C.c_int),
+                ("lm_init_lambda_factor", C.c_double), ("max_process_time_us", C.c_int64), ("k_correspondences", C.c_int),
+                ("max_corr_dist", C.c_double), ("normal_search_sq", C.c_double), ("map_resolution", C.c_double),
+                ("map_log2_lines", C.c_int)]
+
+
+REG_NDT_P2D, REG_GICP = 0, 1
+
 # every symbol include/lsdreg.h declares: (name, restype, argtypes)
 _vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
 _pp = C.POINTER(C.c_void_p)
@@ -84,6 +94,19 @@ SIGNATURES = [
     ("lsd_lio_map_incremental", _i, [_vp, _vp, _pi]),
     ("lsd_lio_scan", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(LioInfo)]),
     ("lsd_lio_scan_dev", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(LioInfo)]),
+    ("lsd_reg_default_params", None, [C.POINTER(RegParams), _i]),
+    ("lsd_reg_create", _i, [_pp, C.POINTER(RegParams)]),
+    ("lsd_reg_destroy", _i, [_vp]),
+    ("lsd_reg_set_target", _i, [_vp, _vp, _i]),
+    ("lsd_reg_set_target_dev", _i, [_vp, _vp, _i]),
+    ("lsd_reg_set_source", _i, [_vp, _vp, _i]),
+    ("lsd_reg_set_source_dev", _i, [_vp, _vp, _i]),
+    ("lsd_reg_set_max_correspondence_distance", _i, [_vp, _d]),
+    ("lsd_reg_align", _i, [_vp, _vp, _vp, _pi, _pi]),
+    ("lsd_reg_get_final", _i, [_vp, _vp, _vp]),
+    ("lsd_reg_fitness", _i, [_vp, _vp, _d, C.POINTER(_d)]),
+    ("lsd_reg_cost", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_d), _pi]),
+    ("lsd_reg_stats", _i, [_vp, _pi, C.POINTER(C.c_longlong)]),
     ("lsd_lio_init_cov", None, [_vp]),
     ("lsd_state_boxplus", None, [_vp, _vp]),
     ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
@@ -231,6 +254,81 @@ def state_boxminus(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     r = np.zeros(DOF)
     lib.lsd_state_boxminus(_ptr(a), _ptr(b), _ptr(r))
     return r
+
+
+class Matcher:
+    """Scan matcher with the call protocol of pcl::Registration (what select_registration_method()
+    returns in the reference): set_target / set_source / align / has_converged / final / fitness."""
+
+    def __init__(self, kind: str = "NDT_CUDA", **kw):
+        kinds = {"NDT_CUDA": REG_NDT_P2D, "NDT": REG_NDT_P2D, "FAST_GICP": REG_GICP, "GICP": REG_GICP}
+        if kind not in kinds:
+            raise ValueError(f"unknown registration method {kind}")
+        self.params = RegParams()
+        lib.lsd_reg_default_params(C.byref(self.params), kinds[kind])
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown matcher parameter {k}")
+            setattr(self.params, k, v)
+        self.h = C.c_void_p()
+        check(lib.lsd_reg_create(C.byref(self.h), C.byref(self.params)))
+        self.converged, self.iterations = False, 0
+
+    def close(self):
+        if self.h:
+            lib.lsd_reg_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def set_target(self, pts):
+        if isinstance(pts, np.ndarray):
+            pts = _f32(pts)
+            check(lib.lsd_reg_set_target(self.h, _ptr(pts), pts.shape[0]))
+        else:
+            check(lib.lsd_reg_set_target_dev(self.h, _ptr(pts), pts.shape[0]))
+
+    def set_source(self, pts):
+        if isinstance(pts, np.ndarray):
+            pts = _f32(pts)
+            check(lib.lsd_reg_set_source(self.h, _ptr(pts), pts.shape[0]))
+        else:
+            check(lib.lsd_reg_set_source_dev(self.h, _ptr(pts), pts.shape[0]))
+
+    def set_max_correspondence_distance(self, d: float):
+        check(lib.lsd_reg_set_max_correspondence_distance(self.h, d))
+
+    def align(self, guess=None) -> np.ndarray:
+        g = np.ascontiguousarray(np.eye(4) if guess is None else guess, np.float32)
+        out = np.zeros((4, 4), np.float32)
+        cv, it = C.c_int(), C.c_int()
+        check(lib.lsd_reg_align(self.h, _ptr(g), _ptr(out), C.byref(cv), C.byref(it)))
+        self.converged, self.iterations = bool(cv.value), it.value
+        return out
+
+    def final(self):
+        T, H = np.zeros((4, 4)), np.zeros((6, 6))
+        check(lib.lsd_reg_get_final(self.h, _ptr(T), _ptr(H)))
+        return T, H
+
+    def fitness(self, max_range: float = 25.0, T=None) -> float:
+        sc = C.c_double()
+        Tp = None if T is None else np.ascontiguousarray(T, np.float64)
+        check(lib.lsd_reg_fitness(self.h, None if Tp is None else _ptr(Tp), max_range, C.byref(sc)))
+        return sc.value
+
+    def cost(self, T, update: bool = True, deriv: bool = True):
+        T = np.ascontiguousarray(T, np.float64)
+        H, b = np.zeros((6, 6)), np.zeros(6)
+        e, nc = C.c_double(), C.c_int()
+        check(lib.lsd_reg_cost(self.h, _ptr(T), int(update), _ptr(H) if deriv else None, _ptr(b) if deriv else None,
+                               C.byref(e), C.byref(nc)))
+        return e.value, H, b, nc.value
+
+    def stats(self):
+        nv, ln = C.c_int(), C.c_longlong()
+        check(lib.lsd_reg_stats(self.h, C.byref(nv), C.byref(ln)))
+        return dict(n_voxels=nv.value, launches=ln.value)
 
 
 def eskf_update_table(state, P, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=0.001, literal=False):

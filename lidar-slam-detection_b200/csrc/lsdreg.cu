@@ -3,3 +3,4 @@
 #include "map.cu"
 #include "voxelgrid.cu"
 #include "lio.cu"
+#include "reg.cu"

@@ -570,3 +570,223 @@ int orc_map_incremental(OrcIvox* map, const float* body, int n, const double* R,
     for (int i = 0; i < n; i++) if (flag[i] == pass) { int id = id0 + i; orc_ivox_add(map, world + 4 * (size_t)i, 4, 1, 0, &id); added++; }
   return added;
 }
+
+/* ===================================================================================== */
+/* a15  NDT (P2D, DIRECT1/7/27) — restated from the reference's CUDA functors, which are   */
+/*      __host__ __device__ arithmetic over a hash of Gaussian voxels:                     */
+/*        slam/thirdparty/fast_gicp/src/fast_gicp/cuda/gaussian_voxelmap.cu:76-202         */
+/*        .../covariance_regularization.cu:15-52,105-116 (PLANE: V diag(1e-3,1,1) V^-1)    */
+/*        .../find_voxel_correspondences.cu:16-111, ndt_compute_derivatives.cu:15-102      */
+/*        include/fast_gicp/cuda/vector3_hash.cuh:35-38 (coord = floor(x/res - 0.5))       */
+/*      PARITY UNPINNED: the reference NDT exists only as CUDA (thrust) code, SASS-built   */
+/*      for sm_72..89; it cannot run or be compiled for the host here.         */
+/*      fp32 per-element arithmetic as the reference; sums are carried in double (the      */
+/*      reference reduces fp32 tuples in thrust's unspecified tree order).                 */
+/*      PLANE-regularised covariance: V diag(1e-3,1,1) V^T  =>  C^-1 = I + 999 n n^T with  */
+/*      n the eigenvector of the smallest eigenvalue; used in that closed form.            */
+/* ===================================================================================== */
+typedef struct { int kx, ky, kz, used, n; double sum[3], sxx[9]; float mean[3], nrm[3]; } OrcNdtVox;
+typedef struct { float res; size_t tab_size, n_vox; OrcNdtVox* tab; } OrcNdt;
+
+static inline void ndt_coord(const float* p, float res, int* c) {
+  c[0] = (int)floorf(p[0] / res - 0.5f); c[1] = (int)floorf(p[1] / res - 0.5f); c[2] = (int)floorf(p[2] / res - 0.5f);
+}
+static OrcNdtVox* ndt_find(const OrcNdt* m, int x, int y, int z) {
+  size_t mask = m->tab_size - 1, s = cell_hash(x, y, z) & mask;
+  for (;;) {
+    OrcNdtVox* v = &m->tab[s];
+    if (!v->used) return NULL;
+    if (v->kx == x && v->ky == y && v->kz == z) return v;
+    s = (s + 1) & mask;
+  }
+}
+OrcNdt* orc_ndt_build(const float* pts, int stride, int n, float res) {
+  OrcNdt* m = (OrcNdt*)calloc(1, sizeof(OrcNdt));
+  m->res = res;
+  size_t t = 1024; while (t < (size_t)n * 2) t <<= 1;
+  m->tab_size = t; m->tab = (OrcNdtVox*)calloc(t, sizeof(OrcNdtVox));
+  size_t mask = t - 1;
+  for (int i = 0; i < n; i++) {
+    const float* p = pts + (size_t)stride * i;
+    int c[3]; ndt_coord(p, res, c);
+    size_t s = cell_hash(c[0], c[1], c[2]) & mask;
+    OrcNdtVox* v;
+    for (;;) { v = &m->tab[s]; if (!v->used) { v->used = 1; v->kx = c[0]; v->ky = c[1]; v->kz = c[2]; m->n_vox++; break; }
+               if (v->kx == c[0] && v->ky == c[1] && v->kz == c[2]) break; s = (s + 1) & mask; }
+    v->n++;
+    for (int a = 0; a < 3; a++) { v->sum[a] += (double)p[a]; for (int b = 0; b < 3; b++) v->sxx[3 * a + b] += (double)p[a] * (double)p[b]; }
+  }
+  for (size_t s = 0; s < t; s++) {
+    OrcNdtVox* v = &m->tab[s];
+    if (!v->used) continue;
+    /* The reference accumulates these moments in fp32 with atomicAdd in arbitrary thread order
+     * (gaussian_voxelmap.cu:138-147): its own result scatters run to run by the fp32 cancellation
+     * error of sum(xx^T) - mean sum^T.  Both restatements (this one and the CUDA path) carry the
+     * moments in double, the value that scatter is centred on. */
+    double cov[9], mean[3];
+    for (int a = 0; a < 3; a++) { mean[a] = v->sum[a] / (double)v->n; v->mean[a] = (float)mean[a]; }
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) cov[3 * a + b] = (v->sxx[3 * a + b] - mean[a] * v->sum[b]) / (double)v->n;
+    double A[9], w[3], V[9];
+    for (int k = 0; k < 9; k++) A[k] = cov[k];
+    for (int a = 0; a < 3; a++) for (int b = a + 1; b < 3; b++) A[3 * a + b] = A[3 * b + a] = 0.5 * (A[3 * a + b] + A[3 * b + a]);
+    eig3_sym(A, w, V);
+    int k0 = 0; if (w[1] < w[k0]) k0 = 1; if (w[2] < w[k0]) k0 = 2;
+    for (int a = 0; a < 3; a++) v->nrm[a] = (float)V[3 * a + k0];
+  }
+  return m;
+}
+void orc_ndt_destroy(OrcNdt* m) { if (m) { free(m->tab); free(m); } }
+size_t orc_ndt_num_voxels(const OrcNdt* m) { return m->n_vox; }
+
+static const int ndt_off7[7][3] = {{0,0,0},{1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1}};
+/* linearize at T_lin (row-major 4x4 double), evaluate at T_eval.  H36/b6 may be NULL.  n_off in {1,7,27}. */
+double orc_ndt_cost(const OrcNdt* m, const float* src, int stride, int n, const double* T_lin, const double* T_eval,
+                    int n_off, double* H36, double* b6, int* n_corr) {
+  float Rl[9], tl[3], R[9], t[3];
+  for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) { Rl[3 * a + b] = (float)T_lin[4 * a + b]; R[3 * a + b] = (float)T_eval[4 * a + b]; } tl[a] = (float)T_lin[4 * a + 3]; t[a] = (float)T_eval[4 * a + 3]; }
+  double H[36] = {0}, b[6] = {0}, err = 0; int nc = 0;
+  const float k_sq = m->res * m->res;
+  for (int i = 0; i < n; i++) {
+    const float* a = src + (size_t)stride * i;
+    float pl[3], tA[3];
+    for (int r = 0; r < 3; r++) { pl[r] = Rl[3 * r] * a[0] + Rl[3 * r + 1] * a[1] + Rl[3 * r + 2] * a[2] + tl[r];
+                                  tA[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2] + t[r]; }
+    int c[3]; ndt_coord(pl, m->res, c);
+    for (int o = 0; o < n_off; o++) {
+      int ox, oy, oz;
+      if (n_off == 27) { ox = o / 9 - 1; oy = (o / 3) % 3 - 1; oz = o % 3 - 1; }
+      else { ox = ndt_off7[o][0]; oy = ndt_off7[o][1]; oz = ndt_off7[o][2]; }
+      const OrcNdtVox* v = ndt_find(m, c[0] + ox, c[1] + oy, c[2] + oz);
+      if (!v) continue;
+      nc++;
+      if (v->n <= 6) continue; /* ndt_compute_derivatives.cu:62-64 */
+      float e[3], Ce[3];
+      for (int r = 0; r < 3; r++) e[r] = v->mean[r] - tA[r];
+      float ne = v->nrm[0] * e[0] + v->nrm[1] * e[1] + v->nrm[2] * e[2];
+      for (int r = 0; r < 3; r++) Ce[r] = e[r] + 999.0f * v->nrm[r] * ne;
+      float x = sqrtf(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+      float w = k_sq / (k_sq + x * x); /* cauchy, :15-18 */
+      err += (double)(w * (e[0] * Ce[0] + e[1] * Ce[1] + e[2] * Ce[2]));
+      if (!H36) continue;
+      /* J = [skew(tA) | -I] (3x6) */
+      float J[3][6] = {{0, -tA[2], tA[1], -1, 0, 0}, {tA[2], 0, -tA[0], 0, -1, 0}, {-tA[1], tA[0], 0, 0, 0, -1}};
+      float M[3][6]; /* C^-1 J */
+      for (int cc = 0; cc < 6; cc++) {
+        float nj = v->nrm[0] * J[0][cc] + v->nrm[1] * J[1][cc] + v->nrm[2] * J[2][cc];
+        for (int r = 0; r < 3; r++) M[r][cc] = J[r][cc] + 999.0f * v->nrm[r] * nj;
+      }
+      for (int p = 0; p < 6; p++) {
+        for (int q = 0; q < 6; q++) H[6 * p + q] += (double)(w * (J[0][p] * M[0][q] + J[1][p] * M[1][q] + J[2][p] * M[2][q]));
+        b[p] += (double)(w * (J[0][p] * Ce[0] + J[1][p] * Ce[1] + J[2][p] * Ce[2]));
+      }
+    }
+  }
+  if (H36) { memcpy(H36, H, sizeof(H)); memcpy(b6, b, sizeof(b)); }
+  if (n_corr) *n_corr = nc;
+  return err;
+}
+
+/* ===================================================================================== */
+/* a12/a13  FastGICP (fast_gicp_impl.hpp:119-303): k-NN covariances with PLANE             */
+/*      regularisation (U diag(1,1,1e-3) V^T  =  I - 0.999 n n^T), 1-NN correspondences    */
+/*      within max_corr, D2D cost, all double.  Neighbour search is exact (the reference   */
+/*      uses pcl::search::KdTree/FLANN: exact k-NN, method-independent up to ties).         */
+/*      PARITY UNPINNED against compiled code (needs PCL/FLANN); the k-NN it relies on is   */
+/*      the one pinned against the ikd-Tree above.                                          */
+/* ===================================================================================== */
+/* normals[n,3] (double) = smallest-eigenvalue direction of the k-NN covariance; cnt[n] = #neighbours used */
+void orc_gicp_normals(const OrcIvox* map, const float* pts, int stride, int n, int k, double max_sq, double* normals, int* cnt,
+                      int nthreads) {
+  omp_set_num_threads(nthreads > 0 ? nthreads : 1);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < n; i++) {
+    OrcCand best[64];
+    int kk = k > 64 ? 64 : k;
+    int nb = exact_knn_one(map, pts + (size_t)stride * i, kk, max_sq, best);
+    cnt[i] = nb;
+    double mean[3] = {0, 0, 0}, C[9] = {0};
+    for (int j = 0; j < nb; j++) { mean[0] += best[j].x; mean[1] += best[j].y; mean[2] += best[j].z; }
+    for (int a = 0; a < 3; a++) mean[a] /= (double)k; /* rowwise().mean() over k columns (zero-padded if fewer) */
+    for (int j = 0; j < k; j++) {
+      double d[3] = {(j < nb ? best[j].x : 0.0) - mean[0], (j < nb ? best[j].y : 0.0) - mean[1], (j < nb ? best[j].z : 0.0) - mean[2]};
+      for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) C[3 * a + b] += d[a] * d[b];
+    }
+    for (int a = 0; a < 9; a++) C[a] /= (double)k;
+    double w[3], V[9]; eig3_sym(C, w, V);
+    int k0 = 0; if (w[1] < w[k0]) k0 = 1; if (w[2] < w[k0]) k0 = 2;
+    for (int a = 0; a < 3; a++) normals[3 * (size_t)i + a] = V[3 * a + k0];
+  }
+}
+static void inv3(const double* A, double* I) {
+  double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  double det = A[0] * c00 + A[1] * c01 + A[2] * c02, id = 1.0 / det;
+  I[0] = c00 * id; I[1] = (A[2] * A[7] - A[1] * A[8]) * id; I[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  I[3] = c01 * id; I[4] = (A[0] * A[8] - A[2] * A[6]) * id; I[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  I[6] = c02 * id; I[7] = (A[1] * A[6] - A[0] * A[7]) * id; I[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+/* corr[n] in/out: when update != 0 correspondences (1-NN ids within max_corr, else -1) and Mahalanobis
+ * matrices maha[n,9] are recomputed at T (update_correspondences); otherwise reused (compute_error). */
+double orc_gicp_cost(const OrcIvox* tgt_map, const float* tgt, int tstride, const double* tgt_nrm, const float* src, int sstride,
+                     const double* src_nrm, int n, const double* T, double max_corr, int update, int* corr, double* maha,
+                     double* H36, double* b6, int nthreads) {
+  double R[9], t[3];
+  for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) R[3 * a + b] = T[4 * a + b]; t[a] = T[4 * a + 3]; }
+  if (update) {
+    float Rf[9], tf[3];
+    for (int a = 0; a < 9; a++) Rf[a] = (float)R[a];
+    for (int a = 0; a < 3; a++) tf[a] = (float)t[a];
+    omp_set_num_threads(nthreads > 0 ? nthreads : 1);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; i++) {
+      const float* a = src + (size_t)sstride * i;
+      float q[3];
+      for (int r = 0; r < 3; r++) q[r] = Rf[3 * r] * a[0] + Rf[3 * r + 1] * a[1] + Rf[3 * r + 2] * a[2] + tf[r];
+      OrcCand best[1];
+      int nb = exact_knn_one(tgt_map, q, 1, max_corr * max_corr, best);
+      corr[i] = (nb > 0 && (double)best[0].d2 < max_corr * max_corr) ? best[0].id : -1;
+      if (corr[i] < 0) continue;
+      const double* nb_ = tgt_nrm + 3 * (size_t)corr[i]; const double* na = src_nrm + 3 * (size_t)i;
+      double Rn[3]; mat3_vec(R, na, Rn);
+      double RCR[9];
+      for (int p = 0; p < 3; p++) for (int c = 0; c < 3; c++) RCR[3 * p + c] = (p == c ? 2.0 : 0.0) - 0.999 * (nb_[p] * nb_[c] + Rn[p] * Rn[c]);
+      inv3(RCR, maha + 9 * (size_t)i);
+    }
+  }
+  double H[36] = {0}, b[6] = {0}, err = 0;
+  for (int i = 0; i < n; i++) {
+    if (corr[i] < 0) continue;
+    const float* a = src + (size_t)sstride * i; const float* bb = tgt + (size_t)tstride * corr[i];
+    double A[3] = {a[0], a[1], a[2]}, tA[3], e[3], Me[3];
+    mat3_vec(R, A, tA);
+    for (int r = 0; r < 3; r++) { tA[r] += t[r]; e[r] = (double)bb[r] - tA[r]; }
+    const double* M = maha + 9 * (size_t)i;
+    mat3_vec(M, e, Me);
+    err += e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+    if (!H36) continue;
+    double J[3][6] = {{0, -tA[2], tA[1], -1, 0, 0}, {tA[2], 0, -tA[0], 0, -1, 0}, {-tA[1], tA[0], 0, 0, 0, -1}};
+    double MJ[3][6];
+    for (int c = 0; c < 6; c++) for (int r = 0; r < 3; r++) MJ[r][c] = M[3 * r] * J[0][c] + M[3 * r + 1] * J[1][c] + M[3 * r + 2] * J[2][c];
+    for (int p = 0; p < 6; p++) {
+      for (int q = 0; q < 6; q++) H[6 * p + q] += J[0][p] * MJ[0][q] + J[1][p] * MJ[1][q] + J[2][p] * MJ[2][q];
+      b[p] += J[0][p] * Me[0] + J[1][p] * Me[1] + J[2][p] * Me[2];
+    }
+  }
+  if (H36) { memcpy(H36, H, sizeof(H)); memcpy(b6, b, sizeof(b)); }
+  return err;
+}
+
+/* a16  pcl::Registration::getFitnessScore(max_range) (PCL 1.9.1 registration.hpp): mean of the squared
+ * 1-NN distances d2 <= max_range (the reference compares the SQUARED distance with max_range). */
+double orc_fitness(const OrcIvox* tgt_map, const float* src, int stride, int n, const double* T, double max_range, double search_sq) {
+  float R[9], t[3];
+  for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) R[3 * a + b] = (float)T[4 * a + b]; t[a] = (float)T[4 * a + 3]; }
+  double sum = 0; int nr = 0;
+  for (int i = 0; i < n; i++) {
+    const float* a = src + (size_t)stride * i; float q[3];
+    for (int r = 0; r < 3; r++) q[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2] + t[r];
+    OrcCand best[1];
+    int nb = exact_knn_one(tgt_map, q, 1, search_sq, best);
+    if (nb > 0 && (double)best[0].d2 <= max_range) { sum += (double)best[0].d2; nr++; }
+  }
+  return nr > 0 ? sum / nr : 1.7976931348623157e308;
+}

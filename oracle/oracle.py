@@ -45,6 +45,19 @@ def _load_port():
     L.orc_lio_hmodel.restype = C.c_int
     L.orc_lio_hmodel.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, C.c_int, C.c_int, _f, _i, _i, _u8,
                                  _f, _f, _d, _d, _d, _i, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_ndt_build.restype = C.c_void_p
+    L.orc_ndt_build.argtypes = [_f, C.c_int, C.c_int, C.c_float]
+    L.orc_ndt_destroy.argtypes = [C.c_void_p]
+    L.orc_ndt_num_voxels.restype = C.c_size_t
+    L.orc_ndt_num_voxels.argtypes = [C.c_void_p]
+    L.orc_ndt_cost.restype = C.c_double
+    L.orc_ndt_cost.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _d, _d, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_gicp_normals.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_int, C.c_double, _d, _i, C.c_int]
+    L.orc_gicp_cost.restype = C.c_double
+    L.orc_gicp_cost.argtypes = [C.c_void_p, _f, C.c_int, _d, _f, C.c_int, _d, C.c_int, _d, C.c_double, C.c_int, _i, _d,
+                                C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_fitness.restype = C.c_double
+    L.orc_fitness.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _d, C.c_double, C.c_double]
     L.orc_map_incremental.restype = C.c_int
     L.orc_map_incremental.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, _f, _i, C.c_int, C.c_double, _f, _u8, C.c_int]
     return L
