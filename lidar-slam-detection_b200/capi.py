@@ -261,6 +261,7 @@ class Matcher:
     returns in the reference): set_target / set_source / align / has_converged / final / fitness."""
 
     def __init__(self, kind: str = "NDT_CUDA", **kw):
+        self.h = None
         kinds = {"NDT_CUDA": REG_NDT_P2D, "NDT": REG_NDT_P2D, "FAST_GICP": REG_GICP, "GICP": REG_GICP}
         if kind not in kinds:
             raise ValueError(f"unknown registration method {kind}")

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) ndt_cost_kernel(NdtView v, const float4* 
 // One warp per point: exact K-NN, lanes hold the neighbours, warp-shuffle moments in double.
 constexpr int kRegWarps = 8;
 __global__ void __launch_bounds__(kRegWarps * 32, 3) gicp_normals_kernel(MapView mv, const float4* __restrict__ pts, int n, int k,
-                                                                         float max_sq, float4* __restrict__ nrm) {
+                                                                         float max_sq, double* __restrict__ nrm) {
   __shared__ __align__(16) unsigned char s_list[kRegWarps * kWarpListBytes];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpList wl;
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(kRegWarps * 32, 3) gicp_normals_kernel(MapView
     if (lane == 0) {
       double nr[3];
       smallest_eigvec(C, nr);
-      nrm[i] = make_float4((float)nr[0], (float)nr[1], (float)nr[2], __int_as_float(nf));
+      double* o = nrm + 4 * (size_t)i;  // double: C = I - 0.999 n n^T is inverted with condition number 1000
+      o[0] = nr[0]; o[1] = nr[1]; o[2] = nr[2]; o[3] = (double)nf;
     }
   }
 }
@@ -242,8 +243,8 @@ struct Pose34d { double R[9], t[3]; };
 // update_correspondences (fast_gicp_impl.hpp:119-157): 1-NN of the transformed source point, Mahalanobis
 // matrix (C_B + R C_A R^T)^-1 in double.  One warp per source point.
 __global__ void __launch_bounds__(kRegWarps * 32, 3) gicp_corr_kernel(MapView mv, const float4* __restrict__ src,
-                                                                      const float4* __restrict__ src_nrm, int n,
-                                                                      const float4* __restrict__ tgt_nrm, Pose34d T, Pose34f Tf,
+                                                                      const double* __restrict__ src_nrm, int n,
+                                                                      const double* __restrict__ tgt_nrm, Pose34d T, Pose34f Tf,
                                                                       float max_corr_sq, int* __restrict__ corr,
                                                                       double* __restrict__ maha) {
   __shared__ __align__(16) unsigned char s_list[kRegWarps * kWarpListBytes];
@@ -266,8 +267,8 @@ __global__ void __launch_bounds__(kRegWarps * 32, 3) gicp_corr_kernel(MapView mv
     const int c = (nf > 0 && d2 < max_corr_sq) ? id : -1;
     corr[i] = c;
     if (c < 0) continue;
-    const float4 na4 = __ldg(src_nrm + i), nb4 = __ldg(tgt_nrm + c);
-    const double na[3] = {na4.x, na4.y, na4.z}, nbv[3] = {nb4.x, nb4.y, nb4.z};
+    const double* na = src_nrm + 4 * (size_t)i;
+    const double* nbv = tgt_nrm + 4 * (size_t)c;
     const double rn[3] = {T.R[0] * na[0] + T.R[1] * na[1] + T.R[2] * na[2], T.R[3] * na[0] + T.R[4] * na[1] + T.R[5] * na[2],
                           T.R[6] * na[0] + T.R[7] * na[1] + T.R[8] * na[2]};
     double A[9];
@@ -371,7 +372,8 @@ struct lsd_reg {
   lsd_reg_params_t p{};
   int device = 0;
   cudaStream_t stream = nullptr;
-  float4 *d_src = nullptr, *d_tgt = nullptr, *d_src_nrm = nullptr, *d_tgt_nrm = nullptr;
+  float4 *d_src = nullptr, *d_tgt = nullptr;
+  double *d_src_nrm = nullptr, *d_tgt_nrm = nullptr;  // [n,4]: smallest-eigenvalue direction of the k-NN covariance, #neighbours
   int n_src = 0, n_tgt = 0, cap_src = 0, cap_tgt = 0;
   lsd_map* tgt_map = nullptr;  // exact-NN index of the target cloud (GICP, fitness)
   lsd_map* src_map = nullptr;  // exact-NN index of the source cloud (GICP covariances)
@@ -607,7 +609,7 @@ static lsd_status_t reg_alloc_src(lsd_reg* r, int n) {
   r->d_src = nullptr; r->d_src_nrm = nullptr; r->d_corr = nullptr; r->d_maha = nullptr;
   const size_t c = (size_t)n + (size_t)n / 4 + 1024;
   LSD_CUDA(cudaMalloc((void**)&r->d_src, c * 16));
-  LSD_CUDA(cudaMalloc((void**)&r->d_src_nrm, c * 16));
+  LSD_CUDA(cudaMalloc((void**)&r->d_src_nrm, c * 32));
   LSD_CUDA(cudaMalloc((void**)&r->d_corr, c * 27 * sizeof(int)));
   LSD_CUDA(cudaMalloc((void**)&r->d_maha, c * 6 * sizeof(double)));
   r->cap_src = (int)c;
@@ -715,7 +717,7 @@ lsd_status_t lsd_reg_set_target_dev(lsd_reg_t* r, const float* pts_dev, int n) {
   if (n > r->cap_tgt) {
     cudaFree(r->d_tgt); cudaFree(r->d_tgt_nrm); r->d_tgt = nullptr; r->d_tgt_nrm = nullptr;
     LSD_CUDA(cudaMalloc((void**)&r->d_tgt, (size_t)n * 16));
-    LSD_CUDA(cudaMalloc((void**)&r->d_tgt_nrm, (size_t)n * 16));
+    LSD_CUDA(cudaMalloc((void**)&r->d_tgt_nrm, (size_t)n * 32));
     r->cap_tgt = n;
   }
   LSD_CUDA(cudaMemcpyAsync(r->d_tgt, pts_dev, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
