@@ -248,6 +248,33 @@ lsd_status_t lsd_reg_fitness(lsd_reg_t* r, const double* T16_or_null, double max
 lsd_status_t lsd_reg_cost(lsd_reg_t* r, const double* T16, int update, double* H36, double* b6, double* err, int* n_corr);
 lsd_status_t lsd_reg_stats(lsd_reg_t* r, int* n_voxels, long long* launches);
 
+/* ------------------------------------------------------------------------------------------
+ * Detection voxelizer (config 5) — replaces sensor_driver/inference/voxelize:
+ * Preprocess::forward (preprocess_kernel.cu:56-101: sliding window of max_frame_num frames, older frames
+ * re-projected by a 3x4 motion, time channel + 0.1) and Voxelization::forward (voxelization_kernel.cu:
+ * 225-255: hash voxelisation, <= max_points_per_voxel points per voxel, mean -> fp16).  Output rows are in
+ * order of each voxel's first point; features [V, num_feature] fp16, indices [V,4] u32 = (0, z, y, x) or
+ * (0, x, y, z).  The closed libspconv engine that consumes them is out of scope.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_vfe lsd_vfe_t;
+typedef struct lsd_vfe_params {
+  float min_range[3], max_range[3], voxel_size[3];  /* [-64,-64,-2 .. 64,64,4], 0.1 x 0.1 x 0.15 (detection_object.yaml:7-16) */
+  int max_points_per_voxel;                          /* 5   (inference.h:16-38) */
+  int max_voxels;                                    /* 300000 */
+  int max_points;                                    /* 500000 */
+  int num_feature;                                   /* 5: x, y, z, intensity, time */
+  int max_frame_num;                                 /* POINT_FRAME_NUM 2 (README's best model: 4) */
+} lsd_vfe_params_t;
+void lsd_vfe_default_params(lsd_vfe_params_t* p);
+lsd_status_t lsd_vfe_create(lsd_vfe_t** out, const lsd_vfe_params_t* p);
+lsd_status_t lsd_vfe_destroy(lsd_vfe_t* v);
+lsd_status_t lsd_vfe_accumulate(lsd_vfe_t* v, const float* points_host, int num_points, const float* motion16_host, int realtime,
+                                int* total_points);
+lsd_status_t lsd_vfe_voxelize(lsd_vfe_t* v, int order_zyx, int* num_voxels);
+lsd_status_t lsd_vfe_get_output(lsd_vfe_t* v, void* features_fp16_host, unsigned* indices_host, unsigned* num_points_host);
+lsd_status_t lsd_vfe_get_output_dev(lsd_vfe_t* v, const void** features_fp16, const unsigned** indices, const unsigned** num_points);
+lsd_status_t lsd_vfe_get_points(lsd_vfe_t* v, float* points_host, int cap, int* total);
+
 /* Host-side manifold helpers (exported so bindings/tests use the same algebra as the filter).
  * IMU_Processing.hpp:224-230 initial covariance; state_ikfom boxplus/boxminus. */
 void lsd_lio_init_cov(double* P529);

@@ -51,6 +51,12 @@ class RegParams(C.Structure):
 
 REG_NDT_P2D, REG_GICP = 0, 1
 
+
+class VfeParams(C.Structure):
+    _fields_ = [("min_range", C.c_float * 3), ("max_range", C.c_float * 3), ("voxel_size", C.c_float * 3),
+                ("max_points_per_voxel", C.c_int), ("max_voxels", C.c_int), ("max_points", C.c_int), ("num_feature", C.c_int),
+                ("max_frame_num", C.c_int)]
+
 # every symbol include/lsdreg.h declares: (name, restype, argtypes)
 _vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
 _pp = C.POINTER(C.c_void_p)
@@ -107,6 +113,14 @@ SIGNATURES = [
     ("lsd_reg_fitness", _i, [_vp, _vp, _d, C.POINTER(_d)]),
     ("lsd_reg_cost", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_d), _pi]),
     ("lsd_reg_stats", _i, [_vp, _pi, C.POINTER(C.c_longlong)]),
+    ("lsd_vfe_default_params", None, [C.POINTER(VfeParams)]),
+    ("lsd_vfe_create", _i, [_pp, C.POINTER(VfeParams)]),
+    ("lsd_vfe_destroy", _i, [_vp]),
+    ("lsd_vfe_accumulate", _i, [_vp, _vp, _i, _vp, _i, _pi]),
+    ("lsd_vfe_voxelize", _i, [_vp, _i, _pi]),
+    ("lsd_vfe_get_output", _i, [_vp, _vp, _vp, _vp]),
+    ("lsd_vfe_get_output_dev", _i, [_vp, _pp, _pp, _pp]),
+    ("lsd_vfe_get_points", _i, [_vp, _vp, _i, _pi]),
     ("lsd_lio_init_cov", None, [_vp]),
     ("lsd_state_boxplus", None, [_vp, _vp]),
     ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
@@ -254,6 +268,55 @@ def state_boxminus(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     r = np.zeros(DOF)
     lib.lsd_state_boxminus(_ptr(a), _ptr(b), _ptr(r))
     return r
+
+
+class Voxelizer:
+    """Detection voxelizer: Preprocess (multi-frame window) + Voxelization (mean VFE, fp16)."""
+
+    def __init__(self, **kw):
+        self.h = None
+        self.params = VfeParams()
+        lib.lsd_vfe_default_params(C.byref(self.params))
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown voxelizer parameter {k}")
+            if k in ("min_range", "max_range", "voxel_size"):
+                v = (C.c_float * 3)(*v)
+            setattr(self.params, k, v)
+        self.h = C.c_void_p()
+        check(lib.lsd_vfe_create(C.byref(self.h), C.byref(self.params)))
+
+    def close(self):
+        if self.h:
+            lib.lsd_vfe_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def accumulate(self, points: np.ndarray, motion=None, realtime: bool = True) -> int:
+        points = np.ascontiguousarray(points, np.float32)
+        assert points.ndim == 2 and points.shape[1] == self.params.num_feature
+        m = np.ascontiguousarray(np.eye(4) if motion is None else motion, np.float32)
+        tot = C.c_int()
+        check(lib.lsd_vfe_accumulate(self.h, _ptr(points), points.shape[0], _ptr(m), int(realtime), C.byref(tot)))
+        return tot.value
+
+    def points(self) -> np.ndarray:
+        tot = C.c_int()
+        check(lib.lsd_vfe_get_points(self.h, None, 0, C.byref(tot)))
+        out = np.empty((tot.value, self.params.num_feature), np.float32)
+        check(lib.lsd_vfe_get_points(self.h, _ptr(out), tot.value, C.byref(tot)))
+        return out
+
+    def voxelize(self, order_zyx: bool = True):
+        nv = C.c_int()
+        check(lib.lsd_vfe_voxelize(self.h, int(order_zyx), C.byref(nv)))
+        V = nv.value
+        feat = np.empty((V, self.params.num_feature), np.float16)
+        idx = np.empty((V, 4), np.uint32)
+        npts = np.empty(V, np.uint32)
+        check(lib.lsd_vfe_get_output(self.h, _ptr(feat), _ptr(idx), _ptr(npts)))
+        return feat, idx, npts
 
 
 class Matcher:

@@ -4,3 +4,4 @@
 #include "voxelgrid.cu"
 #include "lio.cu"
 #include "reg.cu"
+#include "vfe.cu"
