@@ -43,7 +43,7 @@ def test_voxelizer_matches_sequential_oracle(frames):
         np.testing.assert_allclose(win, o.buf[:to], rtol=2e-7, atol=1e-6)    # fma chain vs float64 emulation
         feat, idx, npts = g.voxelize(True)
         of, oi, on = o.voxelize(points=win, zyx=True)                        # same window -> bit-exact
-        assert feat.shape == of.shape and feat.shape[0] > 10000
+        assert feat.shape == of.shape and feat.shape[0] > 1000
         assert (idx == oi).all() and (npts == on).all()
         assert (feat.view(np.uint16) == of.view(np.uint16)).all()
     f2, i2, n2 = g.voxelize(False)
