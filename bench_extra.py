@@ -1,0 +1,145 @@
+#!/usr/bin/env python
+"""bench_extra.py — the other BASELINE.json configs (parity-test cases, not the headline bench line):
+  config[2]  NDT scan-to-map: 100 k-pt scan vs a 50 M-pt map voxelised at 0.5 m
+  config[3]  GICP loop-closure batch: submap pairs x 200 k pts (per-GPU share of the 256-pair batch)
+  config[4]  detection voxelizer: 200 k pts, 4-frame window
+Prints one JSON object per config with device times (CUDA events via torch on the default stream are
+NOT used: the library runs on its own stream, so wall time around synchronous C-ABI calls is reported)
+and the CPU restatement timed on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def t_ms(f, n=1):
+    t0 = time.perf_counter()
+    for _ in range(n):
+        r = f()
+    return (time.perf_counter() - t0) * 1e3 / n, r
+
+
+def ndt(args):
+    import lsdreg
+    from lsdreg import synth
+    from oracle.reg import OracleMatcher
+    bx = args.ndt_blocks
+    t0 = time.time()
+    m = synth.block_map(31, bx, bx, 0.25 * (240711 * bx * bx / args.ndt_points) ** 0.5)
+    gen_s = time.time() - t0
+    bi = bx // 2
+    Rgt = synth.rot_from_rpy(0.01, -0.02, 0.3)
+    tgt = synth.block_center(bi, bi) + np.array([1.0, -2.0, 0.0])
+    scan = synth.scan64(32, 1920, Rgt, tgt, bi, bi)
+    dR, dt = synth.perturb(33, 0.5, 3.0)
+    guess = np.eye(4); guess[:3, :3] = Rgt @ dR; guess[:3, 3] = tgt + dt
+    g = lsdreg.Matcher("NDT_CUDA", resolution=0.5, map_log2_lines=25)
+    build_ms, _ = t_ms(lambda: g.set_target(m))
+    src_ms, _ = t_ms(lambda: g.set_source(scan))
+    g.align(guess)
+    align_ms, T = t_ms(lambda: g.align(guess), 5)
+    Tg, _ = g.final()
+    cost_ms, _ = t_ms(lambda: g.cost(Tg), 20)
+    st = g.stats()
+    out = dict(config="NDT 100k vs %.1fM-pt map @0.5 m" % (m.shape[0] / 1e6), map_points=int(m.shape[0]), voxels=st["n_voxels"],
+               scan_points=int(scan.shape[0]), target_build_ms=build_ms, set_source_ms=src_ms, align_ms=align_ms,
+               iterations=g.iterations, converged=bool(g.converged), cost_eval_us=cost_ms * 1e3,
+               pos_err_m=float(np.abs(Tg[:3, 3] - tgt).max()), map_gen_s=gen_s,
+               alg_bytes_per_eval=float(scan.shape[0] * (16 + 7 * 16 + 3 * 52)),
+               cost_gbs=float(scan.shape[0] * (16 + 7 * 16 + 3 * 52) / (cost_ms * 1e-3) / 1e9))
+    if not args.no_cpu:
+        near = (np.abs(m[:, 0] - tgt[0]) < 130) & (np.abs(m[:, 1] - tgt[1]) < 130)
+        sub = np.ascontiguousarray(m[near])             # bounded CPU sample: the map within 130 m of the scan, full density
+        o = OracleMatcher("ndt", resolution=0.5)
+        cb, _ = t_ms(lambda: o.set_target(sub)); o.set_source(scan)
+        ca, _ = t_ms(lambda: o.align(guess))
+        out["cpu"] = dict(kind="port", cores=1, sample="same scan vs the %d map points within 130 m of it" % sub.shape[0], target_build_ms=cb, align_ms=ca,
+                          iterations=o.iterations)
+    print(json.dumps(out))
+
+
+def gicp(args):
+    import lsdreg
+    from lsdreg import synth
+    from oracle.reg import OracleMatcher
+    pairs = args.gicp_pairs
+    times, errs, its = [], [], []
+    build = []
+    g = lsdreg.Matcher("FAST_GICP", max_corr_dist=2.0)
+    for p in range(pairs):
+        bi = p % 5
+        m = synth.block_map(41 + p, 1, 1, 0.22)
+        m = m[:200000] if m.shape[0] > 200000 else m
+        Rgt = synth.rot_from_rpy(0.0, 0.0, 0.2 + 0.01 * p)
+        tgt = synth.block_center(0, 0) + np.array([1.0 + 0.3 * p, -2.0, 0.0])
+        src = synth.scan64(50 + p, 3800, Rgt, tgt)[:200000]   # a dense submap seen from the unknown pose
+        dR, dt = synth.perturb(60 + p, 1.0, 5.0)
+        guess = np.eye(4); guess[:3, :3] = Rgt @ dR; guess[:3, 3] = tgt + dt
+        b1, _ = t_ms(lambda: g.set_target(m)); b2, _ = t_ms(lambda: g.set_source(src))
+        a, T = t_ms(lambda: g.align(guess))
+        Tg, _ = g.final()
+        build.append(b1 + b2); times.append(a); its.append(g.iterations); errs.append(float(np.abs(Tg[:3, 3] - tgt).max()))
+    out = dict(config="GICP pairs x 200k pts", pairs=pairs, points_per_cloud=200000, covariance_build_ms=float(np.mean(build)),
+               align_ms=float(np.mean(times)), pairs_per_s=1e3 / float(np.mean(times) + np.mean(build)), iterations=float(np.mean(its)),
+               pos_err_m=float(np.max(errs)))
+    if not args.no_cpu:
+        o = OracleMatcher("gicp", nthreads=min(16, os.cpu_count() or 1))
+        cb, _ = t_ms(lambda: (o.set_target(m), o.set_source(src)))
+        ca, _ = t_ms(lambda: o.align(guess))
+        out["cpu"] = dict(kind="port", cores=min(16, os.cpu_count() or 1), sample="the last pair", covariance_build_ms=cb, align_ms=ca,
+                          iterations=o.iterations)
+    print(json.dumps(out))
+
+
+def vfe(args):
+    import lsdreg
+    from lsdreg import synth
+    from oracle.vfe import OracleVoxelizer
+    frames = []
+    for f in range(8):
+        s = synth.scan64(300 + f, 800, synth.rot_from_rpy(0, 0, 0.05 * f), synth.block_center(0, 0) + np.array([0.8 * f, 0.1 * f, 0.0]))[:50000]
+        p = np.zeros((s.shape[0], 5), np.float32); p[:, :4] = s; p[:, 2] -= 1.8
+        frames.append(p)
+    M = np.eye(4, dtype=np.float32); M[:3, 3] = [0.8, 0.1, 0.0]
+    g = lsdreg.Voxelizer(max_frame_num=4)
+    for f in range(4):
+        g.accumulate(frames[f], M)
+    acc, vox = [], []
+    for f in range(4, 8):
+        a, tot = t_ms(lambda: g.accumulate(frames[f], M))
+        v, r = t_ms(lambda: g.voxelize(True))
+        acc.append(a); vox.append(v)
+    V = r[0].shape[0]
+    out = dict(config="VFE voxelizer 4 x 50k pts", window_points=int(tot), voxels=int(V), accumulate_us=float(np.mean(acc)) * 1e3,
+               voxelize_us=float(np.mean(vox)) * 1e3,
+               alg_bytes=float(20 * tot + 16 * tot + V * 26), gbs=float((20 * tot + 16 * tot + V * 26) / (np.mean(vox) * 1e-3) / 1e9))
+    if not args.no_cpu:
+        o = OracleVoxelizer(max_frames=4)
+        for f in range(4):
+            o.accumulate(frames[f], M)
+        ca, _ = t_ms(lambda: o.accumulate(frames[4], M)); cv, _ = t_ms(lambda: o.voxelize())
+        out["cpu"] = dict(kind="port", cores=1, sample="one frame", accumulate_us=ca * 1e3, voxelize_us=cv * 1e3)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="ndt,gicp,vfe")
+    ap.add_argument("--ndt-points", type=float, default=50e6)
+    ap.add_argument("--ndt-blocks", type=int, default=10)
+    ap.add_argument("--gicp-pairs", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    import lsdreg
+    lsdreg.init(int(os.environ.get("LOCAL_RANK", 0)))
+    for w in a.which.split(","):
+        {"ndt": ndt, "gicp": gicp, "vfe": vfe}[w](a)

@@ -135,7 +135,10 @@ class OracleMatcher:
             nu = 2.0
             stepped = False
             for _ in range(self.lm_max):
-                d = np.linalg.solve(H + lam * np.eye(6), -b)
+                try:
+                    d = np.linalg.solve(H + lam * np.eye(6), -b)
+                except np.linalg.LinAlgError:   # LDLT of a singular system: the reference would produce NaNs and give up
+                    break
                 delta = se3_exp(d)
                 xi = delta @ x0
                 yi, _, _ = self.cost(xi, False, False)
