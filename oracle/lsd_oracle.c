@@ -775,6 +775,120 @@ double orc_gicp_cost(const OrcIvox* tgt_map, const float* tgt, int tstride, cons
   return err;
 }
 
+/* ===================================================================================== */
+/* a14  FastVGICP (fast_vgicp_impl.hpp:72-207) + GaussianVoxelMap, ADDITIVE voxels          */
+/*      (fast_vgicp_voxel.hpp:108-182): target voxel = mean of the points and MEAN of their */
+/*      PLANE-regularised covariances (I - 0.999 n n^T); coord = floor(x/res - 0.5) in      */
+/*      double; correspondences = voxels at coord + offsets (DIRECT1/7/27) of the           */
+/*      transformed source point; weight sqrt(num_points).  Pinned against the compiled     */
+/*      reference (oracle/_ref/libref_reg.so) in tests/test_oracle_reg.py.                  */
+/* ===================================================================================== */
+typedef struct { int kx, ky, kz, used, n; double mean[3], cov[9]; } OrcVgVox;
+typedef struct { double res; size_t tab_size, n_vox; OrcVgVox* tab; } OrcVg;
+
+static OrcVgVox* vg_find(const OrcVg* m, int x, int y, int z) {
+  size_t mask = m->tab_size - 1, s = cell_hash(x, y, z) & mask;
+  for (;;) {
+    OrcVgVox* v = &m->tab[s];
+    if (!v->used) return NULL;
+    if (v->kx == x && v->ky == y && v->kz == z) return v;
+    s = (s + 1) & mask;
+  }
+}
+static inline void vg_coord(const double* p, double res, int* c) {
+  for (int a = 0; a < 3; a++) c[a] = (int)floor(p[a] / res - 0.5);
+}
+/* normals[n,3]: the targets' covariance directions from orc_gicp_normals */
+OrcVg* orc_vgicp_build(const float* pts, int stride, int n, const double* normals, double res) {
+  OrcVg* m = (OrcVg*)calloc(1, sizeof(OrcVg));
+  m->res = res;
+  size_t t = 1024; while (t < (size_t)n * 2) t <<= 1;
+  m->tab_size = t; m->tab = (OrcVgVox*)calloc(t, sizeof(OrcVgVox));
+  size_t mask = t - 1;
+  for (int i = 0; i < n; i++) {
+    const float* pf = pts + (size_t)stride * i;
+    double p[3] = {pf[0], pf[1], pf[2]};
+    int c[3]; vg_coord(p, res, c);
+    size_t s = cell_hash(c[0], c[1], c[2]) & mask;
+    OrcVgVox* v;
+    for (;;) { v = &m->tab[s]; if (!v->used) { v->used = 1; v->kx = c[0]; v->ky = c[1]; v->kz = c[2]; m->n_vox++; break; }
+               if (v->kx == c[0] && v->ky == c[1] && v->kz == c[2]) break; s = (s + 1) & mask; }
+    v->n++;
+    const double* nr = normals + 3 * (size_t)i;
+    for (int a = 0; a < 3; a++) { v->mean[a] += p[a]; for (int b = 0; b < 3; b++) v->cov[3 * a + b] += (a == b ? 1.0 : 0.0) - 0.999 * nr[a] * nr[b]; }
+  }
+  for (size_t s = 0; s < t; s++) {
+    OrcVgVox* v = &m->tab[s];
+    if (!v->used) continue;
+    for (int a = 0; a < 3; a++) v->mean[a] /= (double)v->n;
+    for (int a = 0; a < 9; a++) v->cov[a] /= (double)v->n;
+  }
+  return m;
+}
+void orc_vgicp_destroy(OrcVg* m) { if (m) { free(m->tab); free(m); } }
+size_t orc_vgicp_num_voxels(const OrcVg* m) { return m->n_vox; }
+int orc_vgicp_voxel(const OrcVg* m, int x, int y, int z, double* mean, double* cov) {
+  const OrcVgVox* v = vg_find(m, x, y, z);
+  if (!v) return 0;
+  memcpy(mean, v->mean, sizeof(v->mean)); memcpy(cov, v->cov, sizeof(v->cov));
+  return v->n;
+}
+/* update != 0: correspondences (voxel table slots, corr[n_off*n], -1 = none) and Mahalanobis matrices
+ * maha[n_off*n, 9] are recomputed at T; otherwise reused.  Returns the weighted error. */
+double orc_vgicp_cost(const OrcVg* m, const float* src, int stride, const double* src_nrm, int n, const double* T, int n_off,
+                      int update, long long* corr, double* maha, double* H36, double* b6, int* n_corr) {
+  double R[9], t[3];
+  for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) R[3 * a + b] = T[4 * a + b]; t[a] = T[4 * a + 3]; }
+  if (update) {
+    for (int i = 0; i < n; i++) {
+      const float* a = src + (size_t)stride * i;
+      double A[3] = {a[0], a[1], a[2]}, tA[3];
+      mat3_vec(R, A, tA);
+      for (int r = 0; r < 3; r++) tA[r] += t[r];
+      int c[3]; vg_coord(tA, m->res, c);
+      double Rn[3]; mat3_vec(R, src_nrm + 3 * (size_t)i, Rn);
+      for (int o = 0; o < n_off; o++) {
+        int ox, oy, oz;
+        if (n_off == 27) { ox = o / 9 - 1; oy = (o / 3) % 3 - 1; oz = o % 3 - 1; }
+        else { ox = ndt_off7[o][0]; oy = ndt_off7[o][1]; oz = ndt_off7[o][2]; }
+        const OrcVgVox* v = vg_find(m, c[0] + ox, c[1] + oy, c[2] + oz);
+        const size_t q = (size_t)o * n + i;
+        corr[q] = v ? (long long)(v - m->tab) : -1;
+        if (!v) continue;
+        double RCR[9];
+        for (int p = 0; p < 3; p++) for (int cc = 0; cc < 3; cc++) RCR[3 * p + cc] = v->cov[3 * p + cc] + (p == cc ? 1.0 : 0.0) - 0.999 * Rn[p] * Rn[cc];
+        inv3(RCR, maha + 9 * q);
+      }
+    }
+  }
+  double H[36] = {0}, b[6] = {0}, err = 0; int nc = 0;
+  for (int o = 0; o < n_off; o++) for (int i = 0; i < n; i++) {
+    const size_t q = (size_t)o * n + i;
+    if (corr[q] < 0) continue;
+    nc++;
+    const OrcVgVox* v = m->tab + corr[q];
+    const float* a = src + (size_t)stride * i;
+    double A[3] = {a[0], a[1], a[2]}, tA[3], e[3], Me[3];
+    mat3_vec(R, A, tA);
+    for (int r = 0; r < 3; r++) { tA[r] += t[r]; e[r] = v->mean[r] - tA[r]; }
+    const double* M = maha + 9 * q;
+    mat3_vec(M, e, Me);
+    const double w = sqrt((double)v->n);
+    err += w * (e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2]);
+    if (!H36) continue;
+    double J[3][6] = {{0, -tA[2], tA[1], -1, 0, 0}, {tA[2], 0, -tA[0], 0, -1, 0}, {-tA[1], tA[0], 0, 0, 0, -1}};
+    double MJ[3][6];
+    for (int c = 0; c < 6; c++) for (int r = 0; r < 3; r++) MJ[r][c] = M[3 * r] * J[0][c] + M[3 * r + 1] * J[1][c] + M[3 * r + 2] * J[2][c];
+    for (int p = 0; p < 6; p++) {
+      for (int q2 = 0; q2 < 6; q2++) H[6 * p + q2] += w * (J[0][p] * MJ[0][q2] + J[1][p] * MJ[1][q2] + J[2][p] * MJ[2][q2]);
+      b[p] += w * (J[0][p] * Me[0] + J[1][p] * Me[1] + J[2][p] * Me[2]);
+    }
+  }
+  if (H36) { memcpy(H36, H, sizeof(H)); memcpy(b6, b, sizeof(b)); }
+  if (n_corr) *n_corr = nc;
+  return err;
+}
+
 /* a16  pcl::Registration::getFitnessScore(max_range) (PCL 1.9.1 registration.hpp): mean of the squared
  * 1-NN distances d2 <= max_range (the reference compares the SQUARED distance with max_range). */
 double orc_fitness(const OrcIvox* tgt_map, const float* src, int stride, int n, const double* T, double max_range, double search_sq) {

@@ -56,6 +56,16 @@ def _load_port():
     L.orc_gicp_cost.restype = C.c_double
     L.orc_gicp_cost.argtypes = [C.c_void_p, _f, C.c_int, _d, _f, C.c_int, _d, C.c_int, _d, C.c_double, C.c_int, _i, _d,
                                 C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_vgicp_build.restype = C.c_void_p
+    L.orc_vgicp_build.argtypes = [_f, C.c_int, C.c_int, _d, C.c_double]
+    L.orc_vgicp_destroy.argtypes = [C.c_void_p]
+    L.orc_vgicp_num_voxels.restype = C.c_size_t
+    L.orc_vgicp_num_voxels.argtypes = [C.c_void_p]
+    L.orc_vgicp_voxel.restype = C.c_int
+    L.orc_vgicp_voxel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _d, _d]
+    L.orc_vgicp_cost.restype = C.c_double
+    L.orc_vgicp_cost.argtypes = [C.c_void_p, _f, C.c_int, _d, C.c_int, _d, C.c_int, C.c_int,
+                                 np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _d, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_fitness.restype = C.c_double
     L.orc_fitness.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _d, C.c_double, C.c_double]
     L.orc_map_incremental.restype = C.c_int
@@ -88,9 +98,40 @@ def _load_ref():
     return L
 
 
+def _load_ref_reg():
+    """The compiled reference matcher (oracle/ref_reg.cpp -> oracle/_ref/libref_reg.so)."""
+    path = os.path.join(_HERE, "_ref", "libref_reg.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_reg_create.restype = C.c_void_p
+    L.ref_reg_create.argtypes = [C.c_int, C.c_int]
+    L.ref_reg_destroy.argtypes = [C.c_void_p]
+    L.ref_reg_config.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, C.c_longlong]
+    L.ref_reg_set_source.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
+    L.ref_reg_set_target.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
+    L.ref_reg_align.restype = C.c_int
+    L.ref_reg_align.argtypes = [C.c_void_p, _f, _f]
+    L.ref_reg_fitness.restype = C.c_double
+    L.ref_reg_fitness.argtypes = [C.c_void_p, C.c_double]
+    L.ref_reg_linearize.restype = C.c_double
+    L.ref_reg_linearize.argtypes = [C.c_void_p, _d, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_reg_compute_error.restype = C.c_double
+    L.ref_reg_compute_error.argtypes = [C.c_void_p, _d]
+    L.ref_reg_get_corr.argtypes = [C.c_void_p, _i]
+    L.ref_reg_get_covs.argtypes = [C.c_void_p, C.c_int, _d]
+    L.ref_vgicp_voxel.restype = C.c_int
+    L.ref_vgicp_voxel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _d, _d]
+    L.ref_vgicp_coord.argtypes = [C.c_void_p, _d, _i]
+    L.ref_se3_exp.argtypes = [_d, _d]
+    return L
+
+
 port = _load_port()
 ref = _load_ref()
 HAVE_REF = ref is not None
+ref_reg = _load_ref_reg()
+HAVE_REF_REG = ref_reg is not None
 
 
 def _c32(a):

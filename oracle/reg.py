@@ -4,8 +4,11 @@
   (slam/thirdparty/fast_gicp/include/fast_gicp/gicp/impl/lsq_registration_impl.hpp:71-131,163-208),
   se3_exp (include/fast_gicp/so3/so3.hpp:60-104) — numpy, written independently of csrc/reg.cu.
 * cost functions: oracle/lsd_oracle.c (orc_ndt_cost, orc_gicp_cost, orc_fitness).
-PARITY UNPINNED (see the headers in lsd_oracle.c): fast_gicp needs PCL/FLANN (GICP) or a GPU of an
-older architecture (NDT CUDA) — neither can be built here.
+Pin status: the GICP / VGICP cost functions, the covariances, se3_exp and the whole LM loop are checked
+against the COMPILED reference classes (oracle/ref_reg.cpp -> oracle/_ref/libref_reg.so: the reference's
+own LsqRegistration / FastGICP / FastVGICP headers, with our PCL/Boost shims) in tests/test_oracle_reg.py.
+NDT (P2D) stays PARITY UNPINNED: the reference NDT exists only as CUDA code for older architectures;
+it shares the pinned LM loop and se3_exp.
 """
 from __future__ import annotations
 
@@ -56,7 +59,7 @@ def rot_angle_deg(R):
 
 
 class OracleMatcher:
-    """kind 'ndt' (P2D) or 'gicp'.  Protocol of pcl::Registration."""
+    """kind 'ndt' (P2D), 'gicp' or 'vgicp'.  Protocol of pcl::Registration."""
 
     def __init__(self, kind="ndt", resolution=1.0, neighbors=7, max_iterations=64, trans_eps=0.01, rot_eps=None, k=20,
                  max_corr=2.0, map_res=0.5, normal_sq=25.0, nthreads=8):
@@ -67,10 +70,13 @@ class OracleMatcher:
         self.lm_max, self.lm_init = 10, 1e-9
         self.ndt = None
         self.tmap = None
+        self.vg = None
 
     def __del__(self):
         if getattr(self, "ndt", None):
             O.port.orc_ndt_destroy(self.ndt)
+        if getattr(self, "vg", None):
+            O.port.orc_vgicp_destroy(self.vg)
 
     def _normals(self, pts):
         m = O.OracleIvox(self.map_res, 18, max(pts.shape[0], 1024))
@@ -89,6 +95,11 @@ class OracleMatcher:
             self.n_voxels = O.port.orc_ndt_num_voxels(self.ndt)
         else:
             self.tmap, self.tgt_nrm = self._normals(self.tgt)
+            if self.kind == "vgicp":
+                if self.vg:
+                    O.port.orc_vgicp_destroy(self.vg)
+                self.vg = O.port.orc_vgicp_build(self.tgt, self.tgt.shape[1], self.tgt.shape[0], self.tgt_nrm, float(self.res))
+                self.n_voxels = O.port.orc_vgicp_num_voxels(self.vg)
 
     def set_source(self, pts):
         self.src = np.ascontiguousarray(pts, np.float32)
@@ -97,6 +108,10 @@ class OracleMatcher:
             _, self.src_nrm = self._normals(self.src)
             self.corr = np.full(n, -1, np.int32)
             self.maha = np.zeros((n, 9))
+        elif self.kind == "vgicp":
+            _, self.src_nrm = self._normals(self.src)
+            self.vcorr = np.full(self.nb * n, -1, np.int64)
+            self.vmaha = np.zeros((self.nb * n, 9))
 
     def cost(self, T, update=True, deriv=True):
         T = np.ascontiguousarray(T, np.float64)
@@ -108,6 +123,11 @@ class OracleMatcher:
                 self.T_lin = T.copy()
             nc = C.c_int()
             e = O.port.orc_ndt_cost(self.ndt, self.src, self.src.shape[1], self.src.shape[0], self.T_lin, T, self.nb, Hp, bp, C.byref(nc))
+            self.n_corr = nc.value
+        elif self.kind == "vgicp":
+            nc = C.c_int()
+            e = O.port.orc_vgicp_cost(self.vg, self.src, self.src.shape[1], self.src_nrm, self.src.shape[0], T, self.nb, int(update),
+                                      self.vcorr, self.vmaha, Hp, bp, C.byref(nc))
             self.n_corr = nc.value
         else:
             e = O.port.orc_gicp_cost(self.tmap.h, self.tgt, self.tgt.shape[1], self.tgt_nrm, self.src, self.src.shape[1], self.src_nrm,
@@ -167,3 +187,75 @@ class OracleMatcher:
         T = np.ascontiguousarray(self.final if T is None else T, np.float64)
         return O.port.orc_fitness(self.tmap.h, self.src, self.src.shape[1], self.src.shape[0], T, max_range,
                                   min(max_range, 64.0 * self.map_res * self.map_res * 64.0))
+
+
+class RefMatcher:
+    """The COMPILED reference matcher (fast_gicp::FastGICP / FastVGICP through oracle/_ref/libref_reg.so)."""
+
+    def __init__(self, kind="gicp", resolution=1.0, neighbors=1, max_iterations=64, trans_eps=0.01, rot_eps=1e-2, k=20,
+                 max_corr=2.0, nthreads=1, max_process_time_us=0):
+        if not O.HAVE_REF_REG:
+            raise RuntimeError("oracle/_ref/libref_reg.so missing (built only where /root/reference exists)")
+        self.kind = kind
+        self.h = O.ref_reg.ref_reg_create(1 if kind == "gicp" else 2, nthreads)
+        O.ref_reg.ref_reg_config(self.h, max_iterations, trans_eps, rot_eps, max_corr if kind == "gicp" else -1.0, k, resolution,
+                                 neighbors, max_process_time_us)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            O.ref_reg.ref_reg_destroy(self.h)
+            self.h = None
+
+    def set_target(self, pts):
+        self.tgt = np.ascontiguousarray(pts, np.float32)
+        O.ref_reg.ref_reg_set_target(self.h, self.tgt, self.tgt.shape[0], self.tgt.shape[1])
+
+    def set_source(self, pts):
+        self.src = np.ascontiguousarray(pts, np.float32)
+        O.ref_reg.ref_reg_set_source(self.h, self.src, self.src.shape[0], self.src.shape[1])
+
+    def covs(self, which):
+        n = (self.tgt if which else self.src).shape[0]
+        out = np.zeros((n, 9))
+        O.ref_reg.ref_reg_get_covs(self.h, int(which), out)
+        return out.reshape(n, 3, 3)
+
+    def linearize(self, T, deriv=True):
+        T = np.ascontiguousarray(T, np.float64)
+        H, b = np.zeros(36), np.zeros(6)
+        nc = C.c_int()
+        e = O.ref_reg.ref_reg_linearize(self.h, T, H.ctypes.data if deriv else None, b.ctypes.data if deriv else None, C.byref(nc))
+        self.n_corr = nc.value
+        return e, H.reshape(6, 6), b
+
+    def compute_error(self, T):
+        return O.ref_reg.ref_reg_compute_error(self.h, np.ascontiguousarray(T, np.float64))
+
+    def corr(self):
+        out = np.zeros(self.src.shape[0], np.int32)
+        O.ref_reg.ref_reg_get_corr(self.h, out)
+        return out
+
+    def align(self, guess):
+        out = np.zeros(16, np.float32)
+        self.converged = bool(O.ref_reg.ref_reg_align(self.h, np.ascontiguousarray(guess, np.float32).reshape(16), out))
+        return out.reshape(4, 4).astype(np.float64)
+
+    def fitness(self, max_range=25.0):
+        return O.ref_reg.ref_reg_fitness(self.h, float(max_range))
+
+    def voxel(self, x, y, z):
+        mean, cov = np.zeros(3), np.zeros(9)
+        n = O.ref_reg.ref_vgicp_voxel(self.h, int(x), int(y), int(z), mean, cov)
+        return n, mean, cov.reshape(3, 3)
+
+    def coord(self, p):
+        c = np.zeros(3, np.int32)
+        O.ref_reg.ref_vgicp_coord(self.h, np.ascontiguousarray(p, np.float64), c)
+        return c
+
+
+def ref_se3_exp(a):
+    T = np.zeros(16)
+    O.ref_reg.ref_se3_exp(np.ascontiguousarray(a, np.float64), T)
+    return T.reshape(4, 4)
