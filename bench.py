@@ -167,6 +167,39 @@ def run_cpu(args, rank, world):
                 iters=float(np.mean(iters)), map_points=int(m.shape[0]))
 
 
+def run_knn_batch(torch, hmap, m, dev, nq):
+    """5-NN (NEARBY18, d2 < 5) for nq queries against the resident map through lsd_knn_query_dev, timed with CUDA
+    events on the library's stream.  Queries = map points + N(0, 0.1 m) noise: 'random' = random order over the
+    whole 10 M-point map (every query's cell lines are cold), 'sorted' = the same queries in voxel order."""
+    rng = np.random.default_rng(99)
+    sel = rng.integers(0, m.shape[0], nq)
+    q = m[sel].copy()
+    q[:, :3] += rng.normal(0.0, 0.1, (nq, 3)).astype(np.float32)
+    cell = np.round(q[:, :3] / 0.5).astype(np.int64)
+    order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
+    stream = torch.cuda.ExternalStream(hmap.stream(), device=dev)
+    idx = torch.empty((nq, 5), dtype=torch.int32, device=dev)
+    d2 = torch.empty((nq, 5), dtype=torch.float32, device=dev)
+    cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"queries": nq, "k": 5, "stencil": "NEARBY18"}
+    for name, qq in (("random", q), ("sorted", q[order])):
+        qd = torch.from_numpy(np.ascontiguousarray(qq)).to(dev)
+        times = []
+        for rep in range(5):
+            flush.fill_(rep)                      # > L2: the next launch starts from HBM
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            hmap.knn_dev(qd, idx, d2, cnt, k=5, max_sq=5.0)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e3)
+        out[name + "_us"] = float(np.median(times[1:]))
+        out[name + "_found5"] = float((cnt == 5).float().mean().item())
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,6 +208,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-knn-batch", action="store_true")
+    ap.add_argument("--knn-batch", type=int, default=1 << 21, help="queries in the batched k-NN leg (N=1)")
     ap.add_argument("--mg-mode", default="replicas", choices=["replicas", "shard"],
                     help="N>1: 'replicas' = one map replica and one independent scan stream per GPU (weak scaling, no "
                          "collective); 'shard' = ONE scan stream, map tile-sharded across the GPUs, normal equations "
@@ -295,6 +330,11 @@ def main():
     prof = lio.get_profile()
     lio.set_profile(False)
 
+    # ---------------- (4) batched k-NN (BASELINE metric "kNN GB/s vs HBM peak"): many scans' worth of queries in flight
+    knn_batch = None
+    if world == 1 and not args.no_knn_batch:
+        knn_batch = run_knn_batch(torch, lio.map, m, dev, args.knn_batch)
+
     dev_ms = float(np.sum([i["gpu_ms"] for i in infos_a]))
     t = torch.tensor([wall_a, wall_b, dev_ms * 1e-3], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -366,6 +406,12 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_query": bytes_per_query, "rho": rho,
                      "queries_per_launch": n_q, "us_per_launch": dur_s * 1e6, "launches_timed": hs["count"]},
         "kernels_ms": {k: (v["ms"] / max(v["count"], 1)) for k, v in prof.items()},
+        "knn_batch": None if knn_batch is None else {
+            **knn_batch, "bytes_per_query": bytes_per_query, "peak": peak,
+            **{k + "_gbs": knn_batch[k + "_us"] and knn_batch["queries"] * bytes_per_query / (knn_batch[k + "_us"] * 1e-6) / 1e9
+               for k in ("random", "sorted")},
+            **{k + "_frac": knn_batch["queries"] * bytes_per_query / (knn_batch[k + "_us"] * 1e-6) / 1e9 / peak
+               for k in ("random", "sorted")}},
         "cpu_baseline": cpu, "clocks": clocks, "map_build_s": build_s,
         "pos_err_max_m": float(np.max([i["pos_err"] for i in infos_a])),
     }

@@ -74,25 +74,28 @@ def gicp(args):
     pairs = args.gicp_pairs
     times, errs, its = [], [], []
     build = []
-    g = lsdreg.Matcher("FAST_GICP", max_corr_dist=2.0)
+    method = args.gicp_method
+    g = lsdreg.Matcher(method, max_corr_dist=2.0)
     for p in range(pairs):
         bi = p % 5
         m = synth.block_map(41 + p, 1, 1, 0.22)
         m = m[:200000] if m.shape[0] > 200000 else m
         Rgt = synth.rot_from_rpy(0.0, 0.0, 0.2 + 0.01 * p)
         tgt = synth.block_center(0, 0) + np.array([1.0 + 0.3 * p, -2.0, 0.0])
-        src = synth.scan64(50 + p, 3800, Rgt, tgt)[:200000]   # a dense submap seen from the unknown pose
-        dR, dt = synth.perturb(60 + p, 1.0, 5.0)
+        src = synth.scan64(50 + p, 3800, Rgt, tgt)            # a dense submap seen from the unknown pose
+        src = np.ascontiguousarray(src[np.linspace(0, src.shape[0] - 1, 200000).astype(np.int64)]) if src.shape[0] > 200000 else src
+        dR, dt = synth.perturb(60 + p, 0.5, 2.0)              # a loop-closure candidate: odometry drift of <= 0.5 m / 2 deg
         guess = np.eye(4); guess[:3, :3] = Rgt @ dR; guess[:3, 3] = tgt + dt
         b1, _ = t_ms(lambda: g.set_target(m)); b2, _ = t_ms(lambda: g.set_source(src))
         a, T = t_ms(lambda: g.align(guess))
         Tg, _ = g.final()
         build.append(b1 + b2); times.append(a); its.append(g.iterations); errs.append(float(np.abs(Tg[:3, 3] - tgt).max()))
-    out = dict(config="GICP pairs x 200k pts", pairs=pairs, points_per_cloud=200000, covariance_build_ms=float(np.mean(build)),
+    out = dict(config="%s pairs x 200k pts" % method, pairs=pairs, points_per_cloud=200000, covariance_build_ms=float(np.mean(build)),
                align_ms=float(np.mean(times)), pairs_per_s=1e3 / float(np.mean(times) + np.mean(build)), iterations=float(np.mean(its)),
                pos_err_m=float(np.max(errs)))
     if not args.no_cpu:
-        o = OracleMatcher("gicp", nthreads=min(16, os.cpu_count() or 1))
+        o = (OracleMatcher("gicp", nthreads=min(16, os.cpu_count() or 1)) if method == "FAST_GICP" else
+             OracleMatcher("vgicp", neighbors=1, trans_eps=0.1, rot_eps=0.1, nthreads=min(16, os.cpu_count() or 1)))
         cb, _ = t_ms(lambda: (o.set_target(m), o.set_source(src)))
         ca, _ = t_ms(lambda: o.align(guess))
         out["cpu"] = dict(kind="port", cores=min(16, os.cpu_count() or 1), sample="the last pair", covariance_build_ms=cb, align_ms=ca,
@@ -137,6 +140,7 @@ if __name__ == "__main__":
     ap.add_argument("--ndt-points", type=float, default=50e6)
     ap.add_argument("--ndt-blocks", type=int, default=10)
     ap.add_argument("--gicp-pairs", type=int, default=4)
+    ap.add_argument("--gicp-method", default="FAST_GICP", choices=["FAST_GICP", "FAST_VGICP"])
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     import lsdreg

@@ -32,6 +32,7 @@ typedef int lsd_status_t;
 #define LSD_NO_EFFECTIVE_POINTS 1   /* ekfom_data.valid == false, laserMapping.cpp:888-893      */
 #define LSD_SCAN_TOO_SMALL 2        /* feats_down_size < 5, laserMapping.cpp:1252-1256           */
 #define LSD_MAP_SEEDED 3            /* first scan only seeded the map, laserMapping.cpp:1227-1239 */
+#define LSD_IMU_INITIALIZING 4      /* ImuProcess::Process returned before undistorting (IMU_Processing.hpp:416-443) */
 #define LSD_ERR_INVALID (-1)
 #define LSD_ERR_CUDA (-2)
 #define LSD_ERR_NO_DEVICE (-3)
@@ -71,6 +72,9 @@ lsd_status_t lsd_map_insert(lsd_map_t* m, const float* xyzi_host, int n, int32_t
 lsd_status_t lsd_map_insert_dev(lsd_map_t* m, const float* xyzi_dev, int n, int32_t id0);
 /* IVox::NumValidGrids / NumPoints; n_dropped counts points refused for capacity/range. */
 lsd_status_t lsd_map_stats(lsd_map_t* m, uint64_t* n_cells, uint64_t* n_points, uint64_t* n_dropped);
+/* The cudaStream_t every *_dev call of this map is enqueued on (no reference counterpart): lets a
+ * caller order its own work after the library's, or time it with CUDA events on the right stream. */
+lsd_status_t lsd_map_stream(lsd_map_t* m, void** cuda_stream_out);
 /* IVox::GetClosestPoint(pt, out, k, max_sq) for a batch.  k in {1, 5, 20}.  Results per query are
  * sorted ascending by (d2, id); out_idx is -1 padded, out_d2 is -1 padded; out_cnt = #found.
  * fp32 d2 = (dx*dx + dy*dy) + dz*dz without FMA, as ivox3d_node.hpp:11-14 / ikd_Tree.cpp:1374. */
@@ -211,9 +215,10 @@ lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double
 typedef struct lsd_reg lsd_reg_t;
 #define LSD_REG_NDT_P2D 0
 #define LSD_REG_GICP 1
+#define LSD_REG_VGICP 2     /* fast_gicp::FastVGICP ("FAST_VGICP", registrations.cpp:56-66) */
 
 typedef struct lsd_reg_params {
-  int kind;                       /* LSD_REG_NDT_P2D | LSD_REG_GICP                                        */
+  int kind;                       /* LSD_REG_NDT_P2D | LSD_REG_GICP | LSD_REG_VGICP                        */
   double resolution;              /* NDT voxel size (1.0, registrations.cpp:106)                          */
   int ndt_neighbors;              /* 1 | 7 | 27 = DIRECT1 / DIRECT7 / DIRECT27 (ndt_cuda.cu:35-69)        */
   int max_iterations;             /* 64                                                                   */
@@ -274,6 +279,47 @@ lsd_status_t lsd_vfe_voxelize(lsd_vfe_t* v, int order_zyx, int* num_voxels);
 lsd_status_t lsd_vfe_get_output(lsd_vfe_t* v, void* features_fp16_host, unsigned* indices_host, unsigned* num_points_host);
 lsd_status_t lsd_vfe_get_output_dev(lsd_vfe_t* v, const void** features_fp16, const unsigned** indices, const unsigned** num_points);
 lsd_status_t lsd_vfe_get_points(lsd_vfe_t* v, float* points_host, int cap, int* total);
+
+/* ------------------------------------------------------------------------------------------
+ * IMU forward propagation + per-point undistortion — replaces ImuProcess
+ * (slam/mapping/fastlio/src/IMU_Processing.hpp:28-450; called at laserMapping.cpp:1188) and
+ * esekf::predict (IKFoM_toolkit/esekfom/esekfom.hpp:279-383 with use-ikfom.hpp:36-88).
+ *   imu7: double [n_imu, 7] = (stamp s, gyr xyz rad/s, acc xyz in units of g) — MeasureGroup::imu;
+ *   ins_vel3: MeasureGroup::ins.back() (Ve, Vn, Vu) or NULL; lidar_beg/end_time: MeasureGroup's;
+ *   xyzi [n,4] + time_ms [n] (PointType::curvature, ms since lidar_beg_time): MeasureGroup::lidar.
+ * lsd_imu_process = ImuProcess::Process: LSD_IMU_INITIALIZING while the first MAX_INI_COUNT (100) IMU
+ * samples are being averaged (state/P are initialised as IMU_init does), then LSD_OK with the state and
+ * covariance propagated to the scan end and the undistorted cloud left on the device
+ * (lsd_imu_get_cloud_dev) ready for lsd_lio_scan_dev.  Points stay in INPUT order (the reference sorts by
+ * time; nothing downstream depends on the order).  Forward propagation runs on the host in double like the
+ * reference; the backward propagation of the points is one kernel.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_imu lsd_imu_t;
+typedef struct lsd_imu_params {
+  double ext_R[9], ext_t[3];                     /* Lidar_R_wrt_IMU (row-major), Lidar_T_wrt_IMU: set_extrinsic          */
+  double gyr_cov, acc_cov, b_gyr_cov, b_acc_cov; /* 0.1, 0.1, 1e-4, 1e-4 (laserMapping.cpp:1076-1079, :1102-1105)       */
+  int undistort;                                 /* fastlio_init(..., undistort), laserMapping.cpp:1106                  */
+} lsd_imu_params_t;
+void lsd_imu_default_params(lsd_imu_params_t* p);
+lsd_status_t lsd_imu_create(lsd_imu_t** out, const lsd_imu_params_t* p);
+lsd_status_t lsd_imu_destroy(lsd_imu_t* m);
+lsd_status_t lsd_imu_reset(lsd_imu_t* m);                         /* ImuProcess::Reset + first-frame flag */
+lsd_status_t lsd_imu_is_init(lsd_imu_t* m, int* flag);            /* ImuProcess::IsInit */
+lsd_status_t lsd_imu_process(lsd_imu_t* m, const double* imu7, int n_imu, const double* ins_vel3_or_null, double lidar_beg_time,
+                             double lidar_end_time, const float* xyzi_host, const float* time_ms_host, int n, double* state26_inout,
+                             double* P529_inout, int* n_out);
+lsd_status_t lsd_imu_process_dev(lsd_imu_t* m, const double* imu7, int n_imu, const double* ins_vel3_or_null, double lidar_beg_time,
+                                 double lidar_end_time, const float* xyzi_dev, const float* time_ms_dev, int n, double* state26_inout,
+                                 double* P529_inout, int* n_out);
+/* The undistorted cloud of the last lsd_imu_process call; *cuda_stream_out (may be NULL) is the stream it
+ * is produced on — synchronise it (or use lsd_imu_get_cloud) before reading from another stream. */
+lsd_status_t lsd_imu_get_cloud_dev(lsd_imu_t* m, const float** xyzi_dev, int* n, void** cuda_stream_out);
+lsd_status_t lsd_imu_get_cloud(lsd_imu_t* m, float* xyzi_host, int cap, int* n);
+/* Parity tap: the IMUpose list of the last scan, double [n, 22] = (offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]). */
+lsd_status_t lsd_imu_get_poses(lsd_imu_t* m, double* poses22, int cap, int* n);
+/* esekf::predict alone (host, no GPU): Q144 = 12x12 process noise (ng, na, nbg, nba). */
+lsd_status_t lsd_eskf_predict(double* state26_inout, double* P529_inout, double dt, const double* Q144, const double* acc3,
+                              const double* gyro3);
 
 /* Host-side manifold helpers (exported so bindings/tests use the same algebra as the filter).
  * IMU_Processing.hpp:224-230 initial covariance; state_ikfom boxplus/boxminus. */

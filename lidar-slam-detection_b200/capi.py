@@ -49,7 +49,12 @@ class RegParams(C.Structure):
                 ("map_log2_lines", C.c_int)]
 
 
-REG_NDT_P2D, REG_GICP = 0, 1
+REG_NDT_P2D, REG_GICP, REG_VGICP = 0, 1, 2
+
+
+class ImuParams(C.Structure):
+    _fields_ = [("ext_R", C.c_double * 9), ("ext_t", C.c_double * 3), ("gyr_cov", C.c_double), ("acc_cov", C.c_double),
+                ("b_gyr_cov", C.c_double), ("b_acc_cov", C.c_double), ("undistort", C.c_int)]
 
 
 class VfeParams(C.Structure):
@@ -73,6 +78,7 @@ SIGNATURES = [
     ("lsd_map_insert", _i, [_vp, _vp, _i, C.c_int32]),
     ("lsd_map_insert_dev", _i, [_vp, _vp, _i, C.c_int32]),
     ("lsd_map_stats", _i, [_vp, _pu64, _pu64, _pu64]),
+    ("lsd_map_stream", _i, [_vp, C.POINTER(C.c_void_p)]),
     ("lsd_knn_query", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_knn_query_dev", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_voxelgrid_create", _i, [_pp, _i, _i]),
@@ -121,6 +127,17 @@ SIGNATURES = [
     ("lsd_vfe_get_output", _i, [_vp, _vp, _vp, _vp]),
     ("lsd_vfe_get_output_dev", _i, [_vp, _pp, _pp, _pp]),
     ("lsd_vfe_get_points", _i, [_vp, _vp, _i, _pi]),
+    ("lsd_imu_default_params", None, [C.POINTER(ImuParams)]),
+    ("lsd_imu_create", _i, [_pp, C.POINTER(ImuParams)]),
+    ("lsd_imu_destroy", _i, [_vp]),
+    ("lsd_imu_reset", _i, [_vp]),
+    ("lsd_imu_is_init", _i, [_vp, _pi]),
+    ("lsd_imu_process", _i, [_vp, _vp, _i, _vp, _d, _d, _vp, _vp, _i, _vp, _vp, _pi]),
+    ("lsd_imu_process_dev", _i, [_vp, _vp, _i, _vp, _d, _d, _vp, _vp, _i, _vp, _vp, _pi]),
+    ("lsd_imu_get_cloud_dev", _i, [_vp, _pp, _pi, _pp]),
+    ("lsd_imu_get_cloud", _i, [_vp, _vp, _i, _pi]),
+    ("lsd_imu_get_poses", _i, [_vp, _vp, _i, _pi]),
+    ("lsd_eskf_predict", _i, [_vp, _vp, _d, _vp, _vp, _vp]),
     ("lsd_lio_init_cov", None, [_vp]),
     ("lsd_state_boxplus", None, [_vp, _vp]),
     ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
@@ -200,6 +217,12 @@ class HashVoxelMap:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(lib.lsd_map_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(cells=a.value, points=b.value, dropped=c.value)
+
+    def stream(self) -> int:
+        """cudaStream_t (as an integer) the map's device calls run on."""
+        p = C.c_void_p()
+        check(lib.lsd_map_stream(self.h, C.byref(p)))
+        return p.value or 0
 
     def knn(self, q, k: int = 5, max_sq: float = 5.0, stencil: int = STENCIL_NEARBY18):
         """IVox::GetClosestPoint for a batch -> (idx [nq,k], d2 [nq,k], cnt [nq]), canonical order."""
@@ -325,7 +348,8 @@ class Matcher:
 
     def __init__(self, kind: str = "NDT_CUDA", **kw):
         self.h = None
-        kinds = {"NDT_CUDA": REG_NDT_P2D, "NDT": REG_NDT_P2D, "FAST_GICP": REG_GICP, "GICP": REG_GICP}
+        kinds = {"NDT_CUDA": REG_NDT_P2D, "NDT": REG_NDT_P2D, "FAST_GICP": REG_GICP, "GICP": REG_GICP,
+                 "FAST_VGICP": REG_VGICP, "FAST_VGICP_CUDA": REG_VGICP, "VGICP": REG_VGICP}
         if kind not in kinds:
             raise ValueError(f"unknown registration method {kind}")
         self.params = RegParams()
@@ -405,6 +429,87 @@ def eskf_update_table(state, P, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=
     ev = lib.lsd_eskf_update_table(_ptr(state), _ptr(P), _ptr(HTH), _ptr(HTh), _ptr(n_eff), HTH.shape[0], R, max_iterations,
                                    eps, int(literal))
     return state, P, ev
+
+
+IMU_INITIALIZING = 4
+
+
+def eskf_predict(state, P, dt, Q, acc, gyro):
+    """esekf::predict on the host (no GPU): returns (state, P) after one step."""
+    state = np.ascontiguousarray(state, np.float64).copy()
+    P = np.ascontiguousarray(P, np.float64).copy()
+    Q = np.ascontiguousarray(Q, np.float64); acc = np.ascontiguousarray(acc, np.float64); gyro = np.ascontiguousarray(gyro, np.float64)
+    check(lib.lsd_eskf_predict(_ptr(state), _ptr(P), float(dt), _ptr(Q), _ptr(acc), _ptr(gyro)))
+    return state, P
+
+
+class ImuProcess:
+    """ImuProcess (IMU_Processing.hpp): IMU initialisation, forward propagation, undistortion."""
+
+    def __init__(self, ext_R=None, ext_t=None, **kw):
+        self.h = None
+        self.params = ImuParams()
+        lib.lsd_imu_default_params(C.byref(self.params))
+        if ext_R is not None:
+            self.params.ext_R[:] = list(np.asarray(ext_R, np.float64).reshape(9))
+        if ext_t is not None:
+            self.params.ext_t[:] = list(np.asarray(ext_t, np.float64).reshape(3))
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown ImuProcess parameter {k}")
+            setattr(self.params, k, v)
+        self.h = C.c_void_p()
+        check(lib.lsd_imu_create(C.byref(self.h), C.byref(self.params)))
+
+    def close(self):
+        if self.h:
+            lib.lsd_imu_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def is_init(self) -> bool:
+        f = C.c_int()
+        check(lib.lsd_imu_is_init(self.h, C.byref(f)))
+        return bool(f.value)
+
+    def process(self, imu, beg, end, points, time_ms, state, P, ins_vel=None):
+        """-> (status, state, P, n_undistorted).  status IMU_INITIALIZING until the IMU is initialised.
+        points/time_ms: numpy (host path) or CUDA torch tensors (device path)."""
+        imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 7)
+        state = np.ascontiguousarray(state, np.float64).copy()
+        P = np.ascontiguousarray(P, np.float64).copy()
+        iv = None if ins_vel is None else np.ascontiguousarray(ins_vel, np.float64)
+        n = C.c_int()
+        if isinstance(points, np.ndarray):
+            points = _f32(points)
+            time_ms = np.ascontiguousarray(time_ms, np.float32)
+            fn = lib.lsd_imu_process
+        else:
+            fn = lib.lsd_imu_process_dev
+        st = check(fn(self.h, _ptr(imu), imu.shape[0], None if iv is None else _ptr(iv), float(beg), float(end), _ptr(points),
+                      _ptr(time_ms), points.shape[0], _ptr(state), _ptr(P), C.byref(n)))
+        return st, state, P, n.value
+
+    def cloud(self) -> np.ndarray:
+        n = C.c_int()
+        check(lib.lsd_imu_get_cloud(self.h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), np.float32)
+        check(lib.lsd_imu_get_cloud(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def cloud_dev(self):
+        """(device pointer, n, cudaStream_t) of the undistorted cloud."""
+        p, n, st = C.c_void_p(), C.c_int(), C.c_void_p()
+        check(lib.lsd_imu_get_cloud_dev(self.h, C.byref(p), C.byref(n), C.byref(st)))
+        return p.value, n.value, st.value or 0
+
+    def poses(self) -> np.ndarray:
+        n = C.c_int()
+        check(lib.lsd_imu_get_poses(self.h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 22), np.float64)
+        check(lib.lsd_imu_get_poses(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
 
 
 class LioFrontend:

@@ -83,6 +83,27 @@ inline void q2R(const double* q, double* R) {
   R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
   R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
 }
+// Eigen's rotation-matrix -> quaternion (Quaternion.h, "Quaternion Calculus and Fast Animation"): SO3(matrix), SOn.hpp:222
+inline void R2q(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+}
 // SOn.hpp:284-288 + mtkmath.hpp:254-275 (scale 2, plus_minus_periodicity)
 inline void so3_log(const double* q, double* r) {
   double nv = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);

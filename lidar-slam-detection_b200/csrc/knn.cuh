@@ -60,6 +60,7 @@ __device__ __forceinline__ int list_select(WarpList& wl, Neighbor& out) {
     // common case: one candidate per lane, selection entirely in registers (redux.sync)
     unsigned d = kTaken; int id = 0x7fffffff; unsigned loc = 0;
     if (lane < wl.n) { d = wl.d[lane]; id = wl.id[lane]; loc = wl.loc[lane]; }
+    __syncwarp();  // every candidate is in a register now: the head of the list doubles as the output staging
 #pragma unroll 1
     for (int r = 0; r < nf; r++) {
       const unsigned m = __reduce_min_sync(kFull, d);
@@ -69,11 +70,10 @@ __device__ __forceinline__ int list_select(WarpList& wl, Neighbor& out) {
         const int mi = __reduce_min_sync(kFull, d == m ? id : 0x7fffffff);
         win = __ffs(__ballot_sync(kFull, d == m && id == mi)) - 1;
       }
-      const int wid = __shfl_sync(kFull, id, win);
-      const unsigned wloc = __shfl_sync(kFull, loc, win);
-      if (lane == r) { out.d2 = __uint_as_float(m); out.id = wid; out.loc = wloc; }
-      if (lane == win) d = kTaken;
+      if (lane == win) { wl.d[r] = m; wl.id[r] = id; wl.loc[r] = loc; d = kTaken; }
     }
+    __syncwarp();
+    if (lane < nf) { out.d2 = __uint_as_float(wl.d[lane]); out.id = wl.id[lane]; out.loc = wl.loc[lane]; }
     __syncwarp();
     return nf;
   }
@@ -118,26 +118,42 @@ __device__ __forceinline__ void warp_scan_cells(const MapView& mv, unsigned long
   const CellLine* ln = mv.lines;
   unsigned cnt = 0;
   {
-    uint4 h = make_uint4(0, 0, 0, 0);
     float4 p[3];
     p[0] = p[1] = p[2] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (key != 0ull) {
-      s = hash_key(key) & mv.mask;
-      ln = mv.lines + s;
-      h = ldg_u4(ln);
-      p[0] = ldg_f4(&ln->pts[0]); p[1] = ldg_f4(&ln->pts[1]); p[2] = ldg_f4(&ln->pts[2]);
-      unsigned long long k = (unsigned long long)h.x | ((unsigned long long)h.y << 32);
-      if (k != key && k != 0ull) {  // home slot taken by another voxel: linear probe (rare at load <= 0.5)
-        for (unsigned probe = 1; probe < kMaxProbe; probe++) {
-          s = (s + 1) & mv.mask;
-          ln = mv.lines + s;
-          h = ldg_u4(ln);
-          k = (unsigned long long)h.x | ((unsigned long long)h.y << 32);
-          if (k == key || k == 0ull) break;
+      // Walk the probe sequence in the TAG array (8 slots per 8-byte load, L2-resident): an absent
+      // voxel is recognised without touching a line, a present one costs exactly one line access
+      // (plus one per tag collision, 1/255 per occupied slot walked).
+      constexpr unsigned long long k01 = 0x0101010101010101ull, k7f = 0x7f7f7f7f7f7f7f7full;
+      const unsigned long long hh = hash_key(key);
+      const unsigned long long tagv = (unsigned long long)slot_tag(hh) * k01;
+      s = hh & mv.mask;
+      bool present = false;
+      for (unsigned walked = 0; walked < kMaxProbe && !present;) {
+        const unsigned pos = (unsigned)(s & 7ull), nv = 8u - pos;
+        const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long*>(mv.tags + (s & ~7ull))) >> (8u * pos);
+        // exact zero-byte flags (bit 7 of each zero byte); bytes shifted in above nv are zero, so fe <= nv
+        const unsigned long long ze = ~(((v & k7f) + k7f) | v | k7f);
+        const unsigned long long x = v ^ tagv;
+        unsigned long long zm = ~(((x & k7f) + k7f) | x | k7f);
+        const unsigned fe = ze ? (unsigned)(__ffsll((long long)ze) - 1) >> 3 : 8u;
+        while (zm) {
+          const unsigned fm = (unsigned)(__ffsll((long long)zm) - 1) >> 3;
+          if (fm >= fe) break;  // the probe sequence ends at the first empty slot
+          zm &= zm - 1ull;
+          const unsigned long long c = (s + fm) & mv.mask;
+          const CellLine* cl = mv.lines + c;
+          const uint4 h = ldg_u4(cl);
+          const float4 a0 = ldg_f4(&cl->pts[0]), a1 = ldg_f4(&cl->pts[1]), a2 = ldg_f4(&cl->pts[2]);
+          if (((unsigned long long)h.x | ((unsigned long long)h.y << 32)) == key) {
+            present = true; s = c; ln = cl; cnt = h.z; p[0] = a0; p[1] = a1; p[2] = a2;
+            break;
+          }
         }
-        if (k == key) { p[0] = ldg_f4(&ln->pts[0]); p[1] = ldg_f4(&ln->pts[1]); p[2] = ldg_f4(&ln->pts[2]); }
+        if (present || fe < nv) break;
+        walked += nv;
+        s = (s + nv) & mv.mask;
       }
-      if (k == key) cnt = h.z;
     }
 #pragma unroll
     for (int j = 0; j < 3; j++) {

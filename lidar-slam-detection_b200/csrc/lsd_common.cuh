@@ -40,6 +40,7 @@ constexpr unsigned kMaxProbe = 4096;
 
 struct MapView {
   CellLine* lines;
+  unsigned char* tags;      // one byte per line: 0 = empty, else slot_tag(hash) — the query-side filter (L2-resident)
   unsigned long long mask;  // n_lines - 1
   float res, inv_res;
   unsigned long long* counters;  // [0] cells, [1] points, [2] dropped
@@ -80,6 +81,11 @@ __host__ __device__ __forceinline__ unsigned long long hash_key(unsigned long lo
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return k;
 }
+
+// Tag of an occupied line: 1..255 from hash bits the slot index does not use.  Queries read the tag
+// array (1 B/line: 32 MB for a 4 GB table, L2-resident) instead of the 128-byte lines to learn that a
+// voxel is absent or where its line is, so only voxels that exist cost a DRAM access.
+__host__ __device__ __forceinline__ unsigned slot_tag(unsigned long long h) { return (unsigned)(((h >> 56) * 255ull) >> 8) + 1u; }
 
 // Pos2Grid (ivox3d.h:258-261): round-half-away-from-zero of p * inv_res, in fp32
 __device__ __forceinline__ int3 pos2grid(float x, float y, float z, float inv_res) {

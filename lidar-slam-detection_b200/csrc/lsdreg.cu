@@ -5,3 +5,4 @@
 #include "lio.cu"
 #include "reg.cu"
 #include "vfe.cu"
+#include "imu.cu"

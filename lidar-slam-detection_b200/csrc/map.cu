@@ -7,6 +7,7 @@
 // The LRU list of the reference (ivox3d.h:246-255) is not reproduced: the table is sized for the
 // whole map in HBM (180 GB) instead of evicting at 100 000 voxels.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -70,7 +71,8 @@ lsd_status_t upload_stencils() {
 
 // ------------------------------------------------------------------ K2: insert
 __device__ __forceinline__ long long find_or_claim(const MapView& mv, unsigned long long key, bool* fresh) {
-  unsigned long long s = hash_key(key) & mv.mask;
+  const unsigned long long h = hash_key(key);
+  unsigned long long s = h & mv.mask;
   *fresh = false;
   for (unsigned probe = 0; probe < kMaxProbe; probe++) {
     unsigned long long* kp = &mv.lines[s].key;
@@ -78,7 +80,7 @@ __device__ __forceinline__ long long find_or_claim(const MapView& mv, unsigned l
     if (cur == key) return (long long)s;
     if (cur == 0ull) {
       unsigned long long old = atomicCAS(kp, 0ull, key);
-      if (old == 0ull) { *fresh = true; return (long long)s; }
+      if (old == 0ull) { mv.tags[s] = (unsigned char)slot_tag(h); *fresh = true; return (long long)s; }
       if (old == key) return (long long)s;
     }
     s = (s + 1) & mv.mask;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) map_insert_kernel(MapView mv, const float
 // ------------------------------------------------------------------ K3: batched k-NN query
 constexpr int kKnnWarps = 8;
 template <int K>
-__global__ void __launch_bounds__(kKnnWarps * 32, 4) knn_query_kernel(MapView mv, const float4* __restrict__ q, int nq, float max_sq,
+__global__ void __launch_bounds__(kKnnWarps * 32, 5) knn_query_kernel(MapView mv, const float4* __restrict__ q, int nq, float max_sq,
                                                                    int stencil, int* __restrict__ out_idx,
                                                                    float* __restrict__ out_d2, int* __restrict__ out_cnt) {
   __shared__ __align__(16) unsigned char s_list[kKnnWarps * kWarpListBytes];
@@ -181,6 +183,14 @@ lsd_status_t lsd_init(int device) {
   if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return LSD_ERR_INVALID; }
   g_device = device;
   LSD_CUDA(cudaSetDevice(device));
+  // L2 fetch granularity stays at the driver default: measured on B200 (profiles/r01g_knn_batch.txt), asking
+  // for 32-byte fetches halves the DRAM bytes of a hash probe but makes the batched k-NN 19 % SLOWER.
+  // LSD_L2_FETCH_GRANULARITY=32|64|128 overrides it for A/B measurements.
+  if (const char* e = getenv("LSD_L2_FETCH_GRANULARITY")) {
+    const size_t g = (size_t)atoi(e);
+    if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+    cudaGetLastError();
+  }
   return LSD_OK;
 }
 
@@ -198,6 +208,7 @@ lsd_status_t lsd_map_create(lsd_map_t** out, float resolution, int log2_lines) {
   m->view.inv_res = (float)(1.0 / (double)resolution);  // ivox3d.h:58
   m->view.shard_rank = 0; m->view.shard_world = 1; m->view.shard_tile = 32; m->view.shard_reach = 1;
   cudaError_t e = cudaMalloc(&m->view.lines, m->n_lines * sizeof(CellLine));
+  if (e == cudaSuccess) e = cudaMalloc(&m->view.tags, m->n_lines);
   if (e == cudaSuccess) e = cudaMalloc(&m->view.counters, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { lsd_status_t r = cuda_fail(e, "lsd_map_create alloc", __FILE__, __LINE__); delete m; return r; }
@@ -209,7 +220,7 @@ lsd_status_t lsd_map_destroy(lsd_map_t* m) {
   if (!m) return LSD_OK;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream); else cudaDeviceSynchronize();
-  cudaFree(m->view.lines); cudaFree(m->view.counters); cudaFree(m->scratch);
+  cudaFree(m->view.lines); cudaFree(m->view.tags); cudaFree(m->view.counters); cudaFree(m->scratch);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return LSD_OK;
@@ -228,6 +239,7 @@ lsd_status_t lsd_map_clear(lsd_map_t* m) {
   if (!m) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(m->device));
   LSD_CUDA(cudaMemsetAsync(m->view.lines, 0, m->n_lines * sizeof(CellLine), m->stream));
+  LSD_CUDA(cudaMemsetAsync(m->view.tags, 0, m->n_lines, m->stream));
   LSD_CUDA(cudaMemsetAsync(m->view.counters, 0, 4 * sizeof(unsigned long long), m->stream));
   LSD_CUDA(cudaStreamSynchronize(m->stream));
   return LSD_OK;
@@ -273,6 +285,12 @@ lsd_status_t lsd_map_stats(lsd_map_t* m, uint64_t* n_cells, uint64_t* n_points, 
   if (n_cells) *n_cells = h[0];
   if (n_points) *n_points = h[1];
   if (n_dropped) *n_dropped = h[2];
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_stream(lsd_map_t* m, void** cuda_stream_out) {
+  if (!m || !cuda_stream_out) return LSD_ERR_INVALID;
+  *cuda_stream_out = static_cast<void*>(m->stream);
   return LSD_OK;
 }
 

@@ -331,6 +331,167 @@ __global__ void __launch_bounds__(256) gicp_cost_kernel(const float4* __restrict
   grid_finalize<29>(partials, done, result, 0, -1, 0.0, kResSeq, seq, sc, 0);
 }
 
+// ------------------------------------------------------------------ VGICP
+// FastVGICP (fast_vgicp_impl.hpp:72-207) on a GaussianVoxelMap with ADDITIVE voxels
+// (fast_vgicp_voxel.hpp:108-182): voxel = mean of its points and MEAN of their PLANE-regularised
+// covariances I - 0.999 n n^T; coord = floor(x/res - 0.5) in double; weight sqrt(num_points).
+struct __align__(128) VgLine { unsigned long long key; int n; int pad; double mean[3]; double cov[6]; double pad2[4]; };
+static_assert(sizeof(VgLine) == 128, "VgLine must be one line");
+struct VgView { VgLine* lines; unsigned long long mask; double res; };
+
+__device__ __forceinline__ int3 vg_coord(double x, double y, double z, double res) {
+  return make_int3((int)floor(x / res - 0.5), (int)floor(y / res - 0.5), (int)floor(z / res - 0.5));
+}
+
+// GaussianVoxelMap::create_voxelmap: sum[] = sum of points, sxx[] = sum of covariances (xx xy xz yy yz zz)
+__global__ void __launch_bounds__(256) vgicp_accum_kernel(NdtBuildLine* __restrict__ tab, unsigned long long mask, double res,
+                                                          const float4* __restrict__ pts, const double* __restrict__ nrm, int n,
+                                                          unsigned* __restrict__ fail) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(pts + i);
+  const double x = p.x, y = p.y, z = p.z;
+  const int3 c = vg_coord(x, y, z, res);
+  if (!coord_ok(c.x, c.y, c.z)) { atomicAdd(fail, 1u); return; }
+  const unsigned long long key = pack_key(c.x, c.y, c.z, 0);
+  const double nx = nrm[4 * (size_t)i], ny = nrm[4 * (size_t)i + 1], nz = nrm[4 * (size_t)i + 2];
+  unsigned long long s = hash_key(key) & mask;
+  for (unsigned probe = 0; probe < kMaxProbe; probe++) {
+    unsigned long long* kp = &tab[s].key;
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+    if (cur == 0ull) cur = atomicCAS(kp, 0ull, key), cur = cur == 0ull ? key : cur;
+    if (cur == key) {
+      atomicAdd(&tab[s].count, 1u);
+      atomicAdd(&tab[s].sum[0], x); atomicAdd(&tab[s].sum[1], y); atomicAdd(&tab[s].sum[2], z);
+      atomicAdd(&tab[s].sxx[0], 1.0 - 0.999 * nx * nx); atomicAdd(&tab[s].sxx[1], -0.999 * nx * ny); atomicAdd(&tab[s].sxx[2], -0.999 * nx * nz);
+      atomicAdd(&tab[s].sxx[3], 1.0 - 0.999 * ny * ny); atomicAdd(&tab[s].sxx[4], -0.999 * ny * nz); atomicAdd(&tab[s].sxx[5], 1.0 - 0.999 * nz * nz);
+      return;
+    }
+    s = (s + 1) & mask;
+  }
+  atomicAdd(fail, 1u);
+}
+
+// AdditiveGaussianVoxel::finalize
+__global__ void __launch_bounds__(256) vgicp_finalize_kernel(const NdtBuildLine* __restrict__ tab, VgLine* __restrict__ out,
+                                                             unsigned long long n_lines, unsigned* __restrict__ n_vox) {
+  const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_lines) return;
+  VgLine o;
+  o.key = tab[s].key; o.n = 0; o.pad = 0;
+  for (int k = 0; k < 3; k++) o.mean[k] = 0.0;
+  for (int k = 0; k < 6; k++) o.cov[k] = 0.0;
+  for (int k = 0; k < 4; k++) o.pad2[k] = 0.0;
+  if (o.key != 0ull) {
+    const double n = (double)tab[s].count;
+    o.n = (int)tab[s].count;
+    for (int k = 0; k < 3; k++) o.mean[k] = tab[s].sum[k] / n;
+    for (int k = 0; k < 6; k++) o.cov[k] = tab[s].sxx[k] / n;
+    atomicAdd(n_vox, 1u);
+  }
+  out[s] = o;
+}
+
+__device__ __forceinline__ int vg_lookup(const VgView& v, int x, int y, int z) {
+  if (!coord_ok(x, y, z)) return -1;
+  const unsigned long long key = pack_key(x, y, z, 0);
+  unsigned long long s = hash_key(key) & v.mask;
+  for (unsigned probe = 0; probe < kMaxProbe; probe++) {
+    const unsigned long long k = __ldg(&v.lines[s].key);
+    if (k == key) return (int)s;
+    if (k == 0ull) return -1;
+    s = (s + 1) & v.mask;
+  }
+  return -1;
+}
+
+// linearize (UPDATE: update_correspondences at T, Mahalanobis matrices stored) / compute_error (reuse).
+// One thread per source point, double.
+template <bool UPDATE, bool DERIV>
+__global__ void __launch_bounds__(256) vgicp_cost_kernel(VgView v, const float4* __restrict__ src, const double* __restrict__ src_nrm,
+                                                         int n, int n_off, Pose34d T, int* __restrict__ corr,
+                                                         double* __restrict__ maha, double* __restrict__ partials,
+                                                         unsigned* __restrict__ done, double* __restrict__ result, double seq,
+                                                         ShardComm sc) {
+  double vals[29];
+#pragma unroll
+  for (int j = 0; j < 29; j++) vals[j] = 0.0;
+#pragma unroll 1
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = __ldg(src + i);
+    const double ax = a.x, ay = a.y, az = a.z;
+    const double tx = T.R[0] * ax + T.R[1] * ay + T.R[2] * az + T.t[0];
+    const double ty = T.R[3] * ax + T.R[4] * ay + T.R[5] * az + T.t[1];
+    const double tz = T.R[6] * ax + T.R[7] * ay + T.R[8] * az + T.t[2];
+    int3 c = make_int3(0, 0, 0);
+    double rn[3] = {0.0, 0.0, 0.0};
+    if (UPDATE) {
+      c = vg_coord(tx, ty, tz, v.res);
+      const double* na = src_nrm + 4 * (size_t)i;
+      rn[0] = T.R[0] * na[0] + T.R[1] * na[1] + T.R[2] * na[2];
+      rn[1] = T.R[3] * na[0] + T.R[4] * na[1] + T.R[5] * na[2];
+      rn[2] = T.R[6] * na[0] + T.R[7] * na[1] + T.R[8] * na[2];
+    }
+#pragma unroll 1
+    for (int o = 0; o < n_off; o++) {
+      const size_t q = (size_t)o * n + i;
+      int slot;
+      if (UPDATE) {
+        int ox, oy, oz;
+        if (n_off == 27) { ox = o / 9 - 1; oy = (o / 3) % 3 - 1; oz = o % 3 - 1; }
+        else { ox = c_ndt_off7[o][0]; oy = c_ndt_off7[o][1]; oz = c_ndt_off7[o][2]; }
+        slot = vg_lookup(v, c.x + ox, c.y + oy, c.z + oz);
+        corr[q] = slot;
+      } else {
+        slot = corr[q];
+      }
+      if (slot < 0) continue;
+      vals[28] += 1.0;
+      const VgLine* ln = v.lines + slot;
+      double M[3][3];
+      if (UPDATE) {
+        // RCR = cov_B + R cov_A R^T with cov_A = I - 0.999 n n^T
+        const double A0 = ln->cov[0] + 1.0 - 0.999 * rn[0] * rn[0], A1 = ln->cov[1] - 0.999 * rn[0] * rn[1], A2 = ln->cov[2] - 0.999 * rn[0] * rn[2];
+        const double A4 = ln->cov[3] + 1.0 - 0.999 * rn[1] * rn[1], A5 = ln->cov[4] - 0.999 * rn[1] * rn[2], A8 = ln->cov[5] + 1.0 - 0.999 * rn[2] * rn[2];
+        const double c00 = A4 * A8 - A5 * A5, c01 = A5 * A2 - A1 * A8, c02 = A1 * A5 - A4 * A2;
+        const double idet = 1.0 / (A0 * c00 + A1 * c01 + A2 * c02);
+        M[0][0] = c00 * idet; M[0][1] = c01 * idet; M[0][2] = c02 * idet;
+        M[1][1] = (A0 * A8 - A2 * A2) * idet; M[1][2] = (A2 * A1 - A0 * A5) * idet; M[2][2] = (A0 * A4 - A1 * A1) * idet;
+        M[1][0] = M[0][1]; M[2][0] = M[0][2]; M[2][1] = M[1][2];
+        double* Ms = maha + 6 * q;
+        Ms[0] = M[0][0]; Ms[1] = M[0][1]; Ms[2] = M[0][2]; Ms[3] = M[1][1]; Ms[4] = M[1][2]; Ms[5] = M[2][2];
+      } else {
+        const double* Ms = maha + 6 * q;
+        M[0][0] = Ms[0]; M[0][1] = M[1][0] = Ms[1]; M[0][2] = M[2][0] = Ms[2]; M[1][1] = Ms[3]; M[1][2] = M[2][1] = Ms[4]; M[2][2] = Ms[5];
+      }
+      const double w = sqrt((double)ln->n);
+      const double ex = ln->mean[0] - tx, ey = ln->mean[1] - ty, ez = ln->mean[2] - tz;
+      const double cx = M[0][0] * ex + M[0][1] * ey + M[0][2] * ez, cy = M[1][0] * ex + M[1][1] * ey + M[1][2] * ez,
+                   cz = M[2][0] * ex + M[2][1] * ey + M[2][2] * ez;
+      vals[27] += w * (ex * cx + ey * cy + ez * cz);
+      if (DERIV) {
+        const double J[3][6] = {{0., -tz, ty, -1., 0., 0.}, {tz, 0., -tx, 0., -1., 0.}, {-ty, tx, 0., 0., 0., -1.}};
+        double MJ[3][6];
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++) {
+          MJ[0][cc] = M[0][0] * J[0][cc] + M[0][1] * J[1][cc] + M[0][2] * J[2][cc];
+          MJ[1][cc] = M[1][0] * J[0][cc] + M[1][1] * J[1][cc] + M[1][2] * J[2][cc];
+          MJ[2][cc] = M[2][0] * J[0][cc] + M[2][1] * J[1][cc] + M[2][2] * J[2][cc];
+        }
+        int qq = 0;
+#pragma unroll
+        for (int p = 0; p < 6; p++) {
+#pragma unroll
+          for (int r = p; r < 6; r++) vals[qq++] += w * (J[0][p] * MJ[0][r] + J[1][p] * MJ[1][r] + J[2][p] * MJ[2][r]);
+          vals[21 + p] += w * (J[0][p] * cx + J[1][p] * cy + J[2][p] * cz);
+        }
+      }
+    }
+  }
+  block_partials<29>(vals, partials);
+  grid_finalize<29>(partials, done, result, 0, -1, 0.0, kResSeq, seq, sc, 0);
+}
+
 // getFitnessScore: sum of squared 1-NN distances <= max_range, and their count.  One warp per point.
 __global__ void __launch_bounds__(kRegWarps * 32, 3) fitness_kernel(MapView mv, const float4* __restrict__ src, int n, Pose34f Tf,
                                                                     float search_sq, float max_range, double* __restrict__ partials,
@@ -380,6 +541,8 @@ struct lsd_reg {
   bool tgt_map_built = false, src_normals_built = false;
   lsd::NdtView ndt{};
   unsigned long long ndt_lines = 0;
+  lsd::VgView vg{};
+  unsigned long long vg_lines = 0;
   unsigned n_voxels = 0;
   int* d_corr = nullptr; size_t corr_cap = 0;
   double* d_maha = nullptr; size_t maha_cap = 0;
@@ -438,6 +601,17 @@ static lsd_status_t reg_cost(lsd_reg* r, const double* T, bool update, double* H
     else if (update) ndt_cost_kernel<true, false><<<g, 256, 0, st>>>(r->ndt, r->d_src, r->n_src, no, lin, ev, r->d_corr, r->d_partials, r->d_done, r->d_result, seq, r->sc);
     else if (deriv) ndt_cost_kernel<false, true><<<g, 256, 0, st>>>(r->ndt, r->d_src, r->n_src, no, lin, ev, r->d_corr, r->d_partials, r->d_done, r->d_result, seq, r->sc);
     else ndt_cost_kernel<false, false><<<g, 256, 0, st>>>(r->ndt, r->d_src, r->n_src, no, lin, ev, r->d_corr, r->d_partials, r->d_done, r->d_result, seq, r->sc);
+    r->launches++;
+  } else if (r->p.kind == LSD_REG_VGICP) {
+    if (!r->vg.lines || !r->tgt_map_built) { set_error("registration: no target cloud"); return LSD_ERR_INVALID; }
+    Pose34d Td;
+    T_to_pose(T, &Td, nullptr);
+    const int no = r->p.ndt_neighbors;
+    const int g = reg_grid(r->n_src);
+    if (update && deriv) vgicp_cost_kernel<true, true><<<g, 256, 0, st>>>(r->vg, r->d_src, r->d_src_nrm, r->n_src, no, Td, r->d_corr, r->d_maha, r->d_partials, r->d_done, r->d_result, seq, r->sc);
+    else if (update) vgicp_cost_kernel<true, false><<<g, 256, 0, st>>>(r->vg, r->d_src, r->d_src_nrm, r->n_src, no, Td, r->d_corr, r->d_maha, r->d_partials, r->d_done, r->d_result, seq, r->sc);
+    else if (deriv) vgicp_cost_kernel<false, true><<<g, 256, 0, st>>>(r->vg, r->d_src, r->d_src_nrm, r->n_src, no, Td, r->d_corr, r->d_maha, r->d_partials, r->d_done, r->d_result, seq, r->sc);
+    else vgicp_cost_kernel<false, false><<<g, 256, 0, st>>>(r->vg, r->d_src, r->d_src_nrm, r->n_src, no, Td, r->d_corr, r->d_maha, r->d_partials, r->d_done, r->d_result, seq, r->sc);
     r->launches++;
   } else {
     if (!r->tgt_map_built) { set_error("registration: no target cloud"); return LSD_ERR_INVALID; }
@@ -611,7 +785,7 @@ static lsd_status_t reg_alloc_src(lsd_reg* r, int n) {
   LSD_CUDA(cudaMalloc((void**)&r->d_src, c * 16));
   LSD_CUDA(cudaMalloc((void**)&r->d_src_nrm, c * 32));
   LSD_CUDA(cudaMalloc((void**)&r->d_corr, c * 27 * sizeof(int)));
-  LSD_CUDA(cudaMalloc((void**)&r->d_maha, c * 6 * sizeof(double)));
+  LSD_CUDA(cudaMalloc((void**)&r->d_maha, c * 6 * sizeof(double) * (r->p.kind == LSD_REG_VGICP ? (size_t)r->p.ndt_neighbors : 1)));
   r->cap_src = (int)c;
   return LSD_OK;
 }
@@ -640,6 +814,11 @@ void lsd_reg_default_params(lsd_reg_params_t* p, int kind) {
     p->rotation_epsilon_deg = 0.1;        // registrations.cpp:110
     p->resolution = 1.0;                  // registrations.cpp:106
     p->ndt_neighbors = 7;                 // DIRECT7, registrations.cpp:114
+  } else if (kind == LSD_REG_VGICP) {
+    p->transformation_epsilon = 0.1;      // registrations.cpp:61
+    p->rotation_epsilon_deg = 0.1;        // registrations.cpp:62
+    p->resolution = 1.0;                  // registrations.cpp:60
+    p->ndt_neighbors = 1;                 // DIRECT1, fast_vgicp_impl.hpp:23
   } else {
     p->rotation_epsilon_deg = 1e-2;       // LsqRegistration default (lsq_registration_impl.hpp:24), compared against degrees (:113-116)
     p->resolution = 1.0;
@@ -648,7 +827,7 @@ void lsd_reg_default_params(lsd_reg_params_t* p, int kind) {
 }
 
 lsd_status_t lsd_reg_create(lsd_reg_t** out, const lsd_reg_params_t* p) {
-  if (!out || !p || (p->kind != LSD_REG_NDT_P2D && p->kind != LSD_REG_GICP) || p->resolution <= 0 ||
+  if (!out || !p || (p->kind != LSD_REG_NDT_P2D && p->kind != LSD_REG_GICP && p->kind != LSD_REG_VGICP) || p->resolution <= 0 ||
       (p->ndt_neighbors != 1 && p->ndt_neighbors != 7 && p->ndt_neighbors != 27) || p->k_correspondences < 3 || p->k_correspondences > 20) {
     set_error("lsd_reg_create: bad params (kind, resolution, ndt_neighbors in {1,7,27}, 3 <= k <= 20)");
     return LSD_ERR_INVALID;
@@ -678,7 +857,7 @@ lsd_status_t lsd_reg_destroy(lsd_reg_t* r) {
   if (!r) return LSD_OK;
   cudaSetDevice(r->device);
   if (r->stream) cudaStreamSynchronize(r->stream);
-  void* ptrs[] = {r->d_src, r->d_tgt, r->d_src_nrm, r->d_tgt_nrm, r->ndt.lines, r->d_corr, r->d_maha, r->d_partials, r->d_done};
+  void* ptrs[] = {r->d_src, r->d_tgt, r->d_src_nrm, r->d_tgt_nrm, r->ndt.lines, r->vg.lines, r->d_corr, r->d_maha, r->d_partials, r->d_done};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(r->h_result);
   if (r->tgt_map) lsd_map_destroy(r->tgt_map);
@@ -755,6 +934,31 @@ lsd_status_t lsd_reg_set_target_dev(lsd_reg_t* r, const float* pts_dev, int n) {
     LSD_CUDA(cudaGetLastError());
     r->launches += 2;
     r->tgt_map_built = true;
+    if (r->p.kind == LSD_REG_VGICP) {  // GaussianVoxelMap::create_voxelmap (built lazily by the reference, fast_vgicp_impl.hpp:121-124)
+      const int l2 = r->p.map_log2_lines > 0 ? r->p.map_log2_lines : auto_log2((size_t)n / 2 + 1024, 12, 27);
+      const unsigned long long lines = 1ull << l2;
+      NdtBuildLine* build = nullptr;
+      LSD_CUDA(cudaMalloc((void**)&build, lines * sizeof(NdtBuildLine)));
+      LSD_CUDA(cudaMemsetAsync(build, 0, lines * sizeof(NdtBuildLine), st));
+      if (r->vg_lines != lines) {
+        cudaFree(r->vg.lines); r->vg.lines = nullptr;
+        LSD_CUDA(cudaMalloc((void**)&r->vg.lines, lines * sizeof(VgLine)));
+        r->vg_lines = lines;
+      }
+      r->vg.mask = lines - 1;
+      r->vg.res = r->p.resolution;
+      unsigned* d_cnt = reinterpret_cast<unsigned*>(r->d_done) + 4;
+      LSD_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+      vgicp_accum_kernel<<<(n + 255) / 256, 256, 0, st>>>(build, lines - 1, r->vg.res, r->d_tgt, r->d_tgt_nrm, n, d_cnt);
+      vgicp_finalize_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(build, r->vg.lines, lines, d_cnt + 1);
+      r->launches += 2;
+      unsigned h[2] = {0, 0};
+      LSD_CUDA(cudaMemcpyAsync(h, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+      LSD_CUDA(cudaStreamSynchronize(st));
+      LSD_CUDA(cudaFree(build));
+      r->n_voxels = h[1];
+      if (h[0]) { set_error("VGICP voxel table too small / coordinates out of range: %u points dropped (raise map_log2_lines)", h[0]); return LSD_ERR_CAPACITY; }
+    }
     LSD_CUDA(cudaStreamSynchronize(st));
   }
   return LSD_OK;
@@ -768,7 +972,7 @@ lsd_status_t lsd_reg_set_source_dev(lsd_reg_t* r, const float* pts_dev, int n) {
   cudaStream_t st = r->stream;
   LSD_CUDA(cudaMemcpyAsync(r->d_src, pts_dev, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
   r->n_src = n;
-  if (r->p.kind == LSD_REG_GICP) {  // source covariances (fast_gicp_impl.hpp:109-111)
+  if (r->p.kind != LSD_REG_NDT_P2D) {  // source covariances (fast_gicp_impl.hpp:109-111)
     s = build_point_map(r, &r->src_map, r->d_src, n);
     if (s) return s;
     gicp_normals_kernel<<<warp_grid(n), kRegWarps * 32, 0, st>>>(r->src_map->view, r->d_src, n, r->p.k_correspondences,

@@ -320,3 +320,80 @@ def update_iterated(x: State, P: np.ndarray, h_model, R: float = 0.001, maximum_
             P = L - K_x[:, :15] @ P[:15, :]
             return x, P, iters
     return x, P, iters
+
+
+# ---------------------------------------------------------------------------------------------
+# Forward propagation (row N1).  esekf::predict (esekfom.hpp:279-383, dense branch) with the process
+# model of use-ikfom.hpp:49-88 (get_f, df_dx, df_dw).  Flattened DIM layout (24): pos 0, rot 3,
+# offset_R 6, offset_T 9, vel 12, bg 15, ba 18, grav 21.  The reference evaluates
+# MTK::exp(.., scalar_type(1/2)) with an INTEGER 1/2 == 0 (esekfom.hpp:312,344), i.e. the "exp"
+# blocks of F_x1 are identities; restated as such.
+# ---------------------------------------------------------------------------------------------
+def get_f(x: State, acc, gyro):
+    f = np.zeros(24)
+    f[0:3] = x.vel
+    f[3:6] = gyro - x.bg
+    f[12:15] = quat_to_R(x.rot) @ (acc - x.ba) + x.grav
+    return f
+
+
+def df_dx(x: State, acc, gyro):
+    F = np.zeros((24, 23))
+    F[0:3, 12:15] = np.eye(3)
+    R = quat_to_R(x.rot)
+    F[12:15, 3:6] = -R @ hat(acc - x.ba)
+    F[12:15, 18:21] = -R
+    F[12:15, 21:23] = s2_Mx(x.grav, np.zeros(2))
+    F[3:6, 15:18] = -np.eye(3)
+    return F
+
+
+def df_dw(x: State):
+    W = np.zeros((24, 12))
+    W[12:15, 3:6] = -quat_to_R(x.rot)
+    W[3:6, 0:3] = -np.eye(3)
+    W[15:18, 6:9] = np.eye(3)
+    W[18:21, 9:12] = np.eye(3)
+    return W
+
+
+def state_oplus(x: State, f, dt):
+    """MTK_BUILD_MANIFOLD oplus: vect += f*dt; SO3 *= exp(f, dt) (SOn.hpp:242-245); S2 rotated by exp(f, dt) (S2.hpp:129-134)."""
+    x.pos = x.pos + f[0:3] * dt
+    x.rot = quat_mul(x.rot, so3_exp(f[3:6], dt))
+    x.offset_R_L_I = quat_mul(x.offset_R_L_I, so3_exp(f[6:9], dt))
+    x.offset_T_L_I = x.offset_T_L_I + f[9:12] * dt
+    x.vel = x.vel + f[12:15] * dt
+    x.bg = x.bg + f[15:18] * dt
+    x.ba = x.ba + f[18:21] * dt
+    x.grav = quat_to_R(so3_exp(f[21:24], dt)) @ x.grav
+
+
+def predict(x: State, P: np.ndarray, dt: float, Q: np.ndarray, acc, gyro):
+    """In place on x; returns the propagated covariance."""
+    acc = np.asarray(acc, np.float64); gyro = np.asarray(gyro, np.float64)
+    f = get_f(x, acc, gyro)
+    fx = df_dx(x, acc, gyro)
+    fw = df_dw(x)
+    x_before = x.copy()
+    state_oplus(x, f, dt)
+    F1 = np.eye(N)
+    fx_final = np.zeros((N, N)); fw_final = np.zeros((N, 12))
+    for idx, dim, dof in ((0, 0, 3), (9, 9, 3), (12, 12, 3), (15, 15, 3), (18, 18, 3)):   # vect states
+        fx_final[idx:idx + dof] = fx[dim:dim + dof]
+        fw_final[idx:idx + dof] = fw[dim:dim + dof]
+    for idx, dim in ((3, 3), (6, 6)):                                                     # SO3 states
+        seg = -f[dim:dim + 3] * dt
+        A = A_matrix(seg)
+        fx_final[idx:idx + 3] = A @ fx[dim:dim + 3]
+        fw_final[idx:idx + 3] = A @ fw[dim:dim + 3]
+    idx, dim = 21, 21                                                                     # S2 state
+    seg = f[dim:dim + 3] * dt
+    Nx = s2_Nx_yy(x.grav)
+    Mx = s2_Mx(x_before.grav, np.zeros(2))
+    F1[idx:idx + 2, idx:idx + 2] = Nx @ Mx
+    tmp = -Nx @ hat(x_before.grav) @ A_matrix(seg).T
+    fx_final[idx:idx + 2] = tmp @ fx[dim:dim + 3]
+    fw_final[idx:idx + 2] = tmp @ fw[dim:dim + 3]
+    F1 = F1 + fx_final * dt
+    return F1 @ P @ F1.T + (dt * fw_final) @ Q @ (dt * fw_final).T

@@ -68,9 +68,35 @@ def test_fails_loudly_without_a_device():
         lsdreg.LioFrontend()
     with pytest.raises(lsdreg.LsdError):
         lsdreg.VoxelGrid(100)
+    with pytest.raises(lsdreg.LsdError):
+        lsdreg.ImuProcess()
+    with pytest.raises(lsdreg.LsdError):
+        lsdreg.Matcher("FAST_VGICP")
 
 
 def test_host_only_helpers_work_anywhere():
     P = lsdreg.init_cov()
     assert P.shape == (23, 23) and P[0, 0] == 1.0 and P[6, 6] == 1e-5   # IMU_Processing.hpp:224-230
     assert capi.lib.lsd_version().startswith(b"lsdreg")
+
+
+def test_slam_wrapper_module_has_the_reference_entry():
+    """The pybind11 module keeps the reference's name, function name and argument names
+    (slam_wrapper.cpp:241-242) and, like every entry point, refuses to run without a GPU."""
+    import importlib
+    import inspect
+    import os
+    import sys
+    import numpy as np
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lidar-slam-detection_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    slam = importlib.import_module("slam_wrapper")
+    doc = slam.pointcloud_align.__doc__
+    for name in ("source_point", "target_point", "guess"):
+        assert name in doc
+    import torch
+    if not torch.cuda.is_available():
+        import pytest
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            slam.pointcloud_align(np.zeros((10, 4), np.float32), np.zeros((10, 4), np.float32), np.eye(4, dtype=np.float32))

@@ -109,3 +109,29 @@ def test_invalid_measurements_leave_state_untouched():
     x, P, ev = lsdreg.eskf_update_table(x0, P0, HTH, HTh, np.zeros(1, np.int32))
     assert ev == 5                                   # i = -1 .. maximum_iter-1, all `continue`d (esekfom.hpp:1633-1641)
     np.testing.assert_array_equal(x, x0); np.testing.assert_array_equal(P, P0)
+
+
+def test_predict_matches_oracle():
+    """esekf::predict (host C++, csrc/imu.cu) against the numpy restatement (oracle/eskf.py::predict):
+    state and covariance after chains of IMU steps from random states."""
+    import lsdreg
+    from oracle import eskf as E
+    rng = np.random.default_rng(11)
+    Q = np.diag([0.1] * 3 + [0.1] * 3 + [1e-4] * 3 + [1e-4] * 3)
+    for trial in range(5):
+        x = E.State()
+        x.boxplus(rng.normal(0, 0.3, 23))
+        x.vel = rng.normal(0, 2.0, 3)
+        A = rng.normal(0, 0.05, (23, 23))
+        P = E.init_P() + A @ A.T
+        xv = x.to_vec()
+        Pv = P.copy()
+        for step in range(12):
+            acc = np.array([0.1, -0.2, 9.7]) + rng.normal(0, 0.5, 3)
+            gyr = rng.normal(0, 0.4, 3)
+            dt = float(rng.uniform(0.001, 0.02))
+            P = E.predict(x, P, dt, Q, acc, gyr)
+            xv, Pv = lsdreg.eskf_predict(xv, Pv, dt, Q, acc, gyr)
+        np.testing.assert_allclose(xv, x.to_vec(), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(Pv, P, rtol=1e-11, atol=1e-14)
+        assert np.linalg.eigvalsh(0.5 * (Pv + Pv.T)).min() > 0

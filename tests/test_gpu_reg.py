@@ -29,15 +29,16 @@ def _rot_err(Ra, Rb):
 
 
 @pytest.mark.parametrize("kind,okind,kw", [("NDT_CUDA", "ndt", dict()), ("NDT_CUDA", "ndt", dict(ndt_neighbors=1)),
-                                           ("NDT_CUDA", "ndt", dict(ndt_neighbors=27)), ("FAST_GICP", "gicp", dict())])
+                                           ("NDT_CUDA", "ndt", dict(ndt_neighbors=27)), ("FAST_GICP", "gicp", dict()),
+                                           ("FAST_VGICP", "vgicp", dict()), ("FAST_VGICP", "vgicp", dict(ndt_neighbors=7))])
 def test_cost_evaluation_matches_oracle(scene, kind, okind, kw):
     import lsdreg
     from oracle.reg import OracleMatcher
     g = lsdreg.Matcher(kind, **kw)
-    o = OracleMatcher(okind, neighbors=kw.get("ndt_neighbors", 7))
+    o = OracleMatcher(okind, neighbors=kw.get("ndt_neighbors", 7 if okind == "ndt" else 1))
     for mm in (g, o):
         mm.set_target(scene["tgt"]); mm.set_source(scene["src"])
-    if okind == "ndt":
+    if okind in ("ndt", "vgicp"):
         assert g.stats()["n_voxels"] == o.n_voxels
     for T in (scene["guess"], scene["Tgt"]):
         eg, Hg, bg, ncg = g.cost(T)
@@ -54,12 +55,12 @@ def test_cost_evaluation_matches_oracle(scene, kind, okind, kw):
     np.testing.assert_allclose(g.cost(T2, update=False, deriv=False)[0], o.cost(T2, update=False, deriv=False)[0], rtol=1e-6)
 
 
-@pytest.mark.parametrize("kind,okind", [("NDT_CUDA", "ndt"), ("FAST_GICP", "gicp")])
+@pytest.mark.parametrize("kind,okind", [("NDT_CUDA", "ndt"), ("FAST_GICP", "gicp"), ("FAST_VGICP", "vgicp")])
 def test_align_pose_parity_and_fitness(scene, kind, okind):
     import lsdreg
     from oracle.reg import OracleMatcher
     g = lsdreg.Matcher(kind)
-    o = OracleMatcher(okind)
+    o = OracleMatcher(okind, **(dict(neighbors=1, trans_eps=0.1, rot_eps=0.1) if okind == "vgicp" else {}))
     for mm in (g, o):
         mm.set_target(scene["tgt"]); mm.set_source(scene["src"])
     Tf32 = g.align(scene["guess"])
@@ -90,3 +91,28 @@ def test_registration_protocol_edge_cases(scene):
     assert g.fitness(25.0, T=far) > 1e300                   # PCL returns DBL_MAX when nothing is in range
     with pytest.raises(ValueError):
         lsdreg.Matcher("ICP")
+
+
+def test_slam_wrapper_pointcloud_align(scene):
+    """The pybind11 entry map_manager.py:190-192 calls: same result as the C-ABI GICP with the settings of
+    graph_utils.cpp:35-37, the >= 50 m guess guard, and the right answer."""
+    import os
+    import sys
+    import lsdreg
+    pkg = os.path.dirname(lsdreg.capi.LIB_PATH)
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    import slam_wrapper as slam
+    src, tgt, guess = scene["src"], scene["tgt"], scene["guess"].astype(np.float32)
+    T = slam.pointcloud_align(src, tgt, guess)
+    assert T.dtype == np.float32 and T.shape == (4, 4)
+    g = lsdreg.Matcher("FAST_GICP", max_corr_dist=5.0, transformation_epsilon=1e-2, max_iterations=64, k_correspondences=20)
+    g.set_source(src); g.set_target(tgt)
+    np.testing.assert_allclose(T, g.align(guess), atol=1e-6)
+    assert np.abs(T[:3, 3] - scene["Tgt"][:3, 3]).max() < 0.05
+    # a guess 50 m or more away has its translation zeroed before the solve (graph_utils.cpp:24-32)
+    far = guess.copy(); far[:3, 3] += np.array([60.0, 0, 0], np.float32)
+    zeroed = guess.copy(); zeroed[:3, 3] = 0
+    np.testing.assert_allclose(slam.pointcloud_align(src, tgt, far), slam.pointcloud_align(src, tgt, zeroed), atol=1e-6)
+    T2, conv, fit = slam.registration_align("FAST_VGICP", src, tgt, guess)
+    assert conv and np.abs(T2[:3, 3] - scene["Tgt"][:3, 3]).max() < 0.1 and fit < 1.0
