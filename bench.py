@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knn-batch", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: upload each scan inside lsd_lio_scan instead of one scan ahead")
     ap.add_argument("--knn-batch", type=int, default=1 << 21, help="queries in the batched k-NN leg (N=1)")
     ap.add_argument("--mg-mode", default="replicas", choices=["replicas", "shard"],
                     help="N>1: 'replicas' = one map replica and one independent scan stream per GPU (weak scaling, no "
@@ -272,16 +273,21 @@ def main():
     def prior_vec(stp):
         return lsdreg.make_state(pos=stp[4], rot_xyzw=quat_from_R(stp[3]))
 
-    def run_steps(steps, scans, timed_from):
-        """Returns (wall seconds of the timed part, per-step infos).  Bracketed by sync + barrier."""
+    def run_steps(steps, scans, timed_from, prefetch=False):
+        """Returns (wall seconds of the timed part, per-step infos).  Bracketed by sync + barrier.
+        prefetch: double-buffered ingest — the H2D copy of scan s+1 is started before scan s is registered."""
         infos = []
         t_start = None
+        if prefetch:
+            lio.prefetch(scans[0])
         for s, stp in enumerate(steps):
             if s == timed_from:
                 torch.cuda.synchronize()
                 if dist is not None:
                     dist.barrier()
                 t_start = time.perf_counter()
+            if prefetch and s + 1 < len(steps):
+                lio.prefetch(scans[s + 1])
             x, P, info = lio.scan(scans[s], prior_vec(stp), P0)
             if s >= timed_from:
                 info["pos_err"] = float(np.abs(x[:3] - stp[2]).max())
@@ -307,7 +313,7 @@ def main():
     for hs in host_scans:  # first DMA from a freshly pinned buffer pays a one-off mapping cost: take it here
         scratch[:hs.shape[0]].copy_(hs, non_blocking=True)
     torch.cuda.synchronize()
-    wall_b, infos_b = run_steps(steps_b, host_scans, W)
+    wall_b, infos_b = run_steps(steps_b, host_scans, W, prefetch=not args.no_prefetch)
     # H2D probe: what this box's PCIe path gives a 1.6 MB pinned copy (explains e2e - value)
     probe_src = host_scans[0]
     probe_dst = torch.empty(probe_src.shape, dtype=probe_src.dtype, device=dev)
@@ -399,7 +405,10 @@ def main():
         "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * wall_b / K, "h2d_probe_us": h2d_us,
                 "h2d_probe_gbs": probe_src.numel() * 4 / (h2d_us * 1e-6) / 1e9,
-                "host_binding": f"{numa_cpus} CPUs local to the GPU (NVML affinity)" if numa_cpus else "unbound"},
+                "host_binding": f"{numa_cpus} CPUs local to the GPU (NVML affinity)" if numa_cpus else "unbound",
+                "ingest": "serial: H2D inside lsd_lio_scan" if args.no_prefetch else
+                          "double-buffered: lsd_lio_prefetch uploads scan k+1 on a copy stream while scan k is registered; "
+                          "every scan's H2D copy and result read-back are inside the timed region"},
         "gpu_launches": int(np.sum([i["kernel_launches"] for i in infos_a])),
         "roofline": {"kernel": "lio_hmodel_kernel<search>", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -198,6 +198,11 @@ lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* s
                           lsd_lio_info_t* info);
 lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double* state26_inout,
                               double* P529_inout, lsd_lio_info_t* info);
+/* Double-buffered ingest (no reference counterpart: the reference copies nothing).  Starts the host->device copy
+ * of the NEXT scan on a copy stream and returns at once; a following lsd_lio_scan with the same (pointer, n)
+ * uses the staged copy instead of uploading again, so the PCIe transfer of scan k+1 overlaps the registration
+ * of scan k.  The host buffer must stay unchanged (and, to overlap, pinned) until that lsd_lio_scan returns. */
+lsd_status_t lsd_lio_prefetch(lsd_lio_t* l, const float* scan_host, int n);
 
 /* ------------------------------------------------------------------------------------------
  * Scan matcher — replaces what select_registration_method() hands out

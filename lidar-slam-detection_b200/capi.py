@@ -106,6 +106,7 @@ SIGNATURES = [
     ("lsd_lio_map_incremental", _i, [_vp, _vp, _pi]),
     ("lsd_lio_scan", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(LioInfo)]),
     ("lsd_lio_scan_dev", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(LioInfo)]),
+    ("lsd_lio_prefetch", _i, [_vp, _vp, _i]),
     ("lsd_reg_default_params", None, [C.POINTER(RegParams), _i]),
     ("lsd_reg_create", _i, [_pp, C.POINTER(RegParams)]),
     ("lsd_reg_destroy", _i, [_vp]),
@@ -618,6 +619,14 @@ class LioFrontend:
         n = C.c_int()
         check(lib.lsd_lio_map_incremental(self.h, _ptr(state), C.byref(n)))
         return n.value
+
+    def prefetch(self, scan):
+        """Start the H2D copy of the NEXT scan (host numpy / pinned torch tensor); the following scan() with the
+        same buffer uses the staged copy.  Keep the buffer alive and unchanged until then."""
+        if isinstance(scan, np.ndarray):
+            if scan.dtype != np.float32 or not scan.flags.c_contiguous:
+                raise ValueError("prefetch needs the exact float32 C-contiguous buffer later passed to scan()")
+        check(lib.lsd_lio_prefetch(self.h, _ptr(scan), scan.shape[0]))
 
     def scan(self, scan, state: np.ndarray, P: np.ndarray):
         """Whole pass.  `scan`: numpy [n,4] (host pointer, H2D inside) or CUDA torch tensor (device)."""

@@ -852,6 +852,14 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
 
 using namespace lsd;
 
+// a staging slot that holds no pending prefetch (else the older pending one, which is then dropped)
+static lsd_lio::Stage* free_stage(lsd_lio* l) {
+  for (int i = 0; i < 2; i++) if (!l->stage[i].valid) return &l->stage[i];
+  lsd_lio::Stage* s = l->stage[0].age <= l->stage[1].age ? &l->stage[0] : &l->stage[1];
+  s->valid = false;
+  return s;
+}
+
 extern "C" {
 
 void lsd_lio_default_params(lsd_lio_params_t* p) {
@@ -890,7 +898,11 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   l->max_search_blocks = 148 * 6;
   cudaError_t e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking);
   auto A = [&](void** ptr, size_t b) { if (e == cudaSuccess) e = cudaMalloc(ptr, b); if (e == cudaSuccess) e = cudaMemset(*ptr, 0, b); };
-  A((void**)&l->d_scan, (size_t)p->max_scan_points * 16);
+  for (int i = 0; i < 2; i++) {
+    A((void**)&l->stage[i].buf, (size_t)p->max_scan_points * 16);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->stage[i].ev, cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking);
   A((void**)&l->d_body, (size_t)p->max_scan_points * 16);  // voxel-grid output may equal the input size
   A((void**)&l->d_n, 64);
   A((void**)&l->d_near, mp * 5 * 16);
@@ -927,7 +939,9 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   if (!l) return LSD_OK;
   cudaSetDevice(l->device);
   if (l->stream) cudaStreamSynchronize(l->stream);
-  void* ptrs[] = {l->d_scan, l->d_body, l->d_n, l->d_near, l->d_near_cnt, l->d_selected, l->d_flags, l->d_plane, l->d_world,
+  if (l->copy_stream) { cudaStreamSynchronize(l->copy_stream); cudaStreamDestroy(l->copy_stream); }
+  for (int i = 0; i < 2; i++) if (l->stage[i].ev) cudaEventDestroy(l->stage[i].ev);
+  void* ptrs[] = {l->stage[0].buf, l->stage[1].buf, l->d_body, l->d_n, l->d_near, l->d_near_cnt, l->d_selected, l->d_flags, l->d_plane, l->d_world,
                   l->d_partials, l->d_done, l->d_added, l->d_pabcd, l->d_plane_ok};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(l->h_result); cudaFreeHost(l->h_added);
@@ -1059,8 +1073,9 @@ lsd_status_t lsd_lio_load_scan(lsd_lio_t* l, const float* scan_host, int n, int 
   if (!l || (n > 0 && !scan_host)) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(l->device));
   if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
-  LSD_CUDA(cudaMemcpyAsync(l->d_scan, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
-  return lsd_lio_load_scan_dev(l, reinterpret_cast<const float*>(l->d_scan), n, downsample, n_down);
+  lsd_lio::Stage* sg = free_stage(l);
+  LSD_CUDA(cudaMemcpyAsync(sg->buf, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
+  return lsd_lio_load_scan_dev(l, reinterpret_cast<const float*>(sg->buf), n, downsample, n_down);
 }
 
 lsd_status_t lsd_lio_get_down(lsd_lio_t* l, float* out_host, int cap, int* n_down) {
@@ -1121,6 +1136,19 @@ lsd_status_t lsd_lio_map_incremental(lsd_lio_t* l, const double* state26, int* n
   return s;
 }
 
+lsd_status_t lsd_lio_prefetch(lsd_lio_t* l, const float* scan_host, int n) {
+  if (!l || !scan_host || n <= 0) return LSD_ERR_INVALID;
+  if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
+  LSD_CUDA(cudaSetDevice(l->device));
+  // Every staging buffer is idle here: the voxel grid of the last scan (their only reader) finished before
+  // lsd_lio_scan returned.  A slot holding a prefetched, not yet consumed scan is kept.
+  lsd_lio::Stage* sg = free_stage(l);
+  LSD_CUDA(cudaMemcpyAsync(sg->buf, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->copy_stream));
+  LSD_CUDA(cudaEventRecord(sg->ev, l->copy_stream));
+  sg->host = scan_host; sg->n = n; sg->valid = true; sg->age = ++l->stage_clock;
+  return LSD_OK;
+}
+
 lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double* state26_inout, double* P529_inout,
                               lsd_lio_info_t* info) {
   if (!l || (n > 0 && !scan_dev) || !state26_inout || !P529_inout) return LSD_ERR_INVALID;
@@ -1133,8 +1161,16 @@ lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* s
   if (!l || (n > 0 && !scan_host) || !state26_inout || !P529_inout) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(l->device));
   if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
-  LSD_CUDA(cudaMemcpyAsync(l->d_scan, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
-  return lio_scan(l, l->d_scan, n, state26_inout, P529_inout, info);
+  lsd_lio::Stage* sg = nullptr;
+  for (int i = 0; i < 2; i++) if (l->stage[i].valid && l->stage[i].host == scan_host && l->stage[i].n == n) sg = &l->stage[i];
+  if (sg) {  // uploaded by lsd_lio_prefetch while the previous scan was being registered
+    LSD_CUDA(cudaStreamWaitEvent(l->stream, sg->ev, 0));
+  } else {
+    sg = free_stage(l);
+    LSD_CUDA(cudaMemcpyAsync(sg->buf, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
+  }
+  sg->valid = false;
+  return lio_scan(l, sg->buf, n, state26_inout, P529_inout, info);
 }
 
 void lsd_lio_init_cov(double* P529) { if (P529) eskf::init_cov(P529); }

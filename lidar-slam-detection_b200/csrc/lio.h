@@ -25,7 +25,12 @@ struct lsd_lio {
   lsd_map* map = nullptr;       // hash-voxel map (iVox replacement), owned
   lsd_voxelgrid* vg = nullptr;  // scan downsampler, owned
   cudaStream_t stream = nullptr;
-  float4* d_scan = nullptr;     // raw scan staging (host-pointer entry points)
+  // raw scan staging (host-pointer entry points): two slots, so lsd_lio_prefetch can upload scan k+1
+  // while scan k (staged in the other slot) is being registered
+  struct Stage { float4* buf = nullptr; const float* host = nullptr; int n = 0; bool valid = false; cudaEvent_t ev = nullptr; long long age = 0; };
+  Stage stage[2];
+  long long stage_clock = 0;
+  cudaStream_t copy_stream = nullptr;
   float4* d_body = nullptr;     // feats_down_body
   int* d_n = nullptr;           // feats_down_size, device resident
   float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)

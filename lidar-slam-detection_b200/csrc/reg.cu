@@ -238,6 +238,58 @@ __global__ void __launch_bounds__(kRegWarps * 32, 3) gicp_normals_kernel(MapView
   }
 }
 
+// Exact nearest neighbour with d2 <= max_sq for ONE THREAD (batched shape, cf. knn_query_thread_kernel): Chebyshev
+// shells around the query's voxel, tag probes in L2, cells pruned by their distance to the query, stop as soon as
+// no unseen shell can hold a closer point.  Same result as knn_exact_warp<1> (any exact search gives the same
+// (d2, id) minimum).
+__device__ __forceinline__ bool nn1_exact_thread(const MapView& mv, float qx, float qy, float qz, float max_sq, float* d2_out,
+                                                 int* id_out) {
+  const int3 c = pos2grid(qx, qy, qz, mv.inv_res);
+  const float fx = qx * mv.inv_res - (float)c.x, fy = qy * mv.inv_res - (float)c.y, fz = qz * mv.inv_res - (float)c.z;
+  const int rmax = (int)ceilf(sqrtf(max_sq) * mv.inv_res) + 1;
+  float bd = 3.0e38f; int bi = 0x7fffffff;
+  bool found = false;
+  const float res2 = mv.res * mv.res * (1.0f - 4e-5f);
+  for (int r = 0; r <= rmax; r++) {
+    const float bound = found ? bd : max_sq;
+    if (r >= 1) { const float lo = (float)(r - 1); if (bound < lo * lo * res2) break; }
+    for (int i = -r; i <= r; i++) {
+      const float gx = fmaxf(0.f, fmaxf((float)i - 0.5f - fx, fx - ((float)i + 0.5f)));
+      for (int j = -r; j <= r; j++) {
+        const float gy = fmaxf(0.f, fmaxf((float)j - 0.5f - fy, fy - ((float)j + 0.5f)));
+        const bool face = (i == -r || i == r || j == -r || j == r);
+        const int step = face ? 1 : max(2 * r, 1);
+        for (int l = -r; l <= r; l += step) {
+          const float gz = fmaxf(0.f, fmaxf((float)l - 0.5f - fz, fz - ((float)l + 0.5f)));
+          const float cur = found ? bd : max_sq;
+          if ((gx * gx + gy * gy + gz * gz) * res2 > cur) continue;  // no point of this voxel can beat the current best
+          const int x = c.x + i, y = c.y + j, z = c.z + l;
+          if (!coord_ok(x, y, z)) continue;
+          const unsigned long long key = pack_key(x, y, z, 0);
+          uint4 h;
+          const CellLine* ln = tag_find(mv, key, &h);
+          if (!ln) continue;
+          const unsigned cnt = h.z;
+          const int levels = cnt > (unsigned)kPtsPerLine ? min((int)((cnt - 1) / kPtsPerLine), kMaxLevel) : 0;
+          for (int L = 0; L <= levels; L++) {
+            const CellLine* ll = ln;
+            if (L > 0) { uint4 hl; ll = tag_find(mv, key | ((unsigned long long)L << 57), &hl); if (!ll) continue; }
+            const int n = (int)min(cnt - (unsigned)(L * kPtsPerLine), (unsigned)kPtsPerLine);
+            for (int k = 0; k < n; k++) {
+              const float4 a = ldg_f4(&ll->pts[k]);
+              const float d2 = dist2(qx, qy, qz, a.x, a.y, a.z);
+              const int pid = __float_as_int(a.w);
+              if (d2 <= max_sq && (d2 < bd || (d2 == bd && pid < bi))) { bd = d2; bi = pid; found = true; }
+            }
+          }
+        }
+      }
+    }
+  }
+  *d2_out = bd; *id_out = bi;
+  return found;
+}
+
 struct Pose34d { double R[9], t[3]; };
 
 // update_correspondences (fast_gicp_impl.hpp:119-157): 1-NN of the transformed source point, Mahalanobis
@@ -282,6 +334,37 @@ __global__ void __launch_bounds__(kRegWarps * 32, 3) gicp_corr_kernel(MapView mv
     M[0] = c00 * idet; M[1] = (A[2] * A[7] - A[1] * A[8]) * idet; M[2] = (A[1] * A[5] - A[2] * A[4]) * idet;
     M[3] = (A[0] * A[8] - A[2] * A[6]) * idet; M[4] = (A[2] * A[3] - A[0] * A[5]) * idet; M[5] = (A[0] * A[4] - A[1] * A[3]) * idet;
   }
+}
+
+// update_correspondences, batched shape: one thread per source point (nn1_exact_thread)
+__global__ void __launch_bounds__(256) gicp_corr_thread_kernel(MapView mv, const float4* __restrict__ src, const double* __restrict__ src_nrm,
+                                                               int n, const double* __restrict__ tgt_nrm, Pose34d T, Pose34f Tf,
+                                                               float max_corr_sq, int* __restrict__ corr, double* __restrict__ maha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = __ldg(src + i);
+  const float qx = Tf.R[0] * a.x + Tf.R[1] * a.y + Tf.R[2] * a.z + Tf.t[0];
+  const float qy = Tf.R[3] * a.x + Tf.R[4] * a.y + Tf.R[5] * a.z + Tf.t[1];
+  const float qz = Tf.R[6] * a.x + Tf.R[7] * a.y + Tf.R[8] * a.z + Tf.t[2];
+  float d2; int id;
+  const bool f = nn1_exact_thread(mv, qx, qy, qz, max_corr_sq, &d2, &id);
+  const int c = (f && d2 < max_corr_sq) ? id : -1;
+  corr[i] = c;
+  if (c < 0) return;
+  const double* na = src_nrm + 4 * (size_t)i;
+  const double* nbv = tgt_nrm + 4 * (size_t)c;
+  const double rn[3] = {T.R[0] * na[0] + T.R[1] * na[1] + T.R[2] * na[2], T.R[3] * na[0] + T.R[4] * na[1] + T.R[5] * na[2],
+                        T.R[6] * na[0] + T.R[7] * na[1] + T.R[8] * na[2]};
+  double A[9];
+#pragma unroll
+  for (int p = 0; p < 3; p++)
+#pragma unroll
+    for (int q = 0; q < 3; q++) A[3 * p + q] = (p == q ? 2.0 : 0.0) - 0.999 * (nbv[p] * nbv[q] + rn[p] * rn[q]);
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double idet = 1.0 / (A[0] * c00 + A[1] * c01 + A[2] * c02);
+  double* M = maha + 6 * (size_t)i;
+  M[0] = c00 * idet; M[1] = (A[2] * A[7] - A[1] * A[8]) * idet; M[2] = (A[1] * A[5] - A[2] * A[4]) * idet;
+  M[3] = (A[0] * A[8] - A[2] * A[6]) * idet; M[4] = (A[2] * A[3] - A[0] * A[5]) * idet; M[5] = (A[0] * A[4] - A[1] * A[3]) * idet;
 }
 
 // linearize / compute_error (fast_gicp_impl.hpp:159-242), one thread per source point, double.
@@ -526,6 +609,32 @@ __global__ void __launch_bounds__(kRegWarps * 32, 3) fitness_kernel(MapView mv, 
   grid_finalize<2>(partials, done, result, 0, -1, 0.0, kResSeq, seq, sc, 0);
 }
 
+// getFitnessScore, batched shape: one thread per source point, block reduction, same last-block fold
+__global__ void __launch_bounds__(256) fitness_thread_kernel(MapView mv, const float4* __restrict__ src, int n, Pose34f Tf, float search_sq,
+                                                             float max_range, double* __restrict__ partials, unsigned* __restrict__ done,
+                                                             double* __restrict__ result, double seq, ShardComm sc) {
+  __shared__ double s_acc[8][2];
+  double sum = 0.0, cnt = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = __ldg(src + i);
+    const float qx = Tf.R[0] * a.x + Tf.R[1] * a.y + Tf.R[2] * a.z + Tf.t[0];
+    const float qy = Tf.R[3] * a.x + Tf.R[4] * a.y + Tf.R[5] * a.z + Tf.t[1];
+    const float qz = Tf.R[6] * a.x + Tf.R[7] * a.y + Tf.R[8] * a.z + Tf.t[2];
+    float d2; int id;
+    if (nn1_exact_thread(mv, qx, qy, qz, search_sq, &d2, &id) && d2 <= max_range) { sum += (double)d2; cnt += 1.0; }
+  }
+  sum = warp_sum(sum); cnt = warp_sum(cnt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_acc[warp][0] = sum; s_acc[warp][1] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += s_acc[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * kNV + threadIdx.x] = s;
+  }
+  grid_finalize<2>(partials, done, result, 0, -1, 0.0, kResSeq, seq, sc, 0);
+}
+
 }  // namespace lsd
 
 // ==================================================================== host side
@@ -580,6 +689,7 @@ static lsd_status_t reg_wait(lsd_reg* r, double seq) {
   }
 }
 
+constexpr int kThreadShapeMin = 16384;  // clouds from this size on use the thread-per-point search kernels
 static int reg_grid(int n) { return std::max(1, std::min((n + 255) / 256, kLioMaxGrid)); }
 static int warp_grid(int n) { return std::max(1, std::min((n + kRegWarps - 1) / kRegWarps, 148 * 6)); }
 
@@ -619,8 +729,12 @@ static lsd_status_t reg_cost(lsd_reg* r, const double* T, bool update, double* H
     T_to_pose(T, &Td, &Tf);
     if (update) {
       const float mc = (float)r->p.max_corr_dist;
-      gicp_corr_kernel<<<warp_grid(r->n_src), kRegWarps * 32, 0, st>>>(r->tgt_map->view, r->d_src, r->d_src_nrm, r->n_src, r->d_tgt_nrm, Td, Tf,
-                                                                     mc * mc, r->d_corr, r->d_maha);
+      if (r->n_src >= kThreadShapeMin)
+        gicp_corr_thread_kernel<<<(r->n_src + 255) / 256, 256, 0, st>>>(r->tgt_map->view, r->d_src, r->d_src_nrm, r->n_src, r->d_tgt_nrm, Td, Tf,
+                                                                        mc * mc, r->d_corr, r->d_maha);
+      else
+        gicp_corr_kernel<<<warp_grid(r->n_src), kRegWarps * 32, 0, st>>>(r->tgt_map->view, r->d_src, r->d_src_nrm, r->n_src, r->d_tgt_nrm, Td, Tf,
+                                                                       mc * mc, r->d_corr, r->d_maha);
       r->launches++;
     }
     const int g = reg_grid(r->n_src);
@@ -1052,8 +1166,12 @@ lsd_status_t lsd_reg_fitness(lsd_reg_t* r, const double* T16_or_null, double max
   T_to_pose(T16_or_null ? T16_or_null : r->final_T, nullptr, &Tf);
   const double seq = (double)(++r->seq);
   const float search_sq = (float)std::min(max_range, 64.0 * r->p.map_resolution * r->p.map_resolution * 64.0);
-  fitness_kernel<<<warp_grid(r->n_src), kRegWarps * 32, 0, st>>>(r->tgt_map->view, r->d_src, r->n_src, Tf, search_sq, (float)max_range,
-                                                                r->d_partials, r->d_done, r->d_result, seq, r->sc);
+  if (r->n_src >= kThreadShapeMin)
+    fitness_thread_kernel<<<reg_grid(r->n_src), 256, 0, st>>>(r->tgt_map->view, r->d_src, r->n_src, Tf, search_sq, (float)max_range,
+                                                              r->d_partials, r->d_done, r->d_result, seq, r->sc);
+  else
+    fitness_kernel<<<warp_grid(r->n_src), kRegWarps * 32, 0, st>>>(r->tgt_map->view, r->d_src, r->n_src, Tf, search_sq, (float)max_range,
+                                                                  r->d_partials, r->d_done, r->d_result, seq, r->sc);
   LSD_CUDA(cudaGetLastError());
   r->launches++;
   lsd_status_t w = reg_wait(r, seq);

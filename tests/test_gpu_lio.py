@@ -141,3 +141,43 @@ def test_no_effective_points(small_world):
     x1, P1, info = g.scan(small_world["scan"], x, P)
     assert info["status"] == lsdreg.NO_EFFECTIVE_POINTS and info["n_eff"] == 0
     np.testing.assert_array_equal(x1, x)
+
+
+def test_prefetch_is_transparent(small_world):
+    """Double-buffered ingest (lsd_lio_prefetch): poses are bit-identical to the serial path, whatever the caller
+    prefetches — the right scan, a scan it then does not register, or two scans in a row."""
+    import lsdreg
+    from lsdreg import synth
+    from oracle import eskf
+    scans = []
+    for k in range(4):
+        Rk = small_world["Rgt"] @ synth.rot_from_rpy(0, 0, 0.02 * k)
+        tk = small_world["tgt"] + np.array([0.4 * k, 0.1 * k, 0.0])
+        scans.append(np.ascontiguousarray(synth.scan64(10 + k, 250, Rk, tk)))
+    decoy = np.ascontiguousarray(scans[0][::-1] + np.float32(3.0))
+
+    def run(mode):
+        g, o, prior = _pair(small_world)
+        x = prior.to_vec(); P = eskf.init_P()
+        out = []
+        if mode == "pipelined":
+            g.prefetch(scans[0])
+        for k in range(4):
+            if mode == "pipelined" and k + 1 < 4:
+                g.prefetch(scans[k + 1])
+            if mode == "decoy":
+                g.prefetch(decoy)                      # never registered: must not leak into scan k
+                if k == 2:
+                    g.prefetch(scans[3])               # two pending prefetches; the second one is used next round
+            P = P + np.eye(23) * 1e-2
+            x, P, info = g.scan(scans[k], x, P)
+            out.append((x.copy(), info["n_down"], info["n_eff"]))
+        g.sync()
+        return out
+
+    ref = run("serial")
+    for mode in ("pipelined", "decoy"):
+        got = run(mode)
+        for (xa, na, ea), (xb, nb, eb) in zip(ref, got):
+            assert na == nb and ea == eb
+            np.testing.assert_array_equal(xa, xb)

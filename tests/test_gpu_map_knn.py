@@ -106,3 +106,39 @@ def test_incremental_insert_equals_bulk(small_world):
     ia, da, ca = a.knn(q)
     ib, db, cb = b.knn(q)
     assert (ia == ib).all() and (da == db).all() and (ca == cb).all()
+
+
+@pytest.mark.parametrize("nearby,k", [(18, 5), (74, 5), (18, 1), (6, 5)])
+def test_batched_thread_per_query_kernel_bit_exact(maps, small_world, nearby, k):
+    """From 65 536 queries on lsd_knn_query switches to the thread-per-query kernel: same bits as the oracle and as
+    the warp-per-query kernel (the same queries in chunks below the threshold), overflow buckets included."""
+    import lsdreg
+    g, o = maps
+    rng = np.random.default_rng(21)
+    m = small_world["map"]
+    nq = 70000
+    q = m[rng.integers(0, m.shape[0], nq)].copy()
+    q[:, :3] += rng.normal(0, 0.15, (nq, 3)).astype(np.float32)
+    q[:100, :3] += 500.0                                            # some queries far from any voxel
+    idx, d2, cnt = g.knn(q, k=k, max_sq=5.0, stencil=nearby)        # thread kernel
+    parts = [g.knn(q[a:a + 30000], k=k, max_sq=5.0, stencil=nearby) for a in range(0, nq, 30000)]   # warp kernel
+    np.testing.assert_array_equal(idx, np.concatenate([p[0] for p in parts]))
+    np.testing.assert_array_equal(d2, np.concatenate([p[1] for p in parts]))
+    np.testing.assert_array_equal(cnt, np.concatenate([p[2] for p in parts]))
+    o.set_nearby(nearby)
+    sub = rng.integers(0, nq, 4000)
+    oi, od, _, oc = o.knn(q[sub], k, 5.0)
+    np.testing.assert_array_equal(idx[sub], oi)
+    np.testing.assert_array_equal(d2[sub].view(np.int32), od.view(np.int32))
+    np.testing.assert_array_equal(cnt[sub], oc)
+    o.set_nearby(18)
+    # a map with 40-point buckets: the overflow-level walk of the thread kernel
+    gm = lsdreg.HashVoxelMap(0.5, 14)
+    pts = np.zeros((4000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-0.2, 0.2, (4000, 3)) + rng.integers(0, 10, (4000, 1)) * np.array([[0.5, 0, 0]])
+    gm.insert(pts, 0)
+    qq = np.repeat(pts[:700], 100, axis=0)[:70000].copy()
+    a = gm.knn(qq, k=k, max_sq=5.0, stencil=nearby)
+    b = [gm.knn(qq[s:s + 30000], k=k, max_sq=5.0, stencil=nearby) for s in range(0, 70000, 30000)]
+    for j in range(3):
+        np.testing.assert_array_equal(a[j], np.concatenate([p[j] for p in b]))

@@ -116,3 +116,31 @@ def test_slam_wrapper_pointcloud_align(scene):
     np.testing.assert_allclose(slam.pointcloud_align(src, tgt, far), slam.pointcloud_align(src, tgt, zeroed), atol=1e-6)
     T2, conv, fit = slam.registration_align("FAST_VGICP", src, tgt, guess)
     assert conv and np.abs(T2[:3, 3] - scene["Tgt"][:3, 3]).max() < 0.1 and fit < 1.0
+
+
+def test_gicp_thread_shape_kernels_match_oracle(scene):
+    """Clouds of >= 16 384 points use the thread-per-point correspondence / fitness kernels: same correspondences,
+    cost, derivatives and fitness as the oracle (and therefore as the warp-per-point kernels tested above)."""
+    import lsdreg
+    from lsdreg import synth
+    from oracle.reg import OracleMatcher
+    Tgt = scene["Tgt"]
+    src = synth.scan64(3, 500, Tgt[:3, :3], Tgt[:3, 3] + np.array([60, 40, 0]))
+    assert src.shape[0] >= 16384
+    g = lsdreg.Matcher("FAST_GICP")
+    o = OracleMatcher("gicp")
+    for mm in (g, o):
+        mm.set_target(scene["tgt"]); mm.set_source(src)
+    far = scene["guess"].copy(); far[:3, 3] += [0.8, -0.6, 0.3]          # many points need several shells / find nothing
+    for T in (scene["guess"], Tgt, far):
+        eg, Hg, bg, ncg = g.cost(T)
+        eo, Ho, bo = o.cost(T)
+        assert ncg == o.n_corr and ncg > 5000
+        np.testing.assert_allclose(eg, eo, rtol=1e-6)
+        np.testing.assert_allclose(Hg, Ho, rtol=1e-3, atol=1e-3 * np.abs(Ho).max())
+        np.testing.assert_allclose(bg, bo, rtol=1e-3, atol=1e-3 * np.abs(bo).max())
+    for rng_ in (25.0, 0.25):
+        np.testing.assert_allclose(g.fitness(rng_, T=Tgt), o.fitness(T=Tgt, max_range=rng_), rtol=1e-5)
+    Tg = g.align(scene["guess"]); To = o.align(scene["guess"])
+    assert g.converged == o.converged and g.iterations == o.iterations
+    assert np.abs(Tg[:3, 3] - To[:3, 3]).max() < 1e-4
