@@ -256,6 +256,9 @@ lsd_status_t lsd_reg_fitness(lsd_reg_t* r, const double* T16_or_null, double max
 /* One cost evaluation (parity tap): update != 0 = linearize(T) (correspondences refreshed), else
  * compute_error(T).  H36/b6 may be NULL. */
 lsd_status_t lsd_reg_cost(lsd_reg_t* r, const double* T16, int update, double* H36, double* b6, double* err, int* n_corr);
+/* Parity tap: the correspondences of the last linearisation.  GICP: [n_src] target point index or -1
+ * (correspondences_, fast_gicp_impl.hpp:119-157); NDT / VGICP: [neighbors, n_src] voxel-table slot or -1. */
+lsd_status_t lsd_reg_get_correspondences(lsd_reg_t* r, int32_t* corr_host, int cap, int* n);
 lsd_status_t lsd_reg_stats(lsd_reg_t* r, int* n_voxels, long long* launches);
 
 /* ------------------------------------------------------------------------------------------

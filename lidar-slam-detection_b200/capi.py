@@ -119,6 +119,7 @@ SIGNATURES = [
     ("lsd_reg_get_final", _i, [_vp, _vp, _vp]),
     ("lsd_reg_fitness", _i, [_vp, _vp, _d, C.POINTER(_d)]),
     ("lsd_reg_cost", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_d), _pi]),
+    ("lsd_reg_get_correspondences", _i, [_vp, _vp, _i, _pi]),
     ("lsd_reg_stats", _i, [_vp, _pi, C.POINTER(C.c_longlong)]),
     ("lsd_vfe_default_params", None, [C.POINTER(VfeParams)]),
     ("lsd_vfe_create", _i, [_pp, C.POINTER(VfeParams)]),
@@ -413,6 +414,14 @@ class Matcher:
         check(lib.lsd_reg_cost(self.h, _ptr(T), int(update), _ptr(H) if deriv else None, _ptr(b) if deriv else None,
                                C.byref(e), C.byref(nc)))
         return e.value, H, b, nc.value
+
+    def correspondences(self) -> np.ndarray:
+        """Correspondences of the last linearisation (GICP: target indices; NDT / VGICP: voxel slots), -1 = none."""
+        n = C.c_int()
+        check(lib.lsd_reg_get_correspondences(self.h, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.int32)
+        check(lib.lsd_reg_get_correspondences(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
 
     def stats(self):
         nv, ln = C.c_int(), C.c_longlong()

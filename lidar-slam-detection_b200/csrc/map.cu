@@ -299,7 +299,7 @@ lsd_status_t lsd_init(int device) {
   if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return LSD_ERR_INVALID; }
   g_device = device;
   LSD_CUDA(cudaSetDevice(device));
-  // L2 fetch granularity stays at the driver default: measured on B200 (profiles/r01g_knn_batch.txt), asking
+  // L2 fetch granularity stays at the driver default: measured on B200 (profiles/r01_knn_batch.txt), asking
   // for 32-byte fetches halves the DRAM bytes of a hash probe but makes the batched k-NN 19 % SLOWER.
   // LSD_L2_FETCH_GRANULARITY=32|64|128 overrides it for A/B measurements.
   if (const char* e = getenv("LSD_L2_FETCH_GRANULARITY")) {

@@ -1181,6 +1181,17 @@ lsd_status_t lsd_reg_fitness(lsd_reg_t* r, const double* T16_or_null, double max
   return LSD_OK;
 }
 
+lsd_status_t lsd_reg_get_correspondences(lsd_reg_t* r, int32_t* corr_host, int cap, int* n) {
+  if (!r || !n || (cap > 0 && !corr_host)) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(r->device));
+  const int per = r->p.kind == LSD_REG_GICP ? 1 : r->p.ndt_neighbors;
+  *n = r->n_src * per;
+  const int c = std::min(cap, *n);
+  if (c > 0) LSD_CUDA(cudaMemcpyAsync(corr_host, r->d_corr, (size_t)c * 4, cudaMemcpyDeviceToHost, r->stream));
+  LSD_CUDA(cudaStreamSynchronize(r->stream));
+  return LSD_OK;
+}
+
 lsd_status_t lsd_reg_stats(lsd_reg_t* r, int* n_voxels, long long* launches) {
   if (!r) return LSD_ERR_INVALID;
   if (n_voxels) *n_voxels = (int)r->n_voxels;

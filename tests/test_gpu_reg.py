@@ -44,6 +44,8 @@ def test_cost_evaluation_matches_oracle(scene, kind, okind, kw):
         eg, Hg, bg, ncg = g.cost(T)
         eo, Ho, bo = o.cost(T)
         assert ncg == o.n_corr and ncg > 1000
+        if okind == "gicp":
+            np.testing.assert_array_equal(g.correspondences(), o.corr)   # warp-per-point kernel: same indices
         np.testing.assert_allclose(eg, eo, rtol=1e-6)
         # GICP: a few points have near-degenerate neighbourhood covariances (two smallest eigenvalues
         # equal to rounding); their "plane normal" is arbitrary in ANY eigen-solver, the reference's included
@@ -132,15 +134,17 @@ def test_gicp_thread_shape_kernels_match_oracle(scene):
     for mm in (g, o):
         mm.set_target(scene["tgt"]); mm.set_source(src)
     far = scene["guess"].copy(); far[:3, 3] += [0.8, -0.6, 0.3]          # many points need several shells / find nothing
+    for rng_ in (25.0, 0.25):                                             # pure 1-NN distances: no covariances involved
+        np.testing.assert_allclose(g.fitness(rng_, T=Tgt), o.fitness(T=Tgt, max_range=rng_), rtol=1e-6)
     for T in (scene["guess"], Tgt, far):
         eg, Hg, bg, ncg = g.cost(T)
         eo, Ho, bo = o.cost(T)
         assert ncg == o.n_corr and ncg > 5000
-        np.testing.assert_allclose(eg, eo, rtol=1e-6)
+        np.testing.assert_array_equal(g.correspondences(), o.corr)       # index work: bit-exact
+        # the cost itself is only as reproducible as the covariance directions of (near-)degenerate neighbourhoods
+        np.testing.assert_allclose(eg, eo, rtol=1e-3)
         np.testing.assert_allclose(Hg, Ho, rtol=1e-3, atol=1e-3 * np.abs(Ho).max())
         np.testing.assert_allclose(bg, bo, rtol=1e-3, atol=1e-3 * np.abs(bo).max())
-    for rng_ in (25.0, 0.25):
-        np.testing.assert_allclose(g.fitness(rng_, T=Tgt), o.fitness(T=Tgt, max_range=rng_), rtol=1e-5)
     Tg = g.align(scene["guess"]); To = o.align(scene["guess"])
     assert g.converged == o.converged and g.iterations == o.iterations
     assert np.abs(Tg[:3, 3] - To[:3, 3]).max() < 1e-4
