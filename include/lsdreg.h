@@ -329,6 +329,19 @@ lsd_status_t lsd_imu_get_poses(lsd_imu_t* m, double* poses22, int cap, int* n);
 lsd_status_t lsd_eskf_predict(double* state26_inout, double* P529_inout, double dt, const double* Q144, const double* acc3,
                               const double* gyro3);
 
+/* ------------------------------------------------------------------------------------------
+ * Key-frame cloud filters (row N3) — replaces, for every new key frame (slam/src/slam.cpp:398-410):
+ * pcl::RadiusOutlierRemoval with setRadiusSearch(radius = 1.0) / setMinNeighborsInRadius(min_neighbors = 3)
+ * (slam.cpp:104-108: a point stays iff its radius search, which includes the point itself, returns MORE than
+ * min_neighbors points) followed by pointsDistanceFilter(cloud, out, min_range = 0, max_range = key_frame_range)
+ * (slam_utils.cpp:236-247: min < |x| < max and min < |y| < max).  Order preserving.  radius == 0 skips the
+ * outlier test.  out must hold n points; *n_out = points kept.
+ * ------------------------------------------------------------------------------------------ */
+lsd_status_t lsd_keyframe_filter(const float* xyzi_host, int n, float radius, int min_neighbors, float min_range, float max_range,
+                                 float* out_host, int* n_out);
+lsd_status_t lsd_keyframe_filter_dev(const float* xyzi_dev, int n, float radius, int min_neighbors, float min_range, float max_range,
+                                     float* out_dev, int* n_out);
+
 /* Host-side manifold helpers (exported so bindings/tests use the same algebra as the filter).
  * IMU_Processing.hpp:224-230 initial covariance; state_ikfom boxplus/boxminus. */
 void lsd_lio_init_cov(double* P529);

@@ -140,6 +140,8 @@ SIGNATURES = [
     ("lsd_imu_get_cloud", _i, [_vp, _vp, _i, _pi]),
     ("lsd_imu_get_poses", _i, [_vp, _vp, _i, _pi]),
     ("lsd_eskf_predict", _i, [_vp, _vp, _d, _vp, _vp, _vp]),
+    ("lsd_keyframe_filter", _i, [_vp, _i, _f, _i, _f, _f, _vp, _pi]),
+    ("lsd_keyframe_filter_dev", _i, [_vp, _i, _f, _i, _f, _f, _vp, _pi]),
     ("lsd_lio_init_cov", None, [_vp]),
     ("lsd_state_boxplus", None, [_vp, _vp]),
     ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
@@ -442,6 +444,15 @@ def eskf_update_table(state, P, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=
 
 
 IMU_INITIALIZING = 4
+
+
+def keyframe_filter(pts, radius: float = 1.0, min_neighbors: int = 3, min_range: float = 0.0, max_range: float = 1e9):
+    """RadiusOutlierRemoval + pointsDistanceFilter of a new key frame (slam.cpp:398-410); order preserving."""
+    pts = _f32(pts)
+    out = np.empty_like(pts)
+    n = C.c_int()
+    check(lib.lsd_keyframe_filter(_ptr(pts), pts.shape[0], radius, min_neighbors, min_range, max_range, _ptr(out), C.byref(n)))
+    return out[:n.value].copy()
 
 
 def eskf_predict(state, P, dt, Q, acc, gyro):

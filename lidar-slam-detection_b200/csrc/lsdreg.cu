@@ -6,3 +6,4 @@
 #include "reg.cu"
 #include "vfe.cu"
 #include "imu.cu"
+#include "filters.cu"
