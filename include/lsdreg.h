@@ -32,6 +32,7 @@ typedef int lsd_status_t;
 #define LSD_NO_EFFECTIVE_POINTS 1   /* ekfom_data.valid == false, laserMapping.cpp:888-893      */
 #define LSD_SCAN_TOO_SMALL 2        /* feats_down_size < 5, laserMapping.cpp:1252-1256           */
 #define LSD_MAP_SEEDED 3            /* first scan only seeded the map, laserMapping.cpp:1227-1239 */
+#define LSD_LOCALMAP_NONE 5         /* Localization would set mLocalMap = nullptr (localization.cpp:352-364)                  */
 #define LSD_IMU_INITIALIZING 4      /* ImuProcess::Process returned before undistorting (IMU_Processing.hpp:416-443) */
 #define LSD_ERR_INVALID (-1)
 #define LSD_ERR_CUDA (-2)
@@ -341,6 +342,23 @@ lsd_status_t lsd_keyframe_filter(const float* xyzi_host, int n, float radius, in
                                  float* out_host, int* n_out);
 lsd_status_t lsd_keyframe_filter_dev(const float* xyzi_dev, int n, float radius, int min_neighbors, float min_range, float max_range,
                                      float* out_dev, int* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Local-map assembly for localisation (row N2) — replaces the body of Localization::runUpdateLocalMap
+ * (slam/localization/src/localization.cpp:303-373): key frames within 30 m of the pose, nearest first, thinned by
+ * key_frame_distance, concatenated up to 200 000 points, VoxelGrid at max(resolution, 0.1).  Key-frame clouds are
+ * uploaded once (lsd_localmap_add_keyframe: mTransfromPoints, map frame) and stay on the device; the assembled map
+ * is handed to the matcher without leaving it: lsd_localmap_get_dev -> lsd_reg_set_target_dev (updateLocalMap).
+ * lsd_localmap_update returns LSD_LOCALMAP_NONE where the reference sets mLocalMap = nullptr (no key frame in
+ * range, or the nearest one >= 20 m away).  The 10 m update hysteresis stays with the caller (:325-327).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_localmap lsd_localmap_t;
+lsd_status_t lsd_localmap_create(lsd_localmap_t** out, double resolution, double key_frame_distance);
+lsd_status_t lsd_localmap_destroy(lsd_localmap_t* h);
+lsd_status_t lsd_localmap_add_keyframe(lsd_localmap_t* h, const float* xyzi_map_host, int n, const double* position3);
+lsd_status_t lsd_localmap_update(lsd_localmap_t* h, const double* pose_xyz, int* n_points, int* n_keyframes_in_radius, double* nearest_dist);
+lsd_status_t lsd_localmap_get_dev(lsd_localmap_t* h, const float** xyzi_dev, int* n);
+lsd_status_t lsd_localmap_get(lsd_localmap_t* h, float* xyzi_host, int cap, int* n);
 
 /* Host-side manifold helpers (exported so bindings/tests use the same algebra as the filter).
  * IMU_Processing.hpp:224-230 initial covariance; state_ikfom boxplus/boxminus. */

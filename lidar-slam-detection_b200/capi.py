@@ -140,6 +140,12 @@ SIGNATURES = [
     ("lsd_imu_get_cloud", _i, [_vp, _vp, _i, _pi]),
     ("lsd_imu_get_poses", _i, [_vp, _vp, _i, _pi]),
     ("lsd_eskf_predict", _i, [_vp, _vp, _d, _vp, _vp, _vp]),
+    ("lsd_localmap_create", _i, [_pp, _d, _d]),
+    ("lsd_localmap_destroy", _i, [_vp]),
+    ("lsd_localmap_add_keyframe", _i, [_vp, _vp, _i, _vp]),
+    ("lsd_localmap_update", _i, [_vp, _vp, _pi, _pi, C.POINTER(_d)]),
+    ("lsd_localmap_get_dev", _i, [_vp, _pp, _pi]),
+    ("lsd_localmap_get", _i, [_vp, _vp, _i, _pi]),
     ("lsd_keyframe_filter", _i, [_vp, _i, _f, _i, _f, _f, _vp, _pi]),
     ("lsd_keyframe_filter_dev", _i, [_vp, _i, _f, _i, _f, _f, _vp, _pi]),
     ("lsd_lio_init_cov", None, [_vp]),
@@ -380,6 +386,10 @@ class Matcher:
         else:
             check(lib.lsd_reg_set_target_dev(self.h, _ptr(pts), pts.shape[0]))
 
+    def set_target_ptr(self, dev_ptr: int, n: int):
+        """setInputTarget from a raw device pointer (e.g. LocalMap.cloud_dev())."""
+        check(lib.lsd_reg_set_target_dev(self.h, C.c_void_p(dev_ptr), n))
+
     def set_source(self, pts):
         if isinstance(pts, np.ndarray):
             pts = _f32(pts)
@@ -444,6 +454,46 @@ def eskf_update_table(state, P, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=
 
 
 IMU_INITIALIZING = 4
+LOCALMAP_NONE = 5
+
+
+class LocalMap:
+    """Localization::runUpdateLocalMap's map assembly (localization.cpp:303-373) on device-resident key frames."""
+
+    def __init__(self, resolution: float = 0.5, key_frame_distance: float = 1.0):
+        self.h = C.c_void_p()
+        check(lib.lsd_localmap_create(C.byref(self.h), resolution, key_frame_distance))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.lsd_localmap_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def add_keyframe(self, pts_map_frame, position):
+        pts = _f32(pts_map_frame)
+        pos = np.ascontiguousarray(position, np.float64)
+        check(lib.lsd_localmap_add_keyframe(self.h, _ptr(pts), pts.shape[0], _ptr(pos)))
+
+    def update(self, pose_xyz):
+        """-> (status, n_points, n_keyframes_in_radius, nearest_dist)"""
+        p = np.ascontiguousarray(pose_xyz, np.float64)
+        n, k, d = C.c_int(), C.c_int(), C.c_double()
+        st = check(lib.lsd_localmap_update(self.h, _ptr(p), C.byref(n), C.byref(k), C.byref(d)))
+        return st, n.value, k.value, d.value
+
+    def cloud(self) -> np.ndarray:
+        n = C.c_int()
+        check(lib.lsd_localmap_get(self.h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), np.float32)
+        check(lib.lsd_localmap_get(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def cloud_dev(self):
+        p, n = C.c_void_p(), C.c_int()
+        check(lib.lsd_localmap_get_dev(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
 
 def keyframe_filter(pts, radius: float = 1.0, min_neighbors: int = 3, min_range: float = 0.0, max_range: float = 1e9):

@@ -7,3 +7,4 @@
 #include "vfe.cu"
 #include "imu.cu"
 #include "filters.cu"
+#include "localmap.cu"
