@@ -17,6 +17,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL banners must not land on stdout next to the JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
