@@ -202,6 +202,51 @@ def run_knn_batch(torch, hmap, m, dev, nq):
     return out
 
 
+def run_streams(torch, lsdreg, local, m, steps, dev_scans, W, K, S, prior_vec, P0):
+    """S host threads, each with its own LioFrontend (own map replica, own CUDA stream), all registering the same K
+    device-resident scans concurrently.  ctypes releases the GIL inside the C calls."""
+    import threading
+    handles = []
+    for _ in range(S):
+        h = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
+        h.map.insert(m, 0)
+        h.set_next_id(m.shape[0])
+        handles.append(h)
+    start = threading.Barrier(S + 1)
+    done = threading.Barrier(S + 1)
+    errs = [0.0] * S
+
+    def worker(k):
+        lsdreg.init(local)
+        h = handles[k]
+        for s in range(W):
+            h.scan(dev_scans[s], prior_vec(steps[s]), P0)
+        h.sync()
+        start.wait()
+        worst = 0.0
+        for s in range(W, W + K):
+            x, P, info = h.scan(dev_scans[s], prior_vec(steps[s]), P0)
+            worst = max(worst, float(np.abs(x[:3] - steps[s][2]).max()))
+        h.sync()
+        errs[k] = worst
+        done.wait()
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(S)]
+    for t in ths:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    for t in ths:
+        t.join()
+    for h in handles:
+        h.close()
+    return {"streams": S, "value": S * K / wall, "unit": "scans/s", "ms_per_scan_per_stream": 1e3 * wall / K,
+            "pos_err_max_m": max(errs), "note": "independent streams, one map replica and one handle each, same GPU"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,6 +256,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knn-batch", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="extra leg (N=1): this many independent scan streams, each with "
+                    "its own map replica and handle, registered concurrently on the one GPU (0/1 = skip)")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: upload each scan inside lsd_lio_scan instead of one scan ahead")
     ap.add_argument("--knn-batch", type=int, default=1 << 21, help="queries in the batched k-NN leg (N=1)")
     ap.add_argument("--mg-mode", default="replicas", choices=["replicas", "shard"],
@@ -343,6 +390,12 @@ def main():
     if world == 1 and not args.no_knn_batch:
         knn_batch = run_knn_batch(torch, lio.map, m, dev, args.knn_batch)
 
+    # ---------------- (5) several independent scan streams on ONE GPU (a fleet server): what the GPU sustains when a
+    # single stream's latency chain no longer leaves it idle.  Reported beside the headline, never instead of it.
+    multi_stream = None
+    if world == 1 and args.streams > 1:
+        multi_stream = run_streams(torch, lsdreg, local, m, steps_a, dev_scans, W, K, args.streams, prior_vec, P0)
+
     dev_ms = float(np.sum([i["gpu_ms"] for i in infos_a]))
     t = torch.tensor([wall_a, wall_b, dev_ms * 1e-3], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -423,6 +476,7 @@ def main():
                for k in ("random", "sorted")},
             **{k + "_frac": knn_batch["queries"] * bytes_per_query / (knn_batch[k + "_us"] * 1e-6) / 1e9 / peak
                for k in ("random", "sorted")}},
+        "multi_stream": multi_stream,
         "cpu_baseline": cpu, "clocks": clocks, "map_build_s": build_s,
         "pos_err_max_m": float(np.max([i["pos_err"] for i in infos_a])),
     }

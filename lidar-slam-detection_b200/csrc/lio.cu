@@ -799,6 +799,21 @@ static lsd_status_t read_n_down(lsd_lio* l) {
   return LSD_OK;
 }
 
+// A prefetch request recorded by lsd_lio_prefetch is turned into the actual copy here, right after this scan's
+// voxel-grid kernels were launched: the driver calls cost host time (~5 us) that is now hidden under GPU work
+// instead of delaying the scan's first launch.  Target: the staging slot this scan does not read.
+static lsd_status_t issue_deferred_prefetch(lsd_lio* l) {
+  if (!l->defer_pending) return LSD_OK;
+  l->defer_pending = false;
+  lsd_lio::Stage* sg = nullptr;
+  for (int i = 0; i < 2; i++) if (i != l->busy_slot && !l->stage[i].valid) sg = &l->stage[i];
+  if (!sg) return LSD_OK;  // both slots taken: the request is dropped, the later lsd_lio_scan uploads inline
+  LSD_CUDA(cudaMemcpyAsync(sg->buf, l->defer_host, (size_t)l->defer_n * 16, cudaMemcpyHostToDevice, l->copy_stream));
+  LSD_CUDA(cudaEventRecord(sg->ev, l->copy_stream));
+  sg->host = l->defer_host; sg->n = l->defer_n; sg->valid = true; sg->age = ++l->stage_clock;
+  return LSD_OK;
+}
+
 lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double* P, lsd_lio_info_t* info) {
   cudaStream_t st = l->stream;
   const long long launches0 = l->launches;
@@ -806,6 +821,8 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
   { lsd_status_t d = lio_drain(l); if (d) return d; }
   LSD_CUDA(cudaEventRecord(l->ev0, st));
   lsd_status_t s = lio_load(l, d_scan, n, 1);
+  if (s) return s;
+  s = issue_deferred_prefetch(l);
   if (s) return s;
   lsd_lio_info_t inf;
   memset(&inf, 0, sizeof(inf));
@@ -1140,8 +1157,14 @@ lsd_status_t lsd_lio_prefetch(lsd_lio_t* l, const float* scan_host, int n) {
   if (!l || !scan_host || n <= 0) return LSD_ERR_INVALID;
   if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
   LSD_CUDA(cudaSetDevice(l->device));
+  if (l->stage[0].valid || l->stage[1].valid) {
+    // a staged scan is waiting to be registered: that lsd_lio_scan call issues this copy once its first kernels
+    // are in flight (issue_deferred_prefetch), so the driver calls do not delay it
+    l->defer_host = scan_host; l->defer_n = n; l->defer_pending = true;
+    return LSD_OK;
+  }
   // Every staging buffer is idle here: the voxel grid of the last scan (their only reader) finished before
-  // lsd_lio_scan returned.  A slot holding a prefetched, not yet consumed scan is kept.
+  // lsd_lio_scan returned.
   lsd_lio::Stage* sg = free_stage(l);
   LSD_CUDA(cudaMemcpyAsync(sg->buf, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->copy_stream));
   LSD_CUDA(cudaEventRecord(sg->ev, l->copy_stream));
@@ -1163,6 +1186,7 @@ lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* s
   if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
   lsd_lio::Stage* sg = nullptr;
   for (int i = 0; i < 2; i++) if (l->stage[i].valid && l->stage[i].host == scan_host && l->stage[i].n == n) sg = &l->stage[i];
+  if (l->defer_pending && l->defer_host == scan_host && l->defer_n == n) l->defer_pending = false;  // requested, never issued: upload inline
   if (sg) {  // uploaded by lsd_lio_prefetch while the previous scan was being registered
     LSD_CUDA(cudaStreamWaitEvent(l->stream, sg->ev, 0));
   } else {
@@ -1170,7 +1194,10 @@ lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* s
     LSD_CUDA(cudaMemcpyAsync(sg->buf, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
   }
   sg->valid = false;
-  return lio_scan(l, sg->buf, n, state26_inout, P529_inout, info);
+  l->busy_slot = (int)(sg - l->stage);
+  const lsd_status_t rc = lio_scan(l, sg->buf, n, state26_inout, P529_inout, info);
+  l->busy_slot = -1;
+  return rc;
 }
 
 void lsd_lio_init_cov(double* P529) { if (P529) eskf::init_cov(P529); }

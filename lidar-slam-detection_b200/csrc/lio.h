@@ -31,6 +31,10 @@ struct lsd_lio {
   Stage stage[2];
   long long stage_clock = 0;
   cudaStream_t copy_stream = nullptr;
+  int busy_slot = -1;                 // slot the scan being registered reads (-1: a device-pointer scan)
+  const float* defer_host = nullptr;  // prefetch request whose copy is issued from inside the next lsd_lio_scan,
+  int defer_n = 0;                    // after that scan's first kernels are in flight
+  bool defer_pending = false;
   float4* d_body = nullptr;     // feats_down_body
   int* d_n = nullptr;           // feats_down_size, device resident
   float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)

@@ -36,8 +36,8 @@ def test_local_map_matches_oracle_and_feeds_the_matcher():
         assert st == lsdreg.OK and k == nk and want is not None
         got = g.cloud()
         assert got.shape == want.shape and n == len(want) and n > 1000
-        np.testing.assert_allclose(got[:, :3], want[:, :3], rtol=0, atol=2e-5)
-        np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=0, atol=2e-3)
+        np.testing.assert_allclose(got[:, :3], want[:, :3], rtol=4e-6, atol=2e-5)   # PCL sums float32 in order (dozens of points per voxel at |x| ~ 100 m); the device sums exactly
+        np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=1e-5, atol=4e-3)
     # nearest key frame 20-30 m away: found by the radius search but rejected; > 30 m: out of map
     for off, in_radius in ((25.0, True), (45.0, False)):
         pose = frames[0][1] + [-off, 0.0, 0.0]
@@ -75,4 +75,4 @@ def test_local_map_caps_at_200k_points():
     want, nk = o.update([0.0, 0.0, 0.0])
     st, n, k, dist = g.update([0.0, 0.0, 0.0])
     assert st == lsdreg.OK and k == nk == 12 and n == len(want)           # 7 key frames reach 210 000 >= 200 000 points
-    np.testing.assert_allclose(g.cloud()[:, :3], want[:, :3], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(g.cloud()[:, :3], want[:, :3], rtol=4e-6, atol=2e-5)
