@@ -17,6 +17,10 @@ struct PointCloud {
   const PointT& at(size_t i) const { return points.at(i); }
   PointT& at(size_t i) { return points.at(i); }
   void push_back(const PointT& p) { points.push_back(p); }
+  auto begin() const { return points.begin(); }
+  auto end() const { return points.end(); }
+  auto begin() { return points.begin(); }
+  auto end() { return points.end(); }
 };
 template <typename PointT>
 void transformPointCloud(const PointCloud<PointT>& in, PointCloud<PointT>& out, const Eigen::Matrix4f& T) {
