@@ -8,8 +8,8 @@
 // The reference's result depends on thread arrival order twice: voxel ids come from an atomicAdd
 // counter, and a voxel with more than max_points_per_voxel points keeps whichever 5 arrive first.
 // Here both follow the SEQUENTIAL order of the same code (ascending point index): voxel ids by first
-// point, the 5 lowest-index points per voxel, summed in index order — one of the outcomes the
-// reference can produce, and the same one every run.  No 30 MB memset of the voxel scratch
+// point, the 5 lowest-index points per voxel (kept by a chain of atomicMin registers in the claim pass), summed in
+// index order — one of the outcomes the reference can produce, and the same one every run.  No 30 MB memset of the voxel scratch
 // (:229-232) and no host synchronisation between the passes (:248).
 #include <cuda_fp16.h>
 
@@ -29,16 +29,17 @@ __device__ __forceinline__ unsigned vfe_hash(unsigned k) {  // murmur3 fmix32, v
 }
 
 // transform_kernel (preprocess_kernel.cu:6-20): older frames re-projected by the 3x4 motion, time + 0.1.
-// The reference is compiled with nvcc's default FMA contraction; spelt out so this build (-fmad=false)
-// produces the same bits.
+// The reference is compiled with nvcc's default FMA contraction; its SASS for m0*x + m1*y + m2*z + m3 is
+// FMUL m1*y; FFMA m0*x + .; FFMA m2*z + .; FADD m3 — spelt out so this build (-fmad=false) produces the same bits
+// (pinned against the recompiled reference kernel, tests/test_gpu_ref_cuda.py).
 __global__ void __launch_bounds__(256) vfe_transform_kernel(int n, const float* __restrict__ src, float* __restrict__ dst, int nf,
                                                             const float* __restrict__ m) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float px = src[nf * i], py = src[nf * i + 1], pz = src[nf * i + 2];
-  dst[nf * i + 0] = __fadd_rn(__fmaf_rn(m[2], pz, __fmaf_rn(m[1], py, __fmul_rn(m[0], px))), m[3]);
-  dst[nf * i + 1] = __fadd_rn(__fmaf_rn(m[6], pz, __fmaf_rn(m[5], py, __fmul_rn(m[4], px))), m[7]);
-  dst[nf * i + 2] = __fadd_rn(__fmaf_rn(m[10], pz, __fmaf_rn(m[9], py, __fmul_rn(m[8], px))), m[11]);
+  dst[nf * i + 0] = __fadd_rn(__fmaf_rn(m[2], pz, __fmaf_rn(m[0], px, __fmul_rn(m[1], py))), m[3]);
+  dst[nf * i + 1] = __fadd_rn(__fmaf_rn(m[6], pz, __fmaf_rn(m[4], px, __fmul_rn(m[5], py))), m[7]);
+  dst[nf * i + 2] = __fadd_rn(__fmaf_rn(m[10], pz, __fmaf_rn(m[8], px, __fmul_rn(m[9], py))), m[11]);
   dst[nf * i + 3] = src[nf * i + 3];
   dst[nf * i + 4] = (float)((double)src[nf * i + 4] + 0.1);
 }
@@ -51,7 +52,10 @@ __device__ __forceinline__ unsigned vfe_voxel_offset(const VfeGrid& g, float px,
   return (unsigned)((z * g.gs[1] + y) * g.gs[0] + x);
 }
 
-// pass 1: claim the voxel's slot, count, lowest point index
+// pass 1: claim the voxel's slot, count it, and insert the point index into the voxel's sorted list of the max_ppv
+// LOWEST indices.  sel[r] is an atomicMin register; a thread offers its index to sel[0], carries the larger of
+// (what was there, what it offered) on to sel[1], and so on.  Whatever the interleaving, the values offered to
+// register r are all indices except the r smallest, so it ends holding the (r+1)-th smallest: deterministic, one pass.
 __global__ void __launch_bounds__(256) vfe_claim_kernel(int n, const float* __restrict__ pts, VfeGrid g, VfeSlot* __restrict__ tab,
                                                         unsigned mask, int* __restrict__ pslot) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,18 +70,19 @@ __global__ void __launch_bounds__(256) vfe_claim_kernel(int n, const float* __re
       if (pre == kVfeEmpty || pre == key) { slot = (int)s; break; }
       s = (s + 1) & mask;
     }
-    if (slot >= 0) { atomicAdd(&tab[slot].count, 1u); atomicMin(&tab[slot].sel[0], (unsigned)i); }
+    if (slot >= 0) {
+      atomicAdd(&tab[slot].count, 1u);
+      unsigned x = (unsigned)i;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        if (r >= g.max_ppv) break;
+        const unsigned old = atomicMin(&tab[slot].sel[r], x);
+        x = max(old, x);
+        if (x == kVfeEmpty) break;  // carrying the "empty" sentinel: nothing left to place
+      }
+    }
   }
   pslot[i] = slot;
-}
-
-// passes 2..5: r-th smallest point index of every voxel
-__global__ void __launch_bounds__(256) vfe_select_kernel(int n, int r, VfeSlot* __restrict__ tab, const int* __restrict__ pslot) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int s = pslot[i];
-  if (s < 0) return;
-  if (tab[s].count > (unsigned)r && (unsigned)i > tab[s].sel[r - 1]) atomicMin(&tab[s].sel[r], (unsigned)i);
 }
 
 // voxel ids in order of first point: exclusive scan of "point i opens its voxel" over the points
@@ -295,13 +300,12 @@ lsd_status_t lsd_vfe_voxelize(lsd_vfe_t* v, int order_zyx, int* num_voxels) {
     const float* pts = v->pts[v->cur];
     const int nb = (n + 255) / 256;
     vfe_claim_kernel<<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->mask, v->pslot);
-    for (int r = 1; r < v->p.max_points_per_voxel; r++) vfe_select_kernel<<<nb, 256, 0, st>>>(n, r, v->tab, v->pslot);
     vfe_scan_kernel<<<(n + 1023) / 1024, 1024, 0, st>>>(n, v->tab, v->pslot, v->local, v->block_sum, v->d_done, v->d_total);
     if (order_zyx) vfe_emit_kernel<true><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
     else vfe_emit_kernel<false><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
     vfe_reset_kernel<<<nb, 256, 0, st>>>(n, v->tab, v->pslot);
     LSD_CUDA(cudaGetLastError());
-    v->launches += 4 + (v->p.max_points_per_voxel - 1);
+    v->launches += 4;
     int h = 0;
     LSD_CUDA(cudaMemcpyAsync(&h, v->d_total, 4, cudaMemcpyDeviceToHost, st));
     LSD_CUDA(cudaStreamSynchronize(st));

@@ -127,6 +127,31 @@ def _load_ref_reg():
     return L
 
 
+def _load_ref_cuda():
+    """The compiled reference CUDA NDT (oracle/ref_cuda.cu -> oracle/_ref/libref_cuda.so).  Loading it needs the
+    CUDA driver, so it is resolved lazily by the GPU tests / bench_extra (never at import time on a CPU box)."""
+    path = os.path.join(_HERE, "_ref", "libref_cuda.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.refndt_create.restype = C.c_void_p
+    L.refndt_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.refndt_destroy.argtypes = [C.c_void_p]
+    L.refndt_set_source.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
+    L.refndt_set_target.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
+    L.refndt_num_voxels.restype = C.c_int
+    L.refndt_num_voxels.argtypes = [C.c_void_p]
+    L.refndt_num_correspondences.restype = C.c_int
+    L.refndt_num_correspondences.argtypes = [C.c_void_p]
+    L.refndt_linearize.restype = C.c_double
+    L.refndt_linearize.argtypes = [C.c_void_p, _d, C.c_void_p, C.c_void_p]
+    L.refndt_compute_error.restype = C.c_double
+    L.refndt_compute_error.argtypes = [C.c_void_p, _d]
+    L.refndt_align.restype = C.c_int
+    L.refndt_align.argtypes = [C.c_void_p, _f, _f]
+    return L
+
+
 port = _load_port()
 ref = _load_ref()
 HAVE_REF = ref is not None

@@ -7,8 +7,9 @@
 Pin status: the GICP / VGICP cost functions, the covariances, se3_exp and the whole LM loop are checked
 against the COMPILED reference classes (oracle/ref_reg.cpp -> oracle/_ref/libref_reg.so: the reference's
 own LsqRegistration / FastGICP / FastVGICP headers, with our PCL/Boost shims) in tests/test_oracle_reg.py.
-NDT (P2D) stays PARITY UNPINNED: the reference NDT exists only as CUDA code for older architectures;
-it shares the pinned LM loop and se3_exp.
+NDT (P2D): the reference NDT exists only as CUDA code; its own sources recompile for sm_100a
+(oracle/ref_cuda.cu -> oracle/_ref/libref_cuda.so, RefNdtCuda below) and pin the NDT restatement and the product's
+NDT kernels on the GPU box (tests/test_gpu_ref_cuda.py).
 """
 from __future__ import annotations
 
@@ -259,3 +260,45 @@ def ref_se3_exp(a):
     T = np.zeros(16)
     O.ref_reg.ref_se3_exp(np.ascontiguousarray(a, np.float64), T)
     return T.reshape(4, 4)
+
+
+class RefNdtCuda:
+    """The COMPILED reference CUDA NDT (fast_gicp::NDTCuda over NDTCudaCore), sm_100a build; needs a GPU."""
+    _lib = None
+
+    def __init__(self, resolution=1.0, neighbors=7, max_iterations=64, trans_eps=0.01, rot_eps=0.1):
+        if RefNdtCuda._lib is None:
+            RefNdtCuda._lib = O._load_ref_cuda()
+        if RefNdtCuda._lib is None:
+            raise RuntimeError("oracle/_ref/libref_cuda.so missing (built only where /root/reference exists)")
+        self.L = RefNdtCuda._lib
+        self.h = self.L.refndt_create(resolution, neighbors, max_iterations, trans_eps, rot_eps)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refndt_destroy(self.h)
+            self.h = None
+
+    def set_target(self, pts):
+        self.tgt = np.ascontiguousarray(pts, np.float32)
+        self.L.refndt_set_target(self.h, self.tgt, self.tgt.shape[0], self.tgt.shape[1])
+        self.n_voxels = self.L.refndt_num_voxels(self.h)
+
+    def set_source(self, pts):
+        self.src = np.ascontiguousarray(pts, np.float32)
+        self.L.refndt_set_source(self.h, self.src, self.src.shape[0], self.src.shape[1])
+
+    def linearize(self, T, deriv=True):
+        T = np.ascontiguousarray(T, np.float64)
+        H, b = np.zeros(36), np.zeros(6)
+        e = self.L.refndt_linearize(self.h, T, H.ctypes.data if deriv else None, b.ctypes.data if deriv else None)
+        self.n_corr = self.L.refndt_num_correspondences(self.h)
+        return e, H.reshape(6, 6), b
+
+    def compute_error(self, T):
+        return self.L.refndt_compute_error(self.h, np.ascontiguousarray(T, np.float64))
+
+    def align(self, guess):
+        out = np.zeros(16, np.float32)
+        self.converged = bool(self.L.refndt_align(self.h, np.ascontiguousarray(guess, np.float32).reshape(16), out))
+        return out.reshape(4, 4).astype(np.float64)

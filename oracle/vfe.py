@@ -36,9 +36,10 @@ class OracleVoxelizer:
             out = old.copy()
             if self.total > 0:
                 x, y, z = old[:, 0].astype(np.float64), old[:, 1].astype(np.float64), old[:, 2].astype(np.float64)
-                for r in range(3):  # fma chain: ((m0*x) then fma(m1,y,.) then fma(m2,z,.)) + m3, each rounded to fp32
-                    t = (np.float64(m[4 * r]) * x).astype(np.float32)
-                    t = (np.float64(m[4 * r + 1]) * y + t.astype(np.float64)).astype(np.float32)
+                for r in range(3):  # as nvcc contracts the reference's m0*x + m1*y + m2*z + m3 (SASS of transform_kernel:
+                    # FMUL m1*y; FFMA m0*x + .; FFMA m2*z + .; FADD m3), each step rounded to fp32
+                    t = (np.float64(m[4 * r + 1]) * y).astype(np.float32)
+                    t = (np.float64(m[4 * r]) * x + t.astype(np.float64)).astype(np.float32)
                     t = (np.float64(m[4 * r + 2]) * z + t.astype(np.float64)).astype(np.float32)
                     out[:, r] = t + m[4 * r + 3]
                 out[:, 4] = (old[:, 4].astype(np.float64) + 0.1).astype(np.float32)
@@ -86,3 +87,59 @@ class OracleVoxelizer:
         c = ijk[firstpt]
         idx[:, 1:] = c[:, ::-1] if zyx else c
         return feat.astype(np.float16), idx, npts
+
+
+class RefVoxelizer:
+    """The COMPILED reference voxelizer (Preprocess + Voxelization kernels recompiled for sm_100a:
+    oracle/ref_vfe.cu -> oracle/_ref/libref_vfe.so).  Needs a GPU; loaded lazily."""
+    _lib = None
+
+    def __init__(self, min_range=(-64.0, -64.0, -2.0), max_range=(64.0, 64.0, 4.0), voxel_size=(0.1, 0.1, 0.15), max_points_per_voxel=5,
+                 max_voxels=300000, max_points=500000, num_feature=5, max_frame_num=2):
+        import ctypes as C
+        import os
+        if RefVoxelizer._lib is None:
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_vfe.so")
+            if not os.path.exists(path):
+                raise RuntimeError("oracle/_ref/libref_vfe.so missing (built only where /root/reference exists)")
+            L = C.CDLL(path)
+            f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+            L.refvfe_create.restype = C.c_void_p
+            L.refvfe_create.argtypes = [f32, f32, f32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+            L.refvfe_destroy.argtypes = [C.c_void_p]
+            L.refvfe_accumulate.restype = C.c_int
+            L.refvfe_accumulate.argtypes = [C.c_void_p, f32, C.c_int, f32, C.c_int]
+            L.refvfe_get_points.restype = C.c_int
+            L.refvfe_get_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            L.refvfe_voxelize.restype = C.c_int
+            L.refvfe_voxelize.argtypes = [C.c_void_p, C.c_int]
+            L.refvfe_get_output.restype = C.c_int
+            L.refvfe_get_output.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            RefVoxelizer._lib = L
+        self.L = RefVoxelizer._lib
+        self.nf = num_feature
+        self.h = self.L.refvfe_create(np.asarray(min_range, np.float32), np.asarray(max_range, np.float32), np.asarray(voxel_size, np.float32),
+                                      max_points_per_voxel, max_voxels, max_points, num_feature, max_frame_num)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refvfe_destroy(self.h)
+            self.h = None
+
+    def accumulate(self, points, motion=None, realtime=True):
+        pts = np.ascontiguousarray(points, np.float32)
+        m = np.ascontiguousarray(np.eye(4) if motion is None else motion, np.float32)
+        return self.L.refvfe_accumulate(self.h, pts, pts.shape[0], m.reshape(-1), int(realtime))
+
+    def points(self):
+        n = self.L.refvfe_get_points(self.h, None, 0)
+        out = np.empty((n, self.nf), np.float32)
+        self.L.refvfe_get_points(self.h, out.ctypes.data, n)
+        return out
+
+    def voxelize(self, zyx=True):
+        v = self.L.refvfe_voxelize(self.h, int(zyx))
+        feat = np.empty((v, self.nf), np.float16)
+        idx = np.empty((v, 4), np.uint32)
+        self.L.refvfe_get_output(self.h, feat.ctypes.data, idx.ctypes.data)
+        return feat, idx

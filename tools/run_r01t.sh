@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_ref_cuda.py -q > gpurun_out/pytest_r01t.log 2>&1; tail -30 gpurun_out/pytest_r01t.log
+timeout 600 python tools/ref_cuda_probe.py 3 > gpurun_out/ref_cuda_probe_t.log 2>&1; tail -2 gpurun_out/ref_cuda_probe_t.log
