@@ -58,6 +58,21 @@ def ndt(args):
                pos_err_m=float(np.abs(Tg[:3, 3] - tgt).max()), map_gen_s=gen_s,
                alg_bytes_per_eval=float(scan.shape[0] * (16 + 7 * 16 + 3 * 52)),
                cost_gbs=float(scan.shape[0] * (16 + 7 * 16 + 3 * 52) / (cost_ms * 1e-3) / 1e9))
+    if not args.no_ref_cuda and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_cuda.so")):
+        # the reference's own CUDA NDT (NDTCudaCore + kernels, recompiled for sm_100a) on the same clouds, same GPU
+        try:
+            from oracle.reg import RefNdtCuda
+            r = RefNdtCuda(0.5, 7)
+            rb, _ = t_ms(lambda: r.set_target(m)); rs, _ = t_ms(lambda: r.set_source(scan))
+            r.align(guess)
+            ra, Tr = t_ms(lambda: r.align(guess), 3)
+            r.linearize(Tg)
+            rl, _ = t_ms(lambda: r.linearize(Tg), 10)
+            out["reference_cuda_sm100a"] = dict(target_build_ms=rb, set_source_ms=rs, align_ms=ra, cost_eval_us=rl * 1e3, voxels=int(r.n_voxels),
+                                                converged=bool(r.converged), pos_err_m=float(np.abs(Tr[:3, 3] - tgt).max()))
+            del r
+        except Exception as e:  # the comparator must never take the measurement down
+            out["reference_cuda_sm100a"] = dict(error=repr(e)[:200])
     if not args.no_cpu:
         near = (np.abs(m[:, 0] - tgt[0]) < 130) & (np.abs(m[:, 1] - tgt[1]) < 130)
         sub = np.ascontiguousarray(m[near])             # bounded CPU sample: the map within 130 m of the scan, full density
@@ -174,6 +189,7 @@ if __name__ == "__main__":
     ap.add_argument("--gicp-pairs", type=int, default=4)
     ap.add_argument("--gicp-method", default="FAST_GICP", choices=["FAST_GICP", "FAST_VGICP"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the leg that times the reference's own CUDA NDT (oracle/_ref/libref_cuda.so)")
     a = ap.parse_args()
     import lsdreg
     lsdreg.init(int(os.environ.get("LOCAL_RANK", 0)))
