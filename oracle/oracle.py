@@ -89,6 +89,8 @@ def _load_ref():
     L.ref_ikd_build.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
     L.ref_ikd_knn.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _i, _f, _i, C.c_int]
     L.ref_esti_plane.argtypes = [_f, C.c_int, C.c_float, _f, _i]
+    if hasattr(L, "ref_so3_exp"):
+        L.ref_so3_exp.argtypes = [_d, C.c_double, _d]
     if hasattr(L, "ref_lio_hmodel"):
         L.ref_lio_hmodel.restype = C.c_int
         L.ref_lio_hmodel.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, C.c_int, C.c_int, _f, _i, _i, _u8,

@@ -271,4 +271,13 @@ int ref_map_incremental(void* hv, const float* body, int n, const double* R_, co
   return int(PointToAdd.size() + PointNoNeedDownsample.size());
 }
 
+
+// so3_math.h:36-58  Exp(ang_vel, dt) — the rotation used by the per-point undistortion (IMU_Processing.hpp:384).
+// common_lib.h already pulled the reference header in; out9 is row-major.
+void ref_so3_exp(const double* ang_vel3, double dt, double* out9) {
+  const Eigen::Vector3d w(ang_vel3[0], ang_vel3[1], ang_vel3[2]);
+  const Eigen::Matrix3d R = Exp(w, dt);
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) out9[3 * a + b] = R(a, b);
+}
+
 }  // extern "C"
