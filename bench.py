@@ -25,7 +25,25 @@ import time
 
 import numpy as np
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL banners must not land on stdout next to the JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+class _QuietStdout:
+    """Route fd 1 to stderr while libraries may chat (NCCL prints its version banner with printf at the first
+    communicator), and give it back for the one JSON line: stdout must carry nothing else."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -487,4 +505,12 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    import contextlib
+    import io
+    buf = io.StringIO()
+    with _QuietStdout():
+        with contextlib.redirect_stdout(buf):      # main() prints the JSON line: hold it until fd 1 is ours again
+            rc = main()
+    sys.stdout.write(buf.getvalue())
+    sys.stdout.flush()
+    sys.exit(rc)

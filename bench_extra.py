@@ -17,7 +17,25 @@ import time
 
 import numpy as np
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL banners must not land on stdout next to the JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+class _QuietStdout:
+    """Route fd 1 to stderr while libraries may chat (NCCL prints its version banner with printf at the first
+    communicator), and give it back for the one JSON line: stdout must carry nothing else."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -191,7 +209,14 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the leg that times the reference's own CUDA NDT (oracle/_ref/libref_cuda.so)")
     a = ap.parse_args()
+    import contextlib
+    import io
     import lsdreg
-    lsdreg.init(int(os.environ.get("LOCAL_RANK", 0)))
-    for w in a.which.split(","):
-        {"ndt": ndt, "gicp": gicp, "vfe": vfe}[w](a)
+    buf = io.StringIO()
+    with _QuietStdout():
+        with contextlib.redirect_stdout(buf):
+            lsdreg.init(int(os.environ.get("LOCAL_RANK", 0)))
+            for w in a.which.split(","):
+                {"ndt": ndt, "gicp": gicp, "vfe": vfe}[w](a)
+    sys.stdout.write(buf.getvalue())
+    sys.stdout.flush()

@@ -73,6 +73,11 @@ lsd_status_t lsd_map_insert(lsd_map_t* m, const float* xyzi_host, int n, int32_t
 lsd_status_t lsd_map_insert_dev(lsd_map_t* m, const float* xyzi_dev, int n, int32_t id0);
 /* IVox::NumValidGrids / NumPoints; n_dropped counts points refused for capacity/range. */
 lsd_status_t lsd_map_stats(lsd_map_t* m, uint64_t* n_cells, uint64_t* n_points, uint64_t* n_dropped);
+/* KD_TREE::Delete_Point_Boxes (slam/mapping/fastlio/include/ikd-Tree/ikd_Tree.cpp:536-556, Delete_by_range :648-672;
+ * how the ikd-Tree path moves its local-map cube, laserMapping.cpp:242-288): deletes every stored point with
+ * min <= p < max on all three axes for any of the n_boxes boxes ([n,6] = min xyz, max xyz).  *n_deleted as the
+ * reference's return value.  Deleted points can never be returned by a query again; their slots are not reused. */
+lsd_status_t lsd_map_delete_boxes(lsd_map_t* m, const float* boxes6_host, int n_boxes, uint64_t* n_deleted);
 /* The cudaStream_t every *_dev call of this map is enqueued on (no reference counterpart): lets a
  * caller order its own work after the library's, or time it with CUDA events on the right stream. */
 lsd_status_t lsd_map_stream(lsd_map_t* m, void** cuda_stream_out);

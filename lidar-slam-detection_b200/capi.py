@@ -78,6 +78,7 @@ SIGNATURES = [
     ("lsd_map_insert", _i, [_vp, _vp, _i, C.c_int32]),
     ("lsd_map_insert_dev", _i, [_vp, _vp, _i, C.c_int32]),
     ("lsd_map_stats", _i, [_vp, _pu64, _pu64, _pu64]),
+    ("lsd_map_delete_boxes", _i, [_vp, _vp, _i, _pu64]),
     ("lsd_map_stream", _i, [_vp, C.POINTER(C.c_void_p)]),
     ("lsd_knn_query", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_knn_query_dev", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
@@ -227,6 +228,13 @@ class HashVoxelMap:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(lib.lsd_map_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(cells=a.value, points=b.value, dropped=c.value)
+
+    def delete_boxes(self, boxes) -> int:
+        """KD_TREE::Delete_Point_Boxes: boxes [n,6] = (min xyz, max xyz); returns the number of points deleted."""
+        b = np.ascontiguousarray(np.asarray(boxes, np.float32).reshape(-1, 6))
+        n = C.c_uint64()
+        check(lib.lsd_map_delete_boxes(self.h, _ptr(b), b.shape[0], C.byref(n)))
+        return int(n.value)
 
     def stream(self) -> int:
         """cudaStream_t (as an integer) the map's device calls run on."""

@@ -249,6 +249,43 @@ __global__ void __launch_bounds__(256) knn_query_thread_kernel(MapView mv, const
   out_cnt[i] = nf;
 }
 
+// ------------------------------------------------------------------ box delete
+// KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:536-556; Delete_by_range :648-672): a point is deleted iff
+// min <= p < max on every axis, for any box.  Deleted points keep their slot and get NaN coordinates: every
+// distance to them is NaN, every `d2 < max_sq` test false, so no query can return them and no table entry moves.
+constexpr int kMaxDeleteBoxes = 16;
+struct DeleteBoxes { int n; float b[kMaxDeleteBoxes][6]; };
+
+__global__ void __launch_bounds__(256) map_delete_boxes_kernel(MapView mv, unsigned long long n_lines, DeleteBoxes bx,
+                                                               unsigned long long* __restrict__ n_deleted) {
+  const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_lines) return;
+  CellLine* ln = mv.lines + s;
+  const unsigned long long key = ln->key;
+  if (key == 0ull) return;
+  const int level = (int)(key >> 57);
+  unsigned total = ln->count;
+  if (level > 0) {  // points 7L.. of a crowded voxel: the voxel's total count lives in its level-0 line
+    uint4 h;
+    const CellLine* base = tag_find(mv, key & ((1ull << 57) - 1ull), &h);
+    if (!base) return;
+    total = h.z;
+  }
+  const int n = (int)min(total > (unsigned)(level * kPtsPerLine) ? total - (unsigned)(level * kPtsPerLine) : 0u, (unsigned)kPtsPerLine);
+  unsigned del = 0;
+  for (int j = 0; j < n; j++) {
+    const float4 p = ln->pts[j];
+    bool inside = false;
+    for (int b = 0; b < bx.n && !inside; b++)
+      inside = bx.b[b][0] <= p.x && bx.b[b][3] > p.x && bx.b[b][1] <= p.y && bx.b[b][4] > p.y && bx.b[b][2] <= p.z && bx.b[b][5] > p.z;
+    if (inside) {  // NaN coordinates compare false with everything, including the box test of a later delete
+      ln->pts[j] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), p.w);
+      del++;
+    }
+  }
+  if (del) { atomicAdd(n_deleted, (unsigned long long)del); atomicAdd(&mv.counters[1], (unsigned long long)(0ull - del)); }
+}
+
 lsd_status_t launch_insert(lsd_map* m, const float4* d_pts, int n, int id0, cudaStream_t st) {
   if (n <= 0) return LSD_OK;
   map_insert_kernel<<<(n + 255) / 256, 256, 0, st>>>(m->view, d_pts, n, id0);
@@ -401,6 +438,29 @@ lsd_status_t lsd_map_stats(lsd_map_t* m, uint64_t* n_cells, uint64_t* n_points, 
   if (n_cells) *n_cells = h[0];
   if (n_points) *n_points = h[1];
   if (n_dropped) *n_dropped = h[2];
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_delete_boxes(lsd_map_t* m, const float* boxes6_host, int n_boxes, uint64_t* n_deleted) {
+  if (!m || n_boxes < 0 || (n_boxes > 0 && !boxes6_host)) return LSD_ERR_INVALID;
+  if (n_deleted) *n_deleted = 0;
+  if (n_boxes == 0) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(m->device));
+  unsigned long long total = 0;
+  for (int o = 0; o < n_boxes; o += kMaxDeleteBoxes) {
+    DeleteBoxes bx;
+    bx.n = std::min(kMaxDeleteBoxes, n_boxes - o);
+    memcpy(bx.b, boxes6_host + 6 * (size_t)o, (size_t)bx.n * 6 * sizeof(float));
+    LSD_CUDA(cudaMemsetAsync(&m->view.counters[3], 0, sizeof(unsigned long long), m->stream));
+    map_delete_boxes_kernel<<<(unsigned)((m->n_lines + 255) / 256), 256, 0, m->stream>>>(m->view, m->n_lines, bx, &m->view.counters[3]);
+    LSD_CUDA(cudaGetLastError());
+    m->launches++;
+    unsigned long long h = 0;
+    LSD_CUDA(cudaMemcpyAsync(&h, &m->view.counters[3], sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+    LSD_CUDA(cudaStreamSynchronize(m->stream));
+    total += h;
+  }
+  if (n_deleted) *n_deleted = total;
   return LSD_OK;
 }
 

@@ -200,6 +200,29 @@ void orc_ivox_add(OrcIvox* m, const float* xyz, int stride, int n, int id0, cons
 
 typedef struct { float d2; int id; float x, y, z; } OrcCand;
 /* canonical order used everywhere in this repo: ascending (d2, id) */
+/* KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:536-556, Delete_by_range :648-672): a point is deleted iff
+ * min <= p < max on every axis, for any of the boxes.  boxes: [n_boxes, 6] = (min xyz, max xyz).  Returns #deleted. */
+size_t orc_ivox_delete_boxes(OrcIvox* m, const float* boxes, int n_boxes) {
+  size_t del = 0;
+  for (size_t s = 0; s < m->tab_size; s++) {
+    OrcCell* c = &m->tab[s];
+    if (!c->used) continue;
+    int w = 0;
+    for (int j = 0; j < c->n; j++) {
+      const OrcPt* p = &c->pts[j];
+      int inside = 0;
+      for (int b = 0; b < n_boxes && !inside; b++) {
+        const float* B = boxes + 6 * b;
+        inside = B[0] <= p->x && B[3] > p->x && B[1] <= p->y && B[4] > p->y && B[2] <= p->z && B[5] > p->z;
+      }
+      if (inside) del++; else c->pts[w++] = *p;
+    }
+    c->n = w;
+  }
+  m->n_points -= del;
+  return del;
+}
+
 static inline int cand_less(const OrcCand* a, const OrcCand* b) {
   return a->d2 < b->d2 || (a->d2 == b->d2 && a->id < b->id);
 }

@@ -40,6 +40,8 @@ def _load_port():
     L.orc_ivox_num_points.restype = C.c_size_t
     L.orc_ivox_num_points.argtypes = [C.c_void_p]
     L.orc_ivox_add.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.orc_ivox_delete_boxes.restype = C.c_size_t
+    L.orc_ivox_delete_boxes.argtypes = [C.c_void_p, _f, C.c_int]
     L.orc_knn.argtypes = [C.c_void_p, C.c_int, _f, C.c_int, C.c_int, C.c_int, C.c_double, _i, _f, _f, _i, C.c_int]
     L.orc_esti_plane_batch.argtypes = [_f, C.c_int, C.c_float, _f, _i]
     L.orc_lio_hmodel.restype = C.c_int
@@ -88,6 +90,9 @@ def _load_ref():
     L.ref_ikd_destroy.argtypes = [C.c_void_p]
     L.ref_ikd_build.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
     L.ref_ikd_knn.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _i, _f, _i, C.c_int]
+    if hasattr(L, "ref_ikd_delete_boxes"):
+        L.ref_ikd_delete_boxes.restype = C.c_int
+        L.ref_ikd_delete_boxes.argtypes = [C.c_void_p, _f, C.c_int]
     L.ref_esti_plane.argtypes = [_f, C.c_int, C.c_float, _f, _i]
     if hasattr(L, "ref_so3_exp"):
         L.ref_so3_exp.argtypes = [_d, C.c_double, _d]
@@ -202,6 +207,11 @@ class OracleIvox:
     def num_cells(self):
         return port.orc_ivox_num_cells(self.h)
 
+    def delete_boxes(self, boxes: np.ndarray) -> int:
+        """KD_TREE::Delete_Point_Boxes semantics on the hash map: min <= p < max per axis."""
+        b = _c32(np.asarray(boxes).reshape(-1, 6))
+        return int(port.orc_ivox_delete_boxes(self.h, b, b.shape[0]))
+
     @property
     def num_points(self):
         return port.orc_ivox_num_points(self.h)
@@ -274,6 +284,10 @@ class RefIkd:
     def build(self, xyz: np.ndarray, id0: int = 0):
         xyz = _c32(xyz[:, :3])
         ref.ref_ikd_build(self.h, xyz, xyz.shape[0], id0)
+
+    def delete_boxes(self, boxes: np.ndarray) -> int:
+        b = _c32(np.asarray(boxes).reshape(-1, 6))
+        return ref.ref_ikd_delete_boxes(self.h, b, b.shape[0])
 
     def knn(self, q: np.ndarray, k: int = 5, nthreads: int = 8):
         q = _c32(q[:, :3])

@@ -86,6 +86,12 @@ void ref_ikd_build(void* h, const float* xyz, int n, int id0) {
   for (int i = 0; i < n; i++) pv.push_back(mk(xyz + 3 * i, id0 + i));
   static_cast<KD_TREE<PointType>*>(h)->Build(pv);
 }
+// Delete_Point_Boxes (ikd_Tree.cpp:536-556): boxes [n,6] = (min xyz, max xyz); returns the tree's own count
+int ref_ikd_delete_boxes(void* h, const float* boxes, int n) {
+  std::vector<BoxPointType> bv(n);
+  for (int i = 0; i < n; i++) for (int a = 0; a < 3; a++) { bv[i].vertex_min[a] = boxes[6 * i + a]; bv[i].vertex_max[a] = boxes[6 * i + 3 + a]; }
+  return static_cast<KD_TREE<PointType>*>(h)->Delete_Point_Boxes(bv);
+}
 // Nearest_Search as laserMapping.cpp:846; out_d2 [nq,k] are the tree's own float distances.
 void ref_ikd_knn(void* h, const float* q, int nq, int k, int* out_ids, float* out_d2, int* out_cnt,
                  int nthreads) {

@@ -142,3 +142,37 @@ def test_batched_thread_per_query_kernel_bit_exact(maps, small_world, nearby, k)
     b = [gm.knn(qq[s:s + 30000], k=k, max_sq=5.0, stencil=nearby) for s in range(0, 70000, 30000)]
     for j in range(3):
         np.testing.assert_array_equal(a[j], np.concatenate([p[j] for p in b]))
+
+
+def test_box_delete_matches_port():
+    """lsd_map_delete_boxes (KD_TREE::Delete_Point_Boxes semantics) against the CPU port, itself pinned against the
+    compiled ikd-Tree (tests/test_oracle_golden.py): same count, and no query — stencil or exact, either kernel shape —
+    ever returns a deleted point."""
+    import lsdreg
+    from oracle import oracle as O
+    rng = np.random.default_rng(12)
+    pts = np.zeros((60000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-20, 20, (60000, 3)); pts[:, 2] *= 0.1          # ~9 points per 0.5 m voxel: overflow lines too
+    boxes = np.array([[-5, -5, -2, 3, 4, 2], [8, -20, -4, 20, -10, 4], [100, 100, 100, 101, 101, 101]], np.float32)
+    boxes[0, 0] = pts[7, 0]; boxes[0, 3] = pts[9, 0]
+    g = lsdreg.HashVoxelMap(0.5, 16); g.insert(pts, 0)
+    o = O.OracleIvox(0.5, 18, 1 << 16); o.add(pts, 0)
+    n_g, n_o = g.delete_boxes(boxes), o.delete_boxes(boxes)
+    assert n_g == n_o > 3000
+    assert g.stats()["points"] == o.num_points == len(pts) - n_o
+    assert g.delete_boxes(boxes) == 0                                        # idempotent
+    q = pts[rng.integers(0, len(pts), 70000)].copy(); q[:, :3] += rng.normal(0, 0.2, (70000, 3)).astype(np.float32)
+    oi, od, _, oc = o.knn(q[:5000], 5, 5.0)
+    for sl in (slice(0, 5000), slice(0, 70000)):                             # warp-per-query and thread-per-query kernels
+        gi, gd, gc = g.knn(q[sl], 5, 5.0, 18)
+        np.testing.assert_array_equal(gi[:5000], oi); np.testing.assert_array_equal(gc[:5000], oc)
+        np.testing.assert_array_equal(gd[:5000].view(np.int32), od.view(np.int32))
+    oi, od, _, oc = o.knn(q[:3000], 20, 5.0, exact=True)
+    gi, gd, gc = g.knn(q[:3000], 20, 5.0, lsdreg.STENCIL_EXACT)
+    np.testing.assert_array_equal(gi, oi); np.testing.assert_array_equal(gc, oc)
+    inside = (pts[:, 0] >= boxes[0, 0]) & (pts[:, 0] < boxes[0, 3]) & (pts[:, 1] >= -5) & (pts[:, 1] < 4) & (pts[:, 2] >= -2) & (pts[:, 2] < 2)
+    assert not np.isin(gi[gi >= 0], np.nonzero(inside)[0]).any()
+    more = pts[:1000].copy(); more[:, 0] += 0.01                              # the map keeps working after a delete
+    g.insert(more, 100000); o.add(more, 100000)
+    gi, gd, gc = g.knn(q[:2000], 5, 5.0, 18); oi, od, _, oc = o.knn(q[:2000], 5, 5.0)
+    np.testing.assert_array_equal(gi, oi); np.testing.assert_array_equal(gc, oc)

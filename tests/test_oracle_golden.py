@@ -143,3 +143,28 @@ def test_full_lio_loop_port_equals_reference_classes():
     assert np_ == nr and ap == ar and cp == cr
     assert np.abs(xp[:3] - xr[:3]).max() < 1e-6
     assert np.linalg.norm(eskf.so3_log(eskf.quat_mul(eskf.quat_conj(xp[3:7]), xr[3:7]))) < 1e-7
+
+
+def test_box_delete_port_equals_compiled_ikdtree():
+    """KD_TREE::Delete_Point_Boxes on the compiled reference tree vs the port's hash map: same count, and the exact k-NN
+    of both after the delete are identical (ids and distances)."""
+    if not O.HAVE_REF or not hasattr(O.ref, "ref_ikd_delete_boxes"):
+        pytest.skip("oracle/_ref/libref_lio.so without ref_ikd_delete_boxes")
+    rng = np.random.default_rng(12)
+    pts = np.zeros((20000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-20, 20, (20000, 3)); pts[:, 2] *= 0.2
+    boxes = np.array([[-5, -5, -2, 3, 4, 2], [8, -20, -4, 20, -10, 4], [100, 100, 100, 101, 101, 101]], np.float32)
+    boxes[0, 0] = pts[7, 0]; boxes[0, 3] = pts[9, 0]      # a point exactly on min (deleted) and one exactly on max (kept)
+    tree = O.RefIkd(); tree.build(pts, 0)
+    m = O.OracleIvox(0.5, 18, 1 << 16); m.add(pts, 0)
+    n_ref = tree.delete_boxes(boxes)
+    n_port = m.delete_boxes(boxes)
+    assert n_ref == n_port > 1000
+    assert m.num_points == len(pts) - n_port
+    q = pts[rng.integers(0, len(pts), 3000)].copy(); q[:, :3] += rng.normal(0, 0.2, (3000, 3)).astype(np.float32)
+    ri, rd, rc = tree.knn(q, 5)
+    pi, pd, _, pc = m.knn(q, 5, 1e9, exact=True)
+    ri, rd = O.canonical_rows(ri, rd)
+    np.testing.assert_array_equal(rc, pc)
+    np.testing.assert_array_equal(ri, pi)
+    np.testing.assert_array_equal(rd.view(np.int32), pd.view(np.int32))
