@@ -9,9 +9,11 @@ Follows, line by line, the parts of IKFoM the LIO hot path executes (paths relat
   * S2 boxplus/boxminus/Bx/Nx_yy/Mx                 IKFoM_toolkit/mtk/types/S2.hpp:132-290
   * A_matrix                                        mtk/src/mtkmath.hpp:222-234
 
-IKFoM needs Boost (absent here) so it cannot be compiled: this restatement is
-PARITY UNPINNED against a compiled reference; it is pinned only by its own algebraic properties
-(tests/test_eskf.py) and is deliberately written independently of the product's C++ host code.
+Pin status: PINNED.  IKFoM needs Boost.Preprocessor (absent here); oracle/ref_shim_ikfom re-implements
+the dozen macros it uses, and the reference's own esekf / state_ikfom then compile unmodified
+(oracle/ref_ikfom.cpp -> oracle/_ref/libref_ikfom.so).  tests/test_oracle_ikfom.py checks this restatement — and the
+product's host C++, written independently — against it: manifold operators 1e-13, predict 1e-12, the iterated update
+(same evaluation count, state 1e-9, covariance 2e-6 relative).
 
 State layout (DOF index): pos 0:3, rot 3:6, offset_R_L_I 6:9, offset_T_L_I 9:12, vel 12:15,
 bg 15:18, ba 18:21, grav 21:23.  Quaternions are (x, y, z, w) like Eigen's coeffs().

@@ -2,8 +2,11 @@
 IMU initialisation, forward propagation and per-point undistortion of
 /root/reference/slam/mapping/fastlio/src/IMU_Processing.hpp:167-450 on top of oracle/eskf.py::predict.
 
-PARITY UNPINNED: IMU_Processing.hpp includes the IKFoM toolkit, which needs Boost (absent here) — it cannot be
-compiled.  so3_math.h::Exp is restated in `exp_rodrigues`.  Written independently of the product's C++ (csrc/imu.hpp).
+Pin status: PINNED.  The reference's ImuProcess compiles unmodified with the Boost.Preprocessor / PCL shims of
+oracle/ref_shim_ikfom (oracle/ref_ikfom.cpp -> oracle/_ref/libref_ikfom.so); tests/test_oracle_ikfom.py runs whole IMU
+streams through both: state 1e-11, covariance 1e-9, the IMU pose list, and every undistorted point (>= 99 % bit-identical,
+the rest within 1 float32 ulp), including the reference's repeated compensation of the earliest point.
+Written independently of the product's C++ (csrc/imu.cu).
 
 A measurement group is (lidar_beg_time, lidar_end_time, points [n,4] float32 (x, y, z, intensity),
 time_ms [n] float32 (PointType::curvature), imu [m,7] float64 (stamp s, gyr xyz rad/s, acc xyz in g-units),

@@ -601,8 +601,9 @@ int orc_map_incremental(OrcIvox* map, const float* body, int n, const double* R,
 /*        .../covariance_regularization.cu:15-52,105-116 (PLANE: V diag(1e-3,1,1) V^-1)    */
 /*        .../find_voxel_correspondences.cu:16-111, ndt_compute_derivatives.cu:15-102      */
 /*        include/fast_gicp/cuda/vector3_hash.cuh:35-38 (coord = floor(x/res - 0.5))       */
-/*      PARITY UNPINNED: the reference NDT exists only as CUDA (thrust) code, SASS-built   */
-/*      for sm_72..89; it cannot run or be compiled for the host here.         */
+/*      Pin status: the reference NDT exists only as CUDA (thrust) code; it recompiles for  */
+/*      sm_100a (oracle/ref_cuda.cu) and pins this restatement on the GPU box               */
+/*      (tests/test_gpu_ref_cuda.py), within the bounds its lossy voxel table allows.       */
 /*      fp32 per-element arithmetic as the reference; sums are carried in double (the      */
 /*      reference reduces fp32 tuples in thrust's unspecified tree order).                 */
 /*      PLANE-regularised covariance: V diag(1e-3,1,1) V^T  =>  C^-1 = I + 999 n n^T with  */
@@ -714,8 +715,8 @@ double orc_ndt_cost(const OrcNdt* m, const float* src, int stride, int n, const 
 /*      regularisation (U diag(1,1,1e-3) V^T  =  I - 0.999 n n^T), 1-NN correspondences    */
 /*      within max_corr, D2D cost, all double.  Neighbour search is exact (the reference   */
 /*      uses pcl::search::KdTree/FLANN: exact k-NN, method-independent up to ties).         */
-/*      PARITY UNPINNED against compiled code (needs PCL/FLANN); the k-NN it relies on is   */
-/*      the one pinned against the ikd-Tree above.                                          */
+/*      Pinned against the compiled reference FastGICP / FastVGICP (oracle/ref_reg.cpp,      */
+/*      PCL shimmed): tests/test_oracle_reg.py.                                              */
 /* ===================================================================================== */
 /* normals[n,3] (double) = smallest-eigenvalue direction of the k-NN covariance; cnt[n] = #neighbours used */
 void orc_gicp_normals(const OrcIvox* map, const float* pts, int stride, int n, int k, double max_sq, double* normals, int* cnt,

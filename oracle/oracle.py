@@ -159,11 +159,36 @@ def _load_ref_cuda():
     return L
 
 
+def _load_ref_ikfom():
+    """The compiled reference filter + IMU stage (oracle/ref_ikfom.cpp -> oracle/_ref/libref_ikfom.so)."""
+    path = os.path.join(_HERE, "_ref", "libref_ikfom.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_ikfom_predict.argtypes = [_d, _d, C.c_double, _d, _d, _d]
+    L.ref_ikfom_update_rows.restype = C.c_int
+    L.ref_ikfom_update_rows.argtypes = [_d, _d, _d, _d, _i, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    L.ref_ikfom_boxplus.argtypes = [_d, _d]
+    L.ref_ikfom_boxminus.argtypes = [_d, _d, _d]
+    L.ref_imu_create.restype = C.c_void_p
+    L.ref_imu_create.argtypes = [_d, _d, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.ref_imu_destroy.argtypes = [C.c_void_p]
+    L.ref_imu_process.restype = C.c_int
+    L.ref_imu_process.argtypes = [C.c_void_p, _d, C.c_int, C.c_void_p, C.c_double, C.c_double, _f, _f, C.c_int, _d, _d, _f, _f]
+    L.ref_imu_get_poses.restype = C.c_int
+    L.ref_imu_get_poses.argtypes = [C.c_void_p, _d, C.c_int]
+    L.ref_imu_is_init.restype = C.c_int
+    L.ref_imu_is_init.argtypes = [C.c_void_p]
+    return L
+
+
 port = _load_port()
 ref = _load_ref()
 HAVE_REF = ref is not None
 ref_reg = _load_ref_reg()
 HAVE_REF_REG = ref_reg is not None
+ref_ikfom = _load_ref_ikfom()
+HAVE_REF_IKFOM = ref_ikfom is not None
 
 
 def _c32(a):

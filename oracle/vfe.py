@@ -4,8 +4,9 @@ Follows sensor_driver/inference/voxelize (relative to /root/reference):
   preprocess_kernel.cu:6-20,56-101   sliding window, 3x4 motion, time + 0.1
   voxelization_kernel.cu:73-180      hash voxelisation, <= max_points_per_voxel points, mean, fp16
 executed SEQUENTIALLY in point order (the reference's GPU result depends on thread arrival order;
-the sequential order is one of its possible outcomes).  PARITY UNPINNED: the reference has no CPU
-implementation of this path and its CUDA build targets sm_72..89 only.
+the sequential order is one of its possible outcomes).  Pin status: the reference has no CPU implementation of this
+path, but its two .cu files recompile unmodified for sm_100a (oracle/ref_vfe.cu -> oracle/_ref/libref_vfe.so, class
+RefVoxelizer below) and pin this restatement's semantics and the product on the GPU box (tests/test_gpu_ref_cuda.py).
 """
 from __future__ import annotations
 
