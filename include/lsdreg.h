@@ -372,10 +372,13 @@ void lsd_state_boxplus(double* state26_inout, const double* delta23);
 void lsd_state_boxminus(const double* a26, const double* b26, double* out23);
 /* The filter alone, on the host (no GPU): runs esekf::update_iterated_dyn_share_modified with the
  * measurement model replaced by a caller-supplied table — evaluation e uses HTH36[e], HTh6[e],
- * n_eff[e] (n_eff[e] < 1 = invalid).  Returns the number of evaluations consumed.  Used by the CPU
+ * n_eff[e] (n_eff[e] < 1 = invalid).  Returns the number of evaluations consumed; converge_log16_or_null[e] receives
+ * the `converge` flag evaluation e was called with (what h_share_model reads to decide on a new neighbour search,
+ * laserMapping.cpp:838-852).  Used by the CPU
  * test-suite to check the host algebra against the oracle without a device. */
 int lsd_eskf_update_table(double* state26_inout, double* P529_inout, const double* HTH36, const double* HTh6,
-                          const int* n_eff, int n_table, double R, int max_iterations, double eps, int literal);
+                          const int* n_eff, int n_table, double R, int max_iterations, double eps, int literal,
+                          int* converge_log16_or_null);
 
 #ifdef __cplusplus
 }

@@ -152,7 +152,7 @@ SIGNATURES = [
     ("lsd_lio_init_cov", None, [_vp]),
     ("lsd_state_boxplus", None, [_vp, _vp]),
     ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
-    ("lsd_eskf_update_table", _i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _i, _d, _i]),
+    ("lsd_eskf_update_table", _i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _i, _d, _i, _vp]),
 ]
 
 
@@ -449,15 +449,16 @@ class Matcher:
         return dict(n_voxels=nv.value, launches=ln.value)
 
 
-def eskf_update_table(state, P, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=0.001, literal=False):
-    """Host-only filter run with a tabulated measurement model (include/lsdreg.h lsd_eskf_update_table)."""
+def eskf_update_table(state, P, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=0.001, literal=False, converge_log=None):
+    """Host-only filter run with a tabulated measurement model (include/lsdreg.h lsd_eskf_update_table).
+    converge_log: optional int32[16] receiving the converge flag of every evaluation."""
     state = np.array(state, np.float64)
     P = np.array(P, np.float64)
     HTH = np.ascontiguousarray(HTH, np.float64).reshape(-1, 36)
     HTh = np.ascontiguousarray(HTh, np.float64).reshape(-1, 6)
     n_eff = np.ascontiguousarray(n_eff, np.int32)
     ev = lib.lsd_eskf_update_table(_ptr(state), _ptr(P), _ptr(HTH), _ptr(HTh), _ptr(n_eff), HTH.shape[0], R, max_iterations,
-                                   eps, int(literal))
+                                   eps, int(literal), None if converge_log is None else _ptr(converge_log))
     return state, P, ev
 
 

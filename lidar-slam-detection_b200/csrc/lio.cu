@@ -1205,10 +1205,11 @@ void lsd_state_boxplus(double* state26_inout, const double* delta23) { if (state
 void lsd_state_boxminus(const double* a26, const double* b26, double* out23) { if (a26 && b26 && out23) eskf::boxminus(a26, b26, out23); }
 
 int lsd_eskf_update_table(double* state26_inout, double* P529_inout, const double* HTH36, const double* HTh6, const int* n_eff,
-                          int n_table, double R, int max_iterations, double eps, int literal) {
+                          int n_table, double R, int max_iterations, double eps, int literal, int* converge_log16_or_null) {
   if (!state26_inout || !P529_inout || !HTH36 || !HTh6 || !n_eff || n_table < 1) return LSD_ERR_INVALID;
   int e = 0;
-  auto hm = [&](const double*, bool, eskf::HModel* out) {
+  auto hm = [&](const double*, bool converge, eskf::HModel* out) {
+    if (converge_log16_or_null && e < 16) converge_log16_or_null[e] = converge ? 1 : 0;
     const int k = e < n_table ? e : n_table - 1;
     e++;
     out->n = n_eff[k];

@@ -167,7 +167,7 @@ def _load_ref_ikfom():
     L = C.CDLL(path)
     L.ref_ikfom_predict.argtypes = [_d, _d, C.c_double, _d, _d, _d]
     L.ref_ikfom_update_rows.restype = C.c_int
-    L.ref_ikfom_update_rows.argtypes = [_d, _d, _d, _d, _i, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    L.ref_ikfom_update_rows.argtypes = [_d, _d, _d, _d, _i, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_void_p]
     L.ref_ikfom_boxplus.argtypes = [_d, _d]
     L.ref_ikfom_boxminus.argtypes = [_d, _d, _d]
     L.ref_imu_create.restype = C.c_void_p

@@ -52,11 +52,12 @@ static void get_kf(const Kf& kf, double* x26, double* P529) {
 }
 
 // ---- tabulated measurement model for update_iterated_dyn_share_modified
-struct Table { const double* rows; const double* h; const int* n_rows; int n_table, max_rows, calls; };
+struct Table { const double* rows; const double* h; const int* n_rows; int n_table, max_rows, calls; int* converge_log; };
 static thread_local Table* g_table = nullptr;
 static void h_table(state_ikfom&, esekfom::dyn_share_datastruct<double>& d) {
   Table* t = g_table;
   const int e = t->calls < t->n_table ? t->calls : t->n_table - 1;
+  if (t->converge_log && t->calls < 16) t->converge_log[t->calls] = d.converge ? 1 : 0;  // what h_share_model reads to decide on a new neighbour search
   t->calls++;
   const int n = t->n_rows[e];
   if (n < 1) { d.valid = false; return; }
@@ -87,13 +88,13 @@ void ref_ikfom_predict(double* x26, double* P529, double dt, const double* Q144,
 // rows: [n_table, max_rows, 6] (the 6 non-zero columns of h_x), h: [n_table, max_rows], n_rows: [n_table] (< 1 = invalid).
 // Returns the number of measurement-model evaluations.
 int ref_ikfom_update_rows(double* x26, double* P529, const double* rows, const double* h, const int* n_rows, int n_table, int max_rows,
-                          double R, int max_iterations, double eps) {
+                          double R, int max_iterations, double eps, int* converge_log16) {
   Kf kf;
   double epsi[23];
   std::fill(epsi, epsi + 23, eps);
   kf.init_dyn_share(get_f, df_dx, df_dw, h_table, max_iterations, epsi);
   set_kf(kf, x26, P529);
-  Table t{rows, h, n_rows, n_table, max_rows, 0};
+  Table t{rows, h, n_rows, n_table, max_rows, 0, converge_log16};
   g_table = &t;
   double solve = 0;
   kf.update_iterated_dyn_share_modified(R, solve);

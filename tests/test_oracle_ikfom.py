@@ -78,17 +78,23 @@ def test_iterated_update_matches_reference(scale_h, invalid_first, n_rows):
         if invalid_first:
             n_eff[0] = 0                                              # "No Effective Points" on the first evaluation: skipped
         xr, Pr = x0.to_vec().copy(), P0.copy()
-        ev_r = R.ref_ikfom_update_rows(xr, Pr, np.ascontiguousarray(rows), np.ascontiguousarray(h), n_eff, n_table, n_rows, 0.001, 4, 0.001)
+        conv_r = np.full(16, -1, np.int32)
+        ev_r = R.ref_ikfom_update_rows(xr, Pr, np.ascontiguousarray(rows), np.ascontiguousarray(h), n_eff, n_table, n_rows, 0.001, 4, 0.001,
+                                       conv_r.ctypes.data)
         HTH = np.einsum("eni,enj->eij", rows, rows); HTh = np.einsum("eni,en->ei", rows, h)
         if n_rows >= 23:                                              # the table form of the product carries no h_x rows
             for literal in (False, True):
-                xg, Pg, ev_g = lsdreg.eskf_update_table(x0.to_vec(), P0, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=0.001, literal=literal)
-                assert ev_g == ev_r
+                conv_g = np.full(16, -1, np.int32)
+                xg, Pg, ev_g = lsdreg.eskf_update_table(x0.to_vec(), P0, HTH, HTh, n_eff, R=0.001, max_iterations=4, eps=0.001, literal=literal,
+                                                        converge_log=conv_g)
+                assert ev_g == ev_r and list(conv_g[:ev_g]) == list(conv_r[:ev_r])   # same search / reuse pattern as the reference filter
                 np.testing.assert_allclose(xg, xr, rtol=0, atol=1e-9)
                 np.testing.assert_allclose(Pg, Pr, rtol=2e-6, atol=2e-6 * np.abs(Pr).max())   # two ill-conditioned 23x23 inversions in the reference
         calls = [0]
+        conv_o = []
 
         def hm(state, converge):
+            conv_o.append(int(converge))                              # the flag that decides on a new neighbour search
             e = min(calls[0], n_table - 1); calls[0] += 1
             if n_eff[e] < 1:
                 return dict(valid=False)
@@ -98,6 +104,7 @@ def test_iterated_update_matches_reference(scale_h, invalid_first, n_rows):
             return dict(valid=True, n=n_rows, HTH=H15, HTh=h15, h_x=Hx, h=h[e])
         xo, Po, _ = E.update_iterated(x0, P0, hm, R=0.001, maximum_iter=4, limit=0.001)
         assert calls[0] == ev_r
+        assert conv_o == list(conv_r[:ev_r])
         np.testing.assert_allclose(xo.to_vec(), xr, rtol=0, atol=1e-9)
         np.testing.assert_allclose(Po, Pr, rtol=2e-6, atol=2e-6 * np.abs(Pr).max())
 
