@@ -24,9 +24,17 @@ class OracleLio:
     FILTER_MAP = 0.5  # laserMapping.cpp:1028
 
     def __init__(self, nearby: int = 18, knn_exact: bool = False, expected_cells: int = 1 << 18,
-                 nthreads: int = 8, degenerate_detect: bool = True, backend: str = "port"):
+                 nthreads: int = 8, degenerate_detect: bool = True, backend: str = "port", stale_neighbours: bool = False):
         """backend "port": oracle/lsd_oracle.c; "reference": the compiled reference IVox +
-        esti_plane (oracle/_ref) inside the same restated loop."""
+        esti_plane (oracle/_ref) inside the same restated loop.
+
+        stale_neighbours: reproduce the reference's Nearest_Points quirk.  Nearest_Points is a file-scope
+        vector<PointVector> that is only resize()d per scan (laserMapping.cpp:1273) and IVox::GetClosestPoint returns
+        BEFORE clearing its output when no candidate is in range (ivox3d.h:155-157): a scan point with nothing near it keeps
+        the neighbours row i held the last time it found any — from an earlier iteration or an earlier scan — and is
+        selected, plane-fitted and gated on those.  False (default) treats such a point as having no neighbours, which is
+        what the product does today (known deviation); tests/test_oracle_fastlio.py measures the difference."""
+        self.stale = bool(stale_neighbours) and not knn_exact
         self.backend = backend
         if backend == "reference":
             assert O.HAVE_REF and not knn_exact
@@ -35,7 +43,8 @@ class OracleLio:
         else:
             self.map = O.OracleIvox(0.5, nearby, expected_cells)  # laserMapping.cpp:1060-1065
             self._hm, self._mi = O.port.orc_lio_hmodel, O.port.orc_map_incremental
-        self.knn_mode = 1 if knn_exact else 0
+        self.knn_mode = (1 if knn_exact else 0) | (2 if self.stale else 0)
+        self._rows = 0  # rows of the persistent neighbour table in use (stale mode): Nearest_Points.size()
         self.nthreads = nthreads
         self.degenerate_detect = degenerate_detect
         self.x = eskf.State()
@@ -91,9 +100,23 @@ class OracleLio:
             return dict(seeded=True, n_down=n)
         if n < 5:  # laserMapping.cpp:1252-1256
             return dict(seeded=False, n_down=n, skipped=True)
-        self.near_xyz = np.zeros((n, 5, 3), np.float32)
-        self.near_ids = np.full((n, 5), -1, np.int32)
-        self.near_cnt = np.zeros(n, np.int32)
+        if not self.stale:
+            self.near_xyz = np.zeros((n, 5, 3), np.float32)
+            self.near_ids = np.full((n, 5), -1, np.int32)
+            self.near_cnt = np.zeros(n, np.int32)
+        else:  # Nearest_Points.resize(feats_down_size): rows < n keep their lists, rows >= n are destroyed
+            if not hasattr(self, "near_cnt") or self.near_cnt.shape[0] < n:
+                cap = max(n, 100000)
+                old = getattr(self, "near_cnt", None)
+                nx, ni, nc = np.zeros((cap, 5, 3), np.float32), np.full((cap, 5), -1, np.int32), np.zeros(cap, np.int32)
+                if old is not None:
+                    k = old.shape[0]
+                    nx[:k], ni[:k], nc[:k] = self.near_xyz, self.near_ids, self.near_cnt
+                self.near_xyz, self.near_ids, self.near_cnt = nx, ni, nc
+            if self._rows > n:
+                self.near_cnt[n:self._rows] = 0
+                self.near_ids[n:self._rows] = -1
+            self._rows = n
         if not hasattr(self, "selected") or self.selected.shape[0] < n:
             self.selected = np.ones(max(n, 100000), np.uint8)  # memset(true), laserMapping.cpp:1089
         self.world = np.zeros((n, 4), np.float32)

@@ -469,7 +469,11 @@ int orc_lio_hmodel(const OrcIvox* map, const float* body, int n, const double* R
     w[3] = pb[3];
     if (search) {
       OrcCand best[5];
-      int nb = knn_mode == 0 ? ivox_knn_one(map, w, 5, 5.0, best) : exact_knn_one(map, w, 5, 5.0, best);
+      int nb = (knn_mode & 1) == 0 ? ivox_knn_one(map, w, 5, 5.0, best) : exact_knn_one(map, w, 5, 5.0, best);
+      /* knn_mode & 2: the reference's stale list.  IVox::GetClosestPoint returns before clearing its output when no
+       * candidate is in range (ivox3d.h:155-157), and Nearest_Points[i] is a file-scope vector that outlives the scan
+       * (laserMapping.cpp:1273): such a point keeps the neighbours row i had the last time it found any. */
+      if ((knn_mode & 2) && nb == 0) { selected[i] = near_cnt[i] >= 5; goto searched; }
       near_cnt[i] = nb;
       for (int j = 0; j < 5; j++) {
         near_ids[5 * (size_t)i + j] = j < nb ? best[j].id : -1;
@@ -478,6 +482,7 @@ int orc_lio_hmodel(const OrcIvox* map, const float* body, int n, const double* R
       }
       selected[i] = nb >= 5; /* laserMapping.cpp:847,850 */
     }
+  searched:
     if (!selected[i]) continue;
     selected[i] = 0;
     float pabcd[4];

@@ -85,6 +85,8 @@ def _load_ref():
     L.ref_ivox_add.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_double]
     L.ref_ivox_num_cells.restype = C.c_size_t
     L.ref_ivox_num_cells.argtypes = [C.c_void_p]
+    if hasattr(L, "ref_ivox_set_nearby"):
+        L.ref_ivox_set_nearby.argtypes = [C.c_void_p, C.c_int]
     L.ref_ivox_knn.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_double, _i, _f, _i, C.c_int]
     L.ref_ikd_create.restype = C.c_void_p
     L.ref_ikd_destroy.argtypes = [C.c_void_p]
@@ -278,6 +280,9 @@ class RefIvox:
     def add(self, xyz: np.ndarray, id0: int):
         xyz = _c32(xyz[:, :3])
         ref.ref_ivox_add(self.h, xyz, xyz.shape[0], id0, 0.0)
+
+    def set_nearby(self, nearby: int):
+        ref.ref_ivox_set_nearby(self.h, nearby)
 
     @property
     def num_cells(self):

@@ -56,6 +56,18 @@ void ref_ivox_add(void* h, const float* xyz, int n, int id0, double distance) {
   static_cast<IVoxType*>(h)->AddPoints(pv, distance);
 }
 size_t ref_ivox_num_cells(void* h) { return static_cast<IVoxType*>(h)->NumValidGrids(); }
+// IVox::SetNearByType (ivox3d.h:64-67): the pipeline starts on NEARBY74 and switches to NEARBY18 (laserMapping.cpp:1241-1243)
+void ref_ivox_set_nearby(void* h, int nearby) {
+  IVoxType::NearbyType t = IVoxType::NearbyType::NEARBY74;
+  switch (nearby) {
+    case 0: t = IVoxType::NearbyType::CENTER; break;
+    case 6: t = IVoxType::NearbyType::NEARBY6; break;
+    case 18: t = IVoxType::NearbyType::NEARBY18; break;
+    case 26: t = IVoxType::NearbyType::NEARBY26; break;
+    default: break;
+  }
+  static_cast<IVoxType*>(h)->SetNearByType(t);
+}
 
 // k-NN exactly as laserMapping.cpp:849 calls it.  out_ids [nq,k] (-1 padded), out_xyz [nq,k,3],
 // out_cnt [nq].  Order within a row is the reference's (nearest first, rest nth_element order).
@@ -135,7 +147,7 @@ void ref_esti_plane(const float* pts5, int n, float thr, float* pabcd, int* ok) 
 // SelfAdjointEigenSolver for the degeneracy test exactly as the reference does.  Same signature as
 // orc_lio_hmodel (oracle/lsd_oracle.c) so oracle/lio.py can drive either.
 int ref_lio_hmodel(void* hv, const float* body, int n, const double* R_, const double* t_, const double* RL_,
-                   const double* tL_, int search, int /*knn_mode*/, float* near_xyz, int* near_ids, int* near_cnt,
+                   const double* tL_, int search, int knn_mode, float* near_xyz, int* near_ids, int* near_cnt,
                    unsigned char* selected, float* world, float* plane, double* HTH, double* HTh, double* res_sum,
                    int* degenerate, int degenerate_detect_en, double* hx_out, double* h_out, int nthreads) {
   IVoxType* iv = static_cast<IVoxType*>(hv);
@@ -155,12 +167,20 @@ int ref_lio_hmodel(void* hv, const float* body, int n, const double* R_, const d
     if (search) {
       iv->GetClosestPoint(point_world, points_near, NUM_MATCH_POINTS, 5);
       int c = int(points_near.size());
-      near_cnt[i] = c;
-      for (int j = 0; j < 5; j++) {
-        near_ids[5 * (size_t)i + j] = j < c ? id_of(points_near[j]) : -1;
-        for (int d = 0; d < 3; d++) near_xyz[(5 * (size_t)i + j) * 3 + d] = j < c ? (&points_near[j].x)[d] : 0.f;
+      // knn_mode & 2: keep row i's previous list when GetClosestPoint found no candidate (it returns before clear(),
+      // ivox3d.h:155-157, and the reference's Nearest_Points[i] outlives the scan, laserMapping.cpp:1273)
+      if (!((knn_mode & 2) && c == 0)) {
+        near_cnt[i] = c;
+        for (int j = 0; j < 5; j++) {
+          near_ids[5 * (size_t)i + j] = j < c ? id_of(points_near[j]) : -1;
+          for (int d = 0; d < 3; d++) near_xyz[(5 * (size_t)i + j) * 3 + d] = j < c ? (&points_near[j].x)[d] : 0.f;
+        }
       }
-      selected[i] = c >= NUM_MATCH_POINTS;
+      selected[i] = near_cnt[i] >= NUM_MATCH_POINTS;
+      if (selected[i] && c == 0) {
+        points_near.resize(5);
+        for (int j = 0; j < 5; j++) for (int d = 0; d < 3; d++) (&points_near[j].x)[d] = near_xyz[(5 * (size_t)i + j) * 3 + d];
+      }
     } else if (selected[i]) {
       points_near.resize(5);
       for (int j = 0; j < 5; j++) for (int d = 0; d < 3; d++) (&points_near[j].x)[d] = near_xyz[(5 * (size_t)i + j) * 3 + d];
