@@ -155,6 +155,14 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l);
 lsd_map_t* lsd_lio_map(lsd_lio_t* l);
 lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil); /* IVox::SetNearByType, laserMapping.cpp:1241-1243 */
 lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag);
+/* The reference's stale Nearest_Points rows.  Nearest_Points is a file-scope vector<PointVector> that is only resize()d
+ * per scan (laserMapping.cpp:1273), and IVox::GetClosestPoint returns BEFORE clearing its output when no map point is in
+ * range (ivox3d.h:155-157): a scan point with nothing near it keeps the neighbours row i held the last time a search
+ * found any (an earlier iteration or an earlier scan), is plane-fitted and gated on those, and map_incremental reads
+ * them too.  flag != 0 reproduces that (iVox stencils on a single-GPU handle; the exact / ikd-Tree search clears its
+ * output); 0 (default this round) treats such a point as having no neighbours.  Either call
+ * empties the rows. */
+lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
 /* Id given to the next point map_incremental inserts (ids of points inserted through
  * lsd_map_insert(lsd_lio_map(l), ...) are the caller's). */
 lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, laserMapping.cpp:1196 */

@@ -92,6 +92,7 @@ SIGNATURES = [
     ("lsd_lio_map", _vp, [_vp]),
     ("lsd_lio_set_nearby", _i, [_vp, _i]),
     ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
+    ("lsd_lio_set_stale_rows", _i, [_vp, _i]),
     ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
     ("lsd_lio_shard_export", _i, [_vp, _i, _i, _i, _i, _vp]),
     ("lsd_lio_shard_connect", _i, [_vp, _vp]),
@@ -622,6 +623,10 @@ class LioFrontend:
 
     def set_ekf_inited(self, flag: bool):
         check(lib.lsd_lio_set_ekf_inited(self.h, int(flag)))
+
+    def set_stale_rows(self, flag: bool):
+        """Keep Nearest_Points[i] when a search finds nothing, as the reference does (include/lsdreg.h)."""
+        check(lib.lsd_lio_set_stale_rows(self.h, int(flag)))
 
     SHARD_BLOB_BYTES = 192
 

@@ -311,7 +311,8 @@ __constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{
 constexpr int kHmWarps = 8;
 __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, int stencil, const float4* __restrict__ body,
                                                                 const int* __restrict__ n_ptr, int cap, LioPose ps,
-                                                                float4* __restrict__ near, int* __restrict__ near_cnt) {
+                                                                float4* __restrict__ near, int* __restrict__ near_cnt,
+                                                                int keep_stale) {
   __shared__ __align__(16) unsigned char s_list[kHmWarps * kWarpListBytes];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(*n_ptr, cap);
@@ -339,12 +340,24 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
     }
     Neighbor nb;
     const int nf = knn_search_warp<5>(mv, stencil, ls, wx, wy, wz, 5.0f, wl, nb);
+    // keep_stale: IVox::GetClosestPoint returns before clearing its output when nothing is in range (ivox3d.h:155-157)
+    // and Nearest_Points outlives the scan (laserMapping.cpp:1273): row i then keeps what it held (lsd_lio_set_stale_rows)
+    if (keep_stale && nf == 0) continue;
     float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     if (lane < nf) q = load_loc(mv, nb.loc);
     if (lane < 5) near[(size_t)i * 5 + lane] = q;
     if (lane == 0) near_cnt[i] = nf;
   }
 }
+
+// Nearest_Points.resize(feats_down_size) (laserMapping.cpp:1273): rows the new scan does not have are destroyed, so a
+// later, larger scan finds them empty.  rows[0] = number of rows alive (the previous scan's size).
+__global__ void lio_resize_rows_kernel(const int* __restrict__ n_ptr, int cap, int* __restrict__ rows, int* __restrict__ near_cnt) {
+  const int n = min(*n_ptr, cap), prev = min(*rows, cap);
+  for (int i = n + blockIdx.x * blockDim.x + threadIdx.x; i < prev; i += gridDim.x * blockDim.x) near_cnt[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) rows[1] = n;  // published by the next launch: every block must read rows[0] first
+}
+__global__ void lio_commit_rows_kernel(int* __restrict__ rows) { rows[0] = rows[1]; }
 
 // ---------------------------------------------------------------- K4+K5: plane fit + residual/Jacobian + reduction
 // One thread per downsampled point.  FIT: first evaluation after a search — fit the plane through
@@ -596,7 +609,8 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
     const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
-    lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt);
+    lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                                                  (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0);
     lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                                        l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
                                                                        l->d_partials, l->d_done, l->d_result, seq, l->sc);
@@ -785,6 +799,12 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
     l->launches++;
     l->n_bound = std::max(n, 1);
     l->n_down = n;
+  }
+  if (l->stale_rows) {
+    lio_resize_rows_kernel<<<32, 256, 0, st>>>(l->d_n, l->p.max_points, l->d_n + 8, l->d_near_cnt);
+    lio_commit_rows_kernel<<<1, 1, 0, st>>>(l->d_n + 8);
+    l->launches += 2;
+    LSD_CUDA(cudaGetLastError());
   }
   return LSD_OK;
 }
@@ -978,6 +998,17 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
 
 lsd_map_t* lsd_lio_map(lsd_lio_t* l) { return l ? l->map : nullptr; }
 
+lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
+  if (!l) return LSD_ERR_INVALID;
+  if (flag && l->map->view.shard_world > 1) { set_error("lsd_lio_set_stale_rows: not available on a tile-sharded handle"); return LSD_ERR_INVALID; }
+  cudaSetDevice(l->device);
+  // start from empty rows either way: a default-constructed Nearest_Points
+  LSD_CUDA(cudaMemsetAsync(l->d_near_cnt, 0, (size_t)l->p.max_points * 4, l->stream));
+  LSD_CUDA(cudaMemsetAsync(l->d_n + 8, 0, 8, l->stream));
+  LSD_CUDA(cudaStreamSynchronize(l->stream));
+  l->stale_rows = flag != 0;
+  return LSD_OK;
+}
 lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil) {
   if (!l || (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0)) return LSD_ERR_INVALID;
   l->p.ivox_nearby = stencil;

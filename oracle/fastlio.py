@@ -141,11 +141,14 @@ class OracleFastLio:
         del self.imu_buf[:k]
         return dict(lidar_beg_time=beg, lidar_end_time=end, points=pts, time_ms=t_ms, imu=imu, ins_vel=None)
 
-    def step(self, teacher=None):
+    def step(self, teacher=None, down_from=None):
         """One fastlio_main() pass.  teacher: optional callable -> (State, P), the reference's posterior of this scan; when
         given, this pipeline's own posterior is kept in self.free_posterior and replaced by the teacher's before
         map_incremental, so that a comparison measures ONE scan's deviation instead of the chaotic growth of fp32
-        rounding differences through the map (a single map point that lands in another voxel moves later poses by 1e-5 m)."""
+        rounding differences through the map (a single map point that lands in another voxel moves later poses by 1e-5 m).
+        down_from: optional callable(undistorted [n,4], prior State, prior P, nearby, ekf_inited) -> downsampled [m,4]; when
+        given it replaces this pipeline's VoxelGrid (a GPU parity test runs the product's whole scan there and hands back the
+        product's downsampled cloud, so both sides search with identical query points)."""
         self.last = {}
         self.free_posterior = None
         meas = self._sync()
@@ -164,7 +167,11 @@ class OracleFastLio:
         if self.lio.map.num_cells > 0 and self.nearby != 18 and since > 10 * INIT_TIME:   # :1241-1243 (after the seeding return)
             self.lio.map.set_nearby(18)
             self.nearby = 18
-        r = self.lio.process_scan(und, downsample=True, update_map=teacher is None)
+        if down_from is not None:
+            body = down_from(und, self.lio.x.copy(), self.lio.P.copy(), self.nearby, self.lio.ekf_inited)
+            r = self.lio.process_scan(body, downsample=False, update_map=teacher is None)
+        else:
+            r = self.lio.process_scan(und, downsample=True, update_map=teacher is None)
         self.last = r
         if teacher is not None and "iters" in r:
             self.free_posterior = (self.lio.x.copy(), self.lio.P.copy())
