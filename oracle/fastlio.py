@@ -50,6 +50,13 @@ def _load():
         L.ref_fastlio_counts.argtypes = [C.c_void_p] * 4
         L.ref_fastlio_get_down.restype = C.c_int
         L.ref_fastlio_get_down.argtypes = [C.c_void_p, C.c_int]
+        if hasattr(L, "ref_fastlio_pass"):
+            L.ref_fastlio_set_threads.argtypes = [C.c_int]
+            L.ref_fastlio_bench_init.restype = C.c_int
+            L.ref_fastlio_bench_init.argtypes = [C.c_size_t]
+            L.ref_fastlio_map_add.argtypes = [f, C.c_int, C.c_int]
+            L.ref_fastlio_pass.restype = C.c_int
+            L.ref_fastlio_pass.argtypes = [f, C.c_int, d, d]
         _lib = L
     return _lib
 
@@ -93,6 +100,41 @@ class RefFastLio:
         out = np.zeros((max(n, 1), 4), np.float32)
         self.L.ref_fastlio_get_down(out.ctypes.data, n)
         return out[:n]
+
+
+class RefFastLioBench:
+    """bench.py's CPU arm: the reference's per-scan hot path (VoxelGrid -> kf.update_iterated_dyn_share_modified with
+    h_share_model -> map_incremental: the statements of fastlio_main after ImuProcess, executed by the compiled reference
+    objects, oracle/ref_fastlio.cpp::ref_fastlio_pass) on a prebuilt map.  One instance per process (file-scope state)."""
+
+    def __init__(self, capacity=1 << 30, threads=8):
+        self.L = _load()
+        if not hasattr(self.L, "ref_fastlio_pass"):
+            raise RuntimeError("oracle/_ref/libref_fastlio.so predates ref_fastlio_pass: rebuild it (make -C oracle ref)")
+        self.L.ref_fastlio_bench_init(capacity)
+        self.set_threads(threads)
+
+    def set_threads(self, n):
+        self.threads = int(n)
+        self.L.ref_fastlio_set_threads(int(n))
+
+    def add_map_points(self, pts, chunk=1 << 20):
+        pts = np.ascontiguousarray(pts, np.float32)
+        for lo in range(0, pts.shape[0], chunk):
+            blk = np.ascontiguousarray(pts[lo:lo + chunk])
+            self.L.ref_fastlio_map_add(blk, blk.shape[0], blk.shape[1])
+
+    def process_scan(self, scan, prior: E.State, P: np.ndarray):
+        """-> (posterior State, posterior P, feats_down_size or -1 if the reference skipped the scan)"""
+        scan = np.ascontiguousarray(scan[:, :4], np.float32)
+        x = prior.to_vec(); P = np.ascontiguousarray(P, np.float64).copy()
+        n = self.L.ref_fastlio_pass(scan, scan.shape[0], x, P)
+        return E.State.from_vec(x), P, n
+
+    def counts(self):
+        v = (C.c_int * 4)()
+        self.L.ref_fastlio_counts(*[C.byref(v, 4 * i) for i in range(4)])
+        return dict(n_down=v[0], n_eff=v[1], map_cells=v[2], degenerate=v[3])
 
 
 class OracleFastLio:
