@@ -39,6 +39,7 @@ typedef int lsd_status_t;
 #define LSD_ERR_NO_DEVICE (-3)
 #define LSD_ERR_CAPACITY (-4)       /* hash table / bucket levels / scratch capacity exceeded    */
 #define LSD_ERR_GRID_OVERFLOW (-5)  /* voxel grid larger than int32 (PCL returns input unchanged) */
+#define LSD_ERR_IO (-6)             /* key-frame file missing / unreadable / not the expected format */
 
 const char* lsd_version(void);
 const char* lsd_last_error(void);
@@ -355,6 +356,24 @@ lsd_status_t lsd_keyframe_filter(const float* xyzi_host, int n, float radius, in
                                  float* out_host, int* n_out);
 lsd_status_t lsd_keyframe_filter_dev(const float* xyzi_dev, int n, float radius, int min_neighbors, float min_range, float max_range,
                                      float* out_dev, int* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Key-frame files (row N3) — the on-disk format the reference's map editor and map loader read.
+ * lsd_keyframe_save == dump_keyframe (slam/src/graph_utils.cpp:123-131, bound at slam/src/slam_wrapper.cpp:273) ->
+ * KeyFrame::save (slam/common/keyframe.cpp:118-132): <directory>/cloud.pcd, a PCL binary PCD of PointXYZI (fields
+ * x y z intensity, 16 bytes per point; an empty cloud gets the ASCII header of slam/common/pcd_writer.cpp:9-25), with the
+ * intensity multiplied by 255 (numpy_to_pointcloud(points, 255.0)), and <directory>/data:
+ *     stamp <sec> <nsec>\n estimate\n <4x4>\n odom \n <4x4>\n id <id>\n
+ * the matrices exactly as Eigen prints them (6 significant digits, columns right-aligned to a common width).
+ * lsd_keyframe_load == KeyFrame(id, directory, true) + loadOdom + loadPcd (keyframe.cpp:18-106): timestamp in us, the
+ * "estimate" matrix, intensity / 255.  pose16: row-major 4x4 doubles.  The directory must exist (the caller makes it,
+ * slam/map_manager.py:286-288).  Host-only: no device is touched.
+ * ------------------------------------------------------------------------------------------ */
+lsd_status_t lsd_keyframe_save(const char* directory, uint64_t stamp_us, int64_t id, const float* xyzi_host, int n,
+                               const double* pose16);
+/* xyzi_out may be NULL to query *n; cap = points xyzi_out can hold (LSD_ERR_CAPACITY if the file has more). */
+lsd_status_t lsd_keyframe_load(const char* directory, uint64_t* stamp_us, int64_t* id, double* pose16, float* xyzi_out, int cap,
+                               int* n);
 
 /* ------------------------------------------------------------------------------------------
  * Local-map assembly for localisation (row N2) — replaces the body of Localization::runUpdateLocalMap

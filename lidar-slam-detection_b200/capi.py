@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblsdreg.so")
 
 OK, NO_EFFECTIVE_POINTS, SCAN_TOO_SMALL, MAP_SEEDED = 0, 1, 2, 3
-ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_GRID_OVERFLOW = -1, -2, -3, -4, -5
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_GRID_OVERFLOW, ERR_IO = -1, -2, -3, -4, -5, -6
 STENCIL_CENTER, STENCIL_NEARBY6, STENCIL_NEARBY18, STENCIL_NEARBY26, STENCIL_NEARBY74, STENCIL_EXACT = 0, 6, 18, 26, 74, 1000
 
 
@@ -150,6 +150,8 @@ SIGNATURES = [
     ("lsd_localmap_get", _i, [_vp, _vp, _i, _pi]),
     ("lsd_keyframe_filter", _i, [_vp, _i, _f, _i, _f, _f, _vp, _pi]),
     ("lsd_keyframe_filter_dev", _i, [_vp, _i, _f, _i, _f, _f, _vp, _pi]),
+    ("lsd_keyframe_save", _i, [C.c_char_p, C.c_uint64, C.c_int64, _vp, _i, _vp]),
+    ("lsd_keyframe_load", _i, [C.c_char_p, _pu64, C.POINTER(C.c_int64), _vp, _vp, _i, _pi]),
     ("lsd_lio_init_cov", None, [_vp]),
     ("lsd_state_boxplus", None, [_vp, _vp]),
     ("lsd_state_boxminus", None, [_vp, _vp, _vp]),
@@ -513,6 +515,23 @@ def keyframe_filter(pts, radius: float = 1.0, min_neighbors: int = 3, min_range:
     n = C.c_int()
     check(lib.lsd_keyframe_filter(_ptr(pts), pts.shape[0], radius, min_neighbors, min_range, max_range, _ptr(out), C.byref(n)))
     return out[:n.value].copy()
+
+
+def keyframe_save(directory: str, stamp_us: int, kf_id: int, pts, pose):
+    """dump_keyframe / KeyFrame::save: <directory>/cloud.pcd (binary PCD, intensity x 255) and <directory>/data."""
+    pts = _f32(pts)
+    pose = np.ascontiguousarray(pose, np.float64).reshape(4, 4)
+    check(lib.lsd_keyframe_save(os.fsencode(directory), int(stamp_us), int(kf_id), _ptr(pts), pts.shape[0], _ptr(pose)))
+
+
+def keyframe_load(directory: str):
+    """KeyFrame(id, directory, True).loadOdom() + loadPcd(): -> (stamp_us, id, pose [4,4], points [n,4] with intensity / 255)."""
+    stamp, kid, n = C.c_uint64(), C.c_int64(), C.c_int()
+    pose = np.zeros((4, 4))
+    check(lib.lsd_keyframe_load(os.fsencode(directory), C.byref(stamp), C.byref(kid), _ptr(pose), None, 0, C.byref(n)))
+    pts = np.zeros((max(n.value, 1), 4), np.float32)
+    check(lib.lsd_keyframe_load(os.fsencode(directory), C.byref(stamp), C.byref(kid), _ptr(pose), _ptr(pts), pts.shape[0], C.byref(n)))
+    return stamp.value, kid.value, pose, pts[:n.value]
 
 
 def eskf_predict(state, P, dt, Q, acc, gyro):

@@ -8,3 +8,4 @@
 #include "imu.cu"
 #include "filters.cu"
 #include "localmap.cu"
+#include "keyframe_io.cu"

@@ -10,6 +10,9 @@
 //       -> (T f32[4,4], converged, fitness): what every C++ caller does with the object handed out by
 //       select_registration_method (registrations.hpp:15-16): setInputTarget/Source, align,
 //       hasConverged, getFinalTransformation, getFitnessScore — exposed for Python tests and tools.
+//   dump_keyframe(directory, stamp, id, points_input f32[N,4], pose_input f32[4,4])
+//       slam_wrapper.cpp:273-276 / graph_utils.cpp:123-131 -> KeyFrame::save: cloud.pcd + data in `directory`
+//       (map_manager.py:286-288 calls it once per key frame when a map is saved).
 // Everything else in the reference module (init_slam / process / graph editing / export) drives
 // subsystems that are out of scope and is not provided here.
 #include <pybind11/numpy.h>
@@ -93,6 +96,18 @@ py::tuple registration_align(const std::string& method, farray source, farray ta
   return py::make_tuple(to_numpy(T), conv != 0, fit);
 }
 
+void dump_keyframe(const std::string& directory, uint64_t stamp, int id, farray points_input, farray pose_input) {
+  if (points_input.ndim() != 2 || points_input.shape(1) != 4) throw std::invalid_argument("points_input must be float32 [N,4]");
+  if (pose_input.ndim() != 2 || pose_input.shape(0) != 4 || pose_input.shape(1) != 4) throw std::invalid_argument("pose_input must be [4,4]");
+  double pose[16];
+  for (int i = 0; i < 16; i++) pose[i] = pose_input.data()[i];   // numpy_to_eigen: float -> double, py_utils.cpp
+  const float* pts = points_input.data();
+  const int n = (int)points_input.shape(0);
+  lsd_status_t s;
+  { py::gil_scoped_release release; s = lsd_keyframe_save(directory.c_str(), stamp, id, pts, n, pose); }
+  check(s);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(slam_wrapper, m) {
@@ -100,5 +115,7 @@ PYBIND11_MODULE(slam_wrapper, m) {
   m.def("pointcloud_align", &pointcloud_align, "pointcloud align", py::arg("source_point"), py::arg("target_point"), py::arg("guess"));
   m.def("registration_align", &registration_align, "select_registration_method(method) + align + fitness", py::arg("method"),
         py::arg("source"), py::arg("target"), py::arg("guess"), py::arg("max_corr") = 0.0, py::arg("max_process_time_us") = 0LL);
+  m.def("dump_keyframe", &dump_keyframe, "dump keyframe", py::arg("directory"), py::arg("stamp"), py::arg("id"), py::arg("points_input"),
+        py::arg("pose_input"));
   m.def("lsd_version", []() { return std::string(lsd_version()); });
 }

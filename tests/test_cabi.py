@@ -38,7 +38,7 @@ def test_product_never_touches_the_oracle():
     """No import / include / dlopen of anything under oracle/ from the product tree."""
     pkg = os.path.join(ROOT, "lidar-slam-detection_b200")
     py_imp = re.compile(r"^\s*(import|from)\s+oracle\b", re.M)
-    c_inc = re.compile(r"#\s*include\s*[<\"][^>\"]*oracle|dlopen\s*\([^)]*oracle|liblsd_oracle|libref_(lio|reg|cuda|vfe|ikfom|fastlio)")
+    c_inc = re.compile(r"#\s*include\s*[<\"][^>\"]*oracle|dlopen\s*\([^)]*oracle|liblsd_oracle|libref_(lio|reg|cuda|vfe|ikfom|fastlio|keyframe)")
     for dp, _, files in os.walk(pkg):
         for f in files:
             txt = None
