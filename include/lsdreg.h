@@ -89,6 +89,12 @@ lsd_status_t lsd_knn_query(lsd_map_t* m, const float* q_host, int nq, int k, flo
                            int32_t* out_idx, float* out_d2, int32_t* out_cnt);
 lsd_status_t lsd_knn_query_dev(lsd_map_t* m, const float* q_dev, int nq, int k, float max_sq, int stencil,
                                int32_t* out_idx_dev, float* out_d2_dev, int32_t* out_cnt_dev);
+/* How the batch is mapped onto the GPU (no reference counterpart; results are bit-identical in every shape):
+ * 0 = auto (warp per query below 65 536 queries, thread per query from there on), 1 = warp per query,
+ * 2 = thread per query, 3 = flat (a warp owns 32 queries and walks the compacted list of existing voxels with
+ * all lanes busy; csrc/knn_flat.cuh).  Shapes 2 and 3 serve k in {1, 5} on the fixed stencils; anything else
+ * uses shape 1. */
+lsd_status_t lsd_knn_set_shape(lsd_map_t* m, int shape);
 
 /* ------------------------------------------------------------------------------------------
  * Voxel-grid downsample — replaces pcl::VoxelGrid<PointXYZINormal>::filter as called at
@@ -164,6 +170,9 @@ lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag);
  * output); 0 (default this round) treats such a point as having no neighbours.  Either call
  * empties the rows. */
 lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
+/* Shape of the per-scan neighbour search (no reference counterpart; Nearest_Points is bit-identical either way):
+ * 0 or 1 = one warp per scan point, 3 = flat (a warp owns 32 scan points, csrc/knn_flat.cuh). */
+lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape);
 /* Id given to the next point map_incremental inserts (ids of points inserted through
  * lsd_map_insert(lsd_lio_map(l), ...) are the caller's). */
 lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, laserMapping.cpp:1196 */

@@ -82,6 +82,7 @@ SIGNATURES = [
     ("lsd_map_stream", _i, [_vp, C.POINTER(C.c_void_p)]),
     ("lsd_knn_query", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_knn_query_dev", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
+    ("lsd_knn_set_shape", _i, [_vp, _i]),
     ("lsd_voxelgrid_create", _i, [_pp, _i, _i]),
     ("lsd_voxelgrid_destroy", _i, [_vp]),
     ("lsd_voxelgrid_filter", _i, [_vp, _vp, _i, _f, _vp, _pi]),
@@ -93,6 +94,7 @@ SIGNATURES = [
     ("lsd_lio_set_nearby", _i, [_vp, _i]),
     ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
     ("lsd_lio_set_stale_rows", _i, [_vp, _i]),
+    ("lsd_lio_set_knn_shape", _i, [_vp, _i]),
     ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
     ("lsd_lio_shard_export", _i, [_vp, _i, _i, _i, _i, _vp]),
     ("lsd_lio_shard_connect", _i, [_vp, _vp]),
@@ -254,6 +256,12 @@ class HashVoxelMap:
         cnt = np.empty(nq, np.int32)
         check(lib.lsd_knn_query(self.h, _ptr(q), nq, k, max_sq, stencil, _ptr(idx), _ptr(d2), _ptr(cnt)))
         return idx, d2, cnt
+
+    KNN_AUTO, KNN_WARP, KNN_THREAD, KNN_FLAT = 0, 1, 2, 3
+
+    def set_knn_shape(self, shape: int):
+        """How a batch is mapped onto the GPU (include/lsdreg.h::lsd_knn_set_shape); results do not depend on it."""
+        check(lib.lsd_knn_set_shape(self.h, int(shape)))
 
     def knn_dev(self, q, idx, d2, cnt, k: int = 5, max_sq: float = 5.0, stencil: int = STENCIL_NEARBY18):
         """Device-pointer variant on CUDA torch tensors; asynchronous."""
@@ -646,6 +654,10 @@ class LioFrontend:
     def set_stale_rows(self, flag: bool):
         """Keep Nearest_Points[i] when a search finds nothing, as the reference does (include/lsdreg.h)."""
         check(lib.lsd_lio_set_stale_rows(self.h, int(flag)))
+
+    def set_knn_shape(self, shape: int):
+        """0/1 = one warp per scan point, 3 = flat (include/lsdreg.h::lsd_lio_set_knn_shape)."""
+        check(lib.lsd_lio_set_knn_shape(self.h, int(shape)))
 
     SHARD_BLOB_BYTES = 192
 

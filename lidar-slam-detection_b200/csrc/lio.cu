@@ -350,6 +350,50 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
   }
 }
 
+// The same search in the flat shape (knn_flat.cuh): a warp owns 32 scan points, every lane fetches lines of voxels that
+// exist.  Selected with lsd_lio_set_knn_shape(l, 3); fixed stencils only.  Writes exactly what lio_knn_kernel writes.
+constexpr int kLioFlatWarps = 2;
+__global__ void __launch_bounds__(kLioFlatWarps * 32) lio_knn_flat_kernel(MapView mv, int st_slot, const float4* __restrict__ body,
+                                                                        const int* __restrict__ n_ptr, int cap, LioPose ps,
+                                                                        float4* __restrict__ near, int* __restrict__ near_cnt,
+                                                                        int keep_stale) {
+  __shared__ FlatSmem<true> sm[kLioFlatWarps];
+  const int n = min(*n_ptr, cap);
+  const int n_round = (n + 31) & ~31;  // whole warps: padding lanes take part in the warp-wide steps
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    bool active = i < n;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (active) {
+      const float4 pb = __ldg(body + i);
+      const double bx = pb.x, by = pb.y, bz = pb.z;
+      const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+      const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+      const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+      wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
+      wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
+      wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+      if (mv.shard_world > 1) {
+        const int3 hc = pos2grid(wx, wy, wz, mv.inv_res);
+        if (!shard_owns(mv, hc.x, hc.y)) { near_cnt[i] = -1; active = false; }
+      }
+    }
+    FlatTopK<5, true> best;
+    best.init();
+    int found = 0;
+    flat_search<5, true>(mv, c_stencils[st_slot], wx, wy, wz, active, 5.0f, sm[threadIdx.x >> 5], best, found);
+    if (!active) continue;
+    const int nf = min(found, 5);
+    if (keep_stale && nf == 0) continue;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+      float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      if (r < nf) q = load_loc(mv, best.loc[r]);
+      near[(size_t)i * 5 + r] = q;
+    }
+    near_cnt[i] = nf;
+  }
+}
+
 // Nearest_Points.resize(feats_down_size) (laserMapping.cpp:1273): rows the new scan does not have are destroyed, so a
 // later, larger scan finds them empty.  rows[0] = number of rows alive (the previous scan's size).
 __global__ void lio_resize_rows_kernel(const int* __restrict__ n_ptr, int cap, int* __restrict__ rows, int* __restrict__ near_cnt) {
@@ -608,9 +652,16 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   const double seq = (double)(++l->seq);
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
-    const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
-    lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                                                  (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0);
+    const int keep_stale = (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0;
+    if (l->knn_shape == 3 && stencil != LSD_STENCIL_EXACT) {
+      const int per = kLioFlatWarps * 32, nbf = std::max(1, std::min((l->n_bound + per - 1) / per, 148 * 8));
+      lio_knn_flat_kernel<<<nbf, per, 0, st>>>(l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
+                                               l->d_near_cnt, keep_stale);
+    } else {
+      const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
+      lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                                                    keep_stale);
+    }
     lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                                        l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
                                                                        l->d_partials, l->d_done, l->d_result, seq, l->sc);
@@ -1007,6 +1058,11 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   LSD_CUDA(cudaMemsetAsync(l->d_n + 8, 0, 8, l->stream));
   LSD_CUDA(cudaStreamSynchronize(l->stream));
   l->stale_rows = flag != 0;
+  return LSD_OK;
+}
+lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape) {
+  if (!l || (shape != 0 && shape != 1 && shape != 3)) return LSD_ERR_INVALID;
+  l->knn_shape = shape;
   return LSD_OK;
 }
 lsd_status_t lsd_lio_set_nearby(lsd_lio_t* l, int stencil) {

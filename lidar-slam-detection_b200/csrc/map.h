@@ -12,6 +12,7 @@ struct lsd_map {
   void* scratch = nullptr;  // staging for the host-pointer entry points
   size_t scratch_bytes = 0;
   long long launches = 0;   // kernels launched on behalf of this handle
+  int knn_shape = 0;        // lsd_knn_set_shape: 0 auto, 1 warp/query, 2 thread/query, 3 flat
 };
 
 namespace lsd {

@@ -1,0 +1,76 @@
+"""A/B of the three k-NN shapes (lsd_knn_set_shape: 1 warp/query, 2 thread/query, 3 flat) on the bench map.
+Prints one JSON line per shape (CUDA events on the library stream, L2 flushed before every launch, random and
+voxel-sorted query order) and checks that the three shapes return identical bits.  Also times one LIO scan stream
+with either per-scan search shape (lsd_lio_set_knn_shape).  Under ncu: `-k regex:knn_query_(flat|thread)_kernel`.
+
+    python tools/knn_shapes_probe.py [n_queries] [--no-lio]
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import lsdreg  # noqa: E402
+from lsdreg import synth  # noqa: E402
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+nq = int(args[0]) if args else 1 << 21
+lsdreg.init(0)
+dev = torch.device("cuda", 0)
+m = synth.block_map(bench.MAP_SEED, bench.BLOCKS_X, bench.BLOCKS_Y, bench.SPACING)
+hmap = lsdreg.HashVoxelMap(0.5, 25)
+hmap.insert(m, 0)
+try:
+    with open(os.path.join(bench.ROOT, "MEASURED_PEAKS.json")) as fh:
+        peak = float(json.load(fh)["hbm_gbs"])
+except Exception:
+    peak = 6650.0   # bench.py's fallback
+ALG_BYTES = 680.0   # 56 + 19 (8 + 16 rho), rho = 1.554 on this map
+
+# identical bits first (a smaller batch, host round trip)
+rng = np.random.default_rng(5)
+qs = m[rng.integers(0, m.shape[0], 200003)].copy()
+qs[:, :3] += rng.normal(0.0, 0.1, (qs.shape[0], 3)).astype(np.float32)
+ref = None
+for shape in (2, 1, 3):
+    hmap.set_knn_shape(shape)
+    r = hmap.knn(qs)
+    if ref is None:
+        ref = r
+    else:
+        same = all((a.view(np.int32) == b.view(np.int32)).all() for a, b in zip(ref, r))
+        print(json.dumps({"shape": shape, "identical_to_thread_shape": bool(same)}))
+        assert same, f"shape {shape} differs from the thread-per-query shape"
+
+for shape, name in ((1, "warp"), (2, "thread"), (3, "flat")):
+    hmap.set_knn_shape(shape)
+    out = bench.run_knn_batch(torch, hmap, m, dev, nq)
+    out["shape"] = name
+    for order in ("random", "sorted"):
+        gbs = nq * ALG_BYTES / (out[order + "_us"] * 1e-6) / 1e9
+        out[order + "_alg_GBps"] = round(gbs, 1)
+        if peak:
+            out[order + "_frac"] = round(gbs / peak, 4)
+    print(json.dumps(out))
+hmap.set_knn_shape(0)
+
+if "--no-lio" not in sys.argv:
+    # one scan stream, device time per scan with either search shape (bench.py's step, host-resident scans)
+    steps = [bench.make_step(s) for s in range(12)]
+    from oracle import eskf
+    for shape in (0, 3):
+        f = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
+        f.map.insert(m, 0)
+        f.set_next_id(m.shape[0])
+        f.set_knn_shape(shape)
+        ms, errs = [], []
+        for s, (scan, Rgt, tgt, Rp, tp) in enumerate(steps):
+            x = eskf.State(); x.rot = eskf.R_to_quat(Rp); x.pos = tp.copy()
+            xs, P, info = f.scan(scan, x.to_vec(), lsdreg.init_cov())
+            if s >= 3:
+                ms.append(info["gpu_ms"]); errs.append(float(np.abs(xs[:3] - tgt).max()))
+        print(json.dumps({"lio_knn_shape": shape, "gpu_ms_per_scan_median": float(np.median(ms)), "max_err_m": max(errs)}))
