@@ -401,6 +401,48 @@ lsd_status_t lsd_localmap_update(lsd_localmap_t* h, const double* pose_xyz, int*
 lsd_status_t lsd_localmap_get_dev(lsd_localmap_t* h, const float** xyzi_dev, int* n);
 lsd_status_t lsd_localmap_get(lsd_localmap_t* h, float* xyzi_host, int cap, int* n);
 
+/* ------------------------------------------------------------------------------------------
+ * ScanContext (row N4) — replaces SCManager (slam/common/Scancontext/Scancontext.h:44-98, Scancontext.cpp) as used by
+ * KeyFrame::computeDescriptor (slam/common/keyframe.cpp:165-167), GlobalLocalization::setInitPoseRange / localSearch /
+ * globalSearch / imageSearch (slam/localization/src/global_localization.cpp:104-118,350-398,439-441) and global_alignment
+ * (slam/localization/include/global_alignment.hpp:206-237).  A descriptor is 20 rings x 60 sectors of doubles in Eigen's
+ * own storage order (column-major, MatrixXd::data(): element (ring, sector) at sector * 20 + ring); ring keys are the
+ * row means (20), sector keys the column means (60).  The database (buildRingKeyKDTree's polarcontexts_ + ring-key tree)
+ * lives on the device.  Descriptors are bit-exact; keys and distances follow Eigen's reduction order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_sc lsd_sc_t;
+#define LSD_SC_MAX_QUERIES 64 /* descriptors made / queried per call */
+#define LSD_SC_CANDIDATES 10  /* NUM_CANDIDATES_FROM_TREE, Scancontext.h:78 */
+lsd_status_t lsd_sc_create(lsd_sc_t** out, int db_capacity);
+lsd_status_t lsd_sc_destroy(lsd_sc_t* s);
+/* SCManager::makeScancontext(cloud, dx, dy) + makeRingkey / makeSectorkeyFromScancontext for n_off offsets of ONE cloud
+ * in one pass (offsets_xy [n_off][2]; NULL = the single offset (0, 0); the reference's search_trans has 9).  Outputs may
+ * be NULL: desc_out [n_off][1200], ringkey_out [n_off][20], sectorkey_out [n_off][60].  The descriptors stay on the
+ * device as query slots 0..n_off-1 for lsd_sc_query(NULL), lsd_sc_detect_* and lsd_sc_db_add_made. */
+lsd_status_t lsd_sc_make(lsd_sc_t* s, const float* xyzi_host, int n, const double* offsets_xy, int n_off, double* desc_out,
+                         double* ringkey_out, double* sectorkey_out);
+lsd_status_t lsd_sc_make_dev(lsd_sc_t* s, const float* xyzi_dev, int n, const double* offsets_xy, int n_off, double* desc_out,
+                             double* ringkey_out, double* sectorkey_out);
+/* buildRingKeyKDTree(polarcontext_invkeys_mat, polarcontexts): clear, then add the key frames' descriptors (their ring
+ * keys are recomputed on the device); lsd_sc_db_add_made appends query slot `slot` of the last lsd_sc_make without a
+ * host round trip.  Database index = order of insertion. */
+lsd_status_t lsd_sc_db_clear(lsd_sc_t* s);
+lsd_status_t lsd_sc_db_add(lsd_sc_t* s, const double* desc_host, int n);
+lsd_status_t lsd_sc_db_add_made(lsd_sc_t* s, int slot);
+lsd_status_t lsd_sc_db_size(lsd_sc_t* s, int* n);
+/* The retrieval common to detectClosestMatch and detectCandidateMatch (Scancontext.cpp:280-299): for each of nq queries
+ * (desc_host [nq][1200], or NULL = the slots of the last lsd_sc_make) the min(10, database size) entries with the
+ * nearest ring keys, ascending, each scored with distanceBtnScanContext.  cand_idx / cand_dist / cand_shift are
+ * [nq][10], padded with -1 / 1e7 / 0; n_cand [nq]. */
+lsd_status_t lsd_sc_query(lsd_sc_t* s, const double* desc_host_or_null, int nq, int32_t* cand_idx, double* cand_dist, int32_t* cand_shift,
+                          int32_t* n_cand);
+/* SCManager::distanceBtnScanContext(sc1, sc2) for n_pairs pairs (localSearch, imageSearch): dist, argmin shift. */
+lsd_status_t lsd_sc_distance(lsd_sc_t* s, const double* desc_a_host, const double* desc_b_host, int n_pairs, double* dist, int32_t* shift);
+/* detectClosestMatch / detectCandidateMatch for query slot `slot`: loop id (-1: none below dist_thres = SC_DIST_THRES),
+ * yaw = deg2rad(shift * 6 deg), score = the smallest distance (untouched on an empty database, like the reference). */
+lsd_status_t lsd_sc_detect_closest(lsd_sc_t* s, int slot, double dist_thres, int32_t* loop_id, float* yaw_rad, double* score);
+lsd_status_t lsd_sc_detect_candidates(lsd_sc_t* s, int slot, double dist_thres, int32_t* idx10, float* yaw10, float* dist10, int32_t* n);
+
 /* Host-side manifold helpers (exported so bindings/tests use the same algebra as the filter).
  * IMU_Processing.hpp:224-230 initial covariance; state_ikfom boxplus/boxminus. */
 void lsd_lio_init_cov(double* P529);

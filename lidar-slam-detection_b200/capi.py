@@ -144,6 +144,18 @@ SIGNATURES = [
     ("lsd_imu_get_cloud", _i, [_vp, _vp, _i, _pi]),
     ("lsd_imu_get_poses", _i, [_vp, _vp, _i, _pi]),
     ("lsd_eskf_predict", _i, [_vp, _vp, _d, _vp, _vp, _vp]),
+    ("lsd_sc_create", _i, [_pp, _i]),
+    ("lsd_sc_destroy", _i, [_vp]),
+    ("lsd_sc_make", _i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    ("lsd_sc_make_dev", _i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    ("lsd_sc_db_clear", _i, [_vp]),
+    ("lsd_sc_db_add", _i, [_vp, _vp, _i]),
+    ("lsd_sc_db_add_made", _i, [_vp, _i]),
+    ("lsd_sc_db_size", _i, [_vp, _pi]),
+    ("lsd_sc_query", _i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    ("lsd_sc_distance", _i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    ("lsd_sc_detect_closest", _i, [_vp, _i, _d, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(_d)]),
+    ("lsd_sc_detect_candidates", _i, [_vp, _i, _d, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
     ("lsd_localmap_create", _i, [_pp, _d, _d]),
     ("lsd_localmap_destroy", _i, [_vp]),
     ("lsd_localmap_add_keyframe", _i, [_vp, _vp, _i, _vp]),
@@ -514,6 +526,85 @@ class LocalMap:
         p, n = C.c_void_p(), C.c_int()
         check(lib.lsd_localmap_get_dev(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+
+class ScanContext:
+    """SCManager (slam/common/Scancontext/Scancontext.cpp) on the device: descriptors, database, retrieval.
+    Descriptors are [60, 20] (sector, ring) float64 arrays = Eigen's column-major 20 x 60 MatrixXd."""
+
+    MAX_QUERIES, CANDIDATES = 64, 10
+    SEARCH_TRANS = [(0, 0), (-4, 0), (4, 0), (0, -4), (0, 4), (-4, -4), (-4, 4), (4, -4), (4, 4)]   # global_localization.cpp:390-392
+
+    def __init__(self, db_capacity: int = 16384, dist_thres: float = 0.2):
+        self.h = C.c_void_p()
+        self.dist_thres = dist_thres   # SC_DIST_THRES
+        check(lib.lsd_sc_create(C.byref(self.h), db_capacity))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.lsd_sc_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def make(self, pts, offsets=None, dev: bool = False):
+        """makeScancontext + keys for every offset -> (desc [n_off,60,20], ringkey [n_off,20], sectorkey [n_off,60])."""
+        off = np.ascontiguousarray(np.zeros((1, 2)) if offsets is None else offsets, np.float64).reshape(-1, 2)
+        k = off.shape[0]
+        desc, rk, sk = np.empty((k, 60, 20)), np.empty((k, 20)), np.empty((k, 60))
+        if dev:
+            check(lib.lsd_sc_make_dev(self.h, _ptr(pts), pts.shape[0], _ptr(off), k, _ptr(desc), _ptr(rk), _ptr(sk)))
+        else:
+            pts = _f32(pts)
+            check(lib.lsd_sc_make(self.h, _ptr(pts), pts.shape[0], _ptr(off), k, _ptr(desc), _ptr(rk), _ptr(sk)))
+        return desc, rk, sk
+
+    def db_clear(self):
+        check(lib.lsd_sc_db_clear(self.h))
+
+    def db_add(self, descs):
+        d = np.ascontiguousarray(descs, np.float64).reshape(-1, 1200)
+        check(lib.lsd_sc_db_add(self.h, _ptr(d), d.shape[0]))
+
+    def db_add_made(self, slot: int = 0):
+        check(lib.lsd_sc_db_add_made(self.h, slot))
+
+    def db_size(self) -> int:
+        n = C.c_int()
+        check(lib.lsd_sc_db_size(self.h, C.byref(n)))
+        return n.value
+
+    def query(self, descs=None, nq: int | None = None):
+        """-> (cand_idx [nq,10], cand_dist [nq,10], cand_shift [nq,10], n_cand [nq]); descs None = the last make()."""
+        d = None
+        if descs is not None:
+            d = np.ascontiguousarray(descs, np.float64).reshape(-1, 1200)
+            nq = d.shape[0]
+        idx, dist = np.empty((nq, 10), np.int32), np.empty((nq, 10))
+        sh, nc = np.empty((nq, 10), np.int32), np.empty(nq, np.int32)
+        check(lib.lsd_sc_query(self.h, _ptr(d) if d is not None else None, nq, _ptr(idx), _ptr(dist), _ptr(sh), _ptr(nc)))
+        return idx, dist, sh, nc
+
+    def distance(self, a, b):
+        """distanceBtnScanContext for pairs -> (dist [n], shift [n])."""
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 1200)
+        b = np.ascontiguousarray(b, np.float64).reshape(-1, 1200)
+        n = a.shape[0]
+        dist, sh = np.empty(n), np.empty(n, np.int32)
+        check(lib.lsd_sc_distance(self.h, _ptr(a), _ptr(b), n, _ptr(dist), _ptr(sh)))
+        return dist, sh
+
+    def detect_closest(self, slot: int = 0):
+        """detectClosestMatch for query slot `slot` -> (loop id or -1, yaw rad, score); score 1.0 on an empty database
+        (what globalSearch passes in, global_localization.cpp:397)."""
+        lid, yaw, score = C.c_int32(), C.c_float(), C.c_double(1.0)
+        check(lib.lsd_sc_detect_closest(self.h, slot, self.dist_thres, C.byref(lid), C.byref(yaw), C.byref(score)))
+        return lid.value, yaw.value, score.value
+
+    def detect_candidates(self, slot: int = 0):
+        idx, yaw, dist, n = np.empty(10, np.int32), np.empty(10, np.float32), np.empty(10, np.float32), C.c_int32()
+        check(lib.lsd_sc_detect_candidates(self.h, slot, self.dist_thres, _ptr(idx), _ptr(yaw), _ptr(dist), C.byref(n)))
+        return [(int(idx[i]), float(yaw[i]), float(dist[i])) for i in range(n.value)]
 
 
 def keyframe_filter(pts, radius: float = 1.0, min_neighbors: int = 3, min_range: float = 0.0, max_range: float = 1e9):

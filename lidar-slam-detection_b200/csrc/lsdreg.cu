@@ -9,3 +9,4 @@
 #include "filters.cu"
 #include "localmap.cu"
 #include "keyframe_io.cu"
+#include "scancontext.cu"

@@ -13,7 +13,7 @@ from oracle import scancontext as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REF = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "libref_keyframe.so")
-pytestmark = pytest.mark.skipif(not os.path.exists(_REF), reason="oracle/_ref/libref_keyframe.so not built (needs /root/reference)")
+needs_ref = pytest.mark.skipif(not os.path.exists(_REF), reason="oracle/_ref/libref_keyframe.so not built (needs /root/reference)")
 
 _pd, _pf, _pi = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
 
@@ -74,6 +74,7 @@ def world(ref):
     return dict(clouds=clouds, descs=descs, n_places=n_places)
 
 
+@needs_ref
 def test_descriptor_and_keys_bit_exact(ref, world):
     rng = np.random.default_rng(1)
     for k, c in enumerate(world["clouds"]):
@@ -91,6 +92,7 @@ def test_descriptor_and_keys_bit_exact(ref, world):
         np.testing.assert_array_equal(S.make(c), d_ref)
 
 
+@needs_ref
 def test_pairwise_distance_bit_exact(ref, world):
     descs = world["descs"]
     n = len(descs)
@@ -111,6 +113,7 @@ def test_pairwise_distance_bit_exact(ref, world):
     assert d == float(dist[0]) == 10000000.0 and s == int(shift[0]) == 0
 
 
+@needs_ref
 def test_retrieval_matches_the_reference(ref, world):
     descs, n_places = world["descs"], world["n_places"]
     db_descs = descs[:n_places]
@@ -149,3 +152,96 @@ def test_retrieval_matches_the_reference(ref, world):
     assert ref.ref_sc_detect_closest(h, _p(np.ascontiguousarray(descs[0]), _pd), _p(yaw, _pf), _p(score, _pd)) == -1
     assert S.Database([]).detect_closest(descs[0])[0] == -1
     ref.ref_sc_db_destroy(h)
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    """The kernels' arithmetic (csrc/sc_math.h) compiled for the host: tests/sc_host_harness.cpp."""
+    import subprocess
+    out = str(tmp_path_factory.mktemp("sc") / "libsc_host_harness.so")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared", "-o", out,
+                           os.path.join(_HERE, "sc_host_harness.cpp")])
+    H = C.CDLL(out)
+    H.h_sc_make.argtypes = [_pf, C.c_int, C.c_double, C.c_double, _pd, _pd, _pf, _pd, _pd]
+    H.h_sc_make.restype = None
+    H.h_sc_distance.argtypes = [_pd, _pd, _pd, _pi]
+    H.h_sc_distance.restype = None
+    H.h_sc_ring_knn.argtypes = [_pf, C.c_int, _pf, _pi, _pf]
+    H.h_sc_ring_knn.restype = C.c_int
+    H.h_sc_yaw.argtypes = [C.c_int]
+    H.h_sc_yaw.restype = C.c_float
+    return H
+
+
+@needs_ref
+def test_kernel_arithmetic_on_the_host(ref, harness, world):
+    """csrc/sc_math.h (what the CUDA kernels execute) against the compiled reference: descriptor, keys, pair distance and
+    shift bit for bit; ring-key candidates as a set."""
+    H = harness
+    descs = []
+    for k, c in enumerate(world["clouds"]):
+        dx, dy = S.SEARCH_TRANS[k % 9]
+        d_ref, rk_ref, sk_ref = ref_make(ref, c, dx, dy)
+        d, rk, rkf, vk, nm = np.zeros(1200), np.zeros(20), np.zeros(20, np.float32), np.zeros(60), np.zeros(60)
+        H.h_sc_make(_p(c, _pf), c.shape[0], dx, dy, _p(d, _pd), _p(rk, _pd), _p(rkf, _pf), _p(vk, _pd), _p(nm, _pd))
+        np.testing.assert_array_equal(d.reshape(60, 20), d_ref)
+        np.testing.assert_array_equal(rk, rk_ref)
+        np.testing.assert_array_equal(vk, sk_ref)
+        np.testing.assert_array_equal(rkf, rk_ref.astype(np.float32))
+        descs.append(d.copy())
+    edge = np.array([[0, 0, 1, 0], [5, 0, 1, 0], [0, 5, 2, 0], [-5, 0, 3, 0], [0, -5, 4, 0], [80.0, 0, 1, 0], [56.6, 56.6, 9, 0],
+                     [79.9999, 0.01, 2, 0], [3, 3, -2000, 0], [-1e-30, 1e-30, 0.25, 0], [1e-20, -1e-20, 0.5, 0],
+                     [np.nan, 1, 1, 0], [1, np.nan, 1, 0], [np.inf, 1, 1, 0]], np.float32)
+    for c in (np.zeros((0, 4), np.float32), edge):
+        d_ref, _, _ = ref_make(ref, c)
+        d, rk, rkf, vk, nm = np.zeros(1200), np.zeros(20), np.zeros(20, np.float32), np.zeros(60), np.zeros(60)
+        H.h_sc_make(_p(c, _pf), c.shape[0], 0.0, 0.0, _p(d, _pd), _p(rk, _pd), _p(rkf, _pf), _p(vk, _pd), _p(nm, _pd))
+        np.testing.assert_array_equal(d.reshape(60, 20), d_ref)
+    rng = np.random.default_rng(4)
+    n = len(descs)
+    zero = np.zeros(1200)
+    for a, b in [(int(x), int(y)) for x, y in rng.integers(0, n, (80, 2))] + [(0, 0), (-1, 0), (0, -1)]:
+        A = zero if a < 0 else descs[a]
+        B = zero if b < 0 else descs[b]
+        dr, sr = np.zeros(1), np.zeros(1, np.int32)
+        ref.ref_sc_distance(_p(A, _pd), _p(B, _pd), _p(dr, _pd), _p(sr, _pi))
+        dh, sh = np.zeros(1), np.zeros(1, np.int32)
+        H.h_sc_distance(_p(A, _pd), _p(B, _pd), _p(dh, _pd), _p(sh, _pi))
+        assert dh[0] == dr[0] and sh[0] == sr[0], (a, b, dh, dr, sh, sr)
+    # ring-key candidates against the reference's nanoflann tree
+    n_db = world["n_places"]
+    flat = np.ascontiguousarray(np.stack(descs[:n_db]))
+    h = ref.ref_sc_db_create(_p(flat, _pd), n_db, 0.2)
+    keys = np.ascontiguousarray(np.stack([S.ringkey(d.reshape(60, 20)).astype(np.float32) for d in descs[:n_db]]))
+    for qd in descs:
+        q = S.ringkey(qd.reshape(60, 20)).astype(np.float32)
+        ri, rd = np.zeros(10, np.int32), np.zeros(10, np.float32)
+        k = ref.ref_sc_ring_knn(h, _p(q, _pf), _p(ri, _pi), _p(rd, _pf), 10)
+        hi, hd = np.zeros(10, np.int32), np.zeros(10, np.float32)
+        kh = H.h_sc_ring_knn(_p(keys, _pf), n_db, _p(q, _pf), _p(hi, _pi), _p(hd, _pf))
+        assert k == kh
+        np.testing.assert_array_equal(np.sort(ri[:k]), np.sort(hi[:k]))
+        np.testing.assert_array_equal(np.sort(rd[:k]), np.sort(hd[:k]))
+        assert (np.diff(hd[:k]) >= 0).all()
+    ref.ref_sc_db_destroy(h)
+    for s in range(60):
+        assert H.h_sc_yaw(s) == S._deg2rad(s * S.UNIT_SECTORANGLE)
+
+
+def test_restatement_matches_the_committed_golden_vectors():
+    """tests/golden/scancontext_ref.npz (made by the compiled reference, tests/golden/make_golden_scancontext.py) — the
+    check that still runs where /root/reference and oracle/_ref do not exist."""
+    g = np.load(os.path.join(_HERE, "golden", "scancontext_ref.npz"))
+    K = g["clouds_n"].shape[0]
+    for k in range(K):
+        c = g["clouds"][k][: g["clouds_n"][k]]
+        d = S.make(c, *g["offsets"][k])
+        np.testing.assert_array_equal(d.reshape(-1), g["desc"][k])
+        np.testing.assert_array_equal(S.ringkey(d), g["ringkey"][k])
+        np.testing.assert_array_equal(S.sectorkey(d), g["sectorkey"][k])
+    for (a, b), dist, shift in zip(g["pairs"], g["pair_dist"], g["pair_shift"]):
+        assert S.distance(g["desc"][a].reshape(60, 20), g["desc"][b].reshape(60, 20)) == (dist, shift)
+    db = S.Database(g["desc"][: int(g["db_n"])], 0.2)
+    for k in range(K):
+        lid, yaw, score = db.detect_closest(g["desc"][k].reshape(60, 20))
+        assert (lid, yaw, score) == tuple(g["closest"][k]), k
