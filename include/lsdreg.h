@@ -349,6 +349,9 @@ lsd_status_t lsd_imu_get_cloud_dev(lsd_imu_t* m, const float** xyzi_dev, int* n,
 lsd_status_t lsd_imu_get_cloud(lsd_imu_t* m, float* xyzi_host, int cap, int* n);
 /* Parity tap: the IMUpose list of the last scan, double [n, 22] = (offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]). */
 lsd_status_t lsd_imu_get_poses(lsd_imu_t* m, double* poses22, int cap, int* n);
+/* ImuProcess::start_state_point (the state at the scan start, IMU_Processing.hpp:234,266) and mean_acc_norm (:206): what
+ * fastlio_state() and fastlio_odometry() hand to the caller (laserMapping.cpp:690-738).  Host only. */
+lsd_status_t lsd_imu_get_start_state(lsd_imu_t* m, double* state26, double* mean_acc_norm);
 /* esekf::predict alone (host, no GPU): Q144 = 12x12 process noise (ng, na, nbg, nba). */
 lsd_status_t lsd_eskf_predict(double* state26_inout, double* P529_inout, double dt, const double* Q144, const double* acc3,
                               const double* gyro3);
@@ -400,6 +403,47 @@ lsd_status_t lsd_localmap_add_keyframe(lsd_localmap_t* h, const float* xyzi_map_
 lsd_status_t lsd_localmap_update(lsd_localmap_t* h, const double* pose_xyz, int* n_points, int* n_keyframes_in_radius, double* nearest_dist);
 lsd_status_t lsd_localmap_get_dev(lsd_localmap_t* h, const float** xyzi_dev, int* n);
 lsd_status_t lsd_localmap_get(lsd_localmap_t* h, float* xyzi_host, int cap, int* n);
+
+/* ------------------------------------------------------------------------------------------
+ * The LIO seam (SURVEY.md 8b "C++ seam 1") — the eight free functions slam/mapping/fastlio/src/fastlio.cpp:9-16 binds,
+ * with the reference's file-scope state (laserMapping.cpp:60-200) in a handle.  Same contract: any thread may enqueue,
+ * one consumer thread calls lsd_fastlio_main (fastlio.cpp:263-277).
+ *   fastlio_init(extT, extR, filter_num, max_point_num, scan_period, undistort)   -> lsd_fastlio_create   (:1025-1124)
+ *   fastlio_imu_enqueue(ImuType)              -> lsd_fastlio_imu_enqueue (stamp s, gyr rad/s, acc m/s^2; / 9.81 inside, :414)
+ *   fastlio_ins_enqueue(bool, RTKType)        -> lsd_fastlio_ins_enqueue (ENU velocity, heading / pitch / roll in degrees, :418-443)
+ *   fastlio_pcl_enqueue(PointCloudAttrPtr&)   -> lsd_fastlio_pcl_enqueue (xyzi [n,4], PointAttr::stamp [n] in us relative to the
+ *                                                header stamp; Preprocess::velodyne_handler's decimation and blind zone inside)
+ *   fastlio_main()                            -> lsd_fastlio_main: 1 = a package was consumed, 0 = nothing ready, < 0 = error
+ *   fastlio_odometry(odom_s, odom_e)          -> lsd_fastlio_odometry (row-major 4x4)
+ *   fastlio_state()                           -> lsd_fastlio_state (20 doubles, :714-738)
+ *   fastlio_is_init()                         -> lsd_fastlio_is_init
+ * lsd_fastlio_main = sync_packages (:445-520) -> ImuProcess::Process (lsd_imu_process) -> flg_EKF_inited, NEARBY74 -> NEARBY18
+ * after 1 s -> lsd_lio_scan_dev with the reference's stale Nearest_Points rows on.  The engines are created on the first
+ * package that needs them; everything before that (queues, decimation, package synchronisation) is host code and works
+ * without a device — lsd_fastlio_pop_package is the parity tap on it.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lsd_fastlio lsd_fastlio_t;
+lsd_status_t lsd_fastlio_create(lsd_fastlio_t** out, const double* extT3, const double* extR9, int filter_num, int max_point_num,
+                                double scan_period, int undistort);
+/* optional, before the first lsd_fastlio_main: map table size (default 2^22 lines) and raw scan capacity (default 262144) */
+lsd_status_t lsd_fastlio_set_capacity(lsd_fastlio_t* f, int map_log2_lines, int max_scan_points);
+lsd_status_t lsd_fastlio_destroy(lsd_fastlio_t* f);
+lsd_status_t lsd_fastlio_imu_enqueue(lsd_fastlio_t* f, double stamp_s, const double* gyr3, const double* acc3);
+lsd_status_t lsd_fastlio_ins_enqueue(lsd_fastlio_t* f, int rtk_valid, int is_wheel, uint64_t timestamp_us, const double* vel_enu3,
+                                     double heading_deg, double pitch_deg, double roll_deg);
+lsd_status_t lsd_fastlio_pcl_enqueue(lsd_fastlio_t* f, const float* xyzi, const uint32_t* stamp_us, int n, uint64_t header_stamp_us);
+int lsd_fastlio_main(lsd_fastlio_t* f);
+lsd_status_t lsd_fastlio_odometry(lsd_fastlio_t* f, double* odom_start16, double* odom_end16);
+lsd_status_t lsd_fastlio_state(lsd_fastlio_t* f, double* out20);
+int lsd_fastlio_is_init(lsd_fastlio_t* f);
+/* What the last lsd_fastlio_main did: the lsd_lio_scan status (LSD_OK, LSD_MAP_SEEDED, LSD_SCAN_TOO_SMALL,
+ * LSD_NO_EFFECTIVE_POINTS) or LSD_IMU_INITIALIZING, and the scan's counters; kf.get_x() / kf.get_P(); the LIO handle. */
+lsd_status_t lsd_fastlio_last(lsd_fastlio_t* f, int* status, lsd_lio_info_t* info);
+lsd_status_t lsd_fastlio_get_filter(lsd_fastlio_t* f, double* state26, double* P529);
+lsd_lio_t* lsd_fastlio_lio(lsd_fastlio_t* f);
+/* Parity tap, host only: sync_packages alone — pops the next package instead of processing it.  1 = filled, 0 = none ready. */
+int lsd_fastlio_pop_package(lsd_fastlio_t* f, double* lidar_beg_time, double* lidar_end_time, int* n_points, float* xyzi, float* time_ms,
+                            int cap_points, int* n_imu, double* imu7, int cap_imu, int* have_ins, double* ins_vel3);
 
 /* ------------------------------------------------------------------------------------------
  * ScanContext (row N4) — replaces SCManager (slam/common/Scancontext/Scancontext.h:44-98, Scancontext.cpp) as used by

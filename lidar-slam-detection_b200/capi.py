@@ -144,6 +144,21 @@ SIGNATURES = [
     ("lsd_imu_get_cloud", _i, [_vp, _vp, _i, _pi]),
     ("lsd_imu_get_poses", _i, [_vp, _vp, _i, _pi]),
     ("lsd_eskf_predict", _i, [_vp, _vp, _d, _vp, _vp, _vp]),
+    ("lsd_imu_get_start_state", _i, [_vp, _vp, C.POINTER(_d)]),
+    ("lsd_fastlio_create", _i, [_pp, _vp, _vp, _i, _i, _d, _i]),
+    ("lsd_fastlio_set_capacity", _i, [_vp, _i, _i]),
+    ("lsd_fastlio_destroy", _i, [_vp]),
+    ("lsd_fastlio_imu_enqueue", _i, [_vp, _d, _vp, _vp]),
+    ("lsd_fastlio_ins_enqueue", _i, [_vp, _i, _i, C.c_uint64, _vp, _d, _d, _d]),
+    ("lsd_fastlio_pcl_enqueue", _i, [_vp, _vp, _vp, _i, C.c_uint64]),
+    ("lsd_fastlio_main", _i, [_vp]),
+    ("lsd_fastlio_odometry", _i, [_vp, _vp, _vp]),
+    ("lsd_fastlio_state", _i, [_vp, _vp]),
+    ("lsd_fastlio_is_init", _i, [_vp]),
+    ("lsd_fastlio_last", _i, [_vp, _pi, C.POINTER(LioInfo)]),
+    ("lsd_fastlio_get_filter", _i, [_vp, _vp, _vp]),
+    ("lsd_fastlio_lio", _vp, [_vp]),
+    ("lsd_fastlio_pop_package", _i, [_vp, C.POINTER(_d), C.POINTER(_d), _pi, _vp, _vp, _i, _pi, _vp, _i, _pi, _vp]),
     ("lsd_sc_create", _i, [_pp, _i]),
     ("lsd_sc_destroy", _i, [_vp]),
     ("lsd_sc_make", _i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
@@ -526,6 +541,85 @@ class LocalMap:
         p, n = C.c_void_p(), C.c_int()
         check(lib.lsd_localmap_get_dev(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+
+class FastLio:
+    """The reference's LIO seam (fastlio.cpp:9-16: fastlio_init / _imu_enqueue / _ins_enqueue / _pcl_enqueue / fastlio_main /
+    _odometry / _state / _is_init) on lsd_fastlio_*.  Same feeding protocol as oracle/fastlio.py's RefFastLio."""
+
+    def __init__(self, ext_R=None, ext_t=None, filter_num=1, max_point_num=-1, scan_period=0.1, undistort=True,
+                 map_log2_lines=None, max_scan_points=None):
+        R = np.ascontiguousarray(np.eye(3) if ext_R is None else ext_R, np.float64).reshape(-1)
+        t = np.ascontiguousarray(np.zeros(3) if ext_t is None else ext_t, np.float64)
+        self.h = C.c_void_p()
+        check(lib.lsd_fastlio_create(C.byref(self.h), _ptr(t), _ptr(R), filter_num, max_point_num, scan_period, int(undistort)))
+        if map_log2_lines is not None or max_scan_points is not None:
+            check(lib.lsd_fastlio_set_capacity(self.h, map_log2_lines or 22, max_scan_points or 262144))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.lsd_fastlio_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def push_imu(self, stamp, gyr, acc_g):
+        """acc in units of g like the rest of the package; the entry point takes m/s^2 (fastlio_imu_enqueue divides by 9.81)."""
+        g = np.ascontiguousarray(gyr, np.float64)
+        a = np.ascontiguousarray(acc_g, np.float64) * 9.81
+        check(lib.lsd_fastlio_imu_enqueue(self.h, float(stamp), _ptr(g), _ptr(a)))
+
+    def push_ins(self, timestamp_us, vel_enu, heading_deg, pitch_deg, roll_deg, rtk_valid=True, is_wheel=False):
+        v = np.ascontiguousarray(vel_enu, np.float64)
+        check(lib.lsd_fastlio_ins_enqueue(self.h, int(rtk_valid), int(is_wheel), int(timestamp_us), _ptr(v), heading_deg, pitch_deg, roll_deg))
+
+    def push_scan(self, xyzi, stamp_us, header_stamp_us):
+        xyzi = _f32(xyzi)
+        st = np.ascontiguousarray(stamp_us, np.uint32)
+        check(lib.lsd_fastlio_pcl_enqueue(self.h, _ptr(xyzi), _ptr(st), xyzi.shape[0], int(header_stamp_us)))
+
+    def step(self) -> bool:
+        """fastlio_main()"""
+        return bool(check(lib.lsd_fastlio_main(self.h)))
+
+    def last(self):
+        st, info = C.c_int(), LioInfo()
+        check(lib.lsd_fastlio_last(self.h, C.byref(st), C.byref(info)))
+        return dict(info.as_dict(), status=st.value)
+
+    def filter(self):
+        x, P = np.zeros(26), np.zeros((23, 23))
+        check(lib.lsd_fastlio_get_filter(self.h, _ptr(x), _ptr(P)))
+        return x, P
+
+    def odometry(self):
+        a, b = np.zeros((4, 4)), np.zeros((4, 4))
+        check(lib.lsd_fastlio_odometry(self.h, _ptr(a), _ptr(b)))
+        return a, b
+
+    def state(self) -> np.ndarray:
+        out = np.zeros(20)
+        check(lib.lsd_fastlio_state(self.h, _ptr(out)))
+        return out
+
+    @property
+    def initialised(self) -> bool:
+        return bool(lib.lsd_fastlio_is_init(self.h))
+
+    def lio_handle(self):
+        return lib.lsd_fastlio_lio(self.h)
+
+    def pop_package(self, cap_points=400000, cap_imu=4096):
+        """Parity tap (host only): sync_packages alone -> dict or None."""
+        beg, end, n, ni, hi = C.c_double(), C.c_double(), C.c_int(), C.c_int(), C.c_int()
+        xyzi, t = np.zeros((cap_points, 4), np.float32), np.zeros(cap_points, np.float32)
+        imu, iv = np.zeros((cap_imu, 7)), np.zeros(3)
+        r = check(lib.lsd_fastlio_pop_package(self.h, C.byref(beg), C.byref(end), C.byref(n), _ptr(xyzi), _ptr(t), cap_points, C.byref(ni),
+                                              _ptr(imu), cap_imu, C.byref(hi), _ptr(iv)))
+        if not r:
+            return None
+        return dict(lidar_beg_time=beg.value, lidar_end_time=end.value, points=xyzi[:n.value].copy(), time_ms=t[:n.value].copy(),
+                    imu=imu[:ni.value].copy(), ins_vel=iv.copy() if hi.value else None)
 
 
 class ScanContext:

@@ -216,6 +216,8 @@ struct lsd_imu {
   double last_lidar_end_time = 0.0, first_lidar_time = 0.0;
   int init_iter_num = 1;
   bool b_first_frame = true, imu_need_init = true, state_init_done = false;
+  double start_state[26];        // start_state_point (IMU_Processing.hpp:58): a default state_ikfom until the first assignment
+  double mean_acc_norm = 0.0;    // IMU_Processing.hpp:59,206
   std::vector<lsd::ImuPoseDev> poses;
   // device staging
   float4 *d_in = nullptr, *d_out = nullptr;
@@ -289,6 +291,7 @@ static void imu_init(lsd_imu* m, const double* imu, int n_imu, const double* ins
   m->init_iter_num = N;
   if (ins_vel) for (int i = 0; i < 3; i++) m->vel_last[i] = ins_vel[i];
   const double na = norm3(m->mean_acc);
+  m->mean_acc_norm = na;
   if (fabs(na - 1.0) > 0.1 || norm3(m->mean_gyr) > 10.0 / 180.0 * M_PI) { m->b_first_frame = true; return; }  // "init is not stable, reset"
   double g[3] = {-m->mean_acc[0] / na * kGms2, -m->mean_acc[1] / na * kGms2, -m->mean_acc[2] / na * kGms2};
   const double gn = norm3(g);
@@ -298,6 +301,7 @@ static void imu_init(lsd_imu* m, const double* imu, int n_imu, const double* ins
   eskf::init_cov(P);
   memcpy(m->last_imu, imu + 7 * (n_imu - 1), sizeof(m->last_imu));
   m->last_lidar_end_time = end;
+  memcpy(m->start_state, x, sizeof(m->start_state));   // start_state_point = kf_state.get_x(), :234
 }
 
 // forward propagation of UndistortPcl, :237-361: fills m->poses, leaves x / P at the scan end
@@ -311,6 +315,7 @@ static void imu_forward(lsd_imu* m, const double* imu, int n_imu, double beg, do
     after_predict(m, x, acc, gyr);
     m->last_lidar_end_time = beg;
   }
+  memcpy(m->start_state, x, sizeof(m->start_state));   // start_state_point = kf_state.get_x(), :266
   m->poses.clear();
   push_pose(m, 0.0, x);
   const double imu_end_time = imu[7 * (n_imu - 1)];
@@ -424,6 +429,8 @@ lsd_status_t lsd_imu_create(lsd_imu_t** out, const lsd_imu_params_t* p) {
   for (int i = 0; i < 6; i++) m->Q[i * 13] = 0.0001;    // process_noise_cov(), use-ikfom.hpp:36-44
   for (int i = 6; i < 12; i++) m->Q[i * 13] = 0.00001;
   imu_reset(m);
+  memset(m->start_state, 0, sizeof(m->start_state));   // state_ikfom(): identity rotations, grav = S2() = length * e_x
+  m->start_state[eskf::S_ROT + 3] = 1.0; m->start_state[eskf::S_OFFR + 3] = 1.0; m->start_state[eskf::S_GRAV] = eskf::kS2Len;
   cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&m->h_poses, kMaxImuPoses * sizeof(ImuPoseDev), cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&m->d_poses, m->h_poses, 0);
@@ -499,6 +506,14 @@ lsd_status_t lsd_imu_get_cloud(lsd_imu_t* m, float* xyzi_host, int cap, int* n) 
   const int c = std::min(cap, m->n_out);
   if (c > 0) LSD_CUDA(cudaMemcpyAsync(xyzi_host, m->d_out, (size_t)c * 16, cudaMemcpyDeviceToHost, m->stream));
   LSD_CUDA(cudaStreamSynchronize(m->stream));
+  return LSD_OK;
+}
+
+// ImuProcess::start_state_point and mean_acc_norm: what fastlio_state / fastlio_odometry read (laserMapping.cpp:690-738)
+lsd_status_t lsd_imu_get_start_state(lsd_imu_t* m, double* state26, double* mean_acc_norm) {
+  if (!m || !state26) return LSD_ERR_INVALID;
+  memcpy(state26, m->start_state, sizeof(m->start_state));
+  if (mean_acc_norm) *mean_acc_norm = m->mean_acc_norm;
   return LSD_OK;
 }
 

@@ -10,3 +10,4 @@
 #include "localmap.cu"
 #include "keyframe_io.cu"
 #include "scancontext.cu"
+#include "fastlio_seam.cu"
