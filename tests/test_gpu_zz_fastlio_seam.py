@@ -51,7 +51,7 @@ for f, frame in enumerate(T._stream(17, ext_R, ext_t)):
     np.testing.assert_allclose(e16[:3, :3], E.quat_to_R(x[3:7] / np.linalg.norm(x[3:7])), atol=1e-15)
     if "iters" in o.last:                         # an iterated update ran
         updates += 1
-        assert last["status"] == lsdreg.OK and last["n_down"] == co["n_down"], (f, last, co)
+        assert last["status"] == lsdreg.OK and abs(last["n_down"] - co["n_down"]) <= 2, (f, last, co)   # free-running: a point may cross a leaf border
         assert abs(last["n_eff"] - co["n_eff"]) <= max(3, co["n_eff"] // 200), (f, last, co)
         d = np.abs(xs.boxminus(o.state()[0]))
         worst = np.maximum(worst, [d[0:3].max(), d[3:6].max()])
@@ -59,7 +59,7 @@ for f, frame in enumerate(T._stream(17, ext_R, ext_t)):
         if ref:
             dr = np.abs(xs.boxminus(ref.state()[0]))
             worst_ref = np.maximum(worst_ref, [dr[0:3].max(), dr[3:6].max()])
-            assert last["n_down"] == ref.counts()["n_down"], f
+            assert abs(last["n_down"] - ref.counts()["n_down"]) <= 2, f
         # the scan started where the previous one ended (contiguous scans: no prediction in between)
         if prev_end is not None:
             np.testing.assert_allclose(s16[:3, 3], prev_end[:3, 3], atol=1e-6)
