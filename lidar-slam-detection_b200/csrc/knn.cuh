@@ -35,7 +35,11 @@ struct WarpList {
 };
 constexpr int kWarpListBytes = kCandCap * 12;
 
+#ifdef LSD_SIMT_EMU  // tests/simt: the host emulator has no PTX
+__device__ __forceinline__ unsigned lanemask_lt() { return simt_lanemask_lt(); }
+#else
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+#endif
 
 // ballot-compact one candidate per lane into the list
 __device__ __forceinline__ void list_push(WarpList& wl, bool valid, float d2, int id, unsigned loc) {

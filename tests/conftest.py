@@ -13,6 +13,14 @@ def pytest_configure(config):
     # make sure the native artefacts exist (nvcc cross-compiles without a GPU)
     import __graft_entry__ as g
     g.build()   # no-op when liblsdreg.so, slam_wrapper and the oracle libraries are newer than their sources
+    if os.environ.get("LSDREG_EMU"):
+        # run the `gpu` tests against the SIMT emulator build (tests/simt): the same sources, kernels executed by fibers on
+        # the CPU.  A debugging aid for kernels written without a GPU at hand; never a substitute for the B200 run.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+        import build_emu
+        import lsdreg
+        lsdreg.capi.lib = lsdreg.capi.load_library(build_emu.build())
+        lsdreg.lib = lsdreg.capi.lib
 
 
 @pytest.fixture(scope="session")
