@@ -171,7 +171,8 @@ lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag);
  * empties the rows. */
 lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
 /* Shape of the per-scan neighbour search (no reference counterpart; Nearest_Points is bit-identical either way):
- * 0 or 1 = one warp per scan point, 3 = flat (a warp owns 32 scan points, csrc/knn_flat.cuh). */
+ * 0 or 1 = one warp per scan point, 3 = flat (a warp owns 32 scan points, csrc/knn_flat.cuh), 4 = flat search fused with
+ * the plane fit and the reduction in one launch (lio_search_fused_kernel; sums equal the two-kernel path's to rounding). */
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape);
 /* Id given to the next point map_incremental inserts (ids of points inserted through
  * lsd_map_insert(lsd_lio_map(l), ...) are the caller's). */

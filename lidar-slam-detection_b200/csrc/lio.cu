@@ -474,6 +474,97 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
   grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq, sc, 0);
 }
 
+// ---------------------------------------------------------------- K3+K4+K5 in ONE launch (flat search shape)
+// lio_knn_flat_kernel followed by lio_hmodel_kernel<true>, fused: the lane that searched a scan point fits its plane and
+// accumulates its Jacobian row straight from the registers, so a search evaluation costs one launch and one grid drain
+// instead of two and Nearest_Points is written but not read back.  Same arithmetic in the same order per point; the
+// reduction tree differs from the two-kernel path only in its block size (64 points per block instead of 256), so sums
+// agree to rounding, not bit for bit.  Selected with lsd_lio_set_knn_shape(l, 4); single-GPU, fixed stencils.
+constexpr int kLioFusedWarps = 2;
+__global__ void __launch_bounds__(kLioFusedWarps * 32) lio_search_fused_kernel(MapView mv, int st_slot, const float4* __restrict__ body,
+                                                                            const int* __restrict__ n_ptr, int cap, LioPose ps,
+                                                                            float4* __restrict__ near, int* __restrict__ near_cnt, int keep_stale,
+                                                                            unsigned char* __restrict__ selected, float4* __restrict__ pabcd_io,
+                                                                            unsigned char* __restrict__ plane_ok, float4* __restrict__ plane,
+                                                                            float4* __restrict__ world, double* __restrict__ partials,
+                                                                            unsigned* __restrict__ done, double* __restrict__ result, double seq,
+                                                                            ShardComm sc) {
+  __shared__ FlatSmem<true> sm[kLioFusedWarps];
+  const int n_true = *n_ptr;
+  const int n = min(n_true, cap);
+  const int n_round = (n + 31) & ~31;
+  double vals[29];
+#pragma unroll
+  for (int j = 0; j < 29; j++) vals[j] = 0.0;
+#pragma unroll 1
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool active = i < n;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    double bx = 0, by = 0, bz = 0, lx = 0, ly = 0, lz = 0;
+    float bw = 0.f;
+    if (active) {
+      const float4 pb = __ldg(body + i);
+      bx = pb.x; by = pb.y; bz = pb.z; bw = pb.w;
+      lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+      ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+      lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+      wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
+      wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
+      wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+    }
+    FlatTopK<5, true> best;
+    best.init();
+    int found = 0;
+    flat_search<5, true>(mv, c_stencils[st_slot], wx, wy, wz, active, 5.0f, sm[threadIdx.x >> 5], best, found);
+    if (!active) continue;
+    world[i] = make_float4(wx, wy, wz, bw);
+    int nf = min(found, 5);
+    float px[5], py[5], pz[5];
+    if (keep_stale && nf == 0) {   // the row keeps what it held (lsd_lio_set_stale_rows): fit on the stored neighbours
+      nf = near_cnt[i];
+#pragma unroll
+      for (int r = 0; r < 5; r++) { const float4 q = near[(size_t)i * 5 + r]; px[r] = q.x; py[r] = q.y; pz[r] = q.z; }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (r < nf) q = load_loc(mv, best.loc[r]);
+        near[(size_t)i * 5 + r] = q;
+        px[r] = q.x; py[r] = q.y; pz[r] = q.z;
+      }
+      near_cnt[i] = nf;
+    }
+    float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
+    bool ok = false;
+    if (nf >= 5) ok = esti_plane_dev(px, py, pz, 0.1f, pabcd);
+    pabcd_io[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
+    plane_ok[i] = ok ? 1 : 0;
+    bool keep = false;
+    if (ok) {
+      const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];
+      const double s = 1 - 0.9 * fabs((double)pd2) / sqrt(sqrt(bx * bx + by * by + bz * bz));  // laserMapping.cpp:861
+      if ((float)s > 0.9) {
+        keep = true;
+        plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
+        const RowH r = make_row(ps, lx, ly, lz, pabcd, pd2);
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+          for (int c = a; c < 6; c++) vals[q++] += r.row[a] * r.row[c];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) vals[21 + a] += r.row[a] * r.h;
+        vals[27] += (double)fabsf(pd2);
+        vals[28] += 1.0;
+      }
+    }
+    selected[i] = keep ? 1 : 0;
+  }
+  block_partials<29>(vals, partials);
+  grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq, sc, 0);
+}
+
 // ---------------------------------------------------------------- degeneracy sums (laserMapping.cpp:946-970)
 // Only launched when the host cannot certify non-degeneracy from the eigenvalues (lio_linearize).
 struct Eig3 { double V[9]; };  // columns = eigenvectors
@@ -653,7 +744,14 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
     const int keep_stale = (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0;
-    if (l->knn_shape == 3 && stencil != LSD_STENCIL_EXACT) {
+    const bool fused = l->knn_shape == 4 && stencil != LSD_STENCIL_EXACT && l->map->view.shard_world <= 1;
+    if (fused) {
+      const int per = kLioFusedWarps * 32, nbf = std::max(1, std::min((l->n_bound + per - 1) / per, kLioMaxGrid));
+      lio_search_fused_kernel<<<nbf, per, 0, st>>>(l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
+                                                   l->d_near_cnt, keep_stale, l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+                                                   l->d_partials, l->d_done, l->d_result, seq, l->sc);
+      l->launches -= 1;   // one launch, not two (the common += 2 follows)
+    } else if ((l->knn_shape == 3 || l->knn_shape == 4) && stencil != LSD_STENCIL_EXACT) {
       const int per = kLioFlatWarps * 32, nbf = std::max(1, std::min((l->n_bound + per - 1) / per, 148 * 8));
       lio_knn_flat_kernel<<<nbf, per, 0, st>>>(l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
                                                l->d_near_cnt, keep_stale);
@@ -662,9 +760,10 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
       lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                                                     keep_stale);
     }
-    lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                                                                       l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                                       l->d_partials, l->d_done, l->d_result, seq, l->sc);
+    if (!fused)
+      lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                                                                         l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+                                                                         l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches += 2;
   } else {
     lio_hmodel_kernel<false><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
@@ -1061,7 +1160,7 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   return LSD_OK;
 }
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape) {
-  if (!l || (shape != 0 && shape != 1 && shape != 3)) return LSD_ERR_INVALID;
+  if (!l || (shape != 0 && shape != 1 && shape != 3 && shape != 4)) return LSD_ERR_INVALID;
   l->knn_shape = shape;
   return LSD_OK;
 }

@@ -83,7 +83,7 @@ scan = synth.scan64(2, 250, Rgt, tgt)
 dR, dt = synth.perturb(5)
 prior = eskf.State(); prior.rot = eskf.R_to_quat(Rgt @ dR); prior.pos = tgt + dt
 res = []
-for shape in (0, 3):
+for shape in (0, 3, 4):
     f = lsdreg.LioFrontend(map_log2_lines=20)
     f.map.insert(m, 0); f.set_next_id(m.shape[0])
     f.set_knn_shape(shape)
@@ -98,6 +98,14 @@ for a, b in ((res[0], res[2]), (res[1], res[3])):
     np.testing.assert_array_equal(a[2], b[2]); np.testing.assert_array_equal(a[3], b[3])
     assert a[5] == b[5] and a[6] == b[6]
     print("lio ok", a[1], "n_eff", a[5])
+# shape 4 = the flat search fused with the plane fit and the reduction: same Nearest_Points, same rows, another reduction
+# tree (64 points per block instead of 256) -> sums and pose equal to rounding
+for a, b in ((res[0], res[4]), (res[1], res[5])):
+    assert a[1] == b[1]
+    np.testing.assert_array_equal(a[4], b[4])
+    assert a[5] == b[5] and a[6] == b[6]
+    np.testing.assert_allclose(a[2], b[2], rtol=0, atol=1e-11); np.testing.assert_allclose(a[3], b[3], rtol=1e-5, atol=1e-13)
+    print("lio fused ok", a[1], "n_eff", a[5], "max |dx|", float(np.abs(a[2] - b[2]).max()))
 print("FLAT_OK")
 '''
 

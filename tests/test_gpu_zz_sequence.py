@@ -26,11 +26,12 @@ from oracle import eskf as E
 from oracle import fastlio as F
 import test_oracle_fastlio as T
 
-def run(stale):
+def run(stale, shape=0):
     ext_R, ext_t = np.eye(3), np.zeros(3)
     orc = F.OracleFastLio(ext_R, ext_t, backend="port", stale_neighbours=stale)
     g = lsdreg.LioFrontend(map_log2_lines=18, ivox_nearby=lsdreg.STENCIL_NEARBY74)
     g.set_stale_rows(stale)
+    g.set_knn_shape(shape)        # 0 = warp per point (default), 3 = flat, 4 = flat fused with the plane fit
     got = {}
     def product(und, x, P, nearby, ekf_inited):
         g.set_nearby(nearby); g.set_ekf_inited(ekf_inited)
@@ -62,13 +63,15 @@ def run(stale):
         np.testing.assert_allclose(got["P"], Po, rtol=1e-6, atol=1e-12)
         n_eff.append(info["n_eff"])
     assert updates == 10
-    print("stale", stale, "worst", worst, "n_eff", n_eff)
+    print("stale", stale, "shape", shape, "worst", worst, "n_eff", n_eff)
     return n_eff
 
 a = run(True)
 b = run(False)
 # the stale rows matter on this stream: some update keeps effective points the plain search does not have
 assert any(x > y for x, y in zip(a, b)) and all(x >= y - 2 for x, y in zip(a, b)), (a, b)
+# the same stream with the flat search shapes (never the default): the stale rows are kept by those kernels too
+assert run(True, 3) == a and run(True, 4) == a
 print("SEQUENCE_OK")
 '''
 

@@ -62,7 +62,7 @@ if "--no-lio" not in sys.argv:
     # one scan stream, device time per scan with either search shape (bench.py's step, host-resident scans)
     steps = [bench.make_step(s) for s in range(12)]
     from oracle import eskf
-    for shape in (0, 3):
+    for shape in (0, 3, 4):      # warp per point (default) / flat / flat fused with the plane fit and the reduction
         f = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
         f.map.insert(m, 0)
         f.set_next_id(m.shape[0])
