@@ -140,6 +140,9 @@ __device__ __forceinline__ void flat_search(const MapView& mv, const Stencil& st
       n_ent += __popc(m);
     }
     __syncwarp();
+#ifdef LSD_SIMT_EMU  // occupancy statistics for tuning kFlatEnt / kFlatCand (tests/simt only)
+    if (lane == 0) { SIMT_STAT_ADD(1, 1); SIMT_STAT_ADD(2, n_ent); SIMT_STAT_MAX(6, n_ent); }
+#endif
     // ---------------- phase B: one existing voxel per lane, two in flight
     struct Ent { const CellLine* cl; unsigned long long key; float4 qp; uint4 h; float4 a0, a1, a2; int ql; };
     auto fetch = [&](int e, Ent& t) {
@@ -166,6 +169,9 @@ __device__ __forceinline__ void flat_search(const MapView& mv, const Stencil& st
     };
     auto consume = [&](Ent& t) {
       if (((unsigned long long)t.h.x | ((unsigned long long)t.h.y << 32)) != t.key) {  // tag collision: resolve properly
+#ifdef LSD_SIMT_EMU
+        SIMT_STAT_ADD(5, 1);
+#endif
         t.cl = tag_find(mv, t.key, &t.h);
         if (!t.cl) return;
         t.a0 = ldg_f4(&t.cl->pts[0]); t.a1 = ldg_f4(&t.cl->pts[1]); t.a2 = ldg_f4(&t.cl->pts[2]);
@@ -203,6 +209,11 @@ __device__ __forceinline__ void flat_search(const MapView& mv, const Stencil& st
     __syncwarp();
     // ---------------- phase C: fold the own query's candidates into the register top-K
     const unsigned nc = sm.cand_n[lane];
+#ifdef LSD_SIMT_EMU
+    if (active && o_begin == 0) SIMT_STAT_ADD(0, 1);
+    SIMT_STAT_ADD(3, nc); SIMT_STAT_MAX(7, nc);
+    if (nc > (unsigned)kFlatCand) SIMT_STAT_ADD(4, 1);
+#endif
     if (nc > (unsigned)kFlatCand) {
       // the list lost points: walk this pass's cells serially instead (exact; the list is ignored)
       for (int oo = o_begin; oo < o; oo++) {

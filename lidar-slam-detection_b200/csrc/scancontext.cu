@@ -242,13 +242,9 @@ using namespace lsd;
 
 extern "C" {
 
-lsd_status_t lsd_sc_create(lsd_sc_t** out, int db_capacity) {
-  if (!out || db_capacity < 1) return LSD_ERR_INVALID;
-  lsd_status_t e = ensure_device();
-  if (e) return e;
-  lsd_sc* s = new lsd_sc();
-  cudaGetDevice(&s->device);
-  *out = s;
+lsd_status_t lsd_sc_destroy(lsd_sc_t* s);
+static lsd_status_t sc_alloc_all(lsd_sc* s, int db_capacity) {
+  lsd_status_t e;
   LSD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   if ((e = set_alloc(&s->db, db_capacity)) || (e = set_alloc(&s->q, kScMaxQueries)) || (e = set_alloc(&s->pa, kScMaxQueries)) ||
       (e = set_alloc(&s->pb, kScMaxQueries)))
@@ -260,6 +256,19 @@ lsd_status_t lsd_sc_create(lsd_sc_t** out, int db_capacity) {
   LSD_CUDA(cudaMalloc((void**)&s->d_ncand, (size_t)kScMaxQueries * 4));
   LSD_CUDA(cudaMalloc((void**)&s->d_dist, (size_t)kScMaxQueries * kCand * 8));
   LSD_CUDA(cudaMalloc((void**)&s->d_shift, (size_t)kScMaxQueries * kCand * 4));
+  return LSD_OK;
+}
+
+lsd_status_t lsd_sc_create(lsd_sc_t** out, int db_capacity) {
+  if (!out || db_capacity < 1) return LSD_ERR_INVALID;
+  *out = nullptr;
+  lsd_status_t e = ensure_device();
+  if (e) return e;
+  lsd_sc* s = new lsd_sc();
+  cudaGetDevice(&s->device);
+  e = sc_alloc_all(s, db_capacity);
+  if (e) { lsd_sc_destroy(s); return e; }
+  *out = s;
   return LSD_OK;
 }
 

@@ -104,7 +104,8 @@ def build(force=False):
         s = s.replace('#include "../../include/lsdreg.h"', f'#include "{os.path.join(ROOT, "include", "lsdreg.h")}"')
         open(os.path.join(tr, f), "w").write(s)
     main = os.path.join(OUT, "emu_main.cpp")
-    open(main, "w").write(f'#include "{os.path.join(HERE, "simt.h")}"\n#include "csrc/lsdreg.cu"\n')
+    open(main, "w").write(f'#include "{os.path.join(HERE, "simt.h")}"\n#include "csrc/lsdreg.cu"\n'
+                          'extern "C" long long* simt_stats_export() { return simt_stats(); }\n')
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
            "-x", "c++", main, "-o", LIB, "-I" + CUDA_INC, "-I" + OUT, "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=OUT)

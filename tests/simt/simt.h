@@ -224,6 +224,14 @@ template <class T> inline cudaError_t rt_set(T* p, T v) { *p = v; return cudaSuc
 
 }  // namespace simt
 
+// counters device code may bump under #ifdef LSD_SIMT_EMU (tuning aids: list occupancies, fallback rates); read through
+// the extra export simt_stats() of liblsdreg_emu.so
+namespace simt { inline long long* stats() { static long long v[32]; return v; } }
+#define SIMT_STAT_ADD(i, v) (simt::stats()[(i)] += (long long)(v))
+#define SIMT_STAT_MAX(i, v) (simt::stats()[(i)] = std::max(simt::stats()[(i)], (long long)(v)))
+extern "C" inline long long* simt_stats() { return simt::stats(); }
+extern "C" inline long long simt_collectives() { return simt::S().collectives; }
+
 // ---------------------------------------------------------------- CUDA built-in variables and functions
 #define threadIdx (simt::tid3())
 #define blockIdx (simt::S().block_idx)
