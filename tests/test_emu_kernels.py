@@ -20,6 +20,7 @@ _CASES = {
     "scancontext": ("test_gpu_zz_scancontext.py", "SC_OK"),
     "sequence": ("test_gpu_zz_sequence.py", "SEQUENCE_OK"),
     "fastlio_seam": ("test_gpu_zz_fastlio_seam.py", "SEAM_OK"),
+    "fuzz_knn": ("simt/fuzz_knn.py", "FUZZ_OK"),   # adversarial map / k-NN inputs, three shapes vs each other and the oracle
 }
 
 _PROLOGUE = r'''
@@ -32,6 +33,8 @@ lsdreg.lib = lsdreg.capi.lib
 
 
 def _script(fname):
+    if fname.startswith("simt/"):      # a plain script, not a test module
+        return _PROLOGUE % {"root": _ROOT} + open(os.path.join(_HERE, fname)).read()
     spec = importlib.util.spec_from_file_location("zz_" + fname[:-3], os.path.join(_HERE, fname))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
