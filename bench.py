@@ -268,6 +268,39 @@ def run_knn_batch(torch, hmap, m, dev, nq):
     return out
 
 
+def run_experimental_flat(m, nq, timeout_s=240):
+    """The flat k-NN shape (csrc/knn_flat.cuh; lsd_knn_set_shape(m, 3)) on the same map and query generator as `knn_batch`,
+    in a SEPARATE PROCESS: the kernel was written with no GPU at hand (its logic runs under tests/simt, its first hardware
+    run may be this one), so nothing it does can reach the numbers above — a fault or a hang costs this leg only.
+    Reports timing only if its results are bit-identical to the validated thread-per-query shape."""
+    import subprocess
+    import tempfile
+    out = {"what": "flat k-NN shape, isolated subprocess, reported only when bit-identical to the thread-per-query shape"}
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "map.npy")
+            np.save(path, m)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), str(nq), "--no-lio", "--shapes", "3",
+                                "--map", path], cwd=ROOT, capture_output=True, text=True, timeout=timeout_s)
+        rows = []
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                try:
+                    rows.append(json.loads(ln))
+                except ValueError:
+                    pass
+        ident = [x for x in rows if "identical_to_thread_shape" in x]
+        timed = [x for x in rows if x.get("shape") == "flat" and "random_us" in x]
+        out["identical_to_thread_shape"] = bool(ident and ident[0]["identical_to_thread_shape"])
+        if r.returncode == 0 and out["identical_to_thread_shape"] and timed:
+            out.update({k: timed[0][k] for k in timed[0] if k != "shape"})
+        else:
+            out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")
+    except Exception as e:  # noqa: BLE001  (timeout, spawn failure: the leg is optional)
+        out["error"] = f"{type(e).__name__}: {str(e)[:300]}"
+    return out
+
+
 def run_streams(torch, lsdreg, local, m, steps, dev_scans, W, K, S, prior_vec, P0):
     """S host threads, each with its own LioFrontend (own map replica, own CUDA stream), all registering the same K
     device-resident scans concurrently.  ctypes releases the GIL inside the C calls."""
@@ -322,6 +355,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knn-batch", action="store_true")
+    ap.add_argument("--no-experimental", action="store_true", help="skip the isolated legs of code that has not been validated on a GPU yet")
     ap.add_argument("--streams", type=int, default=4, help="extra leg (N=1): this many independent scan streams, each with "
                     "its own map replica and handle, registered concurrently on the one GPU (0/1 = skip)")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: upload each scan inside lsd_lio_scan instead of one scan ahead")
@@ -455,6 +489,9 @@ def main():
     knn_batch = None
     if world == 1 and not args.no_knn_batch:
         knn_batch = run_knn_batch(torch, lio.map, m, dev, args.knn_batch)
+    experimental = None
+    if world == 1 and not args.no_knn_batch and not args.no_experimental:
+        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch)}
 
     # ---------------- (5) several independent scan streams on ONE GPU (a fleet server): what the GPU sustains when a
     # single stream's latency chain no longer leaves it idle.  Reported beside the headline, never instead of it.
@@ -542,7 +579,7 @@ def main():
                for k in ("random", "sorted")},
             **{k + "_frac": knn_batch["queries"] * bytes_per_query / (knn_batch[k + "_us"] * 1e-6) / 1e9 / peak
                for k in ("random", "sorted")}},
-        "multi_stream": multi_stream,
+        "multi_stream": multi_stream, "experimental": experimental,
         "cpu_baseline": cpu, "clocks": clocks, "map_build_s": build_s,
         "pos_err_max_m": float(np.max([i["pos_err"] for i in infos_a])),
     }

@@ -3,7 +3,7 @@ Prints one JSON line per shape (CUDA events on the library stream, L2 flushed be
 voxel-sorted query order) and checks that the three shapes return identical bits.  Also times one LIO scan stream
 with either per-scan search shape (lsd_lio_set_knn_shape).  Under ncu: `-k regex:knn_query_(flat|thread)_kernel`.
 
-    python tools/knn_shapes_probe.py [n_queries] [--no-lio]
+    python tools/knn_shapes_probe.py [n_queries] [--no-lio] [--shapes 1,2,3] [--map points.npy]
 """
 import json
 import os
@@ -17,11 +17,20 @@ import bench  # noqa: E402
 import lsdreg  # noqa: E402
 from lsdreg import synth  # noqa: E402
 
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
+def _opt(name, default=None):
+    for i, a in enumerate(sys.argv):
+        if a == name and i + 1 < len(sys.argv):
+            return sys.argv[i + 1]
+    return default
+
+
+_skip = {i + 1 for i, a in enumerate(sys.argv) if a in ("--map", "--shapes")}
+args = [a for i, a in enumerate(sys.argv) if i > 0 and not a.startswith("--") and i not in _skip]
 nq = int(args[0]) if args else 1 << 21
+SHAPES = [(int(x), {1: "warp", 2: "thread", 3: "flat"}[int(x)]) for x in _opt("--shapes", "1,2,3").split(",")]
 lsdreg.init(0)
 dev = torch.device("cuda", 0)
-m = synth.block_map(bench.MAP_SEED, bench.BLOCKS_X, bench.BLOCKS_Y, bench.SPACING)
+m = np.load(_opt("--map")) if _opt("--map") else synth.block_map(bench.MAP_SEED, bench.BLOCKS_X, bench.BLOCKS_Y, bench.SPACING)
 hmap = lsdreg.HashVoxelMap(0.5, 25)
 hmap.insert(m, 0)
 try:
@@ -35,18 +44,18 @@ ALG_BYTES = 680.0   # 56 + 19 (8 + 16 rho), rho = 1.554 on this ma
 rng = np.random.default_rng(5)
 qs = m[rng.integers(0, m.shape[0], 200003)].copy()
 qs[:, :3] += rng.normal(0.0, 0.1, (qs.shape[0], 3)).astype(np.float32)
-ref = None
-for shape in (2, 1, 3):
+hmap.set_knn_shape(2)
+ref = hmap.knn(qs)
+for shape, name in SHAPES:
+    if shape == 2:
+        continue
     hmap.set_knn_shape(shape)
     r = hmap.knn(qs)
-    if ref is None:
-        ref = r
-    else:
-        same = all((a.view(np.int32) == b.view(np.int32)).all() for a, b in zip(ref, r))
-        print(json.dumps({"shape": shape, "identical_to_thread_shape": bool(same)}))
-        assert same, f"shape {shape} differs from the thread-per-query shape"
+    same = all((a.view(np.int32) == b.view(np.int32)).all() for a, b in zip(ref, r))
+    print(json.dumps({"shape": name, "identical_to_thread_shape": bool(same), "queries_compared": int(qs.shape[0])}), flush=True)
+    assert same, f"shape {shape} differs from the thread-per-query shape"
 
-for shape, name in ((1, "warp"), (2, "thread"), (3, "flat")):
+for shape, name in SHAPES:
     hmap.set_knn_shape(shape)
     out = bench.run_knn_batch(torch, hmap, m, dev, nq)
     out["shape"] = name
@@ -55,7 +64,7 @@ for shape, name in ((1, "warp"), (2, "thread"), (3, "flat")):
         out[order + "_alg_GBps"] = round(gbs, 1)
         if peak:
             out[order + "_frac"] = round(gbs / peak, 4)
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 hmap.set_knn_shape(0)
 
 if "--no-lio" not in sys.argv:
