@@ -70,7 +70,6 @@ hmap.set_knn_shape(0)
 if "--no-lio" not in sys.argv:
     # one scan stream, device time per scan with either search shape (bench.py's step, host-resident scans)
     steps = [bench.make_step(s) for s in range(12)]
-    from oracle import eskf
     for shape in (0, 3, 4):      # warp per point (default) / flat / flat fused with the plane fit and the reduction
         f = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
         f.map.insert(m, 0)
@@ -78,8 +77,7 @@ if "--no-lio" not in sys.argv:
         f.set_knn_shape(shape)
         ms, errs = [], []
         for s, (scan, Rgt, tgt, Rp, tp) in enumerate(steps):
-            x = eskf.State(); x.rot = eskf.R_to_quat(Rp); x.pos = tp.copy()
-            xs, P, info = f.scan(scan, x.to_vec(), lsdreg.init_cov())
+            xs, P, info = f.scan(scan, lsdreg.make_state(pos=tp, rot_xyzw=bench.quat_from_R(Rp)), lsdreg.init_cov())
             if s >= 3:
                 ms.append(info["gpu_ms"]); errs.append(float(np.abs(xs[:3] - tgt).max()))
         print(json.dumps({"lio_knn_shape": shape, "gpu_ms_per_scan_median": float(np.median(ms)), "max_err_m": max(errs)}))
