@@ -84,6 +84,6 @@ print("SEAM_OK")
 
 @pytest.mark.xfail(strict=False, reason="never run on a GPU yet (written after the round's GPU budget was spent); see the module docstring")
 def test_the_lio_seam_end_to_end_against_the_restated_and_the_compiled_pipeline():
-    r = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": _ROOT}], cwd=_ROOT, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": _ROOT}], cwd=_ROOT, capture_output=True, text=True, timeout=420)
     tail = (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
     assert r.returncode == 0 and "SEAM_OK" in r.stdout, tail

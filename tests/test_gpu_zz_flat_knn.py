@@ -112,6 +112,6 @@ print("FLAT_OK")
 
 @pytest.mark.xfail(strict=False, reason="never run on a GPU yet (written after the round's GPU budget was spent); see the module docstring")
 def test_flat_shape_is_bit_identical_to_the_validated_shapes():
-    r = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": _ROOT}], cwd=_ROOT, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": _ROOT}], cwd=_ROOT, capture_output=True, text=True, timeout=420)
     tail = (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
     assert r.returncode == 0 and "FLAT_OK" in r.stdout, tail
