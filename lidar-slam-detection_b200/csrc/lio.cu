@@ -395,13 +395,14 @@ __global__ void __launch_bounds__(kLioFlatWarps * 32) lio_knn_flat_kernel(MapVie
 }
 
 // Nearest_Points.resize(feats_down_size) (laserMapping.cpp:1273): rows the new scan does not have are destroyed, so a
-// later, larger scan finds them empty.  rows[0] = number of rows alive (the previous scan's size).
-__global__ void lio_resize_rows_kernel(const int* __restrict__ n_ptr, int cap, int* __restrict__ rows, int* __restrict__ near_cnt) {
-  const int n = min(*n_ptr, cap), prev = min(*rows, cap);
+// later, larger scan finds them empty.  rows[2] is double-buffered by scan parity: this launch reads the number of rows
+// alive from rows[parity ^ 1] (written by the previous scan's launch) and publishes its own in rows[parity], so no block
+// can read a value another block of the same launch has already replaced.
+__global__ void lio_resize_rows_kernel(const int* __restrict__ n_ptr, int cap, int* __restrict__ rows, int parity, int* __restrict__ near_cnt) {
+  const int n = min(*n_ptr, cap), prev = min(rows[parity ^ 1], cap);
   for (int i = n + blockIdx.x * blockDim.x + threadIdx.x; i < prev; i += gridDim.x * blockDim.x) near_cnt[i] = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) rows[1] = n;  // published by the next launch: every block must read rows[0] first
+  if (blockIdx.x == 0 && threadIdx.x == 0) rows[parity] = n;
 }
-__global__ void lio_commit_rows_kernel(int* __restrict__ rows) { rows[0] = rows[1]; }
 
 // ---------------------------------------------------------------- K4+K5: plane fit + residual/Jacobian + reduction
 // One thread per downsampled point.  FIT: first evaluation after a search — fit the plane through
@@ -951,9 +952,9 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
     l->n_down = n;
   }
   if (l->stale_rows) {
-    lio_resize_rows_kernel<<<32, 256, 0, st>>>(l->d_n, l->p.max_points, l->d_n + 8, l->d_near_cnt);
-    lio_commit_rows_kernel<<<1, 1, 0, st>>>(l->d_n + 8);
-    l->launches += 2;
+    lio_resize_rows_kernel<<<32, 256, 0, st>>>(l->d_n, l->p.max_points, l->d_n + 8, l->rows_parity, l->d_near_cnt);
+    l->rows_parity ^= 1;
+    l->launches += 1;
     LSD_CUDA(cudaGetLastError());
   }
   return LSD_OK;
@@ -1157,6 +1158,7 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   LSD_CUDA(cudaMemsetAsync(l->d_n + 8, 0, 8, l->stream));
   LSD_CUDA(cudaStreamSynchronize(l->stream));
   l->stale_rows = flag != 0;
+  l->rows_parity = 0;
   return LSD_OK;
 }
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape) {
