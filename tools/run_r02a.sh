@@ -15,6 +15,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn_
   python tools/knn_shapes_probe.py 1048576 --no-lio > gpurun_out/r02a_ncu_flat.log 2>&1; tail -2 gpurun_out/r02a_ncu_flat.log
 timeout 600 ncu --set full --clock-control none -k regex:knn_query_thread_kernel -c 2 -o gpurun_out/r02a_knn_thread \
   python tools/knn_shapes_probe.py 1048576 --no-lio > gpurun_out/r02a_ncu_thread.log 2>&1; tail -2 gpurun_out/r02a_ncu_thread.log
+for k in flat thread; do
+  ncu -i gpurun_out/r02a_knn_$k.ncu-rep --page raw --csv > gpurun_out/r02a_knn_${k}_ncu_raw.csv 2>/dev/null
+  python tools/ncu_summary.py gpurun_out/r02a_knn_${k}_ncu_raw.csv --items 1048576 --alg-bytes 680 > gpurun_out/r02a_knn_${k}_summary.txt 2>&1; cat gpurun_out/r02a_knn_${k}_summary.txt
+done
 # 5. the bench line of the unchanged default path (reference arm first, as the driver does)
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r02a_bench_ref.json 2> gpurun_out/r02a_bench_ref.err; tail -c 600 gpurun_out/r02a_bench_ref.json
 timeout 900 python bench.py > gpurun_out/r02a_bench.json 2> gpurun_out/r02a_bench.err; tail -c 1500 gpurun_out/r02a_bench.json
