@@ -301,6 +301,34 @@ def run_experimental_flat(m, nq, timeout_s=240):
     return out
 
 
+def run_experimental_lio_shapes(m, timeout_s=300):
+    """The LIO scan stream with the flat (3) and fused (4) per-scan search shapes next to the default (0), same isolation
+    and the same rule: a shape's device time is reported only if its poses agree with the default's."""
+    import subprocess
+    import tempfile
+    out = {"what": "per-scan search shapes 0 (default) / 3 (flat) / 4 (flat fused with plane fit + reduction), isolated subprocess, "
+                   "12 bench steps each, device ms per scan (median of 9)"}
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "map.npy")
+            np.save(path, m)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), "--no-knn", "--map", path], cwd=ROOT,
+                               capture_output=True, text=True, timeout=timeout_s)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{") and "lio_knn_shape" in ln:
+                try:
+                    row = json.loads(ln)
+                except ValueError:
+                    continue
+                key = f"shape_{row.pop('lio_knn_shape')}"
+                out[key] = row if row.get("agrees_with_default") else {"agrees_with_default": False, "max_abs_state_diff_vs_default": row.get("max_abs_state_diff_vs_default")}
+        if r.returncode != 0:
+            out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")
+    except Exception as e:  # noqa: BLE001
+        out["error"] = f"{type(e).__name__}: {str(e)[:300]}"
+    return out
+
+
 def run_streams(torch, lsdreg, local, m, steps, dev_scans, W, K, S, prior_vec, P0):
     """S host threads, each with its own LioFrontend (own map replica, own CUDA stream), all registering the same K
     device-resident scans concurrently.  ctypes releases the GIL inside the C calls."""
@@ -491,7 +519,7 @@ def main():
         knn_batch = run_knn_batch(torch, lio.map, m, dev, args.knn_batch)
     experimental = None
     if world == 1 and not args.no_knn_batch and not args.no_experimental:
-        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch)}
+        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch), "lio_search_shapes": run_experimental_lio_shapes(m)}
 
     # ---------------- (5) several independent scan streams on ONE GPU (a fleet server): what the GPU sustains when a
     # single stream's latency chain no longer leaves it idle.  Reported beside the headline, never instead of it.

@@ -3,7 +3,7 @@ Prints one JSON line per shape (CUDA events on the library stream, L2 flushed be
 voxel-sorted query order) and checks that the three shapes return identical bits.  Also times one LIO scan stream
 with either per-scan search shape (lsd_lio_set_knn_shape).  Under ncu: `-k regex:knn_query_(flat|thread)_kernel`.
 
-    python tools/knn_shapes_probe.py [n_queries] [--no-lio] [--shapes 1,2,3] [--map points.npy]
+    python tools/knn_shapes_probe.py [n_queries] [--no-lio] [--no-knn] [--shapes 1,2,3] [--map points.npy]
 """
 import json
 import os
@@ -16,6 +16,11 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 import lsdreg  # noqa: E402
 from lsdreg import synth  # noqa: E402
+
+if os.environ.get("LSDREG_EMU"):   # dry run of this script's control flow against the SIMT emulator build (tests/simt)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "simt"))
+    import build_emu  # noqa: E402
+    lsdreg.capi.lib = lsdreg.capi.load_library(build_emu.build())
 
 def _opt(name, default=None):
     for i, a in enumerate(sys.argv):
@@ -31,8 +36,10 @@ SHAPES = [(int(x), {1: "warp", 2: "thread", 3: "flat"}[int(x)]) for x in _opt("-
 lsdreg.init(0)
 dev = torch.device("cuda", 0)
 m = np.load(_opt("--map")) if _opt("--map") else synth.block_map(bench.MAP_SEED, bench.BLOCKS_X, bench.BLOCKS_Y, bench.SPACING)
-hmap = lsdreg.HashVoxelMap(0.5, 25)
-hmap.insert(m, 0)
+hmap = None
+if "--no-knn" not in sys.argv:
+    hmap = lsdreg.HashVoxelMap(0.5, 25)
+    hmap.insert(m, 0)
 try:
     with open(os.path.join(bench.ROOT, "MEASURED_PEAKS.json")) as fh:
         peak = float(json.load(fh)["hbm_gbs"])
@@ -44,9 +51,11 @@ ALG_BYTES = 680.0   # 56 + 19 (8 + 16 rho), rho = 1.554 on this ma
 rng = np.random.default_rng(5)
 qs = m[rng.integers(0, m.shape[0], 200003)].copy()
 qs[:, :3] += rng.normal(0.0, 0.1, (qs.shape[0], 3)).astype(np.float32)
-hmap.set_knn_shape(2)
-ref = hmap.knn(qs)
-for shape, name in SHAPES:
+ref = None
+if hmap is not None:
+    hmap.set_knn_shape(2)
+    ref = hmap.knn(qs)
+for shape, name in ([] if "--no-knn" in sys.argv else SHAPES):
     if shape == 2:
         continue
     hmap.set_knn_shape(shape)
@@ -55,7 +64,7 @@ for shape, name in SHAPES:
     print(json.dumps({"shape": name, "identical_to_thread_shape": bool(same), "queries_compared": int(qs.shape[0])}), flush=True)
     assert same, f"shape {shape} differs from the thread-per-query shape"
 
-for shape, name in SHAPES:
+for shape, name in ([] if "--no-knn" in sys.argv or os.environ.get("LSDREG_EMU") else SHAPES):   # timing needs the GPU
     hmap.set_knn_shape(shape)
     out = bench.run_knn_batch(torch, hmap, m, dev, nq)
     out["shape"] = name
@@ -65,19 +74,32 @@ for shape, name in SHAPES:
         if peak:
             out[order + "_frac"] = round(gbs / peak, 4)
     print(json.dumps(out), flush=True)
-hmap.set_knn_shape(0)
+if hmap is not None:
+    hmap.set_knn_shape(0)
+    hmap.close()
 
 if "--no-lio" not in sys.argv:
-    # one scan stream, device time per scan with either search shape (bench.py's step, host-resident scans)
+    # one scan stream, device time per scan with either search shape (bench.py's step, host-resident scans); the poses of
+    # shape 3 must equal the default's bit for bit, those of shape 4 (another reduction tree) to rounding
     steps = [bench.make_step(s) for s in range(12)]
+    base = None
     for shape in (0, 3, 4):      # warp per point (default) / flat / flat fused with the plane fit and the reduction
         f = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
         f.map.insert(m, 0)
         f.set_next_id(m.shape[0])
         f.set_knn_shape(shape)
-        ms, errs = [], []
+        ms, errs, poses, launches = [], [], [], []
         for s, (scan, Rgt, tgt, Rp, tp) in enumerate(steps):
             xs, P, info = f.scan(scan, lsdreg.make_state(pos=tp, rot_xyzw=bench.quat_from_R(Rp)), lsdreg.init_cov())
+            poses.append(xs.copy())
             if s >= 3:
-                ms.append(info["gpu_ms"]); errs.append(float(np.abs(xs[:3] - tgt).max()))
-        print(json.dumps({"lio_knn_shape": shape, "gpu_ms_per_scan_median": float(np.median(ms)), "max_err_m": max(errs)}))
+                ms.append(info["gpu_ms"]); errs.append(float(np.abs(xs[:3] - tgt).max())); launches.append(info["kernel_launches"])
+        poses = np.array(poses)
+        if base is None:
+            base = poses
+        dmax = float(np.abs(poses - base).max())
+        ok = dmax == 0.0 if shape == 3 else dmax < 1e-9
+        print(json.dumps({"lio_knn_shape": shape, "gpu_ms_per_scan_median": float(np.median(ms)), "max_err_m": max(errs),
+                          "kernel_launches_per_scan": float(np.mean(launches)), "max_abs_state_diff_vs_default": dmax,
+                          "agrees_with_default": bool(ok)}), flush=True)
+        f.close()
