@@ -268,7 +268,7 @@ def run_knn_batch(torch, hmap, m, dev, nq):
     return out
 
 
-def run_experimental_flat(m, nq, timeout_s=240):
+def run_experimental_flat(m, nq, timeout_s=150):
     """The flat k-NN shape (csrc/knn_flat.cuh; lsd_knn_set_shape(m, 3)) on the same map and query generator as `knn_batch`,
     in a SEPARATE PROCESS: the kernel was written with no GPU at hand (its logic runs under tests/simt, its first hardware
     run may be this one), so nothing it does can reach the numbers above — a fault or a hang costs this leg only.
@@ -301,7 +301,7 @@ def run_experimental_flat(m, nq, timeout_s=240):
     return out
 
 
-def run_experimental_lio_shapes(m, timeout_s=300):
+def run_experimental_lio_shapes(m, timeout_s=200):
     """The LIO scan stream with the flat (3) and fused (4) per-scan search shapes next to the default (0), same isolation
     and the same rule: a shape's device time is reported only if its poses agree with the default's."""
     import subprocess
