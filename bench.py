@@ -517,9 +517,6 @@ def main():
     knn_batch = None
     if world == 1 and not args.no_knn_batch:
         knn_batch = run_knn_batch(torch, lio.map, m, dev, args.knn_batch)
-    experimental = None
-    if world == 1 and not args.no_knn_batch and not args.no_experimental:
-        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch), "lio_search_shapes": run_experimental_lio_shapes(m)}
 
     # ---------------- (5) several independent scan streams on ONE GPU (a fleet server): what the GPU sustains when a
     # single stream's latency chain no longer leaves it idle.  Reported beside the headline, never instead of it.
@@ -570,6 +567,12 @@ def main():
                "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
                "sample": f"{args.cpu_sample} full scans of the same workload (same map, same generator) after 1 warm-up scan",
                "ms_per_scan": r["ms_per_step"], "mean_iterations": r["iters"]}
+
+    # last of all: code that has not been validated on a GPU yet, each leg in its own process (everything reported above
+    # is already measured; clocks were sampled during the timed region)
+    experimental = None
+    if world == 1 and not args.no_knn_batch and not args.no_experimental:
+        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch), "lio_search_shapes": run_experimental_lio_shapes(m)}
 
     iters = float(np.mean([i["iterations"] for i in infos_a]))
     h2d = int(np.mean([stp[0].shape[0] for stp in steps_b[W:]]) * 16)
