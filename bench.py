@@ -268,7 +268,7 @@ def run_knn_batch(torch, hmap, m, dev, nq):
     return out
 
 
-def run_experimental_flat(m, nq, timeout_s=150):
+def run_experimental_flat(m, nq, timeout_s=150, l2_fetch=None):
     """The flat k-NN shape (csrc/knn_flat.cuh; lsd_knn_set_shape(m, 3)) on the same map and query generator as `knn_batch`,
     in a SEPARATE PROCESS: the kernel was written with no GPU at hand (its logic runs under tests/simt, its first hardware
     run may be this one), so nothing it does can reach the numbers above — a fault or a hang costs this leg only.
@@ -280,8 +280,12 @@ def run_experimental_flat(m, nq, timeout_s=150):
         with tempfile.TemporaryDirectory() as td:
             path = os.path.join(td, "map.npy")
             np.save(path, m)
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), str(nq), "--no-lio", "--shapes", "3",
-                                "--map", path], cwd=ROOT, capture_output=True, text=True, timeout=timeout_s)
+            env = dict(os.environ)
+            if l2_fetch:   # cudaLimitMaxL2FetchGranularity in the child's context only (read by lsd_init, csrc/map.cu)
+                env["LSD_L2_FETCH_GRANULARITY"] = str(l2_fetch)
+                out["l2_fetch_granularity"] = l2_fetch
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), str(nq), "--no-lio", "--shapes", "2,3" if l2_fetch else "3",
+                                "--map", path], cwd=ROOT, capture_output=True, text=True, timeout=timeout_s, env=env)
         rows = []
         for ln in r.stdout.splitlines():
             if ln.startswith("{"):
@@ -294,6 +298,9 @@ def run_experimental_flat(m, nq, timeout_s=150):
         out["identical_to_thread_shape"] = bool(ident and ident[0]["identical_to_thread_shape"])
         if r.returncode == 0 and out["identical_to_thread_shape"] and timed:
             out.update({k: timed[0][k] for k in timed[0] if k != "shape"})
+            th = [x for x in rows if x.get("shape") == "thread" and "random_us" in x]
+            if th:   # the validated shape under the same fetch granularity, for reference
+                out["thread_shape_same_setting"] = {k: th[0][k] for k in ("random_us", "sorted_us", "random_frac", "sorted_frac") if k in th[0]}
         else:
             out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")
     except Exception as e:  # noqa: BLE001  (timeout, spawn failure: the leg is optional)
@@ -572,7 +579,12 @@ def main():
     # is already measured; clocks were sampled during the timed region)
     experimental = None
     if world == 1 and not args.no_knn_batch and not args.no_experimental:
-        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch), "lio_search_shapes": run_experimental_lio_shapes(m)}
+        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch)}
+        if "error" not in experimental["knn_flat_shape"]:
+            # the 128-byte cell line holds header + 3 points in its first 64 bytes (rho = 1.5): with 64-byte L2 fetches a
+            # voxel costs half the DRAM traffic.  No gain for the thread shape in round 1 (issue bound); the flat shape may differ
+            experimental["knn_flat_shape_l2_fetch_64"] = run_experimental_flat(m, args.knn_batch, l2_fetch=64)
+        experimental["lio_search_shapes"] = run_experimental_lio_shapes(m)
 
     iters = float(np.mean([i["iterations"] for i in infos_a]))
     h2d = int(np.mean([stp[0].shape[0] for stp in steps_b[W:]]) * 16)

@@ -10,6 +10,7 @@ done
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r02a_pytest.log 2>&1; tail -4 gpurun_out/r02a_pytest.log
 # 3. A/B of the three k-NN shapes (bit identity, batch timing random / sorted, per-scan search inside the LIO stream)
 timeout 600 python tools/knn_shapes_probe.py > gpurun_out/r02a_knn_shapes.jsonl 2> gpurun_out/r02a_knn_shapes.err; cat gpurun_out/r02a_knn_shapes.jsonl; tail -3 gpurun_out/r02a_knn_shapes.err
+LSD_L2_FETCH_GRANULARITY=64 timeout 600 python tools/knn_shapes_probe.py --no-lio --shapes 2,3 > gpurun_out/r02a_knn_shapes_l2fetch64.jsonl 2>&1; tail -3 gpurun_out/r02a_knn_shapes_l2fetch64.jsonl
 # 4. ncu: the flat kernel next to the thread kernel, 1 M queries (one launch each is enough: -c bounds the replay cost)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn_query_flat_kernel -c 2 -o gpurun_out/r02a_knn_flat \
   python tools/knn_shapes_probe.py 1048576 --no-lio > gpurun_out/r02a_ncu_flat.log 2>&1; tail -2 gpurun_out/r02a_ncu_flat.log
