@@ -72,6 +72,9 @@ def test_fails_loudly_without_a_device():
         lsdreg.ImuProcess()
     with pytest.raises(lsdreg.LsdError):
         lsdreg.Matcher("FAST_VGICP")
+    with pytest.raises(lsdreg.LsdError) as e:
+        lsdreg.ScanContext(db_capacity=16)
+    assert e.value.status == lsdreg.ERR_NO_DEVICE
 
 
 def test_host_only_helpers_work_anywhere():
