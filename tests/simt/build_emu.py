@@ -88,7 +88,14 @@ def translate(src: str) -> str:
 _EXT = re.compile(r"extern\s+__shared__\s+([A-Za-z_][\w:<>\s\*]*?)\s+(\w+)\s*\[\s*\]\s*;")
 
 
-def build(force=False):
+def build(force=False, asan=None):
+    """asan (default: env LSDREG_EMU_ASAN): also instrument with AddressSanitizer — out-of-bounds accesses to "device" memory
+    (heap) and to shared-memory arrays (static storage, red-zoned like any global) abort with a report.  Run python with
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0."""
+    global LIB
+    asan = bool(os.environ.get("LSDREG_EMU_ASAN")) if asan is None else asan
+    if asan:
+        LIB = os.path.join(OUT, "liblsdreg_emu_asan.so")
     os.makedirs(OUT, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".hpp")))
     deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, "simt.h"), os.path.abspath(__file__),
@@ -108,6 +115,8 @@ def build(force=False):
                           'extern "C" long long* simt_stats_export() { return simt_stats(); }\n')
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
            "-x", "c++", main, "-o", LIB, "-I" + CUDA_INC, "-I" + OUT, "-lpthread"]
+    if asan:
+        cmd[1:1] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=OUT)
     if r.returncode:
         sys.stderr.write(r.stdout[-6000:] + r.stderr[-12000:])
