@@ -64,8 +64,8 @@ def make(xyzi: np.ndarray, dx: float = 0.0, dy: float = 0.0) -> np.ndarray:
     with np.errstate(invalid="ignore"):
         ring_f = np.ceil((rng.astype(np.float64) / MAX_RADIUS) * N_RING)
         sect_f = np.ceil((ang.astype(np.float64) / 360.0) * N_SECTOR)
-    ring_f = np.where(np.isnan(ring_f), -2147483648.0, ring_f)   # int(NaN) on x86-64
-    sect_f = np.where(np.isnan(sect_f), -2147483648.0, sect_f)
+    ring_f = np.where(~np.isfinite(ring_f), -2147483648.0, ring_f)   # int(NaN) / int(inf) on x86-64 (cvttsd2si -> INT_MIN)
+    sect_f = np.where(~np.isfinite(sect_f), -2147483648.0, sect_f)
     ring = np.maximum(np.minimum(N_RING, ring_f.astype(np.int64)), 1) - 1
     sect = np.maximum(np.minimum(N_SECTOR, sect_f.astype(np.int64)), 1) - 1
     desc = np.full((N_SECTOR, N_RING), NO_POINT, np.float64)

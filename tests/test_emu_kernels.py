@@ -21,6 +21,7 @@ _CASES = {
     "sequence": ("test_gpu_zz_sequence.py", "SEQUENCE_OK"),
     "fastlio_seam": ("test_gpu_zz_fastlio_seam.py", "SEAM_OK"),
     "fuzz_knn": ("simt/fuzz_knn.py", "FUZZ_OK"),   # adversarial map / k-NN inputs, three shapes vs each other and the oracle
+    "fuzz_misc": ("simt/fuzz_misc.py", "FUZZ_MISC_OK"),   # voxel grid, key-frame filters, ScanContext descriptor on degenerate inputs
 }
 
 _PROLOGUE = r'''
