@@ -62,9 +62,10 @@ struct FlatSmem {  // per warp
 // First slot on `key`'s probe sequence whose TAG matches, before the first empty slot (no line touched).
 // The key itself is verified by whoever fetches the line (1/255 false positives per occupied slot walked).
 __device__ __forceinline__ bool tag_first(const MapView& mv, unsigned long long key, unsigned* line) {
-  constexpr unsigned long long k01 = 0x0101010101010101ull, k7f = 0x7f7f7f7f7f7f7f7full;
+  constexpr unsigned long long k7f = 0x7f7f7f7f7f7f7f7full;
   const unsigned long long hh = hash_key(key);
-  const unsigned long long tagv = (unsigned long long)slot_tag(hh) * k01;
+  const unsigned t4 = slot_tag(hh) * 0x01010101u;                 // the tag in every byte: one 32-bit multiply, then doubled
+  const unsigned long long tagv = ((unsigned long long)t4 << 32) | t4;
   unsigned long long s = hh & mv.mask;
   for (unsigned walked = 0; walked < kMaxProbe;) {
     const unsigned pos = (unsigned)(s & 7ull), nv = 8u - pos;
@@ -117,6 +118,11 @@ __device__ __forceinline__ void flat_search(const MapView& mv, const Stencil& st
                                             float max_sq, FlatSmem<LOC>& sm, FlatTopK<K, LOC>& best, int& found) {
   const int lane = threadIdx.x & 31;
   const int3 c = pos2grid(qx, qy, qz, mv.inv_res);
+  // A stencil cell's key is the home voxel's key plus a per-cell constant as long as no coordinate field can leave its 19
+  // bits: true when the home voxel is at least 3 voxels inside the representable cube (stencil offsets are within +-2).
+  constexpr int kInner = kCoordBias - 3;
+  const bool inner = c.x > -kInner && c.x < kInner && c.y > -kInner && c.y < kInner && c.z > -kInner && c.z < kInner;
+  const unsigned long long key_c = inner ? pack_key(c.x, c.y, c.z, 0) : 0ull;
   sm.q[lane] = make_float4(qx, qy, qz, 0.f);
   sm.cand_n[lane] = 0u;
   __syncwarp();
@@ -127,10 +133,16 @@ __device__ __forceinline__ void flat_search(const MapView& mv, const Stencil& st
     int n_ent = 0;
     for (; o < st.n && n_ent <= kFlatEnt - 32; o++) {
       const int dx = st.off[o][0], dy = st.off[o][1], dz = st.off[o][2];
-      const int x = c.x + dx, y = c.y + dy, z = c.z + dz;
+      const long long dkey = ((long long)dx << 38) + ((long long)dy << 19) + (long long)dz;   // warp-uniform
       unsigned line = 0u;
       bool hit = false;
-      if (active && coord_ok(x, y, z)) hit = tag_first(mv, pack_key(x, y, z, 0), &line);
+      if (active) {
+        if (inner) hit = tag_first(mv, key_c + (unsigned long long)dkey, &line);
+        else {   // at the rim of the representable cube: per-coordinate range check (queries this far out are rare)
+          const int x = c.x + dx, y = c.y + dy, z = c.z + dz;
+          if (coord_ok(x, y, z)) hit = tag_first(mv, pack_key(x, y, z, 0), &line);
+        }
+      }
       const unsigned m = __ballot_sync(kFull, hit);
       if (hit) {
         const int pos = n_ent + __popc(m & lanemask_lt());
