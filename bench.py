@@ -308,27 +308,38 @@ def run_experimental_flat(m, nq, timeout_s=150, l2_fetch=None):
     return out
 
 
-def run_experimental_lio_shapes(m, timeout_s=200):
-    """The LIO scan stream with the flat (3) and fused (4) per-scan search shapes next to the default (0), same isolation
-    and the same rule: a shape's device time is reported only if its poses agree with the default's."""
+def run_experimental_lio_shapes(m, timeout_s=280):
+    """The LIO scan stream with the flat (3) and fused (4) per-scan search shapes next to the default (0), then shapes 0 and 4
+    with programmatic dependent launch; same isolation and the same rule: a variant's times are reported only if its poses
+    agree with the default's.  Rows printed before a timeout are kept."""
     import subprocess
     import tempfile
-    out = {"what": "per-scan search shapes 0 (default) / 3 (flat) / 4 (flat fused with plane fit + reduction), isolated subprocess, "
-                   "12 bench steps each, device ms per scan (median of 9)"}
-    try:
-        with tempfile.TemporaryDirectory() as td:
-            path = os.path.join(td, "map.npy")
-            np.save(path, m)
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), "--no-knn", "--map", path], cwd=ROOT,
-                               capture_output=True, text=True, timeout=timeout_s)
-        for ln in r.stdout.splitlines():
+    out = {"what": "per-scan search shapes 0 (default) / 3 (flat) / 4 (flat fused with plane fit + reduction), and shapes 0 / 4 with "
+                   "programmatic dependent launch (_pdl), isolated subprocess, 12 bench steps each, device and wall ms per scan (median of 9)"}
+
+    def rows(text):
+        for ln in (text or "").splitlines():
             if ln.startswith("{") and "lio_knn_shape" in ln:
                 try:
                     row = json.loads(ln)
                 except ValueError:
                     continue
-                key = f"shape_{row.pop('lio_knn_shape')}"
+                key = f"shape_{row.pop('lio_knn_shape')}" + ("_pdl" if row.pop("pdl", 0) else "")
                 out[key] = row if row.get("agrees_with_default") else {"agrees_with_default": False, "max_abs_state_diff_vs_default": row.get("max_abs_state_diff_vs_default")}
+
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "map.npy")
+            np.save(path, m)
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), "--no-knn", "--map", path], cwd=ROOT,
+                                   capture_output=True, text=True, timeout=timeout_s)
+            except subprocess.TimeoutExpired as e:
+                so = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else e.stdout
+                rows(so)
+                out["error"] = f"timeout after {timeout_s} s (rows above were printed before it)"
+                return out
+        rows(r.stdout)
         if r.returncode != 0:
             out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")
     except Exception as e:  # noqa: BLE001
@@ -600,6 +611,7 @@ def main():
                        f"map tile-sharded over {world} GPUs, one scan stream, peer-memory all-reduce of the normal equations"
                        if sharded else f"{world} replicas, independent scan streams, no collective"),
                    "shard_points_this_rank": int(st["points"]),
+                   "pdl": os.environ.get("LSD_PDL", "")[:1] == "1",   # programmatic dependent launch (opt-in, lsd_lio_set_pdl)
                    "l2": "every step visits a different 120x80 m map block; table+points 4.3 GB >> 126 MB L2",
                    "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream"},
         "device_ms_per_step": 1e3 * dev_s / K,

@@ -174,6 +174,12 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
  * 0 or 1 = one warp per scan point, 3 = flat (a warp owns 32 scan points, csrc/knn_flat.cuh), 4 = flat search fused with
  * the plane fit and the reduction in one launch (lio_search_fused_kernel; sums equal the two-kernel path's to rounding). */
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape);
+/* Programmatic dependent launch for the per-scan kernel chain (no reference counterpart; results are bit-identical either
+ * way): flag != 0 launches the voxel-grid, search, h-model and map_incremental kernels with the programmatic stream
+ * serialization attribute, so that each kernel's blocks are resident and parked in griddepcontrol.wait when its
+ * predecessor drains (csrc/lsd_common.cuh).  Default 0, or 1 when LSD_PDL=1 is in the environment at lsd_lio_create;
+ * ignored on a tile-sharded handle. */
+lsd_status_t lsd_lio_set_pdl(lsd_lio_t* l, int flag);
 /* Id given to the next point map_incremental inserts (ids of points inserted through
  * lsd_map_insert(lsd_lio_map(l), ...) are the caller's). */
 lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, laserMapping.cpp:1196 */

@@ -95,6 +95,7 @@ SIGNATURES = [
     ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
     ("lsd_lio_set_stale_rows", _i, [_vp, _i]),
     ("lsd_lio_set_knn_shape", _i, [_vp, _i]),
+    ("lsd_lio_set_pdl", _i, [_vp, _i]),
     ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
     ("lsd_lio_shard_export", _i, [_vp, _i, _i, _i, _i, _vp]),
     ("lsd_lio_shard_connect", _i, [_vp, _vp]),
@@ -843,6 +844,10 @@ class LioFrontend:
     def set_knn_shape(self, shape: int):
         """0/1 = one warp per scan point, 3 = flat (include/lsdreg.h::lsd_lio_set_knn_shape)."""
         check(lib.lsd_lio_set_knn_shape(self.h, int(shape)))
+
+    def set_pdl(self, flag: bool):
+        """Programmatic dependent launch for the scan's kernel chain (include/lsdreg.h::lsd_lio_set_pdl)."""
+        check(lib.lsd_lio_set_pdl(self.h, int(flag)))
 
     SHARD_BLOB_BYTES = 192
 

@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
                                                                 const int* __restrict__ n_ptr, int cap, LioPose ps,
                                                                 float4* __restrict__ near, int* __restrict__ near_cnt,
                                                                 int keep_stale) {
+  pdl_enter();
   __shared__ __align__(16) unsigned char s_list[kHmWarps * kWarpListBytes];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(*n_ptr, cap);
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(kLioFlatWarps * 32) lio_knn_flat_kernel(MapVie
                                                                         const int* __restrict__ n_ptr, int cap, LioPose ps,
                                                                         float4* __restrict__ near, int* __restrict__ near_cnt,
                                                                         int keep_stale) {
+  pdl_enter();
   __shared__ FlatSmem<true> sm[kLioFlatWarps];
   const int n = min(*n_ptr, cap);
   const int n_round = (n + 31) & ~31;  // whole warps: padding lanes take part in the warp-wide steps
@@ -399,6 +401,7 @@ __global__ void __launch_bounds__(kLioFlatWarps * 32) lio_knn_flat_kernel(MapVie
 // alive from rows[parity ^ 1] (written by the previous scan's launch) and publishes its own in rows[parity], so no block
 // can read a value another block of the same launch has already replaced.
 __global__ void lio_resize_rows_kernel(const int* __restrict__ n_ptr, int cap, int* __restrict__ rows, int parity, int* __restrict__ near_cnt) {
+  pdl_enter();
   const int n = min(*n_ptr, cap), prev = min(rows[parity ^ 1], cap);
   for (int i = n + blockIdx.x * blockDim.x + threadIdx.x; i < prev; i += gridDim.x * blockDim.x) near_cnt[i] = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) rows[parity] = n;
@@ -417,6 +420,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
                                                                float4* __restrict__ plane, float4* __restrict__ world,
                                                                double* __restrict__ partials, unsigned* __restrict__ done,
                                                                double* __restrict__ result, double seq, ShardComm sc) {
+  pdl_enter();
   const int n_true = *n_ptr;
   const int n = min(n_true, cap);
   double vals[29];
@@ -490,6 +494,7 @@ __global__ void __launch_bounds__(kLioFusedWarps * 32) lio_search_fused_kernel(M
                                                                             float4* __restrict__ world, double* __restrict__ partials,
                                                                             unsigned* __restrict__ done, double* __restrict__ result, double seq,
                                                                             ShardComm sc) {
+  pdl_enter();
   __shared__ FlatSmem<true> sm[kLioFusedWarps];
   const int n_true = *n_ptr;
   const int n = min(n_true, cap);
@@ -574,6 +579,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restr
                                                               const float4* __restrict__ plane, Eig3 e, double* __restrict__ partials,
                                                               unsigned* __restrict__ done, double* __restrict__ result, double seq,
                                                               ShardComm sc) {
+  pdl_enter();
   const int n = min(*n_ptr, cap);
   const double* V = e.V;
   double vals[6] = {0, 0, 0, 0, 0, 0};
@@ -604,6 +610,7 @@ __global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, co
                                                                   float4* __restrict__ world, unsigned char* __restrict__ flags,
                                                                   unsigned* __restrict__ n_added, ShardComm sc, double seq,
                                                                   unsigned* __restrict__ done) {
+  pdl_enter();
   const int n = min(*n_ptr, cap);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -666,6 +673,7 @@ __global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, co
 __global__ void __launch_bounds__(256) lio_halo_insert_kernel(MapView mv, const int* __restrict__ n_ptr, int cap,
                                                               const float4* __restrict__ world, int id0, ShardComm sc, double seq,
                                                               unsigned* __restrict__ n_added) {
+  pdl_enter();
   __shared__ int ready;
   if (threadIdx.x < sc.world && threadIdx.x != sc.rank) {
     volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(sc.flagbox[sc.rank] + cap) + threadIdx.x;
@@ -742,34 +750,35 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   cudaStream_t st = l->stream;
   const int stencil = l->p.knn_mode_exact ? LSD_STENCIL_EXACT : l->p.ivox_nearby;
   const double seq = (double)(++l->seq);
+  const int pdl = l->pdl && l->sc.world <= 1;   // programmatic dependent launch (lsd_lio_set_pdl); single-GPU chains only
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
     const int keep_stale = (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0;
     const bool fused = l->knn_shape == 4 && stencil != LSD_STENCIL_EXACT && l->map->view.shard_world <= 1;
     if (fused) {
       const int per = kLioFusedWarps * 32, nbf = std::max(1, std::min((l->n_bound + per - 1) / per, kLioMaxGrid));
-      lio_search_fused_kernel<<<nbf, per, 0, st>>>(l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
-                                                   l->d_near_cnt, keep_stale, l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                   l->d_partials, l->d_done, l->d_result, seq, l->sc);
+      LSD_LAUNCH(pdl, lio_search_fused_kernel, nbf, per, st, l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
+                 l->d_near_cnt, keep_stale, l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+                 l->d_partials, l->d_done, l->d_result, seq, l->sc);
       l->launches -= 1;   // one launch, not two (the common += 2 follows)
     } else if ((l->knn_shape == 3 || l->knn_shape == 4) && stencil != LSD_STENCIL_EXACT) {
       const int per = kLioFlatWarps * 32, nbf = std::max(1, std::min((l->n_bound + per - 1) / per, 148 * 8));
-      lio_knn_flat_kernel<<<nbf, per, 0, st>>>(l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
-                                               l->d_near_cnt, keep_stale);
+      LSD_LAUNCH(pdl, lio_knn_flat_kernel, nbf, per, st, l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
+                 l->d_near_cnt, keep_stale);
     } else {
       const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
-      lio_knn_kernel<<<nb, kHmWarps * 32, 0, st>>>(l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                                                    keep_stale);
+      LSD_LAUNCH(pdl, lio_knn_kernel, nb, kHmWarps * 32, st, l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                 keep_stale);
     }
     if (!fused)
-      lio_hmodel_kernel<true><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                                                                         l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                                         l->d_partials, l->d_done, l->d_result, seq, l->sc);
+      LSD_LAUNCH(pdl, lio_hmodel_kernel<true>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+                 l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+                 l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches += 2;
   } else {
-    lio_hmodel_kernel<false><<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                                                                        l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                                                                        l->d_partials, l->d_done, l->d_result, seq, l->sc);
+    LSD_LAUNCH(pdl, lio_hmodel_kernel<false>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+               l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+               l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches++;
   }
   LSD_CUDA(cudaGetLastError());
@@ -799,8 +808,8 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
     if (wmin - 0.0302 * (double)*n_eff < 260.0) {
       Eig3 e;
       memcpy(e.V, V, sizeof(V));
-      lio_degen_kernel<<<grid_for(l->n_bound), kLioBlock, 0, st>>>(l->d_n, l->p.max_points, l->d_selected, l->d_plane, e, l->d_partials,
-                                                                  l->d_done, l->d_result, seq, l->sc);
+      LSD_LAUNCH(pdl, lio_degen_kernel, grid_for(l->n_bound), kLioBlock, st, l->d_n, l->p.max_points, l->d_selected, l->d_plane, e, l->d_partials,
+                 l->d_done, l->d_result, seq, l->sc);
       LSD_CUDA(cudaGetLastError());
       l->launches++;
       { lsd_status_t w = wait_seq(l, kResSeqDegen, seq); if (w) return w; }
@@ -910,9 +919,10 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
   ProfScope prof(l, 3);
   const int nb = std::max(1, (l->n_bound + 255) / 256);
   const double mseq = (double)(++l->mi_seq);
-  lio_map_incremental_kernel<<<nb, 256, 0, st>>>(l->map->view, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt, l->ekf_inited,
-                                                 (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added,
-                                                 l->sc, mseq, l->d_done);
+  const int pdl = l->pdl && l->sc.world <= 1;
+  LSD_LAUNCH(pdl, lio_map_incremental_kernel, nb, 256, st, l->map->view, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt, l->ekf_inited,
+             (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added,
+             l->sc, mseq, l->d_done);
   LSD_CUDA(cudaGetLastError());
   l->launches++;
   if (l->sc.world > 1) {
@@ -937,6 +947,7 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
   if (n < 0 || n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
   if (downsample) {
     ProfScope prof(l, 2);
+    l->vg->pdl = (l->pdl && l->sc.world <= 1) ? 1 : 0;
     lsd_status_t s = vg_run(l->vg, d_scan, n, l->p.filter_size_surf, l->d_body, l->d_n, st);
     if (s) return s;
     prof.stop();
@@ -952,7 +963,7 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
     l->n_down = n;
   }
   if (l->stale_rows) {
-    lio_resize_rows_kernel<<<32, 256, 0, st>>>(l->d_n, l->p.max_points, l->d_n + 8, l->rows_parity, l->d_near_cnt);
+    LSD_LAUNCH(l->pdl && l->sc.world <= 1, lio_resize_rows_kernel, 32, 256, st, l->d_n, l->p.max_points, l->d_n + 8, l->rows_parity, l->d_near_cnt);
     l->rows_parity ^= 1;
     l->launches += 1;
     LSD_CUDA(cudaGetLastError());
@@ -1119,6 +1130,7 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   // the map and the voxel grid run on the LIO stream
   cudaStreamDestroy(l->map->stream); l->map->stream = l->stream;
   cudaStreamDestroy(l->vg->stream); l->vg->stream = l->stream;
+  { const char* ev = getenv("LSD_PDL"); l->pdl = (ev && ev[0] == '1') ? 1 : 0; }
   *out = l;
   return LSD_OK;
 }
@@ -1161,6 +1173,14 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   l->rows_parity = 0;
   return LSD_OK;
 }
+// Programmatic dependent launch for the scan's kernel chain (lsd_common.cuh).  Off by default; LSD_PDL=1 in the
+// environment turns it on at lsd_lio_create.  Results are bit-identical either way: only launch latency is hidden.
+lsd_status_t lsd_lio_set_pdl(lsd_lio_t* l, int flag) {
+  if (!l) return LSD_ERR_INVALID;
+  l->pdl = flag ? 1 : 0;
+  return LSD_OK;
+}
+
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape) {
   if (!l || (shape != 0 && shape != 1 && shape != 3 && shape != 4)) return LSD_ERR_INVALID;
   l->knn_shape = shape;

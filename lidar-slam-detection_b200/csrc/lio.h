@@ -40,6 +40,7 @@ struct lsd_lio {
   float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)
   int* d_near_cnt = nullptr;
   int knn_shape = 0;            // lsd_lio_set_knn_shape: 0/1 warp per scan point (lio_knn_kernel), 3 flat (lio_knn_flat_kernel)
+  int pdl = 0;                  // lsd_lio_set_pdl: launch the scan's kernels with programmatic dependent launch
   int rows_parity = 0;          // which of d_n[8..9] the next lio_resize_rows_kernel publishes (the other one is read)
   bool stale_rows = false;      // lsd_lio_set_stale_rows: keep Nearest_Points[i] when a search finds nothing (d_n[8..9]: rows alive)
   unsigned char* d_selected = nullptr;  // point_selected_surf

@@ -108,6 +108,47 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (sm_90+)
+// A scan is a chain of ~15 short kernels (5-40 us each) on one stream; between two dependent kernels the GPU idles for
+// the grid drain plus the next grid's launch latency.  With the programmatic-stream-serialization attribute the next
+// kernel's blocks are scheduled as soon as every block of the running one has passed pdl_trigger(), and park in
+// pdl_wait() until that grid has completed and its memory is visible.  Every kernel of the chain executes
+// pdl_wait() as its FIRST statement, on every thread, before touching global memory: the ordering the stream gave is
+// kept link by link (B's completion implies its wait returned, hence A's completion), only the launch latency is hidden.
+// Both instructions are no-ops in a kernel launched without the attribute (the default: lsd_lio_set_pdl).
+__device__ __forceinline__ void pdl_wait() {
+#ifndef LSD_SIMT_EMU
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef LSD_SIMT_EMU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+
+#ifdef LSD_SIMT_EMU
+#define LSD_LAUNCH(pdl, kern, g, b, st, ...) kern<<<g, b, 0, st>>>(__VA_ARGS__)
+#else
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 g, dim3 b, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through cudaGetLastError, as for a plain launch
+}
+// Launch on `st`; pdl != 0 adds the programmatic-serialization attribute (the kernel must start with pdl_enter()).
+#define LSD_LAUNCH(pdl, kern, g, b, st, ...)                                    \
+  do {                                                                          \
+    if (pdl) lsd::launch_pdl(kern, dim3(g), dim3(b), st, __VA_ARGS__);          \
+    else kern<<<g, b, 0, st>>>(__VA_ARGS__);                                    \
+  } while (0)
+#endif
+
 // ------------------------------------------------------------------ stencils (ivox3d.h:178-215)
 constexpr int kStencilMax = 75;
 struct Stencil { int n; signed char off[kStencilMax][3]; };

@@ -73,6 +73,7 @@ __device__ __forceinline__ int block_scan_step(int v, int* warp_tot, int* carry,
 
 // ---- kernel 1: bounding box.  Block-level reduction, then 6 atomics per block.
 __global__ void __launch_bounds__(256) vg_minmax_kernel(const float4* __restrict__ in, int n, int* __restrict__ bbox) {
+  pdl_enter();
   float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = __ldg(in + i);
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) vg_minmax_kernel(const float4* __restrict
 __global__ void __launch_bounds__(256) vg_mark_kernel(const float4* __restrict__ in, int n, float leaf, long long max_cells,
                                                       const int* __restrict__ bbox, VgGrid* __restrict__ gp,
                                                       unsigned* __restrict__ bitmap, int* __restrict__ vidx) {
+  pdl_enter();
   __shared__ VgGrid g;
   if (threadIdx.x == 0) { vg_setup(bbox, leaf, max_cells, &g); if (blockIdx.x == 0) *gp = g; }
   __syncthreads();
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) vg_mark_kernel(const float4* __restrict__
 __global__ void __launch_bounds__(256) vg_scan_kernel(const VgGrid* __restrict__ gp, const unsigned* __restrict__ bitmap,
                                                       int* __restrict__ word_prefix, int* __restrict__ chunk_sum,
                                                       unsigned* __restrict__ done, int* __restrict__ m_out, int n_in) {
+  pdl_enter();
   __shared__ int warp_tot[8];
   __shared__ int carry;
   __shared__ bool is_last;
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(256) vg_accum_kernel(const float4* __restrict_
                                                        const int* __restrict__ word_prefix, const int* __restrict__ chunk_off,
                                                        long long* __restrict__ sums, int* __restrict__ cnt,
                                                        int* __restrict__ out_vidx, float4* __restrict__ out) {
+  pdl_enter();
   const int status = gp->status;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = __ldg(in + i);
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(256) vg_finalize_kernel(const VgGrid* __restri
                                                           long long* __restrict__ sums, int* __restrict__ cnt,
                                                           const int* __restrict__ out_vidx, unsigned* __restrict__ bitmap,
                                                           float4* __restrict__ out, int* __restrict__ bbox) {
+  pdl_enter();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     bbox[0] = bbox[1] = bbox[2] = 0x7f7f7f7f;
     bbox[3] = bbox[4] = bbox[5] = (int)0x80808080;
@@ -215,12 +220,13 @@ lsd_status_t vg_run(lsd_voxelgrid* g, const float4* d_in, int n, float leaf, flo
   if (n > g->max_points) { set_error("voxelgrid: %d points exceed capacity %d", n, g->max_points); return LSD_ERR_CAPACITY; }
   if (n <= 0) { LSD_CUDA(cudaMemsetAsync(d_m, 0, sizeof(int), st)); return LSD_OK; }
   const int nb = std::min((n + 255) / 256, 592);
-  vg_minmax_kernel<<<std::min(nb, 148), 256, 0, st>>>(d_in, n, g->bbox);
-  vg_mark_kernel<<<nb, 256, 0, st>>>(d_in, n, leaf, g->max_cells, g->bbox, g->grid, g->bitmap, g->vidx);
-  vg_scan_kernel<<<g->scan_blocks, 256, 0, st>>>(g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->done, d_m, n);
-  vg_accum_kernel<<<nb, 256, 0, st>>>(d_in, n, g->grid, g->bitmap, g->vidx, g->word_prefix, g->chunk_sum, g->sums, g->cnt,
-                                      g->out_vidx, d_out);
-  vg_finalize_kernel<<<nb, 256, 0, st>>>(g->grid, d_m, g->sums, g->cnt, g->out_vidx, g->bitmap, d_out, g->bbox);
+  const int pdl = g->pdl;
+  LSD_LAUNCH(pdl, vg_minmax_kernel, std::min(nb, 148), 256, st, d_in, n, g->bbox);
+  LSD_LAUNCH(pdl, vg_mark_kernel, nb, 256, st, d_in, n, leaf, g->max_cells, g->bbox, g->grid, g->bitmap, g->vidx);
+  LSD_LAUNCH(pdl, vg_scan_kernel, g->scan_blocks, 256, st, g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->done, d_m, n);
+  LSD_LAUNCH(pdl, vg_accum_kernel, nb, 256, st, d_in, n, g->grid, g->bitmap, g->vidx, g->word_prefix, g->chunk_sum, g->sums, g->cnt,
+             g->out_vidx, d_out);
+  LSD_LAUNCH(pdl, vg_finalize_kernel, nb, 256, st, g->grid, d_m, g->sums, g->cnt, g->out_vidx, g->bitmap, d_out, g->bbox);
   LSD_CUDA(cudaGetLastError());
   g->launches += 5;
   return LSD_OK;

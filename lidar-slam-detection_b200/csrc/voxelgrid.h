@@ -30,6 +30,7 @@ struct lsd_voxelgrid {
   int* d_m = nullptr;
   unsigned* done = nullptr;       // last-block ticket of vg_scan_kernel
   long long launches = 0;
+  int pdl = 0;                    // launch the five kernels with programmatic dependent launch (lsd_lio_set_pdl)
 };
 
 namespace lsd {

@@ -20,6 +20,7 @@ _CASES = {
     "scancontext": ("test_gpu_zz_scancontext.py", "SC_OK"),
     "sequence": ("test_gpu_zz_sequence.py", "SEQUENCE_OK"),
     "fastlio_seam": ("test_gpu_zz_fastlio_seam.py", "SEAM_OK"),
+    "pdl": ("test_gpu_zz_pdl.py", "PDL_OK"),      # control flow only: the emulator serialises launches, PDL on == off by construction
     "fuzz_knn": ("simt/fuzz_knn.py", "FUZZ_OK"),   # adversarial map / k-NN inputs, three shapes vs each other and the oracle
     "fuzz_misc": ("simt/fuzz_misc.py", "FUZZ_MISC_OK"),   # voxel grid, key-frame filters, ScanContext descriptor on degenerate inputs
 }

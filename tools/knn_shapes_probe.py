@@ -83,23 +83,31 @@ if "--no-lio" not in sys.argv:
     # shape 3 must equal the default's bit for bit, those of shape 4 (another reduction tree) to rounding
     steps = [bench.make_step(s) for s in range(12)]
     base = None
-    for shape in (0, 3, 4):      # warp per point (default) / flat / flat fused with the plane fit and the reduction
+    import time
+    # (shape, pdl): warp per point (default) / flat / flat fused with the plane fit and the reduction; then the default and the
+    # fused shape again with programmatic dependent launch (lsd_lio_set_pdl: same kernels, launch latency hidden)
+    for shape, pdl in ((0, 0), (3, 0), (4, 0), (0, 1), (4, 1)):
         f = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
         f.map.insert(m, 0)
         f.set_next_id(m.shape[0])
         f.set_knn_shape(shape)
-        ms, errs, poses, launches = [], [], [], []
+        f.set_pdl(pdl)
+        ms, wall, errs, poses, launches = [], [], [], [], []
         for s, (scan, Rgt, tgt, Rp, tp) in enumerate(steps):
+            t0 = time.perf_counter()
             xs, P, info = f.scan(scan, lsdreg.make_state(pos=tp, rot_xyzw=bench.quat_from_R(Rp)), lsdreg.init_cov())
+            t1 = time.perf_counter()
             poses.append(xs.copy())
             if s >= 3:
                 ms.append(info["gpu_ms"]); errs.append(float(np.abs(xs[:3] - tgt).max())); launches.append(info["kernel_launches"])
+                wall.append((t1 - t0) * 1e3)
         poses = np.array(poses)
         if base is None:
             base = poses
         dmax = float(np.abs(poses - base).max())
-        ok = dmax == 0.0 if shape == 3 else dmax < 1e-9
-        print(json.dumps({"lio_knn_shape": shape, "gpu_ms_per_scan_median": float(np.median(ms)), "max_err_m": max(errs),
+        ok = dmax == 0.0 if shape in (0, 3) else dmax < 1e-9
+        print(json.dumps({"lio_knn_shape": shape, "pdl": pdl, "gpu_ms_per_scan_median": float(np.median(ms)),
+                          "wall_ms_per_scan_median": float(np.median(wall)), "max_err_m": max(errs),
                           "kernel_launches_per_scan": float(np.mean(launches)), "max_abs_state_diff_vs_default": dmax,
                           "agrees_with_default": bool(ok)}), flush=True)
         f.close()
