@@ -155,6 +155,23 @@ def gicp(args):
                    covariance_build_ms=float(np.mean(build)), align_ms=float(np.mean(times)), pairs_per_s=pairs / wall,
                    wall_s=wall, iterations=float(np.mean(its)), pos_err_m=err_max,
                    note="host clouds in, H2D + index build + covariances + align inside the timed region; rank r takes pairs r, r+N, ...")
+        if (method == "FAST_VGICP" and world == 1 and not args.no_ref_cuda
+                and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_cuda_vgicp.so"))):
+            # the reference's own CUDA VGICP (FastVGICPCuda + FastVGICPCudaCore, recompiled for sm_100a; "FAST_VGICP_CUDA",
+            # registrations.cpp:43-55: neighbours from its CPU k-d tree, covariances / voxel map / LM loop on the GPU), same pair
+            try:
+                from oracle.reg import RefVgicpCuda
+                m, src, guess, tgt = data[-1]
+                r = RefVgicpCuda(1.0, 64, 0.01, 0)
+                rb, _ = t_ms(lambda: (r.set_target(m), r.set_source(src)))
+                r.align(guess)
+                ra, Tr = t_ms(lambda: r.align(guess), 3)
+                out["reference_cuda_sm100a"] = dict(method="FAST_VGICP_CUDA", covariance_build_ms=rb, align_ms=ra, converged=bool(r.converged),
+                                                    pos_err_m=float(np.abs(Tr[:3, 3] - tgt).max()),
+                                                    note="first run on hardware pending (compiled after round 1's GPU budget was spent)")
+                del r
+            except Exception as e:  # the comparator must never take the measurement down
+                out["reference_cuda_sm100a"] = dict(error=repr(e)[:200])
         if not args.no_cpu and world == 1:
             m, src, guess, tgt = data[-1]
             o = (OracleMatcher("gicp", nthreads=min(16, os.cpu_count() or 1)) if method == "FAST_GICP" else
@@ -207,7 +224,7 @@ if __name__ == "__main__":
     ap.add_argument("--gicp-pairs", type=int, default=4)
     ap.add_argument("--gicp-method", default="FAST_GICP", choices=["FAST_GICP", "FAST_VGICP"])
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the leg that times the reference's own CUDA NDT (oracle/_ref/libref_cuda.so)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the legs that time the reference's own CUDA NDT / VGICP (oracle/_ref/libref_cuda*.so)")
     a = ap.parse_args()
     import contextlib
     import io

@@ -161,6 +161,27 @@ def _load_ref_cuda():
     return L
 
 
+def _load_ref_cuda_vgicp():
+    """The compiled reference CUDA VGICP (oracle/ref_cuda_vgicp.cu -> oracle/_ref/libref_cuda_vgicp.so); lazily, like
+    _load_ref_cuda: loading it needs the CUDA driver."""
+    path = os.path.join(_HERE, "_ref", "libref_cuda_vgicp.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.refvgicp_create.restype = C.c_void_p
+    L.refvgicp_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_int]
+    L.refvgicp_destroy.argtypes = [C.c_void_p]
+    L.refvgicp_set_source.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
+    L.refvgicp_set_target.argtypes = [C.c_void_p, _f, C.c_int, C.c_int]
+    L.refvgicp_linearize.restype = C.c_double
+    L.refvgicp_linearize.argtypes = [C.c_void_p, _d, C.c_void_p, C.c_void_p]
+    L.refvgicp_compute_error.restype = C.c_double
+    L.refvgicp_compute_error.argtypes = [C.c_void_p, _d]
+    L.refvgicp_align.restype = C.c_int
+    L.refvgicp_align.argtypes = [C.c_void_p, _f, _f]
+    return L
+
+
 def _load_ref_ikfom():
     """The compiled reference filter + IMU stage (oracle/ref_ikfom.cpp -> oracle/_ref/libref_ikfom.so)."""
     path = os.path.join(_HERE, "_ref", "libref_ikfom.so")

@@ -302,3 +302,45 @@ class RefNdtCuda:
         out = np.zeros(16, np.float32)
         self.converged = bool(self.L.refndt_align(self.h, np.ascontiguousarray(guess, np.float32).reshape(16), out))
         return out.reshape(4, 4).astype(np.float64)
+
+
+class RefVgicpCuda:
+    """The COMPILED reference CUDA VGICP (fast_gicp::FastVGICPCuda over FastVGICPCudaCore), sm_100a build; needs a GPU.
+    Parameters of registrations.cpp:43-55 ("FAST_VGICP_CUDA"): resolution 1.0, eps 0.01, 64 iterations, k = 20, source /
+    target neighbours from a CPU k-d tree (nn_method 0), DIRECT1 voxel correspondences."""
+    _lib = None
+
+    def __init__(self, resolution=1.0, max_iterations=64, trans_eps=0.01, nn_method=0):
+        if RefVgicpCuda._lib is None:
+            RefVgicpCuda._lib = O._load_ref_cuda_vgicp()
+        if RefVgicpCuda._lib is None:
+            raise RuntimeError("oracle/_ref/libref_cuda_vgicp.so missing (built only where /root/reference exists)")
+        self.L = RefVgicpCuda._lib
+        self.h = self.L.refvgicp_create(resolution, max_iterations, trans_eps, nn_method)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refvgicp_destroy(self.h)
+            self.h = None
+
+    def set_target(self, pts):
+        self.tgt = np.ascontiguousarray(pts, np.float32)
+        self.L.refvgicp_set_target(self.h, self.tgt, self.tgt.shape[0], self.tgt.shape[1])
+
+    def set_source(self, pts):
+        self.src = np.ascontiguousarray(pts, np.float32)
+        self.L.refvgicp_set_source(self.h, self.src, self.src.shape[0], self.src.shape[1])
+
+    def linearize(self, T, deriv=True):
+        T = np.ascontiguousarray(T, np.float64)
+        H, b = np.zeros(36), np.zeros(6)
+        e = self.L.refvgicp_linearize(self.h, T, H.ctypes.data if deriv else None, b.ctypes.data if deriv else None)
+        return e, H.reshape(6, 6), b
+
+    def compute_error(self, T):
+        return self.L.refvgicp_compute_error(self.h, np.ascontiguousarray(T, np.float64))
+
+    def align(self, guess):
+        out = np.zeros(16, np.float32)
+        self.converged = bool(self.L.refvgicp_align(self.h, np.ascontiguousarray(guess, np.float32).reshape(16), out))
+        return out.reshape(4, 4).astype(np.float64)
