@@ -2,8 +2,8 @@
 # Everything written after round 1's GPU budget was spent, on its own, before anything else depends on it.
 set -x
 mkdir -p gpurun_out
-# 1. the five never-run GPU tests, each reported separately (they are non-strict xfails: look for XPASS / the tail on XFAIL)
-for t in flat_knn scancontext sequence fastlio_seam pdl; do
+# 1. the six never-run GPU tests, each reported separately (they are non-strict xfails: look for XPASS / the tail on XFAIL)
+for t in flat_knn scancontext sequence fastlio_seam pdl ref_cuda_vgicp; do
   timeout 900 python -m pytest tests/test_gpu_zz_$t.py -m gpu -q -rxX --runxfail > gpurun_out/r02a_$t.log 2>&1; tail -15 gpurun_out/r02a_$t.log
 done
 # 2. the validated suite, to see that nothing moved
