@@ -308,14 +308,15 @@ def run_experimental_flat(m, nq, timeout_s=150, l2_fetch=None):
     return out
 
 
-def run_experimental_lio_shapes(m, timeout_s=280):
+def run_experimental_lio_shapes(m, timeout_s=330):
     """The LIO scan stream with the flat (3) and fused (4) per-scan search shapes next to the default (0), then shapes 0 and 4
     with programmatic dependent launch; same isolation and the same rule: a variant's times are reported only if its poses
     agree with the default's.  Rows printed before a timeout are kept."""
     import subprocess
     import tempfile
     out = {"what": "per-scan search shapes 0 (default) / 3 (flat) / 4 (flat fused with plane fit + reduction), and shapes 0 / 4 with "
-                   "programmatic dependent launch (_pdl), isolated subprocess, 12 bench steps each, device and wall ms per scan (median of 9)"}
+                   "programmatic dependent launch (_pdl), then with the next scan announced (_prefetch) and its voxel grid pipelined under the "
+                   "running scan (_pipe); isolated subprocess, 12 bench steps each, main-stream device ms and wall ms per scan (median of 9)"}
 
     def rows(text):
         for ln in (text or "").splitlines():
@@ -324,7 +325,8 @@ def run_experimental_lio_shapes(m, timeout_s=280):
                     row = json.loads(ln)
                 except ValueError:
                     continue
-                key = f"shape_{row.pop('lio_knn_shape')}" + ("_pdl" if row.pop("pdl", 0) else "")
+                key = (f"shape_{row.pop('lio_knn_shape')}" + ("_pdl" if row.pop("pdl", 0) else "") + ("_prefetch" if row.pop("prefetch", 0) else "")
+                       + ("_pipe" if row.pop("pipeline_vg", 0) else ""))
                 out[key] = row if row.get("agrees_with_default") else {"agrees_with_default": False, "max_abs_state_diff_vs_default": row.get("max_abs_state_diff_vs_default")}
 
     try:
@@ -500,7 +502,8 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    wall_a, infos_a = run_steps(steps_a, dev_scans, W)
+    PIPE = os.environ.get("LSD_PIPELINE_VG", "")[:1] == "1"   # opt-in: scan s+1 is announced, its voxel grid runs under scan s
+    wall_a, infos_a = run_steps(steps_a, dev_scans, W, prefetch=PIPE)
     clocks = sampler.stop()
     # ---------------- (2) end to end: pinned host buffers, H2D inside the timed region
     host_scans = [torch.from_numpy(stp[0]).pin_memory() for stp in steps_b]
@@ -611,6 +614,7 @@ def main():
                        f"map tile-sharded over {world} GPUs, one scan stream, peer-memory all-reduce of the normal equations"
                        if sharded else f"{world} replicas, independent scan streams, no collective"),
                    "shard_points_this_rank": int(st["points"]),
+                   "pipeline_vg": PIPE,   # voxel grid of scan s+1 on the copy stream under scan s (opt-in, lsd_lio_set_pipeline)
                    "pdl": os.environ.get("LSD_PDL", "")[:1] == "1",   # programmatic dependent launch (opt-in, lsd_lio_set_pdl)
                    "l2": "every step visits a different 120x80 m map block; table+points 4.3 GB >> 126 MB L2",
                    "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream"},

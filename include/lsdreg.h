@@ -234,6 +234,16 @@ lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double
  * uses the staged copy instead of uploading again, so the PCIe transfer of scan k+1 overlaps the registration
  * of scan k.  The host buffer must stay unchanged (and, to overlap, pinned) until that lsd_lio_scan returns. */
 lsd_status_t lsd_lio_prefetch(lsd_lio_t* l, const float* scan_host, int n);
+/* Pipelined voxel grid (no reference counterpart; bit-identical results).  The downsample of a scan depends on nothing the
+ * previous scan computes, so with flag != 0 a prefetched scan is also voxel-grid filtered ahead — on the copy stream, behind
+ * its copy, while the previous scan iterates — and the lsd_lio_scan that adopts it starts at its first neighbour search.
+ * Default 0, or 1 when LSD_PIPELINE_VG=1 is in the environment at lsd_lio_create; ignored on a tile-sharded handle. */
+lsd_status_t lsd_lio_set_pipeline(lsd_lio_t* l, int flag);
+/* How many scans were downsampled ahead, and how many of those a later lsd_lio_scan adopted (either pointer may be NULL). */
+lsd_status_t lsd_lio_pipeline_stats(lsd_lio_t* l, long long* issued, long long* adopted);
+/* The same announcement for a device-resident scan (the pointer later passed to lsd_lio_scan_dev, unchanged until then):
+ * nothing to copy, so this only does something when the pipelined voxel grid is on. */
+lsd_status_t lsd_lio_prefetch_dev(lsd_lio_t* l, const float* scan_dev, int n);
 
 /* ------------------------------------------------------------------------------------------
  * Scan matcher — replaces what select_registration_method() hands out

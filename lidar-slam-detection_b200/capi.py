@@ -96,6 +96,9 @@ SIGNATURES = [
     ("lsd_lio_set_stale_rows", _i, [_vp, _i]),
     ("lsd_lio_set_knn_shape", _i, [_vp, _i]),
     ("lsd_lio_set_pdl", _i, [_vp, _i]),
+    ("lsd_lio_set_pipeline", _i, [_vp, _i]),
+    ("lsd_lio_pipeline_stats", _i, [_vp, _vp, _vp]),
+    ("lsd_lio_prefetch_dev", _i, [_vp, _vp, _i]),
     ("lsd_lio_set_next_id", _i, [_vp, C.c_int32]),
     ("lsd_lio_shard_export", _i, [_vp, _i, _i, _i, _i, _vp]),
     ("lsd_lio_shard_connect", _i, [_vp, _vp]),
@@ -845,6 +848,15 @@ class LioFrontend:
         """0/1 = one warp per scan point, 3 = flat (include/lsdreg.h::lsd_lio_set_knn_shape)."""
         check(lib.lsd_lio_set_knn_shape(self.h, int(shape)))
 
+    def set_pipeline(self, flag: bool):
+        """Voxel grid of a prefetched scan on the copy stream while the previous scan iterates (include/lsdreg.h::lsd_lio_set_pipeline)."""
+        check(lib.lsd_lio_set_pipeline(self.h, int(flag)))
+
+    def pipeline_stats(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        check(lib.lsd_lio_pipeline_stats(self.h, C.byref(a), C.byref(b)))
+        return dict(issued=a.value, adopted=b.value)
+
     def set_pdl(self, flag: bool):
         """Programmatic dependent launch for the scan's kernel chain (include/lsdreg.h::lsd_lio_set_pdl)."""
         check(lib.lsd_lio_set_pdl(self.h, int(flag)))
@@ -931,6 +943,9 @@ class LioFrontend:
         if isinstance(scan, np.ndarray):
             if scan.dtype != np.float32 or not scan.flags.c_contiguous:
                 raise ValueError("prefetch needs the exact float32 C-contiguous buffer later passed to scan()")
+        elif getattr(scan, "is_cuda", False):      # device-resident scan: only the pipelined voxel grid has work to do ahead
+            check(lib.lsd_lio_prefetch_dev(self.h, _ptr(scan), scan.shape[0]))
+            return
         check(lib.lsd_lio_prefetch(self.h, _ptr(scan), scan.shape[0]))
 
     def scan(self, scan, state: np.ndarray, P: np.ndarray):

@@ -741,6 +741,8 @@ static lsd_status_t wait_seq(lsd_lio* l, int slot, double seq) {
 
 static int grid_for(int n) { return std::max(1, std::min((n + kLioBlock - 1) / kLioBlock, kLioMaxGrid)); }
 
+static lsd_status_t issue_deferred_prefetch(lsd_lio* l);
+
 // One h_share_model_geometric evaluation on the loaded scan.  Fills HTH6/HTh6 (after the
 // degeneracy projection when it triggers).  One host synchronisation per evaluation.
 lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH6, double* HTh6, double* res_sum,
@@ -783,6 +785,7 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   }
   LSD_CUDA(cudaGetLastError());
   prof.stop();
+  if (l->issue_in_linearize) { lsd_status_t d = issue_deferred_prefetch(l); if (d) return d; }   // hidden under this evaluation
   { lsd_status_t w = wait_seq(l, kResSeq, seq); if (w) return w; }
   const double* r = l->h_result;
   int q = 0;
@@ -945,7 +948,23 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
 lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
   cudaStream_t st = l->stream;
   if (n < 0 || n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
-  if (downsample) {
+  lsd_lio::Stage* pre = l->pre;
+  l->pre = nullptr;
+  if (downsample && pre && pre->down) {
+    // downsampled on the copy stream while the previous scan iterated (issue_side_vg); the caller made the stream wait
+    // for pre->ev.  The buffers change hands: this scan's feats_down_body / size are the stage's, and the stage gets the
+    // previous scan's (idle once everything queued on the stream so far has run, which the next side voxel grid waits for).
+    std::swap(l->d_body, pre->body);
+    std::swap(l->d_n, pre->dn);
+    pre->down = false;
+    l->side_vg_adopted++;
+    l->n_bound = std::min(n, l->p.max_points);
+    l->n_down = -1;
+  } else if (downsample) {
+    if (l->side_vg_inflight) {   // the voxel grid's scratch is shared with the copy stream's instance
+      LSD_CUDA(cudaStreamWaitEvent(st, l->ev_side_vg, 0));
+      l->side_vg_inflight = false;
+    }
     ProfScope prof(l, 2);
     l->vg->pdl = (l->pdl && l->sc.world <= 1) ? 1 : 0;
     lsd_status_t s = vg_run(l->vg, d_scan, n, l->p.filter_size_surf, l->d_body, l->d_n, st);
@@ -963,7 +982,7 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
     l->n_down = n;
   }
   if (l->stale_rows) {
-    LSD_LAUNCH(l->pdl && l->sc.world <= 1, lio_resize_rows_kernel, 32, 256, st, l->d_n, l->p.max_points, l->d_n + 8, l->rows_parity, l->d_near_cnt);
+    LSD_LAUNCH(l->pdl && l->sc.world <= 1, lio_resize_rows_kernel, 32, 256, st, l->d_n, l->p.max_points, l->d_rows, l->rows_parity, l->d_near_cnt);
     l->rows_parity ^= 1;
     l->launches += 1;
     LSD_CUDA(cudaGetLastError());
@@ -984,15 +1003,48 @@ static lsd_status_t read_n_down(lsd_lio* l) {
 // A prefetch request recorded by lsd_lio_prefetch is turned into the actual copy here, right after this scan's
 // voxel-grid kernels were launched: the driver calls cost host time (~5 us) that is now hidden under GPU work
 // instead of delaying the scan's first launch.  Target: the staging slot this scan does not read.
+// Pipelined voxel grid (lsd_lio_set_pipeline): downsample the staged scan on the copy stream, behind its H2D copy, into the
+// stage's own feats_down_body / size.  The voxel grid's scratch is shared with the main stream's instance, hence the event
+// hand-shake: this one starts after everything queued on the main stream so far (the running scan's own voxel grid, the
+// previous scan's map insert — the last reader of the buffer the stage now owns), and a later voxel grid on the main
+// stream waits for ev_side_vg.  sg->ev is re-recorded behind the voxel grid, so the scan that adopts the stage waits once.
+static lsd_status_t issue_side_vg(lsd_lio* l, lsd_lio::Stage* sg, const float4* src) {
+  if (!l->main_ev_fresh) LSD_CUDA(cudaEventRecord(l->ev_main_vg, l->stream));   // else: recorded right behind this scan's load step
+  l->main_ev_fresh = false;
+  LSD_CUDA(cudaStreamWaitEvent(l->copy_stream, l->ev_main_vg, 0));
+  l->vg->pdl = (l->pdl && l->sc.world <= 1) ? 1 : 0;
+  lsd_status_t s = vg_run(l->vg, src, sg->n, l->p.filter_size_surf, sg->body, sg->dn, l->copy_stream);
+  if (s) return s;
+  l->launches += 5;
+  LSD_CUDA(cudaEventRecord(sg->ev, l->copy_stream));
+  LSD_CUDA(cudaEventRecord(l->ev_side_vg, l->copy_stream));
+  l->side_vg_inflight = true;
+  l->side_vg_issued++;
+  sg->down = true;
+  return LSD_OK;
+}
+
+// A prefetch request recorded by lsd_lio_prefetch(_dev) is turned into the actual copy (and, pipelined, the voxel grid)
+// here, once this scan's first kernels are in flight: the driver calls cost host time (~5 us, ~20 us with the voxel grid)
+// that is hidden under GPU work instead of delaying the scan's first launch.  Target: the staging slot this scan does not read.
 static lsd_status_t issue_deferred_prefetch(lsd_lio* l) {
+  l->issue_in_linearize = false;
   if (!l->defer_pending) return LSD_OK;
   l->defer_pending = false;
   lsd_lio::Stage* sg = nullptr;
   for (int i = 0; i < 2; i++) if (i != l->busy_slot && !l->stage[i].valid) sg = &l->stage[i];
   if (!sg) return LSD_OK;  // both slots taken: the request is dropped, the later lsd_lio_scan uploads inline
-  LSD_CUDA(cudaMemcpyAsync(sg->buf, l->defer_host, (size_t)l->defer_n * 16, cudaMemcpyHostToDevice, l->copy_stream));
-  LSD_CUDA(cudaEventRecord(sg->ev, l->copy_stream));
-  sg->host = l->defer_host; sg->n = l->defer_n; sg->valid = true; sg->age = ++l->stage_clock;
+  sg->down = false;
+  sg->is_dev = l->defer_is_dev;
+  sg->host = l->defer_host; sg->n = l->defer_n;
+  const float4* src = reinterpret_cast<const float4*>(l->defer_host);
+  if (!l->defer_is_dev) {
+    LSD_CUDA(cudaMemcpyAsync(sg->buf, l->defer_host, (size_t)l->defer_n * 16, cudaMemcpyHostToDevice, l->copy_stream));
+    LSD_CUDA(cudaEventRecord(sg->ev, l->copy_stream));
+    src = sg->buf;
+  }
+  sg->valid = true; sg->age = ++l->stage_clock;
+  if (l->pipeline_vg && l->sc.world <= 1) return issue_side_vg(l, sg, src);
   return LSD_OK;
 }
 
@@ -1002,10 +1054,21 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
   const bool async = l->p.async_map_insert != 0;
   { lsd_status_t d = lio_drain(l); if (d) return d; }
   LSD_CUDA(cudaEventRecord(l->ev0, st));
+  const bool adopted = l->pre && l->pre->down;
   lsd_status_t s = lio_load(l, d_scan, n, 1);
   if (s) return s;
-  s = issue_deferred_prefetch(l);
-  if (s) return s;
+  if (l->pipeline_vg && l->defer_pending) {
+    // everything the next scan's voxel grid must wait for is queued by now (this scan's own voxel grid if it ran one, the
+    // previous scan's map insert): mark the spot, so that it may overlap this scan's first evaluation too
+    LSD_CUDA(cudaEventRecord(l->ev_main_vg, st));
+    l->main_ev_fresh = true;
+  }
+  if (adopted) {
+    l->issue_in_linearize = true;   // no voxel grid in flight to hide the driver calls behind: wait for the first search
+  } else {
+    s = issue_deferred_prefetch(l);
+    if (s) return s;
+  }
   lsd_lio_info_t inf;
   memset(&inf, 0, sizeof(inf));
   lsd_status_t ret = LSD_OK;
@@ -1027,6 +1090,8 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
       if (m) return m;
     }
   }
+  if (l->issue_in_linearize) { s = issue_deferred_prefetch(l); if (s) return s; }   // no evaluation ran (seeding scan)
+  l->main_ev_fresh = false;
   LSD_CUDA(cudaEventRecord(l->ev1, st));
   if (async && inf.n_added == -1) {
     // the pose is final; the map insert finishes in the background.  gpu_ms / n_added reported now
@@ -1099,11 +1164,14 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   auto A = [&](void** ptr, size_t b) { if (e == cudaSuccess) e = cudaMalloc(ptr, b); if (e == cudaSuccess) e = cudaMemset(*ptr, 0, b); };
   for (int i = 0; i < 2; i++) {
     A((void**)&l->stage[i].buf, (size_t)p->max_scan_points * 16);
+    A((void**)&l->stage[i].body, (size_t)p->max_scan_points * 16);   // pipelined voxel grid: the stage's feats_down_body / size
+    A((void**)&l->stage[i].dn, 64);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->stage[i].ev, cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking);
   A((void**)&l->d_body, (size_t)p->max_scan_points * 16);  // voxel-grid output may equal the input size
   A((void**)&l->d_n, 64);
+  A((void**)&l->d_rows, 64);
   A((void**)&l->d_near, mp * 5 * 16);
   A((void**)&l->d_near_cnt, mp * 4);
   A((void**)&l->d_selected, mp);
@@ -1120,6 +1188,8 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_added, 64);
   if (e == cudaSuccess) { *l->h_added = 0; e = cudaEventCreate(&l->ev0); }
   if (e == cudaSuccess) e = cudaEventCreate(&l->ev1);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->ev_main_vg, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->ev_side_vg, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&l->pev[0]);
   if (e == cudaSuccess) e = cudaEventCreate(&l->pev[1]);
   if (e == cudaSuccess) {  // memset(point_selected_surf, true), laserMapping.cpp:1089
@@ -1131,6 +1201,7 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   cudaStreamDestroy(l->map->stream); l->map->stream = l->stream;
   cudaStreamDestroy(l->vg->stream); l->vg->stream = l->stream;
   { const char* ev = getenv("LSD_PDL"); l->pdl = (ev && ev[0] == '1') ? 1 : 0; }
+  { const char* ev = getenv("LSD_PIPELINE_VG"); l->pipeline_vg = (ev && ev[0] == '1') ? 1 : 0; }
   *out = l;
   return LSD_OK;
 }
@@ -1141,7 +1212,9 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   if (l->stream) cudaStreamSynchronize(l->stream);
   if (l->copy_stream) { cudaStreamSynchronize(l->copy_stream); cudaStreamDestroy(l->copy_stream); }
   for (int i = 0; i < 2; i++) if (l->stage[i].ev) cudaEventDestroy(l->stage[i].ev);
-  void* ptrs[] = {l->stage[0].buf, l->stage[1].buf, l->d_body, l->d_n, l->d_near, l->d_near_cnt, l->d_selected, l->d_flags, l->d_plane, l->d_world,
+  if (l->ev_main_vg) cudaEventDestroy(l->ev_main_vg);
+  if (l->ev_side_vg) cudaEventDestroy(l->ev_side_vg);
+  void* ptrs[] = {l->stage[0].buf, l->stage[1].buf, l->stage[0].body, l->stage[1].body, l->stage[0].dn, l->stage[1].dn, l->d_rows, l->d_body, l->d_n, l->d_near, l->d_near_cnt, l->d_selected, l->d_flags, l->d_plane, l->d_world,
                   l->d_partials, l->d_done, l->d_added, l->d_pabcd, l->d_plane_ok};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(l->h_result); cudaFreeHost(l->h_added);
@@ -1167,7 +1240,7 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   cudaSetDevice(l->device);
   // start from empty rows either way: a default-constructed Nearest_Points
   LSD_CUDA(cudaMemsetAsync(l->d_near_cnt, 0, (size_t)l->p.max_points * 4, l->stream));
-  LSD_CUDA(cudaMemsetAsync(l->d_n + 8, 0, 8, l->stream));
+  LSD_CUDA(cudaMemsetAsync(l->d_rows, 0, 8, l->stream));
   LSD_CUDA(cudaStreamSynchronize(l->stream));
   l->stale_rows = flag != 0;
   l->rows_parity = 0;
@@ -1178,6 +1251,22 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
 lsd_status_t lsd_lio_set_pdl(lsd_lio_t* l, int flag) {
   if (!l) return LSD_ERR_INVALID;
   l->pdl = flag ? 1 : 0;
+  return LSD_OK;
+}
+
+// Pipelined voxel grid (lio.h): the downsample of a prefetched scan runs on the copy stream while the previous scan
+// iterates.  Off by default; LSD_PIPELINE_VG=1 in the environment turns it on at lsd_lio_create.  Bit-identical results:
+// the voxel grid is deterministic and reads nothing a scan computes.
+lsd_status_t lsd_lio_set_pipeline(lsd_lio_t* l, int flag) {
+  if (!l) return LSD_ERR_INVALID;
+  l->pipeline_vg = flag ? 1 : 0;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_lio_pipeline_stats(lsd_lio_t* l, long long* issued, long long* adopted) {
+  if (!l) return LSD_ERR_INVALID;
+  if (issued) *issued = l->side_vg_issued;
+  if (adopted) *adopted = l->side_vg_adopted;
   return LSD_OK;
 }
 
@@ -1361,29 +1450,48 @@ lsd_status_t lsd_lio_map_incremental(lsd_lio_t* l, const double* state26, int* n
   return s;
 }
 
-lsd_status_t lsd_lio_prefetch(lsd_lio_t* l, const float* scan_host, int n) {
-  if (!l || !scan_host || n <= 0) return LSD_ERR_INVALID;
-  if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
-  LSD_CUDA(cudaSetDevice(l->device));
+static lsd_status_t prefetch_request(lsd_lio* l, const float* scan, int n, bool is_dev) {
   if (l->stage[0].valid || l->stage[1].valid) {
-    // a staged scan is waiting to be registered: that lsd_lio_scan call issues this copy once its first kernels
-    // are in flight (issue_deferred_prefetch), so the driver calls do not delay it
-    l->defer_host = scan_host; l->defer_n = n; l->defer_pending = true;
+    // a staged scan is waiting to be registered: that lsd_lio_scan call issues this copy (and voxel grid) once its first
+    // kernels are in flight (issue_deferred_prefetch), so the driver calls do not delay it
+    l->defer_host = scan; l->defer_n = n; l->defer_pending = true; l->defer_is_dev = is_dev;
     return LSD_OK;
   }
   // Every staging buffer is idle here: the voxel grid of the last scan (their only reader) finished before
   // lsd_lio_scan returned.
-  lsd_lio::Stage* sg = free_stage(l);
-  LSD_CUDA(cudaMemcpyAsync(sg->buf, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->copy_stream));
-  LSD_CUDA(cudaEventRecord(sg->ev, l->copy_stream));
-  sg->host = scan_host; sg->n = n; sg->valid = true; sg->age = ++l->stage_clock;
-  return LSD_OK;
+  l->defer_host = scan; l->defer_n = n; l->defer_pending = true; l->defer_is_dev = is_dev;
+  return issue_deferred_prefetch(l);
+}
+
+lsd_status_t lsd_lio_prefetch(lsd_lio_t* l, const float* scan_host, int n) {
+  if (!l || !scan_host || n <= 0) return LSD_ERR_INVALID;
+  if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
+  LSD_CUDA(cudaSetDevice(l->device));
+  return prefetch_request(l, scan_host, n, false);
+}
+
+lsd_status_t lsd_lio_prefetch_dev(lsd_lio_t* l, const float* scan_dev, int n) {
+  if (!l || !scan_dev || n <= 0) return LSD_ERR_INVALID;
+  if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
+  if (!l->pipeline_vg || l->sc.world > 1) return LSD_OK;   // nothing to copy: only the pipelined voxel grid has work to do ahead
+  LSD_CUDA(cudaSetDevice(l->device));
+  return prefetch_request(l, scan_dev, n, true);
 }
 
 lsd_status_t lsd_lio_scan_dev(lsd_lio_t* l, const float* scan_dev, int n, double* state26_inout, double* P529_inout,
                               lsd_lio_info_t* info) {
   if (!l || (n > 0 && !scan_dev) || !state26_inout || !P529_inout) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(l->device));
+  l->pre = nullptr;
+  if (l->defer_pending && l->defer_is_dev && l->defer_host == scan_dev && l->defer_n == n) l->defer_pending = false;  // requested, never issued
+  for (int i = 0; i < 2; i++) {
+    lsd_lio::Stage* sg = &l->stage[i];
+    if (sg->valid && sg->is_dev && sg->host == scan_dev && sg->n == n) {   // downsampled ahead by lsd_lio_prefetch_dev
+      LSD_CUDA(cudaStreamWaitEvent(l->stream, sg->ev, 0));
+      sg->valid = false;
+      l->pre = sg->down ? sg : nullptr;
+    }
+  }
   return lio_scan(l, reinterpret_cast<const float4*>(scan_dev), n, state26_inout, P529_inout, info);
 }
 
@@ -1393,12 +1501,15 @@ lsd_status_t lsd_lio_scan(lsd_lio_t* l, const float* scan_host, int n, double* s
   LSD_CUDA(cudaSetDevice(l->device));
   if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
   lsd_lio::Stage* sg = nullptr;
-  for (int i = 0; i < 2; i++) if (l->stage[i].valid && l->stage[i].host == scan_host && l->stage[i].n == n) sg = &l->stage[i];
-  if (l->defer_pending && l->defer_host == scan_host && l->defer_n == n) l->defer_pending = false;  // requested, never issued: upload inline
+  l->pre = nullptr;
+  for (int i = 0; i < 2; i++) if (l->stage[i].valid && !l->stage[i].is_dev && l->stage[i].host == scan_host && l->stage[i].n == n) sg = &l->stage[i];
+  if (l->defer_pending && !l->defer_is_dev && l->defer_host == scan_host && l->defer_n == n) l->defer_pending = false;  // requested, never issued: upload inline
   if (sg) {  // uploaded by lsd_lio_prefetch while the previous scan was being registered
     LSD_CUDA(cudaStreamWaitEvent(l->stream, sg->ev, 0));
+    l->pre = sg->down ? sg : nullptr;   // also downsampled ahead (lsd_lio_set_pipeline)
   } else {
     sg = free_stage(l);
+    sg->down = false; sg->is_dev = false;
     LSD_CUDA(cudaMemcpyAsync(sg->buf, scan_host, (size_t)n * 16, cudaMemcpyHostToDevice, l->stream));
   }
   sg->valid = false;

@@ -27,7 +27,11 @@ struct lsd_lio {
   cudaStream_t stream = nullptr;
   // raw scan staging (host-pointer entry points): two slots, so lsd_lio_prefetch can upload scan k+1
   // while scan k (staged in the other slot) is being registered
-  struct Stage { float4* buf = nullptr; const float* host = nullptr; int n = 0; bool valid = false; cudaEvent_t ev = nullptr; long long age = 0; };
+  struct Stage {
+    float4* buf = nullptr; const float* host = nullptr; int n = 0; bool valid = false; cudaEvent_t ev = nullptr; long long age = 0;
+    // pipelined voxel grid (lsd_lio_set_pipeline): the staged scan, already downsampled on the copy stream
+    float4* body = nullptr; int* dn = nullptr; bool down = false; bool is_dev = false;
+  };
   Stage stage[2];
   long long stage_clock = 0;
   cudaStream_t copy_stream = nullptr;
@@ -35,6 +39,17 @@ struct lsd_lio {
   const float* defer_host = nullptr;  // prefetch request whose copy is issued from inside the next lsd_lio_scan,
   int defer_n = 0;                    // after that scan's first kernels are in flight
   bool defer_pending = false;
+  bool defer_is_dev = false;          // the request names a device-resident scan (lsd_lio_prefetch_dev): no copy, voxel grid only
+  // pipelined voxel grid: the downsample of scan k+1 depends on nothing scan k computes, so with the flag on it runs on
+  // the copy stream (after the H2D copy) while scan k iterates, and lsd_lio_scan(k+1) starts at its first search
+  int pipeline_vg = 0;                // lsd_lio_set_pipeline
+  long long side_vg_issued = 0, side_vg_adopted = 0;   // lsd_lio_pipeline_stats
+  Stage* pre = nullptr;               // stage whose downsampled scan the lio_scan in progress adopts (buffers are swapped)
+  bool issue_in_linearize = false;    // deferred prefetch to be issued behind the first evaluation's kernels
+  bool main_ev_fresh = false;         // ev_main_vg was recorded by the lio_scan in progress, right behind its load step
+  bool side_vg_inflight = false;      // a voxel grid is queued on the copy stream (its scratch is shared with the main stream's)
+  cudaEvent_t ev_main_vg = nullptr, ev_side_vg = nullptr;
+  int* d_rows = nullptr;              // rows alive in Nearest_Points, double-buffered by scan parity (lio_resize_rows_kernel)
   float4* d_body = nullptr;     // feats_down_body
   int* d_n = nullptr;           // feats_down_size, device resident
   float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)

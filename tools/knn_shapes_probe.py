@@ -84,18 +84,30 @@ if "--no-lio" not in sys.argv:
     steps = [bench.make_step(s) for s in range(12)]
     base = None
     import time
-    # (shape, pdl): warp per point (default) / flat / flat fused with the plane fit and the reduction; then the default and the
-    # fused shape again with programmatic dependent launch (lsd_lio_set_pdl: same kernels, launch latency hidden)
-    for shape, pdl in ((0, 0), (3, 0), (4, 0), (0, 1), (4, 1)):
+    # (shape, pdl, prefetch, pipeline): warp per point (default) / flat / flat fused with the plane fit and the reduction; the
+    # default and the fused shape again with programmatic dependent launch (lsd_lio_set_pdl: same kernels, launch latency
+    # hidden); then with the next scan announced (lsd_lio_prefetch: H2D copy of scan k+1 under scan k) and, on top of that,
+    # the pipelined voxel grid (lsd_lio_set_pipeline: scan k+1 is also downsampled under scan k)
+    pinned = None
+    for shape, pdl, pre, pipe in ((0, 0, 0, 0), (3, 0, 0, 0), (4, 0, 0, 0), (0, 1, 0, 0), (4, 1, 0, 0),
+                                  (0, 0, 1, 0), (0, 0, 1, 1), (0, 1, 1, 1), (4, 1, 1, 1)):
         f = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
         f.map.insert(m, 0)
         f.set_next_id(m.shape[0])
         f.set_knn_shape(shape)
         f.set_pdl(pdl)
+        f.set_pipeline(pipe)
+        if pre and pinned is None:
+            pinned = [torch.from_numpy(np.ascontiguousarray(st[0], np.float32)).pin_memory() if torch.cuda.is_available()
+                      else np.ascontiguousarray(st[0], np.float32) for st in steps]
         ms, wall, errs, poses, launches = [], [], [], [], []
+        if pre:
+            f.prefetch(pinned[0])
         for s, (scan, Rgt, tgt, Rp, tp) in enumerate(steps):
             t0 = time.perf_counter()
-            xs, P, info = f.scan(scan, lsdreg.make_state(pos=tp, rot_xyzw=bench.quat_from_R(Rp)), lsdreg.init_cov())
+            if pre and s + 1 < len(steps):
+                f.prefetch(pinned[s + 1])
+            xs, P, info = f.scan(pinned[s] if pre else scan, lsdreg.make_state(pos=tp, rot_xyzw=bench.quat_from_R(Rp)), lsdreg.init_cov())
             t1 = time.perf_counter()
             poses.append(xs.copy())
             if s >= 3:
@@ -106,8 +118,11 @@ if "--no-lio" not in sys.argv:
             base = poses
         dmax = float(np.abs(poses - base).max())
         ok = dmax == 0.0 if shape in (0, 3) else dmax < 1e-9
-        print(json.dumps({"lio_knn_shape": shape, "pdl": pdl, "gpu_ms_per_scan_median": float(np.median(ms)),
-                          "wall_ms_per_scan_median": float(np.median(wall)), "max_err_m": max(errs),
-                          "kernel_launches_per_scan": float(np.mean(launches)), "max_abs_state_diff_vs_default": dmax,
-                          "agrees_with_default": bool(ok)}), flush=True)
+        row = {"lio_knn_shape": shape, "pdl": pdl, "prefetch": pre, "pipeline_vg": pipe, "gpu_ms_per_scan_median": float(np.median(ms)),
+               "wall_ms_per_scan_median": float(np.median(wall)), "max_err_m": max(errs),
+               "kernel_launches_per_scan": float(np.mean(launches)), "max_abs_state_diff_vs_default": dmax,
+               "agrees_with_default": bool(ok)}
+        if pipe:
+            row["pipeline_stats"] = f.pipeline_stats()
+        print(json.dumps(row), flush=True)
         f.close()
