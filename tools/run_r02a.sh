@@ -26,3 +26,4 @@ done
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r02a_bench_ref.json 2> gpurun_out/r02a_bench_ref.err; tail -c 600 gpurun_out/r02a_bench_ref.json
 timeout 900 python bench.py > gpurun_out/r02a_bench.json 2> gpurun_out/r02a_bench.err; tail -c 1500 gpurun_out/r02a_bench.json
 LSD_PDL=1 timeout 600 python bench.py --no-experimental --no-knn-batch > gpurun_out/r02a_bench_pdl.json 2> gpurun_out/r02a_bench_pdl.err; tail -c 1500 gpurun_out/r02a_bench_pdl.json
+LSD_PDL=1 LSD_PIPELINE_VG=1 timeout 600 python bench.py --no-experimental --no-knn-batch > gpurun_out/r02a_bench_pdl_pipe.json 2> gpurun_out/r02a_bench_pdl_pipe.err; tail -c 1500 gpurun_out/r02a_bench_pdl_pipe.json
