@@ -922,7 +922,7 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
   ProfScope prof(l, 3);
   const int nb = std::max(1, (l->n_bound + 255) / 256);
   const double mseq = (double)(++l->mi_seq);
-  const int pdl = l->pdl && l->sc.world <= 1;
+  const int pdl = 0;   // its stream predecessor is the memset above, not a kernel: nothing to hide, so keep the plain launch
   LSD_LAUNCH(pdl, lio_map_incremental_kernel, nb, 256, st, l->map->view, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt, l->ekf_inited,
              (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added,
              l->sc, mseq, l->d_done);
