@@ -1451,6 +1451,8 @@ lsd_status_t lsd_lio_map_incremental(lsd_lio_t* l, const double* state26, int* n
 }
 
 static lsd_status_t prefetch_request(lsd_lio* l, const float* scan, int n, bool is_dev) {
+  for (int i = 0; i < 2; i++)   // already staged (announced twice): one copy is enough, a second would outlive the scan that adopts the first
+    if (l->stage[i].valid && l->stage[i].is_dev == is_dev && l->stage[i].host == scan && l->stage[i].n == n) return LSD_OK;
   if (l->stage[0].valid || l->stage[1].valid) {
     // a staged scan is waiting to be registered: that lsd_lio_scan call issues this copy (and voxel grid) once its first
     // kernels are in flight (issue_deferred_prefetch), so the driver calls do not delay it

@@ -22,7 +22,8 @@ _CASES = {
     "fastlio_seam": ("test_gpu_zz_fastlio_seam.py", "SEAM_OK"),
     "pdl": ("test_gpu_zz_pdl.py", "PDL_OK"),      # control flow only: the emulator serialises launches, PDL on == off by construction
     "fuzz_knn": ("simt/fuzz_knn.py", "FUZZ_OK"),   # adversarial map / k-NN inputs, three shapes vs each other and the oracle
-    "fuzz_misc": ("simt/fuzz_misc.py", "FUZZ_MISC_OK"),   # voxel grid, key-frame filters, ScanContext descriptor on degenerate inputs
+    "fuzz_misc": ("simt/fuzz_misc.py", "FUZZ_MISC_OK"),
+    "fuzz_pipeline": ("simt/fuzz_pipeline.py", "FUZZ_PIPELINE_OK"),   # random announce / register schedules: staging slots, deferred requests, buffer hand-over   # voxel grid, key-frame filters, ScanContext descriptor on degenerate inputs
 }
 
 _PROLOGUE = r'''
