@@ -1052,6 +1052,7 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
   cudaStream_t st = l->stream;
   const long long launches0 = l->launches;
   const bool async = l->p.async_map_insert != 0;
+  l->main_ev_fresh = false;   // (a scan that returned early on an error may have left it set)
   { lsd_status_t d = lio_drain(l); if (d) return d; }
   LSD_CUDA(cudaEventRecord(l->ev0, st));
   const bool adopted = l->pre && l->pre->down;
