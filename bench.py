@@ -349,6 +349,40 @@ def run_experimental_lio_shapes(m, timeout_s=330):
     return out
 
 
+def run_experimental_flags_bench(args, pos_err_ref, timeout_s=300):
+    """This very bench (value + e2e legs only) in a child process with the two launch-side switches on — programmatic
+    dependent launch and the pipelined voxel grid (LSD_PDL=1 LSD_PIPELINE_VG=1).  Both leave every bit of
+    the result unchanged, so the child's worst position error over the timed steps must EQUAL this process's: its numbers
+    are reported only then.  Nothing here can reach `value`, `e2e` or `roofline` of this line."""
+    import subprocess
+    out = {"what": "child bench.py with LSD_PDL=1 LSD_PIPELINE_VG=1 (same steps, same K / W), reported only if its pos_err_max_m equals the parent's"}
+    env = dict(os.environ, LSD_PDL="1", LSD_PIPELINE_VG="1")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline",
+           "--no-knn-batch", "--no-experimental", "--streams", "0"]
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout_s, env=env)
+        row = None
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{") and '"metric"' in ln:
+                try:
+                    row = json.loads(ln)
+                except ValueError:
+                    pass
+        if row is None:
+            out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no JSON line")
+            return out
+        same = row.get("pos_err_max_m") == pos_err_ref
+        out["identical_pos_err"] = bool(same)
+        out["pos_err_max_m"] = row.get("pos_err_max_m")
+        if same and row.get("config", {}).get("pdl") and row.get("config", {}).get("pipeline_vg"):
+            out.update(value=row["value"], unit=row["unit"], ms_per_step=row["ms_per_step"], device_ms_per_step=row.get("device_ms_per_step"),
+                       e2e=row.get("e2e", {}).get("value"), e2e_ms_per_step=row.get("e2e", {}).get("ms_per_step"),
+                       gpu_launches=row.get("gpu_launches"))
+    except Exception as e:  # noqa: BLE001  (timeout, spawn failure: the leg is optional)
+        out["error"] = f"{type(e).__name__}: {str(e)[:300]}"
+    return out
+
+
 def run_streams(torch, lsdreg, local, m, steps, dev_scans, W, K, S, prior_vec, P0):
     """S host threads, each with its own LioFrontend (own map replica, own CUDA stream), all registering the same K
     device-resident scans concurrently.  ctypes releases the GIL inside the C calls."""
@@ -599,6 +633,7 @@ def main():
             # voxel costs half the DRAM traffic.  No gain for the thread shape in round 1 (issue bound); the flat shape may differ
             experimental["knn_flat_shape_l2_fetch_64"] = run_experimental_flat(m, args.knn_batch, l2_fetch=64)
         experimental["lio_search_shapes"] = run_experimental_lio_shapes(m)
+        experimental["flags_on_bench"] = run_experimental_flags_bench(args, float(np.max([i["pos_err"] for i in infos_a])))
 
     iters = float(np.mean([i["iterations"] for i in infos_a]))
     h2d = int(np.mean([stp[0].shape[0] for stp in steps_b[W:]]) * 16)
