@@ -25,6 +25,7 @@ import time
 
 import numpy as np
 
+_T0 = time.time()   # process start: the experimental legs' wall-clock budget counts from here
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 
@@ -627,13 +628,26 @@ def main():
     # is already measured; clocks were sampled during the timed region)
     experimental = None
     if world == 1 and not args.no_knn_batch and not args.no_experimental:
-        experimental = {"knn_flat_shape": run_experimental_flat(m, args.knn_batch)}
-        if "error" not in experimental["knn_flat_shape"]:
+        # The JSON line is printed after these legs, so together they get a wall-clock budget counted from process start
+        # (LSD_BENCH_BUDGET_S, default 600 s): a leg starts only with more than a minute left and its timeout is clipped to
+        # what is left, so the line is out within ~10 minutes whatever the legs do.  Most informative legs first.
+        budget = float(os.environ.get("LSD_BENCH_BUDGET_S", "600"))
+        left = lambda: budget - (time.time() - _T0)   # noqa: E731
+        experimental = {}
+
+        def leg(name, fn, default_timeout):
+            if left() < 60.0:
+                experimental[name] = {"skipped": "bench wall-clock budget spent (LSD_BENCH_BUDGET_S)"}
+                return
+            experimental[name] = fn(min(default_timeout, left() - 20.0))
+
+        leg("lio_search_shapes", lambda t: run_experimental_lio_shapes(m, timeout_s=t), 330)
+        leg("flags_on_bench", lambda t: run_experimental_flags_bench(args, float(np.max([i["pos_err"] for i in infos_a])), timeout_s=t), 300)
+        leg("knn_flat_shape", lambda t: run_experimental_flat(m, args.knn_batch, timeout_s=t), 150)
+        if "error" not in experimental["knn_flat_shape"] and "skipped" not in experimental["knn_flat_shape"]:
             # the 128-byte cell line holds header + 3 points in its first 64 bytes (rho = 1.5): with 64-byte L2 fetches a
             # voxel costs half the DRAM traffic.  No gain for the thread shape in round 1 (issue bound); the flat shape may differ
-            experimental["knn_flat_shape_l2_fetch_64"] = run_experimental_flat(m, args.knn_batch, l2_fetch=64)
-        experimental["lio_search_shapes"] = run_experimental_lio_shapes(m)
-        experimental["flags_on_bench"] = run_experimental_flags_bench(args, float(np.max([i["pos_err"] for i in infos_a])))
+            leg("knn_flat_shape_l2_fetch_64", lambda t: run_experimental_flat(m, args.knn_batch, timeout_s=t, l2_fetch=64), 150)
 
     iters = float(np.mean([i["iterations"] for i in infos_a]))
     h2d = int(np.mean([stp[0].shape[0] for stp in steps_b[W:]]) * 16)
