@@ -170,9 +170,8 @@ lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag);
  * output); 0 (default this round) treats such a point as having no neighbours.  Either call
  * empties the rows. */
 lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
-/* Shape of the per-scan neighbour search (no reference counterpart; Nearest_Points is bit-identical either way):
- * 0 or 1 = one warp per scan point, 3 = flat (a warp owns 32 scan points, csrc/knn_flat.cuh), 4 = flat search fused with
- * the plane fit and the reduction in one launch (lio_search_fused_kernel; sums equal the two-kernel path's to rounding). */
+/* Shape of the per-scan neighbour search (no reference counterpart): 0 or 1 = one warp per scan point (the only shape;
+ * the flat shapes of round 1 measured slower on B200 and were retired). */
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape);
 /* Programmatic dependent launch for the per-scan kernel chain (no reference counterpart; results are bit-identical either
  * way): flag != 0 launches the voxel-grid, search, h-model and map_incremental kernels with the programmatic stream

@@ -15,6 +15,8 @@
 // (bit-reproducible).  No N x 15 matrix ever exists.
 #include <unistd.h>
 
+#include <chrono>
+
 #include "eskf.hpp"
 #include "knn.cuh"
 #include "lio.h"
@@ -312,11 +314,26 @@ constexpr int kHmWarps = 8;
 __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, int stencil, const float4* __restrict__ body,
                                                                 const int* __restrict__ n_ptr, int cap, LioPose ps,
                                                                 float4* __restrict__ near, int* __restrict__ near_cnt,
-                                                                int keep_stale) {
+                                                                int keep_stale, int* __restrict__ rows, int resize_parity) {
   pdl_enter();
   __shared__ __align__(16) unsigned char s_list[kHmWarps * kWarpListBytes];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = min(*n_ptr, cap);
+  const int n = min(__ldcg(n_ptr), cap);
+  if (resize_parity >= 0) {
+    // Nearest_Points.resize(feats_down_size) (laserMapping.cpp:1273), folded into the scan's first search: rows the new
+    // scan does not have are destroyed, so a later, larger scan finds them empty.  The reference returns before the
+    // resize when feats_down_size < 5 (:1252-1256).  rows[2] is double-buffered by scan parity: this launch reads the
+    // number of rows alive from rows[parity ^ 1] (published by the previous resize) and publishes its own in
+    // rows[parity], so no block can read a value another block of the same launch has already replaced.
+    const int prev = min(__ldcg(rows + (resize_parity ^ 1)), cap);
+    if (n >= 5)
+      for (int i = n + blockIdx.x * blockDim.x + threadIdx.x; i < prev; i += gridDim.x * blockDim.x) {
+        near_cnt[i] = 0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) near[(size_t)i * 5 + r] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      }
+    if (blockIdx.x == 0 && threadIdx.x == 0) rows[resize_parity] = n >= 5 ? n : prev;
+  }
   WarpList wl;
   wl.d = reinterpret_cast<unsigned*>(s_list + warp * kWarpListBytes);
   wl.id = reinterpret_cast<int*>(wl.d + kCandCap);
@@ -351,62 +368,6 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
   }
 }
 
-// The same search in the flat shape (knn_flat.cuh): a warp owns 32 scan points, every lane fetches lines of voxels that
-// exist.  Selected with lsd_lio_set_knn_shape(l, 3); fixed stencils only.  Writes exactly what lio_knn_kernel writes.
-constexpr int kLioFlatWarps = 2;
-__global__ void __launch_bounds__(kLioFlatWarps * 32) lio_knn_flat_kernel(MapView mv, int st_slot, const float4* __restrict__ body,
-                                                                        const int* __restrict__ n_ptr, int cap, LioPose ps,
-                                                                        float4* __restrict__ near, int* __restrict__ near_cnt,
-                                                                        int keep_stale) {
-  pdl_enter();
-  __shared__ FlatSmem<true> sm[kLioFlatWarps];
-  const int n = min(*n_ptr, cap);
-  const int n_round = (n + 31) & ~31;  // whole warps: padding lanes take part in the warp-wide steps
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-    bool active = i < n;
-    float wx = 0.f, wy = 0.f, wz = 0.f;
-    if (active) {
-      const float4 pb = __ldg(body + i);
-      const double bx = pb.x, by = pb.y, bz = pb.z;
-      const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
-      const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
-      const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
-      wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
-      wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
-      wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
-      if (mv.shard_world > 1) {
-        const int3 hc = pos2grid(wx, wy, wz, mv.inv_res);
-        if (!shard_owns(mv, hc.x, hc.y)) { near_cnt[i] = -1; active = false; }
-      }
-    }
-    FlatTopK<5, true> best;
-    best.init();
-    int found = 0;
-    flat_search<5, true>(mv, c_stencils[st_slot], wx, wy, wz, active, 5.0f, sm[threadIdx.x >> 5], best, found);
-    if (!active) continue;
-    const int nf = min(found, 5);
-    if (keep_stale && nf == 0) continue;
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-      float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-      if (r < nf) q = load_loc(mv, best.loc[r]);
-      near[(size_t)i * 5 + r] = q;
-    }
-    near_cnt[i] = nf;
-  }
-}
-
-// Nearest_Points.resize(feats_down_size) (laserMapping.cpp:1273): rows the new scan does not have are destroyed, so a
-// later, larger scan finds them empty.  rows[2] is double-buffered by scan parity: this launch reads the number of rows
-// alive from rows[parity ^ 1] (written by the previous scan's launch) and publishes its own in rows[parity], so no block
-// can read a value another block of the same launch has already replaced.
-__global__ void lio_resize_rows_kernel(const int* __restrict__ n_ptr, int cap, int* __restrict__ rows, int parity, int* __restrict__ near_cnt) {
-  pdl_enter();
-  const int n = min(*n_ptr, cap), prev = min(rows[parity ^ 1], cap);
-  for (int i = n + blockIdx.x * blockDim.x + threadIdx.x; i < prev; i += gridDim.x * blockDim.x) near_cnt[i] = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) rows[parity] = n;
-}
-
 // ---------------------------------------------------------------- K4+K5: plane fit + residual/Jacobian + reduction
 // One thread per downsampled point.  FIT: first evaluation after a search — fit the plane through
 // Nearest_Points[i] and cache it; !FIT: iterations with ekfom_data.converge == false
@@ -421,7 +382,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
                                                                double* __restrict__ partials, unsigned* __restrict__ done,
                                                                double* __restrict__ result, double seq, ShardComm sc) {
   pdl_enter();
-  const int n_true = *n_ptr;
+  const int n_true = __ldcg(n_ptr);
   const int n = min(n_true, cap);
   double vals[29];
 #pragma unroll
@@ -479,98 +440,6 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
   grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq, sc, 0);
 }
 
-// ---------------------------------------------------------------- K3+K4+K5 in ONE launch (flat search shape)
-// lio_knn_flat_kernel followed by lio_hmodel_kernel<true>, fused: the lane that searched a scan point fits its plane and
-// accumulates its Jacobian row straight from the registers, so a search evaluation costs one launch and one grid drain
-// instead of two and Nearest_Points is written but not read back.  Same arithmetic in the same order per point; the
-// reduction tree differs from the two-kernel path only in its block size (64 points per block instead of 256), so sums
-// agree to rounding, not bit for bit.  Selected with lsd_lio_set_knn_shape(l, 4); single-GPU, fixed stencils.
-constexpr int kLioFusedWarps = 2;
-__global__ void __launch_bounds__(kLioFusedWarps * 32) lio_search_fused_kernel(MapView mv, int st_slot, const float4* __restrict__ body,
-                                                                            const int* __restrict__ n_ptr, int cap, LioPose ps,
-                                                                            float4* __restrict__ near, int* __restrict__ near_cnt, int keep_stale,
-                                                                            unsigned char* __restrict__ selected, float4* __restrict__ pabcd_io,
-                                                                            unsigned char* __restrict__ plane_ok, float4* __restrict__ plane,
-                                                                            float4* __restrict__ world, double* __restrict__ partials,
-                                                                            unsigned* __restrict__ done, double* __restrict__ result, double seq,
-                                                                            ShardComm sc) {
-  pdl_enter();
-  __shared__ FlatSmem<true> sm[kLioFusedWarps];
-  const int n_true = *n_ptr;
-  const int n = min(n_true, cap);
-  const int n_round = (n + 31) & ~31;
-  double vals[29];
-#pragma unroll
-  for (int j = 0; j < 29; j++) vals[j] = 0.0;
-#pragma unroll 1
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-    const bool active = i < n;
-    float wx = 0.f, wy = 0.f, wz = 0.f;
-    double bx = 0, by = 0, bz = 0, lx = 0, ly = 0, lz = 0;
-    float bw = 0.f;
-    if (active) {
-      const float4 pb = __ldg(body + i);
-      bx = pb.x; by = pb.y; bz = pb.z; bw = pb.w;
-      lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
-      ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
-      lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
-      wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
-      wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
-      wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
-    }
-    FlatTopK<5, true> best;
-    best.init();
-    int found = 0;
-    flat_search<5, true>(mv, c_stencils[st_slot], wx, wy, wz, active, 5.0f, sm[threadIdx.x >> 5], best, found);
-    if (!active) continue;
-    world[i] = make_float4(wx, wy, wz, bw);
-    int nf = min(found, 5);
-    float px[5], py[5], pz[5];
-    if (keep_stale && nf == 0) {   // the row keeps what it held (lsd_lio_set_stale_rows): fit on the stored neighbours
-      nf = near_cnt[i];
-#pragma unroll
-      for (int r = 0; r < 5; r++) { const float4 q = near[(size_t)i * 5 + r]; px[r] = q.x; py[r] = q.y; pz[r] = q.z; }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 5; r++) {
-        float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (r < nf) q = load_loc(mv, best.loc[r]);
-        near[(size_t)i * 5 + r] = q;
-        px[r] = q.x; py[r] = q.y; pz[r] = q.z;
-      }
-      near_cnt[i] = nf;
-    }
-    float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
-    bool ok = false;
-    if (nf >= 5) ok = esti_plane_dev(px, py, pz, 0.1f, pabcd);
-    pabcd_io[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
-    plane_ok[i] = ok ? 1 : 0;
-    bool keep = false;
-    if (ok) {
-      const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];
-      const double s = 1 - 0.9 * fabs((double)pd2) / sqrt(sqrt(bx * bx + by * by + bz * bz));  // laserMapping.cpp:861
-      if ((float)s > 0.9) {
-        keep = true;
-        plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
-        const RowH r = make_row(ps, lx, ly, lz, pabcd, pd2);
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-#pragma unroll
-          for (int c = a; c < 6; c++) vals[q++] += r.row[a] * r.row[c];
-        }
-#pragma unroll
-        for (int a = 0; a < 6; a++) vals[21 + a] += r.row[a] * r.h;
-        vals[27] += (double)fabsf(pd2);
-        vals[28] += 1.0;
-      }
-    }
-    selected[i] = keep ? 1 : 0;
-  }
-  block_partials<29>(vals, partials);
-  grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq, sc, 0);
-}
-
 // ---------------------------------------------------------------- degeneracy sums (laserMapping.cpp:946-970)
 // Only launched when the host cannot certify non-degeneracy from the eigenvalues (lio_linearize).
 struct Eig3 { double V[9]; };  // columns = eigenvectors
@@ -580,7 +449,7 @@ __global__ void __launch_bounds__(kLioBlock) lio_degen_kernel(const int* __restr
                                                               unsigned* __restrict__ done, double* __restrict__ result, double seq,
                                                               ShardComm sc) {
   pdl_enter();
-  const int n = min(*n_ptr, cap);
+  const int n = min(__ldcg(n_ptr), cap);
   const double* V = e.V;
   double vals[6] = {0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -611,7 +480,7 @@ __global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, co
                                                                   unsigned* __restrict__ n_added, ShardComm sc, double seq,
                                                                   unsigned* __restrict__ done) {
   pdl_enter();
-  const int n = min(*n_ptr, cap);
+  const int n = min(__ldcg(n_ptr), cap);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const float4 pb = __ldg(body + i);
@@ -682,7 +551,7 @@ __global__ void __launch_bounds__(256) lio_halo_insert_kernel(MapView mv, const 
   if (threadIdx.x == 0) ready = 1;
   __syncthreads();
   __threadfence_system();
-  const int n = min(*n_ptr, cap);
+  const int n = min(__ldcg(n_ptr), cap);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !ready) return;
   const float4 w = world[i];
@@ -700,6 +569,14 @@ __global__ void lio_fill_u8_kernel(unsigned char* p, int n, unsigned char v) {
   if (i < n) p[i] = v;
 }
 __global__ void lio_set_int_kernel(int* p, int v) { *p = v; }
+// a default-constructed Nearest_Points: empty rows (ids -1)
+__global__ void lio_clear_rows_kernel(float4* near, int* near_cnt, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  near_cnt[i] = 0;
+#pragma unroll
+  for (int r = 0; r < 5; r++) near[(size_t)i * 5 + r] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+}
 
 // ---------------------------------------------------------------- host side
 static void pose_from_state(const double* x, LioPose* ps) {
@@ -722,17 +599,24 @@ struct ProfScope {  // CUDA-event timing of one launch group on the LIO stream (
   }
 };
 
-// Spin on the sequence number the kernel publishes into mapped host memory.
+// Spin on the sequence number the kernel publishes into mapped host memory.  The load is an acquire: the sums the
+// kernel stored before the sequence number must not be read ahead of it (aarch64 hosts reorder loads).  Bounded by a
+// wall-clock limit so that a hung kernel (e.g. a peer that never answers the in-kernel all-reduce) becomes an error.
 static lsd_status_t wait_seq(lsd_lio* l, int slot, double seq) {
-  volatile double* r = l->h_result;
+  const double* r = l->h_result + slot;
+  const auto t0 = std::chrono::steady_clock::now();
   for (unsigned long long spins = 0;; spins++) {
-    if (r[slot] == seq) return LSD_OK;
+    if (__atomic_load_n(reinterpret_cast<const unsigned long long*>(r), __ATOMIC_ACQUIRE) == *reinterpret_cast<const unsigned long long*>(&seq)) return LSD_OK;
     if ((spins & 0xfff) == 0xfff) {
       cudaError_t e = cudaStreamQuery(l->stream);
       if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "kernel while waiting for the reduction", __FILE__, __LINE__);
-      if (e == cudaSuccess && r[slot] != seq) {  // stream drained but nothing published: should not happen
-        if (r[slot] == seq) return LSD_OK;
+      if (e == cudaSuccess) {  // stream drained: the result must be there
+        if (__atomic_load_n(reinterpret_cast<const unsigned long long*>(r), __ATOMIC_ACQUIRE) == *reinterpret_cast<const unsigned long long*>(&seq)) return LSD_OK;
         set_error("reduction result never published");
+        return LSD_ERR_CUDA;
+      }
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > l->wait_timeout_s) {
+        set_error("timed out after %.0f s waiting for a reduction result (kernel hung?)", l->wait_timeout_s);
         return LSD_ERR_CUDA;
       }
     }
@@ -756,26 +640,14 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
     const int keep_stale = (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0;
-    const bool fused = l->knn_shape == 4 && stencil != LSD_STENCIL_EXACT && l->map->view.shard_world <= 1;
-    if (fused) {
-      const int per = kLioFusedWarps * 32, nbf = std::max(1, std::min((l->n_bound + per - 1) / per, kLioMaxGrid));
-      LSD_LAUNCH(pdl, lio_search_fused_kernel, nbf, per, st, l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
-                 l->d_near_cnt, keep_stale, l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                 l->d_partials, l->d_done, l->d_result, seq, l->sc);
-      l->launches -= 1;   // one launch, not two (the common += 2 follows)
-    } else if ((l->knn_shape == 3 || l->knn_shape == 4) && stencil != LSD_STENCIL_EXACT) {
-      const int per = kLioFlatWarps * 32, nbf = std::max(1, std::min((l->n_bound + per - 1) / per, 148 * 8));
-      LSD_LAUNCH(pdl, lio_knn_flat_kernel, nbf, per, st, l->map->view, stencil_slot(stencil), l->d_body, l->d_n, l->p.max_points, ps, l->d_near,
-                 l->d_near_cnt, keep_stale);
-    } else {
-      const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
-      LSD_LAUNCH(pdl, lio_knn_kernel, nb, kHmWarps * 32, st, l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                 keep_stale);
-    }
-    if (!fused)
-      LSD_LAUNCH(pdl, lio_hmodel_kernel<true>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-                 l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-                 l->d_partials, l->d_done, l->d_result, seq, l->sc);
+    int resize_parity = -1;
+    if (l->rows_resize_pending) { resize_parity = l->rows_parity; l->rows_parity ^= 1; l->rows_resize_pending = false; }
+    const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
+    LSD_LAUNCH(pdl, lio_knn_kernel, nb, kHmWarps * 32, st, l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+               keep_stale, l->d_rows, resize_parity);
+    LSD_LAUNCH(pdl, lio_hmodel_kernel<true>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
+               l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
+               l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches += 2;
   } else {
     LSD_LAUNCH(pdl, lio_hmodel_kernel<false>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
@@ -981,12 +853,7 @@ lsd_status_t lio_load(lsd_lio* l, const float4* d_scan, int n, int downsample) {
     l->n_bound = std::max(n, 1);
     l->n_down = n;
   }
-  if (l->stale_rows) {
-    LSD_LAUNCH(l->pdl && l->sc.world <= 1, lio_resize_rows_kernel, 32, 256, st, l->d_n, l->p.max_points, l->d_rows, l->rows_parity, l->d_near_cnt);
-    l->rows_parity ^= 1;
-    l->launches += 1;
-    LSD_CUDA(cudaGetLastError());
-  }
+  l->rows_resize_pending = l->stale_rows && l->map->view.shard_world <= 1;   // done by this scan's first search (lio_knn_kernel)
   return LSD_OK;
 }
 
@@ -1121,7 +988,10 @@ using namespace lsd;
 static lsd_lio::Stage* free_stage(lsd_lio* l) {
   for (int i = 0; i < 2; i++) if (!l->stage[i].valid) return &l->stage[i];
   lsd_lio::Stage* s = l->stage[0].age <= l->stage[1].age ? &l->stage[0] : &l->stage[1];
-  s->valid = false;
+  // the dropped request's H2D copy (and side voxel grid) may still be running on the copy stream and reading s->buf:
+  // whatever the caller queues on the main stream next has to wait for it
+  cudaStreamWaitEvent(l->stream, s->ev, 0);
+  s->valid = false; s->down = false;
   return s;
 }
 
@@ -1195,14 +1065,21 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   if (e == cudaSuccess) e = cudaEventCreate(&l->pev[1]);
   if (e == cudaSuccess) {  // memset(point_selected_surf, true), laserMapping.cpp:1089
     lio_fill_u8_kernel<<<(int)((mp + 255) / 256), 256, 0, l->stream>>>(l->d_selected, (int)mp, 1);
+    lio_clear_rows_kernel<<<(int)((mp + 255) / 256), 256, 0, l->stream>>>(l->d_near, l->d_near_cnt, (int)mp);
     e = cudaStreamSynchronize(l->stream);
   }
   if (e != cudaSuccess) { lsd_status_t r = cuda_fail(e, "lsd_lio_create", __FILE__, __LINE__); lsd_lio_destroy(l); return r; }
   // the map and the voxel grid run on the LIO stream
   cudaStreamDestroy(l->map->stream); l->map->stream = l->stream;
   cudaStreamDestroy(l->vg->stream); l->vg->stream = l->stream;
-  { const char* ev = getenv("LSD_PDL"); l->pdl = (ev && ev[0] == '1') ? 1 : 0; }
-  { const char* ev = getenv("LSD_PIPELINE_VG"); l->pipeline_vg = (ev && ev[0] == '1') ? 1 : 0; }
+  // Defaults validated on B200 in round 1 (bit-identical results, tests/test_gpu_zz_pdl.py): programmatic dependent launch for
+  // the scan's kernel chain, and the voxel grid of an announced scan pipelined under the running one.  LSD_PDL=0 /
+  // LSD_PIPELINE_VG=0 in the environment (or lsd_lio_set_pdl / lsd_lio_set_pipeline) turn them off.
+  { const char* ev = getenv("LSD_PDL"); l->pdl = (ev && ev[0] == '0') ? 0 : 1; }
+  { const char* ev = getenv("LSD_PIPELINE_VG"); l->pipeline_vg = (ev && ev[0] == '0') ? 0 : 1; }
+  // The reference's Nearest_Points rows outlive a search that finds nothing (laserMapping.cpp:1273, ivox3d.h:155-157);
+  // reproducing that is what default-path parity needs (lsd_lio_set_stale_rows(l, 0) turns it off).
+  l->stale_rows = true;
   *out = l;
   return LSD_OK;
 }
@@ -1240,7 +1117,7 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   if (flag && l->map->view.shard_world > 1) { set_error("lsd_lio_set_stale_rows: not available on a tile-sharded handle"); return LSD_ERR_INVALID; }
   cudaSetDevice(l->device);
   // start from empty rows either way: a default-constructed Nearest_Points
-  LSD_CUDA(cudaMemsetAsync(l->d_near_cnt, 0, (size_t)l->p.max_points * 4, l->stream));
+  lio_clear_rows_kernel<<<(l->p.max_points + 255) / 256, 256, 0, l->stream>>>(l->d_near, l->d_near_cnt, l->p.max_points);
   LSD_CUDA(cudaMemsetAsync(l->d_rows, 0, 8, l->stream));
   LSD_CUDA(cudaStreamSynchronize(l->stream));
   l->stale_rows = flag != 0;
@@ -1272,7 +1149,7 @@ lsd_status_t lsd_lio_pipeline_stats(lsd_lio_t* l, long long* issued, long long* 
 }
 
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape) {
-  if (!l || (shape != 0 && shape != 1 && shape != 3 && shape != 4)) return LSD_ERR_INVALID;
+  if (!l || (shape != 0 && shape != 1)) return LSD_ERR_INVALID;
   l->knn_shape = shape;
   return LSD_OK;
 }
@@ -1313,6 +1190,7 @@ lsd_status_t lsd_lio_shard_export(lsd_lio_t* l, int rank, int world, int tile_ce
   memset(blob_out, 0, LSD_SHARD_BLOB_BYTES);
   memcpy(blob_out, &b, sizeof(b));
   l->shard_rank = rank; l->shard_world = world;
+  if (world > 1) l->stale_rows = false;   // a non-owner rank has no row to keep (near_cnt = -1): documented deviation of the sharded mode
   return LSD_OK;
 }
 

@@ -54,10 +54,12 @@ struct lsd_lio {
   int* d_n = nullptr;           // feats_down_size, device resident
   float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)
   int* d_near_cnt = nullptr;
-  int knn_shape = 0;            // lsd_lio_set_knn_shape: 0/1 warp per scan point (lio_knn_kernel), 3 flat (lio_knn_flat_kernel)
+  int knn_shape = 0;            // lsd_lio_set_knn_shape: 0/1 warp per scan point (lio_knn_kernel)
   int pdl = 0;                  // lsd_lio_set_pdl: launch the scan's kernels with programmatic dependent launch
-  int rows_parity = 0;          // which of d_n[8..9] the next lio_resize_rows_kernel publishes (the other one is read)
-  bool stale_rows = false;      // lsd_lio_set_stale_rows: keep Nearest_Points[i] when a search finds nothing (d_n[8..9]: rows alive)
+  int rows_parity = 0;          // which of d_rows[0..1] the next Nearest_Points.resize publishes (the other one is read)
+  bool rows_resize_pending = false;   // the loaded scan's first search still has to do Nearest_Points.resize (lio_knn_kernel)
+  bool stale_rows = true;       // lsd_lio_set_stale_rows: keep Nearest_Points[i] when a search finds nothing, as the reference does
+  double wait_timeout_s = 20.0; // wall-clock bound on the host's wait for a published reduction (wait_seq)
   unsigned char* d_selected = nullptr;  // point_selected_surf
   unsigned char* d_flags = nullptr;     // map_incremental decision per point
   float4* d_plane = nullptr;    // normvec: (normal, pd2)

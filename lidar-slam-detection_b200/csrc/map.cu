@@ -249,34 +249,6 @@ __global__ void __launch_bounds__(256) knn_query_thread_kernel(MapView mv, const
   out_cnt[i] = nf;
 }
 
-// ---- batched variant: work-flattened, one warp per 32 queries (knn_flat.cuh).  Selected with lsd_knn_set_shape(m, 3).
-}  // namespace lsd
-#include "knn_flat.cuh"
-namespace lsd {
-constexpr int kFlatWarps = 4;
-template <int K>
-__global__ void __launch_bounds__(kFlatWarps * 32) knn_query_flat_kernel(MapView mv, const float4* __restrict__ q, int nq, float max_sq,
-                                                                        int st_slot, int* __restrict__ out_idx, float* __restrict__ out_d2,
-                                                                        int* __restrict__ out_cnt) {
-  __shared__ FlatSmem<false> sm[kFlatWarps];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < nq;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) p = __ldg(q + i);
-  FlatTopK<K, false> best;
-  best.init();
-  int found = 0;
-  flat_search<K, false>(mv, c_stencils[st_slot], p.x, p.y, p.z, active, max_sq, sm[threadIdx.x >> 5], best, found);
-  if (!active) return;
-  const int nf = min(found, K);
-#pragma unroll
-  for (int r = 0; r < K; r++) {
-    out_idx[(size_t)i * K + r] = r < nf ? best.id[r] : -1;
-    out_d2[(size_t)i * K + r] = r < nf ? best.d[r] : -1.0f;
-  }
-  out_cnt[i] = nf;
-}
-
 // ------------------------------------------------------------------ box delete
 // KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:536-556; Delete_by_range :648-672): a point is deleted iff
 // min <= p < max on every axis, for any box.  Deleted points keep their slot and get NaN coordinates: every
@@ -326,15 +298,7 @@ lsd_status_t launch_knn(lsd_map* m, const float4* d_q, int nq, int k, float max_
                         int* d_cnt, cudaStream_t st) {
   if (nq <= 0) return LSD_OK;
   if (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0) { set_error("unknown stencil %d", stencil); return LSD_ERR_INVALID; }
-  const int shape = m->knn_shape;  // 0 auto, 1 warp/query, 2 thread/query, 3 flat (lsd_knn_set_shape)
-  if (shape == 3 && stencil != LSD_STENCIL_EXACT && (k == 1 || k == 5)) {
-    const int ss = stencil_slot(stencil), gb = (nq + kFlatWarps * 32 - 1) / (kFlatWarps * 32);
-    if (k == 1) knn_query_flat_kernel<1><<<gb, kFlatWarps * 32, 0, st>>>(m->view, d_q, nq, max_sq, ss, d_idx, d_d2, d_cnt);
-    else knn_query_flat_kernel<5><<<gb, kFlatWarps * 32, 0, st>>>(m->view, d_q, nq, max_sq, ss, d_idx, d_d2, d_cnt);
-    LSD_CUDA(cudaGetLastError());
-    m->launches++;
-    return LSD_OK;
-  }
+  const int shape = m->knn_shape;  // 0 auto, 1 warp/query, 2 thread/query (lsd_knn_set_shape)
   if (stencil != LSD_STENCIL_EXACT && k <= 5 && shape != 1 && (nq >= kThreadKnnMin || shape == 2)) {  // throughput shape: one thread per query
     const int ss = stencil_slot(stencil), gb = (nq + 255) / 256;
     if (k == 1) knn_query_thread_kernel<1><<<gb, 256, 0, st>>>(m->view, d_q, nq, max_sq, ss, d_idx, d_d2, d_cnt);

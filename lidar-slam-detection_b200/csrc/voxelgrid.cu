@@ -36,15 +36,22 @@ __device__ __forceinline__ void vg_setup(const int* __restrict__ bbox, float lea
                   dz = (long long)((mx[2] - mn[2]) * inv) + 1;
   g->inv = inv;
   g->status = 0;
-  if (dx * dy * dz > 2147483647ll) g->status = LSD_ERR_GRID_OVERFLOW;  // PCL: "Leaf size is too small"
+  // each factor is bounded first: (long long)(huge float) and the triple product must not wrap past the test below
+  const bool sane = dx >= 1 && dy >= 1 && dz >= 1 && dx <= 2147483647ll && dy <= 2147483647ll && dz <= 2147483647ll;
+  if (!sane || dx * dy > 2147483647ll || dx * dy * dz > 2147483647ll) g->status = LSD_ERR_GRID_OVERFLOW;  // PCL: "Leaf size is too small"
+  if (mn[0] > mx[0]) g->status = LSD_ERR_INVALID;   // no finite point at all: empty output
   for (int d = 0; d < 3; d++) {
-    g->minb[d] = (int)floorf(mn[d] * inv);
-    g->divb[d] = (int)floorf(mx[d] * inv) - g->minb[d] + 1;
+    g->minb[d] = g->status ? 0 : (int)floorf(mn[d] * inv);
+    g->divb[d] = g->status ? 1 : (int)floorf(mx[d] * inv) - g->minb[d] + 1;
   }
   const long long cells = (long long)g->divb[0] * g->divb[1] * g->divb[2];
   if (g->status == 0 && cells > max_cells) g->status = LSD_ERR_CAPACITY;
   g->mul[0] = 1; g->mul[1] = g->divb[0]; g->mul[2] = g->divb[0] * g->divb[1];
   g->n_words = g->status ? 0 : (int)((cells + 31) >> 5);
+}
+
+__device__ __forceinline__ bool vg_finite(const float4& p) {
+  return fabsf(p.x) <= 3.0e38f && fabsf(p.y) <= 3.0e38f && fabsf(p.z) <= 3.0e38f;   // false for NaN and +-Inf
 }
 
 __device__ __forceinline__ int leaf_index(const VgGrid& g, const float4& p) {
@@ -77,6 +84,7 @@ __global__ void __launch_bounds__(256) vg_minmax_kernel(const float4* __restrict
   float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = __ldg(in + i);
+    if (!vg_finite(p)) continue;   // pcl::VoxelGrid skips non-finite points (!is_dense branch); one Inf would blow the grid up
     mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
     mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
     mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
@@ -110,8 +118,11 @@ __global__ void __launch_bounds__(256) vg_mark_kernel(const float4* __restrict__
   __syncthreads();
   if (g.status) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int idx = leaf_index(g, __ldg(in + i));
+    const float4 p = __ldg(in + i);
+    int idx = vg_finite(p) ? leaf_index(g, p) : -1;
+    if (idx < 0 || (idx >> 5) >= g.n_words) idx = -1;   // cannot happen for a finite point inside the bbox; never index past the bitmap
     vidx[i] = idx;
+    if (idx < 0) continue;
     const unsigned bit = 1u << (idx & 31);
     unsigned* w = bitmap + (idx >> 5);
     if (!(*reinterpret_cast<volatile unsigned*>(w) & bit)) atomicOr(w, bit);
@@ -176,6 +187,7 @@ __global__ void __launch_bounds__(256) vg_accum_kernel(const float4* __restrict_
     if (status == LSD_ERR_GRID_OVERFLOW) { out[i] = p; continue; }  // PCL: output = input
     if (status) return;
     const int idx = vidx[i];
+    if (idx < 0) continue;   // non-finite point
     const int w = idx >> 5;
     const int rank = chunk_off[w / kScanChunk] + word_prefix[w] + __popc(bitmap[w] & ((1u << (idx & 31)) - 1u));
     long long* s = sums + 4 * (size_t)rank;

@@ -1,5 +1,5 @@
-"""TEST INFRASTRUCTURE: adversarial inputs for map insert + k-NN in all three shapes (warp / thread / flat per query), run by
-tests/test_emu_kernels.py against the SIMT emulator build.  The three shapes must agree bit for bit on EVERYTHING; against the
+"""TEST INFRASTRUCTURE: adversarial inputs for map insert + k-NN in both per-query shapes (warp / thread per query), run by
+tests/test_emu_kernels.py against the SIMT emulator build.  The shapes must agree bit for bit on EVERYTHING; against the
 oracle (iVox restatement) they must agree wherever the input is inside the map's documented capacity: voxel coordinates
 within +-2^18, at most 7 * 128 points per voxel, finite coordinates (the rest is counted in `dropped`, include/lsdreg.h)."""
 import sys
@@ -32,7 +32,7 @@ def case(name, pts, q, res=0.5, log2=14, vs_oracle=True, cells_equal=True):
         o.set_nearby(nearby)
         for k in (1, 5):
             ref = None
-            for shape in (1, 2, 3):
+            for shape in (1, 2):
                 g.set_knn_shape(shape)
                 r = g.knn(q, k=k, max_sq=5.0, stencil=nearby)
                 if ref is None:

@@ -45,6 +45,16 @@ for name, pts in cases.items():
 big = P([[0, 0, 0], [9000.0, 9000.0, 900.0], [1, 1, 1]])      # 45000 x 45000 x 4500 leaves at 0.2 m > INT32_MAX: PCL returns the input
 got = vg.filter(big, 0.2)
 assert got.shape[0] == 3 and (got == big).all(), got
+# non-finite coordinates: skipped like pcl::VoxelGrid's !is_dense branch; the finite points give what they give alone
+fin = P(rng.uniform(-20, 20, (2000, 3)) * [1, 1, 0.2])
+for bad in ([[np.inf, 0, 0]], [[np.nan, 1, 1]], [[0, -np.inf, 0], [1, 1, np.nan], [np.inf, np.inf, np.inf]]):
+    mixed = np.concatenate([fin[:700], P(bad), fin[700:]])
+    got = vg.filter(mixed, 0.5)
+    want = O.voxelgrid(fin, 0.5)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4, (bad, got.shape, want.shape)
+assert vg.filter(P([[np.nan, np.nan, np.nan], [np.inf, 0, 0]]), 0.5).shape[0] == 0      # nothing finite: empty output
+assert vg.filter(fin, 0.5).shape == O.voxelgrid(fin, 0.5).shape                         # and the scratch is clean afterwards
+print("ok voxelgrid non-finite")
 small = lsdreg.VoxelGrid(max_points=1000, log2_max_cells=10)   # capacity of the handle exceeded: an error, not a wrong answer
 try:
     small.filter(P(rng.uniform(-50, 50, (500, 3))), 0.5)

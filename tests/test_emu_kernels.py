@@ -16,7 +16,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 _CASES = {
-    "flat_knn": ("test_gpu_zz_flat_knn.py", "FLAT_OK"),
     "scancontext": ("test_gpu_zz_scancontext.py", "SC_OK"),
     "sequence": ("test_gpu_zz_sequence.py", "SEQUENCE_OK"),
     "fastlio_seam": ("test_gpu_zz_fastlio_seam.py", "SEAM_OK"),

@@ -18,7 +18,8 @@ def _pair(small_world, **kw):
     g.map.insert(m, 0)
     g.set_next_id(m.shape[0])
     kw.pop("eskf_literal", None)
-    o = OracleLio(kw.get("ivox_nearby", 18), knn_exact=bool(kw.get("knn_mode_exact", 0)), expected_cells=1 << 18)
+    # stale_neighbours=True: the reference's Nearest_Points rows outlive a search that finds nothing — the product's default
+    o = OracleLio(kw.get("ivox_nearby", 18), knn_exact=bool(kw.get("knn_mode_exact", 0)), expected_cells=1 << 18, stale_neighbours=True)
     o.add_map_points(m)
     prior = eskf.State()
     prior.rot = eskf.R_to_quat(small_world["Rprior"])
@@ -181,3 +182,45 @@ def test_prefetch_is_transparent(small_world):
         for (xa, na, ea), (xb, nb, eb) in zip(ref, got):
             assert na == nb and ea == eb
             np.testing.assert_array_equal(xa, xb)
+
+
+def test_degenerate_scene_projection():
+    """laserMapping.cpp:934-980 on the device: a ground-plane-only scene (tests/scenes.py) is flagged degenerate in every
+    evaluation — the host eigenvalue certificate fails, lio_degen_kernel computes the per-direction sums, the normal
+    equations are projected with mat_p — and the posterior equals the restated pipeline's, which
+    tests/test_oracle_degenerate.py pins to laserMapping.cpp compiled unmodified (3e-9 m)."""
+    import lsdreg
+    import scenes
+    from oracle import eskf
+    from oracle.lio import OracleLio
+    w = scenes.plane_world()
+    prior = eskf.State(); prior.rot = eskf.R_to_quat(w["Rprior"]); prior.pos = w["tprior"].copy()
+    g = lsdreg.LioFrontend(map_log2_lines=18)
+    g.map.insert(w["map"], 0); g.set_next_id(w["map"].shape[0])
+    o = OracleLio(18, expected_cells=1 << 18, stale_neighbours=True)
+    o.add_map_points(w["map"])
+    # single evaluation first: flag, projected normal equations
+    n = g.load_scan(w["scan"])
+    body = g.get_down()
+    o.near_xyz = np.zeros((n, 5, 3), np.float32); o.near_ids = np.full((n, 5), -1, np.int32)
+    o.near_cnt = np.zeros(n, np.int32); o.selected = np.ones(n, np.uint8)
+    o.world = np.zeros((n, 4), np.float32); o.plane = np.zeros((n, 4), np.float32)
+    ro = o._hmodel(body, prior, True)
+    rg = g.linearize(prior.to_vec(), True)
+    assert rg["degenerate"] == 1 and o.last["degenerate"] == 1 and rg["n_eff"] == ro["n"] > 3000
+    np.testing.assert_allclose(rg["HTH"], o.last["HTH6"], rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(rg["HTh"], o.last["HTh6"], rtol=1e-9, atol=1e-7)
+    # whole scan through lsd_lio_scan vs the restated fastlio_main pass, same downsampled cloud
+    g2 = lsdreg.LioFrontend(map_log2_lines=18)
+    g2.map.insert(w["map"], 0); g2.set_next_id(w["map"].shape[0])
+    x, P, info = g2.scan(w["scan"], prior.to_vec(), eskf.init_P())
+    o2 = OracleLio(18, expected_cells=1 << 18, stale_neighbours=True)
+    o2.add_map_points(w["map"])
+    r = o2.process_scan(g2.get_down(), prior, eskf.init_P(), downsample=False)
+    xo = o2.x.to_vec()
+    assert info["degenerate"] == 1 and info["iterations"] == r["iters"] and info["n_eff"] == r["log"][-1]["n_eff"]
+    assert np.abs(x[0:3] - xo[0:3]).max() < POS_TOL and _rot_err(x[3:7], xo[3:7]) < ROT_TOL
+    np.testing.assert_allclose(x, xo, atol=1e-7)
+    np.testing.assert_allclose(P, o2.P, rtol=1e-4, atol=1e-8)      # unobservable directions: entries of 1e-10 are rounding noise
+    assert np.abs(x[:2] - w["tprior"][:2]).max() < 1e-3 and abs(x[2] - w["tgt"][2]) < 5e-3   # x / y unobservable: untouched
+    assert abs(info["n_added"] - r["added"]) <= 3

