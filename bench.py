@@ -55,6 +55,30 @@ MAP_SEED, SCAN_SEED = 20260922 + 2, 20260922 + 102
 WORKLOAD = "config[1]: 100k-pt 64-beam synthetic scan vs 10M-pt map, full LIO iterate-to-converge"
 
 
+def load_synth():
+    """The seeded generators (lidar-slam-detection_b200/synth.py, numpy only) loaded BY PATH: the reference arm must not import the
+    product package (importing it dlopens liblsdreg.so)."""
+    import importlib.util
+    if "lsd_bench_synth" in sys.modules:
+        return sys.modules["lsd_bench_synth"]
+    spec = importlib.util.spec_from_file_location("lsd_bench_synth", os.path.join(ROOT, "lidar-slam-detection_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["lsd_bench_synth"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+REF_POSES = os.path.join(os.environ.get("TMPDIR", "/tmp"), "lsdreg_bench_reference_poses.json")
+
+
+def workload_config(map_points, scan_points, n_down):
+    """The `config` object: properties of the WORKLOAD only, so that both arms print the same keys and — the inputs being the
+    same seeded scans and the downsample being the same function — the same values.  Everything that describes how an arm
+    runs it goes to `impl_config`."""
+    return {"workload": WORKLOAD, "map_points": int(map_points), "scan_rays": 64 * N_AZ, "scan_points": float(scan_points),
+            "downsampled_points": float(n_down), "l2": "every step visits a different 120x80 m map block; table+points 4.3 GB >> 126 MB L2"}
+
+
 def step_block(s: int):
     return (s * 5 + 2) % BLOCKS_X, (s * 7 + 3) % BLOCKS_Y
 
@@ -62,7 +86,7 @@ def step_block(s: int):
 def make_step(s: int):
     """Scan s: ground-truth pose inside block step_block(s), the scan seen from it, and a prior
     perturbed by |t| <= 0.3 m, |theta| <= 1 deg."""
-    from lsdreg import synth
+    synth = load_synth()
     bi, bj = step_block(s)
     rng = np.random.default_rng([SCAN_SEED, s])
     Rgt = synth.rot_from_rpy(*np.deg2rad(rng.uniform(-2, 2, 2)), rng.uniform(-np.pi, np.pi))
@@ -140,11 +164,15 @@ def pin_to_gpu_numa(index: int):
         return 0
 
 
-def run_cpu_fastlio(args, FL, eskf, synth, cores):
+def run_cpu_fastlio(args, FL, eskf, synth, cores, dump_poses=None):
     """The reference's OWN per-scan code: laserMapping.cpp compiled unmodified with its build's -DMP_EN (oracle/_ref/
     libref_fastlio.so); each step runs the statements of fastlio_main that follow ImuProcess — pcl::VoxelGrid (the one
     restated stage, PCL being external), kf.update_iterated_dyn_share_modified with h_share_model_geometric, and
-    map_incremental — on the 10 M-point map held by the reference's iVox (capacity raised)."""
+    map_incremental — on the 10 M-point map held by the reference's iVox (capacity raised).
+
+    Thread count: the reference build hard-codes MP_PROC_NUM = 8 on x86_64 (fastlio/CMakeLists.txt:20-25); "all the host
+    threads it can use" is not monotone on a many-core host, so every candidate count is timed on THREE COLD blocks (blocks no
+    timed step visits, one scan each, like the timed steps) and the best median wins; the sweep is reported."""
     t0 = time.time()
     m = synth.block_map(MAP_SEED, BLOCKS_X, BLOCKS_Y, SPACING)
     ref = FL.RefFastLioBench(capacity=1 << 30, threads=8)
@@ -156,46 +184,61 @@ def run_cpu_fastlio(args, FL, eskf, synth, cores):
     def prior_of(Rp, tp):
         x = eskf.State(); x.rot = eskf.R_to_quat(Rp); x.pos = tp.copy()
         return x
-    # the reference build hard-codes MP_PROC_NUM = 8 on x86_64 (fastlio/CMakeLists.txt:20-25); "all the host threads it can
-    # use" is not monotone on a many-core host, so sweep (on a block no timed step visits again) and keep the best
-    sweep = {}
-    scan0, _, _, Rp0, tp0 = make_step(W + K)
-    for nt in sorted({t for t in (4, 8, 16, 32, 64, cores) if t <= cores}):
+    cands = sorted({t for t in (4, 8, 16, 32, 64, cores) if t <= cores})
+    fixed = os.environ.get("LSD_BENCH_REF_THREADS")
+    sweep, nxt = {}, 2 * (W + K) + 64          # step indices far from every arm's timed steps
+    if fixed:
+        cands = [int(fixed)]
+    reps = 3 if len(cands) > 1 else 0
+    cold = [make_step(nxt + i) for i in range(reps * len(cands))]
+    for ci, nt in enumerate(cands):
         ref.set_threads(nt)
-        best = 1e9
-        for _ in range(2):
+        ts = []
+        for r in range(reps):
+            scan0, _, _, Rp0, tp0 = cold[ci * reps + r]
             t1 = time.perf_counter()
             ref.process_scan(scan0, prior_of(Rp0, tp0), eskf.init_P())
-            best = min(best, time.perf_counter() - t1)
-        sweep[nt] = best
+            ts.append(time.perf_counter() - t1)
+        sweep[nt] = float(np.median(ts)) if ts else 0.0
     ref.set_threads(min(sweep, key=sweep.get))
-    times = []
+    times, poses, n_downs = [], [], []
     for s, (scan, Rgt, tgt, Rp, tp) in enumerate(steps):
         t1 = time.perf_counter()
         x, P, n_down = ref.process_scan(scan, prior_of(Rp, tp), eskf.init_P())
         dt = time.perf_counter() - t1
+        poses.append(x.to_vec()[:7].tolist())
         if s >= W:
-            times.append(dt)
+            times.append(dt); n_downs.append(n_down)
             err = float(np.abs(x.pos - tgt).max())
             assert n_down > 0 and err < 0.1, f"reference LIO did not converge at step {s}: {err}"
+    if dump_poses:      # the product arm compares its poses of the same steps with these (pose_parity in its JSON line)
+        try:
+            with open(dump_poses, "w") as f:
+                json.dump({"steps": K, "warmup": W, "map_seed": MAP_SEED, "scan_seed": SCAN_SEED, "map_points": int(m.shape[0]),
+                           "pose7_pos_xyz_quat_xyzw": poses}, f)
+        except OSError:
+            pass
     total = float(np.sum(times))
     return dict(value=K / total, ms_per_step=1e3 * total / K, cores=ref.threads, host_cores=cores,
-                thread_sweep_ms={str(k): round(v * 1e3, 2) for k, v in sweep.items()}, kind="reference", setup_s=setup_s,
-                iters=None, map_points=int(m.shape[0]),
+                step_ms={"median": 1e3 * float(np.median(times)), "p95": 1e3 * float(np.percentile(times, 95)), "min": 1e3 * float(np.min(times)), "max": 1e3 * float(np.max(times))},
+                thread_sweep_ms={str(k): round(v * 1e3, 2) for k, v in sweep.items()},
+                thread_sweep="median of 3 cold-block scans per candidate; best median used" if reps else "fixed by LSD_BENCH_REF_THREADS",
+                kind="reference", setup_s=setup_s, poses=poses,
+                iters=None, map_points=int(m.shape[0]), scan_points=float(np.mean([st[0].shape[0] for st in steps[W:]])), n_down=float(np.mean(n_downs)),
                 what="laserMapping.cpp compiled unmodified (-DMP_EN): VoxelGrid -> update_iterated_dyn_share_modified -> map_incremental")
 
 
-def run_cpu(args, rank, world):
+def run_cpu(args, rank, world, dump_poses=None):
     """Reference arm / cpu_baseline: the reference's CPU path on the host cores.  Uses oracle/_ref
-    (compiled reference iVox + esti_plane) when it exists, else the plain-C port."""
+    (laserMapping.cpp compiled unmodified) when it exists, else the plain-C port.  Imports nothing of the product."""
     from oracle import eskf
     from oracle.lio import OracleLio
     from oracle import oracle as O
     from oracle import fastlio as FL
-    from lsdreg import synth
-    cores = os.cpu_count() or 1
+    synth = load_synth()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if FL.HAVE_REF_FASTLIO and not os.environ.get("LSD_BENCH_CPU_RESTATED"):
-        return run_cpu_fastlio(args, FL, eskf, synth, cores)
+        return run_cpu_fastlio(args, FL, eskf, synth, cores, dump_poses)
     kind = "reference" if (O.HAVE_REF and hasattr(O.ref, "ref_lio_hmodel")) else "port"
     t0 = time.time()
     m = synth.block_map(MAP_SEED, BLOCKS_X, BLOCKS_Y, SPACING)
@@ -232,8 +275,9 @@ def run_cpu(args, rank, world):
     total = float(np.sum(times))
     value = K / total
     return dict(value=value, ms_per_step=1e3 * total / K, cores=lio.nthreads, host_cores=cores,
-                thread_sweep_ms={str(k): round(v * 1e3, 2) for k, v in sweep.items()}, kind=kind, setup_s=setup_s,
-                iters=float(np.mean(iters)), map_points=int(m.shape[0]))
+                step_ms={"median": 1e3 * float(np.median(times)), "p95": 1e3 * float(np.percentile(times, 95)), "min": 1e3 * float(np.min(times)), "max": 1e3 * float(np.max(times))},
+                thread_sweep_ms={str(k): round(v * 1e3, 2) for k, v in sweep.items()}, kind=kind, setup_s=setup_s, poses=None,
+                iters=float(np.mean(iters)), map_points=int(m.shape[0]), scan_points=float(np.mean([st[0].shape[0] for st in steps[W:]])), n_down=None)
 
 
 def run_knn_batch(torch, hmap, m, dev, nq):
@@ -269,118 +313,13 @@ def run_knn_batch(torch, hmap, m, dev, nq):
     return out
 
 
-def run_experimental_flat(m, nq, timeout_s=150, l2_fetch=None):
-    """The flat k-NN shape (csrc/knn_flat.cuh; lsd_knn_set_shape(m, 3)) on the same map and query generator as `knn_batch`,
-    in a SEPARATE PROCESS: the kernel was written with no GPU at hand (its logic runs under tests/simt, its first hardware
-    run may be this one), so nothing it does can reach the numbers above — a fault or a hang costs this leg only.
-    Reports timing only if its results are bit-identical to the validated thread-per-query shape."""
-    import subprocess
-    import tempfile
-    out = {"what": "flat k-NN shape, isolated subprocess, reported only when bit-identical to the thread-per-query shape"}
-    try:
-        with tempfile.TemporaryDirectory() as td:
-            path = os.path.join(td, "map.npy")
-            np.save(path, m)
-            env = dict(os.environ)
-            if l2_fetch:   # cudaLimitMaxL2FetchGranularity in the child's context only (read by lsd_init, csrc/map.cu)
-                env["LSD_L2_FETCH_GRANULARITY"] = str(l2_fetch)
-                out["l2_fetch_granularity"] = l2_fetch
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), str(nq), "--no-lio", "--shapes", "2,3" if l2_fetch else "3",
-                                "--map", path], cwd=ROOT, capture_output=True, text=True, timeout=timeout_s, env=env)
-        rows = []
-        for ln in r.stdout.splitlines():
-            if ln.startswith("{"):
-                try:
-                    rows.append(json.loads(ln))
-                except ValueError:
-                    pass
-        ident = [x for x in rows if "identical_to_thread_shape" in x]
-        timed = [x for x in rows if x.get("shape") == "flat" and "random_us" in x]
-        out["identical_to_thread_shape"] = bool(ident and ident[0]["identical_to_thread_shape"])
-        if r.returncode == 0 and out["identical_to_thread_shape"] and timed:
-            out.update({k: timed[0][k] for k in timed[0] if k != "shape"})
-            th = [x for x in rows if x.get("shape") == "thread" and "random_us" in x]
-            if th:   # the validated shape under the same fetch granularity, for reference
-                out["thread_shape_same_setting"] = {k: th[0][k] for k in ("random_us", "sorted_us", "random_frac", "sorted_frac") if k in th[0]}
-        else:
-            out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")
-    except Exception as e:  # noqa: BLE001  (timeout, spawn failure: the leg is optional)
-        out["error"] = f"{type(e).__name__}: {str(e)[:300]}"
-    return out
-
-
-def run_experimental_lio_shapes(m, timeout_s=330):
-    """The LIO scan stream with the flat (3) and fused (4) per-scan search shapes next to the default (0), then shapes 0 and 4
-    with programmatic dependent launch; same isolation and the same rule: a variant's times are reported only if its poses
-    agree with the default's.  Rows printed before a timeout are kept."""
-    import subprocess
-    import tempfile
-    out = {"what": "per-scan search shapes 0 (default) / 3 (flat) / 4 (flat fused with plane fit + reduction), and shapes 0 / 4 with "
-                   "programmatic dependent launch (_pdl), then with the next scan announced (_prefetch) and its voxel grid pipelined under the "
-                   "running scan (_pipe); isolated subprocess, 12 bench steps each, main-stream device ms and wall ms per scan (median of 9)"}
-
-    def rows(text):
-        for ln in (text or "").splitlines():
-            if ln.startswith("{") and "lio_knn_shape" in ln:
-                try:
-                    row = json.loads(ln)
-                except ValueError:
-                    continue
-                key = (f"shape_{row.pop('lio_knn_shape')}" + ("_pdl" if row.pop("pdl", 0) else "") + ("_prefetch" if row.pop("prefetch", 0) else "")
-                       + ("_pipe" if row.pop("pipeline_vg", 0) else ""))
-                out[key] = row if row.get("agrees_with_default") else {"agrees_with_default": False, "max_abs_state_diff_vs_default": row.get("max_abs_state_diff_vs_default")}
-
-    try:
-        with tempfile.TemporaryDirectory() as td:
-            path = os.path.join(td, "map.npy")
-            np.save(path, m)
-            try:
-                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "knn_shapes_probe.py"), "--no-knn", "--map", path], cwd=ROOT,
-                                   capture_output=True, text=True, timeout=timeout_s)
-            except subprocess.TimeoutExpired as e:
-                so = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else e.stdout
-                rows(so)
-                out["error"] = f"timeout after {timeout_s} s (rows above were printed before it)"
-                return out
-        rows(r.stdout)
-        if r.returncode != 0:
-            out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")
-    except Exception as e:  # noqa: BLE001
-        out["error"] = f"{type(e).__name__}: {str(e)[:300]}"
-    return out
-
-
-def run_experimental_flags_bench(args, pos_err_ref, timeout_s=300):
-    """This very bench (value + e2e legs only) in a child process with the two launch-side switches on — programmatic
-    dependent launch and the pipelined voxel grid (LSD_PDL=1 LSD_PIPELINE_VG=1).  Both leave every bit of
-    the result unchanged, so the child's worst position error over the timed steps must EQUAL this process's: its numbers
-    are reported only then.  Nothing here can reach `value`, `e2e` or `roofline` of this line."""
-    import subprocess
-    out = {"what": "child bench.py with LSD_PDL=1 LSD_PIPELINE_VG=1 (same steps, same K / W), reported only if its pos_err_max_m equals the parent's"}
-    env = dict(os.environ, LSD_PDL="1", LSD_PIPELINE_VG="1")
-    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline",
-           "--no-knn-batch", "--no-experimental", "--streams", "0"]
-    try:
-        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout_s, env=env)
-        row = None
-        for ln in r.stdout.splitlines():
-            if ln.startswith("{") and '"metric"' in ln:
-                try:
-                    row = json.loads(ln)
-                except ValueError:
-                    pass
-        if row is None:
-            out["error"] = f"exit {r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no JSON line")
-            return out
-        same = row.get("pos_err_max_m") == pos_err_ref
-        out["identical_pos_err"] = bool(same)
-        out["pos_err_max_m"] = row.get("pos_err_max_m")
-        if same and row.get("config", {}).get("pdl") and row.get("config", {}).get("pipeline_vg"):
-            out.update(value=row["value"], unit=row["unit"], ms_per_step=row["ms_per_step"], device_ms_per_step=row.get("device_ms_per_step"),
-                       e2e=row.get("e2e", {}).get("value"), e2e_ms_per_step=row.get("e2e", {}).get("ms_per_step"),
-                       gpu_launches=row.get("gpu_launches"))
-    except Exception as e:  # noqa: BLE001  (timeout, spawn failure: the leg is optional)
-        out["error"] = f"{type(e).__name__}: {str(e)[:300]}"
+def finish_knn_batch(kb, bytes_per_query, peak):
+    out = dict(kb, bytes_per_query=bytes_per_query, peak=peak)
+    for k in list(kb):
+        if k.endswith("_us") and kb[k]:
+            gbs = kb["queries"] * bytes_per_query / (kb[k] * 1e-6) / 1e9
+            out[k[:-3] + "_gbs"] = gbs
+            out[k[:-3] + "_frac"] = gbs / peak
     return out
 
 
@@ -429,6 +368,19 @@ def run_streams(torch, lsdreg, local, m, steps, dev_scans, W, K, S, prior_vec, P
             "pos_err_max_m": max(errs), "note": "independent streams, one map replica and one handle each, same GPU"}
 
 
+def step_stats(ts):
+    ts = np.asarray(ts, np.float64) * 1e3
+    return {"median": float(np.median(ts)), "p95": float(np.percentile(ts, 95)), "min": float(ts.min()), "max": float(ts.max())}
+
+
+def pose_delta(x_ours, pose7_ref):
+    """|dpos| (m, max over axes) and the rotation angle (rad) between two (pos, quat xyzw) poses."""
+    pa, pb = np.asarray(x_ours[:3]), np.asarray(pose7_ref[:3])
+    qa, qb = np.asarray(x_ours[3:7]), np.asarray(pose7_ref[3:7])
+    dot = abs(float(np.dot(qa / np.linalg.norm(qa), qb / np.linalg.norm(qb))))
+    return float(np.abs(pa - pb).max()), float(2.0 * np.arccos(min(1.0, dot)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -438,15 +390,16 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knn-batch", action="store_true")
-    ap.add_argument("--no-experimental", action="store_true", help="skip the isolated legs of code that has not been validated on a GPU yet")
+    ap.add_argument("--no-shard-leg", action="store_true", help="N>1: skip the tile-sharded leg (replicas only)")
     ap.add_argument("--streams", type=int, default=4, help="extra leg (N=1): this many independent scan streams, each with "
                     "its own map replica and handle, registered concurrently on the one GPU (0/1 = skip)")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: upload each scan inside lsd_lio_scan instead of one scan ahead")
     ap.add_argument("--knn-batch", type=int, default=1 << 21, help="queries in the batched k-NN leg (N=1)")
     ap.add_argument("--mg-mode", default="replicas", choices=["replicas", "shard"],
-                    help="N>1: 'replicas' = one map replica and one independent scan stream per GPU (weak scaling, no "
-                         "collective); 'shard' = ONE scan stream, map tile-sharded across the GPUs, normal equations "
-                         "all-reduced through peer memory inside the reduction kernel (strong scaling)")
+                    help="N>1, what `value` / `e2e` report: 'replicas' = one map replica and one independent scan stream per GPU "
+                         "(weak scaling, no collective); 'shard' = ONE scan stream, map tile-sharded across the GPUs, normal equations "
+                         "all-reduced through peer memory inside the reduction kernel (strong scaling).  The other mode is "
+                         "always reported beside it (`shard` / `replicas` object of the line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
@@ -455,23 +408,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = run_cpu(args, rank, world)
+        r = run_cpu(args, rank, world, dump_poses=REF_POSES)
         line = {"impl": "reference", "metric": "scans/sec", "value": r["value"], "unit": "scans/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "map_points": r["map_points"], "scan_rays": 64 * N_AZ},
+                "config": workload_config(r["map_points"], r["scan_points"], r["n_down"] if r["n_down"] is not None else -1),
+                "impl_config": {"parallelism": f"{r['cores']} OpenMP threads of {r['host_cores']} host cores", "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
+                                "thread_sweep_ms": r["thread_sweep_ms"], "thread_sweep": r.get("thread_sweep"),
+                                "timing": "host wall clock around each fastlio_main pass (ref_fastlio_pass), summed over the K timed steps"},
+                "step_ms": r["step_ms"],
                 "cpu_baseline": {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
                                  "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
                                  "sample": f"{args.steps} full scans of the workload after {args.warmup} warm-up scans"},
                 "e2e": {"value": r["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0, "mean_iterations": r["iters"]}
+                "gpu_launches": 0, "mean_iterations": r["iters"], "poses_written_to": REF_POSES}
         print(json.dumps(line))
         return 0
 
     numa_cpus = pin_to_gpu_numa(local)
     import torch
     import lsdreg
-    from lsdreg import synth
+    synth = load_synth()
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -479,36 +436,19 @@ def main():
     torch.cuda.set_device(local)
     lsdreg.init(local)
     dev = torch.device("cuda", local)
-
-    # ---------------- map (each rank holds a replica; ranks draw different scan streams)
-    m = synth.block_map(MAP_SEED, BLOCKS_X, BLOCKS_Y, SPACING)
-    lio = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
-    t0 = time.perf_counter()
-    sharded = world > 1 and args.mg_mode == "shard"
-    if sharded:
-        from lsdreg import shard as shardlib
-        shardlib.connect(lio, rank, world, tile_cells=shardlib.TILE_CELLS, reach_cells=1)
-    lio.map.insert(m, 0)
-    build_s = time.perf_counter() - t0
-    lio.set_next_id(m.shape[0])
-    st = lio.map.stats()
-    rho = st["points"] / max(st["cells"], 1)
-
     W, K = args.warmup, args.steps
     n_prof = 5
-    base = 0 if sharded else rank * (2 * (W + K) + n_prof)  # shard mode: every rank sees the same scans
-    steps_a = [make_step(base + s) for s in range(W + K)]
-    steps_b = [make_step(base + W + K + s) for s in range(W + K)]
-    steps_p = [make_step(base + 2 * (W + K) + s) for s in range(n_prof)]
     P0 = lsdreg.init_cov()
+    m = synth.block_map(MAP_SEED, BLOCKS_X, BLOCKS_Y, SPACING)
 
     def prior_vec(stp):
         return lsdreg.make_state(pos=stp[4], rot_xyzw=quat_from_R(stp[3]))
 
-    def run_steps(steps, scans, timed_from, prefetch=False):
-        """Returns (wall seconds of the timed part, per-step infos).  Bracketed by sync + barrier.
-        prefetch: double-buffered ingest — the H2D copy of scan s+1 is started before scan s is registered."""
-        infos = []
+    def run_steps(lio, steps, scans, timed_from, prefetch=False):
+        """Returns (wall seconds of the timed part, per-step infos incl. host wall time per call, poses of ALL steps).
+        Bracketed by sync + barrier.  prefetch: the next scan is announced before the current one is registered (host
+        scans: its H2D copy runs on the copy stream; any scan: its voxel grid is pipelined under the running scan)."""
+        infos, poses = [], []
         t_start = None
         if prefetch:
             lio.prefetch(scans[0])
@@ -518,10 +458,13 @@ def main():
                 if dist is not None:
                     dist.barrier()
                 t_start = time.perf_counter()
+            t1 = time.perf_counter()
             if prefetch and s + 1 < len(steps):
                 lio.prefetch(scans[s + 1])
             x, P, info = lio.scan(scans[s], prior_vec(stp), P0)
+            poses.append(x[:7].copy())
             if s >= timed_from:
+                info["call_s"] = time.perf_counter() - t1
                 info["pos_err"] = float(np.abs(x[:3] - stp[2]).max())
                 infos.append(info)
                 if len(infos) >= 2:
@@ -530,25 +473,58 @@ def main():
         torch.cuda.synchronize()
         wall = time.perf_counter() - t_start
         infos[-1]["gpu_ms"] = last_ms
-        return wall, infos
+        return wall, infos, poses
 
-    # ---------------- (1) inputs resident in HBM
-    dev_scans = [torch.from_numpy(stp[0]).to(dev) for stp in steps_a]
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    PIPE = os.environ.get("LSD_PIPELINE_VG", "")[:1] == "1"   # opt-in: scan s+1 is announced, its voxel grid runs under scan s
-    wall_a, infos_a = run_steps(steps_a, dev_scans, W, prefetch=PIPE)
-    clocks = sampler.stop()
-    # ---------------- (2) end to end: pinned host buffers, H2D inside the timed region
-    host_scans = [torch.from_numpy(stp[0]).pin_memory() for stp in steps_b]
-    scratch = torch.empty((131072, 4), dtype=torch.float32, device=dev)
-    for hs in host_scans:  # first DMA from a freshly pinned buffer pays a one-off mapping cost: take it here
-        scratch[:hs.shape[0]].copy_(hs, non_blocking=True)
-    torch.cuda.synchronize()
-    wall_b, infos_b = run_steps(steps_b, host_scans, W, prefetch=not args.no_prefetch)
+    def run_mode(sharded):
+        """The value leg (scans resident in HBM) and the e2e leg (pinned host scans, H2D inside) of one multi-GPU mode."""
+        lio = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
+        t0 = time.perf_counter()
+        if sharded:
+            from lsdreg import shard as shardlib
+            shardlib.connect(lio, rank, world, tile_cells=shardlib.TILE_CELLS, reach_cells=1)
+        lio.map.insert(m, 0)
+        build_s = time.perf_counter() - t0
+        lio.set_next_id(m.shape[0])
+        st = lio.map.stats()
+        base = 0 if sharded else rank * (2 * (W + K) + n_prof)  # shard mode: every rank sees the same scans
+        steps_a = [make_step(base + s) for s in range(W + K)]
+        steps_b = [make_step(base + W + K + s) for s in range(W + K)]
+        dev_scans = [torch.from_numpy(stp[0]).to(dev) for stp in steps_a]
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        wall_a, infos_a, poses_a = run_steps(lio, steps_a, dev_scans, W, prefetch=True)
+        clocks = sampler.stop()
+        host_scans = [torch.from_numpy(stp[0]).pin_memory() for stp in steps_b]
+        scratch = torch.empty((131072, 4), dtype=torch.float32, device=dev)
+        for hs in host_scans:  # first DMA from a freshly pinned buffer pays a one-off mapping cost: take it here
+            scratch[:hs.shape[0]].copy_(hs, non_blocking=True)
+        torch.cuda.synchronize()
+        wall_b, infos_b, _ = run_steps(lio, steps_b, host_scans, W, prefetch=not args.no_prefetch)
+        dev_ms = float(np.sum([i["gpu_ms"] for i in infos_a]))
+        t = torch.tensor([wall_a, wall_b, dev_ms * 1e-3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_a, wall_b, dev_s = [float(v) for v in t.cpu()]
+        for i in infos_a + infos_b:
+            assert i["pos_err"] < 0.1, f"LIO did not converge: {i}"
+        streams = 1 if sharded else world
+        return dict(lio=lio, st=st, build_s=build_s, steps_a=steps_a, steps_b=steps_b, dev_scans=dev_scans, host_scans=host_scans,
+                    infos_a=infos_a, infos_b=infos_b, poses_a=poses_a, clocks=clocks, wall_a=wall_a, wall_b=wall_b, dev_s=dev_s,
+                    value=streams * K / wall_a, e2e=streams * K / wall_b, base=base)
+
+    want_shard = world > 1 and args.mg_mode == "shard"
+    main_run = run_mode(want_shard)
+    other = None
+    if world > 1 and not args.no_shard_leg:      # the other mode, reported beside the headline in the same line
+        other = run_mode(not want_shard)
+        other["lio"].close(); other["lio"] = None
+    R = main_run
+    lio, st, infos_a, infos_b = R["lio"], R["st"], R["infos_a"], R["infos_b"]
+    rho = st["points"] / max(st["cells"], 1)
+
     # H2D probe: what this box's PCIe path gives a 1.6 MB pinned copy (explains e2e - value)
-    probe_src = host_scans[0]
+    probe_src = R["host_scans"][0]
     probe_dst = torch.empty(probe_src.shape, dtype=probe_src.dtype, device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
@@ -560,7 +536,8 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     h2d_us = ev0.elapsed_time(ev1) * 1e3 / 10
-    # ---------------- (3) per-kernel timing pass for the roofline (not part of any throughput number)
+    # ---------------- per-kernel timing pass for the roofline (not part of any throughput number)
+    steps_p = [make_step(R["base"] + 2 * (W + K) + s) for s in range(n_prof)]
     lio.set_profile(True)
     n_down_p = []
     for stp in steps_p:
@@ -569,27 +546,16 @@ def main():
     prof = lio.get_profile()
     lio.set_profile(False)
 
-    # ---------------- (4) batched k-NN (BASELINE metric "kNN GB/s vs HBM peak"): many scans' worth of queries in flight
+    # ---------------- batched k-NN (BASELINE metric "kNN GB/s vs HBM peak"): many scans' worth of queries in flight
     knn_batch = None
     if world == 1 and not args.no_knn_batch:
         knn_batch = run_knn_batch(torch, lio.map, m, dev, args.knn_batch)
 
-    # ---------------- (5) several independent scan streams on ONE GPU (a fleet server): what the GPU sustains when a
+    # ---------------- several independent scan streams on ONE GPU (a fleet server): what the GPU sustains when a
     # single stream's latency chain no longer leaves it idle.  Reported beside the headline, never instead of it.
     multi_stream = None
     if world == 1 and args.streams > 1:
-        multi_stream = run_streams(torch, lsdreg, local, m, steps_a, dev_scans, W, K, args.streams, prior_vec, P0)
-
-    dev_ms = float(np.sum([i["gpu_ms"] for i in infos_a]))
-    t = torch.tensor([wall_a, wall_b, dev_ms * 1e-3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall_a, wall_b, dev_s = [float(v) for v in t.cpu()]
-    streams = 1 if sharded else world
-    value = streams * K / wall_a
-    e2e = streams * K / wall_b
-    for i in infos_a + infos_b:
-        assert i["pos_err"] < 0.1, f"LIO did not converge: {i}"
+        multi_stream = run_streams(torch, lsdreg, local, m, R["steps_a"], R["dev_scans"], W, K, args.streams, prior_vec, P0)
 
     if rank != 0:
         if dist is not None:
@@ -615,82 +581,84 @@ def main():
     except Exception:
         pass
 
+    # ---------------- pose parity with the reference arm: the poses laserMapping.cpp (compiled unmodified) computed for the
+    # SAME steps — from the file `bench.py --impl reference` left behind on this box when it ran before us with the same
+    # K / W, else from the in-process cpu_baseline sample below.  This is parity, not accuracy (pos_err_max_m is vs truth).
+    pose_parity = None
+
+    def compare(ref_poses, source):
+        n = min(len(ref_poses), len(R["poses_a"]))
+        dm = [pose_delta(R["poses_a"][s], ref_poses[s]) for s in range(n)]
+        return {"max_m": max(d[0] for d in dm), "max_rad": max(d[1] for d in dm), "steps_compared": n, "against": source,
+                "bar": "1e-4 m / 1e-5 rad (BASELINE.json north_star)", "within_bar": bool(max(d[0] for d in dm) < 1e-4 and max(d[1] for d in dm) < 1e-5)}
+    if True:     # rank 0 registers steps 0.. in either mode
+        try:
+            with open(REF_POSES) as f:
+                rp = json.load(f)
+            if rp.get("steps") == K and rp.get("warmup") == W and rp.get("map_seed") == MAP_SEED and rp.get("scan_seed") == SCAN_SEED:
+                pose_parity = compare(rp["pose7_pos_xyz_quat_xyzw"], f"bench.py --impl reference on this box ({REF_POSES}): laserMapping.cpp compiled unmodified, all {W}+{K} steps")
+        except Exception:
+            pass
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         a2 = argparse.Namespace(steps=args.cpu_sample, warmup=1)
         r = run_cpu(a2, 0, 1)
         cpu = {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
-               "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
+               "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "thread_sweep": r.get("thread_sweep"), "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
                "sample": f"{args.cpu_sample} full scans of the same workload (same map, same generator) after 1 warm-up scan",
                "ms_per_scan": r["ms_per_step"], "mean_iterations": r["iters"]}
+        if pose_parity is None and r.get("poses"):
+            pose_parity = compare(r["poses"], f"in-process cpu_baseline: laserMapping.cpp compiled unmodified, steps 0..{args.cpu_sample}")
 
-    # last of all: code that has not been validated on a GPU yet, each leg in its own process (everything reported above
-    # is already measured; clocks were sampled during the timed region)
-    experimental = None
-    if world == 1 and not args.no_knn_batch and not args.no_experimental:
-        # The JSON line is printed after these legs, so together they get a wall-clock budget counted from process start
-        # (LSD_BENCH_BUDGET_S, default 600 s): a leg starts only with more than a minute left and its timeout is clipped to
-        # what is left, so the line is out within ~10 minutes whatever the legs do.  Most informative legs first.
-        budget = float(os.environ.get("LSD_BENCH_BUDGET_S", "600"))
-        left = lambda: budget - (time.time() - _T0)   # noqa: E731
-        experimental = {}
-
-        def leg(name, fn, default_timeout):
-            if left() < 60.0:
-                experimental[name] = {"skipped": "bench wall-clock budget spent (LSD_BENCH_BUDGET_S)"}
-                return
-            experimental[name] = fn(min(default_timeout, left() - 20.0))
-
-        leg("lio_search_shapes", lambda t: run_experimental_lio_shapes(m, timeout_s=t), 330)
-        leg("flags_on_bench", lambda t: run_experimental_flags_bench(args, float(np.max([i["pos_err"] for i in infos_a])), timeout_s=t), 300)
-        leg("knn_flat_shape", lambda t: run_experimental_flat(m, args.knn_batch, timeout_s=t), 150)
-        if "error" not in experimental["knn_flat_shape"] and "skipped" not in experimental["knn_flat_shape"]:
-            # the 128-byte cell line holds header + 3 points in its first 64 bytes (rho = 1.5): with 64-byte L2 fetches a
-            # voxel costs half the DRAM traffic.  No gain for the thread shape in round 1 (issue bound); the flat shape may differ
-            leg("knn_flat_shape_l2_fetch_64", lambda t: run_experimental_flat(m, args.knn_batch, timeout_s=t, l2_fetch=64), 150)
+    def mode_summary(X, sharded):
+        return {"mode": "shard" if sharded else "replicas", "scaling": "strong" if sharded else "weak",
+                "value": X["value"], "e2e": X["e2e"], "unit": "scans/s", "ms_per_step": 1e3 * X["wall_a"] / K, "e2e_ms_per_step": 1e3 * X["wall_b"] / K,
+                "device_ms_per_step": 1e3 * X["dev_s"] / K, "pos_err_max_m": float(np.max([i["pos_err"] for i in X["infos_a"]])),
+                "map_points_this_rank": int(X["st"]["points"]), "gpu_launches": int(np.sum([i["kernel_launches"] for i in X["infos_a"]])),
+                "parallelism": (f"map tile-sharded over {world} GPUs, ONE scan stream, peer-memory all-reduce of the normal equations inside the reduction kernel"
+                                if sharded else f"{world} replicas, independent scan streams, no collective")}
 
     iters = float(np.mean([i["iterations"] for i in infos_a]))
-    h2d = int(np.mean([stp[0].shape[0] for stp in steps_b[W:]]) * 16)
+    h2d = int(np.mean([stp[0].shape[0] for stp in R["steps_b"][W:]]) * 16)
     d2h = int(iters * (32 + 8) * 8 + 4)
     line = {
-        "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * wall_a / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+        "metric": "scans/sec", "value": R["value"], "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * R["wall_a"] / K, "higher_is_better": True, "scaling": "strong" if want_shard else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "map_points": int(st["points"]), "map_voxels": int(st["cells"]),
-                   "scan_points": float(np.mean([stp[0].shape[0] for stp in steps_a[W:]])), "scan_rays": 64 * N_AZ,
-                   "downsampled_points": float(np.mean([i["n_down"] for i in infos_a])),
-                   "mean_iterations": iters, "parallelism": "1 GPU" if world == 1 else (
-                       f"map tile-sharded over {world} GPUs, one scan stream, peer-memory all-reduce of the normal equations"
-                       if sharded else f"{world} replicas, independent scan streams, no collective"),
-                   "shard_points_this_rank": int(st["points"]),
-                   "pipeline_vg": PIPE,   # voxel grid of scan s+1 on the copy stream under scan s (opt-in, lsd_lio_set_pipeline)
-                   "pdl": os.environ.get("LSD_PDL", "")[:1] == "1",   # programmatic dependent launch (opt-in, lsd_lio_set_pdl)
-                   "l2": "every step visits a different 120x80 m map block; table+points 4.3 GB >> 126 MB L2",
-                   "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream"},
-        "device_ms_per_step": 1e3 * dev_s / K,
-        "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * wall_b / K, "h2d_probe_us": h2d_us,
+        "config": workload_config(m.shape[0], np.mean([stp[0].shape[0] for stp in R["steps_a"][W:]]), np.mean([i["n_down"] for i in infos_a])),
+        "impl_config": {"map_voxels": int(st["cells"]), "mean_iterations": iters,
+                        "parallelism": "1 GPU" if world == 1 else mode_summary(R, want_shard)["parallelism"],
+                        "shard_points_this_rank": int(st["points"]),
+                        "pipeline_vg": os.environ.get("LSD_PIPELINE_VG", "1")[:1] != "0",   # voxel grid of scan s+1 on the copy stream under scan s (default on)
+                        "pdl": os.environ.get("LSD_PDL", "1")[:1] != "0",                   # programmatic dependent launch (default on)
+                        "stale_rows": True,
+                        "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream; "
+                                  "step_ms = host wall time of each lsd_lio_scan call (what the caller waits for)"},
+        "device_ms_per_step": 1e3 * R["dev_s"] / K,
+        "step_ms": step_stats([i["call_s"] for i in infos_a]),
+        "e2e": {"value": R["e2e"], "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * R["wall_b"] / K, "step_ms": step_stats([i["call_s"] for i in infos_b]), "h2d_probe_us": h2d_us,
                 "h2d_probe_gbs": probe_src.numel() * 4 / (h2d_us * 1e-6) / 1e9,
                 "host_binding": f"{numa_cpus} CPUs local to the GPU (NVML affinity)" if numa_cpus else "unbound",
                 "ingest": "serial: H2D inside lsd_lio_scan" if args.no_prefetch else
                           "double-buffered: lsd_lio_prefetch uploads scan k+1 on a copy stream while scan k is registered; "
                           "every scan's H2D copy and result read-back are inside the timed region"},
         "gpu_launches": int(np.sum([i["kernel_launches"] for i in infos_a])),
-        "roofline": {"kernel": "lio_hmodel_kernel<search>", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "pose_parity": pose_parity,
+        "roofline": {"kernel": "lio_knn_kernel + lio_hmodel_kernel<search> (one search evaluation)", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_query": bytes_per_query, "rho": rho,
                      "queries_per_launch": n_q, "us_per_launch": dur_s * 1e6, "launches_timed": hs["count"]},
         "kernels_ms": {k: (v["ms"] / max(v["count"], 1)) for k, v in prof.items()},
-        "knn_batch": None if knn_batch is None else {
-            **knn_batch, "bytes_per_query": bytes_per_query, "peak": peak,
-            **{k + "_gbs": knn_batch[k + "_us"] and knn_batch["queries"] * bytes_per_query / (knn_batch[k + "_us"] * 1e-6) / 1e9
-               for k in ("random", "sorted")},
-            **{k + "_frac": knn_batch["queries"] * bytes_per_query / (knn_batch[k + "_us"] * 1e-6) / 1e9 / peak
-               for k in ("random", "sorted")}},
-        "multi_stream": multi_stream, "experimental": experimental,
-        "cpu_baseline": cpu, "clocks": clocks, "map_build_s": build_s,
+        "knn_batch": knn_batch and finish_knn_batch(knn_batch, bytes_per_query, peak),
+        "multi_stream": multi_stream,
+        "cpu_baseline": cpu, "clocks": R["clocks"], "map_build_s": R["build_s"],
         "pos_err_max_m": float(np.max([i["pos_err"] for i in infos_a])),
     }
+    if other is not None:
+        line["shard" if not want_shard else "replicas"] = mode_summary(other, not want_shard)
+        line[("shard" if not want_shard else "replicas")]["vs_this_lines_value"] = other["value"] / R["value"]
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -1,0 +1,73 @@
+"""GPU parity at BASELINE.json config[1] scale: the bench workload itself (bench.make_step: ~100 k-return 64-beam scan vs the
+10.1 M-point map, full iterate-to-converge, every step in another block) through lsd_lio_scan, against
+
+  (a) laserMapping.cpp COMPILED UNMODIFIED (oracle/_ref/libref_fastlio.so, RefFastLioBench.process_scan — the very code
+      bench.py --impl reference times): posterior pose within the north_star's 1e-4 m / 1e-5 rad on every step, same
+      feats_down_size, same effective-point count to a handful of gate flips (the compiled reference keeps
+      std::nth_element's neighbour order, esti_plane's QR is order-sensitive in fp32 — DESIGN.md section 4);
+  (b) the plain-C port of iVox on the SAME 10 M-point map: bit-exact neighbour ids for every query of the scan's first
+      search, on the shared downsampled cloud.
+
+Both sides start from the same map and register the same scans in the same order, map_incremental included, so step s sees
+the map the steps before it left behind.  LSD_CONFIG1_BLOCKS=2 shrinks the map (2 x 2 blocks) for a dry run under the SIMT
+emulator; the GPU run uses the full 13 x 13."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_STEPS = 6
+
+
+def test_bench_steps_pose_parity_with_the_compiled_reference():
+    import bench
+    import lsdreg
+    from lsdreg import synth
+    from oracle import eskf
+    from oracle import fastlio as FL
+    from oracle import oracle as O
+    if not FL.HAVE_REF_FASTLIO:
+        pytest.skip("oracle/_ref/libref_fastlio.so not built (needs /root/reference at build time)")
+    nb = int(os.environ.get("LSD_CONFIG1_BLOCKS", bench.BLOCKS_X))
+    bench.BLOCKS_X = bench.BLOCKS_Y = nb
+    m = synth.block_map(bench.MAP_SEED, nb, nb, bench.SPACING)
+    assert nb != 13 or m.shape[0] > 10_000_000
+    g = lsdreg.LioFrontend(map_log2_lines=25 if nb == 13 else 21, max_scan_points=131072, max_points=100000, async_map_insert=1)
+    g.map.insert(m, 0); g.set_next_id(m.shape[0])
+    ref = FL.RefFastLioBench(capacity=1 << 30, threads=8)
+    ref.add_map_points(m)
+    port = O.OracleIvox(0.5, 18, 1 << 24 if nb == 13 else 1 << 20)
+    port.add(np.ascontiguousarray(m[:, :3]), 0)
+    P0 = eskf.init_P()
+    worst = np.zeros(2)
+    for s in range(N_STEPS):
+        scan, Rgt, tgt, Rp, tp = bench.make_step(s)
+        prior = eskf.State(); prior.rot = eskf.R_to_quat(Rp); prior.pos = tp.copy()
+        if s == 0:
+            # (b) the first search of the scan on the device vs the port's iVox, same queries, same 10 M-point map
+            n = g.load_scan(scan)
+            g.linearize(prior.to_vec(), True)
+            mt = g.get_matches()
+            oi, od, _, oc = port.knn(np.ascontiguousarray(mt["world"][:, :4]), 5, 5.0)
+            assert (mt["cnt"] == oc).all() and (oc == 5).mean() > 0.5
+            found = oc > 0                      # rows that found nothing keep what they held (empty on a first scan)
+            assert (mt["idx"][found] == oi[found]).all()
+            assert (mt["idx"][~found] == -1).all()
+        x, P, info = g.scan(scan, prior.to_vec(), P0)
+        xr, Pr, n_down_ref = ref.process_scan(scan, prior, P0)
+        c = ref.counts()
+        assert info["status"] == lsdreg.OK and info["n_down"] == n_down_ref == c["n_down"], (s, info, c)
+        assert abs(info["n_eff"] - c["n_eff"]) <= max(3, c["n_eff"] // 500), (s, info["n_eff"], c["n_eff"])
+        assert info["degenerate"] == c["degenerate"] == 0
+        d = np.abs(eskf.State.from_vec(x).boxminus(xr))
+        worst = np.maximum(worst, [d[0:3].max(), d[3:6].max()])
+        assert d[0:3].max() < 1e-4 and d[3:6].max() < 1e-5, (s, d[:6])
+        assert np.abs(x[:3] - tgt).max() < 0.05          # and both sit on the ground truth (2 cm range noise)
+        sd = np.sqrt(np.abs(np.diag(Pr)))
+        assert (np.abs(P - Pr) <= 1e-3 * np.outer(sd, sd) + 1e-14).all(), s
+    g.sync()
+    st = g.map.stats()
+    assert abs(int(st["cells"]) - c["map_cells"]) <= 8 * N_STEPS, (st, c)     # both maps grew by the same inserts (a gate flip moves a point or two)
+    print(f"config[1] parity vs laserMapping.cpp: worst |dpos| = {worst[0]:.2e} m, |drot| = {worst[1]:.2e} rad over {N_STEPS} steps")
