@@ -90,11 +90,23 @@ lsd_status_t lsd_knn_query(lsd_map_t* m, const float* q_host, int nq, int k, flo
 lsd_status_t lsd_knn_query_dev(lsd_map_t* m, const float* q_dev, int nq, int k, float max_sq, int stencil,
                                int32_t* out_idx_dev, float* out_d2_dev, int32_t* out_cnt_dev);
 /* How the batch is mapped onto the GPU (no reference counterpart; results are bit-identical in every shape):
- * 0 = auto (warp per query below 65 536 queries, thread per query from there on), 1 = warp per query,
- * 2 = thread per query, 3 = flat (a warp owns 32 queries and walks the compacted list of existing voxels with
- * all lanes busy; csrc/knn_flat.cuh).  Shapes 2 and 3 serve k in {1, 5} on the fixed stencils; anything else
- * uses shape 1. */
+ * 0 = auto (warp per query below 65 536 queries; from there on the brick pages when lsd_map_enable_bricks was called and
+ * the stencil / k are served by them, else thread per query), 1 = warp per query, 2 = thread per query over the voxel
+ * lines, 3 = brick pages: the batch is binned by brick, each brick's page (its voxels + a one-voxel halo) is staged into
+ * shared memory with one cp.async.bulk (TMA) and answers all its queries from there (csrc/brick.cuh).  Shape 2 serves
+ * k in {1, 5} on the fixed stencils; shape 3 k in {1, 5} on CENTER / NEARBY6 / NEARBY18 / NEARBY26; anything else uses
+ * shape 1 (shape 3 asked for explicitly on something it does not serve is LSD_ERR_INVALID). */
 lsd_status_t lsd_knn_set_shape(lsd_map_t* m, int shape);
+
+/* Brick layout (no reference counterpart: IVox has one layout, a hash of per-voxel point lists, ivox3d.h:31-112; this is
+ * the same content arranged for batched queries).  After this call every point the map accepts is ALSO stored in the
+ * 4608-byte page of each 8 x 8 x 4-voxel brick whose one-voxel halo contains it (points already in the map are copied
+ * over), lsd_map_delete_boxes tombstones the replicas too, and lsd_knn_query* may use shape 3.  The directory has
+ * 2^log2_bricks slots (memory: 4.6 KB per slot); size it for <= 0.5 load: a 10 M-point outdoor map at 0.5 m needs about
+ * 170 k pages.  Not available on tile-sharded maps.  lsd_map_brick_stats: pages in use, point replicas stored, replicas
+ * dropped for capacity (must stay 0 for shape 3 to be exact). */
+lsd_status_t lsd_map_enable_bricks(lsd_map_t* m, int log2_bricks);
+lsd_status_t lsd_map_brick_stats(lsd_map_t* m, uint64_t* n_pages, uint64_t* n_replicas, uint64_t* n_dropped);
 
 /* ------------------------------------------------------------------------------------------
  * Voxel-grid downsample — replaces pcl::VoxelGrid<PointXYZINormal>::filter as called at

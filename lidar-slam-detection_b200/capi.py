@@ -83,6 +83,8 @@ SIGNATURES = [
     ("lsd_knn_query", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_knn_query_dev", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_knn_set_shape", _i, [_vp, _i]),
+    ("lsd_map_enable_bricks", _i, [_vp, _i]),
+    ("lsd_map_brick_stats", _i, [_vp, _vp, _vp, _vp]),
     ("lsd_voxelgrid_create", _i, [_pp, _i, _i]),
     ("lsd_voxelgrid_destroy", _i, [_vp]),
     ("lsd_voxelgrid_filter", _i, [_vp, _vp, _i, _f, _vp, _pi]),
@@ -289,6 +291,15 @@ class HashVoxelMap:
         return idx, d2, cnt
 
     KNN_AUTO, KNN_WARP, KNN_THREAD, KNN_FLAT = 0, 1, 2, 3
+
+    def enable_bricks(self, log2_bricks: int = 16):
+        """Also keep every point brick by brick (include/lsdreg.h::lsd_map_enable_bricks): batched k-NN shape 3 (TMA-staged pages)."""
+        check(lib.lsd_map_enable_bricks(self.h, int(log2_bricks)))
+
+    def brick_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib.lsd_map_brick_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(pages=a.value, replicas=b.value, dropped=c.value)
 
     def set_knn_shape(self, shape: int):
         """How a batch is mapped onto the GPU (include/lsdreg.h::lsd_knn_set_shape); results do not depend on it."""

@@ -1,0 +1,330 @@
+// brick.cuh — the brick layout of the hash-voxel map and the TMA-staged batched k-NN over it (K3, batch shape).
+//
+// Why: a hash of 128-byte voxel lines costs every query its own DRAM trips (tag -> line, per stencil cell) — measured in
+// round 1 at 1041 B of DRAM per query and 14 of 32 lanes active (profiles/r01k_knn_thread_ncu_raw.csv), 27-33 % of the HBM
+// roofline.  Here the same points are ALSO stored brick by brick: a brick is 8 x 8 x 4 voxels (4 x 4 x 2 m at 0.5 m) and its
+// page holds every point of those voxels PLUS a one-voxel halo (a point near a brick face is stored in up to 8 pages), so
+// the 19-cell NEARBY18 stencil of any query whose home voxel lies in the brick is answered from that ONE page.  A batch
+// is binned by brick (three small kernels), then a persistent CTA per work item pulls the page into shared memory with
+// ONE cp.async.bulk (TMA, mbarrier completion) and answers up to 128 queries from it: a page is read once per ~20
+// queries instead of ~7 lines per query, and every dependent load of the search is a shared-memory load.
+//
+// Page (kPageBytes = 4608, 128-byte aligned), one per directory slot:
+//   [  0,  16)  reserved (brick key, for debugging)
+//   [ 16, 616)  u8 head[600]    first point (index + 1) of each of the 10 x 10 x 6 region cells, 0 = empty
+//   [616, 848)  u8 next[232]    next point (index + 1) of the same cell, 0 = end of list
+//   [848,4560)  float4 pts[232] (x, y, z, id)
+// Directory: open addressing over `keys` (u64: level:7 | bx:19 | by:19 | bz:19, 0 = empty) with the point counter of every
+// brick in the parallel array `totals` (4 B per slot: the whole array stays in L2, so inserts and the planner never touch a
+// page to learn its fill).  Points beyond 232 go to pages keyed (brick, level >= 1) found by hashing — the same
+// no-linked-list, no-spin rule as the voxel lines (lsd_common.cuh).  Inserts are lock-free: atomicAdd slot claim, one
+// float4 store, byte exchange on the cell's list head.  List order depends on arrival; results do not (canonical (d2, id)
+// selection, the same candidate set as IVox::GetClosestPoint, ivox3d.h:139-171 — bit-identical to the line-based kernels).
+// The vertical brick origin is shifted by one voxel (kBrickZOff) so that the z = 0 layer — the ground of a map that starts
+// at the sensor — is not a brick boundary (it would double the replication of the most populated layer).
+#pragma once
+#include "lsd_common.cuh"
+
+namespace lsd {
+
+constexpr int kBrickXY = 8, kBrickZ = 4, kBrickZOff = 1;
+constexpr int kRegXY = kBrickXY + 2, kRegZ = kBrickZ + 2;
+constexpr int kRegCells = kRegXY * kRegXY * kRegZ;   // 600
+constexpr int kBrickCap = 232;                        // points per page (u8 indices: <= 255)
+constexpr int kPageHead = 16;
+constexpr int kPageNext = kPageHead + kRegCells;      // 616
+constexpr int kPagePts = kPageNext + kBrickCap;       // 848
+constexpr int kPageBytes = 4608;
+constexpr int kBrickQC = 128;                         // queries per work item = threads per CTA of the query kernel
+static_assert(kPagePts % 16 == 0 && kPagePts + 16 * kBrickCap <= kPageBytes && kPageBytes % 128 == 0, "page layout");
+
+struct BrickWork { int slot, qbase, qn; unsigned total; };
+
+// ------------------------------------------------------------------ directory
+__device__ __forceinline__ long long brick_find(const BrickView& bv, unsigned long long key) {
+  unsigned long long s = hash_key(key) & bv.mask;
+  for (unsigned probe = 0; probe < kMaxProbe; probe++) {
+    const unsigned long long cur = __ldcg(bv.keys + s);
+    if (cur == key) return (long long)s;
+    if (cur == 0ull) return -1;
+    s = (s + 1) & bv.mask;
+  }
+  return -1;
+}
+__device__ __forceinline__ long long brick_find_or_claim(const BrickView& bv, unsigned long long key) {
+  unsigned long long s = hash_key(key) & bv.mask;
+  for (unsigned probe = 0; probe < kMaxProbe; probe++) {
+    unsigned long long* kp = bv.keys + s;
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+    if (cur == key) return (long long)s;
+    if (cur == 0ull) {
+      const unsigned long long old = atomicCAS(kp, 0ull, key);
+      if (old == 0ull) { atomicAdd(&bv.counters[0], 1ull); return (long long)s; }
+      if (old == key) return (long long)s;
+    }
+    s = (s + 1) & bv.mask;
+  }
+  return -1;
+}
+
+// brick of a voxel, and the voxel's coordinates inside the brick's own 8 x 8 x 4 range
+__device__ __forceinline__ void brick_of(int cx, int cy, int cz, int3* b, int3* l) {
+  b->x = floor_div(cx, kBrickXY); b->y = floor_div(cy, kBrickXY); b->z = floor_div(cz + kBrickZOff, kBrickZ);
+  l->x = cx - b->x * kBrickXY; l->y = cy - b->y * kBrickXY; l->z = cz + kBrickZOff - b->z * kBrickZ;
+}
+
+// exchange one byte of a u8 array (32-bit CAS on the containing word): returns the previous value
+__device__ __forceinline__ unsigned byte_exch(unsigned char* addr, unsigned v) {
+  unsigned* w = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned long long>(addr) & ~3ull);
+  const unsigned sh = (unsigned)(reinterpret_cast<unsigned long long>(addr) & 3ull) * 8u;
+  unsigned old = *reinterpret_cast<volatile unsigned*>(w), assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(w, assumed, (assumed & ~(0xffu << sh)) | (v << sh));
+  } while (old != assumed);
+  return (old >> sh) & 0xffu;
+}
+
+// Store one point (already accepted by the voxel lines) in the page of every brick whose region contains its voxel.
+__device__ __forceinline__ void brick_insert_point(const BrickView& bv, int cx, int cy, int cz, float4 p) {
+  int3 b0, l;
+  brick_of(cx, cy, cz, &b0, &l);
+#pragma unroll 1
+  for (int dz = -1; dz <= 1; dz++) {
+    if ((dz < 0 && l.z != 0) || (dz > 0 && l.z != kBrickZ - 1)) continue;
+#pragma unroll 1
+    for (int dy = -1; dy <= 1; dy++) {
+      if ((dy < 0 && l.y != 0) || (dy > 0 && l.y != kBrickXY - 1)) continue;
+#pragma unroll 1
+      for (int dx = -1; dx <= 1; dx++) {
+        if ((dx < 0 && l.x != 0) || (dx > 0 && l.x != kBrickXY - 1)) continue;
+        const int rc = ((l.z - dz * kBrickZ + 1) * kRegXY + (l.y - dy * kBrickXY + 1)) * kRegXY + (l.x - dx * kBrickXY + 1);
+        const unsigned long long key = pack_key(b0.x + dx, b0.y + dy, b0.z + dz, 0);
+        long long s = brick_find_or_claim(bv, key);
+        if (s < 0) { atomicAdd(&bv.counters[2], 1ull); continue; }
+        const unsigned idx = atomicAdd(bv.totals + s, 1u);
+        const unsigned L = idx / kBrickCap, j = idx % kBrickCap;
+        if (L > 0) {
+          if (L > (unsigned)kMaxLevel) { atomicAdd(&bv.counters[2], 1ull); continue; }
+          s = brick_find_or_claim(bv, key | ((unsigned long long)L << 57));
+          if (s < 0) { atomicAdd(&bv.counters[2], 1ull); continue; }
+        }
+        unsigned char* page = bv.pages + (size_t)s * kPageBytes;
+        reinterpret_cast<float4*>(page + kPagePts)[j] = p;
+        page[kPageNext + j] = (unsigned char)byte_exch(page + kPageHead + rc, j + 1u);
+        atomicAdd(&bv.counters[1], 1ull);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ TMA page load (cp.async.bulk + mbarrier)
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+#ifdef LSD_SIMT_EMU
+  return 0u;
+#else
+  return (unsigned)__cvta_generic_to_shared(p);
+#endif
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) {
+#ifdef LSD_SIMT_EMU
+  *bar = 0ull;
+#else
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+// One thread: arm the barrier with the byte count and issue the two bulk copies of a page holding n points
+// (head + next block, then the points actually stored).  Every byte lands in shared memory without passing a register.
+__device__ __forceinline__ void page_load_issue(unsigned char* smem_page, unsigned long long* bar, const unsigned char* gpage, unsigned n) {
+#ifdef LSD_SIMT_EMU
+  memcpy(smem_page, gpage, kPagePts);
+  if (n) memcpy(smem_page + kPagePts, gpage + kPagePts, 16u * n);
+#else
+  const unsigned bytes_b = 16u * n;
+  const unsigned dst = smem_u32(smem_page), b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((unsigned)kPagePts + bytes_b) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(gpage), "r"((unsigned)kPagePts), "r"(b) : "memory");
+  if (bytes_b)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst + (unsigned)kPagePts), "l"(gpage + kPagePts), "r"(bytes_b), "r"(b) : "memory");
+#endif
+}
+// Every thread: wait until the bytes of the current phase have landed.
+__device__ __forceinline__ void page_load_wait(unsigned long long* bar, unsigned phase) {
+#ifdef LSD_SIMT_EMU
+  __syncthreads();
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LSD_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LSD_DONE;\n"
+      "bra LSD_WAIT;\n"
+      "LSD_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+#endif
+}
+
+// ------------------------------------------------------------------ batch binning
+// K-A: home brick of every query; queries whose brick does not exist are answered here (nothing within reach).
+__global__ void __launch_bounds__(256) brick_bin_kernel(BrickView bv, float inv_res, const float4* __restrict__ q, int nq, int k,
+                                                        int* __restrict__ q_slot, int* __restrict__ q_rank, unsigned* __restrict__ bin_count,
+                                                        int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const float4 p = __ldg(q + i);
+  const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
+  long long s = -1;
+  // beyond +-(2^18) no stencil cell is a valid voxel (coord_ok): nothing can be near
+  if (abs(c.x) <= kCoordBias && abs(c.y) <= kCoordBias && abs(c.z) <= kCoordBias) {
+    int3 b, l;
+    brick_of(c.x, c.y, c.z, &b, &l);
+    s = brick_find(bv, pack_key(b.x, b.y, b.z, 0));
+  }
+  q_slot[i] = (int)s;
+  if (s < 0) {
+    for (int r = 0; r < k; r++) { out_idx[(size_t)i * k + r] = -1; out_d2[(size_t)i * k + r] = -1.0f; }
+    out_cnt[i] = 0;
+    return;
+  }
+  q_rank[i] = (int)atomicAdd(bin_count + s, 1u);
+}
+
+// K-B: one thread per directory slot: a contiguous range of the sorted query list for every brick that has queries, cut
+// into work items of <= kBrickQC queries.  ctr[0] = queries placed, ctr[1] = work items.  Leaves bin_count zeroed.
+__global__ void __launch_bounds__(256) brick_plan_kernel(BrickView bv, unsigned long long n_slots, unsigned* __restrict__ bin_count,
+                                                         int* __restrict__ bin_base, BrickWork* __restrict__ work, unsigned* __restrict__ ctr) {
+  const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const unsigned c = bin_count[s];
+  if (!c) return;
+  bin_count[s] = 0u;
+  const unsigned base = atomicAdd(ctr + 0, c);
+  bin_base[s] = (int)base;
+  const unsigned nch = (c + kBrickQC - 1) / kBrickQC;
+  const unsigned w0 = atomicAdd(ctr + 1, nch);
+  const unsigned total = __ldcg(bv.totals + s);
+  for (unsigned ch = 0; ch < nch; ch++) {
+    BrickWork w;
+    w.slot = (int)s; w.qbase = (int)(base + ch * kBrickQC); w.qn = (int)min((unsigned)kBrickQC, c - ch * kBrickQC); w.total = total;
+    work[w0 + ch] = w;
+  }
+}
+
+// K-C: the sorted query list (indices into the caller's batch)
+__global__ void __launch_bounds__(256) brick_scatter_kernel(const int* __restrict__ q_slot, const int* __restrict__ q_rank,
+                                                            const int* __restrict__ bin_base, int nq, int* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int s = q_slot[i];
+  if (s >= 0) sorted[bin_base[s] + q_rank[i]] = i;
+}
+
+// ------------------------------------------------------------------ K-D: the search
+// Persistent CTAs, one work item at a time: (brick page, <= 128 queries).  Thread t answers query t of the item from the
+// page in shared memory: 19 list heads (u8), then the points of the cells that exist.  Top-K in registers, canonical
+// (d2, id) order (TopK<K>, map.cu).
+template <int K>
+__global__ void __launch_bounds__(kBrickQC) brick_knn_kernel(BrickView bv, float inv_res, int st_slot, float max_sq,
+                                                             const float4* __restrict__ q, const int* __restrict__ sorted,
+                                                             const BrickWork* __restrict__ work, unsigned* __restrict__ ctr,
+                                                             int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
+  __shared__ __align__(128) unsigned char page[kPageBytes];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int s_w;
+  __shared__ long long s_lvl;
+  if (threadIdx.x == 0) mbar_init(&bar);
+  __syncthreads();
+  const unsigned n_work = __ldcg(ctr + 1);
+  const Stencil& st = c_stencils[st_slot];
+  unsigned phase = 0;
+  for (;;) {
+    if (threadIdx.x == 0) s_w = (int)atomicAdd(ctr + 2, 1u);
+    __syncthreads();
+    const unsigned w = (unsigned)s_w;
+    if (w >= n_work) break;
+    const BrickWork it = work[w];
+    const unsigned n0 = min(it.total, (unsigned)kBrickCap);
+    if (threadIdx.x == 0) page_load_issue(page, &bar, bv.pages + (size_t)it.slot * kPageBytes, n0);
+    // the query and its place in the brick's region, while the page is in flight
+    const bool active = (int)threadIdx.x < it.qn;
+    int qi = -1, rc0 = 0;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned long long key = __ldcg(bv.keys + it.slot);
+    if (active) {
+      qi = __ldg(sorted + it.qbase + threadIdx.x);
+      p = __ldg(q + qi);
+      const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
+      const int bx = (int)((key >> 38) & 0x7ffffull) - kCoordBias, by = (int)((key >> 19) & 0x7ffffull) - kCoordBias,
+                bz = (int)(key & 0x7ffffull) - kCoordBias;
+      const int rx = c.x - bx * kBrickXY + 1, ry = c.y - by * kBrickXY + 1, rz = c.z + kBrickZOff - bz * kBrickZ + 1;   // 1..8, 1..8, 1..4
+      rc0 = (rz * kRegXY + ry) * kRegXY + rx;
+    }
+    TopK<K> best;
+    best.init();
+    int found = 0;
+    const unsigned levels = it.total ? (it.total + kBrickCap - 1) / kBrickCap : 1u;
+    for (unsigned L = 0; L < levels && L <= (unsigned)kMaxLevel; L++) {
+      if (L > 0) {   // points 232 L .. of a crowded brick: their page is found by hashing (brick, L)
+        __syncthreads();                       // everyone is done with the previous page
+        if (threadIdx.x == 0) {
+          s_lvl = brick_find(bv, key | ((unsigned long long)L << 57));
+          if (s_lvl >= 0) page_load_issue(page, &bar, bv.pages + (size_t)s_lvl * kPageBytes, min(it.total - L * kBrickCap, (unsigned)kBrickCap));
+        }
+        __syncthreads();
+        if (s_lvl < 0) continue;
+      }
+      page_load_wait(&bar, phase);
+      phase ^= 1u;
+      if (active) {
+        const unsigned char* head = page + kPageHead;
+        const unsigned char* next = page + kPageNext;
+        const float4* pts = reinterpret_cast<const float4*>(page + kPagePts);
+#pragma unroll 1
+        for (int o = 0; o < st.n; o++) {
+          const int rc = rc0 + (st.off[o][2] * kRegXY + st.off[o][1]) * kRegXY + st.off[o][0];
+          unsigned j = head[rc];
+          while (j) {
+            const float4 a = pts[j - 1];
+            const float d2 = dist2(p.x, p.y, p.z, a.x, a.y, a.z);
+            if (d2 < max_sq) { found++; best.push(d2, __float_as_int(a.w)); }
+            j = next[j - 1];
+          }
+        }
+      }
+    }
+    if (active) {
+      const int nf = min(found, K);
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        out_idx[(size_t)qi * K + r] = r < nf ? best.id[r] : -1;
+        out_d2[(size_t)qi * K + r] = r < nf ? best.d[r] : -1.0f;
+      }
+      out_cnt[qi] = nf;
+    }
+    __syncthreads();   // the page buffer and s_w are reused by the next item
+  }
+}
+
+// ------------------------------------------------------------------ box delete on the pages (KD_TREE::Delete_Point_Boxes)
+// Same rule as map_delete_boxes_kernel: a deleted point keeps its slot and gets NaN coordinates.  Unused slots hold zeros
+// or older points of no list; rewriting them is harmless.
+struct BrickBoxes { int n; float b[16][6]; };
+__global__ void __launch_bounds__(256) brick_delete_boxes_kernel(BrickView bv, unsigned long long n_slots, BrickBoxes bx) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long s = t / 8;           // 8 threads per page
+  if (s >= n_slots || bv.keys[s] == 0ull) return;
+  float4* pts = reinterpret_cast<float4*>(bv.pages + (size_t)s * kPageBytes + kPagePts);
+  for (int j = (int)(t & 7); j < kBrickCap; j += 8) {
+    const float4 p = pts[j];
+    bool inside = false;
+    for (int b = 0; b < bx.n && !inside; b++)
+      inside = bx.b[b][0] <= p.x && bx.b[b][3] > p.x && bx.b[b][1] <= p.y && bx.b[b][4] > p.y && bx.b[b][2] <= p.z && bx.b[b][5] > p.z;
+    if (inside) pts[j] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), p.w);
+  }
+}
+
+}  // namespace lsd

@@ -38,6 +38,15 @@ constexpr int kMaxLevel = 127;
 constexpr int kCoordBias = 1 << 18;  // voxel coordinates in (-2^18, 2^18)
 constexpr unsigned kMaxProbe = 4096;
 
+// Brick layout of the same points (brick.cuh): directory + one 4608-byte page per slot.  keys == nullptr: not enabled.
+struct BrickView {
+  unsigned long long* keys;      // [n_slots] level:7 | bx:19 | by:19 | bz:19, 0 = empty
+  unsigned* totals;              // [n_slots] points stored in the brick (all levels), level-0 slot only
+  unsigned char* pages;          // [n_slots] x kPageBytes
+  unsigned long long mask;       // n_slots - 1
+  unsigned long long* counters;  // [0] pages in use, [1] point replicas stored, [2] dropped (directory full / > 127 levels)
+};
+
 struct MapView {
   CellLine* lines;
   unsigned char* tags;      // one byte per line: 0 = empty, else slot_tag(hash) — the query-side filter (L2-resident)
@@ -46,6 +55,7 @@ struct MapView {
   unsigned long long* counters;  // [0] cells, [1] points, [2] dropped
   // tile sharding: world == 1 -> everything is local
   int shard_rank, shard_world, shard_tile, shard_reach;
+  BrickView bricks;              // lsd_map_enable_bricks: every accepted point is also stored brick by brick
 };
 
 // Tile ownership: x-y tiles of `tile` voxels, owner = hash(tile) mod world.  A voxel is RELEVANT to a

@@ -69,6 +69,32 @@ lsd_status_t upload_stencils() {
   return LSD_OK;
 }
 
+// K best candidates of one thread in registers, canonical ascending (d2, id) order (thread-per-query shapes)
+template <int K>
+struct TopK {
+  float d[K]; int id[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < K; i++) { d[i] = 3.0e38f; id[i] = 0x7fffffff; }
+  }
+  // insert (d2, pid) keeping ascending (d2, id) order; fully unrolled compare-exchange chain (registers only)
+  __device__ __forceinline__ void push(float d2, int pid) {
+    if (!(d2 < d[K - 1] || (d2 == d[K - 1] && pid < id[K - 1]))) return;
+    d[K - 1] = d2; id[K - 1] = pid;
+#pragma unroll
+    for (int i = K - 1; i > 0; i--) {
+      const bool sw = d[i] < d[i - 1] || (d[i] == d[i - 1] && id[i] < id[i - 1]);
+      const float td = d[i]; const int ti = id[i];
+      d[i] = sw ? d[i - 1] : d[i]; id[i] = sw ? id[i - 1] : id[i];
+      d[i - 1] = sw ? td : d[i - 1]; id[i - 1] = sw ? ti : id[i - 1];
+    }
+  }
+};
+
+}  // namespace lsd
+#include "brick.cuh"
+namespace lsd {
+
 // ------------------------------------------------------------------ K2: insert
 __device__ __forceinline__ long long find_or_claim(const MapView& mv, unsigned long long key, bool* fresh) {
   const unsigned long long h = hash_key(key);
@@ -107,6 +133,7 @@ __device__ void map_insert_point(const MapView& mv, float x, float y, float z, i
   }
   mv.lines[s].pts[j] = make_float4(x, y, z, __int_as_float(id));
   atomicAdd(&mv.counters[1], 1ull);
+  if (mv.bricks.keys) brick_insert_point(mv.bricks, c.x, c.y, c.z, make_float4(x, y, z, __int_as_float(id)));
 }
 
 __global__ void __launch_bounds__(256) map_insert_kernel(MapView mv, const float4* __restrict__ pts, int n, int id0) {
@@ -148,27 +175,6 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 5) knn_query_kernel(MapView mv
 // its stencil cells serially (tag probe in L2, line fetch only for voxels that exist) and keeps the K best
 // in registers, in canonical (d2, id) order.  ~12x fewer warp instructions per query than the warp-per-query
 // kernel, which stays the right shape for a single scan's 10-40 k queries (latency, not throughput).
-template <int K>
-struct TopK {
-  float d[K]; int id[K];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < K; i++) { d[i] = 3.0e38f; id[i] = 0x7fffffff; }
-  }
-  // insert (d2, pid) keeping ascending (d2, id) order; fully unrolled compare-exchange chain (registers only)
-  __device__ __forceinline__ void push(float d2, int pid) {
-    if (!(d2 < d[K - 1] || (d2 == d[K - 1] && pid < id[K - 1]))) return;
-    d[K - 1] = d2; id[K - 1] = pid;
-#pragma unroll
-    for (int i = K - 1; i > 0; i--) {
-      const bool sw = d[i] < d[i - 1] || (d[i] == d[i - 1] && id[i] < id[i - 1]);
-      const float td = d[i]; const int ti = id[i];
-      d[i] = sw ? d[i - 1] : d[i]; id[i] = sw ? id[i - 1] : id[i];
-      d[i - 1] = sw ? td : d[i - 1]; id[i - 1] = sw ? ti : id[i - 1];
-    }
-  }
-};
-
 // resolve `key` through the tag array (see warp_scan_cells); returns the line or nullptr
 __device__ __forceinline__ const CellLine* tag_find(const MapView& mv, unsigned long long key, uint4* hdr) {
   constexpr unsigned long long k01 = 0x0101010101010101ull, k7f = 0x7f7f7f7f7f7f7f7full;
@@ -286,6 +292,65 @@ __global__ void __launch_bounds__(256) map_delete_boxes_kernel(MapView mv, unsig
   if (del) { atomicAdd(n_deleted, (unsigned long long)del); atomicAdd(&mv.counters[1], (unsigned long long)(0ull - del)); }
 }
 
+// Fill the brick pages from the voxel lines (lsd_map_enable_bricks on a map that already holds points): one thread per
+// line, every stored point (tombstones included: NaN coordinates can never be a candidate) goes to its bricks.
+__global__ void __launch_bounds__(256) brick_rebuild_kernel(MapView mv, unsigned long long n_lines) {
+  const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_lines) return;
+  const CellLine* ln = mv.lines + s;
+  const unsigned long long key = ln->key;
+  if (key == 0ull) return;
+  const int level = (int)(key >> 57);
+  unsigned total = ln->count;
+  if (level > 0) {
+    uint4 h;
+    if (!tag_find(mv, key & ((1ull << 57) - 1ull), &h)) return;
+    total = h.z;
+  }
+  const int n = (int)min(total > (unsigned)(level * kPtsPerLine) ? total - (unsigned)(level * kPtsPerLine) : 0u, (unsigned)kPtsPerLine);
+  const int cx = (int)((key >> 38) & 0x7ffffull) - kCoordBias, cy = (int)((key >> 19) & 0x7ffffull) - kCoordBias,
+            cz = (int)(key & 0x7ffffull) - kCoordBias;
+  for (int j = 0; j < n; j++) brick_insert_point(mv.bricks, cx, cy, cz, ln->pts[j]);
+}
+
+static lsd_status_t brick_scratch(lsd_map* m, size_t bytes) {
+  if (m->bscratch_bytes >= bytes) return LSD_OK;
+  if (m->bscratch) LSD_CUDA(cudaFree(m->bscratch));
+  m->bscratch = nullptr; m->bscratch_bytes = 0;
+  LSD_CUDA(cudaMalloc(&m->bscratch, bytes));
+  m->bscratch_bytes = bytes;
+  return LSD_OK;
+}
+
+// Batched fixed-stencil k-NN over the brick pages: bin the batch by home brick (3 small kernels), then the persistent
+// TMA-staged search (brick.cuh).  Everything on `st`, no host synchronisation.
+static lsd_status_t launch_knn_bricks(lsd_map* m, const float4* d_q, int nq, int k, float max_sq, int st_slot, int* d_idx, float* d_d2,
+                                      int* d_cnt, cudaStream_t st) {
+  const BrickView& bv = m->view.bricks;
+  const size_t n_work_max = std::min<size_t>((size_t)m->n_bricks, (size_t)nq) + (size_t)nq / kBrickQC + 2;
+  const size_t o_slot = 0, o_rank = o_slot + (size_t)nq * 4, o_sorted = o_rank + (size_t)nq * 4, o_work = (o_sorted + (size_t)nq * 4 + 15) & ~(size_t)15,
+               o_ctr = o_work + n_work_max * sizeof(BrickWork), total = o_ctr + 64;
+  lsd_status_t s = brick_scratch(m, total);
+  if (s) return s;
+  char* base = static_cast<char*>(m->bscratch);
+  int* q_slot = reinterpret_cast<int*>(base + o_slot);
+  int* q_rank = reinterpret_cast<int*>(base + o_rank);
+  int* sorted = reinterpret_cast<int*>(base + o_sorted);
+  BrickWork* work = reinterpret_cast<BrickWork*>(base + o_work);
+  unsigned* ctr = reinterpret_cast<unsigned*>(base + o_ctr);
+  LSD_CUDA(cudaMemsetAsync(ctr, 0, 16, st));
+  const int gq = (nq + 255) / 256;
+  brick_bin_kernel<<<gq, 256, 0, st>>>(bv, m->view.inv_res, d_q, nq, k, q_slot, q_rank, m->bin_count, d_idx, d_d2, d_cnt);
+  brick_plan_kernel<<<(unsigned)((m->n_bricks + 255) / 256), 256, 0, st>>>(bv, m->n_bricks, m->bin_count, m->bin_base, work, ctr);
+  brick_scatter_kernel<<<gq, 256, 0, st>>>(q_slot, q_rank, m->bin_base, nq, sorted);
+  const int grid = (int)std::min<size_t>(148 * 16, n_work_max);
+  if (k == 1) brick_knn_kernel<1><<<grid, kBrickQC, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
+  else brick_knn_kernel<5><<<grid, kBrickQC, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
+  LSD_CUDA(cudaGetLastError());
+  m->launches += 4;
+  return LSD_OK;
+}
+
 lsd_status_t launch_insert(lsd_map* m, const float4* d_pts, int n, int id0, cudaStream_t st) {
   if (n <= 0) return LSD_OK;
   map_insert_kernel<<<(n + 255) / 256, 256, 0, st>>>(m->view, d_pts, n, id0);
@@ -298,7 +363,14 @@ lsd_status_t launch_knn(lsd_map* m, const float4* d_q, int nq, int k, float max_
                         int* d_cnt, cudaStream_t st) {
   if (nq <= 0) return LSD_OK;
   if (stencil != LSD_STENCIL_EXACT && stencil_slot(stencil) < 0) { set_error("unknown stencil %d", stencil); return LSD_ERR_INVALID; }
-  const int shape = m->knn_shape;  // 0 auto, 1 warp/query, 2 thread/query (lsd_knn_set_shape)
+  const int shape = m->knn_shape;  // 0 auto, 1 warp/query, 2 thread/query, 3 brick pages (lsd_knn_set_shape)
+  {
+    // brick pages: fixed stencils of reach 1 (CENTER / NEARBY6 / 18 / 26), k in {1, 5}; auto from kThreadKnnMin queries on
+    const int ss = stencil_slot(stencil);
+    const bool can = m->view.bricks.keys && ss >= 0 && ss <= 3 && (k == 1 || k == 5);
+    if (shape == 3 && !can) { set_error("lsd_knn_set_shape(3): bricks not enabled on this map, or stencil / k not served by the brick pages"); return LSD_ERR_INVALID; }
+    if (can && (shape == 3 || (shape == 0 && nq >= kThreadKnnMin))) return launch_knn_bricks(m, d_q, nq, k, max_sq, ss, d_idx, d_d2, d_cnt, st);
+  }
   if (stencil != LSD_STENCIL_EXACT && k <= 5 && shape != 1 && (nq >= kThreadKnnMin || shape == 2)) {  // throughput shape: one thread per query
     const int ss = stencil_slot(stencil), gb = (nq + 255) / 256;
     if (k == 1) knn_query_thread_kernel<1><<<gb, 256, 0, st>>>(m->view, d_q, nq, max_sq, ss, d_idx, d_d2, d_cnt);
@@ -375,6 +447,8 @@ lsd_status_t lsd_map_destroy(lsd_map_t* m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream); else cudaDeviceSynchronize();
   cudaFree(m->view.lines); cudaFree(m->view.tags); cudaFree(m->view.counters); cudaFree(m->scratch);
+  cudaFree(m->view.bricks.keys); cudaFree(m->view.bricks.totals); cudaFree(m->view.bricks.pages); cudaFree(m->view.bricks.counters);
+  cudaFree(m->bin_count); cudaFree(m->bin_base); cudaFree(m->bscratch);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return LSD_OK;
@@ -385,6 +459,7 @@ lsd_status_t lsd_map_set_shard(lsd_map_t* m, int rank, int world, int tile_cells
     set_error("lsd_map_set_shard: need 0 <= rank < world and 2*reach < tile");
     return LSD_ERR_INVALID;
   }
+  if (world > 1 && m->view.bricks.keys) { set_error("lsd_map_set_shard: the brick layout is not available on a tile-sharded map"); return LSD_ERR_INVALID; }
   m->view.shard_rank = rank; m->view.shard_world = world; m->view.shard_tile = tile_cells; m->view.shard_reach = reach_cells;
   return LSD_OK;
 }
@@ -395,7 +470,60 @@ lsd_status_t lsd_map_clear(lsd_map_t* m) {
   LSD_CUDA(cudaMemsetAsync(m->view.lines, 0, m->n_lines * sizeof(CellLine), m->stream));
   LSD_CUDA(cudaMemsetAsync(m->view.tags, 0, m->n_lines, m->stream));
   LSD_CUDA(cudaMemsetAsync(m->view.counters, 0, 4 * sizeof(unsigned long long), m->stream));
+  if (m->view.bricks.keys) {
+    LSD_CUDA(cudaMemsetAsync(m->view.bricks.keys, 0, m->n_bricks * 8, m->stream));
+    LSD_CUDA(cudaMemsetAsync(m->view.bricks.totals, 0, m->n_bricks * 4, m->stream));
+    LSD_CUDA(cudaMemsetAsync(m->view.bricks.pages, 0, m->n_bricks * (size_t)kPageBytes, m->stream));
+    LSD_CUDA(cudaMemsetAsync(m->view.bricks.counters, 0, 4 * sizeof(unsigned long long), m->stream));
+  }
   LSD_CUDA(cudaStreamSynchronize(m->stream));
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_enable_bricks(lsd_map_t* m, int log2_bricks) {
+  if (!m || log2_bricks < 8 || log2_bricks > 24) { set_error("lsd_map_enable_bricks: log2_bricks must be in [8, 24]"); return LSD_ERR_INVALID; }
+  if (m->view.shard_world > 1) { set_error("lsd_map_enable_bricks: not available on a tile-sharded map"); return LSD_ERR_INVALID; }
+  if (m->view.bricks.keys) { set_error("lsd_map_enable_bricks: already enabled"); return LSD_ERR_INVALID; }
+  LSD_CUDA(cudaSetDevice(m->device));
+  const unsigned long long n = 1ull << log2_bricks;
+  BrickView bv;
+  memset(&bv, 0, sizeof(bv));
+  cudaError_t e = cudaMalloc(&bv.keys, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&bv.totals, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&bv.pages, n * (size_t)kPageBytes);
+  if (e == cudaSuccess) e = cudaMalloc(&bv.counters, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&m->bin_count, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&m->bin_base, n * 4);
+  if (e != cudaSuccess) {
+    cudaFree(bv.keys); cudaFree(bv.totals); cudaFree(bv.pages); cudaFree(bv.counters); cudaFree(m->bin_count); cudaFree(m->bin_base);
+    m->bin_count = nullptr; m->bin_base = nullptr;
+    return cuda_fail(e, "lsd_map_enable_bricks alloc", __FILE__, __LINE__);
+  }
+  bv.mask = n - 1;
+  LSD_CUDA(cudaMemsetAsync(bv.keys, 0, n * 8, m->stream));
+  LSD_CUDA(cudaMemsetAsync(bv.totals, 0, n * 4, m->stream));
+  LSD_CUDA(cudaMemsetAsync(bv.pages, 0, n * (size_t)kPageBytes, m->stream));
+  LSD_CUDA(cudaMemsetAsync(bv.counters, 0, 4 * sizeof(unsigned long long), m->stream));
+  LSD_CUDA(cudaMemsetAsync(m->bin_count, 0, n * 4, m->stream));
+  m->n_bricks = n;
+  m->view.bricks = bv;
+  // points already in the map
+  brick_rebuild_kernel<<<(unsigned)((m->n_lines + 255) / 256), 256, 0, m->stream>>>(m->view, m->n_lines);
+  LSD_CUDA(cudaGetLastError());
+  m->launches++;
+  LSD_CUDA(cudaStreamSynchronize(m->stream));
+  return LSD_OK;
+}
+
+lsd_status_t lsd_map_brick_stats(lsd_map_t* m, uint64_t* n_pages, uint64_t* n_replicas, uint64_t* n_dropped) {
+  if (!m || !m->view.bricks.keys) { set_error("lsd_map_brick_stats: bricks not enabled"); return LSD_ERR_INVALID; }
+  LSD_CUDA(cudaSetDevice(m->device));
+  unsigned long long h[4];
+  LSD_CUDA(cudaMemcpyAsync(h, m->view.bricks.counters, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+  LSD_CUDA(cudaStreamSynchronize(m->stream));
+  if (n_pages) *n_pages = h[0];
+  if (n_replicas) *n_replicas = h[1];
+  if (n_dropped) *n_dropped = h[2];
   return LSD_OK;
 }
 
@@ -456,6 +584,13 @@ lsd_status_t lsd_map_delete_boxes(lsd_map_t* m, const float* boxes6_host, int n_
     map_delete_boxes_kernel<<<(unsigned)((m->n_lines + 255) / 256), 256, 0, m->stream>>>(m->view, m->n_lines, bx, &m->view.counters[3]);
     LSD_CUDA(cudaGetLastError());
     m->launches++;
+    if (m->view.bricks.keys) {   // the replicas in the brick pages get the same tombstones
+      BrickBoxes bb;
+      bb.n = bx.n; memcpy(bb.b, bx.b, sizeof(bb.b));
+      brick_delete_boxes_kernel<<<(unsigned)((m->n_bricks * 8 + 255) / 256), 256, 0, m->stream>>>(m->view.bricks, m->n_bricks, bb);
+      LSD_CUDA(cudaGetLastError());
+      m->launches++;
+    }
     unsigned long long h = 0;
     LSD_CUDA(cudaMemcpyAsync(&h, &m->view.counters[3], sizeof(h), cudaMemcpyDeviceToHost, m->stream));
     LSD_CUDA(cudaStreamSynchronize(m->stream));

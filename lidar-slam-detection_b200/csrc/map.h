@@ -12,7 +12,13 @@ struct lsd_map {
   void* scratch = nullptr;  // staging for the host-pointer entry points
   size_t scratch_bytes = 0;
   long long launches = 0;   // kernels launched on behalf of this handle
-  int knn_shape = 0;        // lsd_knn_set_shape: 0 auto, 1 warp/query, 2 thread/query, 3 flat
+  int knn_shape = 0;        // lsd_knn_set_shape: 0 auto, 1 warp/query, 2 thread/query, 3 brick pages (TMA)
+  // brick layout (lsd_map_enable_bricks, brick.cuh): directory size and the per-batch binning scratch
+  unsigned long long n_bricks = 0;
+  unsigned* bin_count = nullptr;   // [n_bricks], zero between batches
+  int* bin_base = nullptr;         // [n_bricks]
+  void* bscratch = nullptr;        // q_slot, q_rank, sorted, work items, counters of the batch in flight
+  size_t bscratch_bytes = 0;
 };
 
 namespace lsd {
