@@ -695,7 +695,7 @@ def main():
                         "parallelism": "1 GPU" if world == 1 else mode_summary(R, want_shard)["parallelism"],
                         "shard_points_this_rank": int(st["points"]),
                         "pipeline_vg": os.environ.get("LSD_PIPELINE_VG", "1")[:1] != "0",   # voxel grid of scan s+1 on the copy stream under scan s (default on)
-                        "pdl": os.environ.get("LSD_PDL", "1")[:1] != "0",                   # programmatic dependent launch (default on)
+                        "pdl": os.environ.get("LSD_PDL", "0")[:1] == "1",                   # programmatic dependent launch (opt-in)
                         "stale_rows": True,
                         "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream; "
                                   "step_ms = host wall time of each lsd_lio_scan call (what the caller waits for)"},

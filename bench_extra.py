@@ -52,6 +52,8 @@ def ndt(args):
     import lsdreg
     from lsdreg import synth
     from oracle.reg import OracleMatcher
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        return ndt_sharded(args)
     bx = args.ndt_blocks
     t0 = time.time()
     m = synth.block_map(31, bx, bx, 0.25 * (240711 * bx * bx / args.ndt_points) ** 0.5)
@@ -102,6 +104,77 @@ def ndt(args):
     print(json.dumps(out))
 
 
+def ndt_sharded(args):
+    """Config 3 on N GPUs: the 50 M-point map voxelised per x-y tile on its owner GPU (every rank
+    uploads only the points of its own tiles), every rank holds the scan, [H, b, err] all-reduced inside the cost kernel
+    through peer memory.  Reports the same fields as the 1-GPU leg plus the 1-GPU align on rank 0's GPU for comparison."""
+    import torch
+    import torch.distributed as dist
+    import lsdreg
+    from lsdreg import shard, synth
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    bx = args.ndt_blocks
+    m = synth.block_map(31, bx, bx, 0.25 * (240711 * bx * bx / args.ndt_points) ** 0.5)
+    bi = bx // 2
+    Rgt = synth.rot_from_rpy(0.01, -0.02, 0.3)
+    tgt = synth.block_center(bi, bi) + np.array([1.0, -2.0, 0.0])
+    scan = synth.scan64(32, 1920, Rgt, tgt, bi, bi)
+    dR, dt = synth.perturb(33, 0.5, 3.0)
+    guess = np.eye(4); guess[:3, :3] = Rgt @ dR; guess[:3, 3] = tgt + dt
+    TILE = 64                                              # 32 m tiles at 0.5 m voxels
+    g = lsdreg.Matcher("NDT_CUDA", resolution=0.5, map_log2_lines=25 if world <= 2 else 24)
+    blob = torch.from_numpy(g.shard_export(rank, world, TILE)).cuda()
+    blobs = [torch.empty_like(blob) for _ in range(world)]
+    dist.all_gather(blobs, blob)
+    g.shard_connect(np.stack([b.cpu().numpy() for b in blobs]))
+    # host-side ownership (mirrors ndt_coord + tile_owner): upload only this rank's tiles
+    c = np.floor(m[:, :2] / np.float32(0.5) - np.float32(0.5)).astype(np.int32)
+    mine = np.ascontiguousarray(m[shard.tile_owner(c[:, 0], c[:, 1], TILE, world) == rank])
+    dist.barrier()
+    build_ms, _ = t_ms(lambda: g.set_target(mine))
+    g.set_source(scan)
+    dist.barrier()
+    g.align(guess)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        g.align(guess)
+    torch.cuda.synchronize()
+    align_ms = (time.perf_counter() - t0) * 1e3 / 5
+    Tg, _ = g.final()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        g.cost(Tg)
+    cost_us = (time.perf_counter() - t0) * 1e6 / 20
+    st = g.stats()
+    t = torch.tensor([build_ms, align_ms, cost_us, float(st["n_voxels"]), float(mine.shape[0])], dtype=torch.float64, device="cuda")
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    poses = [torch.empty(16, dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(poses, torch.from_numpy(Tg.reshape(-1)).cuda())
+    if rank == 0:
+        out = dict(config="NDT 100k vs %.1fM-pt map @0.5 m, target tile-sharded over %d GPUs" % (m.shape[0] / 1e6, world), n_gpus=world,
+                   map_points=int(m.shape[0]), voxels_total=int(tsum[3]), voxels_this_rank=st["n_voxels"], points_uploaded_max=int(tmax[4]),
+                   scan_points=int(scan.shape[0]), target_build_ms=float(tmax[0]), align_ms=float(tmax[1]), cost_eval_us=float(tmax[2]),
+                   iterations=g.iterations, converged=bool(g.converged), pos_err_m=float(np.abs(Tg[:3, 3] - tgt).max()),
+                   ranks_bit_identical=bool(all(torch.equal(poses[0], p) for p in poses[1:])),
+                   collective="28 doubles all-reduced per cost evaluation inside ndt_cost_kernel (peer-memory inbox, rank-ordered fold)")
+        # the unsharded matcher on this rank's GPU, same clouds: what one GPU does alone
+        one = lsdreg.Matcher("NDT_CUDA", resolution=0.5, map_log2_lines=25)
+        b1, _ = t_ms(lambda: one.set_target(m)); one.set_source(scan); one.align(guess)
+        a1, _ = t_ms(lambda: one.align(guess), 5)
+        T1, _ = one.final()
+        c1, _ = t_ms(lambda: one.cost(T1), 20)
+        out["one_gpu"] = dict(target_build_ms=b1, align_ms=a1, cost_eval_us=c1 * 1e3, iterations=one.iterations, converged=bool(one.converged),
+                              pose_diff_vs_sharded_m=float(np.abs(T1[:3, 3] - Tg[:3, 3]).max()))
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def gicp(args):
     """Config 4: a batch of loop-closure pairs.  Pairs are independent, so with N ranks (torchrun) rank r takes pairs
     r, r+N, ... — no collective on the data path; the wall time is the max over ranks."""
@@ -128,7 +201,7 @@ def gicp(args):
         tgt = synth.block_center(0, 0) + np.array([1.0 + 0.3 * (p % 7), -2.0, 0.0])
         src = synth.scan64(50 + p, 3800, Rgt, tgt)            # a dense submap seen from the unknown pose
         src = np.ascontiguousarray(src[np.linspace(0, src.shape[0] - 1, 200000).astype(np.int64)]) if src.shape[0] > 200000 else src
-        dR, dt = synth.perturb(60 + p, 0.5, 2.0)              # a loop-closure candidate: odometry drift of <= 0.5 m / 2 deg
+        dR, dt = synth.perturb(60 + p, args.gicp_perturb_m, args.gicp_perturb_deg)   # guess perturbed by <= 1 m, <= 5 deg
         guess = np.eye(4); guess[:3, :3] = Rgt @ dR; guess[:3, 3] = tgt + dt
         data.append((m, src, guess, tgt))
     g.set_target(data[0][0]); g.set_source(data[0][1]); g.align(data[0][2])    # warm-up
@@ -153,6 +226,7 @@ def gicp(args):
     if rank == 0:
         out = dict(config="%s pairs x 200k pts" % method, pairs=pairs, n_gpus=world, points_per_cloud=200000,
                    covariance_build_ms=float(np.mean(build)), align_ms=float(np.mean(times)), pairs_per_s=pairs / wall,
+                   guess_perturbation="<= %.1f m, <= %.1f deg" % (args.gicp_perturb_m, args.gicp_perturb_deg),
                    wall_s=wall, iterations=float(np.mean(its)), pos_err_m=err_max,
                    note="host clouds in, H2D + index build + covariances + align inside the timed region; rank r takes pairs r, r+N, ...")
         if (method == "FAST_VGICP" and world == 1 and not args.no_ref_cuda
@@ -174,12 +248,23 @@ def gicp(args):
                 out["reference_cuda_sm100a"] = dict(error=repr(e)[:200])
         if not args.no_cpu and world == 1:
             m, src, guess, tgt = data[-1]
-            o = (OracleMatcher("gicp", nthreads=min(16, os.cpu_count() or 1)) if method == "FAST_GICP" else
-                 OracleMatcher("vgicp", neighbors=1, trans_eps=0.1, rot_eps=0.1, nthreads=min(16, os.cpu_count() or 1)))
-            cb, _ = t_ms(lambda: (o.set_target(m), o.set_source(src)))
-            ca, _ = t_ms(lambda: o.align(guess))
-            out["cpu"] = dict(kind="port", cores=min(16, os.cpu_count() or 1), sample="one pair", covariance_build_ms=cb, align_ms=ca,
-                              iterations=o.iterations, pos_err_m=float(np.abs(o.final[:3, 3] - tgt).max()))
+            from oracle import oracle as O
+            if O.HAVE_REF_REG:      # the reference's own classes (fast_gicp::FastGICP / FastVGICP compiled unmodified, oracle/_ref/libref_reg.so)
+                from oracle.reg import RefMatcher
+                nt = 4              # registrations.cpp:36,59: setNumThreads(4)
+                o = RefMatcher("gicp", nthreads=nt) if method == "FAST_GICP" else RefMatcher("vgicp", neighbors=1, trans_eps=0.1, rot_eps=0.1, nthreads=nt)
+                cb, _ = t_ms(lambda: (o.set_target(m), o.set_source(src)))
+                ca, To = t_ms(lambda: o.align(guess))
+                out["cpu"] = dict(kind="reference", cores=nt, sample="one pair", covariance_build_ms=cb, align_ms=ca, pairs_per_s=1e3 / (cb + ca),
+                                  converged=bool(o.converged), pos_err_m=float(np.abs(To[:3, 3] - tgt).max()),
+                                  what="fast_gicp::%s compiled unmodified, 4 OpenMP threads (the reference's setting)" % ("FastGICP" if method == "FAST_GICP" else "FastVGICP"))
+            else:
+                o = (OracleMatcher("gicp", nthreads=min(16, os.cpu_count() or 1)) if method == "FAST_GICP" else
+                     OracleMatcher("vgicp", neighbors=1, trans_eps=0.1, rot_eps=0.1, nthreads=min(16, os.cpu_count() or 1)))
+                cb, _ = t_ms(lambda: (o.set_target(m), o.set_source(src)))
+                ca, _ = t_ms(lambda: o.align(guess))
+                out["cpu"] = dict(kind="port", cores=min(16, os.cpu_count() or 1), sample="one pair", covariance_build_ms=cb, align_ms=ca,
+                                  iterations=o.iterations, pos_err_m=float(np.abs(o.final[:3, 3] - tgt).max()))
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -223,6 +308,8 @@ if __name__ == "__main__":
     ap.add_argument("--ndt-blocks", type=int, default=10)
     ap.add_argument("--gicp-pairs", type=int, default=4)
     ap.add_argument("--gicp-method", default="FAST_GICP", choices=["FAST_GICP", "FAST_VGICP"])
+    ap.add_argument("--gicp-perturb-m", type=float, default=1.0)
+    ap.add_argument("--gicp-perturb-deg", type=float, default=5.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the legs that time the reference's own CUDA NDT / VGICP (oracle/_ref/libref_cuda*.so)")
     a = ap.parse_args()

@@ -286,10 +286,24 @@ typedef struct lsd_reg_params {
   int64_t max_process_time_us;    /* soft timeout, hard stop at 1.5x (lsq_registration_impl.hpp:94-104)   */
   int k_correspondences;          /* GICP covariance neighbourhood, 20 (<= 20)                            */
   double max_corr_dist;           /* GICP max correspondence distance, 2.0 m                              */
-  double normal_search_sq;        /* GICP: squared radius bounding the exact k-NN (25 m^2)                */
+  double normal_search_sq;        /* GICP: squared radius of the FAST grid search for the k-NN (25 m^2); points with
+                                     fewer than k neighbours inside it get the true k-NN by an exact scan of the cloud,
+                                     so the result is nearestKSearch's (fast_gicp_impl.hpp:259) whatever this is        */
   double map_resolution;          /* voxel size of the exact-NN index (0.5 m)                             */
   int map_log2_lines;             /* hash table size, 0 = derive from the cloud size                      */
 } lsd_reg_params_t;
+
+/* Tile-sharded matcher ("NDT localisation: the 50 M-point map voxelised per tile on the owner
+ * GPU, all-reduce of [H, b, err] per LM trial").  No reference counterpart (the reference's NDTCuda is single-GPU,
+ * ndt_cuda.cu:115-178).  NDT_P2D only: after export / all-gather / connect (the hand-shake of lsd_lio_shard_*, same
+ * blob size), lsd_reg_set_target* keeps only the voxels of the x-y tiles (tile_cells NDT voxels wide) this rank owns —
+ * the caller may pass the whole cloud or just the points of its own tiles — every rank sets the SAME source and runs
+ * the SAME lsd_reg_align / lsd_reg_cost calls in lockstep; the 28 sums of every cost evaluation are all-reduced inside
+ * the reduction kernel through peer memory (rank-ordered fold: bit-identical on every rank), so all ranks return the same
+ * pose.  lsd_reg_fitness is not available on a sharded handle. */
+lsd_status_t lsd_reg_shard_export(lsd_reg_t* r, int rank, int world, int tile_cells, unsigned char* blob_out);
+lsd_status_t lsd_reg_shard_connect(lsd_reg_t* r, const unsigned char* blobs);
+
 
 void lsd_reg_default_params(lsd_reg_params_t* p, int kind);
 lsd_status_t lsd_reg_create(lsd_reg_t** out, const lsd_reg_params_t* p);

@@ -131,6 +131,8 @@ SIGNATURES = [
     ("lsd_reg_cost", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_d), _pi]),
     ("lsd_reg_get_correspondences", _i, [_vp, _vp, _i, _pi]),
     ("lsd_reg_stats", _i, [_vp, _pi, C.POINTER(C.c_longlong)]),
+    ("lsd_reg_shard_export", _i, [_vp, _i, _i, _i, _vp]),
+    ("lsd_reg_shard_connect", _i, [_vp, _vp]),
     ("lsd_vfe_default_params", None, [C.POINTER(VfeParams)]),
     ("lsd_vfe_create", _i, [_pp, C.POINTER(VfeParams)]),
     ("lsd_vfe_destroy", _i, [_vp]),
@@ -439,6 +441,16 @@ class Matcher:
         self.h = None
 
     __del__ = close
+
+    def shard_export(self, rank: int, world: int, tile_cells: int = 32) -> np.ndarray:
+        """Tile-sharded NDT target (include/lsdreg.h "Tile-sharded matcher"): this rank's blob for the all-gather."""
+        blob = np.zeros(192, np.uint8)   # LSD_SHARD_BLOB_BYTES
+        check(lib.lsd_reg_shard_export(self.h, rank, world, tile_cells, _ptr(blob)))
+        return blob
+
+    def shard_connect(self, blobs: np.ndarray):
+        blobs = np.ascontiguousarray(blobs, np.uint8)
+        check(lib.lsd_reg_shard_connect(self.h, _ptr(blobs)))
 
     def set_target(self, pts):
         if isinstance(pts, np.ndarray):

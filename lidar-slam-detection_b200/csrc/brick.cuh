@@ -35,7 +35,8 @@ constexpr int kPageHead = 16;
 constexpr int kPageNext = kPageHead + kRegCells;      // 616
 constexpr int kPagePts = kPageNext + kBrickCap;       // 848
 constexpr int kPageBytes = 4608;
-constexpr int kBrickQC = 128;                         // queries per work item = threads per CTA of the query kernel
+constexpr int kBrickQC = 32;                          // queries per work item: one WARP answers an item, one query per lane
+constexpr int kBrickWarps = 4;                        // warps (= page buffers) per CTA of the query kernel
 static_assert(kPagePts % 16 == 0 && kPagePts + 16 * kBrickCap <= kPageBytes && kPageBytes % 128 == 0, "page layout");
 
 struct BrickWork { int slot, qbase, qn; unsigned total; };
@@ -154,7 +155,7 @@ __device__ __forceinline__ void page_load_issue(unsigned char* smem_page, unsign
 // Every thread: wait until the bytes of the current phase have landed.
 __device__ __forceinline__ void page_load_wait(unsigned long long* bar, unsigned phase) {
 #ifdef LSD_SIMT_EMU
-  __syncthreads();
+  __syncwarp();
 #else
   asm volatile(
       "{\n"
@@ -195,17 +196,37 @@ __global__ void __launch_bounds__(256) brick_bin_kernel(BrickView bv, float inv_
 
 // K-B: one thread per directory slot: a contiguous range of the sorted query list for every brick that has queries, cut
 // into work items of <= kBrickQC queries.  ctr[0] = queries placed, ctr[1] = work items.  Leaves bin_count zeroed.
+// The two running totals are claimed once per BLOCK (block-wide exclusive scan, then one atomicAdd each): one atomic per
+// occupied slot on the same two words serialised the whole kernel (232 us for 160 k bricks, profiles/r02b).
+__device__ __forceinline__ unsigned block_excl_scan_256(unsigned v, unsigned* warp_tot, unsigned* total) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += t; }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  unsigned woff = 0, tot = 0;
+  for (unsigned k = 0; k < 8; k++) { const unsigned t = warp_tot[k]; if (k < warp) woff += t; tot += t; }
+  __syncthreads();
+  *total = tot;
+  return woff + inc - v;
+}
 __global__ void __launch_bounds__(256) brick_plan_kernel(BrickView bv, unsigned long long n_slots, unsigned* __restrict__ bin_count,
                                                          int* __restrict__ bin_base, BrickWork* __restrict__ work, unsigned* __restrict__ ctr) {
+  __shared__ unsigned warp_tot[8];
+  __shared__ unsigned s_base[2];
   const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  const unsigned c = bin_count[s];
+  unsigned c = 0;
+  if (s < n_slots) { c = bin_count[s]; if (c) bin_count[s] = 0u; }
+  const unsigned nch = (c + kBrickQC - 1) / kBrickQC;      // items of <= 32 queries; a small last item spreads each query over 2 / 4 / 8 lanes
+  unsigned tot_c, tot_w;
+  const unsigned off_c = block_excl_scan_256(c, warp_tot, &tot_c);
+  const unsigned off_w = block_excl_scan_256(nch, warp_tot, &tot_w);
+  if (threadIdx.x == 0) { s_base[0] = tot_c ? atomicAdd(ctr + 0, tot_c) : 0u; s_base[1] = tot_w ? atomicAdd(ctr + 1, tot_w) : 0u; }
+  __syncthreads();
   if (!c) return;
-  bin_count[s] = 0u;
-  const unsigned base = atomicAdd(ctr + 0, c);
+  const unsigned base = s_base[0] + off_c, w0 = s_base[1] + off_w;
   bin_base[s] = (int)base;
-  const unsigned nch = (c + kBrickQC - 1) / kBrickQC;
-  const unsigned w0 = atomicAdd(ctr + 1, nch);
   const unsigned total = __ldcg(bv.totals + s);
   for (unsigned ch = 0; ch < nch; ch++) {
     BrickWork w;
@@ -224,38 +245,83 @@ __global__ void __launch_bounds__(256) brick_scatter_kernel(const int* __restric
 }
 
 // ------------------------------------------------------------------ K-D: the search
-// Persistent CTAs, one work item at a time: (brick page, <= 128 queries).  Thread t answers query t of the item from the
-// page in shared memory: 19 list heads (u8), then the points of the cells that exist.  Top-K in registers, canonical
-// (d2, id) order (TopK<K>, map.cu).
+// Persistent warps, one work item at a time: (brick page, <= 32 queries).  Every warp owns a page buffer and an mbarrier:
+// lane 0 claims the next item and issues the page's bulk copies, the lanes load their queries meanwhile, the warp waits
+// on the barrier and answers the item's queries from shared memory.
+//
+// What the instruction profile of the first two versions asked for (profiles/r02c, r02d: issue-bound at 85 % with 6-10 of
+// 32 lanes active, half of the instructions in a branchy insertion running 3-5 lanes wide):
+//  * lane groups — a brick of the benchmark batch has ~13 queries, so an item of qn queries gives each query
+//    g = 32 / pow2ceil(qn) lanes (1, 2, 4 or 8); lane `sub` of a group takes stencil cells sub, sub + g, ...
+//  * a FLAT walk — phase 1 collects the heads of the lane's non-empty cells into a 20-byte queue in shared memory (uniform
+//    19 / g iterations, predicated stores); phase 2 is ONE loop that handles one stored point per iteration, hopping to the
+//    next queued cell when a list ends, so lanes diverge only in their total point count, not per cell;
+//  * a branch-free top-K — candidates are 64-bit keys (fp32 bits of d2 << 32 | id: d2 >= 0, so integer order is the
+//    canonical (d2, id) order) inserted by K min / max stages, no early-outs;
+//  * a merge of the group's sorted lists by log2(g) butterfly steps: min(A[i], B[K-1-i]) keeps the K smallest of the union
+//    (a bitonic sequence), a 9-comparator network sorts them again.
+// Any split of the candidate set gives the same K best, so results stay bit-identical to the line-based kernels.
+struct KeyTop5 {
+  unsigned long long k[5];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < 5; i++) k[i] = ~0ull;
+  }
+  __device__ __forceinline__ void insert(unsigned long long x) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) { const unsigned long long lo = min(k[i], x); x = max(k[i], x); k[i] = lo; }
+  }
+  __device__ __forceinline__ static void cx(unsigned long long& a, unsigned long long& b) { const unsigned long long lo = min(a, b); b = max(a, b); a = lo; }
+  // K smallest of this (sorted) and the partner lane's (sorted) list, sorted again
+  __device__ __forceinline__ void merge_xor(int x) {
+    unsigned long long o[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) o[i] = __shfl_xor_sync(0xffffffffu, k[i], x);
+#pragma unroll
+    for (int i = 0; i < 5; i++) k[i] = min(k[i], o[4 - i]);
+    // optimal 9-comparator sorting network for 5 keys
+    cx(k[0], k[1]); cx(k[3], k[4]); cx(k[2], k[4]); cx(k[2], k[3]); cx(k[0], k[3]); cx(k[0], k[2]); cx(k[1], k[4]); cx(k[1], k[3]); cx(k[1], k[2]);
+  }
+};
+
 template <int K>
-__global__ void __launch_bounds__(kBrickQC) brick_knn_kernel(BrickView bv, float inv_res, int st_slot, float max_sq,
-                                                             const float4* __restrict__ q, const int* __restrict__ sorted,
-                                                             const BrickWork* __restrict__ work, unsigned* __restrict__ ctr,
-                                                             int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
-  __shared__ __align__(128) unsigned char page[kPageBytes];
-  __shared__ __align__(8) unsigned long long bar;
-  __shared__ int s_w;
-  __shared__ long long s_lvl;
-  if (threadIdx.x == 0) mbar_init(&bar);
+__global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView bv, float inv_res, int st_slot, float max_sq,
+                                                                     const float4* __restrict__ q, const int* __restrict__ sorted,
+                                                                     const BrickWork* __restrict__ work, unsigned* __restrict__ ctr,
+                                                                     int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
+  __shared__ __align__(128) unsigned char pages[kBrickWarps][kPageBytes];
+  __shared__ __align__(8) unsigned long long bars[kBrickWarps];
+  __shared__ unsigned char cellq[kBrickWarps][32][20];   // per lane: heads of its non-empty stencil cells
+  __shared__ int s_off[32];                              // the stencil as region-index offsets
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* page = pages[warp];
+  unsigned long long* bar = &bars[warp];
+  if (lane == 0) mbar_init(bar);
+  const Stencil& st = c_stencils[st_slot];
+  const int n_cells = st.n;                              // <= 27 for the stencils served here
+  if (threadIdx.x < 32) s_off[threadIdx.x] = (int)threadIdx.x < n_cells ? (st.off[threadIdx.x][2] * kRegXY + st.off[threadIdx.x][1]) * kRegXY + st.off[threadIdx.x][0] : 0;
   __syncthreads();
   const unsigned n_work = __ldcg(ctr + 1);
-  const Stencil& st = c_stencils[st_slot];
+  unsigned char* myq = cellq[warp][lane];
   unsigned phase = 0;
   for (;;) {
-    if (threadIdx.x == 0) s_w = (int)atomicAdd(ctr + 2, 1u);
-    __syncthreads();
-    const unsigned w = (unsigned)s_w;
+    unsigned w = 0;
+    if (lane == 0) w = atomicAdd(ctr + 2, 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
     if (w >= n_work) break;
     const BrickWork it = work[w];
     const unsigned n0 = min(it.total, (unsigned)kBrickCap);
-    if (threadIdx.x == 0) page_load_issue(page, &bar, bv.pages + (size_t)it.slot * kPageBytes, n0);
+    if (lane == 0) page_load_issue(page, bar, bv.pages + (size_t)it.slot * kPageBytes, n0);
+    // lanes per query (warp-uniform): 8 for <= 4 queries, 4 for <= 8, 2 for <= 16, else 1
+    const int lg = it.qn <= 4 ? 3 : it.qn <= 8 ? 2 : it.qn <= 16 ? 1 : 0;
+    const int g = 1 << lg, sub = lane & (g - 1), t = lane >> lg;
     // the query and its place in the brick's region, while the page is in flight
-    const bool active = (int)threadIdx.x < it.qn;
+    const bool active = t < it.qn;
     int qi = -1, rc0 = 0;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     const unsigned long long key = __ldcg(bv.keys + it.slot);
     if (active) {
-      qi = __ldg(sorted + it.qbase + threadIdx.x);
+      qi = __ldg(sorted + it.qbase + t);
       p = __ldg(q + qi);
       const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
       const int bx = (int)((key >> 38) & 0x7ffffull) - kCoordBias, by = (int)((key >> 19) & 0x7ffffull) - kCoordBias,
@@ -263,49 +329,68 @@ __global__ void __launch_bounds__(kBrickQC) brick_knn_kernel(BrickView bv, float
       const int rx = c.x - bx * kBrickXY + 1, ry = c.y - by * kBrickXY + 1, rz = c.z + kBrickZOff - bz * kBrickZ + 1;   // 1..8, 1..8, 1..4
       rc0 = (rz * kRegXY + ry) * kRegXY + rx;
     }
-    TopK<K> best;
+    KeyTop5 best;
     best.init();
     int found = 0;
     const unsigned levels = it.total ? (it.total + kBrickCap - 1) / kBrickCap : 1u;
     for (unsigned L = 0; L < levels && L <= (unsigned)kMaxLevel; L++) {
       if (L > 0) {   // points 232 L .. of a crowded brick: their page is found by hashing (brick, L)
-        __syncthreads();                       // everyone is done with the previous page
-        if (threadIdx.x == 0) {
-          s_lvl = brick_find(bv, key | ((unsigned long long)L << 57));
-          if (s_lvl >= 0) page_load_issue(page, &bar, bv.pages + (size_t)s_lvl * kPageBytes, min(it.total - L * kBrickCap, (unsigned)kBrickCap));
+        __syncwarp();                          // every lane is done with the previous page
+        long long sl = -1;
+        if (lane == 0) {
+          sl = brick_find(bv, key | ((unsigned long long)L << 57));
+          if (sl >= 0) page_load_issue(page, bar, bv.pages + (size_t)sl * kPageBytes, min(it.total - L * kBrickCap, (unsigned)kBrickCap));
         }
-        __syncthreads();
-        if (s_lvl < 0) continue;
+        sl = __shfl_sync(0xffffffffu, sl, 0);
+        if (sl < 0) continue;
       }
-      page_load_wait(&bar, phase);
+      page_load_wait(bar, phase);
       phase ^= 1u;
       if (active) {
         const unsigned char* head = page + kPageHead;
         const unsigned char* next = page + kPageNext;
         const float4* pts = reinterpret_cast<const float4*>(page + kPagePts);
+        // phase 1: heads of this lane's non-empty cells
+        int nc = 0;
 #pragma unroll 1
-        for (int o = 0; o < st.n; o++) {
-          const int rc = rc0 + (st.off[o][2] * kRegXY + st.off[o][1]) * kRegXY + st.off[o][0];
-          unsigned j = head[rc];
-          while (j) {
-            const float4 a = pts[j - 1];
-            const float d2 = dist2(p.x, p.y, p.z, a.x, a.y, a.z);
-            if (d2 < max_sq) { found++; best.push(d2, __float_as_int(a.w)); }
-            j = next[j - 1];
+        for (int o = sub; o < n_cells; o += g) {
+          const unsigned char j = head[rc0 + s_off[o]];
+          myq[nc] = j;
+          nc += j != 0;
+        }
+        // phase 2: one stored point per iteration
+        int qp = 1;
+        unsigned j = nc ? myq[0] : 0u;
+        while (j) {
+          const float4 a = pts[j - 1];
+          const float d2 = dist2(p.x, p.y, p.z, a.x, a.y, a.z);
+          if (d2 < max_sq) {
+            found++;
+            best.insert(((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(a.w) ^ 0x80000000u));   // signed id order
           }
+          j = next[j - 1];
+          if (j == 0u && qp < nc) j = myq[qp++];
         }
       }
+    }
+    // merge the group's lists: after step s every lane holds the K best of 2^(s+1) lanes' candidates
+#pragma unroll 1
+    for (int s = 0; s < lg; s++) {
+      best.merge_xor(1 << s);
+      found += __shfl_xor_sync(0xffffffffu, found, 1 << s);
     }
     if (active) {
       const int nf = min(found, K);
 #pragma unroll
       for (int r = 0; r < K; r++) {
-        out_idx[(size_t)qi * K + r] = r < nf ? best.id[r] : -1;
-        out_d2[(size_t)qi * K + r] = r < nf ? best.d[r] : -1.0f;
+        if ((r & (g - 1)) == sub) {                          // the group's lanes share the K stores
+          out_idx[(size_t)qi * K + r] = r < nf ? (int)((unsigned)(best.k[r] & 0xffffffffull) ^ 0x80000000u) : -1;
+          out_d2[(size_t)qi * K + r] = r < nf ? __uint_as_float((unsigned)(best.k[r] >> 32)) : -1.0f;
+        }
       }
-      out_cnt[qi] = nf;
+      if (sub == 0) out_cnt[qi] = nf;
     }
-    __syncthreads();   // the page buffer and s_w are reused by the next item
+    __syncwarp();   // the page buffer and the cell queues are reused by the next item
   }
 }
 

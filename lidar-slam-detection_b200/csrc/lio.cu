@@ -440,6 +440,107 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
   grid_finalize<29>(partials, done, result, 0, 29, (double)n_true, kResSeq, seq, sc, 0);
 }
 
+// ---------------------------------------------------------------- K4+K5, reuse evaluation, ONE thread-block cluster
+// Iterations that keep Nearest_Points (ekfom_data.converge == false, laserMapping.cpp:842) only re-evaluate the cached
+// planes: ~12 k points x ~200 flops.  The grid-wide shape above spends most of its 15 us on launch + drain + the
+// partials -> atomic ticket -> last-block fold chain.  Here the whole evaluation is ONE cluster of 8 CTAs x 1024 threads
+// (8192 points per pass): warp shuffles -> per-warp accumulators in shared memory -> one partial vector per CTA written
+// into CTA 0's shared memory over DSMEM -> cluster barrier -> CTA 0 folds the 8 vectors in rank order and publishes to
+// the host.  No global partials, no atomics, no __threadfence; fixed order, so bit-reproducible.  Single-GPU handles only
+// (the tile-sharded mode keeps the grid-wide kernel and its in-kernel cross-rank exchange).
+#ifndef LSD_SIMT_EMU
+}  // namespace lsd
+#include <cooperative_groups.h>
+namespace lsd {
+namespace cg = cooperative_groups;
+constexpr int kRcMaxCtas = 16, kRcMaxWarps = 32;   // cluster shape chosen at launch (lsd_lio::rc_ctas x rc_threads)
+__global__ void __launch_bounds__(1024, 1)
+lio_hmodel_reuse_cluster_kernel(const float4* __restrict__ body, const int* __restrict__ n_ptr, int cap, LioPose ps,
+                                unsigned char* __restrict__ selected, const float4* __restrict__ pabcd_io,
+                                const unsigned char* __restrict__ plane_ok, float4* __restrict__ plane, float4* __restrict__ world,
+                                double* __restrict__ result, double seq) {
+  pdl_enter();
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double sm_w[kRcMaxWarps][30];    // per-warp accumulators
+  __shared__ double sm_cta[kRcMaxCtas][32];   // CTA 0's copy collects one partial vector per CTA
+  const int kRcCtas = (int)cluster.num_blocks(), kRcThreads = (int)blockDim.x, kRcWarps = kRcThreads >> 5;
+  const int n_true = __ldcg(n_ptr);
+  const int n = min(n_true, cap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned rank = cluster.block_rank();
+  if (lane < 30) sm_w[warp][lane] = 0.0;
+  __syncwarp();
+  const int stride = kRcCtas * kRcThreads;
+  const int n_pass = (n + stride - 1) / stride;
+#pragma unroll 1
+  for (int pass = 0; pass < n_pass; pass++) {
+    const int i = pass * stride + (int)rank * kRcThreads + (int)threadIdx.x;
+    double row[6] = {0, 0, 0, 0, 0, 0}, h = 0.0, ares = 0.0, one = 0.0;
+    if (i < n) {
+      const float4 pb = __ldg(body + i);
+      const double bx = pb.x, by = pb.y, bz = pb.z;
+      const double lx = ps.RL[0] * bx + ps.RL[1] * by + ps.RL[2] * bz + ps.tL[0];
+      const double ly = ps.RL[3] * bx + ps.RL[4] * by + ps.RL[5] * bz + ps.tL[1];
+      const double lz = ps.RL[6] * bx + ps.RL[7] * by + ps.RL[8] * bz + ps.tL[2];
+      const float wx = (float)(ps.R[0] * lx + ps.R[1] * ly + ps.R[2] * lz + ps.t[0]);
+      const float wy = (float)(ps.R[3] * lx + ps.R[4] * ly + ps.R[5] * lz + ps.t[1]);
+      const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
+      world[i] = make_float4(wx, wy, wz, pb.w);
+      bool keep = false;
+      if (selected[i] && plane_ok[i]) {
+        const float4 pl = pabcd_io[i];
+        const float pabcd[4] = {pl.x, pl.y, pl.z, pl.w};
+        const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];
+        const double s = 1 - 0.9 * fabs((double)pd2) / sqrt(sqrt(bx * bx + by * by + bz * bz));  // laserMapping.cpp:861
+        if ((float)s > 0.9) {
+          keep = true;
+          plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
+          const RowH r = make_row(ps, lx, ly, lz, pabcd, pd2);
+#pragma unroll
+          for (int a = 0; a < 6; a++) row[a] = r.row[a];
+          h = r.h; ares = (double)fabsf(pd2); one = 1.0;
+        }
+      }
+      selected[i] = keep ? 1 : 0;
+    }
+    // 29 sums of this pass: products formed on the fly, warp tree, lane 0 accumulates (ascending passes)
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+#pragma unroll
+      for (int c = a; c < 6; c++) { const double v = warp_sum(row[a] * row[c]); if (lane == 0) sm_w[warp][q] += v; q++; }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) { const double v = warp_sum(row[a] * h); if (lane == 0) sm_w[warp][21 + a] += v; }
+    { const double v = warp_sum(ares); if (lane == 0) sm_w[warp][27] += v; }
+    { const double v = warp_sum(one); if (lane == 0) sm_w[warp][28] += v; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 29) {
+    double s = 0.0;
+    for (int w = 0; w < kRcWarps; w++) s += sm_w[w][threadIdx.x];
+    double* dst = cluster.map_shared_rank(&sm_cta[0][0], 0);     // CTA 0's shared memory, over DSMEM
+    dst[rank * 32 + threadIdx.x] = s;
+  }
+  cluster.sync();
+  if (rank == 0) {
+    if (threadIdx.x < 29) {
+      double t = 0.0;
+      for (int r = 0; r < kRcCtas; r++) t += sm_cta[r][threadIdx.x];
+      reinterpret_cast<volatile double*>(result)[threadIdx.x] = t;
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      volatile double* res = result;
+      res[29] = (double)n_true;
+      __threadfence_system();
+      res[kResSeq] = seq;  // published last
+    }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------- degeneracy sums (laserMapping.cpp:946-970)
 // Only launched when the host cannot certify non-degeneracy from the eigenvalues (lio_linearize).
 struct Eig3 { double V[9]; };  // columns = eigenvectors
@@ -650,6 +751,19 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
                l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches += 2;
   } else {
+#ifndef LSD_SIMT_EMU
+    if (l->sc.world <= 1 && l->reuse_cluster) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(l->rc_ctas); cfg.blockDim = dim3(l->rc_threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cudaLaunchAttribute at[2];
+      int na = 0;
+      at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = l->rc_ctas; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; na++;
+      if (pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+      cfg.attrs = at; cfg.numAttrs = na;
+      (void)cudaLaunchKernelEx(&cfg, lio_hmodel_reuse_cluster_kernel, (const float4*)l->d_body, (const int*)l->d_n, l->p.max_points, ps, l->d_selected,
+                               (const float4*)l->d_pabcd, (const unsigned char*)l->d_plane_ok, l->d_plane, l->d_world, l->d_result, seq);
+    } else
+#endif
     LSD_LAUNCH(pdl, lio_hmodel_kernel<false>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
                l->d_partials, l->d_done, l->d_result, seq, l->sc);
@@ -1072,14 +1186,28 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   // the map and the voxel grid run on the LIO stream
   cudaStreamDestroy(l->map->stream); l->map->stream = l->stream;
   cudaStreamDestroy(l->vg->stream); l->vg->stream = l->stream;
-  // Defaults validated on B200 in round 1 (bit-identical results, tests/test_gpu_zz_pdl.py): programmatic dependent launch for
-  // the scan's kernel chain, and the voxel grid of an announced scan pipelined under the running one.  LSD_PDL=0 /
-  // LSD_PIPELINE_VG=0 in the environment (or lsd_lio_set_pdl / lsd_lio_set_pipeline) turn them off.
-  { const char* ev = getenv("LSD_PDL"); l->pdl = (ev && ev[0] == '0') ? 0 : 1; }
+  // The voxel grid of an announced scan is pipelined under the running one by default (bit-identical results,
+  // tests/test_gpu_zz_pdl.py; LSD_PIPELINE_VG=0 / lsd_lio_set_pipeline turn it off).  Programmatic dependent launch stays
+  // opt-in (LSD_PDL=1 / lsd_lio_set_pdl): measured on B200 in one process on one box (profiles/r02d_lio_probe.jsonl) it
+  // shortens the device time per scan but cudaLaunchKernelEx costs the host ~2.5 us more per launch than <<<>>>, and with
+  // a host loop that is synchronous per evaluation that is on the critical path: 4779 scans/s with it, 5649 without.
+  { const char* ev = getenv("LSD_PDL"); l->pdl = (ev && ev[0] == '1') ? 1 : 0; }
   { const char* ev = getenv("LSD_PIPELINE_VG"); l->pipeline_vg = (ev && ev[0] == '0') ? 0 : 1; }
   // The reference's Nearest_Points rows outlive a search that finds nothing (laserMapping.cpp:1273, ivox3d.h:155-157);
   // reproducing that is what default-path parity needs (lsd_lio_set_stale_rows(l, 0) turns it off).
   l->stale_rows = true;
+  {  // cluster-shaped reuse evaluation: opt-in, LSD_REUSE_CLUSTER="CxT" = C CTAs of T threads.  Measured slower than the
+     // grid-wide kernel in every shape tried on B200 (15.6 us vs 21.5 us for 16 x 256 ... 56 us for 2 x 1024,
+     // profiles/r02d_lio_probe.jsonl): the per-pass shuffle reduction that keeps it inside 64 registers costs more than the
+     // partials -> ticket -> last-block fold it replaces.
+    const char* ev = getenv("LSD_REUSE_CLUSTER");
+    l->reuse_cluster = (ev && ev[0] >= '1' && ev[0] <= '9') ? 1 : 0;
+    int c = 0, t = 0;
+    if (ev && sscanf(ev, "%dx%d", &c, &t) == 2 && c >= 1 && c <= 16 && t >= 32 && t <= 1024 && t % 32 == 0) { l->rc_ctas = c; l->rc_threads = t; }
+#ifndef LSD_SIMT_EMU
+    if (l->rc_ctas > 8) cudaFuncSetAttribute(lio_hmodel_reuse_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+#endif
+  }
   *out = l;
   return LSD_OK;
 }

@@ -55,6 +55,8 @@ struct lsd_lio {
   float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)
   int* d_near_cnt = nullptr;
   int knn_shape = 0;            // lsd_lio_set_knn_shape: 0/1 warp per scan point (lio_knn_kernel)
+  int rc_ctas = 8, rc_threads = 256;   // its cluster shape (LSD_REUSE_CLUSTER=CxT)
+  int reuse_cluster = 0;        // reuse evaluations as ONE thread-block cluster with a DSMEM reduction (lio_hmodel_reuse_cluster_kernel)
   int pdl = 0;                  // lsd_lio_set_pdl: launch the scan's kernels with programmatic dependent launch
   int rows_parity = 0;          // which of d_rows[0..1] the next Nearest_Points.resize publishes (the other one is read)
   bool rows_resize_pending = false;   // the loaded scan's first search still has to do Nearest_Points.resize (lio_knn_kernel)

@@ -78,8 +78,8 @@ struct TopK {
     for (int i = 0; i < K; i++) { d[i] = 3.0e38f; id[i] = 0x7fffffff; }
   }
   // insert (d2, pid) keeping ascending (d2, id) order; fully unrolled compare-exchange chain (registers only)
-  __device__ __forceinline__ void push(float d2, int pid) {
-    if (!(d2 < d[K - 1] || (d2 == d[K - 1] && pid < id[K - 1]))) return;
+  __device__ __forceinline__ bool push(float d2, int pid) {
+    if (!(d2 < d[K - 1] || (d2 == d[K - 1] && pid < id[K - 1]))) return false;
     d[K - 1] = d2; id[K - 1] = pid;
 #pragma unroll
     for (int i = K - 1; i > 0; i--) {
@@ -88,6 +88,7 @@ struct TopK {
       d[i] = sw ? d[i - 1] : d[i]; id[i] = sw ? id[i - 1] : id[i];
       d[i - 1] = sw ? td : d[i - 1]; id[i - 1] = sw ? ti : id[i - 1];
     }
+    return true;
   }
 };
 
@@ -343,9 +344,9 @@ static lsd_status_t launch_knn_bricks(lsd_map* m, const float4* d_q, int nq, int
   brick_bin_kernel<<<gq, 256, 0, st>>>(bv, m->view.inv_res, d_q, nq, k, q_slot, q_rank, m->bin_count, d_idx, d_d2, d_cnt);
   brick_plan_kernel<<<(unsigned)((m->n_bricks + 255) / 256), 256, 0, st>>>(bv, m->n_bricks, m->bin_count, m->bin_base, work, ctr);
   brick_scatter_kernel<<<gq, 256, 0, st>>>(q_slot, q_rank, m->bin_base, nq, sorted);
-  const int grid = (int)std::min<size_t>(148 * 16, n_work_max);
-  if (k == 1) brick_knn_kernel<1><<<grid, kBrickQC, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
-  else brick_knn_kernel<5><<<grid, kBrickQC, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
+  const int grid = (int)std::min<size_t>(148 * 12, (n_work_max + kBrickWarps - 1) / kBrickWarps);   // 12 CTAs x 4 warps x 4.6 KB per SM
+  if (k == 1) brick_knn_kernel<1><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
+  else brick_knn_kernel<5><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
   LSD_CUDA(cudaGetLastError());
   m->launches += 4;
   return LSD_OK;

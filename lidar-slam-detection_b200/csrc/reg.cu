@@ -18,7 +18,10 @@
 //     of 36/128), C^-1 = I + 999 n n^T is applied in closed form, no per-correspondence 3x3 inversion
 //     for NDT.
 //   * GICP neighbours come from the hash-voxel map's exact search (knn.cuh) instead of a k-d tree.
+#include <unistd.h>
+
 #include <chrono>
+#include <vector>
 
 #include "knn.cuh"
 #include "lio.h"
@@ -38,13 +41,18 @@ __device__ __forceinline__ int3 ndt_coord(float x, float y, float z, float res) 
   return make_int3((int)floorf(x / res - 0.5f), (int)floorf(y / res - 0.5f), (int)floorf(z / res - 0.5f));
 }
 
+// Tile-sharded target: with world > 1 a rank keeps only the voxels of the x-y tiles it owns
+// (tile_owner, lsd_common.cuh).  Every (source point, stencil offset) pair then finds its voxel on exactly one rank, so the
+// ranks' sums partition the single-GPU sums and the in-kernel all-reduce (grid_finalize) restores them: no halo needed.
 __global__ void __launch_bounds__(256) ndt_accum_kernel(NdtBuildLine* __restrict__ tab, unsigned long long mask, float res,
-                                                        const float4* __restrict__ pts, int n, unsigned* __restrict__ fail) {
+                                                        const float4* __restrict__ pts, int n, unsigned* __restrict__ fail,
+                                                        int shard_rank, int shard_world, int shard_tile) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = __ldg(pts + i);
   const int3 c = ndt_coord(p.x, p.y, p.z, res);
   if (!coord_ok(c.x, c.y, c.z)) { atomicAdd(fail, 1u); return; }
+  if (shard_world > 1 && tile_owner(c.x, c.y, shard_tile, shard_world) != shard_rank) return;   // another rank's voxel
   const unsigned long long key = pack_key(c.x, c.y, c.z, 0);
   unsigned long long s = hash_key(key) & mask;
   for (unsigned probe = 0; probe < kMaxProbe; probe++) {
@@ -233,6 +241,57 @@ __global__ void __launch_bounds__(kRegWarps * 32, 3) gicp_normals_kernel(MapView
       double nr[3];
       smallest_eigvec(C, nr);
       double* o = nrm + 4 * (size_t)i;  // double: C = I - 0.999 n n^T is inverted with condition number 1000
+      o[0] = nr[0]; o[1] = nr[1]; o[2] = nr[2]; o[3] = (double)nf;
+    }
+  }
+}
+
+// The reference takes the k nearest neighbours wherever they are (pcl::search::KdTree::nearestKSearch,
+// fast_gicp_impl.hpp:259); max_sq above only bounds the fast grid search.  Points that found fewer than k inside the
+// radius — sparse rings of a scan at long range — are completed here by an exact scan of the whole cloud: one warp per
+// such point, the k best kept sorted across lanes 0 .. k-1 in registers (insert = ballot rank + one shuffle).
+__global__ void __launch_bounds__(kRegWarps * 32) gicp_normals_complete_kernel(const float4* __restrict__ pts, int n, int k,
+                                                                              double* __restrict__ nrm) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * kRegWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kRegWarps) {
+    if (nrm[4 * (size_t)i + 3] >= (double)k) continue;     // warp-uniform
+    const float4 p = __ldg(pts + i);
+    float bd = 3.0e38f; int bi = 0x7fffffff;               // lane r: r-th best so far (lanes >= k unused)
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      float d2 = 3.0e38f;
+      if (j < n) { const float4 a = __ldg(pts + j); d2 = dist2(p.x, p.y, p.z, a.x, a.y, a.z); }
+      // worst kept entry (lane k-1) as the admission test
+      const float wd = __shfl_sync(0xffffffffu, bd, k - 1); const int wi = __shfl_sync(0xffffffffu, bi, k - 1);
+      unsigned cand = __ballot_sync(0xffffffffu, j < n && (d2 < wd || (d2 == wd && j < wi)));
+      while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const float nd = __shfl_sync(0xffffffffu, d2, src); const int ni = j0 + src;
+        const bool less = bd < nd || (bd == nd && bi < ni);                 // my entry stays before the new one
+        const int pos = __popc(__ballot_sync(0xffffffffu, less && lane < k));
+        const float ud = __shfl_up_sync(0xffffffffu, bd, 1); const int ui = __shfl_up_sync(0xffffffffu, bi, 1);
+        if (pos < k) {
+          if (lane == pos) { bd = nd; bi = ni; }
+          else if (lane > pos && lane < k) { bd = ud; bi = ui; }
+        }
+      }
+    }
+    const int nf = min(n, k);
+    double x = 0, y = 0, z = 0;
+    if (lane < nf) { const float4 q = __ldg(pts + bi); x = q.x; y = q.y; z = q.z; }
+    const double kk = (double)k;
+    const double mx = warp_sum(x) / kk, my = warp_sum(y) / kk, mz = warp_sum(z) / kk;
+    const double dx = (lane < k ? x : 0.0) - (lane < k ? mx : 0.0), dy = (lane < k ? y : 0.0) - (lane < k ? my : 0.0),
+                 dz = (lane < k ? z : 0.0) - (lane < k ? mz : 0.0);
+    double C[9];
+    C[0] = warp_sum(dx * dx) / kk; C[1] = warp_sum(dx * dy) / kk; C[2] = warp_sum(dx * dz) / kk;
+    C[4] = warp_sum(dy * dy) / kk; C[5] = warp_sum(dy * dz) / kk; C[8] = warp_sum(dz * dz) / kk;
+    C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+    if (lane == 0) {
+      double nr[3];
+      smallest_eigvec(C, nr);
+      double* o = nrm + 4 * (size_t)i;
       o[0] = nr[0]; o[1] = nr[1]; o[2] = nr[2]; o[3] = (double)nf;
     }
   }
@@ -660,6 +719,11 @@ struct lsd_reg {
   double *h_result = nullptr, *d_result = nullptr;
   long long seq = 0;
   lsd::ShardComm sc;
+  int shard_tile = 32;              // lsd_reg_shard_export: x-y tile edge in NDT voxels
+  float4* d_stage = nullptr; size_t stage_cap = 0;   // staging of host clouds (lsd_reg_set_target / _source)
+  int pending_world = 0;            // world announced by lsd_reg_shard_export, active after lsd_reg_shard_connect
+  double* d_inbox = nullptr;        // this rank's inbox of the in-kernel all-reduce (grid_finalize)
+  std::vector<void*> ipc_opened;
   double final_T[16];
   double lin_T[16];
   int converged = 0, iterations = 0;
@@ -700,6 +764,7 @@ static lsd_status_t reg_cost(lsd_reg* r, const double* T, bool update, double* H
   const double seq = (double)(++r->seq);
   const bool deriv = H36 != nullptr;
   if (update) memcpy(r->lin_T, T, sizeof(r->lin_T));
+  if (r->sc.world > 1 && r->p.kind != LSD_REG_NDT_P2D) { set_error("tile-sharded matching serves NDT_P2D only (GICP needs a cross-rank arg-min, not a sum)"); return LSD_ERR_INVALID; }
   if (r->p.kind == LSD_REG_NDT_P2D) {
     if (!r->ndt.lines) { set_error("registration: no target cloud"); return LSD_ERR_INVALID; }
     Pose34f lin, ev;
@@ -974,10 +1039,71 @@ lsd_status_t lsd_reg_destroy(lsd_reg_t* r) {
   void* ptrs[] = {r->d_src, r->d_tgt, r->d_src_nrm, r->d_tgt_nrm, r->ndt.lines, r->vg.lines, r->d_corr, r->d_maha, r->d_partials, r->d_done};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(r->h_result);
+  for (void* q : r->ipc_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(r->d_inbox); cudaFree(r->d_stage);
   if (r->tgt_map) lsd_map_destroy(r->tgt_map);
   if (r->src_map) lsd_map_destroy(r->src_map);
   if (r->stream) cudaStreamDestroy(r->stream);
   delete r;
+  return LSD_OK;
+}
+
+// Tile-sharded NDT target (include/lsdreg.h "Tile-sharded matcher").  Same hand-shake as
+// lsd_lio_shard_*: export a blob naming this rank's inbox, all-gather, connect.  Same-process peers use raw pointers.
+struct RegShardBlob { long long pid; unsigned long long inbox; cudaIpcMemHandle_t h_inbox; };
+static_assert(sizeof(RegShardBlob) <= LSD_SHARD_BLOB_BYTES, "LSD_SHARD_BLOB_BYTES too small");
+
+lsd_status_t lsd_reg_shard_export(lsd_reg_t* r, int rank, int world, int tile_cells, unsigned char* blob_out) {
+  if (!r || !blob_out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || tile_cells < 1) { set_error("lsd_reg_shard_export: bad rank / world (max %d ranks) / tile", kMaxRanks); return LSD_ERR_INVALID; }
+  if (r->p.kind != LSD_REG_NDT_P2D) { set_error("lsd_reg_shard_export: tile sharding serves NDT_P2D only"); return LSD_ERR_INVALID; }
+  LSD_CUDA(cudaSetDevice(r->device));
+  if (!r->d_inbox) {
+    LSD_CUDA(cudaMalloc((void**)&r->d_inbox, 2 * kInboxRegion * sizeof(double)));
+    LSD_CUDA(cudaMemset(r->d_inbox, 0, 2 * kInboxRegion * sizeof(double)));
+    LSD_CUDA(cudaDeviceSynchronize());
+  }
+  RegShardBlob b;
+  memset(&b, 0, sizeof(b));
+  b.pid = (long long)getpid();
+  b.inbox = (unsigned long long)r->d_inbox;
+  LSD_CUDA(cudaIpcGetMemHandle(&b.h_inbox, r->d_inbox));
+  memset(blob_out, 0, LSD_SHARD_BLOB_BYTES);
+  memcpy(blob_out, &b, sizeof(b));
+  memset(&r->sc, 0, sizeof(r->sc));
+  r->sc.rank = rank; r->sc.world = 1;      // not connected yet: lsd_reg_shard_connect sets the world
+  r->shard_tile = tile_cells;
+  r->pending_world = world;
+  return LSD_OK;
+}
+
+lsd_status_t lsd_reg_shard_connect(lsd_reg_t* r, const unsigned char* blobs) {
+  if (!r || !blobs || r->pending_world < 1 || !r->d_inbox) { set_error("lsd_reg_shard_connect: call lsd_reg_shard_export first"); return LSD_ERR_INVALID; }
+  LSD_CUDA(cudaSetDevice(r->device));
+  ShardComm sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.rank = r->sc.rank; sc.world = r->pending_world;
+  for (int p = 0; p < sc.world; p++) {
+    RegShardBlob b;
+    memcpy(&b, blobs + (size_t)p * LSD_SHARD_BLOB_BYTES, sizeof(b));
+    if (p == sc.rank) { sc.inbox[p] = r->d_inbox; continue; }
+    if (b.pid == (long long)getpid()) {
+      sc.inbox[p] = reinterpret_cast<double*>(b.inbox);
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, sc.inbox[p]) == cudaSuccess && at.device != r->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+      }
+    } else {
+      void* pi = nullptr;
+      LSD_CUDA(cudaIpcOpenMemHandle(&pi, b.h_inbox, cudaIpcMemLazyEnablePeerAccess));
+      sc.inbox[p] = static_cast<double*>(pi);
+      r->ipc_opened.push_back(pi);
+    }
+  }
+  r->sc = sc;
+  r->seq = 0;                       // all ranks restart their sequence numbers together
+  r->h_result[kResSeq] = 0.0;
   return LSD_OK;
 }
 
@@ -988,13 +1114,22 @@ static int auto_log2(size_t n_items, int lo, int hi) {
 }
 
 static lsd_status_t build_point_map(lsd_reg* r, lsd_map** mp, const float4* d_pts, int n) {
-  if (*mp) { lsd_map_destroy(*mp); *mp = nullptr; }
   const int l2 = r->p.map_log2_lines > 0 ? r->p.map_log2_lines : auto_log2((size_t)n, 12, 26);
-  lsd_status_t s = lsd_map_create(mp, (float)r->p.map_resolution, l2);
-  if (s) return s;
-  cudaStreamDestroy((*mp)->stream);
-  (*mp)->stream = nullptr;
-  s = launch_insert(*mp, d_pts, n, 0, r->stream);
+  if (*mp && (*mp)->n_lines == (1ull << l2)) {
+    // same table size as the previous cloud (a batch of equally sized submaps, config 4): reset in place on the handle's
+    // stream — two memsets instead of cudaFree + cudaMalloc + a synchronising clear per call
+    lsd_map* m = *mp;
+    LSD_CUDA(cudaMemsetAsync(m->view.lines, 0, m->n_lines * sizeof(CellLine), r->stream));
+    LSD_CUDA(cudaMemsetAsync(m->view.tags, 0, m->n_lines, r->stream));
+    LSD_CUDA(cudaMemsetAsync(m->view.counters, 0, 4 * sizeof(unsigned long long), r->stream));
+  } else {
+    if (*mp) { lsd_map_destroy(*mp); *mp = nullptr; }
+    lsd_status_t s = lsd_map_create(mp, (float)r->p.map_resolution, l2);
+    if (s) return s;
+    cudaStreamDestroy((*mp)->stream);
+    (*mp)->stream = nullptr;
+  }
+  lsd_status_t s = launch_insert(*mp, d_pts, n, 0, r->stream);
   (*mp)->stream = nullptr;
   return s;
 }
@@ -1031,7 +1166,7 @@ lsd_status_t lsd_reg_set_target_dev(lsd_reg_t* r, const float* pts_dev, int n) {
     r->ndt.res = (float)r->p.resolution;
     unsigned* d_cnt = reinterpret_cast<unsigned*>(r->d_done) + 4;
     LSD_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
-    ndt_accum_kernel<<<(n + 255) / 256, 256, 0, st>>>(build, lines - 1, r->ndt.res, r->d_tgt, n, d_cnt);
+    ndt_accum_kernel<<<(n + 255) / 256, 256, 0, st>>>(build, lines - 1, r->ndt.res, r->d_tgt, n, d_cnt, r->sc.rank, r->sc.world, r->shard_tile);
     ndt_finalize_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(build, r->ndt.lines, lines, d_cnt + 1);
     r->launches += 2;
     unsigned h[2] = {0, 0};
@@ -1045,8 +1180,9 @@ lsd_status_t lsd_reg_set_target_dev(lsd_reg_t* r, const float* pts_dev, int n) {
     if (s) return s;
     gicp_normals_kernel<<<warp_grid(n), kRegWarps * 32, 0, st>>>(r->tgt_map->view, r->d_tgt, n, r->p.k_correspondences,
                                                                 (float)r->p.normal_search_sq, r->d_tgt_nrm);
+    gicp_normals_complete_kernel<<<warp_grid(n), kRegWarps * 32, 0, st>>>(r->d_tgt, n, r->p.k_correspondences, r->d_tgt_nrm);
     LSD_CUDA(cudaGetLastError());
-    r->launches += 2;
+    r->launches += 3;
     r->tgt_map_built = true;
     if (r->p.kind == LSD_REG_VGICP) {  // GaussianVoxelMap::create_voxelmap (built lazily by the reference, fast_vgicp_impl.hpp:121-124)
       const int l2 = r->p.map_log2_lines > 0 ? r->p.map_log2_lines : auto_log2((size_t)n / 2 + 1024, 12, 27);
@@ -1091,15 +1227,22 @@ lsd_status_t lsd_reg_set_source_dev(lsd_reg_t* r, const float* pts_dev, int n) {
     if (s) return s;
     gicp_normals_kernel<<<warp_grid(n), kRegWarps * 32, 0, st>>>(r->src_map->view, r->d_src, n, r->p.k_correspondences,
                                                                 (float)r->p.normal_search_sq, r->d_src_nrm);
+    gicp_normals_complete_kernel<<<warp_grid(n), kRegWarps * 32, 0, st>>>(r->d_src, n, r->p.k_correspondences, r->d_src_nrm);
     LSD_CUDA(cudaGetLastError());
-    r->launches += 2;
+    r->launches += 3;
     LSD_CUDA(cudaStreamSynchronize(st));
   }
   return LSD_OK;
 }
 
+// host-pointer entry points: a staging buffer that lives with the handle (grown on demand, never shrunk)
 static lsd_status_t stage_host(lsd_reg* r, const float* host, int n, float4** tmp) {
-  LSD_CUDA(cudaMalloc((void**)tmp, (size_t)n * 16));
+  if ((size_t)n > r->stage_cap) {
+    cudaFree(r->d_stage); r->d_stage = nullptr; r->stage_cap = 0;
+    LSD_CUDA(cudaMalloc((void**)&r->d_stage, (size_t)n * 16));
+    r->stage_cap = (size_t)n;
+  }
+  *tmp = r->d_stage;
   LSD_CUDA(cudaMemcpyAsync(*tmp, host, (size_t)n * 16, cudaMemcpyHostToDevice, r->stream));
   return LSD_OK;
 }
@@ -1110,7 +1253,6 @@ lsd_status_t lsd_reg_set_target(lsd_reg_t* r, const float* pts_host, int n) {
   lsd_status_t s = stage_host(r, pts_host, n, &tmp);
   if (!s) s = lsd_reg_set_target_dev(r, reinterpret_cast<const float*>(tmp), n);
   cudaStreamSynchronize(r->stream);
-  cudaFree(tmp);
   return s;
 }
 lsd_status_t lsd_reg_set_source(lsd_reg_t* r, const float* pts_host, int n) {
@@ -1120,7 +1262,6 @@ lsd_status_t lsd_reg_set_source(lsd_reg_t* r, const float* pts_host, int n) {
   lsd_status_t s = stage_host(r, pts_host, n, &tmp);
   if (!s) s = lsd_reg_set_source_dev(r, reinterpret_cast<const float*>(tmp), n);
   cudaStreamSynchronize(r->stream);
-  cudaFree(tmp);
   return s;
 }
 
@@ -1154,6 +1295,7 @@ lsd_status_t lsd_reg_get_final(lsd_reg_t* r, double* T16, double* H36) {
 
 lsd_status_t lsd_reg_fitness(lsd_reg_t* r, const double* T16_or_null, double max_range, double* score) {
   if (!r || !score || r->n_src <= 0 || r->n_tgt <= 0) return LSD_ERR_INVALID;
+  if (r->sc.world > 1) { set_error("lsd_reg_fitness: not available on a tile-sharded handle (a nearest neighbour is an arg-min across ranks, not a sum)"); return LSD_ERR_INVALID; }
   LSD_CUDA(cudaSetDevice(r->device));
   cudaStream_t st = r->stream;
   if (!r->tgt_map_built) {

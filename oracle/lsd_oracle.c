@@ -732,6 +732,18 @@ void orc_gicp_normals(const OrcIvox* map, const float* pts, int stride, int n, i
     OrcCand best[64];
     int kk = k > 64 ? 64 : k;
     int nb = exact_knn_one(map, pts + (size_t)stride * i, kk, max_sq, best);
+    if (nb < kk && n > nb) {
+      /* The reference takes the k nearest neighbours wherever they are (pcl::search::KdTree::nearestKSearch,
+       * fast_gicp_impl.hpp:259): max_sq only bounds the fast grid search.  A point with fewer than k neighbours inside
+       * the radius (sparse rings of a scan at long range) gets the true k-NN by an exact scan of the cloud. */
+      nb = 0;
+      for (int j = 0; j < n; j++) {
+        const float* b = pts + (size_t)stride * j;
+        OrcPt pj = {b[0], b[1], b[2], j};
+        OrcCand cd = {dist2f(pts + (size_t)stride * i, &pj), j, b[0], b[1], b[2]};
+        topk_insert(best, &nb, kk, &cd);
+      }
+    }
     cnt[i] = nb;
     double mean[3] = {0, 0, 0}, C[9] = {0};
     for (int j = 0; j < nb; j++) { mean[0] += best[j].x; mean[1] += best[j].y; mean[2] += best[j].z; }

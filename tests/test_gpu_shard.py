@@ -79,3 +79,52 @@ def test_sharded_ranks_match_single_gpu(small_world, world):
         # the unsharded run searched at states that differ from the sharded ones in the last bits (other
         # summation order), so a handful of add/skip decisions and voxel-face cases may differ
         assert same.mean() > 0.99, same.mean()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ndt_matches_single_gpu(world):
+    """Row C3 of SURVEY.md section 8e: the NDT target voxelised per x-y tile on its owner, [H, b, err] all-reduced inside the
+    cost kernel.  Ranks are emulated on one device (two / three handles, one thread each).  Bars: the voxel counts of the
+    shards partition the unsharded map; one cost evaluation equals the unsharded one to 1e-12 relative (same fp32
+    per-point terms, double sums in another order); align() returns the same pose to 1e-9 with the same iteration count
+    and flag; all ranks agree bit for bit."""
+    import lsdreg
+    from lsdreg import synth
+    m = synth.block_map(1, 1, 1, 0.25)
+    m[:, :2] -= np.array([60, 40], np.float32)
+    Rgt = synth.rot_from_rpy(0.01, -0.02, 0.3)
+    tgt = np.array([1.0, -2.0, 1.8])
+    scan = synth.scan64(2, 200, Rgt, tgt + np.array([60, 40, 0]))[::2].copy()
+    dR, dt = synth.perturb(5, 0.5, 3.0)
+    guess = np.eye(4); guess[:3, :3] = Rgt @ dR; guess[:3, 3] = tgt + dt
+    single = lsdreg.Matcher("NDT_CUDA")
+    single.set_target(m); single.set_source(scan)
+    e1, H1, b1, nc1 = single.cost(guess)
+    T1 = single.align(guess); T1d, _ = single.final()
+    it1, cv1 = single.iterations, single.converged
+
+    ranks = [lsdreg.Matcher("NDT_CUDA") for _ in range(world)]
+    blobs = np.stack([r.shard_export(k, world, 8) for k, r in enumerate(ranks)])      # 8-voxel tiles: many tiles in a 120 x 80 m block
+    for r in ranks:
+        r.shard_connect(blobs)
+    for r in ranks:
+        r.set_target(m); r.set_source(scan)          # each rank filters the cloud by tile ownership on the device
+    nv = [r.stats()["n_voxels"] for r in ranks]
+    assert sum(nv) == single.stats()["n_voxels"] and min(nv) > 0, (nv, single.stats())
+    res = _run_threads([lambda r=r: r.cost(guess) for r in ranks])
+    for e, H, b, nc in res:
+        assert nc == nc1
+        np.testing.assert_allclose(e, e1, rtol=1e-12)
+        np.testing.assert_allclose(H, H1, rtol=1e-11, atol=1e-11 * np.abs(H1).max())
+        np.testing.assert_allclose(b, b1, rtol=1e-11, atol=1e-11 * np.abs(b1).max())
+    assert all(np.array_equal(res[0][1], x[1]) for x in res[1:])                      # rank-ordered fold: bit-identical
+    outs = _run_threads([lambda r=r: (r.align(guess), r.final()[0], r.iterations, r.converged) for r in ranks])
+    for T, Td, it, cv in outs:
+        assert it == it1 and cv == cv1
+        np.testing.assert_allclose(Td, T1d, rtol=0, atol=1e-9)
+    assert all(np.array_equal(outs[0][1], x[1]) for x in outs[1:])
+    with pytest.raises(lsdreg.LsdError):
+        ranks[0].fitness(25.0)
+    g = lsdreg.Matcher("FAST_GICP")
+    with pytest.raises(lsdreg.LsdError):
+        g.shard_export(0, 2, 8)
