@@ -33,6 +33,7 @@ typedef int lsd_status_t;
 #define LSD_SCAN_TOO_SMALL 2        /* feats_down_size < 5, laserMapping.cpp:1252-1256           */
 #define LSD_MAP_SEEDED 3            /* first scan only seeded the map, laserMapping.cpp:1227-1239 */
 #define LSD_LOCALMAP_NONE 5         /* Localization would set mLocalMap = nullptr (localization.cpp:352-364)                  */
+#define LSD_MAP_SATURATED 6         /* the scan was registered, but the map refused points (lsd_map_saturated): enlarge map_log2_lines or enable the LRU */
 #define LSD_IMU_INITIALIZING 4      /* ImuProcess::Process returned before undistorting (IMU_Processing.hpp:416-443) */
 #define LSD_ERR_INVALID (-1)
 #define LSD_ERR_CUDA (-2)
@@ -97,6 +98,26 @@ lsd_status_t lsd_knn_query_dev(lsd_map_t* m, const float* q_dev, int nq, int k, 
  * k in {1, 5} on the fixed stencils; shape 3 k in {1, 5} on CENTER / NEARBY6 / NEARBY18 / NEARBY26; anything else uses
  * shape 1 (shape 3 asked for explicitly on something it does not serve is LSD_ERR_INVALID). */
 lsd_status_t lsd_knn_set_shape(lsd_map_t* m, int shape);
+
+/* iVox's capacity and LRU eviction (IVox::Options::capacity_ / max_distance_, ivox3d.h:51-52; AddPoints :231-256: every
+ * inserted point moves its voxel to the front of an LRU list, and after every inserted point the voxel at the back is
+ * dropped if the map holds more than `capacity` voxels AND the travel distance handed to AddPoints exceeds the distance
+ * at which that voxel was created by more than max_distance; the reference runs with 100 000 voxels / 100 m,
+ * laserMapping.cpp:1063-1064).  The list order is sequential by nature, so it is replayed on the host from the voxel keys
+ * of each insert batch; the evicted voxels' lines are retired on the device (and the table is rebuilt when retired lines
+ * crowd it).  Call on an EMPTY map.  lsd_map_set_travel_distance: the `distance` argument of the following AddPoints
+ * (lsd_map_insert*) calls; the LIO front-end keeps its own travel_distance (laserMapping.cpp:1289-1291) and needs no
+ * call.  Evictions are applied inside the insert calls; lsd_map_evict waits for them and returns how many voxels were
+ * evicted so far.  Not on tile-sharded maps, not together with the brick layout; with it on, map_incremental is
+ * synchronous (lsd_lio_params::async_map_insert is ignored).  One corner is approximated: a voxel evicted and re-created
+ * inside ONE map_incremental batch keeps the batch's points by id, not by list position. */
+lsd_status_t lsd_map_enable_lru(lsd_map_t* m, uint64_t capacity, double max_distance);
+lsd_status_t lsd_map_set_travel_distance(lsd_map_t* m, double distance);
+lsd_status_t lsd_map_evict(lsd_map_t* m, uint64_t* n_evicted_total);
+/* *saturated = 1 when the map refused points since the previous call (probe chain full, > 127 overflow lines in a
+ * voxel, coordinates beyond +-2^18 voxels): a map that silently stopped growing degrades odometry, so poll this (the
+ * LIO front-end does, and returns LSD_MAP_SATURATED from lsd_lio_scan*). */
+lsd_status_t lsd_map_saturated(lsd_map_t* m, int* saturated, uint64_t* n_dropped_total);
 
 /* Brick layout (no reference counterpart: IVox has one layout, a hash of per-voxel point lists, ivox3d.h:31-112; this is
  * the same content arranged for batched queries).  After this call every point the map accepts is ALSO stored in the

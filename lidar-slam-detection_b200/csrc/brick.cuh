@@ -36,10 +36,11 @@ constexpr int kPageNext = kPageHead + kRegCells;      // 616
 constexpr int kPagePts = kPageNext + kBrickCap;       // 848
 constexpr int kPageBytes = 4608;
 constexpr int kBrickQC = 32;                          // queries per work item: one WARP answers an item, one query per lane
-constexpr int kBrickWarps = 4;                        // warps (= page buffers) per CTA of the query kernel
+constexpr int kBrickWarps = 4;                        // warps per CTA of the query kernel (two page buffers each)
 static_assert(kPagePts % 16 == 0 && kPagePts + 16 * kBrickCap <= kPageBytes && kPageBytes % 128 == 0, "page layout");
 
-struct BrickWork { int slot, qbase, qn; unsigned total; };
+struct __align__(32) BrickQuery { float4 p; int qi; int pad[3]; };   // a query in brick order: one full 32-byte sector (no partial-sector writes)
+struct __align__(8) BrickWork { int slot, qbase, qn; unsigned total; unsigned long long key; };   // one (brick page, <= 32 queries) unit of the search
 
 // ------------------------------------------------------------------ directory
 __device__ __forceinline__ long long brick_find(const BrickView& bv, unsigned long long key) {
@@ -228,20 +229,26 @@ __global__ void __launch_bounds__(256) brick_plan_kernel(BrickView bv, unsigned 
   const unsigned base = s_base[0] + off_c, w0 = s_base[1] + off_w;
   bin_base[s] = (int)base;
   const unsigned total = __ldcg(bv.totals + s);
+  const unsigned long long key = __ldcg(bv.keys + s);
   for (unsigned ch = 0; ch < nch; ch++) {
     BrickWork w;
-    w.slot = (int)s; w.qbase = (int)(base + ch * kBrickQC); w.qn = (int)min((unsigned)kBrickQC, c - ch * kBrickQC); w.total = total;
+    w.slot = (int)s; w.qbase = (int)(base + ch * kBrickQC); w.qn = (int)min((unsigned)kBrickQC, c - ch * kBrickQC); w.total = total; w.key = key;
     work[w0 + ch] = w;
   }
 }
 
-// K-C: the sorted query list (indices into the caller's batch)
-__global__ void __launch_bounds__(256) brick_scatter_kernel(const int* __restrict__ q_slot, const int* __restrict__ q_rank,
-                                                            const int* __restrict__ bin_base, int nq, int* __restrict__ sorted) {
+// K-C: the batch in brick order: query + its index in the caller's batch, one 32-byte sector each, so that the search
+// reads its queries with one contiguous load instead of index -> query (two dependent DRAM trips)
+__global__ void __launch_bounds__(256) brick_scatter_kernel(const float4* __restrict__ q, const int* __restrict__ q_slot,
+                                                            const int* __restrict__ q_rank, const int* __restrict__ bin_base, int nq,
+                                                            BrickQuery* __restrict__ sorted) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   const int s = q_slot[i];
-  if (s >= 0) sorted[bin_base[s] + q_rank[i]] = i;
+  if (s < 0) return;
+  BrickQuery e;
+  e.p = __ldg(q + i); e.qi = i; e.pad[0] = e.pad[1] = e.pad[2] = 0;
+  sorted[bin_base[s] + q_rank[i]] = e;
 }
 
 // ------------------------------------------------------------------ K-D: the search
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(256) brick_scatter_kernel(const int* __restric
 // 32 lanes active, half of the instructions in a branchy insertion running 3-5 lanes wide):
 //  * lane groups — a brick of the benchmark batch has ~13 queries, so an item of qn queries gives each query
 //    g = 32 / pow2ceil(qn) lanes (1, 2, 4 or 8); lane `sub` of a group takes stencil cells sub, sub + g, ...
-//  * a FLAT walk — phase 1 collects the heads of the lane's non-empty cells into a 20-byte queue in shared memory (uniform
+//  * a FLAT walk — phase 1 collects the heads of the lane's non-empty cells into a 28-byte queue in shared memory (uniform
 //    19 / g iterations, predicated stores); phase 2 is ONE loop that handles one stored point per iteration, hopping to the
 //    next queued cell when a list ends, so lanes diverge only in their total point count, not per cell;
 //  * a branch-free top-K — candidates are 64-bit keys (fp32 bits of d2 << 32 | id: d2 >= 0, so integer order is the
@@ -286,43 +293,64 @@ struct KeyTop5 {
 
 template <int K>
 __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView bv, float inv_res, int st_slot, float max_sq,
-                                                                     const float4* __restrict__ q, const int* __restrict__ sorted,
+                                                                     const BrickQuery* __restrict__ sorted,
                                                                      const BrickWork* __restrict__ work, unsigned* __restrict__ ctr,
                                                                      int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
-  __shared__ __align__(128) unsigned char pages[kBrickWarps][kPageBytes];
-  __shared__ __align__(8) unsigned long long bars[kBrickWarps];
-  __shared__ unsigned char cellq[kBrickWarps][32][20];   // per lane: heads of its non-empty stencil cells
+  // Two page buffers per warp: while item N is answered from one, item N + 1's page lands in the other, its queries sit in
+  // registers and item N + 2's descriptor is on its way — after the prologue no item waits for a memory round trip.
+  __shared__ __align__(128) unsigned char pages[kBrickWarps][2][kPageBytes];
+  __shared__ __align__(8) unsigned long long bars[kBrickWarps][2];
+  __shared__ unsigned char cellq[kBrickWarps][32][28];   // per lane: heads of its non-empty stencil cells (<= 27: NEARBY26)
   __shared__ int s_off[32];                              // the stencil as region-index offsets
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* page = pages[warp];
-  unsigned long long* bar = &bars[warp];
-  if (lane == 0) mbar_init(bar);
+  if (lane == 0) { mbar_init(&bars[warp][0]); mbar_init(&bars[warp][1]); }
   const Stencil& st = c_stencils[st_slot];
   const int n_cells = st.n;                              // <= 27 for the stencils served here
   if (threadIdx.x < 32) s_off[threadIdx.x] = (int)threadIdx.x < n_cells ? (st.off[threadIdx.x][2] * kRegXY + st.off[threadIdx.x][1]) * kRegXY + st.off[threadIdx.x][0] : 0;
   __syncthreads();
   const unsigned n_work = __ldcg(ctr + 1);
   unsigned char* myq = cellq[warp][lane];
-  unsigned phase = 0;
-  for (;;) {
-    unsigned w = 0;
-    if (lane == 0) w = atomicAdd(ctr + 2, 1u);
-    w = __shfl_sync(0xffffffffu, w, 0);
-    if (w >= n_work) break;
-    const BrickWork it = work[w];
-    const unsigned n0 = min(it.total, (unsigned)kBrickCap);
-    if (lane == 0) page_load_issue(page, bar, bv.pages + (size_t)it.slot * kPageBytes, n0);
-    // lanes per query (warp-uniform): 8 for <= 4 queries, 4 for <= 8, 2 for <= 16, else 1
-    const int lg = it.qn <= 4 ? 3 : it.qn <= 8 ? 2 : it.qn <= 16 ? 1 : 0;
-    const int g = 1 << lg, sub = lane & (g - 1), t = lane >> lg;
-    // the query and its place in the brick's region, while the page is in flight
-    const bool active = t < it.qn;
-    int qi = -1, rc0 = 0;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    const unsigned long long key = __ldcg(bv.keys + it.slot);
+  unsigned phase = 0u;                                   // bit b = parity the next wait on buffer b expects
+  const BrickWork none = {0, 0, 0, 0u, 0ull};
+
+  auto claim = [&]() { unsigned w = 0; if (lane == 0) w = atomicAdd(ctr + 2, 1u); return __shfl_sync(0xffffffffu, w, 0); };
+  auto lanes_log2 = [](int qn) { return qn <= 4 ? 3 : qn <= 8 ? 2 : qn <= 16 ? 1 : 0; };   // lanes per query: 8 / 4 / 2 / 1
+  auto load_query = [&](const BrickWork& it, float4* p, int* qi) {
+    const int t = lane >> lanes_log2(it.qn);
+    *qi = -1; *p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < it.qn) { const BrickQuery* e = sorted + it.qbase + t; *p = __ldg(&e->p); *qi = __ldg(&e->qi); }
+  };
+
+  // prologue: item 0 in flight, item 1 described
+  unsigned w = claim();
+  BrickWork it = w < n_work ? work[w] : none;
+  float4 p; int qi;
+  int b = 0;
+  if (w < n_work) {
+    if (lane == 0) page_load_issue(pages[warp][0], &bars[warp][0], bv.pages + (size_t)it.slot * kPageBytes, min(it.total, (unsigned)kBrickCap));
+    load_query(it, &p, &qi);
+  }
+  unsigned w1 = w < n_work ? claim() : n_work;
+  BrickWork it1 = w1 < n_work ? work[w1] : none;
+
+  while (w < n_work) {
+    // next item: page into the other buffer, queries into registers; the one after: descriptor
+    float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f); int qi1 = -1;
+    if (w1 < n_work) {
+      if (lane == 0) page_load_issue(pages[warp][b ^ 1], &bars[warp][b ^ 1], bv.pages + (size_t)it1.slot * kPageBytes, min(it1.total, (unsigned)kBrickCap));
+      load_query(it1, &p1, &qi1);
+    }
+    const unsigned w2 = w1 < n_work ? claim() : n_work;
+    const BrickWork it2 = w2 < n_work ? work[w2] : none;
+
+    unsigned char* page = pages[warp][b];
+    unsigned long long* bar = &bars[warp][b];
+    const int lg = lanes_log2(it.qn);
+    const int g = 1 << lg, sub = lane & (g - 1);
+    const bool active = qi >= 0;
+    int rc0 = 0;
+    const unsigned long long key = it.key;
     if (active) {
-      qi = __ldg(sorted + it.qbase + t);
-      p = __ldg(q + qi);
       const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
       const int bx = (int)((key >> 38) & 0x7ffffull) - kCoordBias, by = (int)((key >> 19) & 0x7ffffull) - kCoordBias,
                 bz = (int)(key & 0x7ffffull) - kCoordBias;
@@ -334,7 +362,7 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
     int found = 0;
     const unsigned levels = it.total ? (it.total + kBrickCap - 1) / kBrickCap : 1u;
     for (unsigned L = 0; L < levels && L <= (unsigned)kMaxLevel; L++) {
-      if (L > 0) {   // points 232 L .. of a crowded brick: their page is found by hashing (brick, L)
+      if (L > 0) {   // points 232 L .. of a crowded brick: their page is found by hashing (brick, L); loaded in place
         __syncwarp();                          // every lane is done with the previous page
         long long sl = -1;
         if (lane == 0) {
@@ -344,8 +372,8 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
         sl = __shfl_sync(0xffffffffu, sl, 0);
         if (sl < 0) continue;
       }
-      page_load_wait(bar, phase);
-      phase ^= 1u;
+      page_load_wait(bar, (phase >> b) & 1u);
+      phase ^= 1u << b;
       if (active) {
         const unsigned char* head = page + kPageHead;
         const unsigned char* next = page + kPageNext;
@@ -390,7 +418,10 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
       }
       if (sub == 0) out_cnt[qi] = nf;
     }
-    __syncwarp();   // the page buffer and the cell queues are reused by the next item
+    __syncwarp();   // this page buffer and the cell queues are free for the item after next
+    w = w1; it = it1; p = p1; qi = qi1;
+    w1 = w2; it1 = it2;
+    b ^= 1;
   }
 }
 

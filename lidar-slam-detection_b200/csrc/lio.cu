@@ -921,6 +921,27 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
   }
   prof.stop();
   LSD_CUDA(cudaMemcpyAsync(l->h_added, l->d_added, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  LSD_CUDA(cudaMemcpyAsync(l->h_added + 2, &l->map->view.counters[2], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));   // points the map refused so far
+  if (l->map->lru && l->sc.world <= 1) {
+    // iVox's LRU (lsd_map_enable_lru): replay this scan's AddPoints calls on the host mirror in the reference's order —
+    // PointToAdd first, then PointNoNeedDownsample (laserMapping.cpp:571-572), both at this scan's travel distance —
+    // and apply the evictions before the next search can see the map.
+    const int n = std::max(l->n_down, 0);
+    std::vector<float4> w((size_t)n);
+    std::vector<unsigned char> f((size_t)n);
+    if (n) {
+      LSD_CUDA(cudaMemcpyAsync(w.data(), l->d_world, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+      LSD_CUDA(cudaMemcpyAsync(f.data(), l->d_flags, (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+    LSD_CUDA(cudaStreamSynchronize(st));
+    std::vector<float4> pts; std::vector<int> ids;
+    for (int pass = 1; pass <= 2; pass++)
+      for (int i = 0; i < n; i++) if (f[i] == pass) { pts.push_back(w[i]); ids.push_back(l->next_id + i); }
+    l->map->lru->distance = l->travel;
+    lsd_status_t e = map_lru_touch(l->map, pts.data(), ids.data(), (int)pts.size(), 0, st);
+    if (e) return e;
+    wait = true;
+  }
   l->next_id += l->n_bound;
   if (wait) {
     LSD_CUDA(cudaStreamSynchronize(st));
@@ -1025,7 +1046,9 @@ static lsd_status_t issue_deferred_prefetch(lsd_lio* l) {
     src = sg->buf;
   }
   sg->valid = true; sg->age = ++l->stage_clock;
-  if (l->pipeline_vg && l->sc.world <= 1) return issue_side_vg(l, sg, src);
+  // (tile-sharded handles included: the side voxel grid waits on nothing a peer produces, so it cannot hold up the
+  // in-kernel exchange of the search kernels it overlaps with)
+  if (l->pipeline_vg) return issue_side_vg(l, sg, src);
   return LSD_OK;
 }
 
@@ -1068,6 +1091,15 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
     if (l->n_down < 5) ret = LSD_SCAN_TOO_SMALL;  // laserMapping.cpp:1252-1256 (state untouched: n_eff == 0)
     else {
       ret = s;
+      {  // travel_distance += |pos_lid - last_pos_lid| (laserMapping.cpp:1289-1291): what IVox::AddPoints ages voxels by
+        double R[9], pl[3];
+        eskf::q2R(x + eskf::S_ROT, R);
+        for (int a = 0; a < 3; a++)
+          pl[a] = x[eskf::S_POS + a] + R[3 * a] * x[eskf::S_OFFT] + R[3 * a + 1] * x[eskf::S_OFFT + 1] + R[3 * a + 2] * x[eskf::S_OFFT + 2];
+        const double dx = pl[0] - l->last_pos_lid[0], dy = pl[1] - l->last_pos_lid[1], dz = pl[2] - l->last_pos_lid[2];
+        l->travel += sqrt(dx * dx + dy * dy + dz * dz);
+        for (int a = 0; a < 3; a++) l->last_pos_lid[a] = pl[a];
+      }
       lsd_status_t m = lio_map_incremental(l, x, 1, &inf.n_added, !async);
       if (m) return m;
     }
@@ -1091,6 +1123,14 @@ lsd_status_t lio_scan(lsd_lio* l, const float4* d_scan, int n, double* x, double
   }
   inf.kernel_launches = (int)(l->launches - launches0);
   if (info) *info = inf;
+  {  // a map that refuses points stops growing and odometry degrades silently: say so (one scan late with the async insert)
+    const unsigned long long dropped = *reinterpret_cast<volatile unsigned long long*>(l->h_added + 2);
+    if (dropped > l->map->dropped_seen) {
+      l->map->dropped_seen = dropped;
+      set_error("the map refused %llu points so far (hash table full along a probe chain, a voxel beyond 127 overflow lines, or coordinates beyond +-2^18 voxels): raise map_log2_lines or enable the LRU", dropped);
+      if (ret == LSD_OK) ret = LSD_MAP_SATURATED;
+    }
+  }
   return ret;
 }
 
@@ -1171,7 +1211,7 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&l->h_result, kResDoubles * 8, cudaHostAllocMapped);
   if (e == cudaSuccess) { memset(l->h_result, 0, kResDoubles * 8); e = cudaHostGetDevicePointer((void**)&l->d_result, l->h_result, 0); }
   if (e == cudaSuccess) e = cudaMallocHost((void**)&l->h_added, 64);
-  if (e == cudaSuccess) { *l->h_added = 0; e = cudaEventCreate(&l->ev0); }
+  if (e == cudaSuccess) { memset(l->h_added, 0, 64); e = cudaEventCreate(&l->ev0); }
   if (e == cudaSuccess) e = cudaEventCreate(&l->ev1);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->ev_main_vg, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->ev_side_vg, cudaEventDisableTiming);
@@ -1189,7 +1229,7 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   // The voxel grid of an announced scan is pipelined under the running one by default (bit-identical results,
   // tests/test_gpu_zz_pdl.py; LSD_PIPELINE_VG=0 / lsd_lio_set_pipeline turn it off).  Programmatic dependent launch stays
   // opt-in (LSD_PDL=1 / lsd_lio_set_pdl): measured on B200 in one process on one box (profiles/r02d_lio_probe.jsonl) it
-  // shortens the device time per scan but cudaLaunchKernelEx costs the host ~2.5 us more per launch than <<<>>>, and with
+  // shortens the device time per scan but cudaLaunchKernelEx costs the host ~2.5 us more per launch than a plain triple-chevron launch, and with
   // a host loop that is synchronous per evaluation that is on the critical path: 4779 scans/s with it, 5649 without.
   { const char* ev = getenv("LSD_PDL"); l->pdl = (ev && ev[0] == '1') ? 1 : 0; }
   { const char* ev = getenv("LSD_PIPELINE_VG"); l->pipeline_vg = (ev && ev[0] == '0') ? 0 : 1; }
@@ -1482,7 +1522,7 @@ lsd_status_t lsd_lio_prefetch(lsd_lio_t* l, const float* scan_host, int n) {
 lsd_status_t lsd_lio_prefetch_dev(lsd_lio_t* l, const float* scan_dev, int n) {
   if (!l || !scan_dev || n <= 0) return LSD_ERR_INVALID;
   if (n > l->p.max_scan_points) { set_error("scan of %d points exceeds max_scan_points %d", n, l->p.max_scan_points); return LSD_ERR_CAPACITY; }
-  if (!l->pipeline_vg || l->sc.world > 1) return LSD_OK;   // nothing to copy: only the pipelined voxel grid has work to do ahead
+  if (!l->pipeline_vg) return LSD_OK;   // nothing to copy: only the pipelined voxel grid has work to do ahead
   LSD_CUDA(cudaSetDevice(l->device));
   return prefetch_request(l, scan_dev, n, true);
 }

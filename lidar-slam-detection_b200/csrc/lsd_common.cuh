@@ -37,6 +37,8 @@ constexpr int kPtsPerLine = 7;
 constexpr int kMaxLevel = 127;
 constexpr int kCoordBias = 1 << 18;  // voxel coordinates in (-2^18, 2^18)
 constexpr unsigned kMaxProbe = 4096;
+// key of a retired line (LRU eviction): never 0 (probe chains run through it), never a voxel's (x + bias = 0 is outside coord_ok)
+constexpr unsigned long long kTombKey = 1ull;
 
 // Brick layout of the same points (brick.cuh): directory + one 4608-byte page per slot.  keys == nullptr: not enabled.
 struct BrickView {

@@ -329,26 +329,155 @@ static lsd_status_t launch_knn_bricks(lsd_map* m, const float4* d_q, int nq, int
                                       int* d_cnt, cudaStream_t st) {
   const BrickView& bv = m->view.bricks;
   const size_t n_work_max = std::min<size_t>((size_t)m->n_bricks, (size_t)nq) + (size_t)nq / kBrickQC + 2;
-  const size_t o_slot = 0, o_rank = o_slot + (size_t)nq * 4, o_sorted = o_rank + (size_t)nq * 4, o_work = (o_sorted + (size_t)nq * 4 + 15) & ~(size_t)15,
-               o_ctr = o_work + n_work_max * sizeof(BrickWork), total = o_ctr + 64;
+  const size_t o_slot = 0, o_rank = o_slot + (size_t)nq * 4, o_sorted = (o_rank + (size_t)nq * 4 + 31) & ~(size_t)31,
+               o_work = o_sorted + (size_t)nq * sizeof(BrickQuery), o_ctr = o_work + n_work_max * sizeof(BrickWork), total = o_ctr + 64;
   lsd_status_t s = brick_scratch(m, total);
   if (s) return s;
   char* base = static_cast<char*>(m->bscratch);
   int* q_slot = reinterpret_cast<int*>(base + o_slot);
   int* q_rank = reinterpret_cast<int*>(base + o_rank);
-  int* sorted = reinterpret_cast<int*>(base + o_sorted);
+  BrickQuery* sorted = reinterpret_cast<BrickQuery*>(base + o_sorted);
   BrickWork* work = reinterpret_cast<BrickWork*>(base + o_work);
   unsigned* ctr = reinterpret_cast<unsigned*>(base + o_ctr);
   LSD_CUDA(cudaMemsetAsync(ctr, 0, 16, st));
   const int gq = (nq + 255) / 256;
   brick_bin_kernel<<<gq, 256, 0, st>>>(bv, m->view.inv_res, d_q, nq, k, q_slot, q_rank, m->bin_count, d_idx, d_d2, d_cnt);
   brick_plan_kernel<<<(unsigned)((m->n_bricks + 255) / 256), 256, 0, st>>>(bv, m->n_bricks, m->bin_count, m->bin_base, work, ctr);
-  brick_scatter_kernel<<<gq, 256, 0, st>>>(q_slot, q_rank, m->bin_base, nq, sorted);
-  const int grid = (int)std::min<size_t>(148 * 12, (n_work_max + kBrickWarps - 1) / kBrickWarps);   // 12 CTAs x 4 warps x 4.6 KB per SM
-  if (k == 1) brick_knn_kernel<1><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
-  else brick_knn_kernel<5><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, d_q, sorted, work, ctr, d_idx, d_d2, d_cnt);
+  brick_scatter_kernel<<<gq, 256, 0, st>>>(d_q, q_slot, q_rank, m->bin_base, nq, sorted);
+  const int grid = (int)std::min<size_t>(148 * 5, (n_work_max + kBrickWarps - 1) / kBrickWarps);   // 5 CTAs x 4 warps x 2 x 4.6 KB per SM
+  if (k == 1) brick_knn_kernel<1><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, sorted, work, ctr, d_idx, d_d2, d_cnt);
+  else brick_knn_kernel<5><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, sorted, work, ctr, d_idx, d_d2, d_cnt);
   LSD_CUDA(cudaGetLastError());
   m->launches += 4;
+  return LSD_OK;
+}
+
+static lsd_status_t map_scratch(lsd_map* m, size_t bytes) {
+  if (m->scratch_bytes >= bytes) return LSD_OK;
+  if (m->scratch) LSD_CUDA(cudaFree(m->scratch));
+  m->scratch = nullptr; m->scratch_bytes = 0;
+  LSD_CUDA(cudaMalloc(&m->scratch, bytes));
+  m->scratch_bytes = bytes;
+  return LSD_OK;
+}
+
+// ------------------------------------------------------------------ LRU eviction (IVox::AddPoints, ivox3d.h:246-255)
+// One thread per evicted voxel: its level-0 line and every overflow line are retired (key = kTombKey: the probe chains that
+// run through them stay intact, no query can match them), the counters follow.  keep_from != INT_MIN is the rare case of
+// a voxel evicted and re-created inside one batch: points with id >= keep_from belong to the new voxel and are
+// re-inserted (they claim a fresh line).
+struct MapEvict { unsigned long long key; int keep_from; int pad; };
+__global__ void __launch_bounds__(128) map_evict_kernel(MapView mv, const MapEvict* __restrict__ ev, int n_ev) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_ev) return;
+  const unsigned long long key0 = ev[e].key;
+  const int keep_from = ev[e].keep_from;
+  uint4 h;
+  const CellLine* base = tag_find(mv, key0, &h);
+  if (!base) return;
+  const unsigned total = h.z;
+  const int levels = total > (unsigned)kPtsPerLine ? min((int)((total - 1) / kPtsPerLine), kMaxLevel) : 0;
+  float4 keep[8];
+  int nk = 0;
+  unsigned long long stored = 0;
+  for (int L = 0; L <= levels; L++) {
+    CellLine* ln = const_cast<CellLine*>(base);
+    if (L > 0) { uint4 hl; ln = const_cast<CellLine*>(tag_find(mv, key0 | ((unsigned long long)L << 57), &hl)); if (!ln) continue; }
+    const int n = (int)min(total - (unsigned)(L * kPtsPerLine), (unsigned)kPtsPerLine);
+    for (int j = 0; j < n; j++) {
+      const float4 p = ln->pts[j];
+      stored++;
+      if (keep_from != (int)0x80000000 && __float_as_int(p.w) >= keep_from && nk < 8) keep[nk++] = p;
+    }
+    ln->count = 0u;
+    ln->key = kTombKey;
+  }
+  atomicAdd(&mv.counters[0], ~0ull);                       // cells - 1
+  atomicAdd(&mv.counters[1], 0ull - stored);
+  __threadfence();
+  for (int j = 0; j < nk; j++) map_insert_point(mv, keep[j].x, keep[j].y, keep[j].z, __float_as_int(keep[j].w));
+}
+
+// Fresh table without the retired lines: every live line is copied to its place in the new table (whole 128-byte lines:
+// level-0 and overflow lines alike keep their keys).
+__global__ void __launch_bounds__(256) map_rehash_kernel(MapView src, unsigned long long n_src, MapView dst) {
+  const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_src) return;
+  const CellLine* ln = src.lines + s;
+  const unsigned long long key = ln->key;
+  if (key == 0ull || key == kTombKey) return;
+  bool fresh;
+  const long long d = find_or_claim(dst, key, &fresh);
+  if (d < 0) { atomicAdd(&dst.counters[2], 1ull); return; }
+  CellLine* out = dst.lines + d;
+  out->count = ln->count;
+#pragma unroll
+  for (int j = 0; j < kPtsPerLine; j++) out->pts[j] = ln->pts[j];
+}
+
+static __host__ int3 pos2grid_host(float x, float y, float z, float inv_res) {
+  return make_int3((int)roundf(x * inv_res), (int)roundf(y * inv_res), (int)roundf(z * inv_res));
+}
+
+static lsd_status_t map_rehash(lsd_map* m, cudaStream_t st) {
+  MapView nv = m->view;
+  nv.lines = nullptr; nv.tags = nullptr;
+  LSD_CUDA(cudaMalloc(&nv.lines, m->n_lines * sizeof(CellLine)));
+  LSD_CUDA(cudaMalloc(&nv.tags, m->n_lines));
+  LSD_CUDA(cudaMemsetAsync(nv.lines, 0, m->n_lines * sizeof(CellLine), st));
+  LSD_CUDA(cudaMemsetAsync(nv.tags, 0, m->n_lines, st));
+  nv.bricks.keys = nullptr;                                  // (the brick layout is not combined with the LRU)
+  map_rehash_kernel<<<(unsigned)((m->n_lines + 255) / 256), 256, 0, st>>>(m->view, m->n_lines, nv);
+  LSD_CUDA(cudaGetLastError());
+  LSD_CUDA(cudaStreamSynchronize(st));
+  cudaFree(m->view.lines); cudaFree(m->view.tags);
+  m->view.lines = nv.lines; m->view.tags = nv.tags;
+  m->launches++;
+  if (m->lru) m->lru->tombstones = 0;
+  return LSD_OK;
+}
+
+lsd_status_t map_lru_touch(lsd_map* m, const float4* pts, const int* ids, int n, int id0, cudaStream_t st) {
+  LruMirror* L = m->lru;
+  if (!L || n <= 0) return LSD_OK;
+  std::vector<MapEvict> ev;
+  std::unordered_map<unsigned long long, size_t> in_batch;   // key -> its entry in ev (evicted during this batch)
+  const float inv = m->view.inv_res;
+  for (int i = 0; i < n; i++) {
+    const float4 p = pts[i];
+    const int3 c = pos2grid_host(p.x, p.y, p.z, inv);
+    if (!coord_ok(c.x, c.y, c.z)) continue;                  // the device dropped it too
+    const unsigned long long key = pack_key(c.x, c.y, c.z, 0);
+    auto it = L->idx.find(key);
+    if (it == L->idx.end()) {
+      L->cache.push_front({key, L->distance});
+      L->idx[key] = L->cache.begin();
+      auto b = in_batch.find(key);
+      if (b != in_batch.end()) ev[b->second].keep_from = ids ? ids[i] : id0 + i;   // evicted earlier in this batch, re-created now
+    } else {
+      L->cache.splice(L->cache.begin(), L->cache, it->second);
+    }
+    if (L->idx.size() > L->capacity && (L->distance - L->cache.back().d0) > L->max_distance) {
+      const unsigned long long k = L->cache.back().key;
+      L->idx.erase(k);
+      L->cache.pop_back();
+      auto b = in_batch.find(k);
+      if (b != in_batch.end()) ev[b->second].keep_from = (int)0x80000000;     // evicted again: nothing of it survives
+      else { in_batch[k] = ev.size(); ev.push_back({k, (int)0x80000000, 0}); }
+      L->n_evicted++;
+    }
+  }
+  if (ev.empty()) return LSD_OK;
+  lsd_status_t s = map_scratch(m, ev.size() * sizeof(MapEvict));
+  if (s) return s;
+  LSD_CUDA(cudaMemcpyAsync(m->scratch, ev.data(), ev.size() * sizeof(MapEvict), cudaMemcpyHostToDevice, st));
+  map_evict_kernel<<<(unsigned)((ev.size() + 127) / 128), 128, 0, st>>>(m->view, static_cast<const MapEvict*>(m->scratch), (int)ev.size());
+  LSD_CUDA(cudaGetLastError());
+  LSD_CUDA(cudaStreamSynchronize(st));                        // `ev` lives on this stack frame
+  m->launches++;
+  L->tombstones += ev.size();
+  // retired lines keep their slots: rebuild the table before they crowd the probe chains
+  if ((L->idx.size() + L->tombstones) * 2 > m->n_lines) return map_rehash(m, st);
   return LSD_OK;
 }
 
@@ -450,6 +579,7 @@ lsd_status_t lsd_map_destroy(lsd_map_t* m) {
   cudaFree(m->view.lines); cudaFree(m->view.tags); cudaFree(m->view.counters); cudaFree(m->scratch);
   cudaFree(m->view.bricks.keys); cudaFree(m->view.bricks.totals); cudaFree(m->view.bricks.pages); cudaFree(m->view.bricks.counters);
   cudaFree(m->bin_count); cudaFree(m->bin_base); cudaFree(m->bscratch);
+  delete m->lru;
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return LSD_OK;
@@ -478,6 +608,47 @@ lsd_status_t lsd_map_clear(lsd_map_t* m) {
     LSD_CUDA(cudaMemsetAsync(m->view.bricks.counters, 0, 4 * sizeof(unsigned long long), m->stream));
   }
   LSD_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->lru) { m->lru->cache.clear(); m->lru->idx.clear(); m->lru->tombstones = 0; }
+  m->dropped_seen = 0;
+  return LSD_OK;
+}
+
+// iVox's capacity / LRU (ivox3d.h:51-52,246-255; the reference runs with capacity 100 000 voxels, max_distance 100 m,
+// laserMapping.cpp:1063-1064).  See include/lsdreg.h.
+lsd_status_t lsd_map_enable_lru(lsd_map_t* m, uint64_t capacity, double max_distance) {
+  if (!m || capacity < 1 || !(max_distance >= 0.0)) { set_error("lsd_map_enable_lru: bad arguments"); return LSD_ERR_INVALID; }
+  if (m->view.shard_world > 1 || m->view.bricks.keys) { set_error("lsd_map_enable_lru: not available on a tile-sharded map or together with the brick layout"); return LSD_ERR_INVALID; }
+  uint64_t cells = 0;
+  lsd_status_t s = lsd_map_stats(m, &cells, nullptr, nullptr);
+  if (s) return s;
+  if (cells != 0) { set_error("lsd_map_enable_lru: the map must be empty (the LRU order of points already stored is unknown)"); return LSD_ERR_INVALID; }
+  if (!m->lru) m->lru = new LruMirror();
+  m->lru->capacity = (size_t)capacity;
+  m->lru->max_distance = max_distance;
+  return LSD_OK;
+}
+lsd_status_t lsd_map_set_travel_distance(lsd_map_t* m, double distance) {
+  if (!m) return LSD_ERR_INVALID;
+  if (m->lru) m->lru->distance = distance;
+  return LSD_OK;
+}
+lsd_status_t lsd_map_evict(lsd_map_t* m, uint64_t* n_evicted_total) {
+  if (!m || !m->lru) { set_error("lsd_map_evict: lsd_map_enable_lru was not called"); return LSD_ERR_INVALID; }
+  LSD_CUDA(cudaSetDevice(m->device));
+  if (m->stream) LSD_CUDA(cudaStreamSynchronize(m->stream));   // evictions are applied inside the insert calls; this is the fence + the count
+  if (n_evicted_total) *n_evicted_total = m->lru->n_evicted;
+  return LSD_OK;
+}
+// Did the map refuse points since the last call (table full along a probe chain, > 127 overflow lines in a voxel, voxel
+// coordinates beyond +-2^18)?  A map that stopped growing degrades odometry silently; callers should treat 1 as an alarm.
+lsd_status_t lsd_map_saturated(lsd_map_t* m, int* saturated, uint64_t* n_dropped_total) {
+  if (!m || !saturated) return LSD_ERR_INVALID;
+  uint64_t d = 0;
+  lsd_status_t s = lsd_map_stats(m, nullptr, nullptr, &d);
+  if (s) return s;
+  *saturated = d > m->dropped_seen ? 1 : 0;
+  m->dropped_seen = d;
+  if (n_dropped_total) *n_dropped_total = d;
   return LSD_OK;
 }
 
@@ -528,19 +699,16 @@ lsd_status_t lsd_map_brick_stats(lsd_map_t* m, uint64_t* n_pages, uint64_t* n_re
   return LSD_OK;
 }
 
-static lsd_status_t map_scratch(lsd_map* m, size_t bytes) {
-  if (m->scratch_bytes >= bytes) return LSD_OK;
-  if (m->scratch) LSD_CUDA(cudaFree(m->scratch));
-  m->scratch = nullptr; m->scratch_bytes = 0;
-  LSD_CUDA(cudaMalloc(&m->scratch, bytes));
-  m->scratch_bytes = bytes;
-  return LSD_OK;
-}
 
 lsd_status_t lsd_map_insert_dev(lsd_map_t* m, const float* xyzi_dev, int n, int32_t id0) {
   if (!m || (n > 0 && !xyzi_dev) || n < 0) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(m->device));
-  return launch_insert(m, reinterpret_cast<const float4*>(xyzi_dev), n, id0, m->stream);
+  lsd_status_t s = launch_insert(m, reinterpret_cast<const float4*>(xyzi_dev), n, id0, m->stream);
+  if (s || !m->lru || n == 0) return s;
+  std::vector<float4> h((size_t)n);                            // the LRU order is replayed on the host (map.h::LruMirror)
+  LSD_CUDA(cudaMemcpyAsync(h.data(), xyzi_dev, (size_t)n * 16, cudaMemcpyDeviceToHost, m->stream));
+  LSD_CUDA(cudaStreamSynchronize(m->stream));
+  return map_lru_touch(m, h.data(), nullptr, n, id0, m->stream);
 }
 
 lsd_status_t lsd_map_insert(lsd_map_t* m, const float* xyzi_host, int n, int32_t id0) {
@@ -555,6 +723,7 @@ lsd_status_t lsd_map_insert(lsd_map_t* m, const float* xyzi_host, int n, int32_t
     s = launch_insert(m, reinterpret_cast<const float4*>(m->scratch), c, id0 + o, m->stream);
     if (s) return s;
     LSD_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->lru) { s = map_lru_touch(m, reinterpret_cast<const float4*>(xyzi_host) + o, nullptr, c, id0 + o, m->stream); if (s) return s; }
   }
   return LSD_OK;
 }
