@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblsdreg.so")
 
 OK, NO_EFFECTIVE_POINTS, SCAN_TOO_SMALL, MAP_SEEDED = 0, 1, 2, 3
+MAP_SATURATED = 6
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_GRID_OVERFLOW, ERR_IO = -1, -2, -3, -4, -5, -6
 STENCIL_CENTER, STENCIL_NEARBY6, STENCIL_NEARBY18, STENCIL_NEARBY26, STENCIL_NEARBY74, STENCIL_EXACT = 0, 6, 18, 26, 74, 1000
 
@@ -83,6 +84,10 @@ SIGNATURES = [
     ("lsd_knn_query", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_knn_query_dev", _i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     ("lsd_knn_set_shape", _i, [_vp, _i]),
+    ("lsd_map_enable_lru", _i, [_vp, C.c_uint64, _d]),
+    ("lsd_map_set_travel_distance", _i, [_vp, _d]),
+    ("lsd_map_evict", _i, [_vp, _vp]),
+    ("lsd_map_saturated", _i, [_vp, _pi, _vp]),
     ("lsd_map_enable_bricks", _i, [_vp, _i]),
     ("lsd_map_brick_stats", _i, [_vp, _vp, _vp, _vp]),
     ("lsd_voxelgrid_create", _i, [_pp, _i, _i]),
@@ -293,6 +298,23 @@ class HashVoxelMap:
         return idx, d2, cnt
 
     KNN_AUTO, KNN_WARP, KNN_THREAD, KNN_FLAT = 0, 1, 2, 3
+
+    def enable_lru(self, capacity: int = 100000, max_distance: float = 100.0):
+        """iVox's capacity + LRU eviction (include/lsdreg.h::lsd_map_enable_lru; laserMapping.cpp:1063-1064 runs 100 000 / 100 m)."""
+        check(lib.lsd_map_enable_lru(self.h, int(capacity), float(max_distance)))
+
+    def set_travel_distance(self, d: float):
+        check(lib.lsd_map_set_travel_distance(self.h, float(d)))
+
+    def evict(self) -> int:
+        n = C.c_uint64()
+        check(lib.lsd_map_evict(self.h, C.byref(n)))
+        return n.value
+
+    def saturated(self):
+        f, n = C.c_int(), C.c_uint64()
+        check(lib.lsd_map_saturated(self.h, C.byref(f), C.byref(n)))
+        return bool(f.value), n.value
 
     def enable_bricks(self, log2_bricks: int = 16):
         """Also keep every point brick by brick (include/lsdreg.h::lsd_map_enable_bricks): batched k-NN shape 3 (TMA-staged pages)."""

@@ -298,9 +298,10 @@ class RefIvox:
             ref.ref_ivox_destroy(self.h)
             self.h = None
 
-    def add(self, xyz: np.ndarray, id0: int):
+    def add(self, xyz: np.ndarray, id0: int, distance: float = 0.0):
+        """IVox::AddPoints(points, distance): `distance` = travel_distance, what the LRU ages voxels by (ivox3d.h:251)."""
         xyz = _c32(xyz[:, :3])
-        ref.ref_ivox_add(self.h, xyz, xyz.shape[0], id0, 0.0)
+        ref.ref_ivox_add(self.h, xyz, xyz.shape[0], id0, float(distance))
 
     def set_nearby(self, nearby: int):
         ref.ref_ivox_set_nearby(self.h, nearby)
