@@ -573,7 +573,8 @@ def main():
         for i in infos_a + infos_b:
             assert i["pos_err"] < 0.1, f"LIO did not converge: {i}"
         streams = 1 if sharded else world
-        return dict(lio=lio, st=st, build_s=build_s, steps_a=steps_a, steps_b=steps_b, dev_scans=dev_scans, host_scans=host_scans,
+        xchg = lio.shard_exchange_stats() if sharded else None
+        return dict(xchg=xchg, lio=lio, st=st, build_s=build_s, steps_a=steps_a, steps_b=steps_b, dev_scans=dev_scans, host_scans=host_scans,
                     infos_a=infos_a, infos_b=infos_b, poses_a=poses_a, clocks=clocks, wall_a=wall_a, wall_b=wall_b, dev_s=dev_s,
                     value=streams * K / wall_a, e2e=streams * K / wall_b, base=base)
 
@@ -680,6 +681,7 @@ def main():
                 "value": X["value"], "e2e": X["e2e"], "unit": "scans/s", "ms_per_step": 1e3 * X["wall_a"] / K, "e2e_ms_per_step": 1e3 * X["wall_b"] / K,
                 "device_ms_per_step": 1e3 * X["dev_s"] / K, "pos_err_max_m": float(np.max([i["pos_err"] for i in X["infos_a"]])),
                 "map_points_this_rank": int(X["st"]["points"]), "gpu_launches": int(np.sum([i["kernel_launches"] for i in X["infos_a"]])),
+                "in_kernel_exchange": X.get("xchg") and dict(X["xchg"], what="mean us per h-model evaluation between this rank's partial sums being ready and every peer's having arrived (clock64 in grid_finalize, rank 0)"),
                 "parallelism": (f"map tile-sharded over {world} GPUs, ONE scan stream, peer-memory all-reduce of the normal equations inside the reduction kernel"
                                 if sharded else f"{world} replicas, independent scan streams, no collective")}
 

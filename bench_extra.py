@@ -76,6 +76,7 @@ def ndt(args):
                scan_points=int(scan.shape[0]), target_build_ms=build_ms, set_source_ms=src_ms, align_ms=align_ms,
                iterations=g.iterations, converged=bool(g.converged), cost_eval_us=cost_ms * 1e3,
                pos_err_m=float(np.abs(Tg[:3, 3] - tgt).max()), map_gen_s=gen_s,
+               last_steps_m_deg=[[float("%.3g" % v) for v in row[:2]] for row in g.iteration_log()[-6:]],   # what is_converged saw (eps 0.01 m / 0.1 deg)
                alg_bytes_per_eval=float(scan.shape[0] * (16 + 7 * 16 + 3 * 52)),
                cost_gbs=float(scan.shape[0] * (16 + 7 * 16 + 3 * 52) / (cost_ms * 1e-3) / 1e9))
     if not args.no_ref_cuda and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_cuda.so")):

@@ -231,6 +231,10 @@ lsd_status_t lsd_lio_set_next_id(lsd_lio_t* l, int32_t id); /* flg_EKF_inited, l
 #define LSD_SHARD_BLOB_BYTES 192
 lsd_status_t lsd_lio_shard_export(lsd_lio_t* l, int rank, int world, int tile_cells, int reach_cells, unsigned char* blob_out);
 lsd_status_t lsd_lio_shard_connect(lsd_lio_t* l, const unsigned char* blobs);
+/* Tile-sharded handles: mean time (us) one h-model evaluation spent in the in-kernel exchange — the peer-memory stores plus
+ * waiting for the slowest peer's partial sums (clock64 around it, nominal SM clock) — over the evaluations since the
+ * last call. */
+lsd_status_t lsd_lio_shard_exchange_stats(lsd_lio_t* l, double* mean_us, long long* evaluations);
 /* Wait for everything queued on the handle; returns device time / insert count of the last scan. */
 lsd_status_t lsd_lio_sync(lsd_lio_t* l, double* gpu_ms_last, int* n_added_last);
 lsd_status_t lsd_lio_set_profile(lsd_lio_t* l, int on);
@@ -336,6 +340,11 @@ lsd_status_t lsd_reg_set_source_dev(lsd_reg_t* r, const float* pts_dev, int n);
 lsd_status_t lsd_reg_set_max_correspondence_distance(lsd_reg_t* r, double d);
 /* align(): guess/out are float32[16] like Eigen::Matrix4f; *converged = hasConverged(). */
 lsd_status_t lsd_reg_align(lsd_reg_t* r, const float* guess16, float* out16, int* converged, int* iterations);
+/* Diagnostics of the last lsd_reg_align (no reference counterpart beyond lm_debug_print_, lsq_registration_impl.hpp:176-183):
+ * per outer LM iteration 4 doubles = (|translation|_inf of the accepted step [m], its rotation angle [deg] — the two numbers
+ * is_converged compares with transformation_epsilon / rotation_epsilon, :112-121 — the cost at the linearisation, lambda).
+ * out may be NULL to learn *n_iters. */
+lsd_status_t lsd_reg_iteration_log(lsd_reg_t* r, double* out4_per_iter, int cap_iters, int* n_iters);
 lsd_status_t lsd_reg_get_final(lsd_reg_t* r, double* T16, double* H36);           /* double pose, getFinalHessian */
 /* getFitnessScore(max_range) at T16 (NULL = the final transformation).  NB PCL compares the SQUARED
  * nearest-neighbour distance with max_range. */

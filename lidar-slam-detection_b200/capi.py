@@ -103,6 +103,7 @@ SIGNATURES = [
     ("lsd_lio_set_stale_rows", _i, [_vp, _i]),
     ("lsd_lio_set_knn_shape", _i, [_vp, _i]),
     ("lsd_lio_set_pdl", _i, [_vp, _i]),
+    ("lsd_lio_shard_exchange_stats", _i, [_vp, C.POINTER(_d), C.POINTER(C.c_longlong)]),
     ("lsd_lio_set_pipeline", _i, [_vp, _i]),
     ("lsd_lio_pipeline_stats", _i, [_vp, _vp, _vp]),
     ("lsd_lio_prefetch_dev", _i, [_vp, _vp, _i]),
@@ -136,6 +137,7 @@ SIGNATURES = [
     ("lsd_reg_cost", _i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_d), _pi]),
     ("lsd_reg_get_correspondences", _i, [_vp, _vp, _i, _pi]),
     ("lsd_reg_stats", _i, [_vp, _pi, C.POINTER(C.c_longlong)]),
+    ("lsd_reg_iteration_log", _i, [_vp, _vp, _i, _pi]),
     ("lsd_reg_shard_export", _i, [_vp, _i, _i, _i, _vp]),
     ("lsd_reg_shard_connect", _i, [_vp, _vp]),
     ("lsd_vfe_default_params", None, [C.POINTER(VfeParams)]),
@@ -463,6 +465,14 @@ class Matcher:
         self.h = None
 
     __del__ = close
+
+    def iteration_log(self) -> np.ndarray:
+        """[n_iter, 4] = (|t|_inf of the step, its rotation in degrees, cost at the linearisation, lambda) of the last align()."""
+        n = C.c_int()
+        check(lib.lsd_reg_iteration_log(self.h, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 4))
+        check(lib.lsd_reg_iteration_log(self.h, _ptr(out), n.value, C.byref(n)))
+        return out[:n.value]
 
     def shard_export(self, rank: int, world: int, tile_cells: int = 32) -> np.ndarray:
         """Tile-sharded NDT target (include/lsdreg.h "Tile-sharded matcher"): this rank's blob for the all-gather."""
@@ -916,6 +926,11 @@ class LioFrontend:
     def shard_connect(self, blobs: np.ndarray):
         blobs = np.ascontiguousarray(blobs, np.uint8)
         check(lib.lsd_lio_shard_connect(self.h, _ptr(blobs)))
+
+    def shard_exchange_stats(self):
+        us, n = C.c_double(), C.c_longlong()
+        check(lib.lsd_lio_shard_exchange_stats(self.h, C.byref(us), C.byref(n)))
+        return dict(mean_us=us.value, evaluations=n.value)
 
     def sync(self):
         """Drain the handle's stream -> (gpu_ms, n_added) of the last scan."""

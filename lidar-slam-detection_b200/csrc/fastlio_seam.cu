@@ -96,6 +96,11 @@ static lsd_status_t ensure_engines(lsd_fastlio* f) {
   lp.max_scan_points = f->max_scan_points;
   s = lsd_lio_create(&f->lio, &lp);
   if (s) return s;
+  // ivox_options.capacity_ = 100000, max_distance_ = 100.0 (laserMapping.cpp:1063-1064): the map forgets what the
+  // reference forgets, and a long drive cannot fill the table (2^22 lines for <= ~100 k live voxels; retired lines are
+  // rehashed away)
+  s = lsd_map_enable_lru(lsd_lio_map(f->lio), 100000, 100.0);
+  if (s) return s;
   return lsd_lio_set_stale_rows(f->lio, 1);        // Nearest_Points outlives the scan (laserMapping.cpp:1273, ivox3d.h:155-157)
 }
 

@@ -166,7 +166,7 @@ __device__ __forceinline__ bool esti_plane_dev(const float (&px)[5], const float
 // ---------------------------------------------------------------- grid reduction
 // Result buffer layout (doubles): [0..20] upper triangle of the 6x6 h_x^T h_x, [21..26] h_x^T h,
 // [27] sum |res|, [28] n_eff, [29] feats_down_size, [48..53] degeneracy sums.
-constexpr int kResDegen = 48, kResSeq = 62, kResSeqDegen = 63, kResDoubles = 64;
+constexpr int kResDegen = 48, kResWaitCycles = 56, kResSeq = 62, kResSeqDegen = 63, kResDoubles = 64;
 
 // symmetric 3x3 eigen-decomposition (cyclic Jacobi); V columns = eigenvectors.  Stands in for
 // Eigen::SelfAdjointEigenSolver at laserMapping.cpp:941; only |v . n| and V diag(mask) V^T are used,
@@ -235,6 +235,7 @@ __device__ __forceinline__ void grid_finalize(double* __restrict__ partials, uns
     // into every rank's inbox over NVLink, publishes a sequence number, waits for the other ranks'
     // and folds the world's contributions in rank order (deterministic).  No NCCL call, no extra launch.
     const long long iseq = (long long)seq;
+    const long long t_x0 = clock64();   // exchange time (stores + peers' arrival), published in result[kResWaitCycles]
     const size_t base = (size_t)inbox_region * kInboxRegion + (size_t)((iseq & 1) * kMaxRanks) * kInboxSlot;
     if (threadIdx.x < NV) {
       const double v = sm_fin[0][threadIdx.x];
@@ -256,6 +257,7 @@ __device__ __forceinline__ void grid_finalize(double* __restrict__ partials, uns
       for (int r = 0; r < sc.world; r++) t += *(volatile double*)(sc.inbox[sc.rank] + base + (size_t)r * kInboxSlot + threadIdx.x);
       sm_fin[0][threadIdx.x] = t;
     }
+    if (threadIdx.x == 0 && inbox_region == 0) result[kResWaitCycles] = (double)(clock64() - t_x0);
     __syncthreads();
   }
   if (threadIdx.x < NV) {
@@ -774,6 +776,7 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   if (l->issue_in_linearize) { lsd_status_t d = issue_deferred_prefetch(l); if (d) return d; }   // hidden under this evaluation
   { lsd_status_t w = wait_seq(l, kResSeq, seq); if (w) return w; }
   const double* r = l->h_result;
+  if (l->sc.world > 1) { l->xchg_cycles += r[kResWaitCycles]; l->xchg_count++; }
   int q = 0;
   for (int a = 0; a < 6; a++) for (int c = a; c < 6; c++) { HTH6[6 * a + c] = HTH6[6 * c + a] = r[q]; q++; }
   for (int a = 0; a < 6; a++) HTh6[a] = r[21 + a];
@@ -1395,6 +1398,17 @@ lsd_status_t lsd_lio_shard_connect(lsd_lio_t* l, const unsigned char* blobs) {
   return LSD_OK;
 }
 
+// Tile-sharded handles: mean time one h-model evaluation spent in the in-kernel exchange (peer stores + waiting for the
+// slowest peer's partial sums), in microseconds, and the number of evaluations averaged; resets the counters.
+lsd_status_t lsd_lio_shard_exchange_stats(lsd_lio_t* l, double* mean_us, long long* evaluations) {
+  if (!l || !mean_us) return LSD_ERR_INVALID;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, l->device);
+  *mean_us = (l->xchg_count && khz > 0) ? l->xchg_cycles / (double)l->xchg_count / ((double)khz * 1e-3) : 0.0;
+  if (evaluations) *evaluations = l->xchg_count;
+  l->xchg_cycles = 0.0; l->xchg_count = 0;
+  return LSD_OK;
+}
 lsd_status_t lsd_lio_sync(lsd_lio_t* l, double* gpu_ms_last, int* n_added_last) {
   if (!l) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(l->device));

@@ -55,6 +55,7 @@ struct lsd_lio {
   float4* d_near = nullptr;     // Nearest_Points: [n,5] (x, y, z, id)
   int* d_near_cnt = nullptr;
   int knn_shape = 0;            // lsd_lio_set_knn_shape: 0/1 warp per scan point (lio_knn_kernel)
+  double xchg_cycles = 0.0; long long xchg_count = 0;   // tile-sharded: SM cycles spent in the in-kernel exchange (lsd_lio_shard_exchange_stats)
   double travel = 0.0, last_pos_lid[3] = {0, 0, 0};   // travel_distance / last_pos_lid (laserMapping.cpp:96,145,1289-1291)
   int rc_ctas = 8, rc_threads = 256;   // its cluster shape (LSD_REUSE_CLUSTER=CxT)
   int reuse_cluster = 0;        // reuse evaluations as ONE thread-block cluster with a DSMEM reduction (lio_hmodel_reuse_cluster_kernel)

@@ -720,6 +720,7 @@ struct lsd_reg {
   long long seq = 0;
   lsd::ShardComm sc;
   int shard_tile = 32;              // lsd_reg_shard_export: x-y tile edge in NDT voxels
+  std::vector<double> iter_log;     // 4 doubles per outer LM iteration of the last align (lsd_reg_iteration_log)
   float4* d_stage = nullptr; size_t stage_cap = 0;   // staging of host clouds (lsd_reg_set_target / _source)
   int pending_world = 0;            // world announced by lsd_reg_shard_export, active after lsd_reg_shard_connect
   double* d_inbox = nullptr;        // this rank's inbox of the in-kernel all-reduce (grid_finalize)
@@ -915,6 +916,7 @@ static lsd_status_t reg_align(lsd_reg* r, const double* guess) {
   r->iterations = 0;
   const auto clock0 = std::chrono::steady_clock::now();
   const double timeout_ms = (double)(r->p.max_process_time_us / 1000);
+  r->iter_log.clear();
   for (int it = 0; it < r->p.max_iterations && !r->converged; it++) {
     r->iterations = it;
     double H[36], b[6], y0, delta[16];
@@ -946,6 +948,10 @@ static lsd_status_t reg_align(lsd_reg* r, const double* guess) {
     }
     if (!stepped) break;  // "lm not converged!!"
     r->converged = is_converged(r, delta, 1.0) ? 1 : 0;
+    {  // what is_converged looked at (lsd_reg_iteration_log): |t|_inf of the step, its rotation angle, the cost it started from
+      double tm = 0; for (int k = 0; k < 3; k++) tm = std::max(tm, fabs(delta[4 * k + 3]));
+      r->iter_log.push_back(tm); r->iter_log.push_back(rot_angle(delta) / M_PI * 180.0); r->iter_log.push_back(y0); r->iter_log.push_back(lambda);
+    }
     if (timeout_ms > 0) {
       const double el = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - clock0).count();
       if (el > timeout_ms && is_converged(r, delta, 10.0)) { r->converged = 1; break; }
@@ -1286,6 +1292,13 @@ lsd_status_t lsd_reg_align(lsd_reg_t* r, const float* guess16, float* out16, int
   return LSD_OK;
 }
 
+lsd_status_t lsd_reg_iteration_log(lsd_reg_t* r, double* out4_per_iter, int cap_iters, int* n_iters) {
+  if (!r || !n_iters) return LSD_ERR_INVALID;
+  const int n = (int)(r->iter_log.size() / 4);
+  *n_iters = n;
+  if (out4_per_iter) memcpy(out4_per_iter, r->iter_log.data(), (size_t)std::min(n, std::max(cap_iters, 0)) * 4 * sizeof(double));
+  return LSD_OK;
+}
 lsd_status_t lsd_reg_get_final(lsd_reg_t* r, double* T16, double* H36) {
   if (!r) return LSD_ERR_INVALID;
   if (T16) memcpy(T16, r->final_T, sizeof(r->final_T));

@@ -123,6 +123,9 @@ def _load_ref_reg():
     L.ref_reg_align.argtypes = [C.c_void_p, _f, _f]
     L.ref_reg_fitness.restype = C.c_double
     L.ref_reg_fitness.argtypes = [C.c_void_p, C.c_double]
+    if hasattr(L, "ref_calc_fitness_score"):
+        L.ref_calc_fitness_score.restype = C.c_double
+        L.ref_calc_fitness_score.argtypes = [_f, C.c_int, C.c_int, _f, C.c_int, C.c_int, _d, C.c_double]
     L.ref_reg_linearize.restype = C.c_double
     L.ref_reg_linearize.argtypes = [C.c_void_p, _d, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ref_reg_compute_error.restype = C.c_double

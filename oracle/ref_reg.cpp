@@ -21,6 +21,8 @@
 
 #include <cstring>
 
+#include <hdl_graph_slam/information_matrix_calculator.hpp>   // compiled from the reference's .cpp (oracle/Makefile)
+
 using P = pcl::PointXYZI;
 using Cloud = pcl::PointCloud<P>;
 
@@ -164,3 +166,18 @@ void ref_se3_exp(const double* a6, double* T16) {
 }
 
 }  // extern "C"
+
+
+// InformationMatrixCalculator::calc_fitness_score (slam/backend/hdl_graph_slam/src/hdl_graph_slam/
+// information_matrix_calculator.cpp:71-102), compiled unmodified: the in-tree twin of pcl::Registration::getFitnessScore
+// (mean squared nearest-neighbour distance of the transformed source in the target, nn_dists[0] <= max_range compared
+// UNSQUARED).  cloud1 = target, cloud2 = source, relpose maps source into target.
+extern "C" double ref_calc_fitness_score(const float* tgt, int n_t, int t_stride, const float* src, int n_s, int s_stride, const double* T16, double max_range) {
+  Cloud::Ptr c1(new Cloud), c2(new Cloud);
+  c1->points.resize(n_t); c2->points.resize(n_s);
+  for (int i = 0; i < n_t; i++) { P& p = c1->points[i]; p.x = tgt[(size_t)t_stride * i]; p.y = tgt[(size_t)t_stride * i + 1]; p.z = tgt[(size_t)t_stride * i + 2]; p.w = 1.f; }
+  for (int i = 0; i < n_s; i++) { P& p = c2->points[i]; p.x = src[(size_t)s_stride * i]; p.y = src[(size_t)s_stride * i + 1]; p.z = src[(size_t)s_stride * i + 2]; p.w = 1.f; }
+  Eigen::Isometry3d rel = Eigen::Isometry3d::Identity();
+  for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) rel.linear()(a, b) = T16[4 * a + b]; rel.translation()(a) = T16[4 * a + 3]; }
+  return hdl_graph_slam::InformationMatrixCalculator::calc_fitness_score(c1, c2, rel, max_range);
+}

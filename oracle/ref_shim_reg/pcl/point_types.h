@@ -3,6 +3,7 @@
 // 16-byte-aligned point with getVector4fMap() whose 4th component is 1 (PCL's data[3]).
 #pragma once
 #include <Eigen/Core>
+#include <Eigen/Geometry>   // PCL's point_types.h brings Eigen::Isometry3d etc. with it (information_matrix_calculator.hpp relies on that)
 #include <memory>
 #define PCL_VERSION_CALC(a, b, c) ((a) * 100000 + (b) * 100 + (c))
 #define PCL_VERSION PCL_VERSION_CALC(1, 10, 0)  /* selects the pcl::shared_ptr typedef branch */

@@ -24,6 +24,8 @@ template <typename PointT>
 class KdTree : public Search<PointT> {
  public:
   typedef typename Search<PointT>::PointCloudConstPtr PointCloudConstPtr;
+  typedef std::shared_ptr<KdTree<PointT>> Ptr;
+  typedef std::shared_ptr<const KdTree<PointT>> ConstPtr;
   void setInputCloud(const PointCloudConstPtr& cloud) override {
     this->cloud_ = cloud;
     const int n = (int)cloud->size();

@@ -256,6 +256,14 @@ class RefMatcher:
         return c
 
 
+def ref_calc_fitness_score(tgt, src, T, max_range):
+    """InformationMatrixCalculator::calc_fitness_score (information_matrix_calculator.cpp:71-102) COMPILED from the reference:
+    the in-tree twin of pcl::Registration::getFitnessScore."""
+    tgt = np.ascontiguousarray(tgt, np.float32); src = np.ascontiguousarray(src, np.float32)
+    return O.ref_reg.ref_calc_fitness_score(tgt, tgt.shape[0], tgt.shape[1], src, src.shape[0], src.shape[1],
+                                            np.ascontiguousarray(T, np.float64), float(max_range))
+
+
 def ref_se3_exp(a):
     T = np.zeros(16)
     O.ref_reg.ref_se3_exp(np.ascontiguousarray(a, np.float64), T)

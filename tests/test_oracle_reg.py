@@ -127,3 +127,21 @@ def test_lm_loop_matches_reference(scene, kind):
     assert np.abs(Tr[:3, 3] - scene["Tgt"][:3, 3]).max() < 0.1
     if kind == "gicp":
         np.testing.assert_allclose(o.fitness(Tr, 25.0), r.fitness(25.0), rtol=1e-4)
+
+
+def test_fitness_score_matches_the_compiled_calc_fitness_score(scene):
+    """Row a16: getFitnessScore itself is PCL's (external), but its in-tree twin — InformationMatrixCalculator::
+    calc_fitness_score, the function that weighs every loop edge (information_matrix_calculator.cpp:71-102) — compiles
+    unmodified against the k-d tree shim.  The restated score (what the GPU path is held to) must equal it: same float
+    transform of the source, same exact nearest neighbour, same `d2 <= max_range` test on the UNSQUARED range, same mean."""
+    from oracle.reg import OracleMatcher, ref_calc_fitness_score
+    o = OracleMatcher("gicp")
+    o.set_target(scene["tgt"]); o.set_source(scene["src"])
+    for T in (scene["Tgt"], scene["guess"]):
+        for max_range in (25.0, 1.5, 0.05):
+            want = ref_calc_fitness_score(scene["tgt"], scene["src"], T, max_range)
+            got = o.fitness(T, max_range)
+            assert 0 < want < 1e300
+            np.testing.assert_allclose(got, want, rtol=1e-12)
+    far = np.eye(4); far[:3, 3] = [500.0, 0, 0]
+    assert ref_calc_fitness_score(scene["tgt"], scene["src"], far, 1.5) > 1e300 and o.fitness(far, 1.5) > 1e300      # nothing within range: DBL_MAX
