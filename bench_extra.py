@@ -281,17 +281,23 @@ def vfe(args):
         p = np.zeros((s.shape[0], 5), np.float32); p[:, :4] = s; p[:, 2] -= 1.8
         frames.append(p)
     M = np.eye(4, dtype=np.float32); M[:3, 3] = [0.8, 0.1, 0.0]
-    g = lsdreg.Voxelizer(max_frame_num=4)
-    for f in range(4):
-        g.accumulate(frames[f], M)
-    acc, vox = [], []
-    for f in range(4, 8):
-        a, tot = t_ms(lambda: g.accumulate(frames[f], M))
-        v, r = t_ms(lambda: g.voxelize(True))
-        acc.append(a); vox.append(v)
-    V = r[0].shape[0]
+    res = {}
+    for mode in (1, 0):   # 1 = voxel ids in atomic order (the reference kernels' contract, 2 kernels); 0 = deterministic ids (3 kernels)
+        g = lsdreg.Voxelizer(max_frame_num=4, unordered_ids=mode)
+        for f in range(4):
+            g.accumulate(frames[f], M)
+        acc, vox = [], []
+        for f in range(4, 8):
+            a, tot = t_ms(lambda: g.accumulate(frames[f], M))
+            v, r = t_ms(lambda: g.voxelize(True))
+            acc.append(a); vox.append(v)
+        res[mode] = (float(np.mean(acc)) * 1e3, float(np.mean(vox)) * 1e3, r[0].shape[0], tot)
+        g.close()
+    acc, vox = [res[1][0] / 1e3], [res[1][1] / 1e3]
+    V, tot = res[1][2], res[1][3]
     out = dict(config="VFE voxelizer 4 x 50k pts", window_points=int(tot), voxels=int(V), accumulate_us=float(np.mean(acc)) * 1e3,
-               voxelize_us=float(np.mean(vox)) * 1e3,
+               voxelize_us=float(np.mean(vox)) * 1e3, ids="atomic order (the reference's contract)",
+               deterministic_ids=dict(accumulate_us=res[0][0], voxelize_us=res[0][1]),
                alg_bytes=float(20 * tot + 16 * tot + V * 26), gbs=float((20 * tot + 16 * tot + V * 26) / (np.mean(vox) * 1e-3) / 1e9))
     if not args.no_cpu:
         o = OracleVoxelizer(max_frames=4)

@@ -373,6 +373,9 @@ typedef struct lsd_vfe_params {
   int max_points;                                    /* 500000 */
   int num_feature;                                   /* 5: x, y, z, intensity, time */
   int max_frame_num;                                 /* POINT_FRAME_NUM 2 (README's best model: 4) */
+  int unordered_ids;        /* 0 (default): voxel ids in the order of each voxel's first point (deterministic: one extra scan
+                               kernel); 1: ids in atomic order like the reference's voxelization_kernel (same voxel SET and rows,
+                               any numbering): two kernels instead of three */
 } lsd_vfe_params_t;
 void lsd_vfe_default_params(lsd_vfe_params_t* p);
 lsd_status_t lsd_vfe_create(lsd_vfe_t** out, const lsd_vfe_params_t* p);

@@ -61,7 +61,7 @@ class ImuParams(C.Structure):
 class VfeParams(C.Structure):
     _fields_ = [("min_range", C.c_float * 3), ("max_range", C.c_float * 3), ("voxel_size", C.c_float * 3),
                 ("max_points_per_voxel", C.c_int), ("max_voxels", C.c_int), ("max_points", C.c_int), ("num_feature", C.c_int),
-                ("max_frame_num", C.c_int)]
+                ("max_frame_num", C.c_int), ("unordered_ids", C.c_int)]
 
 # every symbol include/lsdreg.h declares: (name, restype, argtypes)
 _vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double

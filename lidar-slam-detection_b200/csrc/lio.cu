@@ -260,17 +260,15 @@ __device__ __forceinline__ void grid_finalize(double* __restrict__ partials, uns
     if (threadIdx.x == 0 && inbox_region == 0) result[kResWaitCycles] = (double)(clock64() - t_x0);
     __syncthreads();
   }
-  if (threadIdx.x < NV) {
-    result[res_off + threadIdx.x] = sm_fin[0][threadIdx.x];
-    __threadfence_system();
-  }
+  // One system-scope fence round: every writer fences its own stores, the barrier makes them happen-before thread 0's
+  // sequence-number store (fence cumulativity), so the host that sees `seq` sees the sums.  (A second fence in thread 0 cost
+  // another PCIe round trip per evaluation.)
+  if (threadIdx.x < NV) result[res_off + threadIdx.x] = sm_fin[0][threadIdx.x];
+  if (threadIdx.x == NV && n_extra_slot >= 0) result[n_extra_slot] = extra;
+  if (threadIdx.x == NV + 1) *done = 0u;
+  if (threadIdx.x <= NV + 1) __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (n_extra_slot >= 0) result[n_extra_slot] = extra;
-    *done = 0u;
-    __threadfence_system();
-    result[seq_slot] = seq;  // published last
-  }
+  if (threadIdx.x == 0) result[seq_slot] = seq;  // published last
 }
 
 // thread-per-item kernels: warp-shuffle reduce vals[NV] into partials[block]

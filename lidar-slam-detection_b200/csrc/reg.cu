@@ -742,14 +742,24 @@ static void T_to_pose(const double* T, Pose34d* d, Pose34f* f) {
   }
 }
 
+// Spin on the sequence number the cost kernel publishes into mapped host memory (acquire: the sums stored before it must
+// not be read ahead of it on hosts that reorder loads; bounded, so a hung kernel becomes an error).
 static lsd_status_t reg_wait(lsd_reg* r, double seq) {
-  volatile double* h = r->h_result;
+  const unsigned long long* h = reinterpret_cast<const unsigned long long*>(r->h_result + kResSeq);
+  unsigned long long want;
+  memcpy(&want, &seq, 8);
+  const auto t0 = std::chrono::steady_clock::now();
   for (unsigned long long spins = 0;; spins++) {
-    if (h[kResSeq] == seq) return LSD_OK;
+    if (__atomic_load_n(h, __ATOMIC_ACQUIRE) == want) return LSD_OK;
     if ((spins & 0xfff) == 0xfff) {
       cudaError_t e = cudaStreamQuery(r->stream);
       if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "kernel while waiting for the reduction", __FILE__, __LINE__);
-      if (e == cudaSuccess && h[kResSeq] != seq) { if (h[kResSeq] == seq) return LSD_OK; set_error("reduction result never published"); return LSD_ERR_CUDA; }
+      if (e == cudaSuccess) {
+        if (__atomic_load_n(h, __ATOMIC_ACQUIRE) == want) return LSD_OK;
+        set_error("reduction result never published");
+        return LSD_ERR_CUDA;
+      }
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) { set_error("timed out waiting for a cost evaluation (kernel hung?)"); return LSD_ERR_CUDA; }
     }
   }
 }
@@ -924,7 +934,7 @@ static lsd_status_t reg_align(lsd_reg* r, const double* guess) {
     if (s < 0) return s;
     if (lambda < 0.0) { double m = 0; for (int i = 0; i < 6; i++) m = std::max(m, fabs(H[7 * i])); lambda = r->p.lm_init_lambda_factor * m; }
     double nu = 2.0;
-    bool stepped = false;
+    bool stepped = false, stationary = false;
     for (int i = 0; i < r->p.lm_max_iterations; i++) {
       double d[6], xi[16], yi;
       if (!solve6(H, lambda, b, d)) break;
@@ -936,7 +946,7 @@ static lsd_status_t reg_align(lsd_reg* r, const double* guess) {
       for (int k = 0; k < 6; k++) den += d[k] * (lambda * d[k] - b[k]);
       const double rho = (y0 - yi) / den;
       if (rho < 0) {
-        if (is_converged(r, delta, 10.0)) { stepped = true; break; }
+        if (is_converged(r, delta, 10.0)) { stepped = true; stationary = (i == 0); break; }
         lambda = nu * lambda; nu = 2 * nu;
         continue;
       }
@@ -956,6 +966,18 @@ static lsd_status_t reg_align(lsd_reg* r, const double* guess) {
       const double el = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - clock0).count();
       if (el > timeout_ms && is_converged(r, delta, 10.0)) { r->converged = 1; break; }
       else if (el > 1.5 * timeout_ms) break;
+    }
+    if (stationary && !r->converged) {
+      // A stationary point of the reference's loop: the FIRST LM trial was rejected (rho < 0) yet small enough for
+      // is_converged_low, so step_lm returned with x0 and lambda untouched (lsq_registration_impl.hpp:190-193) — and
+      // the step is not small enough for is_converged.  The next iteration linearises at the same x0 with the same lambda:
+      // with deterministic sums it is this iteration again, and again, to the iteration cap (measured on config 3: 60 of
+      // 64 iterations, the same 1.05 cm / 0.001 deg step each; the reference's CUDA build leaves it through the run-to-run
+      // noise of its fp32 atomic sums).  The outcome is known without running them: without a time budget the loop ends at
+      // the cap unconverged; with one it ends when the budget is spent, converged by is_converged_low (:94-104).
+      if (timeout_ms > 0) r->converged = 1;
+      else r->iterations = r->p.max_iterations - 1;
+      break;
     }
   }
   memcpy(r->final_T, x0, sizeof(x0));

@@ -56,8 +56,10 @@ __device__ __forceinline__ unsigned vfe_voxel_offset(const VfeGrid& g, float px,
 // LOWEST indices.  sel[r] is an atomicMin register; a thread offers its index to sel[0], carries the larger of
 // (what was there, what it offered) on to sel[1], and so on.  Whatever the interleaving, the values offered to
 // register r are all indices except the r smallest, so it ends holding the (r+1)-th smallest: deterministic, one pass.
+// next_vid != nullptr (unordered ids, lsd_vfe_params_t::unordered_ids): the thread that opens a slot also numbers the voxel,
+// in atomic order like the reference's voxelization_kernel (voxelization_kernel.cu:119-126) — no scan pass needed.
 __global__ void __launch_bounds__(256) vfe_claim_kernel(int n, const float* __restrict__ pts, VfeGrid g, VfeSlot* __restrict__ tab,
-                                                        unsigned mask, int* __restrict__ pslot) {
+                                                        unsigned mask, int* __restrict__ pslot, int* __restrict__ next_vid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int x, y, z;
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) vfe_claim_kernel(int n, const float* __re
     unsigned s = vfe_hash(key) & mask;
     for (unsigned probe = 0; probe <= mask; probe++) {
       const unsigned pre = atomicCAS(&tab[s].key, kVfeEmpty, key);
+      if (pre == kVfeEmpty && next_vid) tab[s].vid = (unsigned)atomicAdd(next_vid, 1);
       if (pre == kVfeEmpty || pre == key) { slot = (int)s; break; }
       s = (s + 1) & mask;
     }
@@ -131,19 +134,35 @@ __global__ void __launch_bounds__(1024) vfe_scan_kernel(int n, const VfeSlot* __
   if (threadIdx.x == 0) { *total = carry; *done = 0u; }
 }
 
-// voxelization_kernel + reduce_mean_kernel: the opening point of each voxel writes its row
-template <bool ZYX>
-__global__ void __launch_bounds__(256) vfe_emit_kernel(int n, const float* __restrict__ pts, VfeGrid g, const VfeSlot* __restrict__ tab,
+// voxelization_kernel + reduce_mean_kernel: the opening point of each voxel (its smallest point index) writes its row and
+// returns the slot to its idle state (no separate reset pass: nobody else reads the slot in this kernel).
+// ORDERED: voxel id = rank of the opening point among the opening points (vfe_scan_kernel); else the id taken at claim time.
+template <bool ZYX, bool ORDERED>
+__global__ void __launch_bounds__(256) vfe_emit_kernel(int n, const float* __restrict__ pts, VfeGrid g, VfeSlot* __restrict__ tab,
                                                        const int* __restrict__ pslot, const int* __restrict__ local,
                                                        const int* __restrict__ block_off, __half* __restrict__ feat,
                                                        uint4* __restrict__ idx, unsigned* __restrict__ npts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int l = local[i];
-  if (l < 0) return;
-  const int vid = block_off[i >> 10] + l;
+  const int sl = pslot[i];
+  if (sl < 0) return;
+  int vid;
+  if (ORDERED) {
+    const int l = local[i];
+    if (l < 0) return;
+    vid = block_off[i >> 10] + l;
+  } else {
+    if (*reinterpret_cast<volatile unsigned*>(&tab[sl].sel[0]) != (unsigned)i) return;
+    vid = -1;
+  }
+  const VfeSlot s = tab[sl];
+  if (!ORDERED) vid = (int)s.vid;
+  {  // slot back to idle
+    uint4* p = reinterpret_cast<uint4*>(tab + sl);
+    p[0] = make_uint4(kVfeEmpty, 0u, kVfeEmpty, kVfeEmpty);
+    p[1] = make_uint4(kVfeEmpty, kVfeEmpty, kVfeEmpty, 0u);
+  }
   if (vid >= g.max_voxels) return;  // voxelization_kernel.cu:135-137
-  const VfeSlot s = tab[pslot[i]];
   const int cnt = (int)min(s.count, (unsigned)g.max_ppv);
   float acc[8];
   for (int f = 0; f < g.nf; f++) acc[f] = pts[g.nf * (size_t)s.sel[0] + f];
@@ -154,16 +173,6 @@ __global__ void __launch_bounds__(256) vfe_emit_kernel(int n, const float* __res
   vfe_voxel_offset(g, pts[g.nf * i], pts[g.nf * i + 1], pts[g.nf * i + 2], &x, &y, &z);
   idx[vid] = ZYX ? make_uint4(0u, (unsigned)z, (unsigned)y, (unsigned)x) : make_uint4(0u, (unsigned)x, (unsigned)y, (unsigned)z);
   npts[vid] = (unsigned)cnt;
-}
-
-__global__ void __launch_bounds__(256) vfe_reset_kernel(int n, VfeSlot* __restrict__ tab, const int* __restrict__ pslot) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int s = pslot[i];
-  if (s < 0) return;
-  uint4* p = reinterpret_cast<uint4*>(tab + s);
-  p[0] = make_uint4(kVfeEmpty, 0u, kVfeEmpty, kVfeEmpty);
-  p[1] = make_uint4(kVfeEmpty, kVfeEmpty, kVfeEmpty, 0u);
 }
 
 }  // namespace lsd
@@ -198,7 +207,7 @@ void lsd_vfe_default_params(lsd_vfe_params_t* p) {
   // sensor_inference/cfgs/detection_object.yaml:7-16, sensor_driver/inference/inference.h:16-38
   const float mn[3] = {-64.f, -64.f, -2.f}, mx[3] = {64.f, 64.f, 4.f}, vs[3] = {0.1f, 0.1f, 0.15f};
   for (int i = 0; i < 3; i++) { p->min_range[i] = mn[i]; p->max_range[i] = mx[i]; p->voxel_size[i] = vs[i]; }
-  p->max_points_per_voxel = 5; p->max_voxels = 300000; p->max_points = 500000; p->num_feature = 5; p->max_frame_num = 2;
+  p->max_points_per_voxel = 5; p->max_voxels = 300000; p->max_points = 500000; p->num_feature = 5; p->max_frame_num = 2; p->unordered_ids = 0;
 }
 
 lsd_status_t lsd_vfe_create(lsd_vfe_t** out, const lsd_vfe_params_t* p) {
@@ -299,13 +308,20 @@ lsd_status_t lsd_vfe_voxelize(lsd_vfe_t* v, int order_zyx, int* num_voxels) {
   if (n > 0) {
     const float* pts = v->pts[v->cur];
     const int nb = (n + 255) / 256;
-    vfe_claim_kernel<<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->mask, v->pslot);
-    vfe_scan_kernel<<<(n + 1023) / 1024, 1024, 0, st>>>(n, v->tab, v->pslot, v->local, v->block_sum, v->d_done, v->d_total);
-    if (order_zyx) vfe_emit_kernel<true><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
-    else vfe_emit_kernel<false><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
-    vfe_reset_kernel<<<nb, 256, 0, st>>>(n, v->tab, v->pslot);
+    if (v->p.unordered_ids) {   // the reference's contract: voxel ids in atomic order — two kernels
+      LSD_CUDA(cudaMemsetAsync(v->d_total, 0, 4, st));
+      vfe_claim_kernel<<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->mask, v->pslot, v->d_total);
+      if (order_zyx) vfe_emit_kernel<true, false><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
+      else vfe_emit_kernel<false, false><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
+      v->launches += 2;
+    } else {                    // deterministic ids (order of first point): + the scan
+      vfe_claim_kernel<<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->mask, v->pslot, nullptr);
+      vfe_scan_kernel<<<(n + 1023) / 1024, 1024, 0, st>>>(n, v->tab, v->pslot, v->local, v->block_sum, v->d_done, v->d_total);
+      if (order_zyx) vfe_emit_kernel<true, true><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
+      else vfe_emit_kernel<false, true><<<nb, 256, 0, st>>>(n, pts, v->grid, v->tab, v->pslot, v->local, v->block_sum, v->feat, v->idx, v->npts);
+      v->launches += 3;
+    }
     LSD_CUDA(cudaGetLastError());
-    v->launches += 4;
     int h = 0;
     LSD_CUDA(cudaMemcpyAsync(&h, v->d_total, 4, cudaMemcpyDeviceToHost, st));
     LSD_CUDA(cudaStreamSynchronize(st));

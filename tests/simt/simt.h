@@ -280,6 +280,7 @@ template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return 
 template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
 template <class T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
+inline long long clock64() { return 0; }   // no cycle counter in the emulator: timings read 0
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
@@ -337,6 +338,7 @@ inline double max(float a, double b) { return max((double)a, b); }
 #define cudaPeekAtLastError() simt::rt_ok()
 #define cudaDeviceSynchronize() simt::rt_ok()
 #define cudaDeviceSetLimit(a, b) simt::rt_ok()
+#define cudaDeviceGetAttribute(p, a, d) simt::rt_set((p), 1)
 #define cudaStreamCreateWithFlags(p, f) simt::rt_set((p), (cudaStream_t)0x10)
 #define cudaStreamCreate(p) simt::rt_set((p), (cudaStream_t)0x10)
 #define cudaStreamDestroy(s) simt::rt_ok()

@@ -66,3 +66,20 @@ def test_voxelizer_edge_cases():
     assert feat.shape[0] == 7                                                 # max_voxels cap (first 7 voxels kept)
     assert (idx == oi).all() and (npts == on).all() and npts.max() == 5
     assert (feat.view(np.uint16) == of.view(np.uint16)).all()
+
+
+def test_unordered_ids_give_the_same_rows_in_another_numbering():
+    """lsd_vfe_params_t::unordered_ids = 1 (the reference's own contract: voxel ids in atomic order, two kernels instead of
+    three): the same voxel set, and for every voxel the same fp16 features, index row and point count as the ordered mode."""
+    import lsdreg
+    pts, motions = _frames(4)
+    a, b = lsdreg.Voxelizer(max_frame_num=4), lsdreg.Voxelizer(max_frame_num=4, unordered_ids=1)
+    for f in range(4):
+        a.accumulate(pts[f], motions[f]); b.accumulate(pts[f], motions[f])
+    for _ in range(2):                                                         # twice: the slots must come back idle
+        fa, ia, na = a.voxelize(True)
+        fb, ib, nb = b.voxelize(True)
+        assert fa.shape == fb.shape and fa.shape[0] > 1000
+        ka = np.lexsort((ia[:, 3], ia[:, 2], ia[:, 1])); kb = np.lexsort((ib[:, 3], ib[:, 2], ib[:, 1]))
+        assert (ia[ka] == ib[kb]).all() and (na[ka] == nb[kb]).all()
+        assert (fa.view(np.uint16)[ka] == fb.view(np.uint16)[kb]).all()

@@ -55,7 +55,7 @@ for f in range(8):
     pp = np.zeros((sc.shape[0], 5), np.float32); pp[:, :4] = sc; pp[:, 2] -= 1.8
     frames.append(pp)
 M = np.eye(4, dtype=np.float32); M[:3, 3] = [0.8, 0.1, 0.0]
-vg, vr = lsdreg.Voxelizer(max_frame_num=4), RefVoxelizer(max_frame_num=4)
+vg, vr = lsdreg.Voxelizer(max_frame_num=4, unordered_ids=1), RefVoxelizer(max_frame_num=4)   # same contract as the reference: ids in atomic order
 vfe = {}
 for name, v in (("lsdreg", vg), ("reference_cuda_sm100a", vr)):
     for f in range(4):
