@@ -271,6 +271,32 @@ def run_cpu_fastlio(args, FL, eskf, synth, cores, dump_poses=None):
                 what="laserMapping.cpp compiled unmodified (-DMP_EN): VoxelGrid -> update_iterated_dyn_share_modified -> map_incremental")
 
 
+def pin_to_one_socket():
+    """The CPU arm runs on ONE socket (BASELINE.json north_star: "the reference single-socket CPU scans/sec"): bind this process
+    (and the sweep child it spawns) to the CPUs of one NUMA node, so that OpenMP threads and the 10 M-point iVox stay on one
+    memory controller — across two sockets the same code measured anything from 20 to 54 ms per scan on the same box."""
+    try:
+        have = os.sched_getaffinity(0)
+        best = None
+        for d in sorted(os.listdir("/sys/devices/system/node")):
+            if not d.startswith("node") or not d[4:].isdigit():
+                continue
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/{d}/cpulist").read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            cpus &= have
+            if cpus and (best is None or len(cpus) > len(best)):
+                best = cpus
+        if best and len(best) < len(have):
+            os.sched_setaffinity(0, best)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return 0
+
+
 def run_cpu(args, rank, world, dump_poses=None):
     """Reference arm / cpu_baseline: the reference's CPU path on the host cores.  Uses oracle/_ref
     (laserMapping.cpp compiled unmodified) when it exists, else the plain-C port.  Imports nothing of the product."""
@@ -279,6 +305,7 @@ def run_cpu(args, rank, world, dump_poses=None):
     from oracle import oracle as O
     from oracle import fastlio as FL
     synth = load_synth()
+    pin_to_one_socket()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if FL.HAVE_REF_FASTLIO and not os.environ.get("LSD_BENCH_CPU_RESTATED"):
         return run_cpu_fastlio(args, FL, eskf, synth, cores, dump_poses)
@@ -469,6 +496,7 @@ def main():
         if rank != 0:
             return 0
         if args.sweep_only:
+            pin_to_one_socket()
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             sweep_child(cores, args.warmup, args.steps)
             return 0
@@ -477,7 +505,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(r["map_points"], r["scan_points"], r["n_down"] if r["n_down"] is not None else -1),
-                "impl_config": {"parallelism": f"{r['cores']} OpenMP threads of {r['host_cores']} host cores", "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
+                "impl_config": {"parallelism": f"{r['cores']} OpenMP threads on one socket ({r['host_cores']} CPUs of {os.cpu_count()} on the box)", "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
                                 "thread_sweep_ms": r["thread_sweep_ms"], "thread_sweep": r.get("thread_sweep"),
                                 "timing": "host wall clock around each fastlio_main pass (ref_fastlio_pass), summed over the K timed steps"},
                 "step_ms": r["step_ms"],
