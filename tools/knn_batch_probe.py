@@ -27,6 +27,9 @@ def opt(name, default):
 nq = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1 << 21
 shapes = [int(x) for x in opt("--shapes", "3,2").split(",")]
 reps = int(opt("--reps", "4"))
+if "--lib" in sys.argv:      # A/B builds of the library (same C ABI): python tools/knn_batch_probe.py ... --lib path/to/liblsdreg_variant.so
+    lsdreg.capi.lib = lsdreg.capi.load_library(os.path.abspath(opt("--lib", "")))
+    lsdreg.lib = lsdreg.capi.lib
 lsdreg.init(0)
 dev = torch.device("cuda", 0)
 synth = bench.load_synth()
