@@ -1008,6 +1008,18 @@ class LioFrontend:
             return
         check(lib.lsd_lio_prefetch(self.h, _ptr(scan), scan.shape[0]))
 
+    def scan_into(self, scan, state: np.ndarray, P: np.ndarray, info: "LioInfo") -> int:
+        """scan() without the per-call allocations: `state` (float64 state vector) and `P` (float64[23,23], C order) are updated in
+        place, `info` is a caller-owned LioInfo, `scan` must already be float32 [n,4] C-contiguous (numpy, pinned or CUDA
+        torch tensor).  Returns the status code (raises like scan()).  For callers that register thousands of scans per
+        second, where building two arrays and a dict per call is a tenth of the step."""
+        fn = lib.lsd_lio_scan_dev if getattr(scan, "is_cuda", False) else lib.lsd_lio_scan
+        st = fn(self.h, _ptr(scan), scan.shape[0], state.ctypes.data, P.ctypes.data, C.byref(info))
+        if st < 0:
+            check(st)
+        self.n_down = info.n_down
+        return st
+
     def scan(self, scan, state: np.ndarray, P: np.ndarray):
         """Whole pass.  `scan`: numpy [n,4] (host pointer, H2D inside) or CUDA torch tensor (device)."""
         state = np.array(state, np.float64)

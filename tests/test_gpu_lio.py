@@ -176,7 +176,23 @@ def test_prefetch_is_transparent(small_world):
         g.sync()
         return out
 
+    def run_in_place():
+        """scan_into: the same entry point without the per-call arrays / dict (bench.py's timed loop)."""
+        g, o, prior = _pair(small_world)
+        x = np.array(prior.to_vec(), np.float64); P = np.array(eskf.init_P(), np.float64)
+        info = lsdreg.capi.LioInfo()
+        out = []
+        for k in range(4):
+            P += np.eye(23) * 1e-2
+            assert g.scan_into(scans[k], x, P, info) >= 0
+            out.append((x.copy(), info.n_down, info.n_eff))
+        g.sync()
+        return out
+
     ref = run("serial")
+    for (xa, na, ea), (xb, nb, eb) in zip(ref, run_in_place()):
+        assert na == nb and ea == eb
+        np.testing.assert_array_equal(xa, xb)
     for mode in ("pipelined", "decoy"):
         got = run(mode)
         for (xa, na, ea), (xb, nb, eb) in zip(ref, got):
