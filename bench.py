@@ -698,8 +698,21 @@ def main():
     def compare(ref_poses, source):
         n = min(len(ref_poses), len(R["poses_a"]))
         dm = [pose_delta(R["poses_a"][s], ref_poses[s]) for s in range(n)]
-        return {"max_m": max(d[0] for d in dm), "max_rad": max(d[1] for d in dm), "steps_compared": n, "against": source,
-                "bar": "1e-4 m / 1e-5 rad (BASELINE.json north_star)", "within_bar": bool(max(d[0] for d in dm) < 1e-4 and max(d[1] for d in dm) < 1e-5)}
+        out = {"max_m": max(d[0] for d in dm), "max_rad": max(d[1] for d in dm),
+               "median_m": float(np.median([d[0] for d in dm])), "median_rad": float(np.median([d[1] for d in dm])),
+               "steps_within_bar": int(sum(1 for d in dm if d[0] < 1e-4 and d[1] < 1e-5)), "steps_compared": n, "against": source,
+               "bar": "1e-4 m / 1e-5 rad (BASELINE.json north_star)", "within_bar": bool(max(d[0] for d in dm) < 1e-4 and max(d[1] for d in dm) < 1e-5)}
+        try:     # the reference's own build-to-build spread on these steps (tools/ref_build_sensitivity.py, run where the reference tree is)
+            with open(os.path.join(ROOT, "profiles", "r02_ref_build_sensitivity.json")) as f:
+                sens = json.load(f)["variants"]
+            worst = max(sens, key=lambda k: sens[k]["max_rad"])
+            out["reference_vs_itself"] = {"build": worst, "max_m": sens[worst]["max_m"], "max_rad": sens[worst]["max_rad"],
+                                          "steps_over_bar": sens[worst]["steps_over_bar"],
+                                          "what": "the same unmodified sources compiled for another x86 target vs the build compared here, same steps "
+                                                  "(profiles/r02_ref_build_sensitivity.json): the bar sits at the reference's own reproducibility"}
+        except Exception:
+            pass
+        return out
     if True:     # rank 0 registers steps 0.. in either mode
         try:
             with open(REF_POSES) as f:

@@ -36,12 +36,7 @@ constexpr int kPageNext = kPageHead + kRegCells;      // 616
 constexpr int kPagePts = kPageNext + kBrickCap;       // 848
 constexpr int kPageBytes = 4608;
 constexpr int kBrickQC = 32;                          // queries per work item: one WARP answers an item, one query per lane
-constexpr int kBrickWarps = 4;                        // warps per CTA of the query kernel
-#ifdef LSD_BRICK_SINGLE_BUFFER                        // A/B build: one page buffer per warp (10 CTAs / SM) instead of two (5 CTAs / SM)
-constexpr int kBrickBufs = 1;
-#else
-constexpr int kBrickBufs = 2;
-#endif
+constexpr int kBrickWarps = 4;                        // warps per CTA of the query kernel (two page buffers each)
 static_assert(kPagePts % 16 == 0 && kPagePts + 16 * kBrickCap <= kPageBytes && kPageBytes % 128 == 0, "page layout");
 
 struct __align__(32) BrickQuery { float4 p; int qi; int pad[3]; };   // a query in brick order: one full 32-byte sector (no partial-sector writes)
@@ -179,27 +174,18 @@ __device__ __forceinline__ void page_load_wait(unsigned long long* bar, unsigned
 // K-A: home brick of every query; queries whose brick does not exist are answered here (nothing within reach).
 __global__ void __launch_bounds__(256) brick_bin_kernel(BrickView bv, float inv_res, const float4* __restrict__ q, int nq, int k,
                                                         int* __restrict__ q_slot, int* __restrict__ q_rank, unsigned* __restrict__ bin_count,
-                                                        int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt,
-                                                        unsigned* __restrict__ ctr3) {
+                                                        int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < nq;
+  if (i >= nq) return;
+  const float4 p = __ldg(q + i);
+  const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
   long long s = -1;
-  if (valid) {
-    const float4 p = __ldg(q + i);
-    const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
-    // beyond +-(2^18) no stencil cell is a valid voxel (coord_ok): nothing can be near
-    if (abs(c.x) <= kCoordBias && abs(c.y) <= kCoordBias && abs(c.z) <= kCoordBias) {
-      int3 b, l;
-      brick_of(c.x, c.y, c.z, &b, &l);
-      s = brick_find(bv, pack_key(b.x, b.y, b.z, 0));
-    }
+  // beyond +-(2^18) no stencil cell is a valid voxel (coord_ok): nothing can be near
+  if (abs(c.x) <= kCoordBias && abs(c.y) <= kCoordBias && abs(c.z) <= kCoordBias) {
+    int3 b, l;
+    brick_of(c.x, c.y, c.z, &b, &l);
+    s = brick_find(bv, pack_key(b.x, b.y, b.z, 0));
   }
-  {  // ctr3: queries whose predecessor in the batch has the same home brick (a batch that arrives in spatial order)
-    const long long prev = __shfl_up_sync(0xffffffffu, s, 1);
-    const unsigned same = __ballot_sync(0xffffffffu, (threadIdx.x & 31) != 0 && s >= 0 && prev == s);
-    if ((threadIdx.x & 31) == 0 && same) atomicAdd(ctr3, (unsigned)__popc(same));
-  }
-  if (!valid) return;
   q_slot[i] = (int)s;
   if (s < 0) {
     for (int r = 0; r < k; r++) { out_idx[(size_t)i * k + r] = -1; out_d2[(size_t)i * k + r] = -1.0f; }
@@ -251,25 +237,18 @@ __global__ void __launch_bounds__(256) brick_plan_kernel(BrickView bv, unsigned 
   }
 }
 
-// A batch counts as spatially ordered when at least half of its queries share their home brick with their predecessor
-// (ctr[3], counted by the bin kernel).  Then gathering q[qi] in brick order is already contiguous, and copying the queries
-// would only add traffic; a shuffled batch gets the copy, so that the search reads full sectors.
-__device__ __forceinline__ bool brick_batch_is_ordered(const unsigned* ctr, int nq) { return 2u * __ldcg(ctr + 3) >= (unsigned)nq; }
-
 // K-C: the batch in brick order: query + its index in the caller's batch, one 32-byte sector each, so that the search
 // reads its queries with one contiguous load instead of index -> query (two dependent DRAM trips)
 __global__ void __launch_bounds__(256) brick_scatter_kernel(const float4* __restrict__ q, const int* __restrict__ q_slot,
                                                             const int* __restrict__ q_rank, const int* __restrict__ bin_base, int nq,
-                                                            BrickQuery* __restrict__ sorted, const unsigned* __restrict__ ctr) {
+                                                            BrickQuery* __restrict__ sorted) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   const int s = q_slot[i];
   if (s < 0) return;
-  const int pos = bin_base[s] + q_rank[i];
-  if (brick_batch_is_ordered(ctr, nq)) { sorted[pos].qi = i; return; }   // the search reads q[qi] directly: neighbours in the batch are neighbours in memory
   BrickQuery e;
   e.p = __ldg(q + i); e.qi = i; e.pad[0] = e.pad[1] = e.pad[2] = 0;
-  sorted[pos] = e;
+  sorted[bin_base[s] + q_rank[i]] = e;
 }
 
 // ------------------------------------------------------------------ K-D: the search
@@ -314,23 +293,22 @@ struct KeyTop5 {
 
 template <int K>
 __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView bv, float inv_res, int st_slot, float max_sq,
-                                                                     const float4* __restrict__ q, int nq, const BrickQuery* __restrict__ sorted,
+                                                                     const BrickQuery* __restrict__ sorted,
                                                                      const BrickWork* __restrict__ work, unsigned* __restrict__ ctr,
                                                                      int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
   // Two page buffers per warp: while item N is answered from one, item N + 1's page lands in the other, its queries sit in
   // registers and item N + 2's descriptor is on its way — after the prologue no item waits for a memory round trip.
-  __shared__ __align__(128) unsigned char pages[kBrickWarps][kBrickBufs][kPageBytes];
-  __shared__ __align__(8) unsigned long long bars[kBrickWarps][kBrickBufs];
+  __shared__ __align__(128) unsigned char pages[kBrickWarps][2][kPageBytes];
+  __shared__ __align__(8) unsigned long long bars[kBrickWarps][2];
   __shared__ unsigned char cellq[kBrickWarps][32][28];   // per lane: heads of its non-empty stencil cells (<= 27: NEARBY26)
   __shared__ int s_off[32];                              // the stencil as region-index offsets
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { for (int k = 0; k < kBrickBufs; k++) mbar_init(&bars[warp][k]); }
+  if (lane == 0) { mbar_init(&bars[warp][0]); mbar_init(&bars[warp][1]); }
   const Stencil& st = c_stencils[st_slot];
   const int n_cells = st.n;                              // <= 27 for the stencils served here
   if (threadIdx.x < 32) s_off[threadIdx.x] = (int)threadIdx.x < n_cells ? (st.off[threadIdx.x][2] * kRegXY + st.off[threadIdx.x][1]) * kRegXY + st.off[threadIdx.x][0] : 0;
   __syncthreads();
   const unsigned n_work = __ldcg(ctr + 1);
-  const bool direct = brick_batch_is_ordered(ctr, nq);   // warp-uniform: queries gathered from the caller's batch, not from copies
   unsigned char* myq = cellq[warp][lane];
   unsigned phase = 0u;                                   // bit b = parity the next wait on buffer b expects
   const BrickWork none = {0, 0, 0, 0u, 0ull};
@@ -340,11 +318,7 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
   auto load_query = [&](const BrickWork& it, float4* p, int* qi) {
     const int t = lane >> lanes_log2(it.qn);
     *qi = -1; *p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < it.qn) {
-      const BrickQuery* e = sorted + it.qbase + t;
-      *qi = __ldg(&e->qi);
-      *p = direct ? __ldg(q + *qi) : __ldg(&e->p);
-    }
+    if (t < it.qn) { const BrickQuery* e = sorted + it.qbase + t; *p = __ldg(&e->p); *qi = __ldg(&e->qi); }
   };
 
   // prologue: item 0 in flight, item 1 described
@@ -363,8 +337,7 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
     // next item: page into the other buffer, queries into registers; the one after: descriptor
     float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f); int qi1 = -1;
     if (w1 < n_work) {
-      if (kBrickBufs == 2 && lane == 0)
-        page_load_issue(pages[warp][b ^ 1], &bars[warp][b ^ 1], bv.pages + (size_t)it1.slot * kPageBytes, min(it1.total, (unsigned)kBrickCap));
+      if (lane == 0) page_load_issue(pages[warp][b ^ 1], &bars[warp][b ^ 1], bv.pages + (size_t)it1.slot * kPageBytes, min(it1.total, (unsigned)kBrickCap));
       load_query(it1, &p1, &qi1);
     }
     const unsigned w2 = w1 < n_work ? claim() : n_work;
@@ -446,11 +419,9 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
       if (sub == 0) out_cnt[qi] = nf;
     }
     __syncwarp();   // this page buffer and the cell queues are free for the item after next
-    if (kBrickBufs == 1 && w1 < n_work && lane == 0)   // single buffer: the next page can only start now
-      page_load_issue(pages[warp][0], &bars[warp][0], bv.pages + (size_t)it1.slot * kPageBytes, min(it1.total, (unsigned)kBrickCap));
     w = w1; it = it1; p = p1; qi = qi1;
     w1 = w2; it1 = it2;
-    if (kBrickBufs == 2) b ^= 1;
+    b ^= 1;
   }
 }
 

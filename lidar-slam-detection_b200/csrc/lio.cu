@@ -276,10 +276,15 @@ template <int NV>
 __device__ __forceinline__ void block_partials(double (&vals)[NV], double* __restrict__ partials) {
   __shared__ double sm_bp[8][kNV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if constexpr (NV > 8) {
+    const double v = warp_sum_to_lane<NV>(vals);   // lane j <- warp total of vals[j], same bits as warp_sum
+    if (lane < NV) sm_bp[warp][lane] = v;
+  } else {
 #pragma unroll
-  for (int j = 0; j < NV; j++) {
-    const double v = warp_sum(vals[j]);
-    if (lane == 0) sm_bp[warp][j] = v;
+    for (int j = 0; j < NV; j++) {
+      const double v = warp_sum(vals[j]);
+      if (lane == 0) sm_bp[warp][j] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x < NV) {

@@ -120,6 +120,43 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// NV (9..32) per-lane values -> lane j returns the warp total of vals[j] (lanes >= NV return 0).  A transposed butterfly:
+// at offset 16 a lane keeps one half of its values and sends the other half to its partner, then 8, 4, 2, 1 — 31 double
+// shuffles and adds instead of NV x 5.  Every total is formed by the SAME pairing tree as warp_sum (partners l, l^16, then
+// ^8, ...; IEEE addition is commutative), so the sums are bit-identical to NV calls of warp_sum.
+template <int NV>
+__device__ __forceinline__ double warp_sum_to_lane(const double (&vals)[NV]) {
+  static_assert(NV > 8 && NV <= 32, "use warp_sum for a handful of values");
+  const int lane = threadIdx.x & 31;
+  double a[16], b[8], c[4], d[2];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const double lo = (j < NV) ? vals[j < NV ? j : 0] : 0.0;
+      const double hi = (j + 16 < NV) ? vals[j + 16 < NV ? j + 16 : 0] : 0.0;
+      a[j] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) b[j] = (up ? a[j + 8] : a[j]) + __shfl_xor_sync(0xffffffffu, up ? a[j] : a[j + 8], 8);
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) c[j] = (up ? b[j + 4] : b[j]) + __shfl_xor_sync(0xffffffffu, up ? b[j] : b[j + 4], 4);
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int j = 0; j < 2; j++) d[j] = (up ? c[j + 2] : c[j]) + __shfl_xor_sync(0xffffffffu, up ? c[j] : c[j + 2], 2);
+  }
+  const bool up = lane & 1;
+  return (up ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, up ? d[0] : d[1], 1);
+}
+
 // ------------------------------------------------------------------ programmatic dependent launch (sm_90+)
 // A scan is a chain of ~15 short kernels (5-40 us each) on one stream; between two dependent kernels the GPU idles for
 // the grid drain plus the next grid's launch latency.  With the programmatic-stream-serialization attribute the next

@@ -23,7 +23,9 @@ from .imu import OracleImuProcess
 from .lio import OracleLio
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_PATH = os.path.join(_HERE, "_ref", "libref_fastlio.so")
+# LSD_REF_FASTLIO_LIB: another build of the same unmodified sources (tools/ref_build_sensitivity.py compiles the reference
+# with other compiler flags to measure how far the reference's own poses move between its builds)
+_PATH = os.environ.get("LSD_REF_FASTLIO_LIB") or os.path.join(_HERE, "_ref", "libref_fastlio.so")
 HAVE_REF_FASTLIO = os.path.exists(_PATH)
 _lib = None
 

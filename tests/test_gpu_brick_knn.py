@@ -56,7 +56,7 @@ def test_brick_pages_bit_identical(small_world):
     st = g.brick_stats()
     assert st["dropped"] == 0 and st["replicas"] >= g.stats()["points"] and st["pages"] > 100, st
     _check_all(g, o, q, "dual write")
-    # a batch in spatial order takes the other gather path (queries read from the caller's array instead of sorted copies)
+    # the same batch in spatial order (every bin counter contended, long runs of one brick)
     cell = np.round(q[:, :3] / 0.5)
     cell[~np.isfinite(cell)] = 0
     _check_all(g, o, np.ascontiguousarray(q[np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))]), "ordered batch")
