@@ -177,6 +177,8 @@ def sweep_child(cores, W, K):
     ref = FL.RefFastLioBench(capacity=1 << 30, threads=8)
     ref.add_map_points(m)
     cands = sorted({t for t in (4, 8, 16, 32, 64, cores) if t <= cores})
+    if os.environ.get("LSD_BENCH_SWEEP_CANDS"):     # the second (FMA-build) child times only the winner's neighbourhood
+        cands = sorted({int(t) for t in os.environ["LSD_BENCH_SWEEP_CANDS"].split(",") if 0 < int(t) <= cores}) or cands
     reps, nxt = 3, 2 * (W + K) + 64
     out = {}
     for ci, nt in enumerate(cands):
@@ -192,6 +194,9 @@ def sweep_child(cores, W, K):
     print(json.dumps({"sweep_s": out, "cores": cores}))
 
 
+FMA_SWEEP = {}     # {threads: median seconds} of the FMA-target build of the same sources, filled by thread_sweep
+
+
 def thread_sweep(cores, W, K):
     """-> ({threads: median seconds}, how).  LSD_BENCH_REF_THREADS fixes the count; a sweep of this boot (same core count,
     younger than an hour: the reference arm runs right before the product arm) is reused; else a child process measures."""
@@ -202,6 +207,7 @@ def thread_sweep(cores, W, K):
         with open(SWEEP_CACHE) as f:
             c = json.load(f)
         if c.get("cores") == cores and time.time() - c.get("when", 0) < 3600:
+            FMA_SWEEP.clear(); FMA_SWEEP.update({int(k): v for k, v in c.get("fma_build_sweep_s", {}).items()})
             return {int(k): v for k, v in c["sweep_s"].items()}, "median of 3 cold-block scans per candidate in a child process (reused from the reference arm's run on this box); best median used"
     except Exception:
         pass
@@ -209,12 +215,27 @@ def thread_sweep(cores, W, K):
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--sweep-only", "--steps", str(K), "--warmup", str(W)],
                            cwd=ROOT, capture_output=True, text=True, timeout=600)
         row = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{") and "sweep_s" in ln][-1]
+        sweep = {int(k): v for k, v in row["sweep_s"].items()}
+        # The same sources built for an FMA target (oracle/_ref/libref_fastlio_fma.so, -O3 -march=x86-64-v3): SURVEY 8d's "fair
+        # speed baseline".  Timing only, in a child of its own; the arm's value and poses stay the reference-flags build's.
+        fma_lib = os.path.join(ROOT, "oracle", "_ref", "libref_fastlio_fma.so")
+        if os.path.exists(fma_lib):
+            try:
+                best = min(sweep, key=sweep.get)
+                cands = sorted({t for t in (best // 2, best, best * 2) if 4 <= t <= cores})
+                r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--sweep-only", "--steps", str(K), "--warmup", str(W)],
+                                    cwd=ROOT, capture_output=True, text=True, timeout=300,
+                                    env=dict(os.environ, LSD_REF_FASTLIO_LIB=fma_lib, LSD_BENCH_SWEEP_CANDS=",".join(map(str, cands))))
+                row["fma_build_sweep_s"] = [json.loads(ln) for ln in r2.stdout.splitlines() if ln.startswith("{") and "sweep_s" in ln][-1]["sweep_s"]
+            except Exception:  # noqa: BLE001
+                pass
         try:
             with open(SWEEP_CACHE, "w") as f:
                 json.dump(dict(row, when=time.time()), f)
         except OSError:
             pass
-        return {int(k): v for k, v in row["sweep_s"].items()}, "median of 3 cold-block scans per candidate in a child process (own map: the timed steps' map history is untouched); best median used"
+        FMA_SWEEP.clear(); FMA_SWEEP.update({int(k): v for k, v in row.get("fma_build_sweep_s", {}).items()})
+        return sweep, "median of 3 cold-block scans per candidate in a child process (own map: the timed steps' map history is untouched); best median used"
     except Exception as e:  # noqa: BLE001
         return {8: 0.0}, f"sweep child failed ({type(e).__name__}): the reference's own MP_PROC_NUM = 8"
 
@@ -266,6 +287,9 @@ def run_cpu_fastlio(args, FL, eskf, synth, cores, dump_poses=None):
                 step_ms={"median": 1e3 * float(np.median(times)), "p95": 1e3 * float(np.percentile(times, 95)), "min": 1e3 * float(np.min(times)), "max": 1e3 * float(np.max(times))},
                 thread_sweep_ms={str(k): round(v * 1e3, 2) for k, v in sweep.items()},
                 thread_sweep=how,
+                fma_build=({"flags": "-O3 -march=x86-64-v3 (AVX2 + FMA; the arm's value and poses are the reference-flags build's)",
+                            "ms_per_scan": round(1e3 * min(FMA_SWEEP.values()), 2), "threads": min(FMA_SWEEP, key=FMA_SWEEP.get),
+                            "sample": "median of 3 cold-block scans per thread count, child process"} if FMA_SWEEP else None),
                 kind="reference", setup_s=setup_s, poses=poses,
                 iters=None, map_points=int(m.shape[0]), scan_points=float(np.mean([st[0].shape[0] for st in steps[W:]])), n_down=float(np.mean(n_downs)),
                 what="laserMapping.cpp compiled unmodified (-DMP_EN): VoxelGrid -> update_iterated_dyn_share_modified -> map_incremental")
@@ -506,11 +530,11 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(r["map_points"], r["scan_points"], r["n_down"] if r["n_down"] is not None else -1),
                 "impl_config": {"parallelism": f"{r['cores']} OpenMP threads on one socket ({r['host_cores']} CPUs of {os.cpu_count()} on the box)", "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
-                                "thread_sweep_ms": r["thread_sweep_ms"], "thread_sweep": r.get("thread_sweep"),
+                                "thread_sweep_ms": r["thread_sweep_ms"], "thread_sweep": r.get("thread_sweep"), "fma_build": r.get("fma_build"),
                                 "timing": "host wall clock around each fastlio_main pass (ref_fastlio_pass), summed over the K timed steps"},
                 "step_ms": r["step_ms"],
                 "cpu_baseline": {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
-                                 "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
+                                 "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "fma_build": r.get("fma_build"), "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
                                  "sample": f"{args.steps} full scans of the workload after {args.warmup} warm-up scans"},
                 "e2e": {"value": r["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "mean_iterations": r["iters"], "poses_written_to": REF_POSES}
@@ -727,7 +751,8 @@ def main():
         a2 = argparse.Namespace(steps=args.cpu_sample, warmup=1)
         r = run_cpu(a2, 0, 1)
         cpu = {"value": r["value"], "unit": "scans/s", "cores": r["cores"], "kind": r["kind"],
-               "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "thread_sweep": r.get("thread_sweep"), "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
+               "host_cores": r["host_cores"], "thread_sweep_ms": r["thread_sweep_ms"], "thread_sweep": r.get("thread_sweep"), "fma_build": r.get("fma_build"),
+               "what": r.get("what", "restated loop on the compiled reference iVox / esti_plane"),
                "sample": f"{args.cpu_sample} full scans of the same workload (same map, same generator) after 1 warm-up scan",
                "ms_per_scan": r["ms_per_step"], "mean_iterations": r["iters"]}
         if pose_parity is None and r.get("poses"):
