@@ -32,9 +32,99 @@ constexpr int kLioMaxGrid = 296;  // 2 blocks per SM: the final fold reads <= 29
 struct LioPose { double R[9], t[3], RL[9], tL[3]; };
 
 // ---------------------------------------------------------------- esti_plane (common_lib.h:236-268)
-// A (5x3) n = -1 by Householder QR with column pivoting, fp32, same operation order as
-// oracle/lsd_oracle.c::orc_esti_plane (-fmad=false), so GPU and oracle agree bit for bit.
+// A (5x3) n = -1 by Householder QR with column pivoting in fp32, every sum in the order Eigen's ColPivHouseholderQR takes on the
+// reference's x86-64 build (4-float packets, no FMA; -fmad=false here): a whole column as ((t0+t2)+(t1+t3))+t4, a run-time
+// tail of four as (t0+t2)+(t1+t3), shorter tails left to right, the upper-triangular solve column by column, |n|^2 as
+// t0+(t1+t2).  The plane coefficients are bit-identical to the compiled reference's (oracle/lsd_oracle.c::orc_esti_plane is
+// pinned to it on 1 M planes and states the rules with their Eigen sources).
 __device__ __forceinline__ void swap_f(float& a, float& b) { float t = a; a = b; b = t; }
+// sum of t[R0..4] in Eigen's run-time-size order
+template <int R0>
+__device__ __forceinline__ float red_tail(const float (&t)[5]) {
+  if (R0 == 1) return (t[1] + t[3]) + (t[2] + t[4]);
+  if (R0 == 2) return (t[2] + t[3]) + t[4];
+  if (R0 == 3) return t[3] + t[4];
+  return t[4];
+}
+template <int K>
+__device__ __forceinline__ void esti_qr_step(float (&A)[5][3], float (&b)[5], float (&hc)[3], float (&nu)[3], float (&nd)[3], int (&perm)[3],
+                                             int& nonzero, float th_helper, float downdate) {
+  int big = K;
+  float bn = nu[K];
+#pragma unroll
+  for (int j = K + 1; j < 3; j++) if (nu[j] > bn) { bn = nu[j]; big = j; }
+  if (nonzero == 3 && bn * bn < th_helper * (float)(5 - K)) nonzero = K;
+#pragma unroll
+  for (int j = K + 1; j < 3; j++) {
+    if (big == j) {
+#pragma unroll
+      for (int r = 0; r < 5; r++) swap_f(A[r][K], A[r][j]);
+      swap_f(nu[K], nu[j]); swap_f(nd[K], nd[j]);
+      int ti = perm[K]; perm[K] = perm[j]; perm[j] = ti;
+    }
+  }
+  float t[5];
+#pragma unroll
+  for (int r = 0; r < 5; r++) t[r] = A[r][K] * A[r][K];
+  const float tail = red_tail<K + 1>(t);
+  const float c0 = A[K][K];
+  float beta, tau;
+  if (tail <= 1.17549435e-38f) {
+    tau = 0.f; beta = c0;
+#pragma unroll
+    for (int r = K + 1; r < 5; r++) A[r][K] = 0.f;
+  } else {
+    beta = sqrtf(c0 * c0 + tail);
+    if (c0 >= 0.f) beta = -beta;
+    const float den = c0 - beta;
+#pragma unroll
+    for (int r = K + 1; r < 5; r++) A[r][K] = A[r][K] / den;
+    tau = (beta - c0) / beta;
+  }
+  hc[K] = tau; A[K][K] = beta;
+  if (tau != 0.f) {
+#pragma unroll
+    for (int j = K + 1; j < 3; j++) {
+#pragma unroll
+      for (int r = 0; r < 5; r++) t[r] = A[r][K] * A[r][j];
+      float tmp = red_tail<K + 1>(t);
+      tmp += A[K][j];
+      A[K][j] -= tau * tmp;
+#pragma unroll
+      for (int r = K + 1; r < 5; r++) A[r][j] -= (tau * A[r][K]) * tmp;
+    }
+  }
+#pragma unroll
+  for (int j = K + 1; j < 3; j++) {
+    if (nu[j] != 0.f) {
+      float q = fabsf(A[K][j]) / nu[j];
+      q = (1.f + q) * (1.f - q);
+      if (q < 0.f) q = 0.f;
+      const float rr = nu[j] / nd[j];
+      const float t2 = q * (rr * rr);
+      if (t2 <= downdate) {
+#pragma unroll
+        for (int r = 0; r < 5; r++) t[r] = A[r][j] * A[r][j];
+        nd[j] = sqrtf(red_tail<K + 1>(t)); nu[j] = nd[j];
+      } else {
+        nu[j] *= sqrtf(q);
+      }
+    }
+  }
+}
+template <int K>
+__device__ __forceinline__ void esti_apply_b(const float (&A)[5][3], float (&b)[5], const float (&hc)[3], int nonzero) {
+  if (K < nonzero && hc[K] != 0.f) {
+    float t[5];
+#pragma unroll
+    for (int r = 0; r < 5; r++) t[r] = A[r][K] * b[r];
+    float tmp = red_tail<K + 1>(t);
+    tmp += b[K];
+    b[K] -= hc[K] * tmp;
+#pragma unroll
+    for (int r = K + 1; r < 5; r++) b[r] -= (hc[K] * A[r][K]) * tmp;
+  }
+}
 __device__ __forceinline__ bool esti_plane_dev(const float (&px)[5], const float (&py)[5], const float (&pz)[5], float thr,
                                                float (&pabcd)[4]) {
   const float FEPS = 1.1920929e-07f;
@@ -45,10 +135,8 @@ __device__ __forceinline__ bool esti_plane_dev(const float (&px)[5], const float
   int perm[3] = {0, 1, 2};
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 5; r++) s += A[r][k] * A[r][k];
-    nu[k] = nd[k] = sqrtf(s);
+    const float t0 = A[0][k] * A[0][k], t1 = A[1][k] * A[1][k], t2 = A[2][k] * A[2][k], t3 = A[3][k] * A[3][k], t4 = A[4][k] * A[4][k];
+    nu[k] = nd[k] = sqrtf(((t0 + t2) + (t1 + t3)) + t4);
   }
   float mxn = nu[0];
   if (nu[1] > mxn) mxn = nu[1];
@@ -56,103 +144,31 @@ __device__ __forceinline__ bool esti_plane_dev(const float (&px)[5], const float
   const float th_helper = (mxn * FEPS) * (mxn * FEPS) / 5.0f;
   const float downdate = sqrtf(FEPS);
   int nonzero = 3;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    int big = k;
-    float bn = nu[k];
-#pragma unroll
-    for (int j = k + 1; j < 3; j++) if (nu[j] > bn) { bn = nu[j]; big = j; }
-    if (nonzero == 3 && bn * bn < th_helper * (float)(5 - k)) nonzero = k;
-#pragma unroll
-    for (int j = k + 1; j < 3; j++) {
-      if (big == j) {
-#pragma unroll
-        for (int r = 0; r < 5; r++) swap_f(A[r][k], A[r][j]);
-        swap_f(nu[k], nu[j]); swap_f(nd[k], nd[j]);
-        int ti = perm[k]; perm[k] = perm[j]; perm[j] = ti;
-      }
-    }
-    float tail = 0.f;
-#pragma unroll
-    for (int r = k + 1; r < 5; r++) tail += A[r][k] * A[r][k];
-    const float c0 = A[k][k];
-    float beta, tau;
-    if (tail <= 1.17549435e-38f) {
-      tau = 0.f; beta = c0;
-#pragma unroll
-      for (int r = k + 1; r < 5; r++) A[r][k] = 0.f;
-    } else {
-      beta = sqrtf(c0 * c0 + tail);
-      if (c0 >= 0.f) beta = -beta;
-      const float den = c0 - beta;
-#pragma unroll
-      for (int r = k + 1; r < 5; r++) A[r][k] = A[r][k] / den;
-      tau = (beta - c0) / beta;
-    }
-    hc[k] = tau; A[k][k] = beta;
-    if (tau != 0.f) {
-#pragma unroll
-      for (int j = k + 1; j < 3; j++) {
-        float tmp = 0.f;
-#pragma unroll
-        for (int r = k + 1; r < 5; r++) tmp += A[r][k] * A[r][j];
-        tmp += A[k][j];
-        A[k][j] -= tau * tmp;
-#pragma unroll
-        for (int r = k + 1; r < 5; r++) A[r][j] -= tau * A[r][k] * tmp;
-      }
-    }
-#pragma unroll
-    for (int j = k + 1; j < 3; j++) {
-      if (nu[j] != 0.f) {
-        float t = fabsf(A[k][j]) / nu[j];
-        t = (1.f + t) * (1.f - t);
-        if (t < 0.f) t = 0.f;
-        const float rr = nu[j] / nd[j];
-        const float t2 = t * rr * rr;
-        if (t2 <= downdate) {
-          float s = 0.f;
-#pragma unroll
-          for (int r = k + 1; r < 5; r++) s += A[r][j] * A[r][j];
-          nd[j] = sqrtf(s); nu[j] = nd[j];
-        } else {
-          nu[j] *= sqrtf(t);
-        }
-      }
-    }
-  }
+  esti_qr_step<0>(A, b, hc, nu, nd, perm, nonzero, th_helper, downdate);
+  esti_qr_step<1>(A, b, hc, nu, nd, perm, nonzero, th_helper, downdate);
+  esti_qr_step<2>(A, b, hc, nu, nd, perm, nonzero, th_helper, downdate);
   float x[3] = {0.f, 0.f, 0.f};
   if (nonzero > 0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      if (k < nonzero && hc[k] != 0.f) {
-        float tmp = 0.f;
-#pragma unroll
-        for (int r = k + 1; r < 5; r++) tmp += A[r][k] * b[r];
-        tmp += b[k];
-        b[k] -= hc[k] * tmp;
-#pragma unroll
-        for (int r = k + 1; r < 5; r++) b[r] -= hc[k] * A[r][k] * tmp;
-      }
-    }
-    float c[3] = {0.f, 0.f, 0.f};
+    esti_apply_b<0>(A, b, hc, nonzero);
+    esti_apply_b<1>(A, b, hc, nonzero);
+    esti_apply_b<2>(A, b, hc, nonzero);
+    // upper-triangular solve, column by column from the last (Eigen's triangular_solve_vector, ColMajor)
 #pragma unroll
     for (int i = 2; i >= 0; i--) {
-      if (i < nonzero) {
-        float s = b[i];
+      if (i < nonzero && b[i] != 0.f) {
+        b[i] /= A[i][i];
 #pragma unroll
-        for (int j = i + 1; j < 3; j++) if (j < nonzero) s -= A[i][j] * c[j];
-        c[i] = s / A[i][i];
+        for (int r = 0; r < i; r++) b[r] -= b[i] * A[r][i];
       }
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       if (i < nonzero) {
-        if (perm[i] == 0) x[0] = c[i]; else if (perm[i] == 1) x[1] = c[i]; else x[2] = c[i];
+        if (perm[i] == 0) x[0] = b[i]; else if (perm[i] == 1) x[1] = b[i]; else x[2] = b[i];
       }
     }
   }
-  const float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const float n = sqrtf(x[0] * x[0] + (x[1] * x[1] + x[2] * x[2]));
   pabcd[0] = x[0] / n; pabcd[1] = x[1] / n; pabcd[2] = x[2] / n; pabcd[3] = (float)(1.0 / (double)n);
   bool ok = true;
 #pragma unroll

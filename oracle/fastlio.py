@@ -143,10 +143,10 @@ class OracleFastLio:
     """fastlio_main restated on top of OracleImuProcess + OracleLio.  Same feeding protocol as RefFastLio."""
 
     def __init__(self, ext_R=None, ext_t=None, filter_num=1, max_point_num=-1, scan_period=0.1, undistort=True, nthreads=8,
-                 backend="port", stale_neighbours=True):
+                 backend="port", stale_neighbours=True, reference_order=False):
         self.imu_proc = OracleImuProcess(ext_R, ext_t, undistort=undistort)          # laserMapping.cpp:1101-1106
         self.lio = OracleLio(nearby=74, nthreads=nthreads, backend=backend,          # NEARBY74 first, laserMapping.cpp:1062
-                             stale_neighbours=stale_neighbours)
+                             stale_neighbours=stale_neighbours, reference_order=reference_order)
         self.lio.x, self.lio.P = E.State(), np.eye(23)                               # a default-constructed esekf:
         self.lio.x.grav = np.array([E.S2_LEN, 0.0, 0.0])                             # S2() = length * e_x (S2.hpp:62-66) until IMU_init
         self.filter_num, self.max_point_num, self.scan_period = filter_num, max_point_num, scan_period

@@ -24,7 +24,8 @@ class OracleLio:
     FILTER_MAP = 0.5  # laserMapping.cpp:1028
 
     def __init__(self, nearby: int = 18, knn_exact: bool = False, expected_cells: int = 1 << 18,
-                 nthreads: int = 8, degenerate_detect: bool = True, backend: str = "port", stale_neighbours: bool = False):
+                 nthreads: int = 8, degenerate_detect: bool = True, backend: str = "port", stale_neighbours: bool = False,
+                 reference_order: bool = False):
         """backend "port": oracle/lsd_oracle.c; "reference": the compiled reference IVox +
         esti_plane (oracle/_ref) inside the same restated loop.
 
@@ -43,7 +44,9 @@ class OracleLio:
         else:
             self.map = O.OracleIvox(0.5, nearby, expected_cells)  # laserMapping.cpp:1060-1065
             self._hm, self._mi = O.port.orc_lio_hmodel, O.port.orc_map_incremental
-        self.knn_mode = (1 if knn_exact else 0) | (2 if self.stale else 0)
+        # reference_order (port backend): the five neighbours in the order IVox::GetClosestPoint leaves them in (libstdc++'s
+        # nth_element, ivox3d.h:159-164) instead of ascending (d2, id); esti_plane's fp32 solve depends on the row order.
+        self.knn_mode = (1 if knn_exact else 0) | (2 if self.stale else 0) | (4 if reference_order and not knn_exact else 0)
         self._rows = 0  # rows of the persistent neighbour table in use (stale mode): Nearest_Points.size()
         self.nthreads = nthreads
         self.degenerate_detect = degenerate_detect

@@ -116,9 +116,11 @@ static void set_nearby(OrcIvox* m, int nearby) {
     int c = nearby == 6 ? 7 : 19;
     for (int i = 0; i < c; i++) memcpy(m->nearby[i], n18[i], sizeof(int) * 3);
     m->nearby_n = c;
-  } else if (nearby == 26) {
-    for (int i = -1; i <= 1; i++) for (int j = -1; j <= 1; j++) for (int k = -1; k <= 1; k++) {
-      int* d = m->nearby[m->nearby_n++]; d[0] = i; d[1] = j; d[2] = k; }
+  } else if (nearby == 26) { /* ivox3d.h:191-198: the NEARBY18 list (in its order), then the eight corners in this order */
+    static const int corners[8][3] = {{1, 1, 1}, {-1, 1, 1}, {1, -1, 1}, {1, 1, -1}, {-1, -1, 1}, {-1, 1, -1}, {1, -1, -1}, {-1, -1, -1}};
+    for (int i = 0; i < 19; i++) memcpy(m->nearby[i], n18[i], sizeof(int) * 3);
+    for (int i = 0; i < 8; i++) memcpy(m->nearby[19 + i], corners[i], sizeof(int) * 3);
+    m->nearby_n = 27;
   } else { /* NEARBY74: 5x5x3, ivox3d.h:205-211 */
     for (int i = -2; i <= 2; i++) for (int j = -2; j <= 2; j++) for (int k = -1; k <= 1; k++) {
       int* d = m->nearby[m->nearby_n++]; d[0] = i; d[1] = j; d[2] = k; }
@@ -260,6 +262,127 @@ static int ivox_knn_one(const OrcIvox* m, const float* q, int k, double max_sq, 
   return nb;
 }
 
+/* ---- the reference's neighbour ORDER -------------------------------------------------------------------------------
+ * GetClosestPoint hands its candidates to std::nth_element twice (ivox3d.h:159-164) and KNNPointByCondition once per voxel
+ * with more than K points in range (ivox3d_node.hpp:118-123); the five neighbours reach esti_plane in the order libstdc++'s
+ * introselect leaves them in (bits/stl_algo.h: __introselect, __unguarded_partition_pivot, __move_median_to_first,
+ * __unguarded_partition, __insertion_sort, __heap_select), and esti_plane's fp32 solve depends on the row order.  What
+ * follows restates that algorithm (comparison: DistPoint::operator<, the distance alone) on the candidate sequence the
+ * reference builds: nearby_grids_ order, then the voxel's points_ order (= insertion order). */
+static inline int ref_less(const OrcCand* a, const OrcCand* b) { return a->d2 < b->d2; }
+static inline void ref_swap(OrcCand* a, OrcCand* b) { OrcCand t = *a; *a = *b; *b = t; }
+static void ref_adjust_heap(OrcCand* first, long hole, long len, OrcCand value) {   /* std::__adjust_heap + __push_heap */
+  const long top = hole;
+  long child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (ref_less(first + child, first + (child - 1))) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  long parent = (hole - 1) / 2;
+  while (hole > top && ref_less(first + parent, &value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+static void ref_heap_select(OrcCand* first, OrcCand* middle, OrcCand* last) {       /* std::__heap_select */
+  const long len = middle - first;
+  if (len >= 2)
+    for (long parent = (len - 2) / 2;; parent--) {                                  /* std::__make_heap */
+      OrcCand v = first[parent];
+      ref_adjust_heap(first, parent, len, v);
+      if (parent == 0) break;
+    }
+  for (OrcCand* i = middle; i < last; i++)
+    if (ref_less(i, first)) {                                                        /* std::__pop_heap(first, middle, i) */
+      OrcCand v = *i;
+      *i = *first;
+      ref_adjust_heap(first, 0, len, v);
+    }
+}
+static void ref_nth_element(OrcCand* first, OrcCand* nth, OrcCand* last) {          /* std::nth_element */
+  if (first == last || nth == last) return;
+  long depth = 0;
+  for (long n = last - first; n > 1; n >>= 1) depth++;                              /* std::__lg */
+  depth *= 2;
+  while (last - first > 3) {
+    if (depth == 0) {
+      ref_heap_select(first, nth + 1, last);
+      ref_swap(first, nth);
+      return;
+    }
+    depth--;
+    OrcCand* mid = first + (last - first) / 2;
+    OrcCand *a = first + 1, *b = mid, *c = last - 1;                                /* __move_median_to_first(first, a, b, c) */
+    if (ref_less(a, b)) {
+      if (ref_less(b, c)) ref_swap(first, b);
+      else if (ref_less(a, c)) ref_swap(first, c);
+      else ref_swap(first, a);
+    } else if (ref_less(a, c)) ref_swap(first, a);
+    else if (ref_less(b, c)) ref_swap(first, c);
+    else ref_swap(first, b);
+    OrcCand *lo = first + 1, *hi = last;                                             /* __unguarded_partition(first + 1, last, first) */
+    for (;;) {
+      while (ref_less(lo, first)) lo++;
+      hi--;
+      while (ref_less(first, hi)) hi--;
+      if (!(lo < hi)) break;
+      ref_swap(lo, hi);
+      lo++;
+    }
+    if (lo <= nth) first = lo; else last = lo;
+  }
+  for (OrcCand* i = first + 1; i < last; i++) {                                      /* __insertion_sort */
+    OrcCand v = *i;
+    if (ref_less(&v, first)) {
+      for (OrcCand* j = i; j > first; j--) *j = *(j - 1);
+      *first = v;
+    } else {
+      OrcCand* j = i;
+      while (ref_less(&v, j - 1)) { *j = *(j - 1); j--; }
+      *j = v;
+    }
+  }
+}
+#define ORC_REF_CAND_MAX 4096
+/* GetClosestPoint exactly as the reference runs it, order included; `best` receives min(n, k) candidates in the reference's order */
+static int ivox_knn_one_ref(const OrcIvox* m, const float* q, int k, double max_sq, OrcCand* best) {
+  int key[3]; pos2grid(m, q, key);
+  OrcCand stack_c[256];
+  OrcCand* cand = stack_c;
+  int cap = 256, n = 0;
+  for (int c = 0; c < m->nearby_n; c++) {
+    const OrcCell* cell = find_cell(m, key[0] + m->nearby[c][0], key[1] + m->nearby[c][1], key[2] + m->nearby[c][2]);
+    if (!cell) continue;
+    const int old = n;
+    if (n + cell->n > cap) {
+      const int ncap = 2 * (n + cell->n);
+      OrcCand* nc = (OrcCand*)malloc(sizeof(OrcCand) * (size_t)ncap);
+      memcpy(nc, cand, sizeof(OrcCand) * (size_t)n);
+      if (cand != stack_c) free(cand);
+      cand = nc; cap = ncap;
+    }
+    for (int j = 0; j < cell->n; j++) {
+      const float d = dist2f(q, &cell->pts[j]);
+      if ((double)d < max_sq) { OrcCand cd = {d, cell->pts[j].id, cell->pts[j].x, cell->pts[j].y, cell->pts[j].z}; cand[n++] = cd; }
+    }
+    if (n - old > k) { ref_nth_element(cand + old, cand + old + k - 1, cand + n); n = old + k; }
+  }
+  if (n > k) { ref_nth_element(cand, cand + k - 1, cand + n); n = k; }
+  if (n > 0) ref_nth_element(cand, cand, cand + n);
+  for (int j = 0; j < n; j++) best[j] = cand[j];
+  if (cand != stack_c) free(cand);
+  return n;
+}
+
 /* Exact k-NN within radius (d2 <= max_sq) by shell expansion over the same grid: equals the
  * ikd-Tree result Nearest_Search (ikd_Tree.cpp:367-397, :869-1013) whenever the reference accepts
  * it (5 found and d2[4] <= 5, laserMapping.cpp:846-847). */
@@ -289,7 +412,8 @@ static int exact_knn_one(const OrcIvox* m, const float* q, int k, double max_sq,
   return nb;
 }
 
-/* mode 0: iVox stencil (d2 < max_sq); mode 1: exact within radius (d2 <= max_sq).
+/* mode 0: iVox stencil (d2 < max_sq), canonical (d2, id) order; mode 2: the same neighbours in the reference's own order;
+ * mode 1: exact within radius (d2 <= max_sq).
  * q stride in floats; outputs [nq,k] (-1 / 0 padded), out_xyz [nq,k,3] optional. */
 void orc_knn(const OrcIvox* m, int mode, const float* q, int stride, int nq, int k, double max_sq,
              int* out_ids, float* out_d2, float* out_xyz, int* out_cnt, int nthreads) {
@@ -299,7 +423,8 @@ void orc_knn(const OrcIvox* m, int mode, const float* q, int stride, int nq, int
     OrcCand best[64];
     int kk = k > 64 ? 64 : k;
     int nb = mode == 0 ? ivox_knn_one(m, q + (size_t)stride * i, kk, max_sq, best)
-                       : exact_knn_one(m, q + (size_t)stride * i, kk, max_sq, best);
+             : mode == 2 ? ivox_knn_one_ref(m, q + (size_t)stride * i, kk, max_sq, best)     /* the reference's order */
+                         : exact_knn_one(m, q + (size_t)stride * i, kk, max_sq, best);
     out_cnt[i] = nb;
     for (int j = 0; j < k; j++) {
       out_ids[(size_t)i * k + j] = j < nb ? best[j].id : -1;
@@ -318,85 +443,132 @@ void orc_knn(const OrcIvox* m, int mode, const float* q, int stride, int nq, int
 /*     Householder/Householder.h:65-130), normalise, reject if any point is > thr off.     */
 /* ===================================================================================== */
 #define FEPS 1.1920929e-07f
-static float colnorm(const float A[5][3], int c, int r0) {
-  float s = 0.f;
-  for (int r = r0; r < 5; r++) s += A[r][c] * A[r][c];
-  return sqrtf(s);
+/* Eigen's reductions as the reference's x86-64 (SSE2, 4-float packets, no FMA) build orders them — the reference's plane
+ * coefficients are defined by that order:
+ *   fixed size 5 (a whole column; Core/Redux.h, LinearVectorizedTraversal + CompleteUnrolling): one packet of the first four
+ *     terms reduced as (t0 + t2) + (t1 + t3) (arch/SSE/PacketMath.h predux), then + t4;
+ *   run-time size n (Redux.h:243-270, expression without direct access => no alignment peeling): n >= 4: first four terms as one
+ *     packet, the rest added one by one; n < 4: left to right;
+ *   fixed size 3 without packets (DefaultTraversal + CompleteUnrolling, redux_novec_unroller): t0 + (t1 + t2). */
+static float red_dyn(const float* t, int n) {
+  if (n >= 4) {
+    float s = (t[0] + t[2]) + (t[1] + t[3]);
+    for (int i = 4; i < n; i++) s += t[i];
+    return s;
+  }
+  float s = t[0];
+  for (int i = 1; i < n; i++) s += t[i];
+  return s;
 }
-int orc_esti_plane(const float* pts, float thr, float* pabcd) {
-  float A[5][3], b[5];
-  for (int r = 0; r < 5; r++) { A[r][0] = pts[3 * r]; A[r][1] = pts[3 * r + 1]; A[r][2] = pts[3 * r + 2]; b[r] = -1.0f; }
+static float red_fix5(const float* t) { return ((t[0] + t[2]) + (t[1] + t[3])) + t[4]; }
+/* A is column-major 5x3 (A[c][r]) like Eigen's m_qr */
+static float sqn_tail(float A[3][5], int c, int r0) {   /* squared norm of A[r0..4][c] (run-time size) */
+  float t[5]; int n = 0;
+  for (int r = r0; r < 5; r++) t[n++] = A[c][r] * A[c][r];
+  return n ? red_dyn(t, n) : 0.f;
+}
+static float dot_tail(float A[3][5], int ce, const float* v, int r0) {   /* sum_{r>=r0} A[r][ce] * v[r] (run-time size) */
+  float t[5]; int n = 0;
+  for (int r = r0; r < 5; r++) t[n++] = A[ce][r] * v[r];
+  return n ? red_dyn(t, n) : 0.f;
+}
+/* the factorisation + solve of A n = b; returns nonzero pivots.  qr/hc/perm as Eigen's matrixQR() / hCoeffs() / colsPermutation() */
+static int esti_qr(const float* pts, float A[3][5], float hc[3], int perm[3], float x[3]) {
+  float b[5];
+  for (int r = 0; r < 5; r++) { A[0][r] = pts[3 * r]; A[1][r] = pts[3 * r + 1]; A[2][r] = pts[3 * r + 2]; b[r] = -1.0f; }
   const int rows = 5, cols = 3, size = 3;
-  float hc[3], nu[3], nd[3]; int perm[3] = {0, 1, 2};
-  for (int k = 0; k < cols; k++) nu[k] = nd[k] = colnorm(A, k, 0);
+  float nu[3], nd[3];
+  int trans[3];
+  for (int k = 0; k < cols; k++) {
+    float t[5];
+    for (int r = 0; r < 5; r++) t[r] = A[k][r] * A[k][r];
+    nu[k] = nd[k] = sqrtf(red_fix5(t));
+  }
   float mxn = nu[0]; if (nu[1] > mxn) mxn = nu[1]; if (nu[2] > mxn) mxn = nu[2];
-  float th_helper = (mxn * FEPS) * (mxn * FEPS) / (float)rows;
-  float downdate = sqrtf(FEPS);
+  const float th_helper = (mxn * FEPS) * (mxn * FEPS) / (float)rows;
+  const float downdate = sqrtf(FEPS);
   int nonzero = size;
   for (int k = 0; k < size; k++) {
     int big = k; float bn = nu[k];
     for (int j = k + 1; j < cols; j++) if (nu[j] > bn) { bn = nu[j]; big = j; }
     if (nonzero == size && bn * bn < th_helper * (float)(rows - k)) nonzero = k;
+    trans[k] = big;
     if (big != k) {
-      for (int r = 0; r < rows; r++) { float t = A[r][k]; A[r][k] = A[r][big]; A[r][big] = t; }
+      for (int r = 0; r < rows; r++) { float t = A[k][r]; A[k][r] = A[big][r]; A[big][r] = t; }
       float t = nu[k]; nu[k] = nu[big]; nu[big] = t;
       t = nd[k]; nd[k] = nd[big]; nd[big] = t;
-      int ti = perm[k]; perm[k] = perm[big]; perm[big] = ti;
     }
-    /* makeHouseholderInPlace on A[k..4][k] */
-    float tail = 0.f;
-    for (int r = k + 1; r < rows; r++) tail += A[r][k] * A[r][k];
-    float c0 = A[k][k], beta, tau;
-    if (tail <= 1.17549435e-38f) { tau = 0.f; beta = c0; for (int r = k + 1; r < rows; r++) A[r][k] = 0.f; }
+    /* makeHouseholderInPlace on A[k..4][k] (Householder.h:65-100) */
+    const float tail = sqn_tail(A, k, k + 1);
+    const float c0 = A[k][k];
+    float beta, tau;
+    if (tail <= 1.17549435e-38f) { tau = 0.f; beta = c0; for (int r = k + 1; r < rows; r++) A[k][r] = 0.f; }
     else {
       beta = sqrtf(c0 * c0 + tail);
       if (c0 >= 0.f) beta = -beta;
-      float den = c0 - beta;
-      for (int r = k + 1; r < rows; r++) A[r][k] = A[r][k] / den;
+      const float den = c0 - beta;
+      for (int r = k + 1; r < rows; r++) A[k][r] = A[k][r] / den;
       tau = (beta - c0) / beta;
     }
     hc[k] = tau; A[k][k] = beta;
-    /* applyHouseholderOnTheLeft to the trailing columns */
-    if (tau != 0.f)
+    /* applyHouseholderOnTheLeft to the trailing columns (Householder.h:110-135): tmp = essential^T bottom; tmp += row0;
+     * row0 -= tau tmp; bottom -= (tau essential) tmp */
+    if (tau != 0.f && k + 1 < rows) {
+      float te[5];
+      for (int r = k + 1; r < rows; r++) te[r] = tau * A[k][r];
       for (int j = k + 1; j < cols; j++) {
-        float tmp = 0.f;
-        for (int r = k + 1; r < rows; r++) tmp += A[r][k] * A[r][j];
-        tmp += A[k][j];
-        A[k][j] -= tau * tmp;
-        for (int r = k + 1; r < rows; r++) A[r][j] -= tau * A[r][k] * tmp;
+        float tmp = dot_tail(A, k, A[j], k + 1);
+        tmp += A[j][k];
+        A[j][k] -= tau * tmp;
+        for (int r = k + 1; r < rows; r++) A[j][r] -= te[r] * tmp;
       }
+    }
     for (int j = k + 1; j < cols; j++) {
       if (nu[j] != 0.f) {
-        float t = fabsf(A[k][j]) / nu[j];
+        float t = fabsf(A[j][k]) / nu[j];
         t = (1.f + t) * (1.f - t);
         if (t < 0.f) t = 0.f;
-        float rr = nu[j] / nd[j];
-        float t2 = t * rr * rr;
-        if (t2 <= downdate) { nd[j] = colnorm(A, j, k + 1); nu[j] = nd[j]; }
+        const float rr = nu[j] / nd[j];
+        const float t2 = t * (rr * rr);
+        if (t2 <= downdate) { nd[j] = sqrtf(sqn_tail(A, j, k + 1)); nu[j] = nd[j]; }
         else nu[j] *= sqrtf(t);
       }
     }
   }
-  /* solve: c = Q^T b (first `nonzero` reflectors), back-substitute, un-permute */
-  float x[3] = {0, 0, 0};
+  perm[0] = 0; perm[1] = 1; perm[2] = 2;   /* applyTranspositionOnTheRight(k, trans[k]) for k = 0.. */
+  for (int k = 0; k < size; k++) { const int t = perm[k]; perm[k] = perm[trans[k]]; perm[trans[k]] = t; }
+  /* solve (ColPivHouseholderQR.h _solve_impl): c = H_{nz-1} .. H_0 b, upper-triangular solve column by column, un-permute */
+  x[0] = x[1] = x[2] = 0.f;
   if (nonzero > 0) {
     for (int k = 0; k < nonzero; k++) {
       if (hc[k] == 0.f) continue;
-      float tmp = 0.f;
-      for (int r = k + 1; r < rows; r++) tmp += A[r][k] * b[r];
+      float tmp = dot_tail(A, k, b, k + 1);
       tmp += b[k];
       b[k] -= hc[k] * tmp;
-      for (int r = k + 1; r < rows; r++) b[r] -= hc[k] * A[r][k] * tmp;
+      for (int r = k + 1; r < rows; r++) b[r] -= (hc[k] * A[k][r]) * tmp;
     }
-    float c[3];
+    /* triangular_solve_vector<.., OnTheLeft, Upper, false, ColMajor>: from the last column up, axpy into the rows above */
     for (int i = nonzero - 1; i >= 0; i--) {
-      float s = b[i];
-      for (int j = i + 1; j < nonzero; j++) s -= A[i][j] * c[j];
-      c[i] = s / A[i][i];
+      if (b[i] != 0.f) {
+        b[i] /= A[i][i];
+        for (int r = 0; r < i; r++) b[r] -= b[i] * A[i][r];
+      }
     }
-    for (int i = 0; i < nonzero; i++) x[perm[i]] = c[i];
+    for (int i = 0; i < nonzero; i++) x[perm[i]] = b[i];
   }
-  float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  return nonzero;
+}
+void orc_esti_plane_qr(const float* pts5, int n, float* qr15, float* hc3, int* perm3, int* nzp, float* x3) {
+  for (int i = 0; i < n; i++) {
+    float A[3][5];
+    nzp[i] = esti_qr(pts5 + 15 * (size_t)i, A, hc3 + 3 * (size_t)i, perm3 + 3 * (size_t)i, x3 + 3 * (size_t)i);
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 5; r++) qr15[15 * (size_t)i + 5 * c + r] = A[c][r];
+  }
+}
+int orc_esti_plane(const float* pts, float thr, float* pabcd) {
+  float A[3][5], hc[3], x[3]; int perm[3];
+  esti_qr(pts, A, hc, perm, x);
+  const float n = sqrtf(x[0] * x[0] + (x[1] * x[1] + x[2] * x[2]));   /* fixed size 3: t0 + (t1 + t2) */
   pabcd[0] = x[0] / n; pabcd[1] = x[1] / n; pabcd[2] = x[2] / n; pabcd[3] = (float)(1.0 / (double)n);
   for (int j = 0; j < 5; j++) {
     float v = pabcd[0] * pts[3 * j] + pabcd[1] * pts[3 * j + 1] + pabcd[2] * pts[3 * j + 2] + pabcd[3];
@@ -469,7 +641,9 @@ int orc_lio_hmodel(const OrcIvox* map, const float* body, int n, const double* R
     w[3] = pb[3];
     if (search) {
       OrcCand best[5];
-      int nb = (knn_mode & 1) == 0 ? ivox_knn_one(map, w, 5, 5.0, best) : exact_knn_one(map, w, 5, 5.0, best);
+      /* knn_mode & 4: neighbours in the order the reference's GetClosestPoint leaves them in (std::nth_element) */
+      int nb = (knn_mode & 1) ? exact_knn_one(map, w, 5, 5.0, best)
+               : (knn_mode & 4) ? ivox_knn_one_ref(map, w, 5, 5.0, best) : ivox_knn_one(map, w, 5, 5.0, best);
       /* knn_mode & 2: the reference's stale list.  IVox::GetClosestPoint returns before clearing its output when no
        * candidate is in range (ivox3d.h:155-157), and Nearest_Points[i] is a file-scope vector that outlives the scan
        * (laserMapping.cpp:1273): such a point keeps the neighbours row i had the last time it found any. */

@@ -267,15 +267,17 @@ class OracleIvox:
     def num_points(self):
         return port.orc_ivox_num_points(self.h)
 
-    def knn(self, q: np.ndarray, k: int = 5, max_sq: float = 5.0, exact: bool = False, nthreads: int = 8):
-        """-> ids [nq,k] (-1 pad), d2 [nq,k] (-1 pad), xyz [nq,k,3], cnt [nq]; canonical (d2,id) order."""
+    def knn(self, q: np.ndarray, k: int = 5, max_sq: float = 5.0, exact: bool = False, nthreads: int = 8, reference_order: bool = False):
+        """-> ids [nq,k] (-1 pad), d2 [nq,k] (-1 pad), xyz [nq,k,3], cnt [nq]; canonical (d2,id) order, or with
+        reference_order the order IVox::GetClosestPoint leaves its output in (libstdc++'s nth_element, ivox3d.h:159-164)."""
         q = _c32(q)
         nq = q.shape[0]
         ids = np.empty((nq, k), np.int32)
         d2 = np.empty((nq, k), np.float32)
         xyz = np.empty((nq, k, 3), np.float32)
         cnt = np.empty(nq, np.int32)
-        port.orc_knn(self.h, 1 if exact else 0, q, q.shape[1], nq, k, max_sq, ids, d2, xyz, cnt, nthreads)
+        assert not (exact and reference_order)
+        port.orc_knn(self.h, 1 if exact else 2 if reference_order else 0, q, q.shape[1], nq, k, max_sq, ids, d2, xyz, cnt, nthreads)
         return ids, d2, xyz, cnt
 
 
@@ -362,6 +364,30 @@ def ref_esti_plane(pts5: np.ndarray, thr: float = 0.1):
     ok = np.empty(n, np.int32)
     ref.ref_esti_plane(pts5, n, thr, pabcd, ok)
     return pabcd, ok
+
+
+def _qr_call(L, name, pts5):
+    pts5 = _c32(pts5).reshape(-1, 5, 3)
+    n = pts5.shape[0]
+    qr = np.empty((n, 15), np.float32); hc = np.empty((n, 3), np.float32); perm = np.empty((n, 3), np.int32)
+    nz = np.empty(n, np.int32); x = np.empty((n, 3), np.float32)
+    fn = getattr(L, name)
+    fn.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    fn.restype = None
+    fn(pts5.ctypes.data, n, qr.ctypes.data, hc.ctypes.data, perm.ctypes.data, nz.ctypes.data, x.ctypes.data)
+    return dict(qr=qr, hcoeffs=hc, perm=perm, nonzero_pivots=nz, x=x)
+
+
+def esti_plane_qr(pts5: np.ndarray):
+    """The port's factorisation behind esti_plane with its intermediates (packed QR column-major, Householder coefficients,
+    column permutation, non-zero pivots, solution)."""
+    return _qr_call(port, "orc_esti_plane_qr", pts5)
+
+
+def ref_esti_plane_qr(pts5: np.ndarray):
+    """The same intermediates from Eigen's ColPivHouseholderQR as esti_plane instantiates it (oracle/ref_lio.cpp)."""
+    assert HAVE_REF and hasattr(ref, "ref_esti_plane_qr")
+    return _qr_call(ref, "ref_esti_plane_qr", pts5)
 
 
 def canonical_rows(ids: np.ndarray, d2: np.ndarray):

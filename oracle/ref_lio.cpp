@@ -141,6 +141,23 @@ void ref_esti_plane(const float* pts5, int n, float thr, float* pabcd, int* ok) 
 }
 
 
+// The factorisation esti_plane runs (common_lib.h:251: A.colPivHouseholderQr().solve(b)), with its intermediates exposed, so that
+// the plain-C restatement can be pinned step by step: packed QR (column-major 5x3), Householder coefficients, column permutation,
+// number of non-zero pivots, and the solution.  Same Eigen, same flags, same matrix types as esti_plane.
+void ref_esti_plane_qr(const float* pts5, int n, float* qr15, float* hc3, int* perm3, int* nzp, float* x3) {
+  for (int i = 0; i < n; i++) {
+    Eigen::Matrix<float, 5, 3> A;
+    Eigen::Matrix<float, 5, 1> b;
+    A.setZero(); b.setOnes(); b *= -1.0f;
+    for (int j = 0; j < 5; j++) for (int d = 0; d < 3; d++) A(j, d) = pts5[(i * 5 + j) * 3 + d];
+    Eigen::ColPivHouseholderQR<Eigen::Matrix<float, 5, 3>> qr = A.colPivHouseholderQr();
+    Eigen::Matrix<float, 3, 1> x = qr.solve(b);
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 5; r++) qr15[i * 15 + c * 5 + r] = qr.matrixQR()(r, c);
+    for (int c = 0; c < 3; c++) { hc3[i * 3 + c] = qr.hCoeffs()(c); perm3[i * 3 + c] = qr.colsPermutation().indices()(c); x3[i * 3 + c] = x(c); }
+    nzp[i] = (int)qr.nonzeroPivots();
+  }
+}
+
 // ---------------------------------------------------------------- full h-model on reference classes
 // Restates the loop of h_share_model_geometric (laserMapping.cpp:813-982) around the UNMODIFIED
 // reference IVox::GetClosestPoint and esti_plane<float> (Eigen ColPivHouseholderQR), with Eigen's

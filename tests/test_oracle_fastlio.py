@@ -73,11 +73,11 @@ def _sane(x, t=1.7):
     assert 0.1 * p_true[0] < x.pos[0] < 1.1 * p_true[0] and abs(x.pos[2]) < 0.02 and x.vel[0] > 0.1
 
 
-def _setup(ext, backend, stale=True):
+def _setup(ext, backend, stale=True, reference_order=False):
     from lsdreg import synth
     ext_R = synth.rot_from_rpy(0.01, -0.02, 0.03) if ext else np.eye(3)
     ext_t = np.array([0.2, -0.1, 0.15]) if ext else np.zeros(3)
-    return ext_R, ext_t, F.RefFastLio(ext_R, ext_t), F.OracleFastLio(ext_R, ext_t, backend=backend, stale_neighbours=stale)
+    return ext_R, ext_t, F.RefFastLio(ext_R, ext_t), F.OracleFastLio(ext_R, ext_t, backend=backend, stale_neighbours=stale, reference_order=reference_order)
 
 
 @pytest.mark.parametrize("ext,forced", [(False, True), (True, True), (False, False)])
@@ -147,6 +147,28 @@ def test_port_pipeline_scan_by_scan_against_the_compiled_reference(ext):
         assert d[0:3].max() < 5e-5 and d[3:6].max() < 2e-6 and d[12:15].max() < 5e-4, (f, d)
         np.testing.assert_allclose(Po, Pr, rtol=1e-2, atol=2e-7)
     print("worst one-scan deviation: pos %.1e m, rot %.1e rad, vel %.1e m/s" % (worst[0:3].max(), worst[3:6].max(), worst[12:15].max()))
+
+
+@pytest.mark.parametrize("ext", [False, True])
+def test_port_pipeline_in_the_reference_order_is_the_reference(ext):
+    """The plain-C port end to end again — its own hash-voxel map, k-NN and fp32 QR, nothing taken from the compiled reference —
+    but with the neighbours in the order IVox::GetClosestPoint leaves them in (restated libstdc++ introselect) and the plane
+    solve in Eigen's summation order: the 2.7e-5 m of the test above become 1e-12 (measured 2e-16 m / 2e-16 rad per scan),
+    effective-point counts equal on every scan.  Nothing else separates the restatement from laserMapping.cpp."""
+    ext_R, ext_t, ref, orc = _setup(ext, "port", reference_order=True)
+    for f, frame in enumerate(_stream(17, ext_R, ext_t)):
+        _feed(ref, *frame); assert ref.step()
+        _feed(orc, *frame); assert orc.step(teacher=ref.state)
+        cr, co = ref.counts(), orc.counts()
+        assert co["map_cells"] == cr["map_cells"] and co["n_down"] == cr["n_down"], (f, co, cr)
+        if f < 7:
+            continue
+        assert co["n_eff"] == cr["n_eff"] and co["degenerate"] == cr["degenerate"], (f, co, cr)
+        xr, Pr = ref.state()
+        xo, Po = orc.free_posterior
+        d = np.abs(xo.boxminus(xr))
+        assert d[0:3].max() < 1e-12 and d[3:6].max() < 1e-12 and d.max() < 1e-11, (f, d)
+        np.testing.assert_allclose(Po, Pr, rtol=0, atol=1e-11)
 
 
 def test_what_the_stale_neighbour_rows_are_worth():

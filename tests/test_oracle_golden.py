@@ -56,6 +56,69 @@ def test_esti_plane_matches_reference_golden(gold):
     assert np.abs((pa[:, :3] * ra[:, :3]).sum(1))[good].min() > 1 - 1e-5  # same normal up to sign (same sign by construction)
 
 
+def _plane_cloud(rng, n, far, noise):
+    c = rng.uniform(-far, far, (n, 1, 3)); c[:, :, 2] = rng.uniform(-5, 30, (n, 1))
+    nrm = rng.normal(size=(n, 1, 3)); nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    p = rng.uniform(-0.7, 0.7, (n, 5, 3))
+    p = p - (p * nrm).sum(2, keepdims=True) * nrm + nrm * rng.normal(scale=noise, size=(n, 5, 1))
+    return np.ascontiguousarray((c + p).astype(np.float32))
+
+
+@pytest.mark.skipif(not (O.HAVE_REF and hasattr(O.ref, "ref_esti_plane_qr")), reason="oracle/_ref not built (needs /root/reference)")
+def test_esti_plane_bit_exact_vs_compiled_reference():
+    """esti_plane<float> (common_lib.h:236-268) compiled unmodified, Eigen's ColPivHouseholderQR in the x86-64 build the reference
+    arm runs, against the plain-C restatement: EVERY bit of the plane coefficients, the accept flag, and of every intermediate of
+    the factorisation (packed QR, Householder coefficients, permutation, non-zero pivots, solution) — near the origin, 1.5 km
+    from it (where the fp32 solve is ill-conditioned and any change of summation order shows), on noisy neighbourhoods the gate
+    rejects, and on rank-deficient inputs (all-zero, coplanar through the origin, five copies of one point)."""
+    rng = np.random.default_rng(20260923)
+    sets = [_plane_cloud(rng, 40000, far, noise) for far, noise in ((1500.0, 0.01), (1500.0, 0.2), (50.0, 0.01), (1.0, 0.05))]
+    deg = _plane_cloud(rng, 3000, 20.0, 0.0)
+    deg[:1000] = 0; deg[1000:2000, :, 2] = 0; deg[2000:] = deg[2000:, :1]
+    sets.append(deg)
+    for pts in sets:
+        a, oka = O.esti_plane(pts, 0.1)
+        b, okb = O.ref_esti_plane(pts, 0.1)
+        assert (oka == okb).all()
+        assert (a.view(np.uint32) == b.view(np.uint32)).all()      # NaN patterns of the degenerate inputs included
+        qa, qb = O.esti_plane_qr(pts), O.ref_esti_plane_qr(pts)
+        for k in ("qr", "hcoeffs", "x"):
+            assert (qa[k].view(np.uint32) == qb[k].view(np.uint32)).all(), k
+        assert (qa["perm"] == qb["perm"]).all() and (qa["nonzero_pivots"] == qb["nonzero_pivots"]).all()
+
+
+@pytest.mark.skipif(not O.HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("npts,spread,mode,nearby", [(20000, 6.0, "rand", 18), (200000, 6.0, "rand", 18), (20000, 6.0, "dup", 18),
+                                                     (60000, 4.0, "lattice", 18), (100000, 5.0, "rand", 74), (100000, 5.0, "rand", 26),
+                                                     (3000, 6.0, "rand", 18), (30000, 5.0, "rand", 6)])
+def test_reference_neighbour_order_vs_compiled_ivox(npts, spread, mode, nearby):
+    """IVox::GetClosestPoint returns its neighbours in the order two std::nth_element calls (plus one per crowded voxel) leave
+    them in (ivox3d.h:159-164, ivox3d_node.hpp:118-123), and esti_plane's fp32 solve depends on that order.  The restated
+    introselect (oracle/lsd_oracle.c::ref_nth_element, libstdc++'s algorithm) on the restated candidate sequence gives the
+    compiled reference's rows id for id, position for position: sparse and crowded voxels (14 points per voxel: the per-voxel
+    truncation), fewer than k in range, exact duplicates and lattice points (distance ties), every stencil."""
+    rng = np.random.default_rng([7, npts, nearby])
+    pts = np.zeros((npts, 4), np.float32); pts[:, :3] = rng.uniform(-spread, spread, (npts, 3))
+    q = np.zeros((15000, 4), np.float32); q[:, :3] = rng.uniform(-spread, spread, (15000, 3))
+    if mode == "dup":
+        pts[npts // 2:, :3] = pts[:npts - npts // 2, :3]
+    if mode == "lattice":
+        pts[:, :3] = np.round(pts[:, :3] * 8) / 8; q[:, :3] = np.round(q[:, :3] * 4) / 4
+    po, rf = O.OracleIvox(0.5, nearby, 1 << 16), O.RefIvox(0.5, nearby)
+    step = npts // 3 + 1
+    for a in range(0, npts, step):
+        po.add(pts[a:a + step], a); rf.add(pts[a:a + step], a)
+    ids, d2, xyz, cnt = po.knn(q, 5, 5.0, reference_order=True)
+    rid, rxyz, rcnt = rf.knn(q, 5, 5.0)
+    assert (cnt == rcnt).all()
+    assert (ids == rid).all()
+    assert (xyz.view(np.uint32) == rxyz.view(np.uint32)).all()
+    cid, cd2, _, _ = po.knn(q, 5, 5.0)                       # the canonical order holds the same distances, and the same
+    assert (np.sort(cd2, 1) == np.sort(d2, 1)).all()         # ids unless two points tie for the fifth place (nth_element's call)
+    if mode == "rand":
+        assert (np.sort(cid, 1) == np.sort(ids, 1)).all()
+
+
 @pytest.mark.skipif(not O.HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
 def test_port_equals_compiled_reference_on_fresh_data():
     from lsdreg import synth
