@@ -203,6 +203,19 @@ lsd_status_t lsd_lio_set_ekf_inited(lsd_lio_t* l, int flag);
  * output); 0 (default this round) treats such a point as having no neighbours.  Either call
  * empties the rows. */
 lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
+/* The reference's neighbour ORDER.  IVox::GetClosestPoint returns its (up to) five neighbours in the order two std::nth_element
+ * calls leave them in (ivox3d.h:159-164; one more per voxel with over five points in range, ivox3d_node.hpp:118-123), and
+ * esti_plane's fp32 least-squares solve (common_lib.h:251) depends on the order of its rows: on a map a kilometre from the
+ * origin the row order alone moves plane distances by over 1e-4 m.  flag != 0: Nearest_Points rows hold the reference's
+ * neighbours in the reference's order (libstdc++'s introselect replayed on the candidate sequence the reference builds), which
+ * together with esti_plane in Eigen's summation order makes the per-scan posterior equal to laserMapping.cpp's to rounding of
+ * the double-precision sums; 0: ascending (d2, id).  iVox stencils only (the exact / ikd-Tree search returns sorted
+ * neighbours).  LSD_REF_ORDER=1 in the environment turns it on at lsd_lio_create.
+ * lsd_lio_reference_order_fallbacks: scan points since creation whose stencil held more than 256 in-range map points
+ * (those are answered in (d2, id) order).  Costs max_points x 1.5 KB of device memory for the candidate export, and a registered
+ * scan then takes 2 n ids instead of n (ids grow in the reference's insertion order). */
+lsd_status_t lsd_lio_set_reference_order(lsd_lio_t* l, int flag);
+lsd_status_t lsd_lio_reference_order_fallbacks(lsd_lio_t* l, unsigned* count);
 /* Shape of the per-scan neighbour search (no reference counterpart): 0 or 1 = one warp per scan point (the only shape;
  * the flat shapes of round 1 measured slower on B200 and were retired). */
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape);

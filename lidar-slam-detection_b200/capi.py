@@ -101,6 +101,8 @@ SIGNATURES = [
     ("lsd_lio_set_nearby", _i, [_vp, _i]),
     ("lsd_lio_set_ekf_inited", _i, [_vp, _i]),
     ("lsd_lio_set_stale_rows", _i, [_vp, _i]),
+    ("lsd_lio_set_reference_order", _i, [_vp, _i]),
+    ("lsd_lio_reference_order_fallbacks", _i, [_vp, _vp]),
     ("lsd_lio_set_knn_shape", _i, [_vp, _i]),
     ("lsd_lio_set_pdl", _i, [_vp, _i]),
     ("lsd_lio_shard_exchange_stats", _i, [_vp, C.POINTER(_d), C.POINTER(C.c_longlong)]),
@@ -898,6 +900,15 @@ class LioFrontend:
     def set_stale_rows(self, flag: bool):
         """Keep Nearest_Points[i] when a search finds nothing, as the reference does (include/lsdreg.h)."""
         check(lib.lsd_lio_set_stale_rows(self.h, int(flag)))
+
+    def set_reference_order(self, flag: bool):
+        """Nearest_Points rows in the order IVox::GetClosestPoint returns them (include/lsdreg.h)."""
+        check(lib.lsd_lio_set_reference_order(self.h, int(flag)))
+
+    def reference_order_fallbacks(self) -> int:
+        c = C.c_uint()
+        check(lib.lsd_lio_reference_order_fallbacks(self.h, C.byref(c)))
+        return c.value
 
     def set_knn_shape(self, shape: int):
         """0/1 = one warp per scan point, 3 = flat (include/lsdreg.h::lsd_lio_set_knn_shape)."""

@@ -32,6 +32,8 @@ struct WarpList {
   int* id;
   unsigned* loc;  // line * 8 + slot (1..7)
   int n;          // warp-uniform
+  unsigned char* cell = nullptr;  // optional: index of the stencil cell each candidate came from (reference-order export)
+  int clipped = 0;                // the list was cut back to its K best at some point (list_compress): no longer every candidate
 };
 constexpr int kWarpListBytes = kCandCap * 12;
 
@@ -42,11 +44,14 @@ __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0,
 #endif
 
 // ballot-compact one candidate per lane into the list
-__device__ __forceinline__ void list_push(WarpList& wl, bool valid, float d2, int id, unsigned loc) {
+// guarded (reference-order gather, which may not cut the list back): a push that would overflow is dropped and flagged
+__device__ __forceinline__ void list_push(WarpList& wl, bool valid, float d2, int id, unsigned loc, int cell = 0, bool guarded = false) {
   const unsigned m = __ballot_sync(kFull, valid);
+  if (guarded && wl.n + __popc(m) > kCandCap) { wl.clipped = 1; return; }
   if (valid) {
     const int pos = wl.n + __popc(m & lanemask_lt());
     wl.d[pos] = __float_as_uint(d2); wl.id[pos] = id; wl.loc[pos] = loc;
+    if (wl.cell) wl.cell[pos] = (unsigned char)cell;
   }
   wl.n += __popc(m);
 }
@@ -109,6 +114,7 @@ __device__ __forceinline__ void list_compress(WarpList& wl) {
   const int lane = threadIdx.x & 31;
   if (lane < nf) { wl.d[lane] = __float_as_uint(nb.d2); wl.id[lane] = nb.id; wl.loc[lane] = nb.loc; }
   wl.n = nf;
+  wl.clipped = 1;
   __syncwarp();
 }
 
@@ -117,7 +123,8 @@ __device__ __forceinline__ void list_compress(WarpList& wl) {
 // overflow levels (> 7 points in the voxel) are walked cooperatively afterwards.
 template <int K>
 __device__ __forceinline__ void warp_scan_cells(const MapView& mv, unsigned long long key, float qx, float qy, float qz,
-                                                float max_sq, bool inclusive, WarpList& wl) {
+                                                float max_sq, bool inclusive, WarpList& wl, int cell_base = 0, bool guarded = false) {
+  const int my_cell = cell_base + (int)(threadIdx.x & 31);
   unsigned long long s = 0;
   const CellLine* ln = mv.lines;
   unsigned cnt = 0;
@@ -167,7 +174,7 @@ __device__ __forceinline__ void warp_scan_cells(const MapView& mv, unsigned long
         d2 = dist2(qx, qy, qz, p[j].x, p[j].y, p[j].z);
         valid = inclusive ? (d2 <= max_sq) : (d2 < max_sq);
       }
-      list_push(wl, valid, d2, __float_as_int(p[j].w), (unsigned)(s * 8 + j + 1));
+      list_push(wl, valid, d2, __float_as_int(p[j].w), (unsigned)(s * 8 + j + 1), my_cell, guarded);
     }
   }
   if (__any_sync(kFull, cnt > 3u)) {  // phase B: sectors 2,3 of the lines that need them
@@ -183,7 +190,7 @@ __device__ __forceinline__ void warp_scan_cells(const MapView& mv, unsigned long
         d2 = dist2(qx, qy, qz, p[j - 3].x, p[j - 3].y, p[j - 3].z);
         valid = inclusive ? (d2 <= max_sq) : (d2 < max_sq);
       }
-      list_push(wl, valid, d2, __float_as_int(p[j - 3].w), (unsigned)(s * 8 + j + 1));
+      list_push(wl, valid, d2, __float_as_int(p[j - 3].w), (unsigned)(s * 8 + j + 1), my_cell, guarded);
     }
   }
   // overflow levels: voxels with more than 7 points (rare in a 0.5 m-thinned map)
@@ -215,8 +222,8 @@ __device__ __forceinline__ void warp_scan_cells(const MapView& mv, unsigned long
         d2 = dist2(qx, qy, qz, q.x, q.y, q.z);
         valid = inclusive ? (d2 <= max_sq) : (d2 < max_sq);
       }
-      if (wl.n + 7 > kCandCap) list_compress<K>(wl);
-      list_push(wl, valid, d2, __float_as_int(q.w), (unsigned)(sl * 8 + lane + 1));
+      if (!guarded && wl.n + 7 > kCandCap) list_compress<K>(wl);
+      list_push(wl, valid, d2, __float_as_int(q.w), (unsigned)(sl * 8 + lane + 1), cell_base + src, guarded);
     }
   }
 }
@@ -264,6 +271,28 @@ __device__ __forceinline__ int knn_stencil_warp(const MapView& mv, const LaneSte
     }
   }
   return list_select<K>(wl, out);
+}
+
+// The gather half of knn_stencil_warp on its own: every in-range point of the stencil cells in the list, tagged with its cell
+// (wl.cell must be set).  wl.clipped != 0 afterwards: more than kCandCap candidates, the list is incomplete.
+template <int K>
+__device__ __forceinline__ void knn_stencil_gather(const MapView& mv, const LaneStencil& ls, float qx, float qy, float qz,
+                                                   float max_sq, WarpList& wl) {
+  const int3 c = pos2grid(qx, qy, qz, mv.inv_res);
+  wl.n = 0; wl.clipped = 0;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    if (ch < ls.n_chunks) {
+      unsigned long long key = 0ull;
+      const int o = ls.off[ch];
+      if (o) {
+        const int x = c.x + (int)(signed char)(o >> 16), y = c.y + (int)(signed char)(o >> 8), z = c.z + (int)(signed char)o;
+        if (coord_ok(x, y, z)) key = pack_key(x, y, z, 0);
+      }
+      warp_scan_cells<K>(mv, key, qx, qy, qz, max_sq, false, wl, ch * 32, true);
+    }
+  }
+  __syncwarp();
 }
 
 // Exact k-NN with d2 <= max_sq by Chebyshev shells around the query's voxel; stops as soon as the

@@ -327,6 +327,115 @@ __device__ __forceinline__ RowH make_row(const LioPose& ps, double lx, double ly
 __constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},{2,2},{2,3},{2,4},{2,5},
                                            {3,3},{3,4},{3,5},{4,4},{4,5},{5,5}};
 
+// ---------------------------------------------------------------- the reference's neighbour ORDER (lsd_lio_set_reference_order)
+// IVox::GetClosestPoint leaves its (up to) five neighbours in the order std::nth_element's introselect produces on the
+// candidate sequence (ivox3d.h:159-164; per voxel with more than five in range: ivox3d_node.hpp:118-123), and esti_plane's
+// fp32 solve depends on the row order.  With the switch on, the search kernel exports EVERY in-range candidate of a query in the
+// reference's sequence (stencil cell in nearby_grids_ order, then insertion order = ascending id) as (rank of its distance
+// among the candidates, cell, location), and the plane-fit kernel — one thread per query, two thirds of the SMs idle — replays
+// libstdc++'s algorithm on the ranks (comparisons of DistPoint are comparisons of distances, hence of ranks) and fetches the
+// five winners.  oracle/lsd_oracle.c::ref_nth_element states the algorithm with its libstdc++ sources and is pinned id for id
+// to the compiled iVox.  Queries with more than kRefCap = kCandCap candidates (the search's list overflowed) fall back to the canonical (d2, id) order (counted).
+struct RefSeq { unsigned char r[kRefCap]; unsigned char ix[kRefCap]; };
+__device__ __forceinline__ void rs_swap(RefSeq& q, int a, int b) {
+  const unsigned char t = q.r[a]; q.r[a] = q.r[b]; q.r[b] = t;
+  const unsigned char u = q.ix[a]; q.ix[a] = q.ix[b]; q.ix[b] = u;
+}
+__device__ void rs_adjust_heap(RefSeq& q, int first, int hole, int len, unsigned char vr, unsigned char vi) {   // std::__adjust_heap + __push_heap
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (q.r[first + child] < q.r[first + child - 1]) child--;
+    q.r[first + hole] = q.r[first + child]; q.ix[first + hole] = q.ix[first + child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    q.r[first + hole] = q.r[first + child - 1]; q.ix[first + hole] = q.ix[first + child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && q.r[first + parent] < vr) {
+    q.r[first + hole] = q.r[first + parent]; q.ix[first + hole] = q.ix[first + parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  q.r[first + hole] = vr; q.ix[first + hole] = vi;
+}
+// std::nth_element(first, nth, last) of libstdc++ on positions of q (bits/stl_algo.h __introselect)
+__device__ void rs_nth_element(RefSeq& q, int first, int nth, int last) {
+  if (first == last || nth == last) return;
+  int depth = 0;
+  for (int n = last - first; n > 1; n >>= 1) depth++;
+  depth *= 2;
+  while (last - first > 3) {
+    if (depth == 0) {   // __heap_select(first, nth + 1, last) + iter_swap(first, nth)
+      const int middle = nth + 1, len = middle - first;
+      if (len >= 2)
+        for (int parent = (len - 2) / 2;; parent--) {
+          rs_adjust_heap(q, first, parent, len, q.r[first + parent], q.ix[first + parent]);
+          if (parent == 0) break;
+        }
+      for (int i = middle; i < last; i++)
+        if (q.r[i] < q.r[first]) {
+          const unsigned char vr = q.r[i], vi = q.ix[i];
+          q.r[i] = q.r[first]; q.ix[i] = q.ix[first];
+          rs_adjust_heap(q, first, 0, len, vr, vi);
+        }
+      rs_swap(q, first, nth);
+      return;
+    }
+    depth--;
+    const int a = first + 1, b = first + (last - first) / 2, c = last - 1;   // __move_median_to_first
+    if (q.r[a] < q.r[b]) {
+      if (q.r[b] < q.r[c]) rs_swap(q, first, b);
+      else if (q.r[a] < q.r[c]) rs_swap(q, first, c);
+      else rs_swap(q, first, a);
+    } else if (q.r[a] < q.r[c]) rs_swap(q, first, a);
+    else if (q.r[b] < q.r[c]) rs_swap(q, first, c);
+    else rs_swap(q, first, b);
+    int lo = first + 1, hi = last;                                         // __unguarded_partition
+    const unsigned char pv = q.r[first];
+    for (;;) {
+      while (q.r[lo] < pv) lo++;
+      hi--;
+      while (pv < q.r[hi]) hi--;
+      if (!(lo < hi)) break;
+      rs_swap(q, lo, hi);
+      lo++;
+    }
+    if (lo <= nth) first = lo; else last = lo;
+  }
+  for (int i = first + 1; i < last; i++) {                                  // __insertion_sort
+    const unsigned char vr = q.r[i], vi = q.ix[i];
+    int j = i;
+    if (vr < q.r[first]) {
+      for (; j > first; j--) { q.r[j] = q.r[j - 1]; q.ix[j] = q.ix[j - 1]; }
+    } else {
+      while (vr < q.r[j - 1]) { q.r[j] = q.r[j - 1]; q.ix[j] = q.ix[j - 1]; j--; }
+    }
+    q.r[j] = vr; q.ix[j] = vi;
+  }
+}
+// GetClosestPoint's ordering on the exported sequence: per-voxel truncation, the two nth_element calls.  Returns how many
+// neighbours the reference returns (<= 5); their positions in the exported sequence are q.ix[0 ..).
+__device__ int rs_reference_order(RefSeq& q, const unsigned char* __restrict__ rank, const unsigned char* __restrict__ cell, int n) {
+  int m = 0;
+  for (int a = 0; a < n;) {
+    int b = a + 1;
+    const unsigned char c = cell[a];
+    while (b < n && cell[b] == c) b++;
+    const int old = m;
+    for (int t = a; t < b; t++) { q.r[m] = rank[t]; q.ix[m] = (unsigned char)t; m++; }
+    if (m - old > 5) { rs_nth_element(q, old, old + 4, m); m = old + 5; }     // KNNPointByCondition, K = 5
+    a = b;
+  }
+  if (m > 5) { rs_nth_element(q, 0, 4, m); m = 5; }
+  if (m > 0) rs_nth_element(q, 0, 0, m);
+  return m;
+}
+
 // ---------------------------------------------------------------- K3: neighbour search for the scan
 // One warp per downsampled point (knn.cuh): body -> world, 5-NN in the hash-voxel map, neighbours
 // written as Nearest_Points[i] (laserMapping.cpp:842-852).  Kept separate from the plane fit: the
@@ -335,9 +444,11 @@ constexpr int kHmWarps = 8;
 __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, int stencil, const float4* __restrict__ body,
                                                                 const int* __restrict__ n_ptr, int cap, LioPose ps,
                                                                 float4* __restrict__ near, int* __restrict__ near_cnt,
-                                                                int keep_stale, int* __restrict__ rows, int resize_parity) {
+                                                                int keep_stale, int* __restrict__ rows, int resize_parity,
+                                                                int ref_order, RefCand rc) {
   pdl_enter();
   __shared__ __align__(16) unsigned char s_list[kHmWarps * kWarpListBytes];
+  __shared__ unsigned char s_cell[kHmWarps][kCandCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(__ldcg(n_ptr), cap);
   if (resize_parity >= 0) {
@@ -360,6 +471,7 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
   wl.id = reinterpret_cast<int*>(wl.d + kCandCap);
   wl.loc = reinterpret_cast<unsigned*>(wl.id + kCandCap);
   wl.n = 0;
+  wl.cell = ref_order ? s_cell[warp] : nullptr;
   const LaneStencil ls = lane_stencil(stencil_slot(stencil));
   // (An L2-prefetch pass over the warp's queries was measured here and removed: +9 us per launch —
   // the kernel is bound by its dependent instruction chain per query, not by the cold HBM trip.)
@@ -375,10 +487,38 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
     const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
     if (mv.shard_world > 1) {  // tile-sharded: only the owner of the query's home voxel resolves it
       const int3 hc = pos2grid(wx, wy, wz, mv.inv_res);
-      if (!shard_owns(mv, hc.x, hc.y)) { if (lane == 0) near_cnt[i] = -1; continue; }
+      if (!shard_owns(mv, hc.x, hc.y)) { if (lane == 0) { near_cnt[i] = -1; if (ref_order) rc.n[i] = 0; } continue; }
+    }
+    if (ref_order) {
+      // every in-range candidate, in the reference's sequence, for the plane-fit kernel to order (rs_reference_order)
+      knn_stencil_gather<5>(mv, ls, wx, wy, wz, 5.0f, wl);
+      const int n = wl.n;
+      if (n == 0) {                       // GetClosestPoint returns false before touching its output (ivox3d.h:155-157)
+        if (lane == 0) { rc.n[i] = 0; if (!keep_stale) near_cnt[i] = 0; }
+        if (!keep_stale && lane < 5) near[(size_t)i * 5 + lane] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        continue;
+      }
+      if (!wl.clipped && n <= kRefCap) {
+        const size_t base = (size_t)i * kRefCap;
+        for (int p = lane; p < n; p += 32) {
+          const unsigned d = wl.d[p]; const int id = wl.id[p]; const int c = wl.cell[p];
+          int pos = 0, rk = 0;
+          for (int t = 0; t < n; t++) {
+            const int ct = wl.cell[t]; const int it = wl.id[t];
+            pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
+            rk += wl.d[t] < d ? 1 : 0;
+          }
+          rc.rank[base + pos] = (unsigned char)rk; rc.cell[base + pos] = (unsigned char)c; rc.loc[base + pos] = wl.loc[p];
+        }
+        if (lane == 0) { rc.n[i] = n; near_cnt[i] = min(n, 5); }
+        __syncwarp();
+        continue;
+      }
+      if (lane == 0) atomicAdd(rc.fallbacks, 1u);   // too many candidates: canonical order below, marked final
     }
     Neighbor nb;
     const int nf = knn_search_warp<5>(mv, stencil, ls, wx, wy, wz, 5.0f, wl, nb);
+    if (ref_order && lane == 0) rc.n[i] = 0x8000;   // the row below is final
     // keep_stale: IVox::GetClosestPoint returns before clearing its output when nothing is in range (ivox3d.h:155-157)
     // and Nearest_Points outlives the scan (laserMapping.cpp:1273): row i then keeps what it held (lsd_lio_set_stale_rows)
     if (keep_stale && nf == 0) continue;
@@ -396,12 +536,13 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
 // 5 points, so the cached plane is exact.
 template <bool FIT>
 __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __restrict__ body, const int* __restrict__ n_ptr,
-                                                               int cap, LioPose ps, const float4* __restrict__ near,
+                                                               int cap, LioPose ps, float4* near,
                                                                const int* __restrict__ near_cnt, unsigned char* __restrict__ selected,
                                                                float4* __restrict__ pabcd_io, unsigned char* __restrict__ plane_ok,
                                                                float4* __restrict__ plane, float4* __restrict__ world,
                                                                double* __restrict__ partials, unsigned* __restrict__ done,
-                                                               double* __restrict__ result, double seq, ShardComm sc) {
+                                                               double* __restrict__ result, double seq, ShardComm sc,
+                                                               const CellLine* __restrict__ map_lines, int ref_order, RefCand rc) {
   pdl_enter();
   const int n_true = __ldcg(n_ptr);
   const int n = min(n_true, cap);
@@ -422,6 +563,22 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
     float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
     bool ok = false;
     if (FIT) {
+      if (ref_order) {
+        // this query's candidates, exported by the search in the reference's sequence: order them as GetClosestPoint does and
+        // write Nearest_Points[i] (rc.n == 0: nothing in range, the row keeps what it holds; bit 15: the search wrote the row)
+        const int cn = __ldcg(rc.n + i);
+        if (cn > 0 && cn < 0x8000) {
+          RefSeq q;
+          const size_t base = (size_t)i * kRefCap;
+          const int m = rs_reference_order(q, rc.rank + base, rc.cell + base, cn);
+#pragma unroll 1
+          for (int j = 0; j < 5; j++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            if (j < m) { const unsigned loc = __ldcg(rc.loc + base + q.ix[j]); v = ldg_f4(&(map_lines + (loc >> 3))->pts[(loc & 7) - 1]); }
+            near[(size_t)i * 5 + j] = v;
+          }
+        }
+      }
       if (near_cnt[i] >= 5) {  // point_selected_surf, laserMapping.cpp:847,850
         float px[5], py[5], pz[5];
 #pragma unroll
@@ -597,7 +754,7 @@ __device__ __forceinline__ float calc_dist3(float ax, float ay, float az, float 
 __global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, const float4* __restrict__ body,
                                                                   const int* __restrict__ n_ptr, int cap, LioPose ps,
                                                                   const float4* __restrict__ near, const int* __restrict__ near_cnt,
-                                                                  int ekf_inited, double fsize, int id0, int use_near,
+                                                                  int ekf_inited, double fsize, int id0, int id_t2, int use_near,
                                                                   float4* __restrict__ world, unsigned char* __restrict__ flags,
                                                                   unsigned* __restrict__ n_added, ShardComm sc, double seq,
                                                                   unsigned* __restrict__ done) {
@@ -637,7 +794,10 @@ __global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, co
       }
       flags[i] = (unsigned char)f;
       if (f) {
-        map_insert_point(mv, wx, wy, wz, id0 + i);
+        // id_t2 (reference-order mode): ids grow in the reference's insertion order — every PointToAdd of a scan before
+        // every PointNoNeedDownsample (laserMapping.cpp:571-572) — because a voxel's points_ order is part of the
+        // candidate sequence GetClosestPoint hands to nth_element
+        map_insert_point(mv, wx, wy, wz, id0 + i + (f == 2 ? id_t2 : 0));
         atomicAdd(n_added, 1u);
       }
       // halo exchange, step 1: tell every other rank what was decided for this point
@@ -662,7 +822,7 @@ __global__ void __launch_bounds__(256) lio_map_incremental_kernel(MapView mv, co
 // halo exchange, step 2: insert the points other ranks decided to add that fall in this rank's halo
 // (their world coordinates are known locally: every rank holds the whole downsampled scan).
 __global__ void __launch_bounds__(256) lio_halo_insert_kernel(MapView mv, const int* __restrict__ n_ptr, int cap,
-                                                              const float4* __restrict__ world, int id0, ShardComm sc, double seq,
+                                                              const float4* __restrict__ world, int id0, int id_t2, ShardComm sc, double seq,
                                                               unsigned* __restrict__ n_added) {
   pdl_enter();
   __shared__ int ready;
@@ -681,7 +841,7 @@ __global__ void __launch_bounds__(256) lio_halo_insert_kernel(MapView mv, const 
   if (shard_owns(mv, hc.x, hc.y) || !shard_relevant(mv, hc.x, hc.y)) return;
   const unsigned char f = *(volatile unsigned char*)(sc.flagbox[sc.rank] + i);
   if (f == 1 || f == 2) {
-    map_insert_point(mv, w.x, w.y, w.z, id0 + i);
+    map_insert_point(mv, w.x, w.y, w.z, id0 + i + (f == 2 ? id_t2 : 0));
     atomicAdd(n_added, 1u);
   }
 }
@@ -762,14 +922,15 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
     const int keep_stale = (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0;
+    const int ref_order = (l->reference_order && !l->p.knn_mode_exact && l->rc.n) ? 1 : 0;
     int resize_parity = -1;
     if (l->rows_resize_pending) { resize_parity = l->rows_parity; l->rows_parity ^= 1; l->rows_resize_pending = false; }
     const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
     LSD_LAUNCH(pdl, lio_knn_kernel, nb, kHmWarps * 32, st, l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-               keep_stale, l->d_rows, resize_parity);
+               keep_stale, l->d_rows, resize_parity, ref_order, l->rc);
     LSD_LAUNCH(pdl, lio_hmodel_kernel<true>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-               l->d_partials, l->d_done, l->d_result, seq, l->sc);
+               l->d_partials, l->d_done, l->d_result, seq, l->sc, (const CellLine*)l->map->view.lines, ref_order, l->rc);
     l->launches += 2;
   } else {
 #ifndef LSD_SIMT_EMU
@@ -787,7 +948,7 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
 #endif
     LSD_LAUNCH(pdl, lio_hmodel_kernel<false>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-               l->d_partials, l->d_done, l->d_result, seq, l->sc);
+               l->d_partials, l->d_done, l->d_result, seq, l->sc, (const CellLine*)l->map->view.lines, 0, l->rc);
     l->launches++;
   }
   LSD_CUDA(cudaGetLastError());
@@ -931,13 +1092,14 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
   const int nb = std::max(1, (l->n_bound + 255) / 256);
   const double mseq = (double)(++l->mi_seq);
   const int pdl = 0;   // its stream predecessor is the memset above, not a kernel: nothing to hide, so keep the plain launch
+  const int id_t2 = (l->reference_order && use_near) ? l->n_bound : 0;   // reference-order mode: a registered scan takes 2 x n ids (type 1 block, type 2 block)
   LSD_LAUNCH(pdl, lio_map_incremental_kernel, nb, 256, st, l->map->view, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt, l->ekf_inited,
-             (double)l->p.filter_size_map, l->next_id, use_near, l->d_world, l->d_flags, l->d_added,
+             (double)l->p.filter_size_map, l->next_id, id_t2, use_near, l->d_world, l->d_flags, l->d_added,
              l->sc, mseq, l->d_done);
   LSD_CUDA(cudaGetLastError());
   l->launches++;
   if (l->sc.world > 1) {
-    lio_halo_insert_kernel<<<nb, 256, 0, st>>>(l->map->view, l->d_n, l->p.max_points, l->d_world, l->next_id, l->sc, mseq, l->d_added);
+    lio_halo_insert_kernel<<<nb, 256, 0, st>>>(l->map->view, l->d_n, l->p.max_points, l->d_world, l->next_id, id_t2, l->sc, mseq, l->d_added);
     LSD_CUDA(cudaGetLastError());
     l->launches++;
   }
@@ -958,13 +1120,13 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
     LSD_CUDA(cudaStreamSynchronize(st));
     std::vector<float4> pts; std::vector<int> ids;
     for (int pass = 1; pass <= 2; pass++)
-      for (int i = 0; i < n; i++) if (f[i] == pass) { pts.push_back(w[i]); ids.push_back(l->next_id + i); }
+      for (int i = 0; i < n; i++) if (f[i] == pass) { pts.push_back(w[i]); ids.push_back(l->next_id + i + (pass == 2 ? id_t2 : 0)); }
     l->map->lru->distance = l->travel;
     lsd_status_t e = map_lru_touch(l->map, pts.data(), ids.data(), (int)pts.size(), 0, st);
     if (e) return e;
     wait = true;
   }
-  l->next_id += l->n_bound;
+  l->next_id += l->n_bound + id_t2;
   if (wait) {
     LSD_CUDA(cudaStreamSynchronize(st));
     if (n_added) *n_added = (int)*l->h_added;
@@ -1258,6 +1420,7 @@ lsd_status_t lsd_lio_create(lsd_lio_t** out, const lsd_lio_params_t* p) {
   // The reference's Nearest_Points rows outlive a search that finds nothing (laserMapping.cpp:1273, ivox3d.h:155-157);
   // reproducing that is what default-path parity needs (lsd_lio_set_stale_rows(l, 0) turns it off).
   l->stale_rows = true;
+  { const char* ev = getenv("LSD_REF_ORDER"); if (ev && ev[0] == '1') { lsd_status_t r = lsd_lio_set_reference_order(l, 1); if (r) { lsd_lio_destroy(l); return r; } } }
   {  // cluster-shaped reuse evaluation: opt-in, LSD_REUSE_CLUSTER="CxT" = C CTAs of T threads.  Measured slower than the
      // grid-wide kernel in every shape tried on B200 (15.6 us vs 21.5 us for 16 x 256 ... 56 us for 2 x 1024,
      // profiles/r02d_lio_probe.jsonl): the per-pass shuffle reduction that keeps it inside 64 registers costs more than the
@@ -1288,6 +1451,7 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   cudaFreeHost(l->h_result); cudaFreeHost(l->h_added);
   for (void* q : l->ipc_opened) cudaIpcCloseMemHandle(q);
   cudaFree(l->d_inbox); cudaFree(l->d_flagbox);
+  cudaFree(l->rc.n); cudaFree(l->rc.rank); cudaFree(l->rc.cell); cudaFree(l->rc.loc); cudaFree(l->rc.fallbacks);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->pev[0]) cudaEventDestroy(l->pev[0]);
@@ -1312,6 +1476,34 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   LSD_CUDA(cudaStreamSynchronize(l->stream));
   l->stale_rows = flag != 0;
   l->rows_parity = 0;
+  return LSD_OK;
+}
+// Neighbours in the reference's own order (RefCand above).  The export buffers (max_points x (4 + 6 x kRefCap) bytes) are
+// allocated by the first call that turns it on.
+lsd_status_t lsd_lio_set_reference_order(lsd_lio_t* l, int flag) {
+  if (!l) return LSD_ERR_INVALID;
+  LSD_CUDA(cudaSetDevice(l->device));
+  if (flag && !l->rc.n) {
+    const size_t mp = (size_t)l->p.max_points;
+    LSD_CUDA(cudaMalloc((void**)&l->rc.n, mp * 4));
+    LSD_CUDA(cudaMalloc((void**)&l->rc.rank, mp * kRefCap));
+    LSD_CUDA(cudaMalloc((void**)&l->rc.cell, mp * kRefCap));
+    LSD_CUDA(cudaMalloc((void**)&l->rc.loc, mp * kRefCap * 4));
+    LSD_CUDA(cudaMalloc((void**)&l->rc.fallbacks, 4));
+    LSD_CUDA(cudaMemsetAsync(l->rc.n, 0, mp * 4, l->stream));
+    LSD_CUDA(cudaMemsetAsync(l->rc.fallbacks, 0, 4, l->stream));
+    LSD_CUDA(cudaStreamSynchronize(l->stream));
+  }
+  l->reference_order = flag ? 1 : 0;
+  return LSD_OK;
+}
+// -> queries since the handle's creation whose stencil held more than kRefCap candidates (answered in canonical order)
+lsd_status_t lsd_lio_reference_order_fallbacks(lsd_lio_t* l, unsigned* count) {
+  if (!l || !count) return LSD_ERR_INVALID;
+  *count = 0;
+  if (!l->rc.fallbacks) return LSD_OK;
+  LSD_CUDA(cudaSetDevice(l->device));
+  LSD_CUDA(cudaMemcpy(count, l->rc.fallbacks, 4, cudaMemcpyDeviceToHost));
   return LSD_OK;
 }
 // Programmatic dependent launch for the scan's kernel chain (lsd_common.cuh).  Off by default; LSD_PDL=1 in the

@@ -17,6 +17,16 @@ struct ShardComm {
   double* inbox[kMaxRanks];
   unsigned char* flagbox[kMaxRanks];   // [cap] map_incremental decisions, then kMaxRanks u64 "done" sequence numbers
 };
+// Reference neighbour order (lsd_lio_set_reference_order, lio.cu): what the search kernel exports per query for the plane-fit
+// kernel to order as IVox::GetClosestPoint does.
+constexpr int kRefCap = 256;   // = kCandCap (knn.cuh): every list the search can hold can be exported
+struct RefCand {
+  int* n;                 // [cap] candidates exported (0: none in range; bit 15: the search wrote the row itself, canonical order)
+  unsigned char* rank;    // [cap][kRefCap] number of candidates strictly nearer
+  unsigned char* cell;    // [cap][kRefCap] stencil cell index
+  unsigned* loc;          // [cap][kRefCap] line * 8 + slot
+  unsigned* fallbacks;    // queries with more than kRefCap candidates (answered in canonical order)
+};
 }  // namespace lsd
 
 struct lsd_lio {
@@ -62,6 +72,8 @@ struct lsd_lio {
   int pdl = 0;                  // lsd_lio_set_pdl: launch the scan's kernels with programmatic dependent launch
   int rows_parity = 0;          // which of d_rows[0..1] the next Nearest_Points.resize publishes (the other one is read)
   bool rows_resize_pending = false;   // the loaded scan's first search still has to do Nearest_Points.resize (lio_knn_kernel)
+  int reference_order = 0;      // lsd_lio_set_reference_order: neighbours in the order IVox::GetClosestPoint returns them (lio.cu RefCand)
+  lsd::RefCand rc{};            // its export buffers (allocated by the first lsd_lio_set_reference_order(1))
   bool stale_rows = true;       // lsd_lio_set_stale_rows: keep Nearest_Points[i] when a search finds nothing, as the reference does
   double wait_timeout_s = 20.0; // wall-clock bound on the host's wait for a published reduction (wait_seq)
   unsigned char* d_selected = nullptr;  // point_selected_surf

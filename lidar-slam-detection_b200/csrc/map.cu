@@ -53,8 +53,8 @@ static void build_stencils() {
   h_stencils[0].n = 1;
   h_stencils[1].n = 7; memcpy(h_stencils[1].off, n18, 7 * 3);
   h_stencils[2].n = 19; memcpy(h_stencils[2].off, n18, 19 * 3);
-  for (int i = -1; i <= 1; i++) for (int j = -1; j <= 1; j++) for (int k = -1; k <= 1; k++) {
-    signed char* o = h_stencils[3].off[h_stencils[3].n++]; o[0] = i; o[1] = j; o[2] = k; }
+  static const signed char corners[8][3] = {{1,1,1},{-1,1,1},{1,-1,1},{1,1,-1},{-1,-1,1},{-1,1,-1},{1,-1,-1},{-1,-1,-1}};   // ivox3d.h:196-198
+  h_stencils[3].n = 27; memcpy(h_stencils[3].off, n18, 19 * 3); memcpy(h_stencils[3].off[19], corners, 8 * 3);
   for (int i = -2; i <= 2; i++) for (int j = -2; j <= 2; j++) for (int k = -1; k <= 1; k++) {
     signed char* o = h_stencils[4].off[h_stencils[4].n++]; o[0] = i; o[1] = j; o[2] = k; }
 }

@@ -153,8 +153,11 @@ class OracleLio:
         R = np.ascontiguousarray(eskf.quat_to_R(st.rot))
         R_LI = np.ascontiguousarray(eskf.quat_to_R(st.offset_R_L_I))
         self.flags = np.zeros(n, np.uint8)
+        # reference_order: ids grow in the reference's insertion order (all PointToAdd of the scan, then all PointNoNeedDownsample,
+        # laserMapping.cpp:571-572) — the product orders a voxel's points by id to rebuild the reference's candidate sequence
+        id_t2 = n if (self.knn_mode & 4) else 0
         added = self._mi(self.map.h, body, n, R, np.ascontiguousarray(st.pos), R_LI,
                                            np.ascontiguousarray(st.offset_T_L_I), self.near_xyz, self.near_cnt,
-                                           int(self.ekf_inited), self.FILTER_MAP, self.world, self.flags, self.next_id)
-        self.next_id += n
+                                           int(self.ekf_inited), self.FILTER_MAP, self.world, self.flags, self.next_id, id_t2)
+        self.next_id += n + id_t2
         return added

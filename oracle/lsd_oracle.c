@@ -738,7 +738,7 @@ static inline float calc_dist3(const float* a, const float* b) {
 }
 int orc_map_incremental(OrcIvox* map, const float* body, int n, const double* R, const double* t,
                         const double* R_LI, const double* t_LI, const float* near_xyz, const int* near_cnt,
-                        int ekf_inited, double fsize, float* world, unsigned char* flag, int id0) {
+                        int ekf_inited, double fsize, float* world, unsigned char* flag, int id0, int id_t2) {
   int added = 0;
   for (int i = 0; i < n; i++) {
     const float* pb = body + 4 * (size_t)i;
@@ -769,7 +769,7 @@ int orc_map_incremental(OrcIvox* map, const float* body, int n, const double* R,
     flag[i] = (unsigned char)f;
   }
   for (int pass = 1; pass <= 2; pass++) /* PointToAdd first, then PointNoNeedDownsample */
-    for (int i = 0; i < n; i++) if (flag[i] == pass) { int id = id0 + i; orc_ivox_add(map, world + 4 * (size_t)i, 4, 1, 0, &id); added++; }
+    for (int i = 0; i < n; i++) if (flag[i] == pass) { int id = id0 + i + (pass == 2 ? id_t2 : 0); /* id_t2 = n: ids grow in insertion order */ orc_ivox_add(map, world + 4 * (size_t)i, 4, 1, 0, &id); added++; }
   return added;
 }
 

@@ -71,7 +71,7 @@ def _load_port():
     L.orc_fitness.restype = C.c_double
     L.orc_fitness.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _d, C.c_double, C.c_double]
     L.orc_map_incremental.restype = C.c_int
-    L.orc_map_incremental.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, _f, _i, C.c_int, C.c_double, _f, _u8, C.c_int]
+    L.orc_map_incremental.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, _f, _i, C.c_int, C.c_double, _f, _u8, C.c_int, C.c_int]
     return L
 
 
@@ -103,7 +103,7 @@ def _load_ref():
         L.ref_lio_hmodel.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, C.c_int, C.c_int, _f, _i, _i, _u8,
                                      _f, _f, _d, _d, _d, _i, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_map_incremental.restype = C.c_int
-        L.ref_map_incremental.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, _f, _i, C.c_int, C.c_double, _f, _u8, C.c_int]
+        L.ref_map_incremental.argtypes = [C.c_void_p, _f, C.c_int, _d, _d, _d, _d, _f, _i, C.c_int, C.c_double, _f, _u8, C.c_int, C.c_int]
     return L
 
 

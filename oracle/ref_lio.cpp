@@ -274,7 +274,7 @@ int ref_lio_hmodel(void* hv, const float* body, int n, const double* R_, const d
 // map_incremental (laserMapping.cpp:523-576) feeding the reference IVox::AddPoints.
 int ref_map_incremental(void* hv, const float* body, int n, const double* R_, const double* t_, const double* RL_,
                         const double* tL_, const float* near_xyz, const int* near_cnt, int ekf_inited, double fsize,
-                        float* world, unsigned char* flag, int id0) {
+                        float* world, unsigned char* flag, int id0, int id_t2) {
   IVoxType* iv = static_cast<IVoxType*>(hv);
   Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>> R(R_), RL(RL_);
   Eigen::Map<const V3D> t(t_), tL(tL_);
@@ -307,6 +307,7 @@ int ref_map_incremental(void* hv, const float* body, int n, const double* R_, co
       }
     }
     flag[i] = (unsigned char)f;
+    if (f == 2 && id_t2) { PointType p2 = mk(pb, id0 + i + id_t2); p2.x = pw.x; p2.y = pw.y; p2.z = pw.z; pw = p2; }   // label only: ids in insertion order
     if (f == 1) PointToAdd.push_back(pw); else if (f == 2) PointNoNeedDownsample.push_back(pw);
   }
   iv->AddPoints(PointToAdd, 0.0);

@@ -9,17 +9,20 @@ pytestmark = pytest.mark.gpu
 POS_TOL, ROT_TOL = 1e-4, 1e-5
 
 
-def _pair(small_world, **kw):
+def _pair(small_world, reference_order=False, **kw):
     import lsdreg
     from oracle import eskf
     from oracle.lio import OracleLio
     m = small_world["map"]
     g = lsdreg.LioFrontend(map_log2_lines=20, **kw)
+    if reference_order:
+        g.set_reference_order(True)
     g.map.insert(m, 0)
     g.set_next_id(m.shape[0])
     kw.pop("eskf_literal", None)
     # stale_neighbours=True: the reference's Nearest_Points rows outlive a search that finds nothing — the product's default
-    o = OracleLio(kw.get("ivox_nearby", 18), knn_exact=bool(kw.get("knn_mode_exact", 0)), expected_cells=1 << 18, stale_neighbours=True)
+    o = OracleLio(kw.get("ivox_nearby", 18), knn_exact=bool(kw.get("knn_mode_exact", 0)), expected_cells=1 << 18, stale_neighbours=True,
+                  reference_order=reference_order)
     o.add_map_points(m)
     prior = eskf.State()
     prior.rot = eskf.R_to_quat(small_world["Rprior"])
@@ -32,8 +35,12 @@ def _rot_err(qa, qb):
     return np.linalg.norm(eskf.so3_log(eskf.quat_mul(eskf.quat_conj(qa), qb)))
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(ivox_nearby=74), dict(knn_mode_exact=1)])
+@pytest.mark.parametrize("kw", [dict(), dict(ivox_nearby=74), dict(knn_mode_exact=1), dict(reference_order=True),
+                                dict(reference_order=True, ivox_nearby=74)])
 def test_linearize_matches_oracle(small_world, kw):
+    """kw reference_order: Nearest_Points rows in the order IVox::GetClosestPoint returns them (libstdc++'s nth_element on the
+    reference's candidate sequence) — ids compared position by position against the oracle, which is pinned id for id to the
+    compiled iVox; the planes then carry the compiled esti_plane's bits."""
     from oracle import oracle as O
     g, o, prior = _pair(small_world, **kw)
     n = g.load_scan(small_world["scan"])
@@ -65,10 +72,10 @@ def test_linearize_matches_oracle(small_world, kw):
     np.testing.assert_allclose(rg2["HTH"], o.last["HTH6"], rtol=1e-10, atol=1e-9)
 
 
-@pytest.mark.parametrize("literal", [1, 0])
-def test_update_pose_parity_and_map_incremental(small_world, literal):
+@pytest.mark.parametrize("literal,ref_order", [(1, False), (0, False), (0, True)])
+def test_update_pose_parity_and_map_incremental(small_world, literal, ref_order):
     from oracle import eskf
-    g, o, prior = _pair(small_world, eskf_literal=literal)
+    g, o, prior = _pair(small_world, reference_order=ref_order, eskf_literal=literal)
     n = g.load_scan(small_world["scan"])
     body = g.get_down()
     P0 = eskf.init_P()

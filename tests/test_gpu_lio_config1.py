@@ -21,7 +21,15 @@ pytestmark = pytest.mark.gpu
 N_STEPS = 6
 
 
-def test_bench_steps_pose_parity_with_the_compiled_reference():
+@pytest.mark.parametrize("ref_order", [False, True])
+def test_bench_steps_pose_parity_with_the_compiled_reference(ref_order):
+    """ref_order (lsd_lio_set_reference_order): neighbours in the order IVox::GetClosestPoint returns them and — always —
+    esti_plane in Eigen's summation order: nothing separates the product from laserMapping.cpp any more but the order of the
+    double-precision normal-equation sums, the Schur form of the Kalman gain — 2e-16 m per scan on the same downsampled cloud,
+    tests/test_gpu_zz_sequence.py — and the voxel grid's centroids: fixed-point sums here, fp32 running sums in the restated
+    pcl::VoxelGrid the reference arm is built with (PCL is outside the reference tree), one fp32 ulp apart for half the points.
+    Bars then: effective-point counts and map sizes EQUAL, neighbour ids equal position by position, posterior within
+    1e-6 m / 1e-7 rad (measured 1.7e-7 m / 7e-9 rad)."""
     import bench
     import lsdreg
     from lsdreg import synth
@@ -36,6 +44,7 @@ def test_bench_steps_pose_parity_with_the_compiled_reference():
     assert nb != 13 or m.shape[0] > 10_000_000
     g = lsdreg.LioFrontend(map_log2_lines=25 if nb == 13 else 21, max_scan_points=131072, max_points=100000, async_map_insert=1)
     g.map.insert(m, 0); g.set_next_id(m.shape[0])
+    g.set_reference_order(ref_order)
     ref = FL.RefFastLioBench(capacity=1 << 30, threads=8)
     ref.add_map_points(m)
     port = O.OracleIvox(0.5, 18, 1 << 24 if nb == 13 else 1 << 20)
@@ -50,7 +59,7 @@ def test_bench_steps_pose_parity_with_the_compiled_reference():
             n = g.load_scan(scan)
             g.linearize(prior.to_vec(), True)
             mt = g.get_matches()
-            oi, od, _, oc = port.knn(np.ascontiguousarray(mt["world"][:, :4]), 5, 5.0)
+            oi, od, _, oc = port.knn(np.ascontiguousarray(mt["world"][:, :4]), 5, 5.0, reference_order=ref_order)
             assert (mt["cnt"] == oc).all() and (oc == 5).mean() > 0.5
             found = oc > 0                      # rows that found nothing keep what they held (empty on a first scan)
             assert (mt["idx"][found] == oi[found]).all()
@@ -59,15 +68,17 @@ def test_bench_steps_pose_parity_with_the_compiled_reference():
         xr, Pr, n_down_ref = ref.process_scan(scan, prior, P0)
         c = ref.counts()
         assert info["status"] == lsdreg.OK and info["n_down"] == n_down_ref == c["n_down"], (s, info, c)
-        assert abs(info["n_eff"] - c["n_eff"]) <= max(3, c["n_eff"] // 500), (s, info["n_eff"], c["n_eff"])
+        assert abs(info["n_eff"] - c["n_eff"]) <= (0 if ref_order else max(3, c["n_eff"] // 500)), (s, info["n_eff"], c["n_eff"])
         assert info["degenerate"] == c["degenerate"] == 0
         d = np.abs(eskf.State.from_vec(x).boxminus(xr))
         worst = np.maximum(worst, [d[0:3].max(), d[3:6].max()])
-        assert d[0:3].max() < 1e-4 and d[3:6].max() < 1e-5, (s, d[:6])
+        assert d[0:3].max() < (1e-6 if ref_order else 1e-4) and d[3:6].max() < (1e-7 if ref_order else 1e-5), (s, d[:6])
         assert np.abs(x[:3] - tgt).max() < 0.05          # and both sit on the ground truth (2 cm range noise)
         sd = np.sqrt(np.abs(np.diag(Pr)))
         assert (np.abs(P - Pr) <= 1e-3 * np.outer(sd, sd) + 1e-14).all(), s
     g.sync()
     st = g.map.stats()
-    assert abs(int(st["cells"]) - c["map_cells"]) <= 8 * N_STEPS, (st, c)     # both maps grew by the same inserts (a gate flip moves a point or two)
-    print(f"config[1] parity vs laserMapping.cpp: worst |dpos| = {worst[0]:.2e} m, |drot| = {worst[1]:.2e} rad over {N_STEPS} steps")
+    assert abs(int(st["cells"]) - c["map_cells"]) <= (0 if ref_order else 8 * N_STEPS), (st, c)     # both maps grew by the same inserts (a gate flip moves a point or two)
+    if ref_order:
+        assert g.reference_order_fallbacks() == 0
+    print(f"config[1] parity vs laserMapping.cpp (reference order {ref_order}): worst |dpos| = {worst[0]:.2e} m, |drot| = {worst[1]:.2e} rad over {N_STEPS} steps")
