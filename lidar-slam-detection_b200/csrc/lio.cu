@@ -336,35 +336,41 @@ __constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{
 // libstdc++'s algorithm on the ranks (comparisons of DistPoint are comparisons of distances, hence of ranks) and fetches the
 // five winners.  oracle/lsd_oracle.c::ref_nth_element states the algorithm with its libstdc++ sources and is pinned id for id
 // to the compiled iVox.  Queries with more than kRefCap = kCandCap candidates (the search's list overflowed) fall back to the canonical (d2, id) order (counted).
-struct RefSeq { unsigned char r[kRefCap]; unsigned char ix[kRefCap]; };
-__device__ __forceinline__ void rs_swap(RefSeq& q, int a, int b) {
-  const unsigned char t = q.r[a]; q.r[a] = q.r[b]; q.r[b] = t;
-  const unsigned char u = q.ix[a]; q.ix[a] = q.ix[b]; q.ix[b] = u;
+// The working sequence of one query: r[] = rank of the distance, ix[] = position in the exported sequence.  It lives in SHARED
+// memory (a 132-byte slice per thread of the plane-fit block, up to kSeqFast entries; the stride keeps equal indices of
+// neighbouring threads in different banks): the replay is a chain of dependent, data-dependent byte accesses, which per-thread
+// LOCAL arrays serve one 32-byte transaction per lane at a time (measured: +65 us per search evaluation).  Longer sequences
+// (rare) use local arrays.
+constexpr int kSeqFast = 64, kSeqStride = 2 * kSeqFast + 4;
+#define RS_INL __device__ __forceinline__
+RS_INL void rs_swap(unsigned char* r, unsigned char* ix, int a, int b) {
+  const unsigned char t = r[a]; r[a] = r[b]; r[b] = t;
+  const unsigned char u = ix[a]; ix[a] = ix[b]; ix[b] = u;
 }
-__device__ void rs_adjust_heap(RefSeq& q, int first, int hole, int len, unsigned char vr, unsigned char vi) {   // std::__adjust_heap + __push_heap
+RS_INL void rs_adjust_heap(unsigned char* r, unsigned char* ix, int first, int hole, int len, unsigned char vr, unsigned char vi) {   // std::__adjust_heap + __push_heap
   const int top = hole;
   int child = hole;
   while (child < (len - 1) / 2) {
     child = 2 * (child + 1);
-    if (q.r[first + child] < q.r[first + child - 1]) child--;
-    q.r[first + hole] = q.r[first + child]; q.ix[first + hole] = q.ix[first + child];
+    if (r[first + child] < r[first + child - 1]) child--;
+    r[first + hole] = r[first + child]; ix[first + hole] = ix[first + child];
     hole = child;
   }
   if ((len & 1) == 0 && child == (len - 2) / 2) {
     child = 2 * (child + 1);
-    q.r[first + hole] = q.r[first + child - 1]; q.ix[first + hole] = q.ix[first + child - 1];
+    r[first + hole] = r[first + child - 1]; ix[first + hole] = ix[first + child - 1];
     hole = child - 1;
   }
   int parent = (hole - 1) / 2;
-  while (hole > top && q.r[first + parent] < vr) {
-    q.r[first + hole] = q.r[first + parent]; q.ix[first + hole] = q.ix[first + parent];
+  while (hole > top && r[first + parent] < vr) {
+    r[first + hole] = r[first + parent]; ix[first + hole] = ix[first + parent];
     hole = parent;
     parent = (hole - 1) / 2;
   }
-  q.r[first + hole] = vr; q.ix[first + hole] = vi;
+  r[first + hole] = vr; ix[first + hole] = vi;
 }
-// std::nth_element(first, nth, last) of libstdc++ on positions of q (bits/stl_algo.h __introselect)
-__device__ void rs_nth_element(RefSeq& q, int first, int nth, int last) {
+// std::nth_element(first, nth, last) of libstdc++ on positions of the sequence (bits/stl_algo.h __introselect)
+RS_INL void rs_nth_element(unsigned char* r, unsigned char* ix, int first, int nth, int last) {
   if (first == last || nth == last) return;
   int depth = 0;
   for (int n = last - first; n > 1; n >>= 1) depth++;
@@ -374,65 +380,67 @@ __device__ void rs_nth_element(RefSeq& q, int first, int nth, int last) {
       const int middle = nth + 1, len = middle - first;
       if (len >= 2)
         for (int parent = (len - 2) / 2;; parent--) {
-          rs_adjust_heap(q, first, parent, len, q.r[first + parent], q.ix[first + parent]);
+          rs_adjust_heap(r, ix, first, parent, len, r[first + parent], ix[first + parent]);
           if (parent == 0) break;
         }
       for (int i = middle; i < last; i++)
-        if (q.r[i] < q.r[first]) {
-          const unsigned char vr = q.r[i], vi = q.ix[i];
-          q.r[i] = q.r[first]; q.ix[i] = q.ix[first];
-          rs_adjust_heap(q, first, 0, len, vr, vi);
+        if (r[i] < r[first]) {
+          const unsigned char vr = r[i], vi = ix[i];
+          r[i] = r[first]; ix[i] = ix[first];
+          rs_adjust_heap(r, ix, first, 0, len, vr, vi);
         }
-      rs_swap(q, first, nth);
+      rs_swap(r, ix, first, nth);
       return;
     }
     depth--;
     const int a = first + 1, b = first + (last - first) / 2, c = last - 1;   // __move_median_to_first
-    if (q.r[a] < q.r[b]) {
-      if (q.r[b] < q.r[c]) rs_swap(q, first, b);
-      else if (q.r[a] < q.r[c]) rs_swap(q, first, c);
-      else rs_swap(q, first, a);
-    } else if (q.r[a] < q.r[c]) rs_swap(q, first, a);
-    else if (q.r[b] < q.r[c]) rs_swap(q, first, c);
-    else rs_swap(q, first, b);
+    const unsigned char ra = r[a], rb = r[b], rc_ = r[c];
+    int med;
+    if (ra < rb) med = rb < rc_ ? b : (ra < rc_ ? c : a);
+    else med = ra < rc_ ? a : (rb < rc_ ? c : b);
+    rs_swap(r, ix, first, med);
     int lo = first + 1, hi = last;                                         // __unguarded_partition
-    const unsigned char pv = q.r[first];
+    const unsigned char pv = r[first];
     for (;;) {
-      while (q.r[lo] < pv) lo++;
+      while (r[lo] < pv) lo++;
       hi--;
-      while (pv < q.r[hi]) hi--;
+      while (pv < r[hi]) hi--;
       if (!(lo < hi)) break;
-      rs_swap(q, lo, hi);
+      rs_swap(r, ix, lo, hi);
       lo++;
     }
     if (lo <= nth) first = lo; else last = lo;
   }
   for (int i = first + 1; i < last; i++) {                                  // __insertion_sort
-    const unsigned char vr = q.r[i], vi = q.ix[i];
+    const unsigned char vr = r[i], vi = ix[i];
     int j = i;
-    if (vr < q.r[first]) {
-      for (; j > first; j--) { q.r[j] = q.r[j - 1]; q.ix[j] = q.ix[j - 1]; }
+    if (vr < r[first]) {
+      for (; j > first; j--) { r[j] = r[j - 1]; ix[j] = ix[j - 1]; }
     } else {
-      while (vr < q.r[j - 1]) { q.r[j] = q.r[j - 1]; q.ix[j] = q.ix[j - 1]; j--; }
+      while (vr < r[j - 1]) { r[j] = r[j - 1]; ix[j] = ix[j - 1]; j--; }
     }
-    q.r[j] = vr; q.ix[j] = vi;
+    r[j] = vr; ix[j] = vi;
   }
 }
-// GetClosestPoint's ordering on the exported sequence: per-voxel truncation, the two nth_element calls.  Returns how many
-// neighbours the reference returns (<= 5); their positions in the exported sequence are q.ix[0 ..).
-__device__ int rs_reference_order(RefSeq& q, const unsigned char* __restrict__ rank, const unsigned char* __restrict__ cell, int n) {
+// GetClosestPoint's ordering on the exported sequence (ck[t] = cell << 8 | rank): per-voxel truncation, the two nth_element
+// calls.  Returns how many neighbours the reference returns (<= 5); their positions in the exported sequence are ix[0 ..).
+RS_INL int rs_reference_order(unsigned char* r, unsigned char* ix, const unsigned short* __restrict__ ck, int n) {
   int m = 0;
   for (int a = 0; a < n;) {
-    int b = a + 1;
-    const unsigned char c = cell[a];
-    while (b < n && cell[b] == c) b++;
+    const unsigned short ca = __ldcg(ck + a);
     const int old = m;
-    for (int t = a; t < b; t++) { q.r[m] = rank[t]; q.ix[m] = (unsigned char)t; m++; }
-    if (m - old > 5) { rs_nth_element(q, old, old + 4, m); m = old + 5; }     // KNNPointByCondition, K = 5
+    r[m] = (unsigned char)(ca & 0xff); ix[m] = (unsigned char)a; m++;
+    int b = a + 1;
+    for (; b < n; b++) {
+      const unsigned short cb = __ldcg(ck + b);
+      if ((cb >> 8) != (ca >> 8)) break;
+      r[m] = (unsigned char)(cb & 0xff); ix[m] = (unsigned char)b; m++;
+    }
+    if (m - old > 5) { rs_nth_element(r, ix, old, old + 4, m); m = old + 5; }     // KNNPointByCondition, K = 5
     a = b;
   }
-  if (m > 5) { rs_nth_element(q, 0, 4, m); m = 5; }
-  if (m > 0) rs_nth_element(q, 0, 0, m);
+  if (m > 5) { rs_nth_element(r, ix, 0, 4, m); m = 5; }
+  if (m > 0) rs_nth_element(r, ix, 0, 0, m);
   return m;
 }
 
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
             pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
             rk += wl.d[t] < d ? 1 : 0;
           }
-          rc.rank[base + pos] = (unsigned char)rk; rc.cell[base + pos] = (unsigned char)c; rc.loc[base + pos] = wl.loc[p];
+          rc.ck[base + pos] = (unsigned short)((c << 8) | rk); rc.loc[base + pos] = wl.loc[p];
         }
         if (lane == 0) { rc.n[i] = n; near_cnt[i] = min(n, 5); }
         __syncwarp();
@@ -568,13 +576,25 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
         // write Nearest_Points[i] (rc.n == 0: nothing in range, the row keeps what it holds; bit 15: the search wrote the row)
         const int cn = __ldcg(rc.n + i);
         if (cn > 0 && cn < 0x8000) {
-          RefSeq q;
+          __shared__ unsigned char s_seq[kLioBlock * kSeqStride];
           const size_t base = (size_t)i * kRefCap;
-          const int m = rs_reference_order(q, rc.rank + base, rc.cell + base, cn);
+          unsigned char win[5];
+          int m;
+          if (cn <= kSeqFast) {
+            unsigned char* r = s_seq + threadIdx.x * kSeqStride;
+            m = rs_reference_order(r, r + kSeqFast, rc.ck + base, cn);
+#pragma unroll
+            for (int j = 0; j < 5; j++) win[j] = r[kSeqFast + j];
+          } else {
+            unsigned char lr[kRefCap], lix[kRefCap];
+            m = rs_reference_order(lr, lix, rc.ck + base, cn);
+#pragma unroll
+            for (int j = 0; j < 5; j++) win[j] = lix[j];
+          }
 #pragma unroll 1
           for (int j = 0; j < 5; j++) {
             float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            if (j < m) { const unsigned loc = __ldcg(rc.loc + base + q.ix[j]); v = ldg_f4(&(map_lines + (loc >> 3))->pts[(loc & 7) - 1]); }
+            if (j < m) { const unsigned loc = __ldcg(rc.loc + base + win[j]); v = ldg_f4(&(map_lines + (loc >> 3))->pts[(loc & 7) - 1]); }
             near[(size_t)i * 5 + j] = v;
           }
         }
@@ -1451,7 +1471,7 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   cudaFreeHost(l->h_result); cudaFreeHost(l->h_added);
   for (void* q : l->ipc_opened) cudaIpcCloseMemHandle(q);
   cudaFree(l->d_inbox); cudaFree(l->d_flagbox);
-  cudaFree(l->rc.n); cudaFree(l->rc.rank); cudaFree(l->rc.cell); cudaFree(l->rc.loc); cudaFree(l->rc.fallbacks);
+  cudaFree(l->rc.n); cudaFree(l->rc.ck); cudaFree(l->rc.loc); cudaFree(l->rc.fallbacks);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->pev[0]) cudaEventDestroy(l->pev[0]);
@@ -1486,8 +1506,7 @@ lsd_status_t lsd_lio_set_reference_order(lsd_lio_t* l, int flag) {
   if (flag && !l->rc.n) {
     const size_t mp = (size_t)l->p.max_points;
     LSD_CUDA(cudaMalloc((void**)&l->rc.n, mp * 4));
-    LSD_CUDA(cudaMalloc((void**)&l->rc.rank, mp * kRefCap));
-    LSD_CUDA(cudaMalloc((void**)&l->rc.cell, mp * kRefCap));
+    LSD_CUDA(cudaMalloc((void**)&l->rc.ck, mp * kRefCap * 2));
     LSD_CUDA(cudaMalloc((void**)&l->rc.loc, mp * kRefCap * 4));
     LSD_CUDA(cudaMalloc((void**)&l->rc.fallbacks, 4));
     LSD_CUDA(cudaMemsetAsync(l->rc.n, 0, mp * 4, l->stream));

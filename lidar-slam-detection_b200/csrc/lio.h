@@ -22,8 +22,7 @@ struct ShardComm {
 constexpr int kRefCap = 256;   // = kCandCap (knn.cuh): every list the search can hold can be exported
 struct RefCand {
   int* n;                 // [cap] candidates exported (0: none in range; bit 15: the search wrote the row itself, canonical order)
-  unsigned char* rank;    // [cap][kRefCap] number of candidates strictly nearer
-  unsigned char* cell;    // [cap][kRefCap] stencil cell index
+  unsigned short* ck;     // [cap][kRefCap] stencil cell index << 8 | number of candidates strictly nearer
   unsigned* loc;          // [cap][kRefCap] line * 8 + slot
   unsigned* fallbacks;    // queries with more than kRefCap candidates (answered in canonical order)
 };
