@@ -342,7 +342,11 @@ __constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{
 // LOCAL arrays serve one 32-byte transaction per lane at a time (measured: +65 us per search evaluation).  Longer sequences
 // (rare) use local arrays.
 constexpr int kSeqFast = 64, kSeqStride = 2 * kSeqFast + 4;
-#define RS_INL __device__ __forceinline__
+#ifdef LSD_SIMT_EMU
+#define RS_INL __device__
+#else
+#define RS_INL __device__ __noinline__   // one copy of the replay: inlined three times into a kernel it cost that kernel its registers
+#endif
 RS_INL void rs_swap(unsigned char* r, unsigned char* ix, int a, int b) {
   const unsigned char t = r[a]; r[a] = r[b]; r[b] = t;
   const unsigned char u = ix[a]; ix[a] = ix[b]; ix[b] = u;
@@ -427,12 +431,12 @@ RS_INL void rs_nth_element(unsigned char* r, unsigned char* ix, int first, int n
 RS_INL int rs_reference_order(unsigned char* r, unsigned char* ix, const unsigned short* __restrict__ ck, int n) {
   int m = 0;
   for (int a = 0; a < n;) {
-    const unsigned short ca = __ldcg(ck + a);
+    const unsigned short ca = ck[a];
     const int old = m;
     r[m] = (unsigned char)(ca & 0xff); ix[m] = (unsigned char)a; m++;
     int b = a + 1;
     for (; b < n; b++) {
-      const unsigned short cb = __ldcg(ck + b);
+      const unsigned short cb = ck[b];
       if ((cb >> 8) != (ca >> 8)) break;
       r[m] = (unsigned char)(cb & 0xff); ix[m] = (unsigned char)b; m++;
     }
@@ -537,6 +541,45 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
   }
 }
 
+// ---------------------------------------------------------------- reference order: the replay (between K3 and K4)
+// One THREAD per scan point, 64-thread blocks (every SM gets work; the plane-fit kernel stays as lean as without the switch):
+// the exported (cell, rank) sequence is copied into shared memory with independent loads, the replay runs on shared memory,
+// the five winners' coordinates are fetched and written as Nearest_Points[i].
+constexpr int kRoBlock = 64;
+__global__ void __launch_bounds__(kRoBlock) lio_ref_order_kernel(const int* __restrict__ n_ptr, int cap, RefCand rc,
+                                                                 const CellLine* __restrict__ map_lines, float4* __restrict__ near) {
+  pdl_enter();
+  __shared__ unsigned short s_ck[kRoBlock][kSeqFast + 2];
+  __shared__ unsigned char s_seq[kRoBlock * kSeqStride];
+  const int n = min(__ldcg(n_ptr), cap);
+  const int i = blockIdx.x * kRoBlock + threadIdx.x;
+  if (i >= n) return;
+  const int cn = __ldcg(rc.n + i);
+  if (cn <= 0 || cn >= 0x8000) return;     // nothing in range (the row keeps what it holds) / the search wrote the row itself
+  const size_t base = (size_t)i * kRefCap;
+  unsigned char win[5];
+  int m;
+  if (cn <= kSeqFast) {
+    unsigned short* ck = s_ck[threadIdx.x];
+    for (int t = 0; t < cn; t++) ck[t] = __ldcg(rc.ck + base + t);
+    unsigned char* r = s_seq + threadIdx.x * kSeqStride;
+    m = rs_reference_order(r, r + kSeqFast, ck, cn);
+#pragma unroll
+    for (int j = 0; j < 5; j++) win[j] = r[kSeqFast + j];
+  } else {
+    unsigned char lr[kRefCap], lix[kRefCap];
+    m = rs_reference_order(lr, lix, rc.ck + base, cn);
+#pragma unroll
+    for (int j = 0; j < 5; j++) win[j] = lix[j];
+  }
+#pragma unroll 1
+  for (int j = 0; j < 5; j++) {
+    float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (j < m) { const unsigned loc = __ldcg(rc.loc + base + win[j]); v = ldg_f4(&(map_lines + (loc >> 3))->pts[(loc & 7) - 1]); }
+    near[(size_t)i * 5 + j] = v;
+  }
+}
+
 // ---------------------------------------------------------------- K4+K5: plane fit + residual/Jacobian + reduction
 // One thread per downsampled point.  FIT: first evaluation after a search — fit the plane through
 // Nearest_Points[i] and cache it; !FIT: iterations with ekfom_data.converge == false
@@ -544,13 +587,12 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
 // 5 points, so the cached plane is exact.
 template <bool FIT>
 __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __restrict__ body, const int* __restrict__ n_ptr,
-                                                               int cap, LioPose ps, float4* near,
+                                                               int cap, LioPose ps, const float4* __restrict__ near,
                                                                const int* __restrict__ near_cnt, unsigned char* __restrict__ selected,
                                                                float4* __restrict__ pabcd_io, unsigned char* __restrict__ plane_ok,
                                                                float4* __restrict__ plane, float4* __restrict__ world,
                                                                double* __restrict__ partials, unsigned* __restrict__ done,
-                                                               double* __restrict__ result, double seq, ShardComm sc,
-                                                               const CellLine* __restrict__ map_lines, int ref_order, RefCand rc) {
+                                                               double* __restrict__ result, double seq, ShardComm sc) {
   pdl_enter();
   const int n_true = __ldcg(n_ptr);
   const int n = min(n_true, cap);
@@ -571,34 +613,6 @@ __global__ void __launch_bounds__(kLioBlock) lio_hmodel_kernel(const float4* __r
     float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
     bool ok = false;
     if (FIT) {
-      if (ref_order) {
-        // this query's candidates, exported by the search in the reference's sequence: order them as GetClosestPoint does and
-        // write Nearest_Points[i] (rc.n == 0: nothing in range, the row keeps what it holds; bit 15: the search wrote the row)
-        const int cn = __ldcg(rc.n + i);
-        if (cn > 0 && cn < 0x8000) {
-          __shared__ unsigned char s_seq[kLioBlock * kSeqStride];
-          const size_t base = (size_t)i * kRefCap;
-          unsigned char win[5];
-          int m;
-          if (cn <= kSeqFast) {
-            unsigned char* r = s_seq + threadIdx.x * kSeqStride;
-            m = rs_reference_order(r, r + kSeqFast, rc.ck + base, cn);
-#pragma unroll
-            for (int j = 0; j < 5; j++) win[j] = r[kSeqFast + j];
-          } else {
-            unsigned char lr[kRefCap], lix[kRefCap];
-            m = rs_reference_order(lr, lix, rc.ck + base, cn);
-#pragma unroll
-            for (int j = 0; j < 5; j++) win[j] = lix[j];
-          }
-#pragma unroll 1
-          for (int j = 0; j < 5; j++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            if (j < m) { const unsigned loc = __ldcg(rc.loc + base + win[j]); v = ldg_f4(&(map_lines + (loc >> 3))->pts[(loc & 7) - 1]); }
-            near[(size_t)i * 5 + j] = v;
-          }
-        }
-      }
       if (near_cnt[i] >= 5) {  // point_selected_surf, laserMapping.cpp:847,850
         float px[5], py[5], pz[5];
 #pragma unroll
@@ -948,9 +962,14 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
     const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
     LSD_LAUNCH(pdl, lio_knn_kernel, nb, kHmWarps * 32, st, l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                keep_stale, l->d_rows, resize_parity, ref_order, l->rc);
+    if (ref_order) {
+      LSD_LAUNCH(pdl, lio_ref_order_kernel, std::max(1, (l->n_bound + kRoBlock - 1) / kRoBlock), kRoBlock, st, l->d_n, l->p.max_points, l->rc,
+                 (const CellLine*)l->map->view.lines, l->d_near);
+      l->launches++;
+    }
     LSD_LAUNCH(pdl, lio_hmodel_kernel<true>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-               l->d_partials, l->d_done, l->d_result, seq, l->sc, (const CellLine*)l->map->view.lines, ref_order, l->rc);
+               l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches += 2;
   } else {
 #ifndef LSD_SIMT_EMU
@@ -968,7 +987,7 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
 #endif
     LSD_LAUNCH(pdl, lio_hmodel_kernel<false>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
-               l->d_partials, l->d_done, l->d_result, seq, l->sc, (const CellLine*)l->map->view.lines, 0, l->rc);
+               l->d_partials, l->d_done, l->d_result, seq, l->sc);
     l->launches++;
   }
   LSD_CUDA(cudaGetLastError());
