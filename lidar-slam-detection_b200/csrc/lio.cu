@@ -549,7 +549,7 @@ constexpr int kRoBlock = 64;
 __global__ void __launch_bounds__(kRoBlock) lio_ref_order_kernel(const int* __restrict__ n_ptr, int cap, RefCand rc,
                                                                  const CellLine* __restrict__ map_lines, float4* __restrict__ near) {
   pdl_enter();
-  __shared__ unsigned short s_ck[kRoBlock][kSeqFast + 2];
+  __shared__ __align__(4) unsigned short s_ck[kRoBlock][kSeqFast + 2];
   __shared__ unsigned char s_seq[kRoBlock * kSeqStride];
   const int n = min(__ldcg(n_ptr), cap);
   const int i = blockIdx.x * kRoBlock + threadIdx.x;
@@ -560,8 +560,18 @@ __global__ void __launch_bounds__(kRoBlock) lio_ref_order_kernel(const int* __re
   unsigned char win[5];
   int m;
   if (cn <= kSeqFast) {
+    // the row (<= 128 bytes of a 512-byte aligned slot) in up to eight independent 16-byte loads, then into shared memory:
+    // one L2 round trip instead of one per candidate
     unsigned short* ck = s_ck[threadIdx.x];
-    for (int t = 0; t < cn; t++) ck[t] = __ldcg(rc.ck + base + t);
+    const uint4* row = reinterpret_cast<const uint4*>(rc.ck + base);
+    const int nv = (cn * 2 + 15) >> 4;
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = k < nv ? __ldcg(row + k) : make_uint4(0u, 0u, 0u, 0u);
+    unsigned* ckw = reinterpret_cast<unsigned*>(ck);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < nv) { ckw[4 * k] = v[k].x; ckw[4 * k + 1] = v[k].y; ckw[4 * k + 2] = v[k].z; ckw[4 * k + 3] = v[k].w; }
     unsigned char* r = s_seq + threadIdx.x * kSeqStride;
     m = rs_reference_order(r, r + kSeqFast, ck, cn);
 #pragma unroll
@@ -572,12 +582,15 @@ __global__ void __launch_bounds__(kRoBlock) lio_ref_order_kernel(const int* __re
 #pragma unroll
     for (int j = 0; j < 5; j++) win[j] = lix[j];
   }
-#pragma unroll 1
-  for (int j = 0; j < 5; j++) {
-    float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-    if (j < m) { const unsigned loc = __ldcg(rc.loc + base + win[j]); v = ldg_f4(&(map_lines + (loc >> 3))->pts[(loc & 7) - 1]); }
-    near[(size_t)i * 5 + j] = v;
-  }
+  unsigned locs[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) locs[j] = j < m ? __ldcg(rc.loc + base + win[j]) : 0u;   // five independent loads, then five more
+  float4 pts[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++)
+    pts[j] = j < m ? ldg_f4(&(map_lines + (locs[j] >> 3))->pts[(locs[j] & 7) - 1]) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+#pragma unroll
+  for (int j = 0; j < 5; j++) near[(size_t)i * 5 + j] = pts[j];
 }
 
 // ---------------------------------------------------------------- K4+K5: plane fit + residual/Jacobian + reduction
