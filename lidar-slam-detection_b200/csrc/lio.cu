@@ -344,8 +344,10 @@ __constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{
 constexpr int kSeqFast = 64, kSeqStride = 2 * kSeqFast + 4;
 #ifdef LSD_SIMT_EMU
 #define RS_INL __device__
+#define RS_ONE __device__
 #else
-#define RS_INL __device__ __noinline__   // one copy of the replay: inlined three times into a kernel it cost that kernel its registers
+#define RS_INL __device__ __forceinline__
+#define RS_ONE __device__ __noinline__   // rs_nth_element: ONE copy (it has three call sites); everything inside it is inlined
 #endif
 RS_INL void rs_swap(unsigned char* r, unsigned char* ix, int a, int b) {
   const unsigned char t = r[a]; r[a] = r[b]; r[b] = t;
@@ -374,7 +376,7 @@ RS_INL void rs_adjust_heap(unsigned char* r, unsigned char* ix, int first, int h
   r[first + hole] = vr; ix[first + hole] = vi;
 }
 // std::nth_element(first, nth, last) of libstdc++ on positions of the sequence (bits/stl_algo.h __introselect)
-RS_INL void rs_nth_element(unsigned char* r, unsigned char* ix, int first, int nth, int last) {
+RS_INL void rs_nth_element_impl(unsigned char* r, unsigned char* ix, int first, int nth, int last) {
   if (first == last || nth == last) return;
   int depth = 0;
   for (int n = last - first; n > 1; n >>= 1) depth++;
@@ -426,8 +428,11 @@ RS_INL void rs_nth_element(unsigned char* r, unsigned char* ix, int first, int n
     r[j] = vr; ix[j] = vi;
   }
 }
+RS_ONE void rs_nth_element(unsigned char* r, unsigned char* ix, int first, int nth, int last) { rs_nth_element_impl(r, ix, first, nth, last); }
 // GetClosestPoint's ordering on the exported sequence (ck[t] = cell << 8 | rank): per-voxel truncation, the two nth_element
 // calls.  Returns how many neighbours the reference returns (<= 5); their positions in the exported sequence are ix[0 ..).
+// FAST: the arrays are in shared memory and the replay is inlined (two copies: LDS / STS instead of generic accesses).
+template <bool FAST>
 RS_INL int rs_reference_order(unsigned char* r, unsigned char* ix, const unsigned short* __restrict__ ck, int n) {
   int m = 0;
   for (int a = 0; a < n;) {
@@ -440,11 +445,18 @@ RS_INL int rs_reference_order(unsigned char* r, unsigned char* ix, const unsigne
       if ((cb >> 8) != (ca >> 8)) break;
       r[m] = (unsigned char)(cb & 0xff); ix[m] = (unsigned char)b; m++;
     }
-    if (m - old > 5) { rs_nth_element(r, ix, old, old + 4, m); m = old + 5; }     // KNNPointByCondition, K = 5
+    if (m - old > 5) {                                                      // KNNPointByCondition, K = 5 (crowded voxels: rare)
+      rs_nth_element(r, ix, old, old + 4, m); m = old + 5;
+    }
     a = b;
   }
-  if (m > 5) { rs_nth_element(r, ix, 0, 4, m); m = 5; }
-  if (m > 0) rs_nth_element(r, ix, 0, 0, m);
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {                                             // ivox3d.h:159-164: nth_element(.., begin + 4, ..) if more than five, then (.., begin, ..)
+    if (c == 0 && m <= 5) continue;
+    if (m == 0) break;
+    if (FAST) rs_nth_element_impl(r, ix, 0, c == 0 ? 4 : 0, m); else rs_nth_element(r, ix, 0, c == 0 ? 4 : 0, m);
+    if (c == 0) m = 5;
+  }
   return m;
 }
 
@@ -573,12 +585,12 @@ __global__ void __launch_bounds__(kRoBlock) lio_ref_order_kernel(const int* __re
     for (int k = 0; k < 8; k++)
       if (k < nv) { ckw[4 * k] = v[k].x; ckw[4 * k + 1] = v[k].y; ckw[4 * k + 2] = v[k].z; ckw[4 * k + 3] = v[k].w; }
     unsigned char* r = s_seq + threadIdx.x * kSeqStride;
-    m = rs_reference_order(r, r + kSeqFast, ck, cn);
+    m = rs_reference_order<true>(r, r + kSeqFast, ck, cn);
 #pragma unroll
     for (int j = 0; j < 5; j++) win[j] = r[kSeqFast + j];
   } else {
     unsigned char lr[kRefCap], lix[kRefCap];
-    m = rs_reference_order(lr, lix, rc.ck + base, cn);
+    m = rs_reference_order<false>(lr, lix, rc.ck + base, cn);
 #pragma unroll
     for (int j = 0; j < 5; j++) win[j] = lix[j];
   }
