@@ -460,6 +460,60 @@ RS_INL int rs_reference_order(unsigned char* r, unsigned char* ix, const unsigne
   return m;
 }
 
+// ---- the same replay, by the WARP that ran the search, for sequences of up to 32 candidates with no crowded voxel ------------
+// Position p of the working sequence lives in lane p: key = fp32 bits of the distance, src = index into the search's list.
+// A Hoare partition becomes two ballots (where the left / the right scan would stop) and a walk over their bits; its swaps are
+// disjoint, so one shuffle per register applies them all.  No divergence, no memory: ~60 warp instructions per partition
+// against ~3 k dependent per-thread instructions of the serial replay.  Returns false where libstdc++ would fall into
+// __heap_select (depth limit): the serial replay then takes the query.
+__device__ __forceinline__ bool warp_nth_element(unsigned& key, int& src, int first, int nth, int last) {
+  const int lane = threadIdx.x & 31;
+  if (first == last || nth == last) return true;
+  int depth = 2 * (31 - __clz(last - first));                                  // 2 * std::__lg(last - first)
+  while (last - first > 3) {
+    if (depth == 0) return false;
+    depth--;
+    const int a = first + 1, b = first + (last - first) / 2, c = last - 1;     // __move_median_to_first(first, a, b, c)
+    const unsigned ka = __shfl_sync(kFull, key, a), kb = __shfl_sync(kFull, key, b), kc = __shfl_sync(kFull, key, c);
+    const int med = ka < kb ? (kb < kc ? b : (ka < kc ? c : a)) : (ka < kc ? a : (kb < kc ? c : b));
+    {
+      const int sl = lane == first ? med : (lane == med ? first : lane);
+      key = __shfl_sync(kFull, key, sl); src = __shfl_sync(kFull, src, sl);
+    }
+    const unsigned pv = __shfl_sync(kFull, key, first);                       // __unguarded_partition(first + 1, last, first)
+    const bool inr = lane > first && lane < last;
+    unsigned mask_l = __ballot_sync(kFull, inr && !(key < pv));               // where "while (*lo < pivot) ++lo" stops
+    unsigned mask_r = __ballot_sync(kFull, inr && !(pv < key)) | (1u << first);   // where "while (pivot < *hi) --hi" stops (the pivot itself at the latest)
+    int lo = first + 1, hi = last, sl = lane;
+    for (;;) {
+      lo = __ffs((int)(mask_l & ~((1u << lo) - 1u))) - 1;
+      hi--;
+      hi = 31 - __clz((int)(mask_r & (hi >= 31 ? 0xffffffffu : ((2u << hi) - 1u))));
+      if (!(lo < hi)) break;
+      if (lane == lo) sl = hi; else if (lane == hi) sl = lo;                    // iter_swap(lo, hi), applied below
+      mask_l |= 1u << hi; mask_r |= 1u << lo;                                   // what the swap put there stops the other scan
+      lo++;
+    }
+    key = __shfl_sync(kFull, key, sl); src = __shfl_sync(kFull, src, sl);
+    if (lo <= nth) first = lo; else last = lo;
+  }
+  // __insertion_sort(first, last): a stable sort of at most three elements
+  const int cnt = last - first;
+  if (cnt >= 2) {
+    const unsigned k0 = __shfl_sync(kFull, key, first), k1 = __shfl_sync(kFull, key, first + 1);
+    const unsigned k2 = cnt > 2 ? __shfl_sync(kFull, key, first + 2) : 0xffffffffu;
+    const int r0 = (k1 < k0 ? 1 : 0) + (k2 < k0 ? 1 : 0);
+    const int r1 = (k0 <= k1 ? 1 : 0) + (k2 < k1 ? 1 : 0);
+    const int r2 = (k0 <= k2 ? 1 : 0) + (k1 <= k2 ? 1 : 0);
+    int sl = lane;
+    if (lane == first + r0) sl = first;
+    if (lane == first + r1) sl = first + 1;
+    if (cnt > 2 && lane == first + r2) sl = first + 2;
+    key = __shfl_sync(kFull, key, sl); src = __shfl_sync(kFull, src, sl);
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------- K3: neighbour search for the scan
 // One warp per downsampled point (knn.cuh): body -> world, 5-NN in the hash-voxel map, neighbours
 // written as Nearest_Points[i] (laserMapping.cpp:842-852).  Kept separate from the plane fit: the
@@ -473,6 +527,8 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
   pdl_enter();
   __shared__ __align__(16) unsigned char s_list[kHmWarps * kWarpListBytes];
   __shared__ unsigned char s_cell[kHmWarps][kCandCap];
+  __shared__ unsigned s_fkey[kHmWarps][32];
+  __shared__ unsigned char s_fsrc[kHmWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(__ldcg(n_ptr), cap);
   if (resize_parity >= 0) {
@@ -521,6 +577,38 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
         if (lane == 0) { rc.n[i] = 0; if (!keep_stale) near_cnt[i] = 0; }
         if (!keep_stale && lane < 5) near[(size_t)i * 5 + lane] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         continue;
+      }
+      if (!wl.clipped && n <= 32) {
+        // the warp orders the sequence itself (warp_nth_element) unless a voxel holds more than five candidates (its own
+        // nth_element + truncation, ivox3d_node.hpp:118-123) or libstdc++ would leave introselect for __heap_select
+        const unsigned d = lane < n ? wl.d[lane] : 0xffffffffu;
+        const int id = lane < n ? wl.id[lane] : 0x7fffffff;
+        const int c = lane < n ? (int)wl.cell[lane] : 255;
+        int pos = 0, same = 0;
+        for (int t = 0; t < n; t++) {
+          const int ct = wl.cell[t]; const int it = wl.id[t];
+          pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
+          same += ct == c ? 1 : 0;
+        }
+        if (!__any_sync(kFull, lane < n && same > 5)) {
+          if (lane < n) { s_fkey[warp][pos] = d; s_fsrc[warp][pos] = (unsigned char)lane; }
+          __syncwarp();
+          unsigned key = lane < n ? s_fkey[warp][lane] : 0xffffffffu;
+          int src = lane < n ? (int)s_fsrc[warp][lane] : 0;
+          __syncwarp();
+          int m = n;
+          bool done = true;
+          if (m > 5) { done = warp_nth_element(key, src, 0, 4, m); m = 5; }
+          if (done) done = warp_nth_element(key, src, 0, 0, m);
+          if (done) {
+            float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            if (lane < m) q = load_loc(mv, wl.loc[src]);
+            if (lane < 5) near[(size_t)i * 5 + lane] = q;
+            if (lane == 0) { near_cnt[i] = m; rc.n[i] = 0x8000; }               // final: nothing left for the replay kernel
+            __syncwarp();
+            continue;
+          }
+        }
       }
       if (!wl.clipped && n <= kRefCap) {
         const size_t base = (size_t)i * kRefCap;
