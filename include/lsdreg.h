@@ -212,8 +212,8 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
  * the double-precision sums; 0: ascending (d2, id).  iVox stencils only (the exact / ikd-Tree search returns sorted
  * neighbours).  LSD_REF_ORDER=1 in the environment turns it on at lsd_lio_create.
  * lsd_lio_reference_order_fallbacks: scan points since creation whose stencil held more than 256 in-range map points
- * (those are answered in (d2, id) order).  Costs max_points x 1.5 KB of device memory for the candidate export, and a registered
- * scan then takes 2 n ids instead of n (ids grow in the reference's insertion order). */
+ * (those are answered in (d2, id) order).  A registered scan takes 2 n ids instead of n while the switch is on (ids then grow
+ * in the reference's insertion order: every PointToAdd of a scan before every PointNoNeedDownsample). */
 lsd_status_t lsd_lio_set_reference_order(lsd_lio_t* l, int flag);
 lsd_status_t lsd_lio_reference_order_fallbacks(lsd_lio_t* l, unsigned* count);
 /* Shape of the per-scan neighbour search (no reference counterpart): 0 or 1 = one warp per scan point (the only shape;

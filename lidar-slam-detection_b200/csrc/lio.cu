@@ -330,18 +330,19 @@ __constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{
 // ---------------------------------------------------------------- the reference's neighbour ORDER (lsd_lio_set_reference_order)
 // IVox::GetClosestPoint leaves its (up to) five neighbours in the order std::nth_element's introselect produces on the
 // candidate sequence (ivox3d.h:159-164; per voxel with more than five in range: ivox3d_node.hpp:118-123), and esti_plane's
-// fp32 solve depends on the row order.  With the switch on, the search kernel exports EVERY in-range candidate of a query in the
-// reference's sequence (stencil cell in nearby_grids_ order, then insertion order = ascending id) as (rank of its distance
-// among the candidates, cell, location), and the plane-fit kernel — one thread per query, two thirds of the SMs idle — replays
-// libstdc++'s algorithm on the ranks (comparisons of DistPoint are comparisons of distances, hence of ranks) and fetches the
-// five winners.  oracle/lsd_oracle.c::ref_nth_element states the algorithm with its libstdc++ sources and is pinned id for id
-// to the compiled iVox.  Queries with more than kRefCap = kCandCap candidates (the search's list overflowed) fall back to the canonical (d2, id) order (counted).
-// The working sequence of one query: r[] = rank of the distance, ix[] = position in the exported sequence.  It lives in SHARED
-// memory (a 132-byte slice per thread of the plane-fit block, up to kSeqFast entries; the stride keeps equal indices of
-// neighbouring threads in different banks): the replay is a chain of dependent, data-dependent byte accesses, which per-thread
-// LOCAL arrays serve one 32-byte transaction per lane at a time (measured: +65 us per search evaluation).  Longer sequences
-// (rare) use local arrays.
-constexpr int kSeqFast = 64, kSeqStride = 2 * kSeqFast + 4;
+// fp32 solve depends on the row order.  With the switch on, the search keeps EVERY in-range candidate of a query, puts them in
+// the reference's sequence (stencil cell in nearby_grids_ order, then insertion order = ascending id) and replays libstdc++'s
+// algorithm on the distances (DistPoint::operator< compares nothing else): warp_nth_element below for up to 32 candidates — the
+// case that matters: 11 on average, 29 at most on the benchmark map — and rs_reference_order, the algorithm as written, run by
+// lane 0 on shared memory, for longer sequences (NEARBY74 in the first second of a run, crowded maps) and where introselect
+// would leave for __heap_select.  oracle/lsd_oracle.c::ref_nth_element states the algorithm with its libstdc++ sources and is
+// pinned id for id to the compiled iVox.  A query whose candidates overflow the search's list (kCandCap = 256) is answered in
+// the canonical (d2, id) order and counted (lsd_lio_reference_order_fallbacks).
+//
+// History of where the replay ran (B200, per search evaluation, 12 k queries): one thread per query on per-thread local arrays
+// inside the plane-fit kernel +65 us; on shared memory but inlined three times +135 us (it took that kernel's registers); its
+// own 64-thread-block kernel +31 us, with batched global loads +27 us — a chain of ~3 k dependent instructions per thread,
+// one warp per scheduler, nothing to hide latency behind; by the search's own warp, below, see DESIGN.md section 6.
 #ifdef LSD_SIMT_EMU
 #define RS_INL __device__
 #define RS_ONE __device__
@@ -523,12 +524,14 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
                                                                 const int* __restrict__ n_ptr, int cap, LioPose ps,
                                                                 float4* __restrict__ near, int* __restrict__ near_cnt,
                                                                 int keep_stale, int* __restrict__ rows, int resize_parity,
-                                                                int ref_order, RefCand rc) {
+                                                                int ref_order, unsigned* __restrict__ ref_fallbacks) {
   pdl_enter();
   __shared__ __align__(16) unsigned char s_list[kHmWarps * kWarpListBytes];
   __shared__ unsigned char s_cell[kHmWarps][kCandCap];
   __shared__ unsigned s_fkey[kHmWarps][32];
-  __shared__ unsigned char s_fsrc[kHmWarps][32];
+  __shared__ unsigned char s_fsrc[kHmWarps][32], s_fcell[kHmWarps][32];
+  __shared__ unsigned short s_sck[kHmWarps][kCandCap];                                        // the serial replay's arrays
+  __shared__ unsigned char s_sr[kHmWarps][kCandCap], s_six[kHmWarps][kCandCap], s_sp[kHmWarps][kCandCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(__ldcg(n_ptr), cap);
   if (resize_parity >= 0) {
@@ -567,70 +570,90 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
     const float wz = (float)(ps.R[6] * lx + ps.R[7] * ly + ps.R[8] * lz + ps.t[2]);
     if (mv.shard_world > 1) {  // tile-sharded: only the owner of the query's home voxel resolves it
       const int3 hc = pos2grid(wx, wy, wz, mv.inv_res);
-      if (!shard_owns(mv, hc.x, hc.y)) { if (lane == 0) { near_cnt[i] = -1; if (ref_order) rc.n[i] = 0; } continue; }
+      if (!shard_owns(mv, hc.x, hc.y)) { if (lane == 0) near_cnt[i] = -1; continue; }
     }
     if (ref_order) {
-      // every in-range candidate, in the reference's sequence, for the plane-fit kernel to order (rs_reference_order)
+      // every in-range candidate, then the reference's order on them: warp_nth_element for up to 32, the serial replay else
       knn_stencil_gather<5>(mv, ls, wx, wy, wz, 5.0f, wl);
       const int n = wl.n;
       if (n == 0) {                       // GetClosestPoint returns false before touching its output (ivox3d.h:155-157)
-        if (lane == 0) { rc.n[i] = 0; if (!keep_stale) near_cnt[i] = 0; }
-        if (!keep_stale && lane < 5) near[(size_t)i * 5 + lane] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (!keep_stale) { if (lane == 0) near_cnt[i] = 0; if (lane < 5) near[(size_t)i * 5 + lane] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); }
         continue;
       }
-      if (!wl.clipped && n <= 32) {
-        // the warp orders the sequence itself (warp_nth_element) unless a voxel holds more than five candidates (its own
-        // nth_element + truncation, ivox3d_node.hpp:118-123) or libstdc++ would leave introselect for __heap_select
-        const unsigned d = lane < n ? wl.d[lane] : 0xffffffffu;
-        const int id = lane < n ? wl.id[lane] : 0x7fffffff;
-        const int c = lane < n ? (int)wl.cell[lane] : 255;
-        int pos = 0, same = 0;
-        for (int t = 0; t < n; t++) {
-          const int ct = wl.cell[t]; const int it = wl.id[t];
-          pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
-          same += ct == c ? 1 : 0;
-        }
-        if (!__any_sync(kFull, lane < n && same > 5)) {
-          if (lane < n) { s_fkey[warp][pos] = d; s_fsrc[warp][pos] = (unsigned char)lane; }
-          __syncwarp();
-          unsigned key = lane < n ? s_fkey[warp][lane] : 0xffffffffu;
-          int src = lane < n ? (int)s_fsrc[warp][lane] : 0;
-          __syncwarp();
-          int m = n;
-          bool done = true;
-          if (m > 5) { done = warp_nth_element(key, src, 0, 4, m); m = 5; }
-          if (done) done = warp_nth_element(key, src, 0, 0, m);
-          if (done) {
-            float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            if (lane < m) q = load_loc(mv, wl.loc[src]);
-            if (lane < 5) near[(size_t)i * 5 + lane] = q;
-            if (lane == 0) { near_cnt[i] = m; rc.n[i] = 0x8000; }               // final: nothing left for the replay kernel
-            __syncwarp();
-            continue;
-          }
-        }
-      }
-      if (!wl.clipped && n <= kRefCap) {
-        const size_t base = (size_t)i * kRefCap;
-        for (int p = lane; p < n; p += 32) {
-          const unsigned d = wl.d[p]; const int id = wl.id[p]; const int c = wl.cell[p];
-          int pos = 0, rk = 0;
+      if (!wl.clipped) {
+        int m = -1, src = 0;              // m >= 0: lanes j < m hold in `src` the list index of the j-th neighbour
+        if (n <= 32) {
+          // the reference's sequence: stencil cell in nearby_grids_ order, then the voxel's insertion order (= ascending id)
+          const unsigned d = lane < n ? wl.d[lane] : 0xffffffffu;
+          const int id = lane < n ? wl.id[lane] : 0x7fffffff;
+          const int c = lane < n ? (int)wl.cell[lane] : 255;
+          int pos = 0;
           for (int t = 0; t < n; t++) {
             const int ct = wl.cell[t]; const int it = wl.id[t];
             pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
-            rk += wl.d[t] < d ? 1 : 0;
           }
-          rc.ck[base + pos] = (unsigned short)((c << 8) | rk); rc.loc[base + pos] = wl.loc[p];
+          if (lane < n) { s_fkey[warp][pos] = d; s_fsrc[warp][pos] = (unsigned char)lane; s_fcell[warp][pos] = (unsigned char)c; }
+          __syncwarp();
+          unsigned key = lane < n ? s_fkey[warp][lane] : 0xffffffffu;
+          src = lane < n ? (int)s_fsrc[warp][lane] : 0;
+          int cellv = lane < n ? (int)s_fcell[warp][lane] : 256 + lane;
+          __syncwarp();
+          m = n;
+          bool ok = true;
+          for (;;) {     // KNNPointByCondition: a voxel with more than five candidates keeps nth_element's first five (ivox3d_node.hpp:118-123)
+            const int prev = __shfl_up_sync(kFull, cellv, 1);
+            const unsigned starts = __ballot_sync(kFull, lane < m && (lane == 0 || cellv != prev));
+            const int start = 31 - __clz((int)(starts & (lane >= 31 ? 0xffffffffu : ((2u << lane) - 1u))));
+            const unsigned above = lane >= 31 ? 0u : (starts & ~((2u << lane) - 1u));
+            const int end = above ? __ffs((int)above) - 1 : m;
+            const unsigned crowded = __ballot_sync(kFull, lane < m && lane == start && end - start > 5);
+            if (!crowded) break;
+            const int ra = __ffs((int)crowded) - 1;
+            const int rb = __shfl_sync(kFull, end, ra);
+            if (!warp_nth_element(key, src, ra, ra + 4, rb)) { ok = false; break; }
+            const int drop = rb - (ra + 5);
+            const int from = lane < ra + 5 ? lane : lane + drop;
+            const unsigned k2 = __shfl_sync(kFull, key, from & 31); const int s2 = __shfl_sync(kFull, src, from & 31);
+            const int c2 = __shfl_sync(kFull, cellv, from & 31);
+            m -= drop;
+            key = lane < m ? k2 : 0xffffffffu; src = s2; cellv = lane < m ? c2 : 256 + lane;
+          }
+          if (ok && m > 5) { ok = warp_nth_element(key, src, 0, 4, m); m = 5; }       // ivox3d.h:159-162
+          if (ok) ok = warp_nth_element(key, src, 0, 0, m);                            // ivox3d.h:164
+          if (!ok) m = -1;
         }
-        if (lane == 0) { rc.n[i] = n; near_cnt[i] = min(n, 5); }
+        if (m < 0) {
+          // more than 32 candidates (NEARBY74, crowded maps) or introselect's depth limit: lane 0 replays libstdc++ serially
+          unsigned short* ck = s_sck[warp]; unsigned char* sr = s_sr[warp]; unsigned char* six = s_six[warp]; unsigned char* sp = s_sp[warp];
+          for (int p = lane; p < n; p += 32) {
+            const unsigned d = wl.d[p]; const int id = wl.id[p]; const int c = wl.cell[p];
+            int pos = 0, rk = 0;
+            for (int t = 0; t < n; t++) {
+              const int ct = wl.cell[t]; const int it = wl.id[t];
+              pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
+              rk += wl.d[t] < d ? 1 : 0;
+            }
+            ck[pos] = (unsigned short)((c << 8) | rk); sp[pos] = (unsigned char)p;
+          }
+          __syncwarp();
+          int mm = 0;
+          if (lane == 0) mm = rs_reference_order<false>(sr, six, ck, n);
+          m = __shfl_sync(kFull, mm, 0);
+          __syncwarp();
+          src = lane < m ? (int)sp[six[lane]] : 0;
+          __syncwarp();
+        }
+        float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (lane < m) q = load_loc(mv, wl.loc[src]);
+        if (lane < 5) near[(size_t)i * 5 + lane] = q;
+        if (lane == 0) near_cnt[i] = m;
         __syncwarp();
         continue;
       }
-      if (lane == 0) atomicAdd(rc.fallbacks, 1u);   // too many candidates: canonical order below, marked final
+      if (lane == 0) atomicAdd(ref_fallbacks, 1u);   // more candidates than the list holds: canonical order below
     }
     Neighbor nb;
     const int nf = knn_search_warp<5>(mv, stencil, ls, wx, wy, wz, 5.0f, wl, nb);
-    if (ref_order && lane == 0) rc.n[i] = 0x8000;   // the row below is final
     // keep_stale: IVox::GetClosestPoint returns before clearing its output when nothing is in range (ivox3d.h:155-157)
     // and Nearest_Points outlives the scan (laserMapping.cpp:1273): row i then keeps what it held (lsd_lio_set_stale_rows)
     if (keep_stale && nf == 0) continue;
@@ -639,58 +662,6 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
     if (lane < 5) near[(size_t)i * 5 + lane] = q;
     if (lane == 0) near_cnt[i] = nf;
   }
-}
-
-// ---------------------------------------------------------------- reference order: the replay (between K3 and K4)
-// One THREAD per scan point, 64-thread blocks (every SM gets work; the plane-fit kernel stays as lean as without the switch):
-// the exported (cell, rank) sequence is copied into shared memory with independent loads, the replay runs on shared memory,
-// the five winners' coordinates are fetched and written as Nearest_Points[i].
-constexpr int kRoBlock = 64;
-__global__ void __launch_bounds__(kRoBlock) lio_ref_order_kernel(const int* __restrict__ n_ptr, int cap, RefCand rc,
-                                                                 const CellLine* __restrict__ map_lines, float4* __restrict__ near) {
-  pdl_enter();
-  __shared__ __align__(4) unsigned short s_ck[kRoBlock][kSeqFast + 2];
-  __shared__ unsigned char s_seq[kRoBlock * kSeqStride];
-  const int n = min(__ldcg(n_ptr), cap);
-  const int i = blockIdx.x * kRoBlock + threadIdx.x;
-  if (i >= n) return;
-  const int cn = __ldcg(rc.n + i);
-  if (cn <= 0 || cn >= 0x8000) return;     // nothing in range (the row keeps what it holds) / the search wrote the row itself
-  const size_t base = (size_t)i * kRefCap;
-  unsigned char win[5];
-  int m;
-  if (cn <= kSeqFast) {
-    // the row (<= 128 bytes of a 512-byte aligned slot) in up to eight independent 16-byte loads, then into shared memory:
-    // one L2 round trip instead of one per candidate
-    unsigned short* ck = s_ck[threadIdx.x];
-    const uint4* row = reinterpret_cast<const uint4*>(rc.ck + base);
-    const int nv = (cn * 2 + 15) >> 4;
-    uint4 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = k < nv ? __ldcg(row + k) : make_uint4(0u, 0u, 0u, 0u);
-    unsigned* ckw = reinterpret_cast<unsigned*>(ck);
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (k < nv) { ckw[4 * k] = v[k].x; ckw[4 * k + 1] = v[k].y; ckw[4 * k + 2] = v[k].z; ckw[4 * k + 3] = v[k].w; }
-    unsigned char* r = s_seq + threadIdx.x * kSeqStride;
-    m = rs_reference_order<true>(r, r + kSeqFast, ck, cn);
-#pragma unroll
-    for (int j = 0; j < 5; j++) win[j] = r[kSeqFast + j];
-  } else {
-    unsigned char lr[kRefCap], lix[kRefCap];
-    m = rs_reference_order<false>(lr, lix, rc.ck + base, cn);
-#pragma unroll
-    for (int j = 0; j < 5; j++) win[j] = lix[j];
-  }
-  unsigned locs[5];
-#pragma unroll
-  for (int j = 0; j < 5; j++) locs[j] = j < m ? __ldcg(rc.loc + base + win[j]) : 0u;   // five independent loads, then five more
-  float4 pts[5];
-#pragma unroll
-  for (int j = 0; j < 5; j++)
-    pts[j] = j < m ? ldg_f4(&(map_lines + (locs[j] >> 3))->pts[(locs[j] & 7) - 1]) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-#pragma unroll
-  for (int j = 0; j < 5; j++) near[(size_t)i * 5 + j] = pts[j];
 }
 
 // ---------------------------------------------------------------- K4+K5: plane fit + residual/Jacobian + reduction
@@ -1069,17 +1040,12 @@ lsd_status_t lio_linearize(lsd_lio* l, const double* x, bool search, double* HTH
   ProfScope prof(l, search ? 0 : 1);
   if (search) {
     const int keep_stale = (l->stale_rows && !l->p.knn_mode_exact && l->map->view.shard_world <= 1) ? 1 : 0;
-    const int ref_order = (l->reference_order && !l->p.knn_mode_exact && l->rc.n) ? 1 : 0;
+    const int ref_order = (l->reference_order && !l->p.knn_mode_exact && l->d_ref_fallbacks) ? 1 : 0;
     int resize_parity = -1;
     if (l->rows_resize_pending) { resize_parity = l->rows_parity; l->rows_parity ^= 1; l->rows_resize_pending = false; }
     const int nb = std::max(1, std::min((l->n_bound + kHmWarps - 1) / kHmWarps, l->max_search_blocks));
     LSD_LAUNCH(pdl, lio_knn_kernel, nb, kHmWarps * 32, st, l->map->view, stencil, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
-               keep_stale, l->d_rows, resize_parity, ref_order, l->rc);
-    if (ref_order) {
-      LSD_LAUNCH(pdl, lio_ref_order_kernel, std::max(1, (l->n_bound + kRoBlock - 1) / kRoBlock), kRoBlock, st, l->d_n, l->p.max_points, l->rc,
-                 (const CellLine*)l->map->view.lines, l->d_near);
-      l->launches++;
-    }
+               keep_stale, l->d_rows, resize_parity, ref_order, l->d_ref_fallbacks);
     LSD_LAUNCH(pdl, lio_hmodel_kernel<true>, grid_for(l->n_bound), kLioBlock, st, l->d_body, l->d_n, l->p.max_points, ps, l->d_near, l->d_near_cnt,
                l->d_selected, l->d_pabcd, l->d_plane_ok, l->d_plane, l->d_world,
                l->d_partials, l->d_done, l->d_result, seq, l->sc);
@@ -1603,7 +1569,7 @@ lsd_status_t lsd_lio_destroy(lsd_lio_t* l) {
   cudaFreeHost(l->h_result); cudaFreeHost(l->h_added);
   for (void* q : l->ipc_opened) cudaIpcCloseMemHandle(q);
   cudaFree(l->d_inbox); cudaFree(l->d_flagbox);
-  cudaFree(l->rc.n); cudaFree(l->rc.ck); cudaFree(l->rc.loc); cudaFree(l->rc.fallbacks);
+  cudaFree(l->d_ref_fallbacks);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->pev[0]) cudaEventDestroy(l->pev[0]);
@@ -1630,31 +1596,25 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag) {
   l->rows_parity = 0;
   return LSD_OK;
 }
-// Neighbours in the reference's own order (RefCand above).  The export buffers (max_points x (4 + 6 x kRefCap) bytes) are
-// allocated by the first call that turns it on.
+// Neighbours in the reference's own order (warp_nth_element / rs_reference_order above).
 lsd_status_t lsd_lio_set_reference_order(lsd_lio_t* l, int flag) {
   if (!l) return LSD_ERR_INVALID;
   LSD_CUDA(cudaSetDevice(l->device));
-  if (flag && !l->rc.n) {
-    const size_t mp = (size_t)l->p.max_points;
-    LSD_CUDA(cudaMalloc((void**)&l->rc.n, mp * 4));
-    LSD_CUDA(cudaMalloc((void**)&l->rc.ck, mp * kRefCap * 2));
-    LSD_CUDA(cudaMalloc((void**)&l->rc.loc, mp * kRefCap * 4));
-    LSD_CUDA(cudaMalloc((void**)&l->rc.fallbacks, 4));
-    LSD_CUDA(cudaMemsetAsync(l->rc.n, 0, mp * 4, l->stream));
-    LSD_CUDA(cudaMemsetAsync(l->rc.fallbacks, 0, 4, l->stream));
+  if (flag && !l->d_ref_fallbacks) {
+    LSD_CUDA(cudaMalloc((void**)&l->d_ref_fallbacks, 4));
+    LSD_CUDA(cudaMemsetAsync(l->d_ref_fallbacks, 0, 4, l->stream));
     LSD_CUDA(cudaStreamSynchronize(l->stream));
   }
   l->reference_order = flag ? 1 : 0;
   return LSD_OK;
 }
-// -> queries since the handle's creation whose stencil held more than kRefCap candidates (answered in canonical order)
+// -> queries since the handle's creation whose candidates overflowed the search's list (answered in canonical order)
 lsd_status_t lsd_lio_reference_order_fallbacks(lsd_lio_t* l, unsigned* count) {
   if (!l || !count) return LSD_ERR_INVALID;
   *count = 0;
-  if (!l->rc.fallbacks) return LSD_OK;
+  if (!l->d_ref_fallbacks) return LSD_OK;
   LSD_CUDA(cudaSetDevice(l->device));
-  LSD_CUDA(cudaMemcpy(count, l->rc.fallbacks, 4, cudaMemcpyDeviceToHost));
+  LSD_CUDA(cudaMemcpy(count, l->d_ref_fallbacks, 4, cudaMemcpyDeviceToHost));
   return LSD_OK;
 }
 // Programmatic dependent launch for the scan's kernel chain (lsd_common.cuh).  Off by default; LSD_PDL=1 in the

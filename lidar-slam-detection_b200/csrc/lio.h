@@ -17,15 +17,6 @@ struct ShardComm {
   double* inbox[kMaxRanks];
   unsigned char* flagbox[kMaxRanks];   // [cap] map_incremental decisions, then kMaxRanks u64 "done" sequence numbers
 };
-// Reference neighbour order (lsd_lio_set_reference_order, lio.cu): what the search kernel exports per query for the plane-fit
-// kernel to order as IVox::GetClosestPoint does.
-constexpr int kRefCap = 256;   // = kCandCap (knn.cuh): every list the search can hold can be exported
-struct RefCand {
-  int* n;                 // [cap] candidates exported (0: none in range; bit 15: the search wrote the row itself, canonical order)
-  unsigned short* ck;     // [cap][kRefCap] stencil cell index << 8 | number of candidates strictly nearer
-  unsigned* loc;          // [cap][kRefCap] line * 8 + slot
-  unsigned* fallbacks;    // queries with more than kRefCap candidates (answered in canonical order)
-};
 }  // namespace lsd
 
 struct lsd_lio {
@@ -72,7 +63,7 @@ struct lsd_lio {
   int rows_parity = 0;          // which of d_rows[0..1] the next Nearest_Points.resize publishes (the other one is read)
   bool rows_resize_pending = false;   // the loaded scan's first search still has to do Nearest_Points.resize (lio_knn_kernel)
   int reference_order = 0;      // lsd_lio_set_reference_order: neighbours in the order IVox::GetClosestPoint returns them (lio.cu RefCand)
-  lsd::RefCand rc{};            // its export buffers (allocated by the first lsd_lio_set_reference_order(1))
+  unsigned* d_ref_fallbacks = nullptr;   // its counter of queries answered in (d2, id) order (the search's list overflowed)
   bool stale_rows = true;       // lsd_lio_set_stale_rows: keep Nearest_Points[i] when a search finds nothing, as the reference does
   double wait_timeout_s = 20.0; // wall-clock bound on the host's wait for a published reduction (wait_seq)
   unsigned char* d_selected = nullptr;  // point_selected_surf

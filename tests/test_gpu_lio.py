@@ -288,3 +288,45 @@ def test_reference_order_on_crowded_voxels(per_voxel, nearby):
     assert (np.sort(mt["idx"], 1) == np.sort(ids, 1)).all(1).mean() > 0.995   # and even those hold the same neighbours up to ties at the fifth place
     if per_voxel == 30:
         assert fb > 0
+
+
+def test_reference_order_truncates_crowded_voxels_in_short_sequences():
+    """A sparse map (well under 32 candidates per query: the warp-cooperative replay) with clusters of 7-12 points packed into
+    single voxels: KNNPointByCondition's per-voxel nth_element + truncation (ivox3d_node.hpp:118-123) inside the warp path,
+    including two crowded voxels in one stencil and exact duplicates inside a cluster."""
+    import lsdreg
+    from oracle import eskf
+    from oracle import oracle as O
+    rng = np.random.default_rng(77)
+    side = 8.0
+    base = np.zeros((3000, 4), np.float32)
+    base[:, 0:2] = rng.uniform(-side, side, (3000, 2)); base[:, 2] = rng.uniform(-0.6, 0.6, 3000)
+    centres = (np.floor(rng.uniform(-side + 1, side - 1, (120, 3)) * [1, 1, 0.1] / 0.5) * 0.5 + 0.25).astype(np.float32)
+    centres[60:] = centres[:60] + np.float32([0.5, 0, 0])                  # pairs of neighbouring crowded voxels
+    clusters = []
+    for c in centres:
+        k = int(rng.integers(7, 13))
+        pts = c + rng.uniform(-0.2, 0.2, (k, 3)).astype(np.float32)
+        pts[1] = pts[0]                                                     # a duplicate: a tie inside the voxel
+        clusters.append(pts)
+    cl = np.concatenate(clusters)
+    m = np.concatenate([base, np.concatenate([cl, np.zeros((cl.shape[0], 1), np.float32)], 1)])
+    m = np.ascontiguousarray(m[rng.permutation(m.shape[0])])
+    g = lsdreg.LioFrontend(map_log2_lines=16, ivox_nearby=18, max_points=20000)
+    g.set_reference_order(True)
+    po = O.OracleIvox(0.5, 18, 1 << 14)
+    for a in range(0, m.shape[0], 1500):
+        g.map.insert(np.ascontiguousarray(m[a:a + 1500]), a); po.add(np.ascontiguousarray(m[a:a + 1500]), a)
+    q = np.zeros((4000, 4), np.float32)
+    q[:2000, :3] = centres[rng.integers(0, 120, 2000)] + rng.uniform(-0.7, 0.7, (2000, 3)).astype(np.float32)
+    q[2000:, 0:2] = rng.uniform(-side, side, (2000, 2)); q[2000:, 2] = rng.uniform(-1, 1, 2000)
+    assert g.load_scan(q, downsample=False) == 4000
+    g.linearize(eskf.State().to_vec(), True)
+    mt = g.get_matches()
+    qq = np.ascontiguousarray(mt["world"][:, :4])
+    ids, d2, xyz, cnt = po.knn(qq, 5, 5.0, reference_order=True)
+    allc = po.knn(qq, 64, 5.0)[3]
+    assert (allc <= 32).mean() > 0.6 and (allc > 5).mean() > 0.5            # most queries take the warp path, the rest the serial replay
+    assert g.reference_order_fallbacks() == 0
+    assert (mt["cnt"] == cnt).all()
+    assert (mt["idx"] == ids).all()
