@@ -501,7 +501,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knn-batch", action="store_true")
     ap.add_argument("--no-shard-leg", action="store_true", help="N>1: skip the tile-sharded leg (replicas only)")
-    ap.add_argument("--no-reference-order-leg", action="store_true", help="N=1: skip the extra leg with lsd_lio_set_reference_order on")
+    ap.add_argument("--no-reference-order-leg", action="store_true", help="N=1: skip the extra leg with lsd_lio_set_reference_order off (sorted rows)")
     ap.add_argument("--sweep-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--streams", type=int, default=4, help="extra leg (N=1): this many independent scan streams, each with "
                     "its own map replica and handle, registered concurrently on the one GPU (0/1 = skip)")
@@ -691,21 +691,21 @@ def main():
     if world == 1 and args.streams > 1:
         multi_stream = run_streams(torch, lsdreg, local, m, R["steps_a"], R["dev_scans"], W, K, args.streams, prior_vec, P0)
 
-    # ---------------- the same K steps with the neighbours in the reference's own order (lsd_lio_set_reference_order): what
-    # exactness against laserMapping.cpp costs.  Reported beside the headline, never instead of it.
+    # ---------------- the same K steps with Nearest_Points sorted by distance instead of in the reference's own order
+    # (lsd_lio_set_reference_order(0)): what exactness against laserMapping.cpp costs.  Reported beside the headline.
     ref_order_leg = None
     if world == 1 and not args.no_reference_order_leg:
         h = lsdreg.LioFrontend(map_log2_lines=25, max_scan_points=131072, max_points=100000, async_map_insert=1)
         h.map.insert(m, 0)
         h.set_next_id(m.shape[0])
-        h.set_reference_order(True)
+        h.set_reference_order(False)
         wall_r, infos_r, poses_r = run_steps(h, R["steps_a"], R["dev_scans"], W, prefetch=True)
         ref_order_leg = {"value": K / wall_r, "unit": "scans/s", "ms_per_step": 1e3 * wall_r / K,
                          "device_ms_per_step": float(np.sum([i["gpu_ms"] for i in infos_r])) / K,
-                         "vs_this_lines_value": (K / wall_r) / R["value"], "fallbacks": h.reference_order_fallbacks(),
+                         "vs_this_lines_value": (K / wall_r) / R["value"],
                          "pos_err_max_m": max(i["pos_err"] for i in infos_r), "poses": poses_r,
-                         "what": "lsd_lio_set_reference_order(1): Nearest_Points rows in the order IVox::GetClosestPoint returns them (libstdc++'s "
-                                 "nth_element replayed on the reference's candidate sequence); fallbacks = scan points with more candidates than the search's list holds"}
+                         "what": "lsd_lio_set_reference_order(0): Nearest_Points rows in ascending (d2, id) order instead of the order "
+                                 "IVox::GetClosestPoint returns them in (the default, which the headline runs)"}
         h.close()
 
     if rank != 0:
@@ -804,7 +804,8 @@ def main():
                         "pipeline_vg": os.environ.get("LSD_PIPELINE_VG", "1")[:1] != "0",   # voxel grid of scan s+1 on the copy stream under scan s (default on)
                         "pdl": os.environ.get("LSD_PDL", "0")[:1] == "1",                   # programmatic dependent launch (opt-in)
                         "stale_rows": True,
-                        "reference_order": os.environ.get("LSD_REF_ORDER", "0")[:1] == "1",   # neighbours in the reference's own order (opt-in; the `reference_order` leg measures it)
+                        "reference_order": os.environ.get("LSD_REF_ORDER", "1")[:1] != "0",   # neighbours in the reference's own order (default; the `sorted_order` leg measures the alternative)
+                        "reference_order_fallbacks": lio.reference_order_fallbacks(),
                         "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream; "
                                   "step_ms = host wall time of each lsd_lio_scan call (what the caller waits for)"},
         "device_ms_per_step": 1e3 * R["dev_s"] / K,
@@ -825,7 +826,7 @@ def main():
         "kernels_ms": {k: (v["ms"] / max(v["count"], 1)) for k, v in prof.items()},
         "knn_batch": knn_batch and finish_knn_batch(knn_batch, bytes_per_query, peak),
         "multi_stream": multi_stream,
-        "reference_order": ({k: v for k, v in ref_order_leg.items() if k != "poses"} if ref_order_leg else None),
+        "sorted_order": ({k: v for k, v in ref_order_leg.items() if k != "poses"} if ref_order_leg else None),
         "cpu_baseline": cpu, "clocks": R["clocks"], "map_build_s": R["build_s"],
         "pos_err_max_m": float(np.max([i["pos_err"] for i in infos_a])),
     }

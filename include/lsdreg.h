@@ -209,8 +209,9 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
  * origin the row order alone moves plane distances by over 1e-4 m.  flag != 0: Nearest_Points rows hold the reference's
  * neighbours in the reference's order (libstdc++'s introselect replayed on the candidate sequence the reference builds), which
  * together with esti_plane in Eigen's summation order makes the per-scan posterior equal to laserMapping.cpp's to rounding of
- * the double-precision sums; 0: ascending (d2, id).  iVox stencils only (the exact / ikd-Tree search returns sorted
- * neighbours).  LSD_REF_ORDER=1 in the environment turns it on at lsd_lio_create.
+ * the double-precision sums — the DEFAULT; 0: ascending (d2, id), 9 % more scans/s, posterior ~4e-5 m from the reference's.
+ * iVox stencils only (the exact / ikd-Tree search returns sorted neighbours).  LSD_REF_ORDER=0 in the environment turns it off
+ * at lsd_lio_create.
  * lsd_lio_reference_order_fallbacks: scan points since creation whose stencil held more than 256 in-range map points
  * (those are answered in (d2, id) order).  A registered scan takes 2 n ids instead of n while the switch is on (ids then grow
  * in the reference's insertion order: every PointToAdd of a scan before every PointNoNeedDownsample). */

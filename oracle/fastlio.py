@@ -143,7 +143,7 @@ class OracleFastLio:
     """fastlio_main restated on top of OracleImuProcess + OracleLio.  Same feeding protocol as RefFastLio."""
 
     def __init__(self, ext_R=None, ext_t=None, filter_num=1, max_point_num=-1, scan_period=0.1, undistort=True, nthreads=8,
-                 backend="port", stale_neighbours=True, reference_order=False):
+                 backend="port", stale_neighbours=True, reference_order=True):
         self.imu_proc = OracleImuProcess(ext_R, ext_t, undistort=undistort)          # laserMapping.cpp:1101-1106
         self.lio = OracleLio(nearby=74, nthreads=nthreads, backend=backend,          # NEARBY74 first, laserMapping.cpp:1062
                              stale_neighbours=stale_neighbours, reference_order=reference_order)

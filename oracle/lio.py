@@ -25,7 +25,7 @@ class OracleLio:
 
     def __init__(self, nearby: int = 18, knn_exact: bool = False, expected_cells: int = 1 << 18,
                  nthreads: int = 8, degenerate_detect: bool = True, backend: str = "port", stale_neighbours: bool = False,
-                 reference_order: bool = False):
+                 reference_order: bool = True):
         """backend "port": oracle/lsd_oracle.c; "reference": the compiled reference IVox +
         esti_plane (oracle/_ref) inside the same restated loop.
 

@@ -9,14 +9,13 @@ pytestmark = pytest.mark.gpu
 POS_TOL, ROT_TOL = 1e-4, 1e-5
 
 
-def _pair(small_world, reference_order=False, **kw):
+def _pair(small_world, reference_order=True, **kw):
     import lsdreg
     from oracle import eskf
     from oracle.lio import OracleLio
     m = small_world["map"]
     g = lsdreg.LioFrontend(map_log2_lines=20, **kw)
-    if reference_order:
-        g.set_reference_order(True)
+    g.set_reference_order(reference_order)        # on is the library's default
     g.map.insert(m, 0)
     g.set_next_id(m.shape[0])
     kw.pop("eskf_literal", None)
@@ -35,12 +34,12 @@ def _rot_err(qa, qb):
     return np.linalg.norm(eskf.so3_log(eskf.quat_mul(eskf.quat_conj(qa), qb)))
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(ivox_nearby=74), dict(knn_mode_exact=1), dict(reference_order=True),
-                                dict(reference_order=True, ivox_nearby=74)])
+@pytest.mark.parametrize("kw", [dict(), dict(ivox_nearby=74), dict(knn_mode_exact=1), dict(reference_order=False),
+                                dict(reference_order=False, ivox_nearby=74)])
 def test_linearize_matches_oracle(small_world, kw):
-    """kw reference_order: Nearest_Points rows in the order IVox::GetClosestPoint returns them (libstdc++'s nth_element on the
+    """Nearest_Points rows in the order IVox::GetClosestPoint returns them (the default: libstdc++'s nth_element on the
     reference's candidate sequence) — ids compared position by position against the oracle, which is pinned id for id to the
-    compiled iVox; the planes then carry the compiled esti_plane's bits."""
+    compiled iVox; the planes then carry the compiled esti_plane's bits.  kw reference_order=False: ascending (d2, id) rows."""
     from oracle import oracle as O
     g, o, prior = _pair(small_world, **kw)
     n = g.load_scan(small_world["scan"])
@@ -72,7 +71,7 @@ def test_linearize_matches_oracle(small_world, kw):
     np.testing.assert_allclose(rg2["HTH"], o.last["HTH6"], rtol=1e-10, atol=1e-9)
 
 
-@pytest.mark.parametrize("literal,ref_order", [(1, False), (0, False), (0, True)])
+@pytest.mark.parametrize("literal,ref_order", [(1, True), (0, True), (0, False)])
 def test_update_pose_parity_and_map_incremental(small_world, literal, ref_order):
     from oracle import eskf
     g, o, prior = _pair(small_world, reference_order=ref_order, eskf_literal=literal)
