@@ -217,6 +217,11 @@ lsd_status_t lsd_lio_set_stale_rows(lsd_lio_t* l, int flag);
  * in the reference's insertion order: every PointToAdd of a scan before every PointNoNeedDownsample). */
 lsd_status_t lsd_lio_set_reference_order(lsd_lio_t* l, int flag);
 lsd_status_t lsd_lio_reference_order_fallbacks(lsd_lio_t* l, unsigned* count);
+/* Test entry for the above: libstdc++'s std::nth_element(first, nth, last) (bits/stl_algo.h __introselect) as the search kernel
+ * replays it, on n <= 256 non-negative distances (host pointers).  perm_out[p] = index of the element at position p afterwards;
+ * path_out (optional): 1 = warp-cooperative replay, 2 = it left at introselect's depth limit and the serial replay took over,
+ * 3 = serial replay (n > 32). */
+lsd_status_t lsd_debug_nth_element(const float* dist_host, int n, int first, int nth, int last, int* perm_out_host, int* path_out_host);
 /* Shape of the per-scan neighbour search (no reference counterpart): 0 or 1 = one warp per scan point (the only shape;
  * the flat shapes of round 1 measured slower on B200 and were retired). */
 lsd_status_t lsd_lio_set_knn_shape(lsd_lio_t* l, int shape);

@@ -103,6 +103,7 @@ SIGNATURES = [
     ("lsd_lio_set_stale_rows", _i, [_vp, _i]),
     ("lsd_lio_set_reference_order", _i, [_vp, _i]),
     ("lsd_lio_reference_order_fallbacks", _i, [_vp, _vp]),
+    ("lsd_debug_nth_element", _i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     ("lsd_lio_set_knn_shape", _i, [_vp, _i]),
     ("lsd_lio_set_pdl", _i, [_vp, _i]),
     ("lsd_lio_shard_exchange_stats", _i, [_vp, C.POINTER(_d), C.POINTER(C.c_longlong)]),
@@ -375,6 +376,15 @@ def init_cov() -> np.ndarray:
 def make_state(pos=(0, 0, 0), rot_xyzw=(0, 0, 0, 1), off_R_xyzw=(0, 0, 0, 1), off_T=(0, 0, 0), vel=(0, 0, 0),
                bg=(0, 0, 0), ba=(0, 0, 0), grav=(0, 0, -9.809)) -> np.ndarray:
     return np.concatenate([pos, rot_xyzw, off_R_xyzw, off_T, vel, bg, ba, grav]).astype(np.float64)
+
+
+def debug_nth_element(dist: np.ndarray, first: int, nth: int, last: int):
+    """std::nth_element as the search kernel replays it (include/lsdreg.h lsd_debug_nth_element) -> (perm, path)."""
+    d = np.ascontiguousarray(dist, np.float32)
+    perm = np.empty(d.shape[0], np.int32)
+    path = C.c_int()
+    check(lib.lsd_debug_nth_element(_ptr(d), d.shape[0], first, nth, last, _ptr(perm), C.byref(path)))
+    return perm, path.value
 
 
 def state_boxplus(x: np.ndarray, d: np.ndarray) -> np.ndarray:

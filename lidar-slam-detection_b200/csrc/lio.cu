@@ -1611,6 +1611,56 @@ lsd_status_t lsd_lio_set_reference_order(lsd_lio_t* l, int flag) {
   l->reference_order = flag ? 1 : 0;
   return LSD_OK;
 }
+// Test entry: libstdc++'s std::nth_element(first, nth, last) as the search kernel replays it, on an arbitrary sequence of
+// distances.  path_out: 1 = the warp-cooperative replay did it, 2 = it bailed out at introselect's depth limit and the serial
+// replay took over (as in the kernel), 3 = serial replay (more than 32 elements).  perm_out[p] = index of the element at
+// position p afterwards.  tests/test_gpu_lio.py compares it with the oracle's restatement, which is pinned to std::nth_element.
+__global__ void __launch_bounds__(32) debug_nth_element_kernel(const float* __restrict__ dist, int n, int first, int nth, int last,
+                                                               int* __restrict__ perm_out, int* __restrict__ path_out) {
+  __shared__ unsigned char sr[kCandCap], six[kCandCap];
+  const int lane = threadIdx.x & 31;
+  int path = 3;
+  if (n <= 32) {
+    unsigned key = lane < n ? __float_as_uint(dist[lane]) : 0xffffffffu;
+    int src = lane;
+    path = 1;
+    if (warp_nth_element(key, src, first, nth, last)) {
+      if (lane < n) perm_out[lane] = src;
+      if (lane == 0) *path_out = path;
+      return;
+    }
+    path = 2;
+  }
+  for (int p = lane; p < n; p += 32) {
+    int rk = 0;
+    for (int t = 0; t < n; t++) rk += __float_as_uint(dist[t]) < __float_as_uint(dist[p]) ? 1 : 0;
+    sr[p] = (unsigned char)rk; six[p] = (unsigned char)p;
+  }
+  __syncwarp();
+  if (lane == 0) rs_nth_element(sr, six, first, nth, last);
+  __syncwarp();
+  for (int p = lane; p < n; p += 32) perm_out[p] = six[p];
+  if (lane == 0) *path_out = path;
+}
+lsd_status_t lsd_debug_nth_element(const float* dist_host, int n, int first, int nth, int last, int* perm_out_host, int* path_out_host) {
+  if (!dist_host || !perm_out_host || n < 0 || n > kCandCap || first < 0 || first > nth || nth > last || last > n) return LSD_ERR_INVALID;
+  for (int i = 0; i < n; i++) if (!(dist_host[i] >= 0.f)) return LSD_ERR_INVALID;   // distances: non-negative, so that the bit patterns order like the values
+  lsd_status_t s = ensure_device();
+  if (s) return s;
+  float* d = nullptr; int* o = nullptr;
+  LSD_CUDA(cudaMalloc((void**)&d, (size_t)(n + 1) * 4));
+  LSD_CUDA(cudaMalloc((void**)&o, (size_t)(n + 2) * 4));
+  LSD_CUDA(cudaMemcpy(d, dist_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  debug_nth_element_kernel<<<1, 32>>>(d, n, first, nth, last, o, o + n);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(perm_out_host, o, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  int path = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&path, o + n, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d); cudaFree(o);
+  if (e != cudaSuccess) return cuda_fail(e, "lsd_debug_nth_element", __FILE__, __LINE__);
+  if (path_out_host) *path_out_host = path;
+  return LSD_OK;
+}
 // -> queries since the handle's creation whose candidates overflowed the search's list (answered in canonical order)
 lsd_status_t lsd_lio_reference_order_fallbacks(lsd_lio_t* l, unsigned* count) {
   if (!l || !count) return LSD_ERR_INVALID;

@@ -293,7 +293,10 @@ static void ref_adjust_heap(OrcCand* first, long hole, long len, OrcCand value) 
   }
   first[hole] = value;
 }
+static long orc_heap_select_calls = 0;   /* how often introselect's depth limit was hit (tests make sure it is) */
+long orc_heap_select_count(void) { return orc_heap_select_calls; }
 static void ref_heap_select(OrcCand* first, OrcCand* middle, OrcCand* last) {       /* std::__heap_select */
+  orc_heap_select_calls++;
   const long len = middle - first;
   if (len >= 2)
     for (long parent = (len - 2) / 2;; parent--) {                                  /* std::__make_heap */
@@ -351,6 +354,14 @@ static void ref_nth_element(OrcCand* first, OrcCand* nth, OrcCand* last) {      
       *j = v;
     }
   }
+}
+/* the restated nth_element on its own (tests pin it against std::nth_element on the reference's DistPoint, oracle/ref_lio.cpp) */
+void orc_nth_element(const float* dist, int* idx_inout, int n, int first, int nth, int last) {
+  OrcCand* c = (OrcCand*)malloc(sizeof(OrcCand) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) { c[i].d2 = dist[idx_inout[i]]; c[i].id = idx_inout[i]; c[i].x = c[i].y = c[i].z = 0.f; }
+  ref_nth_element(c + first, c + nth, c + last);
+  for (int i = 0; i < n; i++) idx_inout[i] = c[i].id;
+  free(c);
 }
 #define ORC_REF_CAND_MAX 4096
 /* GetClosestPoint exactly as the reference runs it, order included; `best` receives min(n, k) candidates in the reference's order */

@@ -158,6 +158,17 @@ void ref_esti_plane_qr(const float* pts5, int n, float* qr15, float* hc3, int* p
   }
 }
 
+// std::nth_element exactly as IVox::GetClosestPoint / KNNPointByCondition call it: on a std::vector of the reference's own
+// DistPoint (ivox3d_node.hpp:72-85, operator< on the distance alone), this toolchain's libstdc++.  idx_inout carries the
+// payload (DistPoint::idx) so that the resulting permutation can be read back.
+void ref_std_nth_element(const double* dist, int* idx_inout, int n, int first, int nth, int last) {
+  typedef faster_lio::IVoxNode<PointType, 3>::DistPoint DP;
+  std::vector<DP> v(n);
+  for (int i = 0; i < n; i++) v[i] = DP(dist[idx_inout[i]], nullptr, idx_inout[i]);
+  std::nth_element(v.begin() + first, v.begin() + nth, v.begin() + last);
+  for (int i = 0; i < n; i++) idx_inout[i] = v[i].idx;
+}
+
 // ---------------------------------------------------------------- full h-model on reference classes
 // Restates the loop of h_share_model_geometric (laserMapping.cpp:813-982) around the UNMODIFIED
 // reference IVox::GetClosestPoint and esti_plane<float> (Eigen ColPivHouseholderQR), with Eigen's

@@ -329,3 +329,27 @@ def test_reference_order_truncates_crowded_voxels_in_short_sequences():
     assert g.reference_order_fallbacks() == 0
     assert (mt["cnt"] == cnt).all()
     assert (mt["idx"] == ids).all()
+
+
+def test_device_nth_element_is_the_oracles():
+    """lsd_debug_nth_element — std::nth_element as the search kernel replays it (warp-cooperative for up to 32 elements, serial
+    else and past introselect's depth limit) — against the oracle's restatement, itself pinned to std::nth_element
+    (tests/test_oracle_golden.py): the same permutation on every sequence, every path taken."""
+    import ctypes as C
+    import lsdreg
+    from oracle import oracle as O
+    import test_oracle_golden as T
+    paths = {1: 0, 2: 0, 3: 0}
+
+    def check(d, first, nth, last):
+        n = d.shape[0]
+        want = np.arange(n, dtype=np.int32)
+        O.port.orc_nth_element(C.c_void_p(d.ctypes.data), C.c_void_p(want.ctypes.data), n, first, nth, last)
+        got, path = lsdreg.capi.debug_nth_element(d, first, nth, last)
+        assert (got == want).all(), (n, first, nth, last, path)
+        paths[path] += 1
+    for d, first, nth, last in T._nth_sequences(np.random.default_rng(8), 1500):
+        check(d, first, nth, last)
+    for d, first, nth, last in T._depth_limit_sequences():
+        check(d, first, nth, last)
+    assert paths[1] > 300 and paths[3] > 300 and paths[2] >= 8, paths

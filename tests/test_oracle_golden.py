@@ -87,6 +87,57 @@ def test_esti_plane_bit_exact_vs_compiled_reference():
         assert (qa["perm"] == qb["perm"]).all() and (qa["nonzero_pivots"] == qb["nonzero_pivots"]).all()
 
 
+def _nth_sequences(rng, trials):
+    for t in range(trials):
+        n = int(rng.integers(1, 257)) if t % 3 else int(rng.integers(1, 33))
+        kind = t % 5
+        if kind == 0: d = rng.random(n)
+        elif kind == 1: d = np.round(rng.random(n) * 6) / 6                       # many ties
+        elif kind == 2: d = np.sort(rng.random(n))
+        elif kind == 3: d = np.sort(rng.random(n))[::-1].copy()
+        else: d = np.concatenate([np.arange(n // 2)[::-1], np.arange(n - n // 2)]).astype(float)   # organ pipe
+        if t % 2:
+            first = int(rng.integers(0, n)); last = int(rng.integers(first, n + 1)); nth = int(rng.integers(first, last + 1))
+        else:
+            first, last = 0, n; nth = min(4, n) if t % 4 == 0 else 0
+        yield np.ascontiguousarray(d, np.float32), first, min(nth, last), last
+
+
+def _depth_limit_sequences():
+    rows = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nth_element_depth_limit_sequences.npy"))
+    for r in rows:
+        n, nth = int(r[0]), int(r[1])
+        yield np.ascontiguousarray(r[2:2 + n], np.float32), 0, nth, n
+
+
+@pytest.mark.skipif(not (O.HAVE_REF and hasattr(O.ref, "ref_std_nth_element")), reason="oracle/_ref not built (needs /root/reference)")
+def test_restated_nth_element_is_std_nth_element():
+    """oracle/lsd_oracle.c::ref_nth_element (libstdc++'s __introselect restated) against std::nth_element itself, called on a
+    std::vector of the reference's own DistPoint exactly as IVox::GetClosestPoint calls it: the same permutation on random,
+    tied, sorted, reversed and organ-pipe sequences of 1-256 elements, on sub-ranges, and on the committed adversarial
+    sequences that drive introselect past its depth limit into __heap_select (checked: the restatement's counter moves)."""
+    import ctypes as C
+    O.port.orc_heap_select_count.restype = C.c_long
+
+    def both(d, first, nth, last):
+        n = d.shape[0]
+        d64 = d.astype(np.float64)
+        a = np.arange(n, dtype=np.int32); b = a.copy()
+        O.port.orc_nth_element(C.c_void_p(d.ctypes.data), C.c_void_p(a.ctypes.data), n, first, nth, last)
+        O.ref.ref_std_nth_element(C.c_void_p(d64.ctypes.data), C.c_void_p(b.ctypes.data), n, first, nth, last)
+        return a, b
+    for d, first, nth, last in _nth_sequences(np.random.default_rng(3), 6000):
+        a, b = both(d, first, nth, last)
+        assert (a == b).all(), (d.shape[0], first, nth, last)
+    before = O.port.orc_heap_select_count()
+    k = 0
+    for d, first, nth, last in _depth_limit_sequences():
+        a, b = both(d, first, nth, last)
+        assert (a == b).all()
+        k += 1
+    assert k >= 8 and O.port.orc_heap_select_count() - before == k
+
+
 @pytest.mark.skipif(not O.HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("npts,spread,mode,nearby", [(20000, 6.0, "rand", 18), (200000, 6.0, "rand", 18), (20000, 6.0, "dup", 18),
                                                      (60000, 4.0, "lattice", 18), (100000, 5.0, "rand", 74), (100000, 5.0, "rand", 26),
