@@ -1244,7 +1244,10 @@ lsd_status_t lio_map_incremental(lsd_lio* l, const double* x, int use_near, int*
     if (e) return e;
     wait = true;
   }
-  l->next_id += l->n_bound + id_t2;
+  // ids are 31-bit labels (-1 = no point): wrap instead of overflowing.  After a wrap — 2^31 / (2 n) scans, ~2.5 h at 10 Hz and
+  // 12 k points per scan — a voxel that still holds points from before it orders them after the new ones (reference-order
+  // mode only; with iVox's LRU on, nothing that old survives 100 m of travel).
+  l->next_id = (int)(((long long)l->next_id + l->n_bound + id_t2) & 0x7fffffffll);
   if (wait) {
     LSD_CUDA(cudaStreamSynchronize(st));
     if (n_added) *n_added = (int)*l->h_added;
