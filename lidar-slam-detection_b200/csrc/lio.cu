@@ -430,10 +430,9 @@ RS_INL void rs_nth_element_impl(unsigned char* r, unsigned char* ix, int first, 
   }
 }
 RS_ONE void rs_nth_element(unsigned char* r, unsigned char* ix, int first, int nth, int last) { rs_nth_element_impl(r, ix, first, nth, last); }
-// GetClosestPoint's ordering on the exported sequence (ck[t] = cell << 8 | rank): per-voxel truncation, the two nth_element
-// calls.  Returns how many neighbours the reference returns (<= 5); their positions in the exported sequence are ix[0 ..).
-// FAST: the arrays are in shared memory and the replay is inlined (two copies: LDS / STS instead of generic accesses).
-template <bool FAST>
+// GetClosestPoint's ordering, serially, on a query's candidates in the reference's sequence (ck[t] = cell << 8 | rank of the
+// distance): per-voxel truncation, the two nth_element calls.  Returns how many neighbours the reference returns (<= 5); their
+// positions in the sequence are ix[0 ..).  Run by lane 0 of the search's warp for the queries warp_nth_element does not take.
 RS_INL int rs_reference_order(unsigned char* r, unsigned char* ix, const unsigned short* __restrict__ ck, int n) {
   int m = 0;
   for (int a = 0; a < n;) {
@@ -455,7 +454,7 @@ RS_INL int rs_reference_order(unsigned char* r, unsigned char* ix, const unsigne
   for (int c = 0; c < 2; c++) {                                             // ivox3d.h:159-164: nth_element(.., begin + 4, ..) if more than five, then (.., begin, ..)
     if (c == 0 && m <= 5) continue;
     if (m == 0) break;
-    if (FAST) rs_nth_element_impl(r, ix, 0, c == 0 ? 4 : 0, m); else rs_nth_element(r, ix, 0, c == 0 ? 4 : 0, m);
+    rs_nth_element(r, ix, 0, c == 0 ? 4 : 0, m);
     if (c == 0) m = 5;
   }
   return m;
@@ -637,7 +636,7 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
           }
           __syncwarp();
           int mm = 0;
-          if (lane == 0) mm = rs_reference_order<false>(sr, six, ck, n);
+          if (lane == 0) mm = rs_reference_order(sr, six, ck, n);
           m = __shfl_sync(kFull, mm, 0);
           __syncwarp();
           src = lane < m ? (int)sp[six[lane]] : 0;
