@@ -39,7 +39,15 @@ constexpr int kBrickQC = 32;                          // queries per work item: 
 constexpr int kBrickWarps = 4;                        // warps per CTA of the query kernel (two page buffers each)
 static_assert(kPagePts % 16 == 0 && kPagePts + 16 * kBrickCap <= kPageBytes && kPageBytes % 128 == 0, "page layout");
 
+#ifdef LSD_BRICK_Q16    // A/B build: 16-byte entries (x, y, z, index): half the scatter's bytes, two entries per sector
+struct __align__(16) BrickQuery { float4 p; };
+__device__ __forceinline__ BrickQuery brick_query_make(float4 q, int i) { BrickQuery e; e.p = make_float4(q.x, q.y, q.z, __int_as_float(i)); return e; }
+__device__ __forceinline__ void brick_query_load(const BrickQuery* e, float4* p, int* qi) { const float4 v = __ldg(&e->p); *p = v; *qi = __float_as_int(v.w); }
+#else
 struct __align__(32) BrickQuery { float4 p; int qi; int pad[3]; };   // a query in brick order: one full 32-byte sector (no partial-sector writes)
+__device__ __forceinline__ BrickQuery brick_query_make(float4 q, int i) { BrickQuery e; e.p = q; e.qi = i; e.pad[0] = e.pad[1] = e.pad[2] = 0; return e; }
+__device__ __forceinline__ void brick_query_load(const BrickQuery* e, float4* p, int* qi) { *p = __ldg(&e->p); *qi = __ldg(&e->qi); }
+#endif
 struct __align__(8) BrickWork { int slot, qbase, qn; unsigned total; unsigned long long key; };   // one (brick page, <= 32 queries) unit of the search
 
 // ------------------------------------------------------------------ directory
@@ -246,9 +254,7 @@ __global__ void __launch_bounds__(256) brick_scatter_kernel(const float4* __rest
   if (i >= nq) return;
   const int s = q_slot[i];
   if (s < 0) return;
-  BrickQuery e;
-  e.p = __ldg(q + i); e.qi = i; e.pad[0] = e.pad[1] = e.pad[2] = 0;
-  sorted[bin_base[s] + q_rank[i]] = e;
+  sorted[bin_base[s] + q_rank[i]] = brick_query_make(__ldg(q + i), i);
 }
 
 // ------------------------------------------------------------------ K-D: the search
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
   auto load_query = [&](const BrickWork& it, float4* p, int* qi) {
     const int t = lane >> lanes_log2(it.qn);
     *qi = -1; *p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < it.qn) { const BrickQuery* e = sorted + it.qbase + t; *p = __ldg(&e->p); *qi = __ldg(&e->qi); }
+    if (t < it.qn) brick_query_load(sorted + it.qbase + t, p, qi);
   };
 
   // prologue: item 0 in flight, item 1 described
