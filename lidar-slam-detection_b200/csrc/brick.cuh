@@ -39,15 +39,26 @@ constexpr int kBrickQC = 32;                          // queries per work item: 
 constexpr int kBrickWarps = 4;                        // warps per CTA of the query kernel (two page buffers each)
 static_assert(kPagePts % 16 == 0 && kPagePts + 16 * kBrickCap <= kPageBytes && kPageBytes % 128 == 0, "page layout");
 
-#ifdef LSD_BRICK_Q16    // A/B build: 16-byte entries (x, y, z, index): half the scatter's bytes, two entries per sector
-struct __align__(16) BrickQuery { float4 p; };
-__device__ __forceinline__ BrickQuery brick_query_make(float4 q, int i) { BrickQuery e; e.p = make_float4(q.x, q.y, q.z, __int_as_float(i)); return e; }
-__device__ __forceinline__ void brick_query_load(const BrickQuery* e, float4* p, int* qi) { const float4 v = __ldg(&e->p); *p = v; *qi = __float_as_int(v.w); }
-#else
-struct __align__(32) BrickQuery { float4 p; int qi; int pad[3]; };   // a query in brick order: one full 32-byte sector (no partial-sector writes)
-__device__ __forceinline__ BrickQuery brick_query_make(float4 q, int i) { BrickQuery e; e.p = q; e.qi = i; e.pad[0] = e.pad[1] = e.pad[2] = 0; return e; }
-__device__ __forceinline__ void brick_query_load(const BrickQuery* e, float4* p, int* qi) { *p = __ldg(&e->p); *qi = __ldg(&e->qi); }
-#endif
+// A query in brick order, in one of two formats chosen per batch (brick_batch_is_ordered):
+//   32 bytes (x, y, z, w, index, pad) — one full sector per entry: a SHUFFLED batch scatters its entries all over the list, and a
+//     16-byte store into a sector somebody else completes later costs a read-modify-write (404 vs 438 us per 2 M queries);
+//   16 bytes (x, y, z, index) — a batch that arrives in spatial order fills both halves of a sector within one warp, and then
+//     half the bytes are simply half the bytes (351 vs 363 us: 61.6 % of the HBM roofline, profiles/r02y_*).
+struct __align__(32) BrickQuery { float4 p; int qi; int pad[3]; };
+__device__ __forceinline__ void brick_query_store(BrickQuery* list, int pos, float4 q, int i, bool compact) {
+  if (compact) reinterpret_cast<float4*>(list)[pos] = make_float4(q.x, q.y, q.z, __int_as_float(i));
+  else { BrickQuery e; e.p = q; e.qi = i; e.pad[0] = e.pad[1] = e.pad[2] = 0; list[pos] = e; }
+}
+__device__ __forceinline__ void brick_query_load(const BrickQuery* list, int pos, bool compact, float4* p, int* qi) {
+  if (compact) { const float4 v = __ldg(reinterpret_cast<const float4*>(list) + pos); *p = v; *qi = __float_as_int(v.w); }
+  else { *p = __ldg(&list[pos].p); *qi = __ldg(&list[pos].qi); }
+}
+// A batch counts as spatially ordered when, in the sampled blocks of the bin kernel (one in eight), at least half of the
+// queries share their home brick with their predecessor (ctr[3]).
+__device__ __forceinline__ bool brick_batch_is_ordered(const unsigned* ctr, int nq) {
+  const unsigned sampled = (unsigned)((((nq + 255) / 256 + 7) / 8) * 256);
+  return 2u * __ldcg(ctr + 3) >= sampled;
+}
 struct __align__(8) BrickWork { int slot, qbase, qn; unsigned total; unsigned long long key; };   // one (brick page, <= 32 queries) unit of the search
 
 // ------------------------------------------------------------------ directory
@@ -182,18 +193,32 @@ __device__ __forceinline__ void page_load_wait(unsigned long long* bar, unsigned
 // K-A: home brick of every query; queries whose brick does not exist are answered here (nothing within reach).
 __global__ void __launch_bounds__(256) brick_bin_kernel(BrickView bv, float inv_res, const float4* __restrict__ q, int nq, int k,
                                                         int* __restrict__ q_slot, int* __restrict__ q_rank, unsigned* __restrict__ bin_count,
-                                                        int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
+                                                        int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt,
+                                                        unsigned* __restrict__ ctr3) {
+  __shared__ unsigned s_same;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  const float4 p = __ldg(q + i);
-  const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
+  const bool sample = (blockIdx.x & 7) == 0;       // one block in eight tells whether the batch arrives in spatial order
+  if (sample && threadIdx.x == 0) s_same = 0u;
+  if (sample) __syncthreads();
   long long s = -1;
-  // beyond +-(2^18) no stencil cell is a valid voxel (coord_ok): nothing can be near
-  if (abs(c.x) <= kCoordBias && abs(c.y) <= kCoordBias && abs(c.z) <= kCoordBias) {
-    int3 b, l;
-    brick_of(c.x, c.y, c.z, &b, &l);
-    s = brick_find(bv, pack_key(b.x, b.y, b.z, 0));
+  if (i < nq) {
+    const float4 p = __ldg(q + i);
+    const int3 c = pos2grid(p.x, p.y, p.z, inv_res);
+    // beyond +-(2^18) no stencil cell is a valid voxel (coord_ok): nothing can be near
+    if (abs(c.x) <= kCoordBias && abs(c.y) <= kCoordBias && abs(c.z) <= kCoordBias) {
+      int3 b, l;
+      brick_of(c.x, c.y, c.z, &b, &l);
+      s = brick_find(bv, pack_key(b.x, b.y, b.z, 0));
+    }
   }
+  if (sample) {     // block-uniform: every lane takes part in the shuffle; one shared atomic per warp, one global per sampled block
+    const long long prev = __shfl_up_sync(0xffffffffu, s, 1);
+    const unsigned same = __ballot_sync(0xffffffffu, (threadIdx.x & 31) != 0 && s >= 0 && prev == s);
+    if ((threadIdx.x & 31) == 0 && same) atomicAdd(&s_same, (unsigned)__popc(same));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_same) atomicAdd(ctr3, s_same);
+  }
+  if (i >= nq) return;
   q_slot[i] = (int)s;
   if (s < 0) {
     for (int r = 0; r < k; r++) { out_idx[(size_t)i * k + r] = -1; out_d2[(size_t)i * k + r] = -1.0f; }
@@ -249,12 +274,12 @@ __global__ void __launch_bounds__(256) brick_plan_kernel(BrickView bv, unsigned 
 // reads its queries with one contiguous load instead of index -> query (two dependent DRAM trips)
 __global__ void __launch_bounds__(256) brick_scatter_kernel(const float4* __restrict__ q, const int* __restrict__ q_slot,
                                                             const int* __restrict__ q_rank, const int* __restrict__ bin_base, int nq,
-                                                            BrickQuery* __restrict__ sorted) {
+                                                            BrickQuery* __restrict__ sorted, const unsigned* __restrict__ ctr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   const int s = q_slot[i];
   if (s < 0) return;
-  sorted[bin_base[s] + q_rank[i]] = brick_query_make(__ldg(q + i), i);
+  brick_query_store(sorted, bin_base[s] + q_rank[i], __ldg(q + i), i, brick_batch_is_ordered(ctr, nq));
 }
 
 // ------------------------------------------------------------------ K-D: the search
@@ -299,7 +324,7 @@ struct KeyTop5 {
 
 template <int K>
 __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView bv, float inv_res, int st_slot, float max_sq,
-                                                                     const BrickQuery* __restrict__ sorted,
+                                                                     const BrickQuery* __restrict__ sorted, int nq,
                                                                      const BrickWork* __restrict__ work, unsigned* __restrict__ ctr,
                                                                      int* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ out_cnt) {
   // Two page buffers per warp: while item N is answered from one, item N + 1's page lands in the other, its queries sit in
@@ -315,6 +340,7 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
   if (threadIdx.x < 32) s_off[threadIdx.x] = (int)threadIdx.x < n_cells ? (st.off[threadIdx.x][2] * kRegXY + st.off[threadIdx.x][1]) * kRegXY + st.off[threadIdx.x][0] : 0;
   __syncthreads();
   const unsigned n_work = __ldcg(ctr + 1);
+  const bool compact = brick_batch_is_ordered(ctr, nq);   // the list's entry format (warp-uniform)
   unsigned char* myq = cellq[warp][lane];
   unsigned phase = 0u;                                   // bit b = parity the next wait on buffer b expects
   const BrickWork none = {0, 0, 0, 0u, 0ull};
@@ -324,7 +350,7 @@ __global__ void __launch_bounds__(kBrickWarps * 32) brick_knn_kernel(BrickView b
   auto load_query = [&](const BrickWork& it, float4* p, int* qi) {
     const int t = lane >> lanes_log2(it.qn);
     *qi = -1; *p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < it.qn) brick_query_load(sorted + it.qbase + t, p, qi);
+    if (t < it.qn) brick_query_load(sorted, it.qbase + t, compact, p, qi);
   };
 
   // prologue: item 0 in flight, item 1 described

@@ -341,12 +341,12 @@ static lsd_status_t launch_knn_bricks(lsd_map* m, const float4* d_q, int nq, int
   unsigned* ctr = reinterpret_cast<unsigned*>(base + o_ctr);
   LSD_CUDA(cudaMemsetAsync(ctr, 0, 16, st));
   const int gq = (nq + 255) / 256;
-  brick_bin_kernel<<<gq, 256, 0, st>>>(bv, m->view.inv_res, d_q, nq, k, q_slot, q_rank, m->bin_count, d_idx, d_d2, d_cnt);
+  brick_bin_kernel<<<gq, 256, 0, st>>>(bv, m->view.inv_res, d_q, nq, k, q_slot, q_rank, m->bin_count, d_idx, d_d2, d_cnt, ctr + 3);
   brick_plan_kernel<<<(unsigned)((m->n_bricks + 255) / 256), 256, 0, st>>>(bv, m->n_bricks, m->bin_count, m->bin_base, work, ctr);
-  brick_scatter_kernel<<<gq, 256, 0, st>>>(d_q, q_slot, q_rank, m->bin_base, nq, sorted);
+  brick_scatter_kernel<<<gq, 256, 0, st>>>(d_q, q_slot, q_rank, m->bin_base, nq, sorted, ctr);
   const int grid = (int)std::min<size_t>(148 * 5, (n_work_max + kBrickWarps - 1) / kBrickWarps);   // 5 CTAs x 4 warps x 2 x 4.6 KB per SM
-  if (k == 1) brick_knn_kernel<1><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, sorted, work, ctr, d_idx, d_d2, d_cnt);
-  else brick_knn_kernel<5><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, sorted, work, ctr, d_idx, d_d2, d_cnt);
+  if (k == 1) brick_knn_kernel<1><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, sorted, nq, work, ctr, d_idx, d_d2, d_cnt);
+  else brick_knn_kernel<5><<<grid, kBrickWarps * 32, 0, st>>>(bv, m->view.inv_res, st_slot, max_sq, sorted, nq, work, ctr, d_idx, d_d2, d_cnt);
   LSD_CUDA(cudaGetLastError());
   m->launches += 4;
   return LSD_OK;
