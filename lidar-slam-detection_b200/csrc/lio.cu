@@ -342,7 +342,9 @@ __constant__ unsigned char c_tri[21][2] = {{0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{
 // History of where the replay ran (B200, per search evaluation, 12 k queries): one thread per query on per-thread local arrays
 // inside the plane-fit kernel +65 us; on shared memory but inlined three times +135 us (it took that kernel's registers); its
 // own 64-thread-block kernel +31 us, with batched global loads +27 us — a chain of ~3 k dependent instructions per thread,
-// one warp per scheduler, nothing to hide latency behind; by the search's own warp, below, see DESIGN.md section 6.
+// one warp per scheduler, nothing to hide latency behind; by the search's own warp, below, +11 us.  Gathering
+// cell by cell (warp prefix sum of per-cell counts) so that the list is the sequence without the all-pairs placement was
+// tried last and cost 6 us MORE (seven distances and ids per lane held in registers): profiles/r02zc_*_not_kept.jsonl.
 #ifdef LSD_SIMT_EMU
 #define RS_INL __device__
 #define RS_ONE __device__
