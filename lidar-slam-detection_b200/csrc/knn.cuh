@@ -118,46 +118,6 @@ __device__ __forceinline__ void list_compress(WarpList& wl) {
   __syncwarp();
 }
 
-// The probe half of warp_scan_cells: a lane's voxel `key` (0: none) -> its slot, line, point count and first three points.
-// Walks the probe sequence in the TAG array (8 slots per 8-byte load, L2-resident): an absent voxel is recognised without
-// touching a line, a present one costs exactly one line access (plus one per tag collision, 1/255 per occupied slot walked).
-__device__ __forceinline__ void warp_probe_cell(const MapView& mv, unsigned long long key, unsigned long long& s, const CellLine*& ln,
-                                                unsigned& cnt, float4 (&p)[3]) {
-  s = 0; ln = mv.lines; cnt = 0;
-  p[0] = p[1] = p[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (key == 0ull) return;
-  constexpr unsigned long long k01 = 0x0101010101010101ull, k7f = 0x7f7f7f7f7f7f7f7full;
-  const unsigned long long hh = hash_key(key);
-  const unsigned long long tagv = (unsigned long long)slot_tag(hh) * k01;
-  s = hh & mv.mask;
-  bool present = false;
-  for (unsigned walked = 0; walked < kMaxProbe && !present;) {
-    const unsigned pos = (unsigned)(s & 7ull), nv = 8u - pos;
-    const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long*>(mv.tags + (s & ~7ull))) >> (8u * pos);
-    // exact zero-byte flags (bit 7 of each zero byte); bytes shifted in above nv are zero, so fe <= nv
-    const unsigned long long ze = ~(((v & k7f) + k7f) | v | k7f);
-    const unsigned long long x = v ^ tagv;
-    unsigned long long zm = ~(((x & k7f) + k7f) | x | k7f);
-    const unsigned fe = ze ? (unsigned)(__ffsll((long long)ze) - 1) >> 3 : 8u;
-    while (zm) {
-      const unsigned fm = (unsigned)(__ffsll((long long)zm) - 1) >> 3;
-      if (fm >= fe) break;  // the probe sequence ends at the first empty slot
-      zm &= zm - 1ull;
-      const unsigned long long c = (s + fm) & mv.mask;
-      const CellLine* cl = mv.lines + c;
-      const uint4 h = ldg_u4(cl);
-      const float4 a0 = ldg_f4(&cl->pts[0]), a1 = ldg_f4(&cl->pts[1]), a2 = ldg_f4(&cl->pts[2]);
-      if (((unsigned long long)h.x | ((unsigned long long)h.y << 32)) == key) {
-        present = true; s = c; ln = cl; cnt = h.z; p[0] = a0; p[1] = a1; p[2] = a2;
-        break;
-      }
-    }
-    if (present || fe < nv) break;
-    walked += nv;
-    s = (s + nv) & mv.mask;
-  }
-}
-
 // Each lane resolves ONE voxel (key == 0: none) and pushes its in-radius points.
 // Phase A: header + points 0..2 (sectors 0,1) requested together; phase B: points 3..6 if needed;
 // overflow levels (> 7 points in the voxel) are walked cooperatively afterwards.
@@ -165,12 +125,47 @@ template <int K>
 __device__ __forceinline__ void warp_scan_cells(const MapView& mv, unsigned long long key, float qx, float qy, float qz,
                                                 float max_sq, bool inclusive, WarpList& wl, int cell_base = 0, bool guarded = false) {
   const int my_cell = cell_base + (int)(threadIdx.x & 31);
-  unsigned long long s;
-  const CellLine* ln;
-  unsigned cnt;
+  unsigned long long s = 0;
+  const CellLine* ln = mv.lines;
+  unsigned cnt = 0;
   {
     float4 p[3];
-    warp_probe_cell(mv, key, s, ln, cnt, p);
+    p[0] = p[1] = p[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (key != 0ull) {
+      // Walk the probe sequence in the TAG array (8 slots per 8-byte load, L2-resident): an absent
+      // voxel is recognised without touching a line, a present one costs exactly one line access
+      // (plus one per tag collision, 1/255 per occupied slot walked).
+      constexpr unsigned long long k01 = 0x0101010101010101ull, k7f = 0x7f7f7f7f7f7f7f7full;
+      const unsigned long long hh = hash_key(key);
+      const unsigned long long tagv = (unsigned long long)slot_tag(hh) * k01;
+      s = hh & mv.mask;
+      bool present = false;
+      for (unsigned walked = 0; walked < kMaxProbe && !present;) {
+        const unsigned pos = (unsigned)(s & 7ull), nv = 8u - pos;
+        const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long*>(mv.tags + (s & ~7ull))) >> (8u * pos);
+        // exact zero-byte flags (bit 7 of each zero byte); bytes shifted in above nv are zero, so fe <= nv
+        const unsigned long long ze = ~(((v & k7f) + k7f) | v | k7f);
+        const unsigned long long x = v ^ tagv;
+        unsigned long long zm = ~(((x & k7f) + k7f) | x | k7f);
+        const unsigned fe = ze ? (unsigned)(__ffsll((long long)ze) - 1) >> 3 : 8u;
+        while (zm) {
+          const unsigned fm = (unsigned)(__ffsll((long long)zm) - 1) >> 3;
+          if (fm >= fe) break;  // the probe sequence ends at the first empty slot
+          zm &= zm - 1ull;
+          const unsigned long long c = (s + fm) & mv.mask;
+          const CellLine* cl = mv.lines + c;
+          const uint4 h = ldg_u4(cl);
+          const float4 a0 = ldg_f4(&cl->pts[0]), a1 = ldg_f4(&cl->pts[1]), a2 = ldg_f4(&cl->pts[2]);
+          if (((unsigned long long)h.x | ((unsigned long long)h.y << 32)) == key) {
+            present = true; s = c; ln = cl; cnt = h.z; p[0] = a0; p[1] = a1; p[2] = a2;
+            break;
+          }
+        }
+        if (present || fe < nv) break;
+        walked += nv;
+        s = (s + nv) & mv.mask;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       bool valid = (unsigned)j < cnt;
@@ -278,97 +273,26 @@ __device__ __forceinline__ int knn_stencil_warp(const MapView& mv, const LaneSte
   return list_select<K>(wl, out);
 }
 
-// warp_scan_cells for the reference-order search: the lanes' in-range points go into the list CELL BY CELL (a warp prefix sum
-// of the per-lane counts), slot order inside a cell — which is the reference's candidate sequence (nearby_grids_ order, then the
-// voxel's insertion order) whenever the slots of every cell hold ascending ids.  Returns false — and leaves the list as it
-// was — when that is not the case or a voxel has overflow lines: the caller then gathers in push order and places the
-// candidates by an all-pairs count.
-template <int K>
-__device__ __forceinline__ bool warp_scan_cells_ordered(const MapView& mv, unsigned long long key, float qx, float qy, float qz,
-                                                        float max_sq, WarpList& wl, int cell_base) {
-  const int lane = threadIdx.x & 31;
-  unsigned long long s;
-  const CellLine* ln;
-  unsigned cnt;
-  float4 p[3];
-  warp_probe_cell(mv, key, s, ln, cnt, p);
-  float d[kPtsPerLine]; int id[kPtsPerLine];
-  unsigned vm = 0u;
-#pragma unroll
-  for (int j = 0; j < 3; j++) {
-    d[j] = dist2(qx, qy, qz, p[j].x, p[j].y, p[j].z); id[j] = __float_as_int(p[j].w);
-    if ((unsigned)j < cnt && d[j] < max_sq) vm |= 1u << j;
-  }
-  const unsigned n0 = min(cnt, (unsigned)kPtsPerLine);
-  if (__any_sync(kFull, cnt > 3u)) {
-    float4 r[4];
-    r[0] = r[1] = r[2] = r[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n0 > 3) { r[0] = ldg_f4(&ln->pts[3]); r[1] = ldg_f4(&ln->pts[4]); r[2] = ldg_f4(&ln->pts[5]); r[3] = ldg_f4(&ln->pts[6]); }
-#pragma unroll
-    for (int j = 3; j < kPtsPerLine; j++) {
-      d[j] = dist2(qx, qy, qz, r[j - 3].x, r[j - 3].y, r[j - 3].z); id[j] = __float_as_int(r[j - 3].w);
-      if ((unsigned)j < n0 && d[j] < max_sq) vm |= 1u << j;
-    }
-  } else {
-#pragma unroll
-    for (int j = 3; j < kPtsPerLine; j++) { d[j] = 0.f; id[j] = 0; }
-  }
-  bool asc = true;
-  int last = (int)0x80000000;
-#pragma unroll
-  for (int j = 0; j < kPtsPerLine; j++) if (vm >> j & 1u) { asc = asc && id[j] > last; last = id[j]; }
-  if (__any_sync(kFull, cnt > (unsigned)kPtsPerLine || !asc)) return false;
-  const int nv = __popc(vm);
-  int incl = nv;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-  const int total = __shfl_sync(kFull, incl, 31);
-  if (wl.n + total > kCandCap) { wl.clipped = 1; return true; }
-  int pos = wl.n + incl - nv;
-#pragma unroll
-  for (int j = 0; j < kPtsPerLine; j++)
-    if (vm >> j & 1u) { wl.d[pos] = __float_as_uint(d[j]); wl.id[pos] = id[j]; wl.loc[pos] = (unsigned)(s * 8 + j + 1); wl.cell[pos] = (unsigned char)(cell_base + lane); pos++; }
-  wl.n += total;
-  return true;
-}
-
 // The gather half of knn_stencil_warp on its own: every in-range point of the stencil cells in the list, tagged with its cell
 // (wl.cell must be set).  wl.clipped != 0 afterwards: more than kCandCap candidates, the list is incomplete.
 template <int K>
-__device__ __forceinline__ bool knn_stencil_gather(const MapView& mv, const LaneStencil& ls, float qx, float qy, float qz,
+__device__ __forceinline__ void knn_stencil_gather(const MapView& mv, const LaneStencil& ls, float qx, float qy, float qz,
                                                    float max_sq, WarpList& wl) {
   const int3 c = pos2grid(qx, qy, qz, mv.inv_res);
   wl.n = 0; wl.clipped = 0;
-  bool ordered = true;      // the list IS the reference's candidate sequence (warp_scan_cells_ordered)
 #pragma unroll
   for (int ch = 0; ch < 3; ch++) {
-    if (ch < ls.n_chunks && ordered) {
+    if (ch < ls.n_chunks) {
       unsigned long long key = 0ull;
       const int o = ls.off[ch];
       if (o) {
         const int x = c.x + (int)(signed char)(o >> 16), y = c.y + (int)(signed char)(o >> 8), z = c.z + (int)(signed char)o;
         if (coord_ok(x, y, z)) key = pack_key(x, y, z, 0);
       }
-      ordered = warp_scan_cells_ordered<K>(mv, key, qx, qy, qz, max_sq, wl, ch * 32);
-    }
-  }
-  if (!ordered) {           // a voxel with overflow lines or slots out of id order: push order, placed by the caller
-    wl.n = 0; wl.clipped = 0;
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-      if (ch < ls.n_chunks) {
-        unsigned long long key = 0ull;
-        const int o = ls.off[ch];
-        if (o) {
-          const int x = c.x + (int)(signed char)(o >> 16), y = c.y + (int)(signed char)(o >> 8), z = c.z + (int)(signed char)o;
-          if (coord_ok(x, y, z)) key = pack_key(x, y, z, 0);
-        }
-        warp_scan_cells<K>(mv, key, qx, qy, qz, max_sq, false, wl, ch * 32, true);
-      }
+      warp_scan_cells<K>(mv, key, qx, qy, qz, max_sq, false, wl, ch * 32, true);
     }
   }
   __syncwarp();
-  return ordered;
 }
 
 // Exact k-NN with d2 <= max_sq by Chebyshev shells around the query's voxel; stops as soon as the

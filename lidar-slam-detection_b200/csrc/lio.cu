@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
     }
     if (ref_order) {
       // every in-range candidate, then the reference's order on them: warp_nth_element for up to 32, the serial replay else
-      const bool in_sequence = knn_stencil_gather<5>(mv, ls, wx, wy, wz, 5.0f, wl);   // the list already is the reference's sequence
+      knn_stencil_gather<5>(mv, ls, wx, wy, wz, 5.0f, wl);
       const int n = wl.n;
       if (n == 0) {                       // GetClosestPoint returns false before touching its output (ivox3d.h:155-157)
         if (!keep_stale) { if (lane == 0) near_cnt[i] = 0; if (lane < 5) near[(size_t)i * 5 + lane] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); }
@@ -585,25 +585,20 @@ __global__ void __launch_bounds__(kHmWarps * 32, 4) lio_knn_kernel(MapView mv, i
         int m = -1, src = 0;              // m >= 0: lanes j < m hold in `src` the list index of the j-th neighbour
         if (n <= 32) {
           // the reference's sequence: stencil cell in nearby_grids_ order, then the voxel's insertion order (= ascending id)
-          unsigned key; int cellv;
-          if (in_sequence) {
-            key = lane < n ? wl.d[lane] : 0xffffffffu; src = lane; cellv = lane < n ? (int)wl.cell[lane] : 256 + lane;
-          } else {
-            const unsigned d = lane < n ? wl.d[lane] : 0xffffffffu;
-            const int id = lane < n ? wl.id[lane] : 0x7fffffff;
-            const int c = lane < n ? (int)wl.cell[lane] : 255;
-            int pos = 0;
-            for (int t = 0; t < n; t++) {
-              const int ct = wl.cell[t]; const int it = wl.id[t];
-              pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
-            }
-            if (lane < n) { s_fkey[warp][pos] = d; s_fsrc[warp][pos] = (unsigned char)lane; s_fcell[warp][pos] = (unsigned char)c; }
-            __syncwarp();
-            key = lane < n ? s_fkey[warp][lane] : 0xffffffffu;
-            src = lane < n ? (int)s_fsrc[warp][lane] : 0;
-            cellv = lane < n ? (int)s_fcell[warp][lane] : 256 + lane;
-            __syncwarp();
+          const unsigned d = lane < n ? wl.d[lane] : 0xffffffffu;
+          const int id = lane < n ? wl.id[lane] : 0x7fffffff;
+          const int c = lane < n ? (int)wl.cell[lane] : 255;
+          int pos = 0;
+          for (int t = 0; t < n; t++) {
+            const int ct = wl.cell[t]; const int it = wl.id[t];
+            pos += (ct < c || (ct == c && it < id)) ? 1 : 0;
           }
+          if (lane < n) { s_fkey[warp][pos] = d; s_fsrc[warp][pos] = (unsigned char)lane; s_fcell[warp][pos] = (unsigned char)c; }
+          __syncwarp();
+          unsigned key = lane < n ? s_fkey[warp][lane] : 0xffffffffu;
+          src = lane < n ? (int)s_fsrc[warp][lane] : 0;
+          int cellv = lane < n ? (int)s_fcell[warp][lane] : 256 + lane;
+          __syncwarp();
           m = n;
           bool ok = true;
           for (;;) {     // KNNPointByCondition: a voxel with more than five candidates keeps nth_element's first five (ivox3d_node.hpp:118-123)
