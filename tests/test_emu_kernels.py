@@ -22,6 +22,7 @@ _CASES = {
     "pdl": ("test_gpu_zz_pdl.py", "PDL_OK"),      # control flow only: the emulator serialises launches, PDL on == off by construction
     "fuzz_knn": ("simt/fuzz_knn.py", "FUZZ_OK"),   # adversarial map / k-NN inputs, three shapes vs each other and the oracle
     "fuzz_misc": ("simt/fuzz_misc.py", "FUZZ_MISC_OK"),
+    "fuzz_reforder": ("simt/fuzz_reforder.py", "FUZZ_REFORDER_OK"),   # reference-order rows on crowded / clustered maps, every path of the search kernel
     "fuzz_nth": ("simt/fuzz_nth.py", "FUZZ_NTH_OK"),   # std::nth_element as the search kernel replays it vs the restatement (warp path, depth-limit bail-out, serial path)
     "fuzz_pipeline": ("simt/fuzz_pipeline.py", "FUZZ_PIPELINE_OK"),   # random announce / register schedules: staging slots, deferred requests, buffer hand-over   # voxel grid, key-frame filters, ScanContext descriptor on degenerate inputs
 }
