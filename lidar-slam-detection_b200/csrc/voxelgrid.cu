@@ -228,6 +228,102 @@ __global__ void __launch_bounds__(256) vg_finalize_kernel(const VgGrid* __restri
   }
 }
 
+// ---- the centroids as a sequential fp32 sum in INPUT order (kernels 4a-4e instead of 4 and 5) ----------------------------------
+// pcl::VoxelGrid adds a leaf's points one by one into fp32 accumulators, in the order std::sort leaves equal keys in, and divides
+// by the count; the restated filter the oracle and the reference arm use (oracle/lsd_oracle.c::orc_voxelgrid,
+// oracle/ref_shim_fastlio/pcl/filters/voxel_grid.h) fixes that order to the input order.  Reproducing THAT arithmetic — instead
+// of the exact fixed-point sums above, one fp32 ulp away for half the leaves — is what lets a whole scan agree with the
+// reference arm to the last bits of the double-precision sums: a counting sort by leaf (count, exclusive
+// scan, scatter), the rank of every point inside its leaf's segment by counting smaller indices, then one thread per leaf
+// adding its points in that order.
+__global__ void __launch_bounds__(256) vg_count_kernel(const float4* __restrict__ in, int n, const VgGrid* __restrict__ gp,
+                                                       const unsigned* __restrict__ bitmap, int* __restrict__ vidx,
+                                                       const int* __restrict__ word_prefix, const int* __restrict__ chunk_off,
+                                                       int* __restrict__ cnt, int* __restrict__ out_vidx, float4* __restrict__ out) {
+  pdl_enter();
+  const int status = gp->status;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (status == LSD_ERR_GRID_OVERFLOW) { out[i] = __ldg(in + i); continue; }  // PCL: output = input
+    if (status) return;
+    const int idx = vidx[i];
+    if (idx < 0) continue;   // non-finite point
+    const int w = idx >> 5;
+    const int rank = chunk_off[w / kScanChunk] + word_prefix[w] + __popc(bitmap[w] & ((1u << (idx & 31)) - 1u));
+    vidx[i] = rank;          // from here on: the point's output slot
+    atomicAdd(cnt + rank, 1);
+    out_vidx[rank] = idx;
+  }
+}
+// exclusive scan of the per-leaf counts: one block, every thread a contiguous run
+__global__ void __launch_bounds__(1024) vg_offsets_kernel(const VgGrid* __restrict__ gp, const int* __restrict__ m_ptr,
+                                                          const int* __restrict__ cnt, int* __restrict__ off) {
+  pdl_enter();
+  __shared__ int part[1024];
+  if (gp->status) return;
+  const int m = *m_ptr;
+  const int per = (m + 1023) / 1024, a = threadIdx.x * per, b = min(a + per, m);
+  int s = 0;
+  for (int r = a; r < b; r++) s += cnt[r];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int t = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - s;
+  for (int r = a; r < b; r++) { off[r] = run; run += cnt[r]; }
+}
+__global__ void __launch_bounds__(256) vg_scatter_kernel(int n, const VgGrid* __restrict__ gp, const int* __restrict__ vidx,
+                                                         const int* __restrict__ off, int* __restrict__ cur, int* __restrict__ seg) {
+  pdl_enter();
+  if (gp->status) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = vidx[i];
+    if (r < 0) continue;
+    seg[off[r] + atomicAdd(cur + r, 1)] = i;
+  }
+}
+__global__ void __launch_bounds__(256) vg_order_kernel(int n, const VgGrid* __restrict__ gp, const int* __restrict__ vidx,
+                                                       const int* __restrict__ off, const int* __restrict__ cnt,
+                                                       const int* __restrict__ seg, int* __restrict__ ord) {
+  pdl_enter();
+  if (gp->status) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = vidx[i];
+    if (r < 0) continue;
+    const int base = off[r], k = cnt[r];
+    int c = 0;
+    for (int t = 0; t < k; t++) c += seg[base + t] < i ? 1 : 0;
+    ord[base + c] = i;
+  }
+}
+__global__ void __launch_bounds__(256) vg_sum_kernel(const float4* __restrict__ in, const VgGrid* __restrict__ gp,
+                                                     const int* __restrict__ m_ptr, const int* __restrict__ off, int* __restrict__ cnt,
+                                                     int* __restrict__ cur, const int* __restrict__ ord, const int* __restrict__ out_vidx,
+                                                     unsigned* __restrict__ bitmap, float4* __restrict__ out, int* __restrict__ bbox) {
+  pdl_enter();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    bbox[0] = bbox[1] = bbox[2] = 0x7f7f7f7f;
+    bbox[3] = bbox[4] = bbox[5] = (int)0x80808080;
+  }
+  if (gp->status) return;
+  const int m = *m_ptr;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    const int base = off[r], k = cnt[r];
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+    for (int t = 0; t < k; t++) {
+      const float4 p = __ldg(in + ord[base + t]);
+      ax += p.x; ay += p.y; az += p.z; aw += p.w;
+    }
+    const float c = (float)k;
+    out[r] = make_float4(ax / c, ay / c, az / c, aw / c);
+    cnt[r] = 0; cur[r] = 0;
+    bitmap[out_vidx[r] >> 5] = 0u;
+  }
+}
+
 lsd_status_t vg_run(lsd_voxelgrid* g, const float4* d_in, int n, float leaf, float4* d_out, int* d_m, cudaStream_t st) {
   if (n > g->max_points) { set_error("voxelgrid: %d points exceed capacity %d", n, g->max_points); return LSD_ERR_CAPACITY; }
   if (n <= 0) { LSD_CUDA(cudaMemsetAsync(d_m, 0, sizeof(int), st)); return LSD_OK; }
@@ -236,6 +332,16 @@ lsd_status_t vg_run(lsd_voxelgrid* g, const float4* d_in, int n, float leaf, flo
   LSD_LAUNCH(pdl, vg_minmax_kernel, std::min(nb, 148), 256, st, d_in, n, g->bbox);
   LSD_LAUNCH(pdl, vg_mark_kernel, nb, 256, st, d_in, n, leaf, g->max_cells, g->bbox, g->grid, g->bitmap, g->vidx);
   LSD_LAUNCH(pdl, vg_scan_kernel, g->scan_blocks, 256, st, g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->done, d_m, n);
+  if (g->input_order_sums) {
+    LSD_LAUNCH(pdl, vg_count_kernel, nb, 256, st, d_in, n, g->grid, g->bitmap, g->vidx, g->word_prefix, g->chunk_sum, g->cnt, g->out_vidx, d_out);
+    LSD_LAUNCH(pdl, vg_offsets_kernel, 1, 1024, st, g->grid, d_m, g->cnt, g->off);
+    LSD_LAUNCH(pdl, vg_scatter_kernel, nb, 256, st, n, g->grid, g->vidx, g->off, g->cur, g->seg);
+    LSD_LAUNCH(pdl, vg_order_kernel, nb, 256, st, n, g->grid, g->vidx, g->off, g->cnt, g->seg, g->ord);
+    LSD_LAUNCH(pdl, vg_sum_kernel, nb, 256, st, d_in, g->grid, d_m, g->off, g->cnt, g->cur, g->ord, g->out_vidx, g->bitmap, d_out, g->bbox);
+    LSD_CUDA(cudaGetLastError());
+    g->launches += 8;
+    return LSD_OK;
+  }
   LSD_LAUNCH(pdl, vg_accum_kernel, nb, 256, st, d_in, n, g->grid, g->bitmap, g->vidx, g->word_prefix, g->chunk_sum, g->sums, g->cnt,
              g->out_vidx, d_out);
   LSD_LAUNCH(pdl, vg_finalize_kernel, nb, 256, st, g->grid, d_m, g->sums, g->cnt, g->out_vidx, g->bitmap, d_out, g->bbox);
@@ -273,6 +379,11 @@ lsd_status_t lsd_voxelgrid_create(lsd_voxelgrid_t** out, int max_points, int log
   A((void**)&g->out_vidx, (size_t)max_points * 4);
   A((void**)&g->sums, (size_t)max_points * 4 * 8);
   A((void**)&g->cnt, (size_t)max_points * 4);
+  A((void**)&g->off, (size_t)max_points * 4);
+  A((void**)&g->cur, (size_t)max_points * 4);
+  A((void**)&g->seg, (size_t)max_points * 4);
+  A((void**)&g->ord, (size_t)max_points * 4);
+  { const char* ev = getenv("LSD_VG_SUMS"); g->input_order_sums = (ev && ev[0] == 'f') ? 0 : 1; }   // "fixed": the exact fixed-point sums
   A((void**)&g->io_in, (size_t)max_points * 16);
   A((void**)&g->io_out, (size_t)max_points * 16);
   A((void**)&g->d_m, 64);
@@ -289,7 +400,8 @@ lsd_status_t lsd_voxelgrid_destroy(lsd_voxelgrid_t* g) {
   if (!g) return LSD_OK;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  void* ptrs[] = {g->bbox, g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->vidx, g->out_vidx, g->sums, g->cnt, g->io_in, g->io_out, g->d_m, g->done};
+  void* ptrs[] = {g->bbox, g->grid, g->bitmap, g->word_prefix, g->chunk_sum, g->vidx, g->out_vidx, g->sums, g->cnt, g->io_in, g->io_out, g->d_m, g->done,
+                  g->off, g->cur, g->seg, g->ord};
   for (void* p : ptrs) cudaFree(p);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;

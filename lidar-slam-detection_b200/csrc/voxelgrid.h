@@ -26,6 +26,8 @@ struct lsd_voxelgrid {
   int* out_vidx = nullptr;        // leaf index per output point
   long long* sums = nullptr;      // [max_points,4] fixed-point channel sums; all-zero between calls
   int* cnt = nullptr;
+  int *off = nullptr, *cur = nullptr, *seg = nullptr, *ord = nullptr;   // input-order sums: leaf offsets, scatter cursors (zero between calls), members, members in input order
+  int input_order_sums = 1;       // centroids as pcl::VoxelGrid's sequential fp32 sums in input order (LSD_VG_SUMS=fixed: exact fixed-point sums)
   float4 *io_in = nullptr, *io_out = nullptr;  // staging for the host-pointer entry point
   int* d_m = nullptr;
   unsigned* done = nullptr;       // last-block ticket of vg_scan_kernel

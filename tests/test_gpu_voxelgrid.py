@@ -1,6 +1,8 @@
 """GPU parity: voxel-grid downsample (K1) against the restated PCL VoxelGrid.
 Bar: identical leaf set and output order; centroids within 1e-5 m (PCL sums fp32 in sort order,
 we sum exactly in fixed point — SURVEY.md §7 "PCL VoxelGrid centroid summation order")."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,8 +16,13 @@ def _check(scan, leaf):
     vg = lsdreg.VoxelGrid(max(scan.shape[0], 1))
     out = vg.filter(scan, leaf)
     assert out.shape == ref.shape
-    np.testing.assert_allclose(out[:, :3], ref[:, :3], rtol=0, atol=1e-5)
-    np.testing.assert_allclose(out[:, 3], ref[:, 3], rtol=0, atol=2e-3)  # intensity 0..255
+    # every bit of every channel: the centroids are the restated pcl::VoxelGrid's sequential fp32 sums in input order
+    # (LSD_VG_SUMS=fixed selects the exact fixed-point sums of round 1, <= 1e-5 m / 2e-3 intensity units from these)
+    if os.environ.get("LSD_VG_SUMS", "")[:1] == "f":
+        np.testing.assert_allclose(out[:, :3], ref[:, :3], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(out[:, 3], ref[:, 3], rtol=0, atol=2e-3)  # intensity 0..255
+    else:
+        assert (out.view(np.uint32) == ref.view(np.uint32)).all()
     out2 = vg.filter(scan, leaf)  # scratch returned to zero; bit-stable run to run
     assert (out2.view(np.int32) == out.view(np.int32)).all()
     return out
