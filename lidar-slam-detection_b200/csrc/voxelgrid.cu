@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(256) vg_order_kernel(int n, const VgGrid* __re
     if (r < 0) continue;
     const int base = off[r], k = cnt[r];
     int c = 0;
-    for (int t = 0; t < k; t++) c += seg[base + t] < i ? 1 : 0;
+#pragma unroll 8
+    for (int t = 0; t < k; t++) c += __ldcg(seg + base + t) < i ? 1 : 0;
     ord[base + c] = i;
   }
 }
@@ -313,8 +314,19 @@ __global__ void __launch_bounds__(256) vg_sum_kernel(const float4* __restrict__ 
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
     const int base = off[r], k = cnt[r];
     float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
-    for (int t = 0; t < k; t++) {
-      const float4 p = __ldg(in + ord[base + t]);
+    int t = 0;
+    for (; t + 8 <= k; t += 8) {     // eight members' indices, then their points, in flight together; the additions stay in input order
+      int id[8];
+      float4 p[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) id[u] = __ldcg(ord + base + t + u);
+#pragma unroll
+      for (int u = 0; u < 8; u++) p[u] = __ldg(in + id[u]);
+#pragma unroll
+      for (int u = 0; u < 8; u++) { ax += p[u].x; ay += p[u].y; az += p[u].z; aw += p[u].w; }
+    }
+    for (; t < k; t++) {
+      const float4 p = __ldg(in + __ldcg(ord + base + t));
       ax += p.x; ay += p.y; az += p.z; aw += p.w;
     }
     const float c = (float)k;
