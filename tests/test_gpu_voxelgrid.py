@@ -74,3 +74,18 @@ def test_non_finite_points_are_skipped():
     assert vg.filter(bad, 0.5).shape[0] == 0
     got2 = vg.filter(fin, 0.5)
     assert (got2.view(np.int32) == got.view(np.int32)).all()      # bit-identical to the run that had to skip points
+
+
+def test_crowded_leaves_sum_in_input_order():
+    """Leaves with 33 ... 700 points (the warp-cooperative path of vg_sum_kernel) beside sparse ones, points of a leaf scattered
+    all over the input, values spanning five orders of magnitude so that every change of summation order shows: every bit of
+    every centroid equals the restated pcl::VoxelGrid's (sequential fp32 sums in input order)."""
+    rng = np.random.default_rng(12)
+    parts = [rng.uniform(-30, 30, (20000, 4)).astype(np.float32)]
+    for k in (33, 64, 65, 200, 700):
+        c = np.floor(rng.uniform(-20, 20, 3) / 0.5) * 0.5
+        pts = (c + rng.uniform(0.01, 0.49, (k, 3))).astype(np.float32)
+        parts.append(np.concatenate([pts, (10.0 ** rng.uniform(-2, 3, (k, 1))).astype(np.float32)], 1))
+    scan = np.concatenate(parts)
+    scan = np.ascontiguousarray(scan[rng.permutation(scan.shape[0])])
+    _check(scan, 0.5)
