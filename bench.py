@@ -806,6 +806,7 @@ def main():
                         "stale_rows": True,
                         "reference_order": os.environ.get("LSD_REF_ORDER", "1")[:1] != "0",   # neighbours in the reference's own order (default; the `sorted_order` leg measures the alternative)
                         "reference_order_fallbacks": lio.reference_order_fallbacks(),
+                        "voxelgrid_sums": "fixed-point" if os.environ.get("LSD_VG_SUMS", "")[:1] == "f" else "fp32, input order (the restated pcl::VoxelGrid's arithmetic)",
                         "timing": "wall clock around K steps bracketed by cuda sync (+barrier), max over ranks; device_ms_per_step = CUDA events on the library stream; "
                                   "step_ms = host wall time of each lsd_lio_scan call (what the caller waits for)"},
         "device_ms_per_step": 1e3 * R["dev_s"] / K,

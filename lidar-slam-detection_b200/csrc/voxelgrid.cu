@@ -7,14 +7,16 @@
 //   bbox -> min_b = floor(min * inv_leaf); leaf index = (ijk - min_b) . (1, dx, dx*dy);
 //   one centroid of all channels per occupied leaf; output in ascending leaf-index order;
 //   grids above INT32_MAX leaves are refused (PCL warns and returns the input).
-// PCL gets the order from a std::sort of (leaf, point) pairs and sums fp32 in that order.  Here the
-// order comes from a rank over an occupancy bitmap (popcount prefix scan) and the sums are exact
-// 64-bit fixed-point atomics, so the result is independent of thread order and run-to-run
-// bit-stable; it differs from PCL's fp32 sequential sum only by fp32 rounding (<= 1e-5 m).
+// PCL gets the order from a std::sort of (leaf, point) pairs and sums fp32 in that order.  Here the OUTPUT
+// order comes from a rank over an occupancy bitmap (popcount prefix scan); the centroids are, by default,
+// the sequential fp32 sums in input order of the restated filter (oracle/lsd_oracle.c::orc_voxelgrid, the
+// arithmetic the reference arm runs), bit for bit — or, with LSD_VG_SUMS=fixed, exact 64-bit fixed-point
+// atomics (round 1: independent of thread order, one fp32 ulp from the former for half the leaves, 2.2 x faster).
 //
 // Pipeline (all sizes stay on the device, no host round trip):
 //   vg_minmax -> vg_mark (+grid setup) -> vg_scan (word scan; last block scans the chunk totals)
-//   -> vg_accum -> vg_finalize (+scratch cleanup).  A single cooperative kernel with grid barriers
+//   -> vg_count -> vg_offsets -> vg_scatter -> vg_order -> vg_sum (+scratch cleanup)
+//   [fixed-point: -> vg_accum -> vg_finalize (+scratch cleanup)].  A single cooperative kernel with grid barriers
 //   was measured and rejected: no faster (the barriers cost what the launches do) and cooperative
 //   launches serialise badly behind an in-flight H2D copy (e2e 3.5 ms/scan vs 0.39 ms).
 #include "lsd_common.cuh"
